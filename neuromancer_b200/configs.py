@@ -1,0 +1,352 @@
+"""
+The benchmark problems of BASELINE.json (C1..C5) and a few small shape classes used by the tests,
+written against this package's public API exactly the way the reference examples write them:
+
+  c1  examples/control/Part_1_stabilize_linear_system.py:14-67   double integrator, nsteps 50
+  c2  examples/control/Part_3_ref_tracking_ODE.py:32-163         TwoTank + RK4 reference tracking
+  c3  examples/ODEs/Part_1_NODE.py:58-104                        neural ODE system ID (RK4 over an MLP RHS)
+  c4  examples/domain_examples/grid_response.ipynb cells 7-30    building thermal linear SSM, 48-step preview
+  c5  examples/control/Part_2_stabilize_ODE.py:33-135 scaled up  12-state coupled Van der Pol, 4x128 policy
+
+Inputs are synthetic: shapes, value ranges and constants follow the
+examples; there is no network for the building / price data of c4, so its matrices are a fixed
+Schur-stable synthetic system with the example's dimensions.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict
+
+import torch
+import torch.nn as nn
+
+from .constraint import variable
+from .dynamics import integrators, ode
+from .loss import PenaltyLoss
+from .modules import blocks
+from .modules.activations import activations
+from .problem import Problem
+from .system import Node, System
+
+
+@dataclass
+class Case:
+    name: str
+    problem: Problem
+    system: System
+    nsteps: int
+    default_batch: int
+    make_batch: Callable[[int, object, int], Dict[str, torch.Tensor]]
+    flop_per_traj_step: float      # fwd+bwd algorithmic FLOPs
+    bytes_per_traj_step: float
+
+    def plan(self, batch=None):
+        if batch is None:
+            batch = self.make_batch(4, "cpu", 0)
+        return self.system.plan_for(self.system.init(dict(batch)), loss=self.problem.loss)
+
+    def policy_parameters(self):
+        return [p for p in self.problem.parameters() if p.requires_grad]
+
+
+def _frozen_linear(weight: torch.Tensor) -> nn.Linear:
+    lin = nn.Linear(weight.shape[1], weight.shape[0], bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(weight)
+    lin.weight.requires_grad_(False)
+    return lin
+
+
+def _gen(device, seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+# ------------------------------------------------------------------------------------------- C1
+def c1(seed=0) -> Case:
+    torch.manual_seed(seed)
+    nx, nu, nsteps = 2, 1, 50
+    A = torch.tensor([[1.2, 1.0], [0.0, 1.0]])
+    B = torch.tensor([[1.0], [0.5]])
+    mlp = blocks.MLP(nx, nu, bias=True, linear_map=nn.Linear, nonlin=nn.ReLU, hsizes=[20, 20, 20, 20])
+    policy = Node(mlp, ["X"], ["U"], name="policy")
+    # the example's lambda  x @ A.T + u @ B.T  expressed as a recognisable ode.SSM
+    ssm = ode.SSM(_frozen_linear(A), _frozen_linear(B), nx, nu)
+    plant = Node(ssm, ["X", "U"], ["X"], name="double_integrator")
+    system = System([policy, plant], nsteps=nsteps, name="cl_system")
+    u, x = variable("U"), variable("X")
+    action_loss = 0.0001 * (u == 0.) ^ 2
+    regulation_loss = 10. * (x == 0.) ^ 2
+    action_loss.name, regulation_loss.name = "action_loss", "regulation_loss"
+    problem = Problem([system], PenaltyLoss([action_loss, regulation_loss], []))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 1000 + s)
+        return {"X": (3. * torch.randn(Bn, 1, nx, generator=g)).to(device), "name": "train"}
+    return Case("c1", problem, system, nsteps, 3333, make_batch, 7.6e3, 24.0)
+
+
+# ------------------------------------------------------------------------------------------- C2
+def c2(seed=0, nsteps=30) -> Case:
+    torch.manual_seed(seed)
+    nx, nu, nref = 2, 2, 2
+    two_tank = ode.TwoTankParam()
+    two_tank.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)     # psl TwoTank constants
+    two_tank.c2 = nn.Parameter(torch.tensor(0.04), requires_grad=False)
+    integrator = integrators.RK4(two_tank, h=torch.tensor(1.0))
+    model = Node(integrator, ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=nx + nref, outsize=nu, hsizes=[32, 32], nonlin=activations["gelu"],
+                            min=0, max=1.)
+    policy = Node(net, ["x", "r"], ["u"], name="policy")
+    system = System([policy, model], nsteps=nsteps, name="cl_system")
+    x, ref = variable("x"), variable("r")
+    regulation_loss = 5. * ((x == ref) ^ 2)
+    lo = 10. * (x > 0)
+    hi = 10. * (x < 1.)
+    t_lo = 10. * (x[:, [-1], :] > ref - 0.01)
+    t_hi = 10. * (x[:, [-1], :] < ref + 0.01)
+    for term, nm_ in ((regulation_loss, "ref_tracking"), (lo, "x_min"), (hi, "x_max"),
+                      (t_lo, "x_N_min"), (t_hi, "x_N_max")):
+        term.name = nm_
+    problem = Problem([system], PenaltyLoss([regulation_loss], [lo, hi, t_lo, t_hi]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 2000 + s)
+        x0 = torch.rand(Bn, 1, nx, generator=g)
+        r = torch.rand(Bn, 1, 1, generator=g) * torch.ones(nsteps + 1, nref)
+        return {"x": x0.to(device), "r": r.contiguous().to(device), "name": "train"}
+    return Case("c2", problem, system, nsteps, 65536, make_batch, 7.8e3, 48.0)
+
+
+# ------------------------------------------------------------------------------------------- C3
+def c3(seed=0, nsteps=100) -> Case:
+    torch.manual_seed(seed)
+    nx = 2
+    fx = blocks.MLP(nx, nx, bias=True, linear_map=nn.Linear, nonlin=nn.ReLU, hsizes=[60, 60, 60])
+    fx_rk4 = integrators.RK4(fx, h=0.1)
+    model = Node(fx_rk4, ["xn"], ["xn"], name="NODE")
+    system = System([model], name="system")            # nsteps inferred from data['X'] (nstep_key)
+    x = variable("X")
+    xhat = variable("xn")[:, :-1, :]
+    x_fd = (x[:, 1:, :] - x[:, :-1, :])
+    xhat_fd = (xhat[:, 1:, :] - xhat[:, :-1, :])
+    fd_loss = 2. * (x_fd == xhat_fd) ^ 2
+    fd_loss.name = "FD_loss"
+    reference_loss = (xhat == x) ^ 2
+    reference_loss.name = "ref_loss"
+    problem = Problem([system], PenaltyLoss([reference_loss, fd_loss], []))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 3000 + s)
+        X = torch.randn(Bn, nsteps, nx, generator=g)
+        return {"X": X.to(device), "xn": X[:, 0:1, :].contiguous().to(device), "name": "train"}
+    return Case("c3", problem, system, nsteps, 262144, make_batch, 178.6e3, 32.0)
+
+
+# ------------------------------------------------------------------------------------------- C4
+C4_A = [[0.9500, 0.0200, 0.0000, 0.0100],
+        [0.0300, 0.9000, 0.0200, 0.0000],
+        [0.0000, 0.0400, 0.9200, 0.0100],
+        [0.0200, 0.0100, 0.0300, 0.9300]]
+C4_B = [[0.00], [0.00], [0.05], [0.10]]
+C4_E = [[0.010, 0.000, 0.002], [0.020, 0.001, 0.000], [0.005, 0.002, 0.001], [0.002, 0.001, 0.003]]
+C4_C = [[0.0, 0.0, 0.0, 1.0]]
+
+
+def c4(seed=0, nsteps=96, horizon=48) -> Case:
+    torch.manual_seed(seed)
+    nx, nu, nd, ny, nd_obs = 4, 1, 3, 1, 1
+    A, Bm, E, Cm = (torch.tensor(m) for m in (C4_A, C4_B, C4_E, C4_C))
+    ssm = ode.SSM(_frozen_linear(A), _frozen_linear(Bm), nx, nu, fd=_frozen_linear(E), nd=nd)
+    state_model = Node(ssm, ["x", "u", "d"], ["x"], name="SSM")
+    obs_model = Node(_frozen_linear(Cm), ["x"], ["y"], name="y=Cx")
+    forecast = ["d_obs_lookahead", "ymin_lookahead", "ymax_lookahead", "price_lookahead"]
+    insize = ny + horizon * (nd_obs + ny + ny + 1)
+    net = blocks.MLP_bounds(insize=insize, outsize=nu, hsizes=[32, 32], nonlin=nn.LeakyReLU,
+                            min=torch.tensor([0.0]), max=torch.tensor([5000.0]))
+    policy = Node(net, ["y"] + forecast, ["u"], name="policy")
+    system = System([obs_model, policy, state_model], nsteps=nsteps, name="cl_system")
+    y_var, u_var = variable("y"), variable("u")
+    ymin_var = variable("ymin_lookahead")[:, :-1, 0:1]
+    ymax_var = variable("ymax_lookahead")[:, :-1, 0:1]
+    price_var = variable("price_lookahead")[:, :-1, 0:1]
+    price_loss = 1 * ((u_var * price_var) == torch.zeros_like(u_var)) ^ 2
+    comfort_lower = 5e06 * (y_var > ymin_var)
+    comfort_upper = 5e06 * (y_var < ymax_var)
+    price_loss.name, comfort_lower.name, comfort_upper.name = "price_loss", "y_min", "y_max"
+    problem = Problem([system], PenaltyLoss([price_loss], [comfort_lower, comfort_upper]))
+
+    def lookahead(sig):                       # [B, nsteps+horizon, D] -> [B, nsteps+1, D*horizon]
+        Bn, Tn, D = sig.shape
+        win = sig.unfold(1, horizon, 1)       # [B, nsteps+1, D, horizon]
+        return win.permute(0, 1, 3, 2).reshape(Bn, Tn - horizon + 1, horizon * D).contiguous()
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 4000 + s)
+        Tn = nsteps + horizon
+        ymin = (18.0 + 4.5 * torch.rand(Bn, 1, ny, generator=g)).repeat(1, Tn, 1)
+        ymax = (22.5 + 4.5 * torch.rand(Bn, 1, ny, generator=g)).repeat(1, Tn, 1)
+        dist = torch.randn(Bn, Tn, nd, generator=g)
+        dist[:, :, 0] = 5.0 + 8.0 * dist[:, :, 0]
+        price = 0.05 + 0.2 * torch.rand(Bn, Tn, 1, generator=g)
+        x0 = 20.0 + torch.randn(Bn, 1, nx, generator=g)
+        batch = {"x": x0, "d": dist[:, :nsteps, :].contiguous(),
+                 "d_obs_lookahead": lookahead(dist[:, :, 0:1]), "ymin_lookahead": lookahead(ymin),
+                 "ymax_lookahead": lookahead(ymax), "price_lookahead": lookahead(price)}
+        out = {k: v.to(device) for k, v in batch.items()}
+        out["name"] = "train"
+        return out
+    return Case("c4", problem, system, nsteps, 131072, make_batch, 43.7e3, 1600.0)
+
+
+# ------------------------------------------------------------------------------------------- C5
+def c5(seed=0, nsteps=200) -> Case:
+    torch.manual_seed(seed)
+    n_osc = 6
+    nx, nu = 2 * n_osc, n_osc
+    plant = ode.CoupledVanDerPolControl(n_osc=n_osc, mu=1.0, kappa=0.1)
+    integrator = integrators.RK4(plant, h=torch.tensor(0.05))
+    model = Node(integrator, ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=2 * nx, outsize=nu, hsizes=[128, 128, 128, 128],
+                            nonlin=activations["gelu"], min=-5., max=5.)
+    policy = Node(net, ["x", "r"], ["u"], name="policy")
+    system = System([policy, model], nsteps=nsteps, name="cl_system")
+    x, ref, u = variable("x"), variable("r"), variable("u")
+    regulation = 1. * ((x == ref) ^ 2)
+    effort = 0.01 * ((u == 0.) ^ 2)
+    lo, hi = 10. * (x > -4.), 10. * (x < 4.)
+    t_lo = 10. * (x[:, [-1], :] > ref - 0.01)
+    t_hi = 10. * (x[:, [-1], :] < ref + 0.01)
+    for term, nm_ in ((regulation, "state_loss"), (effort, "action_loss"), (lo, "x_min"), (hi, "x_max"),
+                      (t_lo, "x_N_min"), (t_hi, "x_N_max")):
+        term.name = nm_
+    problem = Problem([system], PenaltyLoss([regulation, effort], [lo, hi, t_lo, t_hi]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 5000 + s)
+        return {"x": torch.randn(Bn, 1, nx, generator=g).to(device),
+                "r": torch.zeros(Bn, nsteps + 1, nx, device=device), "name": "train"}
+    return Case("c5", problem, system, nsteps, 4194304, make_batch, 319.5e3, 240.0)
+
+
+# ------------------------------------------------------------------------------------------- test shapes
+def t_vdp_rk4_tanh_clamp(seed=0, nsteps=12) -> Case:
+    torch.manual_seed(seed)
+    plant = ode.VanDerPolControl()
+    plant.mu = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+    model = Node(integrators.RK4(plant, h=0.1), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=4, outsize=1, hsizes=[16, 16], nonlin=nn.Tanh, min=-1., max=1.,
+                            method="relu_clamp")
+    system = System([Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    x, r, u = variable("x"), variable("r"), variable("u")
+    obj = 3. * ((x == r) ^ 2)
+    eff = 0.1 * (u == 0.)                     # norm-1 equality
+    box = 2. * ((x < 1.5) ^ 2)                # norm-2 inequality
+    du = 0.5 * ((u[:, 1:, :] - u[:, :-1, :]) == 0.) ^ 2
+    for t_, n_ in ((obj, "obj"), (eff, "eff"), (box, "box"), (du, "du")):
+        t_.name = n_
+    problem = Problem([system], PenaltyLoss([obj, eff, du], [box]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 6000 + s)
+        return {"x": torch.randn(Bn, 1, 2, generator=g).to(device),
+                "r": (0.5 * torch.randn(Bn, nsteps + 1, 2, generator=g)).to(device), "name": "train"}
+    return Case("t_vdp_rk4_tanh_clamp", problem, system, nsteps, 256, make_batch, 0, 0)
+
+
+def t_vdp_euler_elu(seed=0, nsteps=9) -> Case:
+    torch.manual_seed(seed)
+    plant = ode.VanDerPolControl()
+    plant.mu = nn.Parameter(torch.tensor(0.7), requires_grad=False)
+    model = Node(integrators.Euler(plant, h=0.05), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP(insize=2, outsize=1, hsizes=[8], nonlin=nn.ELU, bias=False)
+    system = System([Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    x, u = variable("x"), variable("u")
+    obj = (x == 0.) ^ 2
+    pen = 4. * (u > -0.2)
+    obj.name, pen.name = "obj", "pen"
+    problem = Problem([system], PenaltyLoss([obj], [pen]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 7000 + s)
+        return {"x": torch.randn(Bn, 1, 2, generator=g).to(device), "name": "train"}
+    return Case("t_vdp_euler_elu", problem, system, nsteps, 200, make_batch, 0, 0)
+
+
+def t_twotank_rk2_sigmoid(seed=0, nsteps=7) -> Case:
+    torch.manual_seed(seed)
+    plant = ode.TwoTankParam()
+    plant.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
+    plant.c2 = nn.Parameter(torch.tensor(0.04), requires_grad=False)
+    model = Node(integrators.RK2(plant, h=0.5), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=4, outsize=2, hsizes=[12], nonlin=nn.Sigmoid, min=0., max=1.)
+    system = System([Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    x, r = variable("x"), variable("r")
+    obj = (x == r) ^ 2
+    obj.name = "obj"
+    problem = Problem([system], PenaltyLoss([obj], []))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 8000 + s)
+        return {"x": (0.1 + 0.8 * torch.rand(Bn, 1, 2, generator=g)).to(device),
+                "r": torch.rand(Bn, nsteps + 1, 2, generator=g).to(device), "name": "train"}
+    return Case("t_twotank_rk2_sigmoid", problem, system, nsteps, 130, make_batch, 0, 0)
+
+
+def t_ssm_softplus(seed=0, nsteps=10) -> Case:
+    torch.manual_seed(seed)
+    nx, nu, nd, ny = 3, 2, 2, 2
+    g0 = _gen("cpu", 99)
+    A = 0.3 * torch.randn(nx, nx, generator=g0) + 0.5 * torch.eye(nx)
+    Bm, E, Cm = (0.5 * torch.randn(*s, generator=g0) for s in ((nx, nu), (nx, nd), (ny, nx)))
+    ssm = ode.SSM(_frozen_linear(A), _frozen_linear(Bm), nx, nu, fd=_frozen_linear(E), nd=nd)
+    net = blocks.MLP(insize=ny + nd + nx, outsize=nu, hsizes=[10, 10], nonlin=nn.Softplus)
+    system = System([Node(_frozen_linear(Cm), ["x"], ["y"], name="obs"),
+                     Node(net, ["y", "d", "x"], ["u"], name="policy"),
+                     Node(ssm, ["x", "u", "d"], ["x"], name="ssm")], nsteps=nsteps, name="sys")
+    x, u, y = variable("x"), variable("u"), variable("y")
+    o1 = (y == 1.) ^ 2
+    o2 = 0.1 * ((u == 0.) ^ 2)
+    c1_ = 5. * (x[:, 1:, 0:2] < 2.0)
+    o1.name, o2.name, c1_.name = "o1", "o2", "c1"
+    problem = Problem([system], PenaltyLoss([o1, o2], [c1_]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 9000 + s)
+        return {"x": torch.randn(Bn, 1, nx, generator=g).to(device),
+                "d": torch.randn(Bn, nsteps + 3, nd, generator=g).to(device), "name": "train"}
+    return Case("t_ssm_softplus", problem, system, nsteps, 77, make_batch, 0, 0)
+
+
+def t_node_policy_euler(seed=0, nsteps=6) -> Case:
+    """Neural policy AND neural right-hand side with a control input (both trainable)."""
+    torch.manual_seed(seed)
+    nx, nu = 3, 2
+    rhs = blocks.MLP(nx + nu, nx, bias=True, linear_map=nn.Linear, nonlin=nn.Tanh, hsizes=[12, 12])
+    model = Node(integrators.RK2(rhs, h=0.2), ["x", "u"], ["x"], name="node")
+    net = blocks.MLP(insize=nx, outsize=nu, hsizes=[8, 8], nonlin=nn.ReLU)
+    system = System([Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    x, u = variable("x"), variable("u")
+    obj = (x == 0.5) ^ 2
+    eff = 0.2 * ((u == 0.) ^ 2)
+    obj.name, eff.name = "obj", "eff"
+    problem = Problem([system], PenaltyLoss([obj, eff], []))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 9500 + s)
+        return {"x": torch.randn(Bn, 1, nx, generator=g).to(device), "name": "train"}
+    return Case("t_node_policy_euler", problem, system, nsteps, 150, make_batch, 0, 0)
+
+
+CASES: Dict[str, Callable[..., Case]] = {
+    "c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
+    "t_vdp_rk4_tanh_clamp": t_vdp_rk4_tanh_clamp, "t_vdp_euler_elu": t_vdp_euler_elu,
+    "t_twotank_rk2_sigmoid": t_twotank_rk2_sigmoid, "t_ssm_softplus": t_ssm_softplus,
+    "t_node_policy_euler": t_node_policy_euler,
+}
+AOT_CASES = list(CASES)
+
+
+def build_case(name: str, batch=None, device="cpu", seed=0, **kw) -> Case:
+    return CASES[name](seed=seed, **kw)

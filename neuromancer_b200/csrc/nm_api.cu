@@ -1,0 +1,248 @@
+// nm_api.cu -- the C ABI of include/nm_rollout.h: kernel registry, plan validation / signature,
+// dispatch to the per-shape-class launchers, and the two small finalise kernels.
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <cuda_runtime.h>
+#include "nm_registry.h"
+
+namespace {
+
+std::mutex g_mu;
+NmKernelEntry* g_head = nullptr;
+int g_count = 0;
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+NmKernelEntry* find_entry(const char* sig) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (NmKernelEntry* e = g_head; e; e = e->next)
+    if (std::strcmp(e->signature, sig) == 0) return e;
+  return nullptr;
+}
+
+void append_mlp(std::string& s, const NmMlp& m) {
+  char buf[64];
+  s += "[";
+  for (int i = 0; i <= m.n_layers; ++i) { std::snprintf(buf, sizeof(buf), i ? "-%d" : "%d", m.sizes[i]); s += buf; }
+  std::snprintf(buf, sizeof(buf), "]a%d_b%d_o%d", m.act, m.has_bias ? 1 : 0, m.bounds);
+  s += buf;
+}
+
+int validate(const NmPlan* p) {
+  if (!p) { nm_set_error("null plan"); return NM_ERR_BAD_PLAN; }
+  if (p->abi_version != NM_ABI_VERSION) { nm_set_error("plan.abi_version does not match the library"); return NM_ERR_ABI; }
+  if (p->nx < 1 || p->nx > NM_MAX_DIM || p->nu < 0 || p->nu > NM_MAX_DIM || p->ny < 0 || p->ny > NM_MAX_DIM) { nm_set_error("nx/nu/ny out of range"); return NM_ERR_BAD_PLAN; }
+  if (p->nsteps < 1) { nm_set_error("nsteps must be >= 1"); return NM_ERR_BAD_PLAN; }
+  if (p->n_exo < 0 || p->n_exo > NM_MAX_EXO || p->n_terms < 0 || p->n_terms > NM_MAX_TERMS || p->n_segs < 0 || p->n_segs > NM_MAX_SEGS) { nm_set_error("count field out of range"); return NM_ERR_BAD_PLAN; }
+  if (p->has_policy && (p->policy.n_layers < 1 || p->policy.n_layers > NM_MAX_LAYERS)) { nm_set_error("policy layer count out of range"); return NM_ERR_BAD_PLAN; }
+  if (p->rhs_kind == NM_RHS_MLP && (p->rhs_mlp.n_layers < 1 || p->rhs_mlp.n_layers > NM_MAX_LAYERS)) { nm_set_error("rhs layer count out of range"); return NM_ERR_BAD_PLAN; }
+  for (int i = 0; i < p->n_segs; ++i) {
+    const NmSegment& s = p->segs[i];
+    if (s.kind == NM_SEG_EXO && (s.index < 0 || s.index >= p->n_exo || p->exo[s.index].width != s.width)) { nm_set_error("policy segment refers to a bad exo input"); return NM_ERR_BAD_PLAN; }
+  }
+  for (int e = 0; e < p->n_exo; ++e)
+    if (p->exo[e].width < 1 || p->exo[e].steps < 1) { nm_set_error("exo shape invalid"); return NM_ERR_BAD_PLAN; }
+  if (p->dist_exo >= p->n_exo) { nm_set_error("dist_exo out of range"); return NM_ERR_BAD_PLAN; }
+  const int T[3] = {p->nsteps + 1, p->nsteps, p->nsteps};
+  const int D[3] = {p->nx, p->nu, p->ny};
+  for (int k = 0; k < p->n_terms; ++k) {
+    const NmTerm& t = p->terms[k];
+    if (t.norm != 1 && t.norm != 2) { nm_set_error("term norm must be 1 or 2"); return NM_ERR_BAD_PLAN; }
+    if (t.t_len < 1 || t.d_len < 1) { nm_set_error("term element shape invalid"); return NM_ERR_BAD_PLAN; }
+    const NmAtom* atoms[4] = {&t.lhs.a, &t.lhs.b, &t.rhs.a, &t.rhs.b};
+    const bool live[4] = {true, t.lhs.op != NM_OP_NONE, true, t.rhs.op != NM_OP_NONE};
+    for (int i = 0; i < 4; ++i) {
+      if (!live[i]) continue;
+      const NmAtom& a = *atoms[i];
+      if (a.var < 0) continue;
+      int vt, vd;
+      if (a.var < NM_VAR_EXO0) { vt = T[a.var]; vd = D[a.var]; }
+      else { const int e = a.var - NM_VAR_EXO0; if (e >= p->n_exo) { nm_set_error("term atom refers to a missing exo input"); return NM_ERR_BAD_PLAN; } vt = p->exo[e].steps; vd = p->exo[e].width; }
+      if (a.t_start < 0 || a.t_len < 1 || a.t_start + a.t_len > vt || a.d_start < 0 || a.d_len < 1 || a.d_start + a.d_len > vd) { nm_set_error("term atom slice out of range"); return NM_ERR_BAD_PLAN; }
+      if ((a.t_len != 1 && a.t_len != t.t_len) || (a.d_len != 1 && a.d_len != t.d_len)) { nm_set_error("term atom shape does not broadcast to the term shape"); return NM_ERR_BAD_PLAN; }
+    }
+  }
+  return NM_OK;
+}
+
+std::string make_signature(const NmPlan* p) {
+  std::string s;
+  char buf[96];
+  std::snprintf(buf, sizeof(buf), "v%d_nx%d_nu%d_ny%d", NM_ABI_VERSION, p->nx, p->nu, p->ny);
+  s += buf;
+  if (p->has_policy) {
+    s += "_pol"; append_mlp(s, p->policy);
+    s += "_seg";
+    for (int i = 0; i < p->n_segs; ++i) {
+      const NmSegment& g = p->segs[i];
+      std::snprintf(buf, sizeof(buf), "%s%c%d.%d", i ? "," : "", g.kind == NM_SEG_STATE ? 'x' : (g.kind == NM_SEG_OUTPUT ? 'y' : 'e'), g.kind == NM_SEG_EXO ? g.index : 0, g.width);
+      s += buf;
+    }
+  }
+  std::snprintf(buf, sizeof(buf), "_out%d_dyn%d_int%d_rhs%d", p->has_output ? 1 : 0, p->dyn_kind, p->dyn_kind == NM_DYN_ODE ? p->integrator : 0, p->rhs_kind);
+  s += buf;
+  if (p->rhs_kind == NM_RHS_MLP) append_mlp(s, p->rhs_mlp);
+  const int nd = p->dist_exo >= 0 ? p->exo[p->dist_exo].width : 0;
+  std::snprintf(buf, sizeof(buf), "_dist%d.%d", p->dist_exo, nd);
+  s += buf;
+  return s;
+}
+
+__global__ void nm_loss_finalize_kernel(const __grid_constant__ NmPlan plan, const double* __restrict__ partials, int grid,
+                                        int64_t B, float* __restrict__ scalars) {
+  __shared__ float term[NM_MAX_TERMS];
+  const int k = threadIdx.x;
+  if (k < plan.n_terms) {
+    double s = 0.0;
+    for (int c = 0; c < grid; ++c) s += partials[size_t(c) * NM_MAX_TERMS + k];
+    const NmTerm& t = plan.terms[k];
+    const float mean = static_cast<float>(s / (static_cast<double>(B) * t.t_len * t.d_len));
+    term[k] = t.weight * mean;                      // Constraint.forward: weight * loss
+    scalars[k] = term[k];
+  }
+  __syncthreads();
+  if (k == 0) {                                      // loss.py:61-108: python-float 0.0 start, list order
+    float obj = 0.f, pen = 0.f;
+    for (int i = 0; i < plan.n_terms; ++i) { if (plan.terms[i].is_objective) obj += term[i]; }
+    for (int i = 0; i < plan.n_terms; ++i) { if (!plan.terms[i].is_objective) pen += term[i]; }
+    scalars[plan.n_terms] = obj;
+    scalars[plan.n_terms + 1] = pen;
+    scalars[plan.n_terms + 2] = obj + pen;
+  }
+}
+
+__global__ void nm_grad_finalize_kernel(const float* __restrict__ partials, int grid, int64_t n, float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < grid; ++c) s += partials[size_t(c) * size_t(n) + i];   // fixed order: deterministic
+  out[i] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+void nm_set_error(const char* msg) { std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
+
+void nm_register_kernel(NmKernelEntry* e) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (NmKernelEntry* q = g_head; q; q = q->next)
+    if (std::strcmp(q->signature, e->signature) == 0) return;   // first registration wins
+  e->next = g_head;
+  g_head = e;
+  ++g_count;
+}
+
+int nm_abi_version(void) { return NM_ABI_VERSION; }
+const char* nm_last_error(void) { return g_err; }
+int nm_last_launch_count(void) { return g_launches; }
+
+int nm_struct_sizes(int* out, int cap) {
+  const int v[7] = {(int)sizeof(NmMlp), (int)sizeof(NmSegment), (int)sizeof(NmExo), (int)sizeof(NmAtom),
+                    (int)sizeof(NmSide), (int)sizeof(NmTerm), (int)sizeof(NmPlan)};
+  for (int i = 0; i < 7 && i < cap; ++i) out[i] = v[i];
+  return 7;
+}
+
+int nm_plan_signature(const NmPlan* plan, char* buf, int cap) {
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  const std::string s = make_signature(plan);
+  if (!buf || cap <= (int)s.size()) { nm_set_error("signature buffer too small"); return NM_ERR_BAD_PLAN; }
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
+int nm_has_kernel(const NmPlan* plan) {
+  if (validate(plan) != NM_OK) return 0;
+  return find_entry(make_signature(plan).c_str()) != nullptr ? 1 : 0;
+}
+
+int nm_num_kernels(void) { return g_count; }
+
+const char* nm_kernel_signature(int i) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int k = 0;
+  for (NmKernelEntry* e = g_head; e; e = e->next, ++k)
+    if (k == i) return e->signature;
+  return nullptr;
+}
+
+const char* nm_kernel_info(const NmPlan* plan) {
+  if (validate(plan) != NM_OK) return nullptr;
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  return e ? e->info : nullptr;
+}
+
+int nm_load_plugin(const char* path) {
+  void* h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { nm_set_error(dlerror()); return NM_ERR_NO_KERNEL; }
+  return NM_OK;                                     // the plugin's static registrar ran during dlopen
+}
+
+int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes, size_t* bwd_bytes) {
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  if (B < 1 || !fwd_bytes || !bwd_bytes) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  return e->workspace(plan, B, fwd_bytes, bwd_bytes);
+}
+
+int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0, const float* const* exo,
+                       float* x_traj, float* u_traj, float* y_traj, float* scalars, void* workspace,
+                       size_t workspace_bytes, int64_t B, void* stream) {
+  g_launches = 0;
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  if (B < 1 || !x0 || !x_traj || !scalars || !workspace || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj) ||
+      (plan->n_params > 0 && !params)) { nm_set_error("null pointer argument"); return NM_ERR_BAD_PLAN; }
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  NmFwdCall c{};
+  c.params = params; c.x0 = x0; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
+  c.workspace = workspace; c.workspace_bytes = workspace_bytes; c.B = B; c.stream = static_cast<cudaStream_t>(stream);
+  rc = e->forward(plan, &c);
+  if (rc != NM_OK) return rc;
+  nm_loss_finalize_kernel<<<1, 32, 0, c.stream>>>(*plan, c.term_partials, c.grid, B, scalars);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
+  g_launches = 3;                                   // weight prep + rollout + loss finalise
+  return NM_OK;
+}
+
+int nm_rollout_backward(const NmPlan* plan, const float* params, const float* const* exo, const float* x_traj,
+                        const float* u_traj, const float* y_traj, const float* grad_scalars, const float* grad_x_ext,
+                        const float* grad_u_ext, const float* grad_y_ext, float* grad_params, float* grad_x0,
+                        void* workspace, size_t workspace_bytes, int64_t B, int64_t b_total, void* stream) {
+  g_launches = 0;
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  if (B < 1 || b_total < B || !x_traj || !workspace || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj) ||
+      (plan->n_params > 0 && (!params || !grad_params))) { nm_set_error("null pointer / bad size argument"); return NM_ERR_BAD_PLAN; }
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  NmBwdCall c{};
+  c.params = params; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
+  c.grad_scalars = grad_scalars; c.gx_ext = grad_x_ext; c.gu_ext = grad_u_ext; c.gy_ext = grad_y_ext;
+  c.grad_x0 = grad_x0; c.workspace = workspace; c.workspace_bytes = workspace_bytes; c.B = B; c.b_total = b_total;
+  c.stream = static_cast<cudaStream_t>(stream);
+  rc = e->backward(plan, &c);
+  if (rc != NM_OK) return rc;
+  g_launches = 2;
+  if (plan->n_params > 0) {
+    const int threads = 256;
+    const int blocks = int((plan->n_params + threads - 1) / threads);
+    nm_grad_finalize_kernel<<<blocks, threads, 0, c.stream>>>(c.grad_partials, c.grid, plan->n_params, grad_params);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
+    g_launches = 3;                                 // weight prep + adjoint + gradient finalise
+  }
+  return NM_OK;
+}
+
+}  // extern "C"

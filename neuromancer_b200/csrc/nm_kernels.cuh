@@ -1,0 +1,859 @@
+// nm_kernels.cuh -- the two fused kernels of the DPC hot path, templated on a shape class `S`
+// (generated header, see neuromancer_b200/build.py):
+//
+//   nm_fwd_kernel<S>  persistent, batch-sliced closed-loop rollout over the whole horizon
+//                     (policy MLP -> bounds -> integrator(RHS) / SSM -> trajectory stores) followed by
+//                     the PenaltyLoss scoring of the tile's trajectories;
+//   nm_bwd_kernel<S>  the matching adjoint / BPTT sweep: per step it recomputes the layer activations
+//                     from the stored state x_t (the emitted trajectory IS the checkpoint), pulls the
+//                     co-state back through integrator, RHS, bounds and MLP, and accumulates weight
+//                     gradients in registers across steps and tiles.
+//
+// Work decomposition per CTA: a tile of TILE trajectories.  Layer contractions are CTA-cooperative
+// register-tiled FFMA GEMMs on shared-memory activations [feature][traj]; everything that is
+// per-trajectory (state, dynamics, bounds, loss terms, co-state) is thread-per-trajectory register
+// math.  Weights are permuted once by nm_prep_kernel and staged into shared memory with one bulk TMA
+// copy per CTA.
+#pragma once
+#include "nm_device.cuh"
+#include "nm_dynamics.cuh"
+#include "nm_terms.cuh"
+
+namespace nm {
+
+// ------------------------------------------------------------------------------------------------
+// Static description of one MLP's staging buffers.
+//   GW0 = number of leading input features whose gradient is needed (state / output segments).
+template <class M, int TILE, int THREADS, int GW0>
+struct MlpCfg {
+  static constexpr int NL = M::NL;
+  static constexpr int LD = TILE + 4;
+  static constexpr int K(int l) { return M::sz(l); }
+  static constexpr int N(int l) { return M::sz(l + 1); }
+  static constexpr int gw(int l) { return l == 0 ? GW0 : K(l); }       // width of the data gradient of layer l
+  // permuted weight block (floats): per layer  Wf[K][NPf] , bias[NPf] ; then per layer Wb[N][NPb]
+  static constexpr int npf(int l) { return g_np(N(l)); }
+  static constexpr int npb(int l) { return g_np(gw(l)); }
+  static constexpr int wf_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += (K(i) + 1) * npf(i); return o; }
+  static constexpr int bf_off(int l) { return wf_off(l) + K(l) * npf(l); }
+  static constexpr int FWD_W = wf_off(NL);
+  static constexpr int wb_off(int l) { int o = FWD_W; for (int i = 0; i < l; ++i) o += N(i) * npb(i); return o; }
+  static constexpr int ALL_W = wb_off(NL);
+  // number of parameters of layer l in the reference's flat order (W [N][K] then b [N])
+  static constexpr int p_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += N(i) * K(i) + (M::BIAS ? N(i) : 0); return o; }
+  static constexpr int N_PARAMS = p_off(NL);
+  static constexpr int max_width() { int m = 1; for (int l = 0; l <= NL; ++l) m = cmax(m, M::sz(l)); return m; }
+  // forward-only activation buffers: layer inputs alternate between two buffers
+  static constexpr int pp_rows(int parity) { int m = 0; for (int l = parity; l <= NL; l += 2) m = cmax(m, M::sz(l)); return cmax(m, 1); }
+  // keep-all activation buffers (adjoint): a_l for l < NL, derivative buffers for hidden layers
+  static constexpr bool DBUF = act_needs_dbuf<M::ACT>();
+  static constexpr int a_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += K(i) * LD; return o; }
+  static constexpr int d_off(int l) { int o = a_off(NL); for (int i = 1; i < l; ++i) o += K(i) * LD; return o; }  // l in [1, NL)
+  static constexpr int KEEP_FLOATS = DBUF ? d_off(NL) : a_off(NL);
+  static constexpr int delta_rows() { int m = 1; for (int l = 0; l < NL; ++l) m = cmax(m, cmax(N(l), gw(l))); return m; }
+  static constexpr int dw_regs() {
+    int r = 0;
+    for (int l = 0; l < NL; ++l) {
+      const int n = N(l), k = K(l);
+      const int rj = cmin(4, n), rk = cmin(4, k);
+      r += cdiv(cdiv(n, rj) * cdiv(k, rk), THREADS) * rj * rk + 1;
+    }
+    return r;
+  }
+};
+template <int TILE, int THREADS> struct NoMlpCfg {
+  static constexpr int NL = 0, FWD_W = 0, ALL_W = 0, N_PARAMS = 0, KEEP_FLOATS = 0;
+  static constexpr int max_width() { return 1; }
+  static constexpr int pp_rows(int) { return 0; }
+  static constexpr int delta_rows() { return 0; }
+  static constexpr int dw_regs() { return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Per-spec static configuration
+template <class S>
+struct KCfg {
+  static constexpr int NX = S::NX, NU = S::NU, NY = S::NY, ND = S::ND;
+  static constexpr int NUA = NU > 0 ? NU : 1, NYA = NY > 0 ? NY : 1, NDA = ND > 0 ? ND : 1;
+  static constexpr bool HAS_POL = S::Pol::NL > 0;
+  static constexpr bool HAS_RHS_MLP = S::RHS == NM_RHS_MLP;
+  static constexpr int THREADS = S::THREADS, TILE = S::TILE, LD = TILE + 4;
+  // gradient is needed for the policy inputs up to the end of the last state/output segment
+  static constexpr int pol_gw0() {
+    int off = 0, gw = 0;
+    for (int i = 0; i < S::NSEG; ++i) { off += S::seg_width(i); if (S::seg_kind(i) != NM_SEG_EXO) gw = off; }
+    return gw;
+  }
+  using PolCfg = std::conditional_t<HAS_POL, MlpCfg<typename S::Pol, TILE, THREADS, pol_gw0()>, NoMlpCfg<TILE, THREADS>>;
+  using RhsCfg = std::conditional_t<HAS_RHS_MLP, MlpCfg<typename S::RhsM, TILE, THREADS, NX + NU>, NoMlpCfg<TILE, THREADS>>;
+  static constexpr int W_FLOATS_FWD = round_up(PolCfg::FWD_W, 4) + round_up(RhsCfg::FWD_W, 4);
+  static constexpr int RHS_WF_OFF = round_up(PolCfg::FWD_W, 4);                     // forward-kernel smem offset
+  static constexpr int W_FLOATS_ALL = round_up(PolCfg::ALL_W, 4) + round_up(RhsCfg::ALL_W, 4);
+  static constexpr int POL_W_OFF = 0, RHS_W_OFF = round_up(PolCfg::ALL_W, 4);       // in the prepared global block
+  // forward kernel shared memory (floats)
+  static constexpr int FWD_PP0 = cmax(cmax(PolCfg::pp_rows(0), RhsCfg::pp_rows(0)), 2) * LD;   // >= 256 floats: reused by the loss reduction
+  static constexpr int FWD_PP1 = cmax(PolCfg::pp_rows(1), RhsCfg::pp_rows(1)) * LD;
+  // weights are staged in shared memory when they fit, else streamed from the prepared global block (L1/L2)
+  static constexpr bool W_SMEM = S::W_SMEM;
+  static constexpr int FWD_SMEM_FLOATS = (W_SMEM ? W_FLOATS_FWD : 0) + FWD_PP0 + FWD_PP1 + 64 + 128;
+  // adjoint kernel shared memory (floats)
+  static constexpr int DELTA_ROWS = cmax(PolCfg::delta_rows(), RhsCfg::delta_rows());
+  static constexpr int BWD_SMEM_FLOATS = (W_SMEM ? W_FLOATS_ALL : 0) + PolCfg::KEEP_FLOATS + RhsCfg::KEEP_FLOATS + 2 * DELTA_ROWS * LD + 64 + 128;
+  static constexpr size_t FWD_SMEM_BYTES = size_t(FWD_SMEM_FLOATS) * 4, BWD_SMEM_BYTES = size_t(BWD_SMEM_FLOATS) * 4;
+  static constexpr bool DW_SPILL = (PolCfg::dw_regs() + RhsCfg::dw_regs()) > 112;   // accumulators do not fit the RF
+  static constexpr int N_PARAMS = PolCfg::N_PARAMS + RhsCfg::N_PARAMS;
+  static constexpr bool FITS = FWD_SMEM_BYTES <= 227 * 1024 && BWD_SMEM_BYTES <= 227 * 1024;
+};
+
+struct FwdArgs {
+  const float* params; const float* wprep; const float* x0;
+  const float* exo[NM_MAX_EXO];
+  float* x_traj; float* u_traj; float* y_traj;
+  double* term_partials;            // [grid][NM_MAX_TERMS]
+  int64_t B; int num_tiles;
+};
+struct BwdArgs {
+  const float* params; const float* wprep;
+  const float* exo[NM_MAX_EXO];
+  const float* x_traj; const float* u_traj; const float* y_traj;
+  const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
+  float* grad_partials;             // [grid][n_params]
+  float* grad_x0;
+  int64_t B; int64_t b_total; int num_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: permute nn.Linear weights into the staged layouts
+template <class MC>
+__device__ void prep_mlp(const float* __restrict__ params, float* __restrict__ dst, bool has_bias, int gtid, int gthreads) {
+  static_for<0, MC::NL>([&](auto lc) {
+    constexpr int l = decltype(lc)::value;
+    constexpr int K = MC::K(l), N = MC::N(l), NPF = MC::npf(l), GW = MC::gw(l), NPB = MC::npb(l);
+    const float* __restrict__ Wg = params + MC::p_off(l);
+    const float* __restrict__ bg = Wg + N * K;
+    float* __restrict__ wf = dst + MC::wf_off(l);
+    for (int idx = gtid; idx < (K + 1) * NPF; idx += gthreads) {
+      const int c = idx / NPF, col = idx % NPF;
+      const int ng = col / g_tn(N), j = col % g_tn(N);
+      const int n = ng + g_ng(N) * j;
+      float v = 0.f;
+      if (ng < g_ng(N) && n < N) v = c < K ? Wg[n * K + c] : (has_bias ? bg[n] : 0.f);
+      wf[idx] = v;
+    }
+    if constexpr (GW > 0) {
+      float* __restrict__ wb = dst + MC::wb_off(l);
+      for (int idx = gtid; idx < N * NPB; idx += gthreads) {
+        const int n = idx / NPB, col = idx % NPB;
+        const int kg = col / g_tn(GW), j = col % g_tn(GW);
+        const int k = kg + g_ng(GW) * j;
+        wb[idx] = (kg < g_ng(GW) && k < GW) ? Wg[n * K + k] : 0.f;
+      }
+    }
+  });
+}
+
+template <class S>
+__global__ void nm_prep_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, float* __restrict__ wprep) {
+  using KC = KCfg<S>;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  if constexpr (KC::HAS_POL)
+    prep_mlp<typename KC::PolCfg>(params + plan.policy.param_offset, wprep + KC::POL_W_OFF, plan.policy.has_bias, gtid, gthreads);
+  if constexpr (KC::HAS_RHS_MLP)
+    prep_mlp<typename KC::RhsCfg>(params + plan.rhs_mlp.param_offset, wprep + KC::RHS_W_OFF, plan.rhs_mlp.has_bias, gtid, gthreads);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLP forward on the tile.  Inputs a_0 must be in place and visible (caller synchronised).
+//   KEEP = false : layer inputs ping-pong between pp0/pp1; raw output of the last layer is left in
+//                  the buffer of parity NL.
+//   KEEP = true  : a_l kept at keep + a_off(l) (and act' at keep + d_off(l)); raw output -> out_raw.
+// Ends with a __syncthreads().
+template <class MC, class M, int TILE, int THREADS, bool KEEP>
+__device__ __forceinline__ void mlp_forward(const float* __restrict__ W, float* __restrict__ pp0, float* __restrict__ pp1,
+                                            float* __restrict__ keep, float* __restrict__ out_raw, float act_prm, int tid) {
+  constexpr int LD = TILE + 4;
+  static_for<0, MC::NL>([&](auto lc) {
+    constexpr int l = decltype(lc)::value;
+    constexpr int K = MC::K(l), N = MC::N(l);
+    constexpr bool LAST = (l == MC::NL - 1);
+    using G = GemmCfg<N, TILE, THREADS>;
+    const float* in = KEEP ? keep + MC::a_off(l) : ((l & 1) ? pp1 : pp0);
+    float* out = KEEP ? (LAST ? out_raw : keep + MC::a_off(l + 1)) : ((l & 1) ? pp0 : pp1);
+    const float* __restrict__ bias = W + MC::bf_off(l);
+    gemm_phase<K, N, TILE, THREADS, LD>(W + MC::wf_off(l), in, tid, [&](int ng, int traj0, float (&acc)[G::TMB][G::TN]) {
+#pragma unroll
+      for (int j = 0; j < G::TN; ++j) {
+        const int n = ng + G::NG * j;
+        if (n < N) {
+          const float bj = bias[ng * G::TN + j];
+          float v[G::TMB];
+#pragma unroll
+          for (int i = 0; i < G::TMB; ++i) v[i] = acc[i][j] + bj;
+          if constexpr (!LAST) {
+            if constexpr (KEEP && MC::DBUF) {
+              float dv[G::TMB];
+#pragma unroll
+              for (int i = 0; i < G::TMB; ++i) dv[i] = act_deriv_z<M::ACT>(v[i], act_prm);
+              st_vec<G::TMB>(keep + MC::d_off(l + 1) + n * LD + traj0, dv);
+            }
+#pragma unroll
+            for (int i = 0; i < G::TMB; ++i) v[i] = act_fwd<M::ACT>(v[i], act_prm);
+          }
+          st_vec<G::TMB>(out + n * LD + traj0, v);
+        }
+      }
+    });
+    __syncthreads();
+  });
+}
+
+// persistent weight-gradient accumulators of one MLP (registers)
+template <class MC, int TILE, int THREADS, int L = 0, bool END = (L >= MC::NL)>
+struct DwStore;
+template <class MC, int TILE, int THREADS, int L>
+struct DwStore<MC, TILE, THREADS, L, true> {};
+template <class MC, int TILE, int THREADS, int L>
+struct DwStore<MC, TILE, THREADS, L, false> {
+  using D = DwCfg<MC::N(L), MC::K(L), TILE, THREADS>;
+  float acc[D::SLOTS][D::RJ][D::RK];
+  float db;
+  DwStore<MC, TILE, THREADS, L + 1> next;
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int s = 0; s < D::SLOTS; ++s)
+#pragma unroll
+      for (int i = 0; i < D::RJ; ++i)
+#pragma unroll
+        for (int j = 0; j < D::RK; ++j) acc[s][i][j] = 0.f;
+    db = 0.f;
+    if constexpr (L + 1 < MC::NL) next.zero();
+  }
+  template <int Q> __device__ __forceinline__ auto& at() {
+    if constexpr (Q == L) return *this; else return next.template at<Q>();
+  }
+};
+struct DwNone { __device__ __forceinline__ void zero() {} };
+
+// add the thread's tile of layer L to  dst[n*K + k]  (atomic: split groups share entries)
+template <class D, int N, int K>
+__device__ __forceinline__ void dw_flush_tile(const float (&acc)[D::RJ][D::RK], float* __restrict__ dst, int unit, bool atomic) {
+  const int tile = unit % D::TILES, grp = unit / D::TILES;
+  if (grp >= D::SPLIT) return;
+  const int kt = tile % D::NKT, jt = tile / D::NKT;
+#pragma unroll
+  for (int i = 0; i < D::RJ; ++i)
+#pragma unroll
+    for (int j = 0; j < D::RK; ++j) {
+      const int n = jt + D::NJ * i, k = kt + D::NKT * j;
+      if (n < N && k < K) {
+        if (atomic) atomicAdd(dst + n * K + k, acc[i][j]); else dst[n * K + k] += acc[i][j];
+      }
+    }
+}
+
+// MLP backward on the tile.  delta_{NL} (cotangent of the raw output) must be in dbuf0 and visible.
+// Leaves the gradient w.r.t. the first gw(0) inputs in the delta buffer of parity NL (dbuf0 if NL even
+// else dbuf1).  `gscratch` != nullptr selects spill mode: per-step tiles are added to the CTA's private
+// global gradient block instead of persistent registers.  Ends with a __syncthreads().
+template <class MC, class M, int TILE, int THREADS, bool SPILL, class Store>
+__device__ __forceinline__ void mlp_backward(const float* __restrict__ W, const float* __restrict__ keep,
+                                             float* __restrict__ dbuf0, float* __restrict__ dbuf1, Store& store,
+                                             float* __restrict__ gscratch, bool has_bias, bool trainable,
+                                             float act_prm, int tid) {
+  constexpr int LD = TILE + 4;
+  static_for_rev<0, MC::NL>([&](auto lc) {
+    constexpr int l = decltype(lc)::value;
+    constexpr int K = MC::K(l), N = MC::N(l), GW = MC::gw(l);
+    constexpr int step = MC::NL - 1 - l;                       // 0 for the last layer
+    const float* dl = (step & 1) ? dbuf1 : dbuf0;              // delta_{l+1}  [N][LD]
+    float* dout = (step & 1) ? dbuf0 : dbuf1;                  // delta_l      [GW][LD]
+    const float* al = keep + MC::a_off(l);
+    if constexpr (GW > 0) {
+      using G = GemmCfg<GW, TILE, THREADS>;
+      gemm_phase<N, GW, TILE, THREADS, LD>(W + MC::wb_off(l), dl, tid, [&](int kg, int traj0, float (&acc)[G::TMB][G::TN]) {
+#pragma unroll
+        for (int j = 0; j < G::TN; ++j) {
+          const int k = kg + G::NG * j;
+          if (k < GW) {
+            float v[G::TMB];
+#pragma unroll
+            for (int i = 0; i < G::TMB; ++i) v[i] = acc[i][j];
+            if constexpr (l > 0) {                               // through the activation of hidden layer l
+              float s[G::TMB];
+              if constexpr (MC::DBUF) ld_vec<G::TMB>(s, keep + MC::d_off(l) + k * LD + traj0);
+              else {
+                ld_vec<G::TMB>(s, al + k * LD + traj0);
+#pragma unroll
+                for (int i = 0; i < G::TMB; ++i) s[i] = act_deriv_a<M::ACT>(s[i], act_prm);
+              }
+#pragma unroll
+              for (int i = 0; i < G::TMB; ++i) v[i] *= s[i];
+            }
+            st_vec<G::TMB>(dout + k * LD + traj0, v);
+          }
+        }
+      });
+    }
+    if (trainable) {
+      using D = DwCfg<N, K, TILE, THREADS>;
+      if constexpr (!SPILL) {
+        auto& st = store.template at<l>();
+#pragma unroll
+        for (int s = 0; s < D::SLOTS; ++s) dw_tile<N, K, TILE, THREADS, LD>(st.acc[s], dl, al, s * THREADS + tid);
+        if (has_bias && tid < N) {
+          const float* row = dl + tid * LD;
+          float s = 0.f;
+#pragma unroll 4
+          for (int t4 = 0; t4 < TILE; t4 += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(row + t4);
+            s += (v.x + v.y) + (v.z + v.w);
+          }
+          st.db += s;
+        }
+      } else {
+        float* gw_dst = gscratch + MC::p_off(l);
+#pragma unroll 1
+        for (int s = 0; s < D::SLOTS; ++s) {
+          float t[D::RJ][D::RK];
+#pragma unroll
+          for (int i = 0; i < D::RJ; ++i)
+#pragma unroll
+            for (int j = 0; j < D::RK; ++j) t[i][j] = 0.f;
+          dw_tile<N, K, TILE, THREADS, LD>(t, dl, al, s * THREADS + tid);
+          dw_flush_tile<D, N, K>(t, gw_dst, s * THREADS + tid, D::SPLIT > 1);
+        }
+        if (has_bias && tid < N) {
+          const float* row = dl + tid * LD;
+          float s = 0.f;
+#pragma unroll 4
+          for (int t4 = 0; t4 < TILE; t4 += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(row + t4);
+            s += (v.x + v.y) + (v.z + v.w);
+          }
+          gw_dst[N * K + tid] += s;
+        }
+      }
+    }
+    __syncthreads();
+  });
+}
+
+// write the persistent accumulators of one MLP into the CTA's gradient block (zeroed beforehand)
+template <class MC, int TILE, int THREADS, class Store>
+__device__ __forceinline__ void dw_writeout(Store& store, float* __restrict__ gdst, bool has_bias, int tid) {
+  static_for<0, MC::NL>([&](auto lc) {
+    constexpr int l = decltype(lc)::value;
+    constexpr int K = MC::K(l), N = MC::N(l);
+    using D = DwCfg<N, K, TILE, THREADS>;
+    auto& st = store.template at<l>();
+    float* dst = gdst + MC::p_off(l);
+#pragma unroll
+    for (int s = 0; s < D::SLOTS; ++s) dw_flush_tile<D, N, K>(st.acc[s], dst, s * THREADS + tid, D::SPLIT > 1);
+    if (has_bias && tid < N) dst[N * K + tid] += st.db;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLP_bounds output maps (reference functions.py:9-34)
+template <int BOUNDS>
+__device__ __forceinline__ float bounds_fwd(float o, float lo, float hi) {
+  if constexpr (BOUNDS == NM_BOUNDS_SIGMOID_SCALE) return (hi - lo) * (1.f / (1.f + expf(-o))) + lo;
+  else if constexpr (BOUNDS == NM_BOUNDS_RELU_CLAMP) {
+    float r = -o + lo; r = r > 0.f ? r : 0.f;
+    const float x1 = o + r;
+    float q = x1 - hi; q = q > 0.f ? q : 0.f;
+    return x1 - q;
+  } else return o;
+}
+template <int BOUNDS>
+__device__ __forceinline__ float bounds_deriv(float o, float lo, float hi) {
+  if constexpr (BOUNDS == NM_BOUNDS_SIGMOID_SCALE) {
+    const float s = 1.f / (1.f + expf(-o));
+    return (hi - lo) * (s * (1.f - s));
+  } else if constexpr (BOUNDS == NM_BOUNDS_RELU_CLAMP) {
+    const float r = -o + lo;
+    const float d1 = 1.f - (r > 0.f ? 1.f : 0.f);
+    const float x1 = o + (r > 0.f ? r : 0.f);
+    const float d2 = 1.f - ((x1 - hi) > 0.f ? 1.f : 0.f);
+    return d1 * d2;
+  } else return 1.f;
+}
+
+// gather the policy input column of trajectory `tid` into a0[feature][tid]
+template <class S>
+__device__ __forceinline__ void build_policy_input(const NmPlan& p, const float* const* exo, float* __restrict__ a0, int tid,
+                                                   int64_t b, int t, const float (&x)[S::NX],
+                                                   const float (&y)[S::NY > 0 ? S::NY : 1]) {
+  constexpr int LD = S::TILE + 4;
+  int off = 0;
+  static_for<0, S::NSEG>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    constexpr int W = S::seg_width(s);
+    if constexpr (S::seg_kind(s) == NM_SEG_STATE) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) a0[(off + i) * LD + tid] = x[i];
+    } else if constexpr (S::seg_kind(s) == NM_SEG_OUTPUT) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) a0[(off + i) * LD + tid] = y[i];
+    } else {
+      constexpr int e = S::seg_index(s);
+      const float* __restrict__ src = exo[e] + (b * p.exo[e].steps + t) * W;
+      if constexpr (W % 4 == 0) {
+#pragma unroll 4
+        for (int i = 0; i < W; i += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+          a0[(off + i + 0) * LD + tid] = v.x; a0[(off + i + 1) * LD + tid] = v.y;
+          a0[(off + i + 2) * LD + tid] = v.z; a0[(off + i + 3) * LD + tid] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) a0[(off + i) * LD + tid] = __ldg(src + i);
+      }
+    }
+    off += W;
+  });
+}
+
+// stage the prepared weight block into shared memory with one bulk TMA copy (UBLKCP)
+template <int FLOATS_A, int FLOATS_B>
+__device__ __forceinline__ void stage_weights(float* __restrict__ dst_a, const float* __restrict__ src_a,
+                                              float* __restrict__ dst_b, const float* __restrict__ src_b,
+                                              uint64_t* bar, int tid) {
+  if constexpr (FLOATS_A + FLOATS_B > 0) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, (FLOATS_A + FLOATS_B) * 4);
+      if constexpr (FLOATS_A > 0) tma_bulk_g2s(dst_a, src_a, FLOATS_A * 4, bar);
+      if constexpr (FLOATS_B > 0) tma_bulk_g2s(dst_b, src_b, FLOATS_B * 4, bar);
+    }
+    mbar_wait(bar, 0);
+  }
+}
+
+// ================================================================================================
+// forward kernel
+template <class S>
+__global__ void __launch_bounds__(S::THREADS) nm_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
+  using KC = KCfg<S>;
+  using PolCfg = typename KC::PolCfg;
+  using RhsCfg = typename KC::RhsCfg;
+  constexpr int NX = KC::NX, NU = KC::NU, NY = KC::NY, ND = KC::ND, NUA = KC::NUA, NYA = KC::NYA, NDA = KC::NDA;
+  constexpr int TILE = KC::TILE, THREADS = KC::THREADS, LD = KC::LD;
+  extern __shared__ __align__(128) float smem[];
+  float* sm_w = smem;
+  float* pp0 = sm_w + (KC::W_SMEM ? KC::W_FLOATS_FWD : 0);
+  float* pp1 = pp0 + KC::FWD_PP0;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(pp1 + KC::FWD_PP1);
+  VarTable& vt = *reinterpret_cast<VarTable*>(pp1 + KC::FWD_PP1 + 16);
+  const int tid = threadIdx.x;
+  const NmPlan& p = plan;
+
+  // only the forward halves of the prepared weight blocks are needed here
+  const float* Wpol;
+  const float* Wrhs;
+  if constexpr (KC::W_SMEM) {
+    stage_weights<round_up(PolCfg::FWD_W, 4), round_up(RhsCfg::FWD_W, 4)>(
+        sm_w, args.wprep + KC::POL_W_OFF, sm_w + KC::RHS_WF_OFF, args.wprep + KC::RHS_W_OFF, bar, tid);
+    Wpol = sm_w;
+    Wrhs = sm_w + KC::RHS_WF_OFF;
+  } else {
+    Wpol = args.wprep + KC::POL_W_OFF;
+    Wrhs = args.wprep + KC::RHS_W_OFF;
+  }
+
+  if (tid == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = p.nsteps + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = p.nsteps; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = p.nsteps; vt.D[NM_VAR_Y] = NY;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+  }
+  __syncthreads();
+
+  float tsum[NM_MAX_TERMS];
+#pragma unroll
+  for (int k = 0; k < NM_MAX_TERMS; ++k) tsum[k] = 0.f;
+
+  const int T = p.nsteps;
+  for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+    const int64_t b_raw = int64_t(tile) * TILE + tid;
+    const bool owner = tid < TILE;
+    const bool valid = owner && b_raw < args.B;
+    const int64_t b = b_raw < args.B ? b_raw : args.B - 1;
+
+    float x[NX];
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = __ldg(args.x0 + b * NX + i);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1)) * NX + i] = x[i];
+      }
+    }
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      float u[NUA], y[NYA], d[NDA];
+      u[0] = 0.f; y[0] = 0.f; d[0] = 0.f;
+      if (owner) {
+        if constexpr (S::HAS_OUTPUT) {                      // y_t = C x_t  (grid_response cell 7)
+#pragma unroll
+          for (int j = 0; j < NY; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) s = fmaf(x[i], p.C[j * NX + i], s);
+            y[j] = s;
+            if (valid) args.y_traj[(b * T + t) * NY + j] = s;
+          }
+        }
+        if constexpr (KC::HAS_POL) build_policy_input<S>(p, args.exo, pp0, tid, b, t, x, y);
+      }
+      if constexpr (KC::HAS_POL) {
+        __syncthreads();
+        mlp_forward<PolCfg, typename S::Pol, TILE, THREADS, false>(Wpol, pp0, pp1, nullptr, nullptr, p.policy.act_param, tid);
+        if (owner) {
+          const float* outp = (PolCfg::NL & 1) ? pp1 : pp0;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            const float o = outp[j * LD + tid];
+            u[j] = bounds_fwd<S::Pol::BOUNDS>(o, p.policy.bmin[j], p.policy.bmax[j]);
+            if (valid) args.u_traj[(b * T + t) * NU + j] = u[j];
+          }
+        }
+      }
+      if constexpr (ND > 0) {
+        if (owner) {
+          const float* src = args.exo[S::DIST_EXO] + (b * p.exo[S::DIST_EXO].steps + t) * ND;
+#pragma unroll
+          for (int j = 0; j < ND; ++j) d[j] = __ldg(src + j);
+        }
+      }
+      float xn[NX];
+      if constexpr (!KC::HAS_RHS_MLP) {
+        if (owner) Dyn<S>::step(p, x, u, d, xn);
+      } else {
+        // neural right-hand side: every stage is a CTA-cooperative MLP evaluation
+        constexpr int NS = Tableau<S::INTEG>::NS;
+        float k[4][NX];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (owner) {
+            float xs[NX];
+            stage_input<S::INTEG, NX>(s, p.h, x, k[s > 0 ? s - 1 : 0], xs);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) pp0[i * LD + tid] = xs[i];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) pp0[(NX + j) * LD + tid] = u[j];
+          }
+          __syncthreads();
+          mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, false>(Wrhs, pp0, pp1, nullptr, nullptr, p.rhs_mlp.act_param, tid);
+          if (owner) {
+            const float* outp = (RhsCfg::NL & 1) ? pp1 : pp0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) k[s][i] = outp[i * LD + tid];
+          }
+          // the next writer of pp0/pp1 is this same thread's own column (stage input) or, behind a
+          // barrier, the next layer GEMM: no extra barrier needed here
+        }
+        if (owner) combine_stages<S::INTEG, NX>(p.h, x, k, xn);
+      }
+      if (owner) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = xn[i];
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1) + t + 1) * NX + i] = x[i];
+        }
+      }
+    }
+    // PenaltyLoss scoring of this thread's trajectory (its entries were stored by this same thread)
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < NM_MAX_TERMS; ++k)
+        if (k < p.n_terms) tsum[k] += term_sum_traj(p.terms[k], vt, b);
+    }
+  }
+
+  // block reduction of the term sums (double) -> per-CTA partials
+  __syncthreads();
+  double* scratch = reinterpret_cast<double*>(pp0);           // activations are dead now
+#pragma unroll
+  for (int k = 0; k < NM_MAX_TERMS; ++k) {
+    if (k < p.n_terms) {
+      double v = static_cast<double>(tsum[k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) scratch[k * (THREADS / 32) + (tid >> 5)] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < p.n_terms) {
+    double v = 0.0;
+    for (int w = 0; w < THREADS / 32; ++w) v += scratch[tid * (THREADS / 32) + w];
+    args.term_partials[size_t(blockIdx.x) * NM_MAX_TERMS + tid] = v;
+  }
+  (void)Wrhs; (void)Wpol;
+}
+
+// ================================================================================================
+// adjoint kernel
+template <class S>
+__global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
+  using KC = KCfg<S>;
+  using PolCfg = typename KC::PolCfg;
+  using RhsCfg = typename KC::RhsCfg;
+  constexpr int NX = KC::NX, NU = KC::NU, NY = KC::NY, ND = KC::ND, NUA = KC::NUA, NYA = KC::NYA;
+  constexpr int TILE = KC::TILE, THREADS = KC::THREADS, LD = KC::LD;
+  constexpr bool SPILL = KC::DW_SPILL;
+  extern __shared__ __align__(128) float smem[];
+  float* sm_w = smem;
+  float* keep_pol = sm_w + (KC::W_SMEM ? KC::W_FLOATS_ALL : 0);
+  float* keep_rhs = keep_pol + PolCfg::KEEP_FLOATS;
+  float* dbuf0 = keep_rhs + RhsCfg::KEEP_FLOATS;
+  float* dbuf1 = dbuf0 + KC::DELTA_ROWS * LD;
+  float* coef = dbuf1 + KC::DELTA_ROWS * LD;                   // [NM_MAX_TERMS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef + 32);
+  VarTable& vt = *reinterpret_cast<VarTable*>(coef + 48);
+  const int tid = threadIdx.x;
+  const NmPlan& p = plan;
+  const int T = p.nsteps;
+
+  const float* Wpol;
+  const float* Wrhs;
+  if constexpr (KC::W_SMEM) {
+    stage_weights<KC::W_FLOATS_ALL, 0>(sm_w, args.wprep, nullptr, nullptr, bar, tid);
+    Wpol = sm_w + KC::POL_W_OFF;
+    Wrhs = sm_w + KC::RHS_W_OFF;
+  } else {
+    Wpol = args.wprep + KC::POL_W_OFF;
+    Wrhs = args.wprep + KC::RHS_W_OFF;
+  }
+
+  // effective upstream gradient of every fused term: d(term) + d(objective|penalty) + d(loss)
+  if (tid < NM_MAX_TERMS) {
+    float c = 0.f;
+    if (tid < p.n_terms) {
+      const NmTerm& tm = p.terms[tid];
+      float up = 1.f;
+      if (args.grad_scalars != nullptr)
+        up = args.grad_scalars[tid] + args.grad_scalars[p.n_terms + (tm.is_objective ? 0 : 1)] + args.grad_scalars[p.n_terms + 2];
+      c = up * tm.weight / (static_cast<float>(args.b_total) * static_cast<float>(tm.t_len) * static_cast<float>(tm.d_len));
+    }
+    coef[tid] = c;
+  }
+  // this CTA's private gradient block (summed over CTAs by nm_grad_finalize_kernel)
+  float* gblock = args.grad_partials + size_t(blockIdx.x) * size_t(p.n_params > 0 ? p.n_params : 1);
+  for (int i = tid; i < p.n_params; i += THREADS) gblock[i] = 0.f;
+  if (tid == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = NY;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+  }
+  __syncthreads();
+
+  using PolStore = std::conditional_t<KC::HAS_POL && !SPILL, DwStore<PolCfg, TILE, THREADS>, DwNone>;
+  using RhsStore = std::conditional_t<KC::HAS_RHS_MLP && !SPILL, DwStore<RhsCfg, TILE, THREADS>, DwNone>;
+  PolStore pol_dw; RhsStore rhs_dw;
+  pol_dw.zero(); rhs_dw.zero();
+  float* gpol = gblock + (KC::HAS_POL ? p.policy.param_offset : 0);
+  float* grhs = gblock + (KC::HAS_RHS_MLP ? p.rhs_mlp.param_offset : 0);
+  const bool pol_train = KC::HAS_POL && p.policy.trainable;
+  const bool rhs_train = KC::HAS_RHS_MLP && p.rhs_mlp.trainable;
+
+  for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+    const int64_t b_raw = int64_t(tile) * TILE + tid;
+    const bool owner = tid < TILE;
+    const bool valid = owner && b_raw < args.B;
+    const int64_t b = b_raw < args.B ? b_raw : args.B - 1;
+
+    float lam[NX];                                              // dL/dx_{t+1}
+#pragma unroll
+    for (int i = 0; i < NX; ++i) lam[i] = 0.f;
+    if (valid) {
+      term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+      if (args.gx_ext != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
+      }
+    }
+#pragma unroll 1
+    for (int t = T - 1; t >= 0; --t) {
+      float x[NX], u[NUA], y[NYA], o[NUA], gx[NX], gu[NUA], gy[NYA];
+      u[0] = 0.f; y[0] = 0.f; o[0] = 0.f; gu[0] = 0.f; gy[0] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) gx[i] = 0.f;
+      if (owner) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = __ldg(args.x_traj + (b * (T + 1) + t) * NX + i);
+        if constexpr (S::HAS_OUTPUT) {
+#pragma unroll
+          for (int j = 0; j < NY; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) s = fmaf(x[i], p.C[j * NX + i], s);
+            y[j] = s;
+          }
+        }
+        if constexpr (KC::HAS_POL) build_policy_input<S>(p, args.exo, keep_pol, tid, b, t, x, y);
+      }
+      if constexpr (KC::HAS_POL) {
+        __syncthreads();
+        mlp_forward<PolCfg, typename S::Pol, TILE, THREADS, true>(Wpol, nullptr, nullptr, keep_pol, dbuf0, p.policy.act_param, tid);
+        if (owner) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            o[j] = dbuf0[j * LD + tid];
+            u[j] = bounds_fwd<S::Pol::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]);
+          }
+        }
+      }
+      // ---- dynamics adjoint: (gx, gu) = (d x_{t+1} / d (x_t, u_t))^T lam
+      if constexpr (!KC::HAS_RHS_MLP) {
+        if (owner) Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
+      } else {
+        constexpr int NS = Tableau<S::INTEG>::NS;
+        const float h = p.h;
+        float k[4][NX];
+        // pass 1: stage derivatives k_0 .. k_{NS-2}
+#pragma unroll
+        for (int s = 0; s + 1 < NS; ++s) {
+          if (owner) {
+            float xs[NX];
+            stage_input<S::INTEG, NX>(s, h, x, k[s > 0 ? s - 1 : 0], xs);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) keep_rhs[(NX + j) * LD + tid] = u[j];
+          }
+          __syncthreads();
+          mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
+          if (owner) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) k[s][i] = dbuf0[i * LD + tid];
+          }
+          __syncthreads();                                       // dbuf0 is rewritten by the next stage
+        }
+        // pass 2: stages in reverse, recomputing each stage's activations
+        float carry[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { carry[i] = 0.f; gx[i] = lam[i]; }
+#pragma unroll
+        for (int s = NS - 1; s >= 0; --s) {
+          if (owner) {
+            float xs[NX];
+            stage_input<S::INTEG, NX>(s, h, x, k[s > 0 ? s - 1 : 0], xs);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) keep_rhs[(NX + j) * LD + tid] = u[j];
+          }
+          __syncthreads();
+          mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
+          if (owner) {
+            const float bw = stage_weight<S::INTEG>(s, h);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) dbuf0[i * LD + tid] = valid ? fmaf(bw, lam[i], carry[i]) : 0.f;
+          }
+          __syncthreads();
+          mlp_backward<RhsCfg, typename S::RhsM, TILE, THREADS, SPILL>(Wrhs, keep_rhs, dbuf0, dbuf1, rhs_dw, grhs,
+                                                                        p.rhs_mlp.has_bias, rhs_train, p.rhs_mlp.act_param, tid);
+          if (owner) {
+            const float* gin = (RhsCfg::NL & 1) ? dbuf1 : dbuf0;
+            const float cp = stage_coupling<S::INTEG>(s, h);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { const float g = gin[i * LD + tid]; gx[i] += g; carry[i] = cp * g; }
+#pragma unroll
+            for (int j = 0; j < NU; ++j) gu[j] += gin[(NX + j) * LD + tid];
+          }
+          __syncthreads();                                       // gin buffer is rewritten by the next stage
+        }
+      }
+      // ---- loss-term gradients w.r.t. u_t and y_t
+      if (valid) {
+        if constexpr (NU > 0) {
+          term_grad_accum<NUA>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+          if (args.gu_ext != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
+          }
+        }
+        if constexpr (NY > 0) {
+          term_grad_accum<NYA>(p, vt, coef, b, NM_VAR_Y, t, NY, gy);
+          if (args.gy_ext != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NY; ++j) gy[j] += __ldg(args.gy_ext + (b * T + t) * NY + j);
+          }
+        }
+      }
+      // ---- policy adjoint
+      if constexpr (KC::HAS_POL) {
+        if (owner) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j)
+            dbuf0[j * LD + tid] = valid ? gu[j] * bounds_deriv<S::Pol::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]) : 0.f;
+        }
+        __syncthreads();
+        mlp_backward<PolCfg, typename S::Pol, TILE, THREADS, SPILL>(Wpol, keep_pol, dbuf0, dbuf1, pol_dw, gpol,
+                                                                     p.policy.has_bias, pol_train, p.policy.act_param, tid);
+        if (owner) {
+          const float* gin = (PolCfg::NL & 1) ? dbuf1 : dbuf0;
+          int off = 0;
+          static_for<0, S::NSEG>([&](auto sc) {
+            constexpr int s = decltype(sc)::value;
+            constexpr int W = S::seg_width(s);
+            if constexpr (S::seg_kind(s) == NM_SEG_STATE) {
+#pragma unroll
+              for (int i = 0; i < W; ++i) gx[i] += gin[(off + i) * LD + tid];
+            } else if constexpr (S::seg_kind(s) == NM_SEG_OUTPUT) {
+#pragma unroll
+              for (int i = 0; i < W; ++i) gy[i] += gin[(off + i) * LD + tid];
+            }
+            off += W;
+          });
+        }
+        // the next step rewrites dbuf0 (raw policy output) only after its own barriers; the input
+        // gradient buffer `gin` is rewritten by the next step's mlp_backward, also behind barriers
+      }
+      if (owner) {
+        if constexpr (S::HAS_OUTPUT) {                           // y_t = C x_t
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NY; ++j) s = fmaf(p.C[j * NX + i], gy[j], s);
+            gx[i] += s;
+          }
+        }
+        if (valid) {
+          term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+          if (args.gx_ext != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] : 0.f;
+      }
+    }
+    if (valid && args.grad_x0 != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) args.grad_x0[b * NX + i] = lam[i];
+    }
+  }
+  // persistent accumulators -> this CTA's gradient block
+  if constexpr (!SPILL) {
+    __syncthreads();
+    if constexpr (KC::HAS_POL) { if (pol_train) dw_writeout<PolCfg, TILE, THREADS>(pol_dw, gpol, p.policy.has_bias, tid); }
+    if constexpr (KC::HAS_RHS_MLP) { if (rhs_train) dw_writeout<RhsCfg, TILE, THREADS>(rhs_dw, grhs, p.rhs_mlp.has_bias, tid); }
+  }
+  (void)ND; (void)Wrhs; (void)Wpol; (void)keep_rhs;
+}
+
+}  // namespace nm

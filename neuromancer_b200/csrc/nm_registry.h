@@ -1,0 +1,33 @@
+// nm_registry.h -- internal interface between the C-ABI translation unit (nm_api.cu) and the
+// per-shape-class translation units (nm_spec_tu.cu compiled once per generated spec header).
+#pragma once
+#include <cuda_runtime.h>
+#include "nm_rollout.h"
+
+struct NmFwdCall {
+  const float* params; const float* x0; const float* const* exo;
+  float* x_traj; float* u_traj; float* y_traj;
+  void* workspace; size_t workspace_bytes; int64_t B; cudaStream_t stream;
+  // outputs of the launcher, consumed by the finalise kernel
+  double* term_partials; int grid;
+};
+struct NmBwdCall {
+  const float* params; const float* const* exo;
+  const float* x_traj; const float* u_traj; const float* y_traj;
+  const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
+  float* grad_x0;
+  void* workspace; size_t workspace_bytes; int64_t B; int64_t b_total; cudaStream_t stream;
+  float* grad_partials; int grid;
+};
+
+struct NmKernelEntry {
+  const char* signature;
+  int (*workspace)(const NmPlan*, int64_t B, size_t* fwd_bytes, size_t* bwd_bytes);
+  int (*forward)(const NmPlan*, NmFwdCall*);      // prep + rollout kernel; returns NM_OK / NM_ERR_*
+  int (*backward)(const NmPlan*, NmBwdCall*);     // prep + adjoint kernel
+  const char* info;                               // tile / threads / smem, for diagnostics
+  NmKernelEntry* next;
+};
+
+extern "C" void nm_register_kernel(NmKernelEntry* e);
+extern "C" void nm_set_error(const char* msg);

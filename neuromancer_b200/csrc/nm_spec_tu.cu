@@ -1,0 +1,154 @@
+// nm_spec_tu.cu -- compiled once per shape class:  nvcc -DNM_SPEC_HEADER='"specs/<name>.h"' ...
+// Instantiates the fused kernels for the generated spec and registers their launchers.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include "nm_kernels.cuh"
+#include "nm_registry.h"
+
+#include NM_SPEC_HEADER   // defines struct NM_SPEC_NAME (the "Shape")
+
+namespace {
+
+using namespace nm;
+
+template <class Shape, int TILE_, int THREADS_, bool W_SMEM_>
+struct Tiled : Shape { static constexpr int TILE = TILE_, THREADS = THREADS_; static constexpr bool W_SMEM = W_SMEM_; };
+
+// widest layer decides the CTA size; the largest batch tile whose buffers fit in 227 KB wins
+constexpr int shape_max_width() {
+  int m = 1;
+  for (int l = 0; l <= NM_SPEC_NAME::Pol::NL; ++l) m = cmax(m, NM_SPEC_NAME::Pol::sz(l));
+  for (int l = 0; l <= NM_SPEC_NAME::RhsM::NL; ++l) m = cmax(m, NM_SPEC_NAME::RhsM::sz(l));
+  return m;
+}
+constexpr int kThreads = shape_max_width() >= 96 ? 256 : 128;
+template <int TILE, bool WS> constexpr bool fits() { return KCfg<Tiled<NM_SPEC_NAME, TILE, kThreads, WS>>::FITS; }
+// preference: weights staged in shared memory with the largest tile; else weights streamed from L2
+constexpr bool kWSmem = fits<128, true>() || fits<64, true>();
+constexpr int kTile = kWSmem ? (fits<128, true>() ? 128 : 64) : (fits<128, false>() ? 128 : (fits<64, false>() ? 64 : 32));
+using S = Tiled<NM_SPEC_NAME, kTile, kThreads, kWSmem>;
+using KC = KCfg<S>;
+static_assert(KC::FITS, "shape class does not fit in shared memory even with a 32-trajectory tile");
+
+struct DeviceInfo { int sms = 0; int occ_fwd = 0; int occ_bwd = 0; bool ready = false; };
+DeviceInfo g_dev[64];
+std::mutex g_mu;
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { nm_set_error("cudaGetDevice failed"); return NM_ERR_CUDA; }
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (!d.ready) {
+    cudaError_t e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::FWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::BWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fwd, nm_fwd_kernel<S>, S::THREADS, KC::FWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_bwd, nm_bwd_kernel<S>, S::THREADS, KC::BWD_SMEM_BYTES);
+    if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
+    if (d.occ_fwd < 1 || d.occ_bwd < 1) { nm_set_error("kernel does not fit on an SM (occupancy 0)"); return NM_ERR_CUDA; }
+    d.ready = true;
+  }
+  *out = &d;
+  return NM_OK;
+}
+
+constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+constexpr size_t kWprepBytes = align256(size_t(KC::W_FLOATS_ALL > 0 ? KC::W_FLOATS_ALL : 4) * 4);
+
+int check_plan(const NmPlan* p) {
+  if (p->n_params < KC::N_PARAMS) { nm_set_error("plan.n_params smaller than the shape class expects"); return NM_ERR_BAD_PLAN; }
+  if (KC::HAS_POL && (p->policy.has_bias != 0) != S::Pol::BIAS) { nm_set_error("policy bias flag mismatch"); return NM_ERR_BAD_PLAN; }
+  if (KC::HAS_RHS_MLP && (p->rhs_mlp.has_bias != 0) != S::RhsM::BIAS) { nm_set_error("rhs bias flag mismatch"); return NM_ERR_BAD_PLAN; }
+  return NM_OK;
+}
+
+int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
+  DeviceInfo* d = nullptr;
+  // sizes must be computable without a device too (host-only tests): assume a B200 (148 SMs, <= 8 CTAs/SM)
+  int sms = 148, occf = 8, occb = 8, ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && device_info(&d) == NM_OK) { sms = d->sms; occf = d->occ_fwd; occb = d->occ_bwd; }
+  else { (void)cudaGetLastError(); }
+  const int64_t tiles = (B + S::TILE - 1) / S::TILE;
+  const int64_t gf = tiles < int64_t(sms) * occf ? tiles : int64_t(sms) * occf;
+  const int64_t gb = tiles < int64_t(sms) * occb ? tiles : int64_t(sms) * occb;
+  *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
+  *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float));
+  return NM_OK;
+}
+
+int launch_prep(const NmPlan* p, const float* params, float* wprep, cudaStream_t st) {
+  if constexpr (KC::W_FLOATS_ALL > 0) {
+    const int blocks = (KC::W_FLOATS_ALL + 4 * 256 - 1) / (4 * 256);
+    nm_prep_kernel<S><<<blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks), 256, 0, st>>>(*p, params, wprep);
+  }
+  return NM_OK;
+}
+
+int forward_fn(const NmPlan* p, NmFwdCall* c) {
+  int rc = check_plan(p); if (rc != NM_OK) return rc;
+  DeviceInfo* d = nullptr; rc = device_info(&d); if (rc != NM_OK) return rc;
+  size_t need_f = 0, need_b = 0; workspace_fn(p, c->B, &need_f, &need_b);
+  if (c->workspace_bytes < need_f || (reinterpret_cast<uintptr_t>(c->workspace) & 255)) { nm_set_error("forward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
+  const int tiles = int((c->B + S::TILE - 1) / S::TILE);
+  int grid = d->sms * d->occ_fwd; if (grid > tiles) grid = tiles; if (grid < 1) grid = 1;
+  char* ws = static_cast<char*>(c->workspace);
+  float* wprep = reinterpret_cast<float*>(ws);
+  c->term_partials = reinterpret_cast<double*>(ws + kWprepBytes);
+  c->grid = grid;
+  launch_prep(p, c->params, wprep, c->stream);
+  FwdArgs a{};
+  a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
+  for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
+  a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
+  a.term_partials = c->term_partials; a.B = c->B; a.num_tiles = tiles;
+  nm_fwd_kernel<S><<<grid, S::THREADS, KC::FWD_SMEM_BYTES, c->stream>>>(*p, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
+  return NM_OK;
+}
+
+int backward_fn(const NmPlan* p, NmBwdCall* c) {
+  int rc = check_plan(p); if (rc != NM_OK) return rc;
+  DeviceInfo* d = nullptr; rc = device_info(&d); if (rc != NM_OK) return rc;
+  size_t need_f = 0, need_b = 0; workspace_fn(p, c->B, &need_f, &need_b);
+  if (c->workspace_bytes < need_b || (reinterpret_cast<uintptr_t>(c->workspace) & 255)) { nm_set_error("backward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
+  const int tiles = int((c->B + S::TILE - 1) / S::TILE);
+  int grid = d->sms * d->occ_bwd; if (grid > tiles) grid = tiles; if (grid < 1) grid = 1;
+  char* ws = static_cast<char*>(c->workspace);
+  float* wprep = reinterpret_cast<float*>(ws);
+  c->grad_partials = reinterpret_cast<float*>(ws + kWprepBytes);
+  c->grid = grid;
+  launch_prep(p, c->params, wprep, c->stream);
+  BwdArgs a{};
+  a.params = c->params; a.wprep = wprep;
+  for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
+  a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
+  a.grad_scalars = c->grad_scalars; a.gx_ext = c->gx_ext; a.gu_ext = c->gu_ext; a.gy_ext = c->gy_ext;
+  a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;
+  a.B = c->B; a.b_total = c->b_total; a.num_tiles = tiles;
+  nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
+  return NM_OK;
+}
+
+char g_info[256];
+NmKernelEntry g_entry;
+
+struct Registrar {
+  Registrar() {
+    std::snprintf(g_info, sizeof(g_info), "tile=%d threads=%d w_smem=%d smem_fwd=%zu smem_bwd=%zu dw_spill=%d wprep_floats=%d",
+                  S::TILE, S::THREADS, int(S::W_SMEM), KC::FWD_SMEM_BYTES, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), KC::W_FLOATS_ALL);
+    g_entry.signature = NM_SPEC_NAME::signature();
+    g_entry.workspace = workspace_fn;
+    g_entry.forward = forward_fn;
+    g_entry.backward = backward_fn;
+    g_entry.info = g_info;
+    g_entry.next = nullptr;
+    nm_register_kernel(&g_entry);
+  }
+} g_registrar;
+
+}  // namespace

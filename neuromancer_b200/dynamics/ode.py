@@ -1,0 +1,130 @@
+"""
+State-space models and ODE right-hand sides on the hot path.
+
+API mirror of the reference (``dynamics/ode.py``: ``SSM`` :7-51, ``ODESystem`` :54-72,
+``TwoTankParam`` :216-237, ``VanDerPolControl`` :352-368).  Each class carries the kernel id
+(``NM_RHS_*``) and the constants the plan compiler copies into ``NmPlan.rhs_const``; the fused
+kernels evaluate the equations in registers.  ``ode_equations`` is the eager form for
+single-module calls.
+
+``CoupledVanDerPolControl`` is this repository's synthetic 12-state plant of benchmark config C5
+(SURVEY.md section 8(d)): a ring of ``nx/2`` ``VanDerPolControl`` oscillators with nearest-neighbour
+linear coupling ``kappa * (x1[j+1] - x1[j])``.
+"""
+import torch
+import torch.nn as nn
+
+NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 1, 2, 3, 4, 5
+
+
+class SSM(nn.Module):
+    """Discrete-time ``x+ = fx(x) + fu(u) [+ fd(d)]`` (reference ode.py:7-51).  It is lowered to
+    ``NM_DYN_SSM`` when ``fx``/``fu``/``fd`` are bias-free dense linear maps."""
+
+    def __init__(self, fx, fu, nx, nu, fd=None, nd=0):
+        super().__init__()
+        self.fx, self.fu, self.fd = fx, fu, fd
+        self.nx, self.nu, self.nd = nx, nu, nd
+        self.in_features, self.out_features = nx + nu + nd, nx
+
+    def forward(self, x, u, d=None):
+        assert x.dim() == 2 and u.dim() == 2
+        nxt = self.fx(x) + self.fu(u)
+        if self.fd is not None and d is not None:
+            assert d.dim() == 2
+            nxt = nxt + self.fd(d)
+        return nxt
+
+
+class ODESystem(nn.Module):
+    """Base class of continuous-time right-hand sides ``dx/dt = f(x, u)``."""
+
+    nm_rhs_id = None
+
+    def __init__(self, insize, outsize):
+        super().__init__()
+        self.in_features, self.out_features = insize, outsize
+        self.nx = outsize
+        self.nu = insize - outsize
+
+    def ode_equations(self, x, *args):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def rhs_constants(self):
+        """Constants handed to the kernel (``NmPlan.rhs_const``)."""
+        return []
+
+    def forward(self, x, *args):
+        assert x.dim() == 2
+        return self.ode_equations(x, *args)
+
+
+class TwoTankParam(ODESystem):
+    """Two-tank level dynamics with pump and valve inputs (reference ode.py:216-237)."""
+
+    nm_rhs_id = NM_RHS_TWOTANK
+
+    def __init__(self, insize=4, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        self.c1 = nn.Parameter(torch.tensor([0.1]), requires_grad=True)
+        self.c2 = nn.Parameter(torch.tensor([0.1]), requires_grad=True)
+
+    def rhs_constants(self):
+        return [float(self.c1), float(self.c2)]
+
+    def ode_equations(self, x, u):
+        lvl = torch.clip(x, min=0, max=1.0)
+        act = torch.clip(u, min=0, max=1.0)
+        h1, h2 = lvl[:, 0:1], lvl[:, 1:2]
+        pump, valve = act[:, 0:1], act[:, 1:2]
+        out1 = self.c2 * torch.sqrt(h1)
+        d1 = self.c1 * (1.0 - valve) * pump - out1
+        d2 = self.c1 * valve * pump + out1 - self.c2 * torch.sqrt(h2)
+        return torch.cat([d1, d2], dim=-1)
+
+
+class VanDerPolControl(ODESystem):
+    """Controlled Van der Pol oscillator (reference ode.py:352-368)."""
+
+    nm_rhs_id = NM_RHS_VDP
+
+    def __init__(self, insize=3, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        self.mu = nn.Parameter(torch.tensor([1.0]), requires_grad=True)
+
+    def rhs_constants(self):
+        return [float(self.mu)]
+
+    def ode_equations(self, x, u):
+        pos, vel = x[:, 0:1], x[:, 1:2]
+        return torch.cat([vel, self.mu * (1 - pos ** 2) * vel - pos + u], dim=-1)
+
+
+class CoupledVanDerPolControl(ODESystem):
+    """Ring of ``n_osc`` controlled Van der Pol oscillators, state ordered
+    ``[x1_0, x2_0, x1_1, x2_1, ...]``, one input per oscillator:
+
+        dx1_j = x2_j
+        dx2_j = mu*(1 - x1_j**2)*x2_j - x1_j + u_j + kappa*(x1_{(j+1) % n} - x1_j)
+    """
+
+    nm_rhs_id = NM_RHS_CVDP
+
+    def __init__(self, n_osc=6, mu=1.0, kappa=0.1):
+        super().__init__(insize=3 * n_osc, outsize=2 * n_osc)
+        self.n_osc = n_osc
+        self.mu = nn.Parameter(torch.tensor([float(mu)]), requires_grad=False)
+        self.kappa = nn.Parameter(torch.tensor([float(kappa)]), requires_grad=False)
+
+    def rhs_constants(self):
+        return [float(self.mu), float(self.kappa)]
+
+    def ode_equations(self, x, u):
+        pos, vel = x[:, 0::2], x[:, 1::2]
+        nxt = torch.roll(pos, shifts=-1, dims=1)
+        acc = self.mu * (1 - pos ** 2) * vel - pos + u + self.kappa * (nxt - pos)
+        return torch.stack([vel, acc], dim=-1).reshape(x.shape[0], -1)
+
+
+ode = {"TwoTankParam": TwoTankParam, "VanDerPolControl": VanDerPolControl,
+       "CoupledVanDerPolControl": CoupledVanDerPolControl}

@@ -1,0 +1,270 @@
+"""
+Bridge between the Python API and the C ABI (``libnm_rollout.so``).
+
+``FusedRollout`` is the ``torch.autograd.Function`` whose forward launches ``nm_rollout_forward``
+(one persistent kernel for the whole horizon + a tiny finalise kernel) and whose backward launches
+``nm_rollout_backward`` (the fused adjoint / BPTT kernel + gradient finalise).  PyTorch is used for
+device memory, streams and autograd bookkeeping only; all arithmetic of the path happens in the
+sm_100a kernels under ``csrc/``.
+
+No fallback: non-CUDA tensors or a missing extension raise immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .plan import PlanError, RolloutPlan
+
+_WORLD = {"size": 1}   # set by neuromancer_b200.distributed when gradients are all-reduced
+
+
+def set_world_size(n: int) -> None:
+    """Loss means are taken over ``B_local * world_size`` trajectories in the adjoint kernel, so a
+    SUM all-reduce of the flat gradient equals the global-mean gradient (DDP-average semantics)."""
+    _WORLD["size"] = int(n)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"neuromancer_b200: '{what}' lives on {t.device}; the fused rollout runs on CUDA (sm_100a) "
+            "only and has no CPU fallback. Move the batch and the problem to a CUDA device.")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"neuromancer_b200: '{what}' must be float32, got {t.dtype}")
+
+
+class ParamArena:
+    """Flat fp32 buffer the kernels read parameters from / write gradients to.
+
+    Module parameters are re-pointed to be views of the arena (``p.data = arena[off:off+n]``), so
+    optimiser updates and ``load_state_dict`` write straight into the buffer the kernel reads and
+    no per-step packing is needed.  If something replaced ``p.data`` (``module.to(...)``) the views
+    are re-adopted on the next call."""
+
+    def __init__(self, plan: RolloutPlan, device):
+        self.n = int(plan.c.n_params)
+        self.flat = torch.empty(max(self.n, 1), dtype=torch.float32, device=device)
+        self.slices = plan.param_slices
+        self.adopt(plan.params)
+
+    def adopt(self, params):
+        for p, (off, n) in zip(params, self.slices):
+            view = self.flat[off:off + n].view(p.shape)
+            if p.data.data_ptr() != view.data_ptr() or p.data.device != self.flat.device:
+                view.copy_(p.data.to(self.flat.device, torch.float32))
+                p.data = view
+
+    def in_sync(self, params) -> bool:
+        base = self.flat.data_ptr()
+        return all(p.data.data_ptr() == base + 4 * off for p, (off, _) in zip(params, self.slices))
+
+
+class _Workspace:
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class FusedRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, x0, *tensors):
+        # tensors = exo tensors (n_exo) followed by the parameters (views of the arena)
+        plan: RolloutPlan = runner.plan
+        p = plan.c
+        lib = L.load()
+        B = x0.shape[0]
+        dev = x0.device
+        n_exo = p.n_exo
+        exo = tensors[:n_exo]
+        x_traj = torch.empty(B, p.nsteps + 1, p.nx, dtype=torch.float32, device=dev)
+        u_traj = torch.empty(B, p.nsteps, p.nu, dtype=torch.float32, device=dev) if p.nu else None
+        y_traj = torch.empty(B, p.nsteps, p.ny, dtype=torch.float32, device=dev) if p.ny else None
+        scalars = torch.empty(plan.n_scalars, dtype=torch.float32, device=dev)
+        fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
+        L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
+                "nm_rollout_workspace_bytes")
+        ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
+        exo_ptrs = (C.c_void_p * max(n_exo, 1))(*[e.data_ptr() for e in exo])
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            L.check(lib.nm_rollout_forward(C.byref(p), _ptr(runner.arena.flat), _ptr(x0), exo_ptrs,
+                                           _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(scalars),
+                                           _ptr(ws), ws.numel(), B, stream), "nm_rollout_forward")
+        runner.launches += lib.nm_last_launch_count()
+        ctx.runner, ctx.B, ctx.exo = runner, B, exo
+        ctx.trajs = (x_traj, u_traj, y_traj)
+        ctx.n_exo = n_exo
+        ctx.n_tensors = len(tensors)
+        outs = [x_traj, u_traj if u_traj is not None else x_traj.new_empty(0),
+                y_traj if y_traj is not None else x_traj.new_empty(0), scalars]
+        ctx.mark_non_differentiable(*[o for o in outs[1:3] if o.numel() == 0])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, gx, gu, gy, gs):
+        runner = ctx.runner
+        plan: RolloutPlan = runner.plan
+        p = plan.c
+        lib = L.load()
+        x_traj, u_traj, y_traj = ctx.trajs
+        dev = x_traj.device
+        B = ctx.B
+
+        def ext(g, ref):
+            if g is None or ref is None or g.numel() == 0:
+                return None
+            return g.contiguous()
+        gx, gu, gy = ext(gx, x_traj), ext(gu, u_traj), ext(gy, y_traj)
+        if gs is not None:
+            gs = gs.contiguous()
+        else:
+            gs = torch.zeros(plan.n_scalars, dtype=torch.float32, device=dev)
+        gflat = torch.empty_like(runner.arena.flat)
+        fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
+        L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
+                "nm_rollout_workspace_bytes")
+        ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
+        exo_ptrs = (C.c_void_p * max(ctx.n_exo, 1))(*[e.data_ptr() for e in ctx.exo])
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        want_x0 = ctx.needs_input_grad[1]
+        gx0 = torch.empty(B, p.nx, dtype=torch.float32, device=dev) if want_x0 else None
+        with torch.cuda.device(dev):
+            L.check(lib.nm_rollout_backward(
+                C.byref(p), _ptr(runner.arena.flat), exo_ptrs, _ptr(x_traj), _ptr(u_traj), _ptr(y_traj),
+                _ptr(gs), _ptr(gx), _ptr(gu), _ptr(gy), _ptr(gflat), _ptr(gx0), _ptr(ws), ws.numel(),
+                B, B * _WORLD["size"], stream), "nm_rollout_backward")
+        runner.launches += lib.nm_last_launch_count()
+        runner.last_grad_flat = gflat
+        grads = [None, gx0] + [None] * ctx.n_exo
+        for q, (off, n) in zip(plan.params, plan.param_slices):
+            grads.append(gflat[off:off + n].view(q.shape) if q.requires_grad else None)
+        return tuple(grads)
+
+
+class RolloutRunner:
+    """Per-plan runtime state: parameter arena, workspace, launch counter."""
+
+    def __init__(self, plan: RolloutPlan, device):
+        self.plan = plan
+        self.arena = ParamArena(plan, device)
+        self.workspace = _Workspace()
+        self.launches = 0
+        self.last_grad_flat = None
+        lib = L.load()
+        if not lib.nm_has_kernel(C.byref(plan.c)):
+            from . import build
+            build.ensure_specialisation(plan)     # compiles + nm_load_plugin; raises on failure
+            if not lib.nm_has_kernel(C.byref(plan.c)):
+                raise L.NmError(f"no sm_100a specialisation for {plan.signature()}")
+
+    def __call__(self, data: Dict[str, torch.Tensor]):
+        plan, lay = self.plan, self.plan.layout
+        x_in = data[lay.state_key]
+        _require_cuda(x_in, lay.state_key)
+        if x_in.dim() != 3 or x_in.shape[2] != lay.nx:
+            raise PlanError(f"'{lay.state_key}' must be [batch, 1, {lay.nx}], got {tuple(x_in.shape)}")
+        if x_in.shape[1] != 1:
+            raise PlanError(
+                f"'{lay.state_key}' carries {x_in.shape[1]} time entries; the fused rollout takes the "
+                "initial condition only ([batch, 1, nx])")
+        for k in (lay.action_key, lay.output_key):
+            if k is not None and k in data:
+                raise PlanError(f"key '{k}' is produced by the rollout but already present in the data")
+        x0 = x_in[:, 0, :].contiguous()
+        exo = []
+        for k in plan.exo_keys:
+            t = data[k]
+            _require_cuda(t, k)
+            exo.append(t.contiguous())
+        if not self.arena.in_sync(plan.params):
+            self.arena.adopt(plan.params)
+        x, u, y, scalars = FusedRollout.apply(self, x0, *exo, *plan.params)
+        return x, (u if lay.action_key is not None else None), (y if lay.output_key is not None else None), scalars
+
+
+def _runner_for(plan: RolloutPlan, device) -> RolloutRunner:
+    r = getattr(plan, "_runner", None)
+    if r is None or r.arena.flat.device != device:
+        r = RolloutRunner(plan, device)
+        plan._runner = r
+    return r
+
+
+def run_rollout(plan: RolloutPlan, data):
+    """Execute ``plan`` on ``data``; returns ``(output dict, scalars tensor)``."""
+    lay = plan.layout
+    runner = _runner_for(plan, data[lay.state_key].device)
+    x, u, y, scalars = runner(data)
+    out = dict(data)
+    out[lay.state_key] = x
+    if u is not None:
+        out[lay.action_key] = u
+    if y is not None:
+        out[lay.output_key] = y
+    return out, scalars
+
+
+def run_problem(system, loss, data):
+    """Fused ``Problem.forward``: rollout + PenaltyLoss scoring (reference problem.py:197-202)."""
+    from .problem import LazyOutputs
+    batch = system.init(dict(data))
+    plan = system.plan_for(batch, loss=loss)
+    traj, scalars = run_rollout(plan, batch)
+    out = LazyOutputs(traj)
+    n = plan.c.n_terms
+    obj_total, pen_total = scalars[n], scalars[n + 1]
+    for i, (term, _) in enumerate(plan.fused_terms):
+        out[term.output_keys[0]] = scalars[i]
+    # terms that could not be lowered: evaluated with torch ops on the kernel's trajectories; their
+    # gradient reaches the adjoint kernel through grad_x_ext / grad_u_ext / grad_y_ext
+    per_constraint = {}
+    for term, is_obj in plan.python_terms:
+        res = term(traj)
+        if isinstance(res, torch.Tensor):
+            res = {term.output_keys[0]: res}
+        out.update(res)
+        val = res[term.output_keys[0]]
+        if is_obj:
+            obj_total = obj_total + val
+        else:
+            pen_total = pen_total + val
+            per_constraint[id(term)] = (res[term.output_keys[1]], res[term.output_keys[2]])
+    out["objective_loss"] = obj_total
+    out["penalty_loss"] = pen_total
+    out["loss"] = scalars[n + 2] if not plan.python_terms else obj_total + pen_total
+
+    # value / violation tensors and the C_* matrices: on demand only
+    fused_constraints = [t for t, is_obj in plan.fused_terms if isinstance(t, type(None)) is False]
+
+    def materialise_term(term):
+        def thunk():
+            _, value, violation = term.evaluate(traj)
+            return {term.output_keys[1]: value, term.output_keys[2]: violation}
+        return thunk
+    for term, _ in plan.fused_terms:
+        out.register(term.output_keys[1:], materialise_term(term))
+
+    if len(loss.constraints):
+        def c_matrices():
+            per = []
+            for con in loss.constraints:
+                if id(con) in per_constraint:
+                    per.append(per_constraint[id(con)])
+                else:
+                    per.append((out[con.output_keys[1]], out[con.output_keys[2]]))
+            return loss.constraint_matrices(loss.constraints, per)
+        out.register(["C_violations", "C_values", "C_eq_violations", "C_ineq_violations",
+                      "C_eq_values", "C_ineq_values"], c_matrices)
+    return out

@@ -1,0 +1,175 @@
+"""
+TEST INFRASTRUCTURE -- oracle-side definitions of the benchmark / test problems.
+
+Each builder returns the ``spec`` consumed by ``dpc_oracle.run_case`` for one named case, given the
+flat list of trainable tensors (W0, b0, W1, b1, ... of the policy, then of the MLP right-hand side).
+The problems are the ones of ``BASELINE.json`` as the reference examples define them (file:line in
+each builder); constants are restated here independently of the product package.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import dpc_oracle as O
+
+
+def _term(name, objective, cmp, norm, weight, left, right):
+    return dict(name=name, objective=objective, cmp=cmp, norm=norm, weight=weight, left=left, right=right)
+
+
+def _t(v, like):
+    return torch.tensor(v, dtype=like.dtype)
+
+
+# c1 -- examples/control/Part_1_stabilize_linear_system.py:14-67 (horizon 50 per BASELINE.json)
+def c1(params: List[torch.Tensor], nsteps=50) -> dict:
+    A = _t([[1.2, 1.0], [0.0, 1.0]], params[0])
+    B = _t([[1.0], [0.5]], params[0])
+    nodes = [dict(fn=lambda x: O.mlp_forward(params, x, "relu"), inputs=["X"], outputs=["U"]),
+             dict(fn=lambda x, u: O.ssm_step(x, u, None, A, B), inputs=["X", "U"], outputs=["X"])]
+    terms = [_term("action_loss", True, "eq", 2, 0.0001, lambda d: d["U"], lambda d: 0.),
+             _term("regulation_loss", True, "eq", 2, 10., lambda d: d["X"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["X", "U"])
+
+
+# c2 -- examples/control/Part_3_ref_tracking_ODE.py:32-163
+def c2(params, nsteps=30) -> dict:
+    c1_, c2_ = _t(0.08, params[0]), _t(0.04, params[0])
+    h = _t(1.0, params[0])
+    rhs = lambda x, u: O.rhs_twotank(x, u, c1_, c2_)
+    nodes = [dict(fn=lambda x, r: O.bounds_scaling(O.mlp_forward(params, torch.cat([x, r], dim=-1), "gelu"), 0, 1.),
+                  inputs=["x", "r"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk4_step(rhs, x, h, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("ref_tracking", True, "eq", 2, 5., lambda d: d["x"], lambda d: d["r"]),
+             _term("x_min", False, "gt", 1, 10., lambda d: d["x"], lambda d: 0),
+             _term("x_max", False, "lt", 1, 10., lambda d: d["x"], lambda d: 1.),
+             _term("x_N_min", False, "gt", 1, 10., lambda d: d["x"][:, [-1], :], lambda d: d["r"] - 0.01),
+             _term("x_N_max", False, "lt", 1, 10., lambda d: d["x"][:, [-1], :], lambda d: d["r"] + 0.01)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+# c3 -- examples/ODEs/Part_1_NODE.py:58-104 with integrators.RK4
+def c3(params, nsteps=100) -> dict:
+    f = lambda x: O.mlp_forward(params, x, "relu")
+    nodes = [dict(fn=lambda x: O.rk4_step(f, x, 0.1), inputs=["xn"], outputs=["xn"])]
+    xhat = lambda d: d["xn"][:, :-1, :]
+    terms = [_term("ref_loss", True, "eq", 2, 1.0, xhat, lambda d: d["X"]),
+             _term("FD_loss", True, "eq", 2, 2., lambda d: d["X"][:, 1:, :] - d["X"][:, :-1, :],
+                   lambda d: xhat(d)[:, 1:, :] - xhat(d)[:, :-1, :])]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["xn"])
+
+
+# c4 -- examples/domain_examples/grid_response.ipynb cells 7-30 with synthetic Schur-stable matrices
+C4_A = [[0.9500, 0.0200, 0.0000, 0.0100], [0.0300, 0.9000, 0.0200, 0.0000],
+        [0.0000, 0.0400, 0.9200, 0.0100], [0.0200, 0.0100, 0.0300, 0.9300]]
+C4_B = [[0.00], [0.00], [0.05], [0.10]]
+C4_E = [[0.010, 0.000, 0.002], [0.020, 0.001, 0.000], [0.005, 0.002, 0.001], [0.002, 0.001, 0.003]]
+C4_C = [[0.0, 0.0, 0.0, 1.0]]
+
+
+def c4(params, nsteps=96) -> dict:
+    A, B, E, C = (_t(m, params[0]) for m in (C4_A, C4_B, C4_E, C4_C))
+    umin, umax = _t([0.0], params[0]), _t([5000.0], params[0])
+    keys = ["y", "d_obs_lookahead", "ymin_lookahead", "ymax_lookahead", "price_lookahead"]
+    nodes = [dict(fn=lambda x: torch.nn.functional.linear(x, C), inputs=["x"], outputs=["y"]),
+             dict(fn=lambda *a: O.bounds_scaling(O.mlp_forward(params, torch.cat(a, dim=-1), "leakyrelu"), umin, umax),
+                  inputs=keys, outputs=["u"]),
+             dict(fn=lambda x, u, d: O.ssm_step(x, u, d, A, B, E), inputs=["x", "u", "d"], outputs=["x"])]
+    terms = [_term("price_loss", True, "eq", 2, 1, lambda d: d["u"] * d["price_lookahead"][:, :-1, 0:1],
+                   lambda d: torch.zeros_like(d["u"])),
+             _term("y_min", False, "gt", 1, 5e06, lambda d: d["y"], lambda d: d["ymin_lookahead"][:, :-1, 0:1]),
+             _term("y_max", False, "lt", 1, 5e06, lambda d: d["y"], lambda d: d["ymax_lookahead"][:, :-1, 0:1])]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u", "y"])
+
+
+# c5 -- examples/control/Part_2_stabilize_ODE.py:33-135 scaled to 6 coupled oscillators
+def c5(params, nsteps=200) -> dict:
+    mu, kappa, h = _t([1.0], params[0]), _t([0.1], params[0]), _t(0.05, params[0])
+    rhs = lambda x, u: O.rhs_cvdp(x, u, mu, kappa)
+    nodes = [dict(fn=lambda x, r: O.bounds_scaling(O.mlp_forward(params, torch.cat([x, r], dim=-1), "gelu"), -5., 5.),
+                  inputs=["x", "r"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk4_step(rhs, x, h, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("state_loss", True, "eq", 2, 1., lambda d: d["x"], lambda d: d["r"]),
+             _term("action_loss", True, "eq", 2, 0.01, lambda d: d["u"], lambda d: 0.),
+             _term("x_min", False, "gt", 1, 10., lambda d: d["x"], lambda d: -4.),
+             _term("x_max", False, "lt", 1, 10., lambda d: d["x"], lambda d: 4.),
+             _term("x_N_min", False, "gt", 1, 10., lambda d: d["x"][:, [-1], :], lambda d: d["r"] - 0.01),
+             _term("x_N_max", False, "lt", 1, 10., lambda d: d["x"][:, [-1], :], lambda d: d["r"] + 0.01)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+# ---- small shape classes exercising the remaining activations / bounds / integrators ------------
+def t_vdp_rk4_tanh_clamp(params, nsteps=12) -> dict:
+    mu = _t(1.0, params[0])
+    rhs = lambda x, u: O.rhs_vdp(x, u, mu)
+    nodes = [dict(fn=lambda x, r: O.bounds_clamp(O.mlp_forward(params, torch.cat([x, r], dim=-1), "tanh"), -1., 1.),
+                  inputs=["x", "r"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk4_step(rhs, x, 0.1, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 3., lambda d: d["x"], lambda d: d["r"]),
+             _term("eff", True, "eq", 1, 0.1, lambda d: d["u"], lambda d: 0.),
+             _term("du", True, "eq", 2, 0.5, lambda d: d["u"][:, 1:, :] - d["u"][:, :-1, :], lambda d: 0.),
+             _term("box", False, "lt", 2, 2., lambda d: d["x"], lambda d: 1.5)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+def t_vdp_euler_elu(params, nsteps=9) -> dict:
+    mu = _t(0.7, params[0])
+    rhs = lambda x, u: O.rhs_vdp(x, u, mu)
+    nodes = [dict(fn=lambda x: O.mlp_forward(params, x, "elu", bias=False), inputs=["x"], outputs=["u"]),
+             dict(fn=lambda x, u: O.euler_step(rhs, x, 0.05, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.),
+             _term("pen", False, "gt", 1, 4., lambda d: d["u"], lambda d: -0.2)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+def t_twotank_rk2_sigmoid(params, nsteps=7) -> dict:
+    c1_, c2_ = _t(0.08, params[0]), _t(0.04, params[0])
+    rhs = lambda x, u: O.rhs_twotank(x, u, c1_, c2_)
+    nodes = [dict(fn=lambda x, r: O.bounds_scaling(O.mlp_forward(params, torch.cat([x, r], dim=-1), "sigmoid"), 0., 1.),
+                  inputs=["x", "r"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk2_step(rhs, x, 0.5, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: d["r"])]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+def _ssm_softplus_mats(like):
+    g0 = torch.Generator(device="cpu")
+    g0.manual_seed(99)
+    nx, nu, nd, ny = 3, 2, 2, 2
+    A = 0.3 * torch.randn(nx, nx, generator=g0) + 0.5 * torch.eye(nx)
+    B, E, C = (0.5 * torch.randn(*s, generator=g0) for s in ((nx, nu), (nx, nd), (ny, nx)))
+    return [m.to(like.dtype) for m in (A, B, E, C)]
+
+
+def t_ssm_softplus(params, nsteps=10) -> dict:
+    A, B, E, C = _ssm_softplus_mats(params[0])
+    nodes = [dict(fn=lambda x: torch.nn.functional.linear(x, C), inputs=["x"], outputs=["y"]),
+             dict(fn=lambda y, d, x: O.mlp_forward(params, torch.cat([y, d, x], dim=-1), "softplus"),
+                  inputs=["y", "d", "x"], outputs=["u"]),
+             dict(fn=lambda x, u, d: O.ssm_step(x, u, d, A, B, E), inputs=["x", "u", "d"], outputs=["x"])]
+    terms = [_term("o1", True, "eq", 2, 1.0, lambda d: d["y"], lambda d: 1.),
+             _term("o2", True, "eq", 2, 0.1, lambda d: d["u"], lambda d: 0.),
+             _term("c1", False, "lt", 1, 5., lambda d: d["x"][:, 1:, 0:2], lambda d: 2.0)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u", "y"])
+
+
+def t_node_policy_euler(params, nsteps=6) -> dict:
+    pol, rhs_p = params[:6], params[6:]
+    f = lambda x, u: O.mlp_forward(rhs_p, torch.cat([x, u], dim=-1), "tanh")
+    nodes = [dict(fn=lambda x: O.mlp_forward(pol, x, "relu"), inputs=["x"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk2_step(f, x, 0.2, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.5),
+             _term("eff", True, "eq", 2, 0.2, lambda d: d["u"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
+         "t_vdp_rk4_tanh_clamp": t_vdp_rk4_tanh_clamp, "t_vdp_euler_elu": t_vdp_euler_elu,
+         "t_twotank_rk2_sigmoid": t_twotank_rk2_sigmoid, "t_ssm_softplus": t_ssm_softplus,
+         "t_node_policy_euler": t_node_policy_euler}
+
+
+def build(name: str, params: List[torch.Tensor], **kw) -> dict:
+    return CASES[name](params, **kw)

@@ -1,0 +1,222 @@
+"""
+TEST INFRASTRUCTURE -- CPU oracle of the fused DPC rollout.  Not part of the product path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module; nothing under ``neuromancer_b200/`` does.
+
+A plain-PyTorch (CPU, fp32 or fp64) *functional restatement* of the reference algorithm for the
+hot path, op for op and in the reference's operation order, so that on CPU it is bit-identical to
+running pnnl/neuromancer 1.5.6 itself (``oracle/pin_oracle.py`` asserts exactly that against the
+unmodified reference wherever ``/root/reference`` exists, and writes the golden fixtures under
+``tests/golden``).  Gradients come from torch autograd over the restated forward -- the same graph
+the reference's ``loss.backward()`` (trainer.py:250) differentiates.
+
+PARITY PIN: pinned against the real reference (torch.equal on trajectories, every loss term, the
+total loss and all parameter gradients) for the ten cases of ``oracle/cases.py`` -- see
+``tests/golden/PINNED.json`` written by ``oracle/pin_oracle.py``.  The reference's own test-suite
+holds no value-level golden vectors for this path, so the fixtures generated
+from the reference are the pin.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------ blocks
+def activation(name: str, param: float = 0.0) -> Callable[[torch.Tensor], torch.Tensor]:
+    """torch.nn activations of the reference registry (modules/activations.py:230-256)."""
+    table = {
+        "identity": lambda z: z,
+        "relu": F.relu,
+        "gelu": F.gelu,                                     # nn.GELU(): exact erf form
+        "leakyrelu": lambda z: F.leaky_relu(z, param if param else 0.01),
+        "tanh": torch.tanh,
+        "elu": lambda z: F.elu(z, param if param else 1.0),
+        "sigmoid": torch.sigmoid,
+        "softplus": F.softplus,
+    }
+    return table[name]
+
+
+def mlp_forward(params: Sequence[torch.Tensor], x: torch.Tensor, act: str, bias: bool = True,
+                act_param: float = 0.0) -> torch.Tensor:
+    """``MLP.block_eval`` (reference blocks.py:169-177): ``x <- nlin(lin(x))`` per layer, the last
+    nonlinearity is the identity.  ``params`` is the flat list W0, b0, W1, b1, ... (nn.Linear
+    layout ``[out, in]``; slim/linear.py:104-119 -> ``F.linear``)."""
+    fn = activation(act, act_param)
+    step = 2 if bias else 1
+    n_layers = len(params) // step
+    for l in range(n_layers):
+        w = params[step * l]
+        b = params[step * l + 1] if bias else None
+        x = F.linear(x, w, b)
+        if l < n_layers - 1:
+            x = fn(x)
+    return x
+
+
+def bounds_scaling(x, xmin, xmax, scaling=1.0):
+    """reference modules/functions.py:9-19"""
+    return (xmax - xmin) * torch.sigmoid(scaling * x) + xmin
+
+
+def bounds_clamp(x, xmin=None, xmax=None):
+    """reference modules/functions.py:22-34"""
+    if xmin is not None:
+        x = x + torch.relu(-x + xmin)
+    if xmax is not None:
+        x = x - torch.relu(x - xmax)
+    return x
+
+
+# ------------------------------------------------------------------------------------------ dynamics
+def rhs_twotank(x, u, c1, c2):
+    """``TwoTankParam.ode_equations`` (reference dynamics/ode.py:227-237)"""
+    h1 = torch.clip(x[:, [0]], min=0, max=1.0)
+    h2 = torch.clip(x[:, [1]], min=0, max=1.0)
+    pump = torch.clip(u[:, [0]], min=0, max=1.0)
+    valve = torch.clip(u[:, [1]], min=0, max=1.0)
+    dhdt1 = c1 * (1.0 - valve) * pump - c2 * torch.sqrt(h1)
+    dhdt2 = c1 * valve * pump + c2 * torch.sqrt(h1) - c2 * torch.sqrt(h2)
+    return torch.cat([dhdt1, dhdt2], dim=-1)
+
+
+def rhs_vdp(x, u, mu):
+    """``VanDerPolControl.ode_equations`` (reference dynamics/ode.py:363-368)"""
+    x1 = x[:, [0]]
+    x2 = x[:, [1]]
+    dx1 = x2
+    dx2 = mu * (1 - x1 ** 2) * x2 - x1 + u
+    return torch.cat([dx1, dx2], dim=-1)
+
+
+def rhs_cvdp(x, u, mu, kappa):
+    """Ring of coupled ``VanDerPolControl`` oscillators (benchmark config C5):
+    the reference equations per oscillator plus ``kappa*(x1[j+1] - x1[j])``."""
+    pos, vel = x[:, 0::2], x[:, 1::2]
+    nxt = torch.roll(pos, shifts=-1, dims=1)
+    acc = mu * (1 - pos ** 2) * vel - pos + u + kappa * (nxt - pos)
+    return torch.stack([vel, acc], dim=-1).reshape(x.shape[0], -1)
+
+
+def euler_step(f, x, h, *args):
+    """``Euler.integrate`` (reference dynamics/integrators.py:153-156)"""
+    k1 = f(x, *args)
+    return x + h * k1
+
+
+def rk2_step(f, x, h, *args):
+    """``RK2.integrate`` (reference dynamics/integrators.py:189-193)"""
+    k1 = f(x, *args)
+    k2 = f(x + h * k1 / 2.0, *args)
+    return x + h * k2
+
+
+def rk4_step(f, x, h, *args):
+    """``RK4.integrate`` (reference dynamics/integrators.py:205-211)"""
+    k1 = f(x, *args)
+    k2 = f(x + h * k1 / 2.0, *args)
+    k3 = f(x + h * k2 / 2.0, *args)
+    k4 = f(x + h * k3, *args)
+    return x + h * (k1 / 6.0 + k2 / 3.0 + k3 / 3.0 + k4 / 6.0)
+
+
+INTEGRATORS = {"euler": euler_step, "rk2": rk2_step, "rk4": rk4_step}
+
+
+def ssm_step(x, u, d, A, B, E=None):
+    """``SSM.forward`` with bias-free linear maps (reference dynamics/ode.py:33-51):
+    ``x = fx(x) + fu(u)`` then ``x += fd(d)``."""
+    out = F.linear(x, A) + F.linear(u, B)
+    if E is not None and d is not None:
+        out = out + F.linear(d, E)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ rollout
+def system_forward(nodes: List[dict], data: Dict[str, torch.Tensor], nsteps: int) -> Dict[str, torch.Tensor]:
+    """``System.forward`` (reference system.py:261-277) with ``Node.forward`` (:48-59) and
+    ``System.cat`` (:234-246): for every step and node, read index ``i`` of each input key, call the
+    node, append the outputs on the time axis.  ``nodes`` = ``[{fn, inputs, outputs}, ...]``."""
+    data = dict(data)
+    for i in range(nsteps):
+        for node in nodes:
+            args = [data[k][:, i] for k in node["inputs"]]
+            out = node["fn"](*args)
+            if not isinstance(out, tuple):
+                out = (out,)
+            for k, v in zip(node["outputs"], out):
+                if k not in data:
+                    data[k] = v[:, None, :]
+                else:
+                    data[k] = torch.cat([data[k], v[:, None, :]], dim=1)
+    return data
+
+
+# ------------------------------------------------------------------------------------------ loss
+def compare(cmp: str, norm: int, left: torch.Tensor, right: torch.Tensor):
+    """``LT/GT/Eq.forward`` (reference constraint.py:85-98, 122-134, 157-173) -> (loss, value, violation)"""
+    if cmp == "lt":
+        value = left - right
+        penalty = F.relu(value)
+        if norm == 2:
+            penalty = penalty ** 2
+        return torch.mean(penalty), value, penalty
+    if cmp == "gt":
+        value = right - left
+        penalty = F.relu(value)
+        if norm == 2:
+            penalty = penalty ** 2
+        return torch.mean(penalty), value, penalty
+    value = left - right
+    left_b, right_b = torch.broadcast_tensors(left, right)
+    if norm == 1:
+        return F.l1_loss(left_b, right_b), value, torch.abs(value)
+    return F.mse_loss(left_b, right_b), value, value ** 2
+
+
+def penalty_loss(terms: List[dict], data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """``PenaltyLoss.forward`` (reference loss.py:168-181) over ``Constraint.forward``
+    (constraint.py:307-324).  ``terms`` = ``[{name, objective, cmp, norm, weight, left, right}]`` with
+    ``left`` / ``right`` callables ``data -> tensor | float`` (the ``Variable`` expression).
+    Sums start from the python float 0.0 and run in list order: objectives, then constraints."""
+    out = {}
+    obj, pen = 0.0, 0.0
+    for t in [t for t in terms if t["objective"]] + [t for t in terms if not t["objective"]]:
+        left, right = t["left"](data), t["right"](data)
+        # Constraint.__init__ wraps python numbers with torch.tensor(.) (constraint.py:245-262); the
+        # fp64 attribution runs of the tests follow the dtype of the other side instead of float32
+        like = left if isinstance(left, torch.Tensor) else (right if isinstance(right, torch.Tensor) else None)
+        dt = like.dtype if like is not None else torch.float32
+        left = left if isinstance(left, torch.Tensor) else torch.tensor(left, dtype=dt)
+        right = right if isinstance(right, torch.Tensor) else torch.tensor(right, dtype=dt)
+        loss, value, violation = compare(t["cmp"], t["norm"], left, right)
+        out[t["name"]] = t["weight"] * loss
+        out[t["name"] + "_value"] = value
+        out[t["name"] + "_violation"] = violation
+        if t["objective"]:
+            obj = obj + out[t["name"]]
+        else:
+            pen = pen + out[t["name"]]
+    out["objective_loss"], out["penalty_loss"] = obj, pen
+    out["loss"] = obj + pen
+    return out
+
+
+def run_case(spec: dict, data: Dict[str, torch.Tensor], want_grad: bool = True) -> Dict[str, object]:
+    """Forward (+ backward) of one problem.  ``spec`` = {nodes, terms, nsteps, params (list of leaf
+    tensors), traj_keys}.  Returns trajectories, per-term scalars, loss and parameter gradients."""
+    traj = system_forward(spec["nodes"], data, spec["nsteps"])
+    scored = penalty_loss(spec["terms"], traj)
+    res = {"traj": {k: traj[k] for k in spec["traj_keys"]},
+           "terms": {t["name"]: scored[t["name"]] for t in spec["terms"]},
+           "objective_loss": scored["objective_loss"], "penalty_loss": scored["penalty_loss"],
+           "loss": scored["loss"]}
+    if want_grad:
+        leaves = [p for p in spec["params"] if p.requires_grad]
+        grads = torch.autograd.grad(scored["loss"], leaves, allow_unused=True)
+        res["grads"] = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, leaves)]
+    return res
