@@ -498,7 +498,12 @@ __global__ void __launch_bounds__(S::THREADS) nm_fwd_kernel(const __grid_constan
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       float u[NUA], y[NYA], d[NDA];
-      u[0] = 0.f; y[0] = 0.f; d[0] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NUA; ++j) u[j] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NYA; ++j) y[j] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NDA; ++j) d[j] = 0.f;
       if (owner) {
         if constexpr (S::HAS_OUTPUT) {                      // y_t = C x_t  (grid_response cell 7)
 #pragma unroll
@@ -686,9 +691,12 @@ __global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constan
 #pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
       float x[NX], u[NUA], y[NYA], o[NUA], gx[NX], gu[NUA], gy[NYA];
-      u[0] = 0.f; y[0] = 0.f; o[0] = 0.f; gu[0] = 0.f; gy[0] = 0.f;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) gx[i] = 0.f;
+      for (int j = 0; j < NUA; ++j) { u[j] = 0.f; o[j] = 0.f; gu[j] = 0.f; }
+#pragma unroll
+      for (int j = 0; j < NYA; ++j) { y[j] = 0.f; gy[j] = 0.f; }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { x[i] = 0.f; gx[i] = 0.f; }
       if (owner) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = __ldg(args.x_traj + (b * (T + 1) + t) * NX + i);

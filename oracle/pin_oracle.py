@@ -1,0 +1,361 @@
+"""
+TEST INFRASTRUCTURE -- pins the oracle against the UNMODIFIED reference and writes golden fixtures.
+
+Run in the build container (where ``/root/reference`` exists):
+
+    python -m oracle.pin_oracle            # asserts + writes tests/golden/*.npz, PINNED.json
+
+For every case it builds the problem with the reference's own classes (``neuromancer.system.System``,
+``blocks.MLP_bounds``, ``integrators.RK4``, ``ode.TwoTankParam``, ``constraint.variable``,
+``loss.PenaltyLoss``, ``problem.Problem`` -- loaded through ``ref_shim``), runs
+``problem(batch)`` and ``loss.backward()``, runs the oracle restatement on the same weights and
+inputs, and requires ``torch.equal`` on trajectories, every loss term, the total loss and every
+parameter gradient.  The reference outputs are then stored as the golden vectors the GPU parity
+tests compare against (the GPU box has no ``/root/reference``).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import cases as ocases  # noqa: E402
+from oracle import dpc_oracle, ref_shim  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _mlp_params(mlp):
+    out = []
+    for lin in mlp.linear:
+        inner = lin if isinstance(lin, nn.Linear) else lin.linear
+        out.append(inner.weight)
+        if inner.bias is not None:
+            out.append(inner.bias)
+    return out
+
+
+def _name(terms):
+    for t, n in terms:
+        t.name = n
+        t.update_name(n)       # deterministic output keys (constant Variables are keyed by id())
+
+
+# ---------------------------------------------------------------------------- reference builders
+def ref_c1(ns, nsteps=50):
+    A = torch.tensor([[1.2, 1.0], [0.0, 1.0]])
+    B = torch.tensor([[1.0], [0.5]])
+    mlp = ns.blocks.MLP(2, 1, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.ReLU, hsizes=[20, 20, 20, 20])
+    policy = ns.system.Node(mlp, ["X"], ["U"], name="policy")
+    xnext = lambda x, u: x @ A.T + u @ B.T
+    plant = ns.system.Node(xnext, ["X", "U"], ["X"], name="plant")
+    system = ns.system.System([policy, plant], nsteps=nsteps, name="cl")
+    u, x = ns.constraint.variable("U"), ns.constraint.variable("X")
+    a = 0.0001 * (u == 0.) ^ 2
+    r = 10. * (x == 0.) ^ 2
+    _name([(a, "action_loss"), (r, "regulation_loss")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([a, r], []))
+    data = lambda B_, g: {"X": 3. * torch.randn(B_, 1, 2, generator=g)}
+    return problem, _mlp_params(mlp), data, ["X", "U"], ["action_loss", "regulation_loss"]
+
+
+def ref_c2(ns, nsteps=30):
+    ode = ns.ode.TwoTankParam()
+    ode.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
+    ode.c2 = nn.Parameter(torch.tensor(0.04), requires_grad=False)
+    model = ns.system.Node(ns.integrators.RK4(ode, h=torch.tensor(1.0)), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=4, outsize=2, hsizes=[32, 32], nonlin=ns.activations.activations["gelu"], min=0, max=1.)
+    system = ns.system.System([ns.system.Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="cl")
+    x, ref = ns.constraint.variable("x"), ns.constraint.variable("r")
+    reg = 5. * ((x == ref) ^ 2)
+    lo, hi = 10. * (x > 0), 10. * (x < 1.)
+    tlo = 10. * (x[:, [-1], :] > ref - 0.01)
+    thi = 10. * (x[:, [-1], :] < ref + 0.01)
+    names = ["ref_tracking", "x_min", "x_max", "x_N_min", "x_N_max"]
+    _name(list(zip([reg, lo, hi, tlo, thi], names)))
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([reg], [lo, hi, tlo, thi]))
+
+    def data(B_, g):
+        x0 = torch.rand(B_, 1, 2, generator=g)
+        r = (torch.rand(B_, 1, 1, generator=g) * torch.ones(nsteps + 1, 2)).contiguous()
+        return {"x": x0, "r": r}
+    return problem, _mlp_params(net), data, ["x", "u"], names
+
+
+def ref_c3(ns, nsteps=100):
+    fx = ns.blocks.MLP(2, 2, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.ReLU, hsizes=[60, 60, 60])
+    model = ns.system.Node(ns.integrators.RK4(fx, h=0.1), ["xn"], ["xn"], name="NODE")
+    system = ns.system.System([model], name="system")
+    x = ns.constraint.variable("X")
+    xhat = ns.constraint.variable("xn")[:, :-1, :]
+    xfd = (x[:, 1:, :] - x[:, :-1, :])
+    xhfd = (xhat[:, 1:, :] - xhat[:, :-1, :])
+    fd = 2. * (xfd == xhfd) ^ 2
+    rl = (xhat == x) ^ 2
+    _name([(rl, "ref_loss"), (fd, "FD_loss")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([rl, fd], []))
+
+    def data(B_, g):
+        X = torch.randn(B_, nsteps, 2, generator=g)
+        return {"X": X, "xn": X[:, 0:1, :].contiguous()}
+    return problem, _mlp_params(fx), data, ["xn"], ["ref_loss", "FD_loss"]
+
+
+def ref_c4(ns, nsteps=96, horizon=48):
+    A, Bm, E, C = (torch.tensor(m) for m in (ocases.C4_A, ocases.C4_B, ocases.C4_E, ocases.C4_C))
+    xnext = lambda x, u, d: x @ A.T + u @ Bm.T + d @ E.T
+    ynext = lambda x: x @ C.T
+    state_model = ns.system.Node(xnext, ["x", "u", "d"], ["x"], name="SSM")
+    obs_model = ns.system.Node(ynext, ["x"], ["y"], name="y=Cx")
+    inputs = ["y"] + [v + "_lookahead" for v in ["d_obs", "ymin", "ymax", "price"]]
+    net = ns.blocks.MLP_bounds(insize=1 + 4 * horizon, outsize=1, hsizes=[32, 32], nonlin=torch.nn.LeakyReLU,
+                               min=torch.tensor([0.0]), max=torch.tensor([5000.0]))
+    policy = ns.system.Node(net, inputs, ["u"], name="policy")
+    system = ns.system.System([obs_model, policy, state_model], nsteps=nsteps, name="cl")
+    v = ns.constraint.variable
+    y_var, u_var = v("y"), v("u")
+    ymin_var = v("ymin_lookahead")[:, :-1, 0:1]
+    ymax_var = v("ymax_lookahead")[:, :-1, 0:1]
+    price_var = v("price_lookahead")[:, :-1, 0:1]
+    price_loss = 1 * ((u_var * price_var) == torch.zeros_like(u_var)) ^ 2
+    lo = 5e06 * (y_var > ymin_var)
+    hi = 5e06 * (y_var < ymax_var)
+    names = ["price_loss", "y_min", "y_max"]
+    _name(list(zip([price_loss, lo, hi], names)))
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([price_loss], [lo, hi]))
+
+    def lookahead(sig):
+        Bn, Tn, D = sig.shape
+        out = torch.zeros(Bn, Tn - horizon + 1, D * horizon)
+        for b in range(Bn):                                   # grid_response.ipynb cell 14, make_lookahead
+            for step in range(Tn - horizon + 1):
+                out[b, step, :] = sig[b, step:step + horizon, :].flatten()
+        return out
+
+    def data(B_, g):
+        Tn = nsteps + horizon
+        ymin = (18.0 + 4.5 * torch.rand(B_, 1, 1, generator=g)).repeat(1, Tn, 1)
+        ymax = (22.5 + 4.5 * torch.rand(B_, 1, 1, generator=g)).repeat(1, Tn, 1)
+        dist = torch.randn(B_, Tn, 3, generator=g)
+        dist[:, :, 0] = 5.0 + 8.0 * dist[:, :, 0]
+        price = 0.05 + 0.2 * torch.rand(B_, Tn, 1, generator=g)
+        x0 = 20.0 + torch.randn(B_, 1, 4, generator=g)
+        return {"x": x0, "d": dist[:, :nsteps, :].contiguous(), "d_obs_lookahead": lookahead(dist[:, :, 0:1]),
+                "ymin_lookahead": lookahead(ymin), "ymax_lookahead": lookahead(ymax),
+                "price_lookahead": lookahead(price)}
+    return problem, _mlp_params(net), data, ["x", "u", "y"], names
+
+
+def ref_c5(ns, nsteps=200):
+    class CoupledVdP(ns.ode.ODESystem):
+        """the synthetic 12-state plant of config C5 written against the reference's ODESystem ABC"""
+
+        def __init__(self, n_osc=6):
+            super().__init__(insize=3 * n_osc, outsize=2 * n_osc)
+            self.mu = nn.Parameter(torch.tensor([1.0]), requires_grad=False)
+            self.kappa = nn.Parameter(torch.tensor([0.1]), requires_grad=False)
+
+        def ode_equations(self, x, u):
+            pos, vel = x[:, 0::2], x[:, 1::2]
+            nxt = torch.roll(pos, shifts=-1, dims=1)
+            acc = self.mu * (1 - pos ** 2) * vel - pos + u + self.kappa * (nxt - pos)
+            return torch.stack([vel, acc], dim=-1).reshape(x.shape[0], -1)
+
+    model = ns.system.Node(ns.integrators.RK4(CoupledVdP(), h=torch.tensor(0.05)), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=24, outsize=6, hsizes=[128] * 4, nonlin=ns.activations.activations["gelu"],
+                               min=-5., max=5.)
+    system = ns.system.System([ns.system.Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="cl")
+    v = ns.constraint.variable
+    x, ref, u = v("x"), v("r"), v("u")
+    reg = 1. * ((x == ref) ^ 2)
+    eff = 0.01 * ((u == 0.) ^ 2)
+    lo, hi = 10. * (x > -4.), 10. * (x < 4.)
+    tlo = 10. * (x[:, [-1], :] > ref - 0.01)
+    thi = 10. * (x[:, [-1], :] < ref + 0.01)
+    names = ["state_loss", "action_loss", "x_min", "x_max", "x_N_min", "x_N_max"]
+    _name(list(zip([reg, eff, lo, hi, tlo, thi], names)))
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([reg, eff], [lo, hi, tlo, thi]))
+    data = lambda B_, g: {"x": torch.randn(B_, 1, 12, generator=g), "r": torch.zeros(B_, nsteps + 1, 12)}
+    return problem, _mlp_params(net), data, ["x", "u"], names
+
+
+def ref_t_vdp_rk4_tanh_clamp(ns, nsteps=12):
+    ode = ns.ode.VanDerPolControl()
+    ode.mu = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+    model = ns.system.Node(ns.integrators.RK4(ode, h=0.1), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=4, outsize=1, hsizes=[16, 16], nonlin=torch.nn.Tanh, min=-1., max=1., method="relu_clamp")
+    system = ns.system.System([ns.system.Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    x, r, u = v("x"), v("r"), v("u")
+    obj = 3. * ((x == r) ^ 2)
+    eff = 0.1 * (u == 0.)
+    box = 2. * ((x < 1.5) ^ 2)
+    du = 0.5 * ((u[:, 1:, :] - u[:, :-1, :]) == 0.) ^ 2
+    _name([(obj, "obj"), (eff, "eff"), (du, "du"), (box, "box")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj, eff, du], [box]))
+    data = lambda B_, g: {"x": torch.randn(B_, 1, 2, generator=g), "r": 0.5 * torch.randn(B_, nsteps + 1, 2, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u"], ["obj", "eff", "du", "box"]
+
+
+def ref_t_vdp_euler_elu(ns, nsteps=9):
+    ode = ns.ode.VanDerPolControl()
+    ode.mu = nn.Parameter(torch.tensor(0.7), requires_grad=False)
+    model = ns.system.Node(ns.integrators.Euler(ode, h=0.05), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP(insize=2, outsize=1, hsizes=[8], nonlin=torch.nn.ELU, bias=False)
+    system = ns.system.System([ns.system.Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    x, u = v("x"), v("u")
+    obj = (x == 0.) ^ 2
+    pen = 4. * (u > -0.2)
+    _name([(obj, "obj"), (pen, "pen")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], [pen]))
+    data = lambda B_, g: {"x": torch.randn(B_, 1, 2, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u"], ["obj", "pen"]
+
+
+def ref_t_twotank_rk2_sigmoid(ns, nsteps=7):
+    ode = ns.ode.TwoTankParam()
+    ode.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
+    ode.c2 = nn.Parameter(torch.tensor(0.04), requires_grad=False)
+    model = ns.system.Node(ns.integrators.RK2(ode, h=0.5), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=4, outsize=2, hsizes=[12], nonlin=torch.nn.Sigmoid, min=0., max=1.)
+    system = ns.system.System([ns.system.Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    x, r = v("x"), v("r")
+    obj = (x == r) ^ 2
+    _name([(obj, "obj")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], []))
+    data = lambda B_, g: {"x": 0.1 + 0.8 * torch.rand(B_, 1, 2, generator=g), "r": torch.rand(B_, nsteps + 1, 2, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u"], ["obj"]
+
+
+def ref_t_ssm_softplus(ns, nsteps=10):
+    A, Bm, E, C = ocases._ssm_softplus_mats(torch.zeros(1))
+    lin = lambda W: (lambda m: (m.weight.data.copy_(W), m.weight.requires_grad_(False), m)[-1])(nn.Linear(W.shape[1], W.shape[0], bias=False))
+    ssm = ns.ode.SSM(lin(A), lin(Bm), 3, 2, fd=lin(E), nd=2)
+    net = ns.blocks.MLP(insize=7, outsize=2, hsizes=[10, 10], nonlin=torch.nn.Softplus)
+    system = ns.system.System([ns.system.Node(lin(C), ["x"], ["y"], name="obs"),
+                               ns.system.Node(net, ["y", "d", "x"], ["u"], name="policy"),
+                               ns.system.Node(ssm, ["x", "u", "d"], ["x"], name="ssm")], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    x, u, y = v("x"), v("u"), v("y")
+    o1 = (y == 1.) ^ 2
+    o2 = 0.1 * ((u == 0.) ^ 2)
+    c1 = 5. * (x[:, 1:, 0:2] < 2.0)
+    _name([(o1, "o1"), (o2, "o2"), (c1, "c1")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([o1, o2], [c1]))
+    data = lambda B_, g: {"x": torch.randn(B_, 1, 3, generator=g), "d": torch.randn(B_, nsteps + 3, 2, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u", "y"], ["o1", "o2", "c1"]
+
+
+def ref_t_node_policy_euler(ns, nsteps=6):
+    rhs = ns.blocks.MLP(5, 3, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh, hsizes=[12, 12])
+    model = ns.system.Node(ns.integrators.RK2(rhs, h=0.2), ["x", "u"], ["x"], name="node")
+    net = ns.blocks.MLP(insize=3, outsize=2, hsizes=[8, 8], nonlin=torch.nn.ReLU)
+    system = ns.system.System([ns.system.Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    x, u = v("x"), v("u")
+    obj = (x == 0.5) ^ 2
+    eff = 0.2 * ((u == 0.) ^ 2)
+    _name([(obj, "obj"), (eff, "eff")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj, eff], []))
+    data = lambda B_, g: {"x": torch.randn(B_, 1, 3, generator=g)}
+    return problem, _mlp_params(net) + _mlp_params(rhs), data, ["x", "u"], ["obj", "eff"]
+
+
+REF_BUILDERS = {
+    "c1": (ref_c1, 16), "c2": (ref_c2, 16), "c3": (ref_c3, 12), "c4": (ref_c4, 6), "c5": (ref_c5, 6),
+    "t_vdp_rk4_tanh_clamp": (ref_t_vdp_rk4_tanh_clamp, 16), "t_vdp_euler_elu": (ref_t_vdp_euler_elu, 16),
+    "t_twotank_rk2_sigmoid": (ref_t_twotank_rk2_sigmoid, 16), "t_ssm_softplus": (ref_t_ssm_softplus, 16),
+    "t_node_policy_euler": (ref_t_node_policy_euler, 16),
+}
+
+
+def run_reference(problem, params, batch, traj_keys, term_names):
+    for p in params:
+        p.grad = None
+    out = problem({**batch, "name": "train"})
+    out["train_loss"].backward()
+    return {"traj": {k: out[f"train_{k}"].detach() for k in traj_keys},
+            "terms": {n: out[f"train_{n}"].detach() for n in term_names},
+            "objective_loss": torch.as_tensor(out["train_objective_loss"]).detach(),
+            "penalty_loss": torch.as_tensor(out["train_penalty_loss"]).detach(),
+            "loss": out["train_loss"].detach(),
+            "grads": [p.grad.detach().clone() for p in params]}
+
+
+def main() -> int:
+    ns = ref_shim.load()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    report = {"torch": torch.__version__, "reference": "pnnl/neuromancer 1.5.6 @ /root/reference", "cases": {}}
+    ok = True
+    for name, (builder, B) in REF_BUILDERS.items():
+        torch.manual_seed(1234)
+        problem, params, data_fn, traj_keys, term_names = builder(ns)
+        batch = data_fn(B, _gen(4321))
+        ref = run_reference(problem, params, batch, traj_keys, term_names)
+        plist = [p.detach().clone().requires_grad_(True) for p in params]
+        spec = ocases.build(name, plist)
+        ora = dpc_oracle.run_case(spec, batch)
+        checks = {}
+        for k in traj_keys:
+            checks[f"traj:{k}"] = torch.equal(ora["traj"][k], ref["traj"][k])
+        for n in term_names:
+            checks[f"term:{n}"] = torch.equal(ora["terms"][n], ref["terms"][n])
+        checks["loss"] = torch.equal(torch.as_tensor(ora["loss"]), ref["loss"])
+        for i, (g, r) in enumerate(zip(ora["grads"], ref["grads"])):
+            checks[f"grad:{i}"] = torch.equal(g, r)
+        bad = [k for k, v in checks.items() if not v]
+        worst = 0.0
+        for k in bad:                                            # report how far off a non-identical entry is
+            kind, key = k.split(":") if ":" in k else (k, "")
+            a, b = {"traj": lambda: (ora["traj"][key], ref["traj"][key]),
+                    "term": lambda: (ora["terms"][key], ref["terms"][key]),
+                    "loss": lambda: (torch.as_tensor(ora["loss"]), ref["loss"]),
+                    "grad": lambda: (ora["grads"][int(key)], ref["grads"][int(key)])}[kind]()
+            worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+        status = "bit-exact" if not bad else f"NOT bit-exact in {bad} (max rel {worst:.2e})"
+        print(f"{name:24s} B={B:3d} loss={float(ref['loss']):.6g}  oracle vs reference: {status}")
+        ok &= not bad
+        report["cases"][name] = {"batch": B, "bit_exact": not bad, "mismatch": bad, "max_rel": worst,
+                                 "loss": float(ref["loss"])}
+        arrays = {}
+        for i, p in enumerate(params):
+            arrays[f"param_{i}"] = p.detach().numpy()
+        for k, v in batch.items():
+            arrays[f"in_{k}"] = v.numpy()
+        for k, v in ref["traj"].items():
+            arrays[f"traj_{k}"] = v.numpy()
+        for n, v in ref["terms"].items():
+            arrays[f"term_{n}"] = v.numpy()
+        for k in ("objective_loss", "penalty_loss", "loss"):
+            arrays[k] = ref[k].numpy()
+        for i, g in enumerate(ref["grads"]):
+            arrays[f"grad_{i}"] = g.numpy()
+        arrays["term_names"] = np.array(term_names)
+        arrays["traj_keys"] = np.array(traj_keys)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **arrays)
+    report["all_bit_exact"] = ok
+    with open(os.path.join(GOLDEN_DIR, "PINNED.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print("oracle pinned bit-exactly to the reference" if ok else "ORACLE DIFFERS FROM THE REFERENCE")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,69 @@
+"""C-ABI library: loads without a GPU, exports every symbol include/nm_rollout.h declares, structure
+layouts match the ctypes mirror, shape-class signatures agree between C and Python.  No compute."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from neuromancer_b200 import _lib as L
+from neuromancer_b200 import build, configs
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "nm_rollout.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_functions_all_exported(nm_lib):
+    names = declared_functions()
+    assert "nm_rollout_forward" in names and "nm_rollout_backward" in names
+    for fn in names:
+        assert hasattr(nm_lib, fn), f"{fn} declared in nm_rollout.h but not exported"
+    assert set(L.EXPORTED_SYMBOLS) <= set(names)
+
+
+def test_abi_version_and_struct_sizes(nm_lib):
+    assert nm_lib.nm_abi_version() == L.NM_ABI_VERSION
+    sizes = (C.c_int * 7)()
+    assert nm_lib.nm_struct_sizes(sizes, 7) == 7
+    mirror = [C.sizeof(t) for t in (L.NmMlp, L.NmSegment, L.NmExo, L.NmAtom, L.NmSide, L.NmTerm, L.NmPlan)]
+    assert list(sizes) == mirror
+
+
+@pytest.mark.parametrize("name", configs.AOT_CASES)
+def test_aot_shape_classes_registered(nm_lib, name):
+    plan = configs.build_case(name).plan()
+    assert L.signature(plan.c) == build.signature_of(plan.c)
+    assert nm_lib.nm_has_kernel(C.byref(plan.c)) == 1
+    info = nm_lib.nm_kernel_info(C.byref(plan.c)).decode()
+    assert "tile=" in info and "threads=" in info
+    f, b = C.c_size_t(), C.c_size_t()
+    assert nm_lib.nm_rollout_workspace_bytes(C.byref(plan.c), 4096, C.byref(f), C.byref(b)) == L.NM_OK
+    assert f.value > 0 and b.value >= 4 * plan.c.n_params
+
+
+def test_bad_plans_are_rejected(nm_lib):
+    plan = configs.build_case("c2").plan()
+    p = L.NmPlan.from_buffer_copy(plan.c)
+    p.abi_version = 999
+    buf = C.create_string_buffer(512)
+    assert nm_lib.nm_plan_signature(C.byref(p), buf, 512) == L.NM_ERR_ABI
+    p = L.NmPlan.from_buffer_copy(plan.c)
+    p.terms[0].lhs.a.t_len = 7          # does not broadcast against the term's 31 steps
+    assert nm_lib.nm_plan_signature(C.byref(p), buf, 512) == L.NM_ERR_BAD_PLAN
+    assert b"broadcast" in nm_lib.nm_last_error()
+    p = L.NmPlan.from_buffer_copy(plan.c)
+    p.policy.sizes[1] = 33              # a shape class nobody compiled
+    assert nm_lib.nm_has_kernel(C.byref(p)) == 0
+    f, b = C.c_size_t(), C.c_size_t()
+    assert nm_lib.nm_rollout_workspace_bytes(C.byref(p), 16, C.byref(f), C.byref(b)) == L.NM_ERR_NO_KERNEL
+
+
+def test_null_arguments_fail_without_touching_the_device(nm_lib):
+    plan = configs.build_case("c1").plan()
+    rc = nm_lib.nm_rollout_forward(C.byref(plan.c), None, None, None, None, None, None, None, None, 0, 8, None)
+    assert rc == L.NM_ERR_BAD_PLAN
