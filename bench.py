@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""
+bench.py -- DPC train-step throughput of the fused rollout (forward + adjoint [+ gradient all-reduce]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--batch B] [--impl reference]
+
+Contract (see the task statement): rank 0 prints ONE JSON line.  A "step" is one pass of the hot path
+over one batch of synthetic input: nm_rollout_forward + nm_rollout_backward on device-resident
+buffers (`value`), timed with CUDA events, L2 flushed between timed steps, max over ranks.  `e2e` is the
+same metric through the public API (`Problem.forward` + `.backward()`) with the batch coming from pinned
+HOST memory and the loss read back every step.  `--impl reference` times the reference's CPU
+implementation of the path (the oracle port: the same torch ops the reference executes, pinned
+bit-exactly to it) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p_ in (ROOT, os.path.join(ROOT, "tests")):
+    if p_ not in sys.path:
+        sys.path.insert(0, p_)
+
+METRIC = "DPC train-step trajectory-steps/sec (fwd+bwd)"
+UNIT = "trajectory-steps/s"
+CPU_SAMPLE_BATCH = {"c1": 3333, "c2": 8192, "c3": 2048, "c4": 2048, "c5": 256}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_cpu_step(name, batch_cpu, params_cpu):
+    """One fwd+bwd of the reference's CPU path (oracle port) -- the thing `--impl reference` times."""
+    import helpers as H
+    res = H.oracle_run(name, params_cpu, batch_cpu)
+    return float(res["loss"])
+
+
+def time_cpu_reference(name, steps, warmup, nsteps, budget_s=25.0):
+    import torch
+    import helpers as H
+    torch.set_num_threads(os.cpu_count() or 1)
+    case = H.make_case(name, "cpu")
+    B = CPU_SAMPLE_BATCH.get(name, 1024)
+    batch = case.make_batch(B, "cpu", 0)
+    params = [p.detach().clone() for p in case.plan_params]
+    for _ in range(max(warmup, 1)):
+        oracle_cpu_step(name, batch, params)
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle_cpu_step(name, batch, params)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    per = sum(times) / len(times)
+    return {"value": B * nsteps / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{name} at batch {B} (full horizon {nsteps}), {len(times)} timed fwd+bwd passes of the "
+                      f"oracle port (same torch CPU ops as the reference, pinned bit-exact to it)",
+            "ms_per_step": per * 1e3, "batch": B, "steps_timed": len(times)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (default: the config's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    import helpers as H
+    case0 = H.configs.build_case(args.workload)
+    nsteps = case0.nsteps
+    cfg = {"workload": args.workload, "nsteps": nsteps, "batch_per_gpu": args.batch or case0.default_batch,
+           "global_batch": (args.batch or case0.default_batch) * max(world, 1), "parallelism": f"dp{world}",
+           "description": {"c1": "DPC double integrator, MLP 2-20-20-20-20-1 ReLU, linear SSM",
+                           "c2": "DPC reference tracking, TwoTank ODE + RK4, MLP_bounds 4-32-32-2 GELU",
+                           "c3": "neural-ODE system ID, RK4 over MLP RHS 2-60-60-60-2 ReLU",
+                           "c4": "building thermal DPC, linear SSM nx=4, 48-step preview, MLP_bounds 193-32-32-1",
+                           "c5": "parametric nonlinear DPC, 12-state coupled VdP + RK4, MLP 24-128x4-6 GELU"}.get(args.workload, args.workload)}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = time_cpu_reference(args.workload, max(args.steps, 1), args.warmup, nsteps)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": res["steps_timed"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {**cfg, "cpu_sample_batch": res["batch"]},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fused rollout has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from neuromancer_b200 import rollout as nr
+    from neuromancer_b200.distributed import GradientSync
+
+    B = cfg["batch_per_gpu"]
+    case = H.make_case(args.workload, dev)                    # same seed on every rank: replicated weights
+    batch_cpu = case.make_batch(B, "cpu", rank)               # per-rank shard of the sampled batch
+    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+    batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()}
+    sync = GradientSync() if world > 1 else None
+    plan = case.system.plan_for(case.system.init(dict(batch)), loss=case.problem.loss)
+    raw = nr.RawTrainStep(plan, batch, world_size=world)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_raw():
+        raw.forward()
+        raw.backward()
+        if sync is not None:
+            sync.allreduce_flat_(raw.gbuf)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_raw()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = raw.launches
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                          # evict the step's working set from L2
+        ev[i][0].record()
+        raw.forward()
+        ev[i][1].record()
+        raw.backward()
+        ev[i][2].record()
+        if sync is not None:
+            sync.allreduce_flat_(raw.gbuf)
+        ev[i][3].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms) / args.steps
+    launches = raw.launches - launches0
+    value = world * B * nsteps / (ms_per_step * 1e-3)
+    loss_val = float(raw.scalars[-1])
+    import ctypes
+    from neuromancer_b200 import _lib
+    kernel_info = _lib.load().nm_kernel_info(ctypes.byref(plan.c)).decode()
+
+    # ------------------------------------------------------------------ end-to-end through the public API
+    e2e = None
+    if not args.no_e2e:
+        params = [q for q in case.plan_params if q.requires_grad]
+        tensors = [k for k, v in pinned.items() if isinstance(v, torch.Tensor)]
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in tensors)
+
+        def step_api():
+            b = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()}
+            out = case.problem(b)
+            for q in params:
+                q.grad = None
+            out["train_loss"].backward()
+            if sync is not None:
+                sync.sync_gradients(params)
+            return float(out["train_loss"])                   # device -> host read of the step's loss
+        for _ in range(args.warmup):
+            step_api()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_api()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * nsteps * args.steps / float(dt), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": float(dt) / args.steps * 1e3,
+               "api": "Problem.forward + loss.backward, batch from pinned host memory, loss read back"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (adjoint)
+    peaks = read_peaks()
+    flop_step = case.flop_per_traj_step                        # fwd+bwd algorithmic FLOP per trajectory-step
+    bwd_flops = (2.0 / 3.0) * flop_step * B * nsteps          # the adjoint launch's share (2 of 3 passes)
+    fwd_flops = (1.0 / 3.0) * flop_step * B * nsteps
+    tf32x3_peak = peaks["bf16_tflops"] / 2.0 / 3.0             # fp32-accurate tensor-pipe peak (3xTF32 split)
+    achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
+    traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    traffic = json.load(open(traffic_path)).get("bwd_dram_bytes_per_launch") if os.path.exists(traffic_path) else None
+    roofline = {"bound": "tensor", "kernel": "nm_bwd_kernel", "achieved": achieved, "peak": tf32x3_peak,
+                "unit": "TFLOP/s", "frac": achieved / tf32x3_peak, "traffic": traffic,
+                "peak_source": f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 2 (tf32) / 3 (3xTF32 fp32-accurate split)",
+                "ffma_peak_tflops": 72.2, "ffma_frac": achieved / 72.2,
+                "ffma_peak_source": "measured, profiles/r01_pipe_rates_microbench.txt",
+                "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
+                "fwd_achieved_tflops": fwd_flops / (fwd_ms * 1e-3) / 1e12,
+                "hbm_gbs_achieved": case.bytes_per_traj_step * B * nsteps / ((fwd_ms + bwd_ms) * 1e-3) / 1e9,
+                "hbm_peak_gbs": peaks["hbm_gbs"]}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        res = time_cpu_reference(args.workload, 3, 1, nsteps)
+        cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**cfg, "l2": "flushed between timed steps (256 MiB memset)", "loss": loss_val,
+                       "kernel_info": kernel_info},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "wall_s_timed_region": t_wall}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -72,7 +72,7 @@ class NmPlan(C.Structure):
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "_C")
-LIB_PATH = os.path.join(LIB_DIR, "libnm_rollout.so")
+LIB_PATH = os.environ.get("NM_LIB_PATH") or os.path.join(LIB_DIR, "libnm_rollout.so")
 
 _lib = None
 
@@ -134,7 +134,7 @@ def load():
         raise NmError(f"libnm_rollout.so ABI {got} != python binding ABI {NM_ABI_VERSION}; rebuild")
     _lib = lib
     # specialisations built on demand for shapes outside the ahead-of-time registry
-    if os.path.isdir(LIB_DIR):
+    if os.path.isdir(LIB_DIR) and not os.environ.get("NM_LIB_PATH"):
         for fn in sorted(os.listdir(LIB_DIR)):
             if fn.startswith("nm_spec_") and fn.endswith(".so"):
                 lib.nm_load_plugin(os.path.join(LIB_DIR, fn).encode())

@@ -92,13 +92,32 @@ def _table(fn: str, vals: List[int]) -> str:
             f"return V[i]; }}\n")
 
 
-def spec_header(p: L.NmPlan) -> str:
+# Per-shape-class launch tuning (tile = trajectories per CTA, threads per CTA, __launch_bounds__ min
+# CTAs/SM for the forward / adjoint kernel), found by measurement on B200 -- see DESIGN.md.
+# NM_TUNE="tile=64,threads=128,minb_fwd=4,minb_bwd=4" overrides it for every class (experiments).
+TUNING: Dict[str, Dict[str, int]] = {}
+
+
+def parse_tune(text: str) -> Dict[str, int]:
+    return {k.strip(): int(v) for k, v in (kv.split("=") for kv in text.split(",") if kv.strip())}
+
+
+def tuning_for(sig: str) -> Dict[str, int]:
+    env = os.environ.get("NM_TUNE")
+    if env:
+        return parse_tune(env)
+    return dict(TUNING.get(sig, {}))
+
+
+def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
     sig = signature_of(p)
     name = spec_name(sig)
+    tune_map = tune_override if tune_override is not None else tuning_for(sig)
+    tune = "".join(f"#define NM_TUNE_{k.upper()} {v}\n" for k, v in sorted(tune_map.items()))
     nd = p.exo[p.dist_exo].width if p.dist_exo >= 0 else 0
     segs = [p.segs[i] for i in range(p.n_segs)] if p.has_policy else []
     integ = p.integrator if p.dyn_kind == L.NM_DYN_ODE else 0
-    out = [f"// generated by neuromancer_b200/build.py -- shape class\n// {sig}\n#pragma once\n",
+    out = [f"// generated by neuromancer_b200/build.py -- shape class\n// {sig}\n#pragma once\n", tune,
            f"#define NM_SPEC_NAME {name}\n", f"struct {name} {{\n",
            f"  static constexpr int NX = {p.nx}, NU = {p.nu}, NY = {p.ny}, ND = {nd};\n",
            _mlp_struct("Pol", p.policy, bool(p.has_policy)),
@@ -148,6 +167,26 @@ def compile_spec_object(header: str, force: bool = False, extra: List[str] = ())
         _run([nvcc_path(), *NVCC_FLAGS, *extra, f'-DNM_SPEC_HEADER="{header}"', "-c",
               os.path.join(CSRC, "nm_spec_tu.cu"), "-o", obj])
     return obj
+
+
+def build_variant(case_name: str, tune: str, out: str) -> str:
+    """Experiment helper: a library holding ONE shape class built with the tuning string ``tune``
+    (same syntax as NM_TUNE), written to ``out``.  bench.py picks it up through NM_LIB_PATH."""
+    from . import configs
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    p = configs.build_case(case_name).plan().c
+    text = spec_header(p, tune_override=parse_tune(tune))
+    tag = hashlib.sha1((case_name + tune).encode()).hexdigest()[:10]
+    vdir = os.path.join(OUT_DIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    header = os.path.join(vdir, f"{spec_name(signature_of(p))}_{tag}.h")
+    with open(header, "w") as f:
+        f.write(text)
+    obj = os.path.join(vdir, f"{tag}.o")
+    _run([nvcc_path(), *NVCC_FLAGS, f'-DNM_SPEC_HEADER="{header}"', "-c", os.path.join(CSRC, "nm_spec_tu.cu"), "-o", obj])
+    api_obj = os.path.join(OBJ_DIR, "nm_api.o")
+    _run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, api_obj, obj, "-lcudart", "-ldl"])
+    return out
 
 
 def build_library(plans: List[L.NmPlan], force: bool = False, verbose: bool = True) -> str:

@@ -7,6 +7,7 @@
 #include <string>
 #include <cuda_runtime.h>
 #include "nm_registry.h"
+#include "nm_terms.cuh"
 
 namespace {
 
@@ -91,20 +92,128 @@ std::string make_signature(const NmPlan* p) {
   return s;
 }
 
-__global__ void nm_loss_finalize_kernel(const __grid_constant__ NmPlan plan, const double* __restrict__ partials, int grid,
-                                        int64_t B, float* __restrict__ scalars) {
+
+constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+constexpr int kScoreThreads = 256;
+constexpr int kScoreMaxBlocks = 148 * 8;
+constexpr size_t kGbufMaxBytes = size_t(6) << 30;     // precompute term gradients only below 6 GiB
+
+nm::VarTable make_vartable(const NmPlan* p, const float* x, const float* u, const float* y, const float* const* exo) {
+  nm::VarTable vt{};
+  vt.base[NM_VAR_X] = x; vt.T[NM_VAR_X] = p->nsteps + 1; vt.D[NM_VAR_X] = p->nx;
+  vt.base[NM_VAR_U] = u; vt.T[NM_VAR_U] = p->nsteps; vt.D[NM_VAR_U] = p->nu;
+  vt.base[NM_VAR_Y] = y; vt.T[NM_VAR_Y] = p->nsteps; vt.D[NM_VAR_Y] = p->ny;
+  for (int e = 0; e < NM_MAX_EXO; ++e) {
+    vt.base[NM_VAR_EXO0 + e] = (e < p->n_exo && exo) ? exo[e] : nullptr;
+    vt.T[NM_VAR_EXO0 + e] = e < p->n_exo ? p->exo[e].steps : 0;
+    vt.D[NM_VAR_EXO0 + e] = e < p->n_exo ? p->exo[e].width : 0;
+  }
+  return vt;
+}
+
+int max_term_steps(const NmPlan* p) {
+  int m = 1;
+  for (int k = 0; k < p->n_terms; ++k) m = p->terms[k].t_len > m ? p->terms[k].t_len : m;
+  return m;
+}
+int score_grid(const NmPlan* p, int64_t B) {
+  const int64_t n = B * max_term_steps(p);
+  int64_t g = (n + kScoreThreads - 1) / kScoreThreads;
+  if (g > kScoreMaxBlocks) g = kScoreMaxBlocks;
+  return g < 1 ? 1 : int(g);
+}
+size_t gbuf_floats(const NmPlan* p, int64_t B) {
+  return size_t(B) * (size_t(p->nsteps + 1) * p->nx + size_t(p->nsteps) * (p->nu + p->ny));
+}
+bool use_gbuf(const NmPlan* p, int64_t B) {
+  return p->n_terms > 0 && gbuf_floats(p, B) * sizeof(float) <= kGbufMaxBytes;
+}
+
+// PenaltyLoss scoring: one thread per (trajectory, time) pair; terms are processed one after another
+// (small code, few registers; the re-read of the pair's entries hits L1), block partial sums in double
+__global__ void __launch_bounds__(kScoreThreads) nm_term_score_kernel(const __grid_constant__ NmPlan plan,
+                                                                      const __grid_constant__ nm::VarTable vt,
+                                                                      int64_t B, int tmax, double* __restrict__ partials) {
+  __shared__ double red[kScoreThreads / 32];
+  const int64_t n = B * tmax;
+#pragma unroll 1
+  for (int k = 0; k < plan.n_terms; ++k) {
+    const NmTerm& tm = plan.terms[k];
+    float ts = 0.f;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
+      const int64_t b = idx / tmax;
+      const int te = int(idx - b * tmax);
+      if (te < tm.t_len) {
+        const nm::TermRef r = nm::term_ref(tm, vt, b, te);
+        for (int de = 0; de < tm.d_len; ++de) ts += nm::term_penalty(tm, nm::term_value_ref(tm, r, de));
+      }
+    }
+    double v = static_cast<double>(ts);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < kScoreThreads / 32; ++w) s += red[w];
+      partials[size_t(blockIdx.x) * NM_MAX_TERMS + k] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// Gradient of the scored scalar w.r.t. every trajectory entry: one thread per entry.  Output is one
+// row per trajectory,  G[b] = [ x(T+1, nx) | u(T, nu) | y(T, ny) ],  which the adjoint kernel reads.
+struct TermGradArgs {
+  const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
+  float* G; int64_t B; int64_t b_total;
+};
+__global__ void __launch_bounds__(kScoreThreads) nm_term_grad_kernel(const __grid_constant__ NmPlan plan,
+                                                                     const __grid_constant__ nm::VarTable vt,
+                                                                     const __grid_constant__ TermGradArgs a) {
+  __shared__ float coef[NM_MAX_TERMS];
+  if (threadIdx.x < NM_MAX_TERMS)
+    coef[threadIdx.x] = threadIdx.x < plan.n_terms ? nm::term_coef(plan, threadIdx.x, a.grad_scalars, a.b_total) : 0.f;
+  __syncthreads();
+  const int T = plan.nsteps, nx = plan.nx, nu = plan.nu, ny = plan.ny;
+  const int nxr = (T + 1) * nx, nur = T * nu, row = nxr + nur + T * ny;
+  const int64_t n = a.B * row;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / row;
+    int r = int(idx - b * row);
+    int var, dim;
+    const float* ext;
+    if (r < nxr) { var = NM_VAR_X; dim = nx; ext = a.gx_ext ? a.gx_ext + b * nxr : nullptr; }
+    else if (r < nxr + nur) { r -= nxr; var = NM_VAR_U; dim = nu; ext = a.gu_ext ? a.gu_ext + b * nur : nullptr; }
+    else { r -= nxr + nur; var = NM_VAR_Y; dim = ny; ext = a.gy_ext ? a.gy_ext + b * int64_t(T) * ny : nullptr; }
+    const int t = r / dim, d = r - t * dim;
+    float g = nm::term_grad_entry<1>(plan, vt, coef, b, var, t, d);   // time-broadcast atoms: adjoint kernel
+    if (ext) g += ext[r];
+    a.G[idx] = g;
+  }
+}
+
+__global__ void __launch_bounds__(256) nm_loss_finalize_kernel(const __grid_constant__ NmPlan plan, const double* __restrict__ partials,
+                                                               int grid, int64_t B, float* __restrict__ scalars) {
+  // thread (k, j): fixed-order strided sum over the scoring blocks, then a fixed-order tree -> deterministic
+  __shared__ double part[NM_MAX_TERMS][16];
   __shared__ float term[NM_MAX_TERMS];
-  const int k = threadIdx.x;
-  if (k < plan.n_terms) {
-    double s = 0.0;
-    for (int c = 0; c < grid; ++c) s += partials[size_t(c) * NM_MAX_TERMS + k];
-    const NmTerm& t = plan.terms[k];
-    const float mean = static_cast<float>(s / (static_cast<double>(B) * t.t_len * t.d_len));
-    term[k] = t.weight * mean;                      // Constraint.forward: weight * loss
-    scalars[k] = term[k];
+  const int k = threadIdx.x / 16, j = threadIdx.x % 16;
+  double s = 0.0;
+  if (k < plan.n_terms)
+    for (int c = j; c < grid; c += 16) s += partials[size_t(c) * NM_MAX_TERMS + k];
+  part[k][j] = s;
+  __syncthreads();
+  if (threadIdx.x < plan.n_terms) {
+    double v = 0.0;
+    for (int q = 0; q < 16; ++q) v += part[threadIdx.x][q];
+    const NmTerm& t = plan.terms[threadIdx.x];
+    const float mean = static_cast<float>(v / (static_cast<double>(B) * t.t_len * t.d_len));
+    term[threadIdx.x] = t.weight * mean;            // Constraint.forward: weight * loss
+    scalars[threadIdx.x] = term[threadIdx.x];
   }
   __syncthreads();
-  if (k == 0) {                                      // loss.py:61-108: python-float 0.0 start, list order
+  if (threadIdx.x == 0) {                            // loss.py:61-108: python-float 0.0 start, list order
     float obj = 0.f, pen = 0.f;
     for (int i = 0; i < plan.n_terms; ++i) { if (plan.terms[i].is_objective) obj += term[i]; }
     for (int i = 0; i < plan.n_terms; ++i) { if (!plan.terms[i].is_objective) pen += term[i]; }
@@ -114,12 +223,22 @@ __global__ void nm_loss_finalize_kernel(const __grid_constant__ NmPlan plan, con
   }
 }
 
-__global__ void nm_grad_finalize_kernel(const float* __restrict__ partials, int grid, int64_t n, float* __restrict__ out) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// grad[i] = sum over CTAs of partials[c][i]: 32 parameters x 8 CTA-lanes per block, fixed order
+__global__ void __launch_bounds__(256) nm_grad_finalize_kernel(const float* __restrict__ partials, int grid, int64_t n, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int px = threadIdx.x % 32, cy = threadIdx.x / 32;
+  const int64_t i = int64_t(blockIdx.x) * 32 + px;
   float s = 0.f;
-  for (int c = 0; c < grid; ++c) s += partials[size_t(c) * size_t(n) + i];   // fixed order: deterministic
-  out[i] = s;
+  if (i < n)
+    for (int c = cy; c < grid; c += 8) s += partials[size_t(c) * size_t(n) + i];
+  part[cy][px] = s;
+  __syncthreads();
+  if (cy == 0 && i < n) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][px];
+    out[i] = v;
+  }
 }
 
 }  // namespace
@@ -190,7 +309,12 @@ int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes,
   if (B < 1 || !fwd_bytes || !bwd_bytes) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
   NmKernelEntry* e = find_entry(make_signature(plan).c_str());
   if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
-  return e->workspace(plan, B, fwd_bytes, bwd_bytes);
+  rc = e->workspace(plan, B, fwd_bytes, bwd_bytes);
+  if (rc != NM_OK) return rc;
+  // API-owned tail: block partials of the scoring kernel / precomputed term gradients
+  *fwd_bytes = align256(*fwd_bytes) + align256(size_t(score_grid(plan, B)) * NM_MAX_TERMS * sizeof(double));
+  *bwd_bytes = align256(*bwd_bytes) + (use_gbuf(plan, B) ? align256(gbuf_floats(plan, B) * sizeof(float)) : 0);
+  return NM_OK;
 }
 
 int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0, const float* const* exo,
@@ -203,15 +327,26 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
       (plan->n_params > 0 && !params)) { nm_set_error("null pointer argument"); return NM_ERR_BAD_PLAN; }
   NmKernelEntry* e = find_entry(make_signature(plan).c_str());
   if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  size_t spec_f = 0, spec_b = 0;
+  rc = e->workspace(plan, B, &spec_f, &spec_b);
+  if (rc != NM_OK) return rc;
+  const int sgrid = score_grid(plan, B);
+  const size_t need = align256(spec_f) + align256(size_t(sgrid) * NM_MAX_TERMS * sizeof(double));
+  if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) { nm_set_error("forward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
   NmFwdCall c{};
   c.params = params; c.x0 = x0; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
-  c.workspace = workspace; c.workspace_bytes = workspace_bytes; c.B = B; c.stream = static_cast<cudaStream_t>(stream);
+  c.workspace = workspace; c.workspace_bytes = align256(spec_f); c.B = B; c.stream = static_cast<cudaStream_t>(stream);
   rc = e->forward(plan, &c);
   if (rc != NM_OK) return rc;
-  nm_loss_finalize_kernel<<<1, 32, 0, c.stream>>>(*plan, c.term_partials, c.grid, B, scalars);
+  double* partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + align256(spec_f));
+  if (plan->n_terms > 0) {
+    const nm::VarTable vt = make_vartable(plan, x_traj, u_traj, y_traj, exo);
+    nm_term_score_kernel<<<sgrid, kScoreThreads, 0, c.stream>>>(*plan, vt, B, max_term_steps(plan), partials);
+  }
+  nm_loss_finalize_kernel<<<1, 256, 0, c.stream>>>(*plan, partials, sgrid, B, scalars);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
-  g_launches = 3;                                   // weight prep + rollout + loss finalise
+  g_launches = plan->n_terms > 0 ? 4 : 3;           // weight prep + rollout + term scoring + loss finalise
   return NM_OK;
 }
 
@@ -226,21 +361,39 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
       (plan->n_params > 0 && (!params || !grad_params))) { nm_set_error("null pointer / bad size argument"); return NM_ERR_BAD_PLAN; }
   NmKernelEntry* e = find_entry(make_signature(plan).c_str());
   if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  size_t spec_f = 0, spec_b = 0;
+  rc = e->workspace(plan, B, &spec_f, &spec_b);
+  if (rc != NM_OK) return rc;
+  const bool pre = use_gbuf(plan, B);
+  const size_t need = align256(spec_b) + (pre ? align256(gbuf_floats(plan, B) * sizeof(float)) : 0);
+  if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) { nm_set_error("backward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
   NmBwdCall c{};
   c.params = params; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
   c.grad_scalars = grad_scalars; c.gx_ext = grad_x_ext; c.gu_ext = grad_u_ext; c.gy_ext = grad_y_ext;
-  c.grad_x0 = grad_x0; c.workspace = workspace; c.workspace_bytes = workspace_bytes; c.B = B; c.b_total = b_total;
+  c.grad_x0 = grad_x0; c.workspace = workspace; c.workspace_bytes = align256(spec_b); c.B = B; c.b_total = b_total;
   c.stream = static_cast<cudaStream_t>(stream);
+  int extra = 0;
+  if (pre) {
+    float* G = reinterpret_cast<float*>(static_cast<char*>(workspace) + align256(spec_b));
+    TermGradArgs ta{};
+    ta.grad_scalars = grad_scalars; ta.gx_ext = grad_x_ext; ta.gu_ext = grad_u_ext; ta.gy_ext = grad_y_ext;
+    ta.G = G; ta.B = B; ta.b_total = b_total;
+    const nm::VarTable vt = make_vartable(plan, x_traj, u_traj, y_traj, exo);
+    int64_t g = (int64_t(gbuf_floats(plan, B)) + kScoreThreads - 1) / kScoreThreads;
+    if (g > 148 * 16) g = 148 * 16;
+    nm_term_grad_kernel<<<int(g), kScoreThreads, 0, c.stream>>>(*plan, vt, ta);
+    c.G_x = G; c.G_u = nullptr; c.G_y = nullptr;     // row layout, see nm_term_grad_kernel
+    extra = 1;
+  }
   rc = e->backward(plan, &c);
   if (rc != NM_OK) return rc;
-  g_launches = 2;
+  g_launches = 2 + extra;
   if (plan->n_params > 0) {
-    const int threads = 256;
-    const int blocks = int((plan->n_params + threads - 1) / threads);
-    nm_grad_finalize_kernel<<<blocks, threads, 0, c.stream>>>(c.grad_partials, c.grid, plan->n_params, grad_params);
+    const int blocks = int((plan->n_params + 31) / 32);
+    nm_grad_finalize_kernel<<<blocks, 256, 0, c.stream>>>(c.grad_partials, c.grid, plan->n_params, grad_params);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
-    g_launches = 3;                                 // weight prep + adjoint + gradient finalise
+    g_launches = 3 + extra;                         // weight prep [+ term gradients] + adjoint + gradient finalise
   }
   return NM_OK;
 }

@@ -44,11 +44,43 @@ constexpr int round_up(int a, int b) { return cdiv(a, b) * b; }
 
 // ------------------------------------------------------------------------------------------------
 // activations: torch.nn semantics incl. the subgradient conventions autograd uses
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Standard normal CDF Phi(z) = 0.5*erfc(-z/sqrt(2)) and exp(-z^2/2), branch-free.
+//   erfc(t) = 2^(-t*Q(t)) on [0, 4.2] (degree-9 minimax fit of the exponent, tools/fit_erfc.py: fit error
+//   1.3e-8, fp32 evaluation error ~7e-8 = 1 ulp of 1.0; erfc(4.2) < 3e-9 so larger arguments are clamped).
+//   The exponent form is used because a rounding error d in the exponent costs only erfc(t)*d absolute.
+//   torch's exact-erf GELU (nn.GELU()) is reproduced to ~1e-7 absolute, far inside the 1e-5 budget;
+//   CUDA's erff costs ~4x the instructions (two code paths, both executed by a diverged warp).
+__device__ __forceinline__ void normal_cdf_pdf(float z, float& cdf, float& gauss) {
+  const float x = z * 0.70710678118654752440f;
+  const float t = fminf(fabsf(x), 4.2f);
+  float q = -1.476634237e-05f;
+  q = fmaf(q, t, 1.797868946e-04f);
+  q = fmaf(q, t, -9.401043775e-04f);
+  q = fmaf(q, t, 2.438597105e-03f);
+  q = fmaf(q, t, -2.483013238e-04f);
+  q = fmaf(q, t, -2.763307886e-02f);
+  q = fmaf(q, t, 1.482808647e-01f);
+  q = fmaf(q, t, 9.184465932e-01f);
+  q = fmaf(q, t, 1.627907100e+00f);
+  const float half_erfc = 0.5f * ex2_approx(-(q * t));            // 0.5*erfc(|x|)
+  cdf = 0.5f + copysignf(0.5f - half_erfc, x);
+  gauss = ex2_approx(z * z * -0.72134752044448170368f);           // exp(-z^2/2)
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float z, float prm) {
   if constexpr (ACT == NM_ACT_IDENTITY) return z;
   else if constexpr (ACT == NM_ACT_RELU) return z > 0.f ? z : 0.f;
-  else if constexpr (ACT == NM_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
+  else if constexpr (ACT == NM_ACT_GELU) {
+    float cdf, g;
+    normal_cdf_pdf(z, cdf, g);
+    return z * cdf;
+  }
   else if constexpr (ACT == NM_ACT_LEAKY) return z > 0.f ? z : z * prm;
   else if constexpr (ACT == NM_ACT_TANH) return tanhf(z);
   else if constexpr (ACT == NM_ACT_ELU) return z > 0.f ? z : prm * expm1f(z);
@@ -59,16 +91,23 @@ __device__ __forceinline__ float act_fwd(float z, float prm) {
 // activations whose derivative cannot be recovered from the output keep a derivative buffer
 template <int ACT> constexpr bool act_needs_dbuf() { return ACT == NM_ACT_GELU || ACT == NM_ACT_SOFTPLUS; }
 
+// activation and its derivative from the pre-activation in one go (shares the transcendental work)
 template <int ACT>
-__device__ __forceinline__ float act_deriv_z(float z, float prm) {   // derivative from the pre-activation
+__device__ __forceinline__ void act_pair_z(float z, float prm, float& a, float& d) {
   if constexpr (ACT == NM_ACT_GELU) {
-    const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
-    return cdf + z * pdf;
+    float cdf, g;
+    normal_cdf_pdf(z, cdf, g);
+    a = z * cdf;
+    d = fmaf(z * 0.39894228040143267794f, g, cdf);
   } else if constexpr (ACT == NM_ACT_SOFTPLUS) {
-    return z > 20.f ? 1.f : 1.f / (1.f + expf(-z));
-  } else return 1.f;
+    a = z > 20.f ? z : log1pf(expf(z));
+    d = z > 20.f ? 1.f : 1.f / (1.f + expf(-z));
+  } else {
+    a = act_fwd<ACT>(z, prm);
+    d = 1.f;
+  }
 }
+
 template <int ACT>
 __device__ __forceinline__ float act_deriv_a(float a, float prm) {   // derivative from the output a = act(z)
   if constexpr (ACT == NM_ACT_IDENTITY) return 1.f;

@@ -109,7 +109,6 @@ struct FwdArgs {
   const float* params; const float* wprep; const float* x0;
   const float* exo[NM_MAX_EXO];
   float* x_traj; float* u_traj; float* y_traj;
-  double* term_partials;            // [grid][NM_MAX_TERMS]
   int64_t B; int num_tiles;
 };
 struct BwdArgs {
@@ -117,6 +116,9 @@ struct BwdArgs {
   const float* exo[NM_MAX_EXO];
   const float* x_traj; const float* u_traj; const float* y_traj;
   const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
+  // loss-term gradients precomputed by nm_term_grad_kernel (already include the *_ext gradients);
+  // when null they are evaluated inline in the sweep
+  const float* G_x; const float* G_u; const float* G_y;
   float* grad_partials;             // [grid][n_params]
   float* grad_x0;
   int64_t B; int64_t b_total; int num_tiles;
@@ -193,11 +195,12 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ W, float* 
             if constexpr (KEEP && MC::DBUF) {
               float dv[G::TMB];
 #pragma unroll
-              for (int i = 0; i < G::TMB; ++i) dv[i] = act_deriv_z<M::ACT>(v[i], act_prm);
+              for (int i = 0; i < G::TMB; ++i) act_pair_z<M::ACT>(v[i], act_prm, v[i], dv[i]);
               st_vec<G::TMB>(keep + MC::d_off(l + 1) + n * LD + traj0, dv);
-            }
+            } else {
 #pragma unroll
-            for (int i = 0; i < G::TMB; ++i) v[i] = act_fwd<M::ACT>(v[i], act_prm);
+              for (int i = 0; i < G::TMB; ++i) v[i] = act_fwd<M::ACT>(v[i], act_prm);
+            }
           }
           st_vec<G::TMB>(out + n * LD + traj0, v);
         }
@@ -437,7 +440,7 @@ __device__ __forceinline__ void stage_weights(float* __restrict__ dst_a, const f
 // ================================================================================================
 // forward kernel
 template <class S>
-__global__ void __launch_bounds__(S::THREADS) nm_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
+__global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
   using KC = KCfg<S>;
   using PolCfg = typename KC::PolCfg;
   using RhsCfg = typename KC::RhsCfg;
@@ -448,7 +451,6 @@ __global__ void __launch_bounds__(S::THREADS) nm_fwd_kernel(const __grid_constan
   float* pp0 = sm_w + (KC::W_SMEM ? KC::W_FLOATS_FWD : 0);
   float* pp1 = pp0 + KC::FWD_PP0;
   uint64_t* bar = reinterpret_cast<uint64_t*>(pp1 + KC::FWD_PP1);
-  VarTable& vt = *reinterpret_cast<VarTable*>(pp1 + KC::FWD_PP1 + 16);
   const int tid = threadIdx.x;
   const NmPlan& p = plan;
 
@@ -464,20 +466,6 @@ __global__ void __launch_bounds__(S::THREADS) nm_fwd_kernel(const __grid_constan
     Wpol = args.wprep + KC::POL_W_OFF;
     Wrhs = args.wprep + KC::RHS_W_OFF;
   }
-
-  if (tid == 0) {
-    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = p.nsteps + 1; vt.D[NM_VAR_X] = NX;
-    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = p.nsteps; vt.D[NM_VAR_U] = NU;
-    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = p.nsteps; vt.D[NM_VAR_Y] = NY;
-    for (int e = 0; e < NM_MAX_EXO; ++e) {
-      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
-    }
-  }
-  __syncthreads();
-
-  float tsum[NM_MAX_TERMS];
-#pragma unroll
-  for (int k = 0; k < NM_MAX_TERMS; ++k) tsum[k] = 0.f;
 
   const int T = p.nsteps;
   for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
@@ -575,39 +563,16 @@ __global__ void __launch_bounds__(S::THREADS) nm_fwd_kernel(const __grid_constan
         }
       }
     }
-    // PenaltyLoss scoring of this thread's trajectory (its entries were stored by this same thread)
-    if (valid) {
-#pragma unroll
-      for (int k = 0; k < NM_MAX_TERMS; ++k)
-        if (k < p.n_terms) tsum[k] += term_sum_traj(p.terms[k], vt, b);
-    }
   }
 
-  // block reduction of the term sums (double) -> per-CTA partials
-  __syncthreads();
-  double* scratch = reinterpret_cast<double*>(pp0);           // activations are dead now
-#pragma unroll
-  for (int k = 0; k < NM_MAX_TERMS; ++k) {
-    if (k < p.n_terms) {
-      double v = static_cast<double>(tsum[k]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((tid & 31) == 0) scratch[k * (THREADS / 32) + (tid >> 5)] = v;
-    }
-  }
-  __syncthreads();
-  if (tid < p.n_terms) {
-    double v = 0.0;
-    for (int w = 0; w < THREADS / 32; ++w) v += scratch[tid * (THREADS / 32) + w];
-    args.term_partials[size_t(blockIdx.x) * NM_MAX_TERMS + tid] = v;
-  }
+  // (PenaltyLoss scoring runs in nm_term_score_kernel over all (trajectory, time) pairs in parallel)
   (void)Wrhs; (void)Wpol;
 }
 
 // ================================================================================================
 // adjoint kernel
 template <class S>
-__global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
+__global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
   using KC = KCfg<S>;
   using PolCfg = typename KC::PolCfg;
   using RhsCfg = typename KC::RhsCfg;
@@ -626,6 +591,19 @@ __global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constan
   const int tid = threadIdx.x;
   const NmPlan& p = plan;
   const int T = p.nsteps;
+  const bool pre = args.G_x != nullptr;
+  // row layout of the precomputed term gradients: G[b] = [ x(T+1, NX) | u(T, NU) | y(T, NY) ]
+  const int g_row = (T + 1) * NX + T * (NU + NY), g_uoff = (T + 1) * NX, g_yoff = g_uoff + T * NU;
+  // which of x / u / y carry time-broadcast atoms (those are not in G, see nm_terms.cuh)
+  int tb_mask = 0;
+  for (int k = 0; k < p.n_terms; ++k) {
+    const NmTerm& tm = p.terms[k];
+    const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
+    const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (live[i] && at[i]->var >= 0 && at[i]->var <= NM_VAR_Y && atom_is_tbcast(*at[i], tm)) tb_mask |= 1 << at[i]->var;
+  }
 
   const float* Wpol;
   const float* Wrhs;
@@ -639,17 +617,7 @@ __global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constan
   }
 
   // effective upstream gradient of every fused term: d(term) + d(objective|penalty) + d(loss)
-  if (tid < NM_MAX_TERMS) {
-    float c = 0.f;
-    if (tid < p.n_terms) {
-      const NmTerm& tm = p.terms[tid];
-      float up = 1.f;
-      if (args.grad_scalars != nullptr)
-        up = args.grad_scalars[tid] + args.grad_scalars[p.n_terms + (tm.is_objective ? 0 : 1)] + args.grad_scalars[p.n_terms + 2];
-      c = up * tm.weight / (static_cast<float>(args.b_total) * static_cast<float>(tm.t_len) * static_cast<float>(tm.d_len));
-    }
-    coef[tid] = c;
-  }
+  if (tid < NM_MAX_TERMS) coef[tid] = tid < p.n_terms ? term_coef(p, tid, args.grad_scalars, args.b_total) : 0.f;
   // this CTA's private gradient block (summed over CTAs by nm_grad_finalize_kernel)
   float* gblock = args.grad_partials + size_t(blockIdx.x) * size_t(p.n_params > 0 ? p.n_params : 1);
   for (int i = tid; i < p.n_params; i += THREADS) gblock[i] = 0.f;
@@ -682,10 +650,16 @@ __global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constan
 #pragma unroll
     for (int i = 0; i < NX; ++i) lam[i] = 0.f;
     if (valid) {
-      term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
-      if (args.gx_ext != nullptr) {
+      if (pre) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
+        for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
+        if (tb_mask & 1) term_grad_accum<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+      } else {
+        term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+        if (args.gx_ext != nullptr) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
+        }
       }
     }
 #pragma unroll 1
@@ -785,18 +759,27 @@ __global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constan
       }
       // ---- loss-term gradients w.r.t. u_t and y_t
       if (valid) {
-        if constexpr (NU > 0) {
-          term_grad_accum<NUA>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
-          if (args.gu_ext != nullptr) {
+        if (pre) {
 #pragma unroll
-            for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
+          for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.G_x + b * g_row + g_uoff + t * NU + j);
+#pragma unroll
+          for (int j = 0; j < NY; ++j) gy[j] += __ldg(args.G_x + b * g_row + g_yoff + t * NY + j);
+          if constexpr (NU > 0) { if (tb_mask & 2) term_grad_accum<NUA, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu); }
+          if constexpr (NY > 0) { if (tb_mask & 4) term_grad_accum<NYA, 2>(p, vt, coef, b, NM_VAR_Y, t, NY, gy); }
+        } else {
+          if constexpr (NU > 0) {
+            term_grad_accum<NUA>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+            if (args.gu_ext != nullptr) {
+#pragma unroll
+              for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
+            }
           }
-        }
-        if constexpr (NY > 0) {
-          term_grad_accum<NYA>(p, vt, coef, b, NM_VAR_Y, t, NY, gy);
-          if (args.gy_ext != nullptr) {
+          if constexpr (NY > 0) {
+            term_grad_accum<NYA>(p, vt, coef, b, NM_VAR_Y, t, NY, gy);
+            if (args.gy_ext != nullptr) {
 #pragma unroll
-            for (int j = 0; j < NY; ++j) gy[j] += __ldg(args.gy_ext + (b * T + t) * NY + j);
+              for (int j = 0; j < NY; ++j) gy[j] += __ldg(args.gy_ext + (b * T + t) * NY + j);
+            }
           }
         }
       }
@@ -840,10 +823,16 @@ __global__ void __launch_bounds__(S::THREADS) nm_bwd_kernel(const __grid_constan
           }
         }
         if (valid) {
-          term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
-          if (args.gx_ext != nullptr) {
+          if (pre) {
 #pragma unroll
-            for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+            for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
+            if (tb_mask & 1) term_grad_accum<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+          } else {
+            term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+            if (args.gx_ext != nullptr) {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+            }
           }
         }
 #pragma unroll

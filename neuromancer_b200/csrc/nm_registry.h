@@ -8,16 +8,16 @@ struct NmFwdCall {
   const float* params; const float* x0; const float* const* exo;
   float* x_traj; float* u_traj; float* y_traj;
   void* workspace; size_t workspace_bytes; int64_t B; cudaStream_t stream;
-  // outputs of the launcher, consumed by the finalise kernel
-  double* term_partials; int grid;
+  int grid;                                        // out: CTAs launched
 };
 struct NmBwdCall {
   const float* params; const float* const* exo;
   const float* x_traj; const float* u_traj; const float* y_traj;
   const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
   float* grad_x0;
+  const float* G_x; const float* G_u; const float* G_y;   // precomputed term gradients or null
   void* workspace; size_t workspace_bytes; int64_t B; int64_t b_total; cudaStream_t stream;
-  float* grad_partials; int grid;
+  float* grad_partials; int grid;                  // out: per-CTA gradient blocks, CTAs launched
 };
 
 struct NmKernelEntry {

@@ -12,8 +12,19 @@ namespace {
 
 using namespace nm;
 
+// optional per-shape-class tuning emitted by build.py into the generated header
+#ifndef NM_TUNE_MINB_FWD
+#define NM_TUNE_MINB_FWD 1
+#endif
+#ifndef NM_TUNE_MINB_BWD
+#define NM_TUNE_MINB_BWD 1
+#endif
 template <class Shape, int TILE_, int THREADS_, bool W_SMEM_>
-struct Tiled : Shape { static constexpr int TILE = TILE_, THREADS = THREADS_; static constexpr bool W_SMEM = W_SMEM_; };
+struct Tiled : Shape {
+  static constexpr int TILE = TILE_, THREADS = THREADS_;
+  static constexpr bool W_SMEM = W_SMEM_;
+  static constexpr int MINB_FWD = NM_TUNE_MINB_FWD, MINB_BWD = NM_TUNE_MINB_BWD;   // __launch_bounds__ min CTAs / SM
+};
 
 // widest layer decides the CTA size; the largest batch tile whose buffers fit in 227 KB wins
 constexpr int shape_max_width() {
@@ -22,11 +33,23 @@ constexpr int shape_max_width() {
   for (int l = 0; l <= NM_SPEC_NAME::RhsM::NL; ++l) m = cmax(m, NM_SPEC_NAME::RhsM::sz(l));
   return m;
 }
+#ifdef NM_TUNE_THREADS
+constexpr int kThreads = NM_TUNE_THREADS;
+#else
 constexpr int kThreads = shape_max_width() >= 96 ? 256 : 128;
+#endif
 template <int TILE, bool WS> constexpr bool fits() { return KCfg<Tiled<NM_SPEC_NAME, TILE, kThreads, WS>>::FITS; }
 // preference: weights staged in shared memory with the largest tile; else weights streamed from L2
+#ifdef NM_TUNE_TILE
+constexpr bool kWSmem = fits<NM_TUNE_TILE, true>();
+#else
 constexpr bool kWSmem = fits<128, true>() || fits<64, true>();
+#endif
+#ifdef NM_TUNE_TILE
+constexpr int kTile = NM_TUNE_TILE;
+#else
 constexpr int kTile = kWSmem ? (fits<128, true>() ? 128 : 64) : (fits<128, false>() ? 128 : (fits<64, false>() ? 64 : 32));
+#endif
 using S = Tiled<NM_SPEC_NAME, kTile, kThreads, kWSmem>;
 using KC = KCfg<S>;
 static_assert(KC::FITS, "shape class does not fit in shared memory even with a 32-trajectory tile");
@@ -73,7 +96,8 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   const int64_t tiles = (B + S::TILE - 1) / S::TILE;
   const int64_t gf = tiles < int64_t(sms) * occf ? tiles : int64_t(sms) * occf;
   const int64_t gb = tiles < int64_t(sms) * occb ? tiles : int64_t(sms) * occb;
-  *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
+  (void)gf;
+  *fwd = kWprepBytes;
   *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float));
   return NM_OK;
 }
@@ -95,14 +119,13 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   int grid = d->sms * d->occ_fwd; if (grid > tiles) grid = tiles; if (grid < 1) grid = 1;
   char* ws = static_cast<char*>(c->workspace);
   float* wprep = reinterpret_cast<float*>(ws);
-  c->term_partials = reinterpret_cast<double*>(ws + kWprepBytes);
   c->grid = grid;
   launch_prep(p, c->params, wprep, c->stream);
   FwdArgs a{};
   a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
-  a.term_partials = c->term_partials; a.B = c->B; a.num_tiles = tiles;
+  a.B = c->B; a.num_tiles = tiles;
   nm_fwd_kernel<S><<<grid, S::THREADS, KC::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
@@ -126,6 +149,7 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
   a.grad_scalars = c->grad_scalars; a.gx_ext = c->gx_ext; a.gu_ext = c->gu_ext; a.gy_ext = c->gy_ext;
+  a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y;
   a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;
   a.B = c->B; a.b_total = c->b_total; a.num_tiles = tiles;
   nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
@@ -139,8 +163,8 @@ NmKernelEntry g_entry;
 
 struct Registrar {
   Registrar() {
-    std::snprintf(g_info, sizeof(g_info), "tile=%d threads=%d w_smem=%d smem_fwd=%zu smem_bwd=%zu dw_spill=%d wprep_floats=%d",
-                  S::TILE, S::THREADS, int(S::W_SMEM), KC::FWD_SMEM_BYTES, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), KC::W_FLOATS_ALL);
+    std::snprintf(g_info, sizeof(g_info), "tile=%d threads=%d minb=%d/%d w_smem=%d smem_fwd=%zu smem_bwd=%zu dw_spill=%d wprep_floats=%d",
+                  S::TILE, S::THREADS, S::MINB_FWD, S::MINB_BWD, int(S::W_SMEM), KC::FWD_SMEM_BYTES, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), KC::W_FLOATS_ALL);
     g_entry.signature = NM_SPEC_NAME::signature();
     g_entry.workspace = workspace_fn;
     g_entry.forward = forward_fn;

@@ -50,6 +50,8 @@ __device__ __forceinline__ float term_dpenalty(const NmTerm& tm, float v) {
   return tm.norm == 1 ? (v > 0.f ? 1.f : 0.f) : (v > 0.f ? 2.f * v : 0.f);
 }
 
+__device__ __forceinline__ bool atom_is_tbcast(const NmAtom& at, const NmTerm& tm) { return at.t_len == 1 && tm.t_len > 1; }
+
 // sum over this trajectory's elements of term k
 __device__ __forceinline__ float term_sum_traj(const NmTerm& tm, const VarTable& vt, int64_t b) {
   float s = 0.f;
@@ -60,7 +62,7 @@ __device__ __forceinline__ float term_sum_traj(const NmTerm& tm, const VarTable&
 
 // Gradient of  sum_k coef[k] * sum_elements penalty_k  w.r.t. entry (var, t_idx, d) of trajectory b,
 // accumulated into g[d] for d < dim.  coef[k] already holds upstream * weight / element count.
-template <int MAXD>
+template <int MAXD, int MODE = 0>
 __device__ __forceinline__ void term_grad_accum(const NmPlan& p, const VarTable& vt, const float* __restrict__ coef,
                                                 int64_t b, int var, int t_idx, int dim, float (&g)[MAXD]) {
   for (int k = 0; k < p.n_terms; ++k) {
@@ -74,6 +76,8 @@ __device__ __forceinline__ void term_grad_accum(const NmPlan& p, const VarTable&
       if (second && side.op == NM_OP_NONE) continue;
       const NmAtom& at = second ? side.b : side.a;
       if (at.var != var) continue;
+      if (MODE == 1 && atom_is_tbcast(at, tm)) continue;
+      if (MODE == 2 && !atom_is_tbcast(at, tm)) continue;
       // time elements this atom entry participates in
       int te_lo, te_hi;
       if (at.t_len == 1) {
@@ -112,6 +116,94 @@ __device__ __forceinline__ void term_grad_accum(const NmPlan& p, const VarTable&
       }
     }
   }
+}
+
+// ---- pre-resolved atoms: hoist the (b, te) addressing out of the per-dimension loop -------------
+struct AtomRef { const float* p; int dstep; float scale, offset; };
+__device__ __forceinline__ AtomRef atom_ref(const NmAtom& a, const VarTable& vt, int64_t b, int te) {
+  AtomRef r;
+  r.scale = a.scale; r.offset = a.offset; r.dstep = 0; r.p = nullptr;
+  if (a.var >= 0) {
+    const int t = a.t_start + (a.t_len == 1 ? 0 : te);
+    r.p = vt.base[a.var] + (b * vt.T[a.var] + t) * vt.D[a.var] + a.d_start;
+    r.dstep = a.d_len == 1 ? 0 : 1;
+  }
+  return r;
+}
+__device__ __forceinline__ float ref_value(const AtomRef& r, int de) {
+  return r.p == nullptr ? r.offset : fmaf(r.scale, r.p[de * r.dstep], r.offset);
+}
+struct TermRef { AtomRef la, lb, ra, rb; };
+__device__ __forceinline__ TermRef term_ref(const NmTerm& tm, const VarTable& vt, int64_t b, int te) {
+  TermRef r;
+  r.la = atom_ref(tm.lhs.a, vt, b, te);
+  r.ra = atom_ref(tm.rhs.a, vt, b, te);
+  if (tm.lhs.op != NM_OP_NONE) r.lb = atom_ref(tm.lhs.b, vt, b, te); else { r.lb = r.la; }
+  if (tm.rhs.op != NM_OP_NONE) r.rb = atom_ref(tm.rhs.b, vt, b, te); else { r.rb = r.ra; }
+  return r;
+}
+__device__ __forceinline__ float combine(int op, float a, float c) {
+  return op == NM_OP_NONE ? a : (op == NM_OP_ADD ? a + c : (op == NM_OP_SUB ? a - c : a * c));
+}
+__device__ __forceinline__ float term_value_ref(const NmTerm& tm, const TermRef& r, int de) {
+  const float l = combine(tm.lhs.op, ref_value(r.la, de), tm.lhs.op != NM_OP_NONE ? ref_value(r.lb, de) : 0.f);
+  const float q = combine(tm.rhs.op, ref_value(r.ra, de), tm.rhs.op != NM_OP_NONE ? ref_value(r.rb, de) : 0.f);
+  return tm.cmp == NM_CMP_GT ? q - l : l - q;
+}
+
+// d(sum_k coef_k * sum penalty_k) / d V[b, t_idx, d]  for ONE trajectory entry
+// An atom is "time-broadcast" when it is a single time entry compared against a whole time range
+// (x[:, [-1], :] against every r_t).  Its gradient is a sum over the range; evaluated per entry in a
+// thread-per-entry kernel it diverges badly, so the entry kernel skips it (MODE 1) and the adjoint
+// sweep -- where all lanes sit at the same t -- adds it (MODE 2).  MODE 0 handles every atom.
+
+template <int MODE>
+__device__ __forceinline__ float term_grad_entry(const NmPlan& p, const VarTable& vt, const float* __restrict__ coef,
+                                                 int64_t b, int var, int t_idx, int d) {
+  float g = 0.f;
+  for (int k = 0; k < p.n_terms; ++k) {
+    const NmTerm& tm = p.terms[k];
+    const float ck = coef[k];
+    if (ck == 0.f) continue;
+#pragma unroll
+    for (int which = 0; which < 4; ++which) {
+      const NmSide& side = which < 2 ? tm.lhs : tm.rhs;
+      const bool second = which & 1;
+      if (second && side.op == NM_OP_NONE) continue;
+      const NmAtom& at = second ? side.b : side.a;
+      if (at.var != var) continue;
+      if (MODE == 1 && atom_is_tbcast(at, tm)) continue;
+      if (MODE == 2 && !atom_is_tbcast(at, tm)) continue;
+      int te_lo, te_hi, de_lo, de_hi;
+      if (at.t_len == 1) { if (t_idx != at.t_start) continue; te_lo = 0; te_hi = tm.t_len; }
+      else { const int te = t_idx - at.t_start; if (te < 0 || te >= at.t_len) continue; te_lo = te; te_hi = te + 1; }
+      if (at.d_len == 1) { if (d != at.d_start) continue; de_lo = 0; de_hi = tm.d_len; }
+      else { const int de = d - at.d_start; if (de < 0 || de >= at.d_len) continue; de_lo = de; de_hi = de + 1; }
+      const float side_sign = (which < 2) ? (tm.cmp == NM_CMP_GT ? -1.f : 1.f) : (tm.cmp == NM_CMP_GT ? 1.f : -1.f);
+      float acc = 0.f;
+      for (int te = te_lo; te < te_hi; ++te) {
+        const TermRef r = term_ref(tm, vt, b, te);
+        for (int de = de_lo; de < de_hi; ++de) {
+          float dv = term_dpenalty(tm, term_value_ref(tm, r, de)) * side_sign;
+          if (side.op == NM_OP_SUB && second) dv = -dv;
+          else if (side.op == NM_OP_MUL) dv *= ref_value(second ? (which < 2 ? r.la : r.ra) : (which < 2 ? r.lb : r.rb), de);
+          acc += dv;
+        }
+      }
+      g = fmaf(ck * at.scale, acc, g);
+    }
+  }
+  return g;
+}
+
+// coefficient of term k in the scalar being differentiated:
+//   (d term_k + d objective|penalty + d loss) * weight / (global element count)
+__device__ __forceinline__ float term_coef(const NmPlan& p, int k, const float* __restrict__ grad_scalars, int64_t b_total) {
+  const NmTerm& tm = p.terms[k];
+  float up = 1.f;
+  if (grad_scalars != nullptr)
+    up = grad_scalars[k] + grad_scalars[p.n_terms + (tm.is_objective ? 0 : 1)] + grad_scalars[p.n_terms + 2];
+  return up * tm.weight / (static_cast<float>(b_total) * static_cast<float>(tm.t_len) * static_cast<float>(tm.d_len));
 }
 
 }  // namespace nm

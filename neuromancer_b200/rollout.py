@@ -103,12 +103,12 @@ class FusedRollout(torch.autograd.Function):
                                            _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(scalars),
                                            _ptr(ws), ws.numel(), B, stream), "nm_rollout_forward")
         runner.launches += lib.nm_last_launch_count()
-        ctx.runner, ctx.B, ctx.exo = runner, B, exo
-        ctx.trajs = (x_traj, u_traj, y_traj)
+        ctx.runner, ctx.B = runner, B
         ctx.n_exo = n_exo
         ctx.n_tensors = len(tensors)
         outs = [x_traj, u_traj if u_traj is not None else x_traj.new_empty(0),
                 y_traj if y_traj is not None else x_traj.new_empty(0), scalars]
+        ctx.save_for_backward(outs[0], outs[1], outs[2], *exo)
         ctx.mark_non_differentiable(*[o for o in outs[1:3] if o.numel() == 0])
         return tuple(outs)
 
@@ -118,7 +118,11 @@ class FusedRollout(torch.autograd.Function):
         plan: RolloutPlan = runner.plan
         p = plan.c
         lib = L.load()
-        x_traj, u_traj, y_traj = ctx.trajs
+        saved = ctx.saved_tensors
+        x_traj = saved[0]
+        u_traj = saved[1] if saved[1].numel() else None
+        y_traj = saved[2] if saved[2].numel() else None
+        exo = saved[3:]
         dev = x_traj.device
         B = ctx.B
 
@@ -136,7 +140,7 @@ class FusedRollout(torch.autograd.Function):
         L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
                 "nm_rollout_workspace_bytes")
         ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
-        exo_ptrs = (C.c_void_p * max(ctx.n_exo, 1))(*[e.data_ptr() for e in ctx.exo])
+        exo_ptrs = (C.c_void_p * max(ctx.n_exo, 1))(*[e.data_ptr() for e in exo])
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         want_x0 = ctx.needs_input_grad[1]
         gx0 = torch.empty(B, p.nx, dtype=torch.float32, device=dev) if want_x0 else None
@@ -268,3 +272,59 @@ def run_problem(system, loss, data):
         out.register(["C_violations", "C_values", "C_eq_violations", "C_ineq_violations",
                       "C_eq_values", "C_ineq_values"], c_matrices)
     return out
+
+
+class RawTrainStep:
+    """Allocation-free train step straight on the C ABI: ``forward()`` + ``backward()`` on buffers that
+    stay resident in HBM.  The gradient buffer carries the loss scalars in its tail
+    (``[n_params | n_terms+3]``) so that data-parallel training needs a single all-reduce.
+    Used by ``bench.py`` for the kernel-path throughput; the public API path is ``Problem.forward``."""
+
+    def __init__(self, plan: RolloutPlan, batch: Dict[str, torch.Tensor], world_size: int = 1):
+        lay, p = plan.layout, plan.c
+        self.plan, self.lib = plan, L.load()
+        x_in = batch[lay.state_key]
+        _require_cuda(x_in, lay.state_key)
+        dev = x_in.device
+        self.dev, self.B, self.world_size = dev, x_in.shape[0], world_size
+        self.runner = _runner_for(plan, dev)
+        if not self.runner.arena.in_sync(plan.params):
+            self.runner.arena.adopt(plan.params)
+        self.x0 = x_in[:, 0, :].contiguous()
+        self.exo = [batch[k].contiguous() for k in plan.exo_keys]
+        for e, k in zip(self.exo, plan.exo_keys):
+            _require_cuda(e, k)
+        B = self.B
+        self.x_traj = torch.empty(B, p.nsteps + 1, p.nx, dtype=torch.float32, device=dev)
+        self.u_traj = torch.empty(B, p.nsteps, p.nu, dtype=torch.float32, device=dev) if p.nu else None
+        self.y_traj = torch.empty(B, p.nsteps, p.ny, dtype=torch.float32, device=dev) if p.ny else None
+        n = int(p.n_params)
+        self.gbuf = torch.zeros(n + plan.n_scalars, dtype=torch.float32, device=dev)
+        self.grad = self.gbuf[:n]
+        self.scalars = self.gbuf[n:]
+        fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
+        L.check(self.lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
+                "nm_rollout_workspace_bytes")
+        self.ws = torch.empty(max(fwd_b.value, bwd_b.value, 256), dtype=torch.uint8, device=dev)
+        self.exo_ptrs = (C.c_void_p * max(len(self.exo), 1))(*[e.data_ptr() for e in self.exo])
+        self.launches = 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def forward(self):
+        p = self.plan.c
+        L.check(self.lib.nm_rollout_forward(
+            C.byref(p), _ptr(self.runner.arena.flat), _ptr(self.x0), self.exo_ptrs, _ptr(self.x_traj),
+            _ptr(self.u_traj), _ptr(self.y_traj), C.c_void_p(self.scalars.data_ptr()), _ptr(self.ws),
+            self.ws.numel(), self.B, self._stream()), "nm_rollout_forward")
+        self.launches += self.lib.nm_last_launch_count()
+
+    def backward(self):
+        p = self.plan.c
+        L.check(self.lib.nm_rollout_backward(
+            C.byref(p), _ptr(self.runner.arena.flat), self.exo_ptrs, _ptr(self.x_traj), _ptr(self.u_traj),
+            _ptr(self.y_traj), None, None, None, None, C.c_void_p(self.grad.data_ptr()), None,
+            _ptr(self.ws), self.ws.numel(), self.B, self.B * self.world_size, self._stream()),
+            "nm_rollout_backward")
+        self.launches += self.lib.nm_last_launch_count()

@@ -1,0 +1,84 @@
+"""
+``Trainer``: the caller of the hot path (reference trainer.py:154-344).
+
+Same loop -- ``zero_grad -> output[train_metric].backward() -> clip_grad_norm_ -> optimizer.step()``
+with best-model tracking on the dev metric -- with an optional ``GradientSync`` that all-reduces the
+gradients between backward and the clip when training data-parallel.  Logging / callbacks /
+Lightning integration of the reference are outside the hot-path scope.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from .dataset import move_batch_to_device
+
+
+class Trainer:
+    def __init__(self, problem, train_data, dev_data=None, test_data=None, optimizer=None, logger=None,
+                 callback=None, lr_scheduler=False, epochs=1000, epoch_verbose=1, patience=5, warmup=0,
+                 train_metric="train_loss", dev_metric="dev_loss", test_metric="test_loss",
+                 eval_metric="dev_loss", eval_mode="min", clip=100.0, multi_fidelity=False,
+                 device="cuda", grad_sync=None):
+        self.model = problem
+        self.optimizer = optimizer if optimizer is not None else torch.optim.Adam(problem.parameters(), 0.01, betas=(0.0, 0.9))
+        self.train_data, self.dev_data, self.test_data = train_data, dev_data, test_data
+        self.epochs, self.current_epoch, self.epoch_verbose = epochs, 0, epoch_verbose
+        self.train_metric, self.dev_metric, self.test_metric = train_metric, dev_metric, test_metric
+        self.eval_metric, self._eval_min = eval_metric, eval_mode == "min"
+        self.patience, self.warmup, self.badcount, self.clip = patience, warmup, 0, clip
+        self.best_devloss = np.finfo(np.float32).max if self._eval_min else 0.
+        self.best_model = deepcopy(self.model.state_dict())
+        self.device, self.grad_sync = device, grad_sync
+        self.lr_scheduler = (torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=0.5, patience=100)
+                             if lr_scheduler else None)
+
+    def train_step(self, batch):
+        output = self.model(batch)
+        self.optimizer.zero_grad()
+        output[self.train_metric].backward()
+        if self.grad_sync is not None:
+            self.grad_sync.sync_gradients(self.model.parameters())
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        self.optimizer.step()
+        return output
+
+    def train(self):
+        output = {}
+        for i in range(self.current_epoch, self.current_epoch + self.epochs):
+            self.model.train()
+            losses = []
+            for batch in self.train_data:
+                batch["epoch"] = i
+                output = self.train_step(move_batch_to_device(batch, self.device))
+                losses.append(output[self.train_metric].detach())
+            output[f"mean_{self.train_metric}"] = torch.mean(torch.stack(losses))
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step(output[f"mean_{self.train_metric}"])
+            with torch.set_grad_enabled(self.model.grad_inference):
+                self.model.eval()
+                if self.dev_data is not None:
+                    losses = []
+                    for batch in self.dev_data:
+                        ev = self.model(move_batch_to_device(batch, self.device))
+                        losses.append(ev[self.dev_metric].detach())
+                    output[self.dev_metric] = ev[self.dev_metric]
+                    output[f"mean_{self.dev_metric}"] = torch.mean(torch.stack(losses))
+                score = output.get(self.eval_metric, output[f"mean_{self.train_metric}"])
+                better = score < self.best_devloss if self._eval_min else score > self.best_devloss
+                if better:
+                    self.best_model = deepcopy(self.model.state_dict())
+                    self.best_devloss = score
+                    self.badcount = 0
+                elif i > self.warmup:
+                    self.badcount += 1
+                if self.epoch_verbose and i % self.epoch_verbose == 0:
+                    print(f"epoch: {i}  {self.train_metric}: {float(output[f'mean_{self.train_metric}'])}")
+                if self.badcount > self.patience:
+                    print("Early stopping!!!")
+                    break
+                self.current_epoch = i + 1
+        self.model.load_state_dict(self.best_model)
+        return self.best_model
