@@ -170,6 +170,11 @@ def main():
     import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line, so park stdout on stderr
+    # until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from neuromancer_b200 import rollout as nr
@@ -228,7 +233,7 @@ def main():
     ms_per_step = float(total_ms) / args.steps
     launches = raw.launches - launches0
     value = world * B * nsteps / (ms_per_step * 1e-3)
-    loss_val = float(raw.scalars[-1])
+    loss_val = float(raw.scalars[-1]) / world                 # the tail was SUM-all-reduced with the gradient
     import ctypes
     from neuromancer_b200 import _lib
     kernel_info = _lib.load().nm_kernel_info(ctypes.byref(plan.c)).decode()
@@ -299,6 +304,8 @@ def main():
                        "kernel_info": kernel_info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "wall_s_timed_region": t_wall}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
