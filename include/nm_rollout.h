@@ -180,6 +180,12 @@ const char* nm_last_error(void);
  * NUL-terminated string into buf (at most cap bytes); returns its length or NM_ERR_*. */
 int nm_plan_signature(const NmPlan* plan, char* buf, int cap);
 
+/* Structure of the plan's fused loss terms (comparators, norms, side ops, variables, broadcast flags).  A
+ * specialisation compiled with the same term structure scores the terms inside the rollout / adjoint
+ * kernels; any other specialisation of the shape class serves the plan through the runtime-descriptor
+ * term kernels.  Same calling convention as nm_plan_signature. */
+int nm_plan_term_signature(const NmPlan* plan, char* buf, int cap);
+
 /* 1 if a compiled sm_100a specialisation is registered for the plan's signature, else 0. */
 int nm_has_kernel(const NmPlan* plan);
 

@@ -88,6 +88,8 @@ def _declare(lib):
     lib.nm_last_error.restype = C.c_char_p
     lib.nm_plan_signature.argtypes = [P(NmPlan), C.c_char_p, C.c_int]
     lib.nm_plan_signature.restype = C.c_int
+    lib.nm_plan_term_signature.argtypes = [P(NmPlan), C.c_char_p, C.c_int]
+    lib.nm_plan_term_signature.restype = C.c_int
     lib.nm_has_kernel.argtypes = [P(NmPlan)]
     lib.nm_has_kernel.restype = C.c_int
     lib.nm_num_kernels.restype = C.c_int
@@ -114,6 +116,7 @@ EXPORTED_SYMBOLS = [
     "nm_abi_version", "nm_last_error", "nm_plan_signature", "nm_has_kernel", "nm_num_kernels",
     "nm_kernel_signature", "nm_load_plugin", "nm_rollout_workspace_bytes", "nm_rollout_forward",
     "nm_rollout_backward", "nm_last_launch_count", "nm_kernel_info", "nm_struct_sizes",
+    "nm_plan_term_signature",
 ]
 
 
@@ -145,6 +148,14 @@ def check(status, what=""):
     if status != NM_OK:
         msg = load().nm_last_error().decode(errors="replace")
         raise NmError(f"{what} failed with status {status}: {msg}")
+
+
+def term_signature(plan: NmPlan) -> str:
+    buf = C.create_string_buffer(4096)
+    n = load().nm_plan_term_signature(C.byref(plan), buf, len(buf))
+    if n < 0:
+        check(n, "nm_plan_term_signature")
+    return buf.value.decode()
 
 
 def signature(plan: NmPlan) -> str:

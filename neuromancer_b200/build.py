@@ -71,8 +71,52 @@ def signature_of(p: L.NmPlan) -> str:
     return s
 
 
+def _atom_sig(a, t) -> str:
+    if a.var < 0:
+        return "k"
+    return f"v{a.var}{'b' if (a.t_len == 1 and t.t_len > 1) else 'r'}{'b' if (a.d_len == 1 and t.d_len > 1) else 'r'}"
+
+
+def term_signature_of(p: L.NmPlan) -> str:
+    """Python twin of ``make_term_signature`` in csrc/nm_api.cu."""
+    parts = []
+    for k in range(p.n_terms):
+        t = p.terms[k]
+        s = f"T{t.cmp}{t.norm}{'o' if t.is_objective else 'c'}"
+        for tag, side in (("L", t.lhs), ("R", t.rhs)):
+            s += f"{tag}{side.op}" + _atom_sig(side.a, t) + (_atom_sig(side.b, t) if side.op != L.NM_OP_NONE else "")
+        parts.append(s)
+    return "|".join(parts)
+
+
 def spec_name(sig: str) -> str:
     return "nmspec_" + hashlib.sha1(sig.encode()).hexdigest()[:16]
+
+
+def _term_tables(p: L.NmPlan) -> str:
+    """Compile-time term structure: per term cmp / norm / side ops, per atom variable + broadcast flags."""
+    n = p.n_terms
+    cmp_, norm, ops, var, tb, db = [], [], [], [], [], []
+    for k in range(n):
+        t = p.terms[k]
+        cmp_.append(t.cmp); norm.append(t.norm); ops += [t.lhs.op, t.rhs.op]
+        for side in (t.lhs, t.rhs):
+            for live, a in ((True, side.a), (side.op != L.NM_OP_NONE, side.b)):
+                if not live:
+                    var.append(-2); tb.append(0); db.append(0)
+                else:
+                    var.append(a.var if a.var >= 0 else -1)
+                    tb.append(int(a.var >= 0 and a.t_len == 1 and t.t_len > 1))
+                    db.append(int(a.var >= 0 and a.d_len == 1 and t.d_len > 1))
+
+    def tab(name, vals, args, index):
+        vals = list(vals) or [0]
+        return (f"  static constexpr int {name}({args}) {{ constexpr int V[] = {{{', '.join(map(str, vals))}}}; "
+                f"return V[{index}]; }}\n")
+    return (f"  static constexpr int NTERMS = {n};\n" + tab("t_cmp", cmp_, "int k", "k") + tab("t_norm", norm, "int k", "k")
+            + tab("t_op", ops, "int k, int side", "2 * k + side") + tab("a_var", var, "int k, int w", "4 * k + w")
+            + tab("a_tb", tb, "int k, int w", "4 * k + w") + tab("a_db", db, "int k, int w", "4 * k + w")
+            + f"  static constexpr const char* term_signature() {{ return \"{term_signature_of(p)}\"; }}\n")
 
 
 # ------------------------------------------------------------------------------- header generation
@@ -111,7 +155,7 @@ def tuning_for(sig: str) -> Dict[str, int]:
 
 def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
     sig = signature_of(p)
-    name = spec_name(sig)
+    name = spec_name(sig + "#" + term_signature_of(p))
     tune_map = tune_override if tune_override is not None else tuning_for(sig)
     tune = "".join(f"#define NM_TUNE_{k.upper()} {v}\n" for k, v in sorted(tune_map.items()))
     nd = p.exo[p.dist_exo].width if p.dist_exo >= 0 else 0
@@ -128,13 +172,13 @@ def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
            _table("seg_index", [s.index for s in segs]),
            _table("seg_width", [s.width for s in segs]),
            f"  static constexpr int DYN = {p.dyn_kind}, INTEG = {integ}, RHS = {p.rhs_kind}, DIST_EXO = {p.dist_exo};\n",
-           f"  static constexpr const char* signature() {{ return \"{sig}\"; }}\n", "};\n"]
+           f"  static constexpr const char* signature() {{ return \"{sig}\"; }}\n", _term_tables(p), "};\n"]
     return "".join(out)
 
 
 def write_spec(p: L.NmPlan) -> str:
     os.makedirs(SPEC_DIR, exist_ok=True)
-    name = spec_name(signature_of(p))
+    name = spec_name(signature_of(p) + "#" + term_signature_of(p))
     path = os.path.join(SPEC_DIR, name + ".h")
     text = spec_header(p)
     if not os.path.exists(path) or open(path).read() != text:
@@ -179,7 +223,7 @@ def build_variant(case_name: str, tune: str, out: str) -> str:
     tag = hashlib.sha1((case_name + tune).encode()).hexdigest()[:10]
     vdir = os.path.join(OUT_DIR, "variants")
     os.makedirs(vdir, exist_ok=True)
-    header = os.path.join(vdir, f"{spec_name(signature_of(p))}_{tag}.h")
+    header = os.path.join(vdir, f"{spec_name(signature_of(p) + '#' + term_signature_of(p))}_{tag}.h")
     with open(header, "w") as f:
         f.write(text)
     obj = os.path.join(vdir, f"{tag}.o")

@@ -17,11 +17,19 @@ int g_count = 0;
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 
-NmKernelEntry* find_entry(const char* sig) {
+// Entry for a shape-class signature.  An entry whose compiled term structure equals `term_sig` is
+// preferred (fused term evaluation, *fused = 1); otherwise any entry of the shape class serves the plan
+// through the runtime-descriptor term kernels (*fused = 0).
+NmKernelEntry* find_entry(const char* sig, const char* term_sig = nullptr, int* fused = nullptr) {
   std::lock_guard<std::mutex> lock(g_mu);
-  for (NmKernelEntry* e = g_head; e; e = e->next)
-    if (std::strcmp(e->signature, sig) == 0) return e;
-  return nullptr;
+  NmKernelEntry* any = nullptr;
+  if (fused) *fused = 0;
+  for (NmKernelEntry* e = g_head; e; e = e->next) {
+    if (std::strcmp(e->signature, sig) != 0) continue;
+    if (term_sig && term_sig[0] && std::strcmp(e->term_signature, term_sig) == 0) { if (fused) *fused = 1; return e; }
+    if (!any) any = e;
+  }
+  return any;
 }
 
 void append_mlp(std::string& s, const NmMlp& m) {
@@ -67,6 +75,32 @@ int validate(const NmPlan* p) {
     }
   }
   return NM_OK;
+}
+
+// structure of the loss terms (what build.py compiles into a shape class): comparator, norm, list, side
+// ops and per atom the variable and its time / dim broadcast flags
+void append_atom_sig(std::string& s, const NmAtom& a, const NmTerm& t) {
+  if (a.var < 0) { s += "k"; return; }
+  char buf[32];
+  std::snprintf(buf, sizeof(buf), "v%d%c%c", a.var, (a.t_len == 1 && t.t_len > 1) ? 'b' : 'r', (a.d_len == 1 && t.d_len > 1) ? 'b' : 'r');
+  s += buf;
+}
+std::string make_term_signature(const NmPlan* p) {
+  std::string s;
+  for (int k = 0; k < p->n_terms; ++k) {
+    const NmTerm& t = p->terms[k];
+    char buf[32];
+    std::snprintf(buf, sizeof(buf), "%sT%d%d%c", k ? "|" : "", t.cmp, t.norm, t.is_objective ? 'o' : 'c');
+    s += buf;
+    const NmSide* sides[2] = {&t.lhs, &t.rhs};
+    for (int i = 0; i < 2; ++i) {
+      std::snprintf(buf, sizeof(buf), "%c%d", i ? 'R' : 'L', sides[i]->op);
+      s += buf;
+      append_atom_sig(s, sides[i]->a, t);
+      if (sides[i]->op != NM_OP_NONE) append_atom_sig(s, sides[i]->b, t);
+    }
+  }
+  return s;
 }
 
 std::string make_signature(const NmPlan* p) {
@@ -250,7 +284,7 @@ void nm_set_error(const char* msg) { std::snprintf(g_err, sizeof(g_err), "%s", m
 void nm_register_kernel(NmKernelEntry* e) {
   std::lock_guard<std::mutex> lock(g_mu);
   for (NmKernelEntry* q = g_head; q; q = q->next)
-    if (std::strcmp(q->signature, e->signature) == 0) return;   // first registration wins
+    if (std::strcmp(q->signature, e->signature) == 0 && std::strcmp(q->term_signature, e->term_signature) == 0) return;   // first registration wins
   e->next = g_head;
   g_head = e;
   ++g_count;
@@ -293,8 +327,21 @@ const char* nm_kernel_signature(int i) {
 
 const char* nm_kernel_info(const NmPlan* plan) {
   if (validate(plan) != NM_OK) return nullptr;
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
-  return e ? e->info : nullptr;
+  int fused = 0;
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &fused);
+  if (!e) return nullptr;
+  static thread_local char buf[320];
+  std::snprintf(buf, sizeof(buf), "%s fused_terms=%d", e->info, fused);
+  return buf;
+}
+
+int nm_plan_term_signature(const NmPlan* plan, char* buf, int cap) {
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  const std::string s = make_term_signature(plan);
+  if (!buf || cap <= (int)s.size()) { nm_set_error("signature buffer too small"); return NM_ERR_BAD_PLAN; }
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
 }
 
 int nm_load_plugin(const char* path) {
@@ -325,7 +372,8 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   if (rc != NM_OK) return rc;
   if (B < 1 || !x0 || !x_traj || !scalars || !workspace || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj) ||
       (plan->n_params > 0 && !params)) { nm_set_error("null pointer argument"); return NM_ERR_BAD_PLAN; }
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  int fused = 0;
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &fused);
   if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
   size_t spec_f = 0, spec_b = 0;
   rc = e->workspace(plan, B, &spec_f, &spec_b);
@@ -336,17 +384,21 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   NmFwdCall c{};
   c.params = params; c.x0 = x0; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
   c.workspace = workspace; c.workspace_bytes = align256(spec_f); c.B = B; c.stream = static_cast<cudaStream_t>(stream);
+  c.fused_terms = fused;
   rc = e->forward(plan, &c);
   if (rc != NM_OK) return rc;
-  double* partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + align256(spec_f));
-  if (plan->n_terms > 0) {
+  const double* partials = c.term_partials;            // written by the rollout kernel when fused
+  int pgrid = c.grid;
+  if (!fused && plan->n_terms > 0) {
+    double* sp = reinterpret_cast<double*>(static_cast<char*>(workspace) + align256(spec_f));
     const nm::VarTable vt = make_vartable(plan, x_traj, u_traj, y_traj, exo);
-    nm_term_score_kernel<<<sgrid, kScoreThreads, 0, c.stream>>>(*plan, vt, B, max_term_steps(plan), partials);
+    nm_term_score_kernel<<<sgrid, kScoreThreads, 0, c.stream>>>(*plan, vt, B, max_term_steps(plan), sp);
+    partials = sp; pgrid = sgrid;
   }
-  nm_loss_finalize_kernel<<<1, 256, 0, c.stream>>>(*plan, partials, sgrid, B, scalars);
+  nm_loss_finalize_kernel<<<1, 256, 0, c.stream>>>(*plan, partials, pgrid, B, scalars);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
-  g_launches = plan->n_terms > 0 ? 4 : 3;           // weight prep + rollout + term scoring + loss finalise
+  g_launches = (!fused && plan->n_terms > 0) ? 4 : 3;   // weight prep + rollout [+ term scoring] + loss finalise
   return NM_OK;
 }
 
@@ -359,12 +411,13 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
   if (rc != NM_OK) return rc;
   if (B < 1 || b_total < B || !x_traj || !workspace || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj) ||
       (plan->n_params > 0 && (!params || !grad_params))) { nm_set_error("null pointer / bad size argument"); return NM_ERR_BAD_PLAN; }
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  int fused = 0;
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &fused);
   if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
   size_t spec_f = 0, spec_b = 0;
   rc = e->workspace(plan, B, &spec_f, &spec_b);
   if (rc != NM_OK) return rc;
-  const bool pre = use_gbuf(plan, B);
+  const bool pre = !fused && use_gbuf(plan, B);
   const size_t need = align256(spec_b) + (pre ? align256(gbuf_floats(plan, B) * sizeof(float)) : 0);
   if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) { nm_set_error("backward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
   NmBwdCall c{};
@@ -372,6 +425,7 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
   c.grad_scalars = grad_scalars; c.gx_ext = grad_x_ext; c.gu_ext = grad_u_ext; c.gy_ext = grad_y_ext;
   c.grad_x0 = grad_x0; c.workspace = workspace; c.workspace_bytes = align256(spec_b); c.B = B; c.b_total = b_total;
   c.stream = static_cast<cudaStream_t>(stream);
+  c.fused_terms = fused;
   int extra = 0;
   if (pre) {
     float* G = reinterpret_cast<float*>(static_cast<char*>(workspace) + align256(spec_b));

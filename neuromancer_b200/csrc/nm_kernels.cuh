@@ -91,7 +91,7 @@ struct KCfg {
   static constexpr int W_FLOATS_ALL = round_up(PolCfg::ALL_W, 4) + round_up(RhsCfg::ALL_W, 4);
   static constexpr int POL_W_OFF = 0, RHS_W_OFF = round_up(PolCfg::ALL_W, 4);       // in the prepared global block
   // forward kernel shared memory (floats)
-  static constexpr int FWD_PP0 = cmax(cmax(PolCfg::pp_rows(0), RhsCfg::pp_rows(0)), 2) * LD;   // >= 256 floats: reused by the loss reduction
+  static constexpr int FWD_PP0 = cmax(cmax(PolCfg::pp_rows(0), RhsCfg::pp_rows(0)), 4) * LD;   // >= 256 floats: reused by the loss reduction
   static constexpr int FWD_PP1 = cmax(PolCfg::pp_rows(1), RhsCfg::pp_rows(1)) * LD;
   // weights are staged in shared memory when they fit, else streamed from the prepared global block (L1/L2)
   static constexpr bool W_SMEM = S::W_SMEM;
@@ -109,6 +109,8 @@ struct FwdArgs {
   const float* params; const float* wprep; const float* x0;
   const float* exo[NM_MAX_EXO];
   float* x_traj; float* u_traj; float* y_traj;
+  double* term_partials;            // [grid][NM_MAX_TERMS], written when fused_terms
+  int fused_terms;                  // the plan's terms match the compiled term structure of S
   int64_t B; int num_tiles;
 };
 struct BwdArgs {
@@ -121,6 +123,7 @@ struct BwdArgs {
   const float* G_x; const float* G_u; const float* G_y;
   float* grad_partials;             // [grid][n_params]
   float* grad_x0;
+  int fused_terms;                  // evaluate term gradients with the compiled term structure of S
   int64_t B; int64_t b_total; int num_tiles;
 };
 
@@ -451,8 +454,23 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
   float* pp0 = sm_w + (KC::W_SMEM ? KC::W_FLOATS_FWD : 0);
   float* pp1 = pp0 + KC::FWD_PP0;
   uint64_t* bar = reinterpret_cast<uint64_t*>(pp1 + KC::FWD_PP1);
+  VarTable& vt = *reinterpret_cast<VarTable*>(pp1 + KC::FWD_PP1 + 16);
   const int tid = threadIdx.x;
   const NmPlan& p = plan;
+  constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  if (tid == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = p.nsteps + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = p.nsteps; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = p.nsteps; vt.D[NM_VAR_Y] = NY;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+  }
+  float tsum[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) tsum[q] = 0.f;
+  __syncthreads();
 
   // only the forward halves of the prepared weight blocks are needed here
   const float* Wpol;
@@ -563,9 +581,34 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
         }
       }
     }
+    // PenaltyLoss scoring of this thread's trajectory with the compiled term structure (its entries
+    // were stored by this same thread; plain loads are coherent)
+    if constexpr (S::NTERMS > 0) {
+      if (fused && valid) score_traj_s<S>(p, vt, b, tsum);
+    }
   }
 
-  // (PenaltyLoss scoring runs in nm_term_score_kernel over all (trajectory, time) pairs in parallel)
+  // block reduction of the term sums (double) -> this CTA's partials; with runtime-descriptor terms the
+  // scoring runs in nm_term_score_kernel instead
+  if constexpr (S::NTERMS > 0) {
+    if (fused) {
+      __syncthreads();
+      double* scratch = reinterpret_cast<double*>(pp0);       // activations are dead now (>= 512 floats)
+      static_for<0, S::NTERMS>([&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        double v = static_cast<double>(tsum[K]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) scratch[K * (THREADS / 32) + (tid >> 5)] = v;
+      });
+      __syncthreads();
+      if (tid < S::NTERMS) {
+        double v = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w) v += scratch[tid * (THREADS / 32) + w];
+        args.term_partials[size_t(blockIdx.x) * NM_MAX_TERMS + tid] = v;
+      }
+    }
+  }
   (void)Wrhs; (void)Wpol;
 }
 
@@ -591,7 +634,8 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
   const int tid = threadIdx.x;
   const NmPlan& p = plan;
   const int T = p.nsteps;
-  const bool pre = args.G_x != nullptr;
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  const bool pre = !fused && args.G_x != nullptr;
   // row layout of the precomputed term gradients: G[b] = [ x(T+1, NX) | u(T, NU) | y(T, NY) ]
   const int g_row = (T + 1) * NX + T * (NU + NY), g_uoff = (T + 1) * NX, g_yoff = g_uoff + T * NU;
   // which of x / u / y carry time-broadcast atoms (those are not in G, see nm_terms.cuh)
@@ -653,9 +697,10 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
       if (pre) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
-        if (tb_mask & 1) term_grad_accum<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+        if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
       } else {
-        term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+        if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, T, lam); }
+        else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
         if (args.gx_ext != nullptr) {
 #pragma unroll
           for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
@@ -764,18 +809,20 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
           for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.G_x + b * g_row + g_uoff + t * NU + j);
 #pragma unroll
           for (int j = 0; j < NY; ++j) gy[j] += __ldg(args.G_x + b * g_row + g_yoff + t * NY + j);
-          if constexpr (NU > 0) { if (tb_mask & 2) term_grad_accum<NUA, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu); }
-          if constexpr (NY > 0) { if (tb_mask & 4) term_grad_accum<NYA, 2>(p, vt, coef, b, NM_VAR_Y, t, NY, gy); }
+          if constexpr (NU > 0) { if (tb_mask & 2) term_grad_accum_ool<NUA, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu); }
+          if constexpr (NY > 0) { if (tb_mask & 4) term_grad_accum_ool<NYA, 2>(p, vt, coef, b, NM_VAR_Y, t, NY, gy); }
         } else {
           if constexpr (NU > 0) {
-            term_grad_accum<NUA>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_U, NU, NUA>(p, vt, coef, b, t, gu); }
+            else term_grad_accum_ool<NUA, 0>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
             if (args.gu_ext != nullptr) {
 #pragma unroll
               for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
             }
           }
           if constexpr (NY > 0) {
-            term_grad_accum<NYA>(p, vt, coef, b, NM_VAR_Y, t, NY, gy);
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_Y, NY, NYA>(p, vt, coef, b, t, gy); }
+            else term_grad_accum_ool<NYA, 0>(p, vt, coef, b, NM_VAR_Y, t, NY, gy);
             if (args.gy_ext != nullptr) {
 #pragma unroll
               for (int j = 0; j < NY; ++j) gy[j] += __ldg(args.gy_ext + (b * T + t) * NY + j);
@@ -826,9 +873,10 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
           if (pre) {
 #pragma unroll
             for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
-            if (tb_mask & 1) term_grad_accum<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
           } else {
-            term_grad_accum<NX>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, t, gx); }
+            else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
             if (args.gx_ext != nullptr) {
 #pragma unroll
               for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);

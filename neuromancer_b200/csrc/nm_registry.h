@@ -8,7 +8,8 @@ struct NmFwdCall {
   const float* params; const float* x0; const float* const* exo;
   float* x_traj; float* u_traj; float* y_traj;
   void* workspace; size_t workspace_bytes; int64_t B; cudaStream_t stream;
-  int grid;                                        // out: CTAs launched
+  int fused_terms;                                 // in: plan terms match the entry's compiled term structure
+  double* term_partials; int grid;                 // out: per-CTA term sums (fused), CTAs launched
 };
 struct NmBwdCall {
   const float* params; const float* const* exo;
@@ -16,12 +17,14 @@ struct NmBwdCall {
   const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
   float* grad_x0;
   const float* G_x; const float* G_u; const float* G_y;   // precomputed term gradients or null
+  int fused_terms;
   void* workspace; size_t workspace_bytes; int64_t B; int64_t b_total; cudaStream_t stream;
   float* grad_partials; int grid;                  // out: per-CTA gradient blocks, CTAs launched
 };
 
 struct NmKernelEntry {
   const char* signature;
+  const char* term_signature;                     // compiled term structure ("" = none)
   int (*workspace)(const NmPlan*, int64_t B, size_t* fwd_bytes, size_t* bwd_bytes);
   int (*forward)(const NmPlan*, NmFwdCall*);      // prep + rollout kernel; returns NM_OK / NM_ERR_*
   int (*backward)(const NmPlan*, NmBwdCall*);     // prep + adjoint kernel

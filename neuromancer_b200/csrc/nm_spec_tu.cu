@@ -86,6 +86,10 @@ int check_plan(const NmPlan* p) {
   if (KC::HAS_RHS_MLP && (p->rhs_mlp.has_bias != 0) != S::RhsM::BIAS) { nm_set_error("rhs bias flag mismatch"); return NM_ERR_BAD_PLAN; }
   return NM_OK;
 }
+int check_fused(const NmPlan* p, int fused) {
+  if (fused && p->n_terms != S::NTERMS) { nm_set_error("fused term count mismatch"); return NM_ERR_BAD_PLAN; }
+  return NM_OK;
+}
 
 int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   DeviceInfo* d = nullptr;
@@ -96,8 +100,7 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   const int64_t tiles = (B + S::TILE - 1) / S::TILE;
   const int64_t gf = tiles < int64_t(sms) * occf ? tiles : int64_t(sms) * occf;
   const int64_t gb = tiles < int64_t(sms) * occb ? tiles : int64_t(sms) * occb;
-  (void)gf;
-  *fwd = kWprepBytes;
+  *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
   *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float));
   return NM_OK;
 }
@@ -112,6 +115,7 @@ int launch_prep(const NmPlan* p, const float* params, float* wprep, cudaStream_t
 
 int forward_fn(const NmPlan* p, NmFwdCall* c) {
   int rc = check_plan(p); if (rc != NM_OK) return rc;
+  rc = check_fused(p, c->fused_terms); if (rc != NM_OK) return rc;
   DeviceInfo* d = nullptr; rc = device_info(&d); if (rc != NM_OK) return rc;
   size_t need_f = 0, need_b = 0; workspace_fn(p, c->B, &need_f, &need_b);
   if (c->workspace_bytes < need_f || (reinterpret_cast<uintptr_t>(c->workspace) & 255)) { nm_set_error("forward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
@@ -120,8 +124,10 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   char* ws = static_cast<char*>(c->workspace);
   float* wprep = reinterpret_cast<float*>(ws);
   c->grid = grid;
+  c->term_partials = reinterpret_cast<double*>(ws + kWprepBytes);
   launch_prep(p, c->params, wprep, c->stream);
   FwdArgs a{};
+  a.term_partials = c->term_partials; a.fused_terms = c->fused_terms;
   a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
@@ -134,6 +140,7 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
 
 int backward_fn(const NmPlan* p, NmBwdCall* c) {
   int rc = check_plan(p); if (rc != NM_OK) return rc;
+  rc = check_fused(p, c->fused_terms); if (rc != NM_OK) return rc;
   DeviceInfo* d = nullptr; rc = device_info(&d); if (rc != NM_OK) return rc;
   size_t need_f = 0, need_b = 0; workspace_fn(p, c->B, &need_f, &need_b);
   if (c->workspace_bytes < need_b || (reinterpret_cast<uintptr_t>(c->workspace) & 255)) { nm_set_error("backward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
@@ -149,7 +156,7 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
   a.grad_scalars = c->grad_scalars; a.gx_ext = c->gx_ext; a.gu_ext = c->gu_ext; a.gy_ext = c->gy_ext;
-  a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y;
+  a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y; a.fused_terms = c->fused_terms;
   a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;
   a.B = c->B; a.b_total = c->b_total; a.num_tiles = tiles;
   nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
@@ -163,9 +170,10 @@ NmKernelEntry g_entry;
 
 struct Registrar {
   Registrar() {
-    std::snprintf(g_info, sizeof(g_info), "tile=%d threads=%d minb=%d/%d w_smem=%d smem_fwd=%zu smem_bwd=%zu dw_spill=%d wprep_floats=%d",
-                  S::TILE, S::THREADS, S::MINB_FWD, S::MINB_BWD, int(S::W_SMEM), KC::FWD_SMEM_BYTES, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), KC::W_FLOATS_ALL);
+    std::snprintf(g_info, sizeof(g_info), "tile=%d threads=%d minb=%d/%d compiled_terms=%d w_smem=%d smem_fwd=%zu smem_bwd=%zu dw_spill=%d wprep_floats=%d",
+                  S::TILE, S::THREADS, S::MINB_FWD, S::MINB_BWD, S::NTERMS, int(S::W_SMEM), KC::FWD_SMEM_BYTES, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), KC::W_FLOATS_ALL);
     g_entry.signature = NM_SPEC_NAME::signature();
+    g_entry.term_signature = NM_SPEC_NAME::term_signature();
     g_entry.workspace = workspace_fn;
     g_entry.forward = forward_fn;
     g_entry.backward = backward_fn;

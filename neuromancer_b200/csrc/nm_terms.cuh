@@ -196,6 +196,143 @@ __device__ __forceinline__ float term_grad_entry(const NmPlan& p, const VarTable
   return g;
 }
 
+
+// ================================================================================================
+// Compile-time-structured terms.  The shape-class header (build.py) records, per term, the comparator,
+// norm, side ops and per atom the variable it reads and whether it is broadcast along time / dim;
+// slice starts, lengths, scale, offset and weight stay runtime (NmPlan).  With the structure known the
+// evaluation compiles to straight-line code (no descriptor decoding), so scoring and the term
+// gradients are fused into the rollout / adjoint sweeps at a few dozen instructions per step.
+template <class S, int K, int W>
+struct AtomS {                                   // W: 0 lhs.a, 1 lhs.b, 2 rhs.a, 3 rhs.b
+  static constexpr int VAR = S::a_var(K, W);     // -2 unused, -1 constant, >= 0 NM_VAR_*
+  static constexpr bool TB = S::a_tb(K, W) != 0; // single time entry broadcast over the term's range
+  static constexpr bool DB = S::a_db(K, W) != 0;
+};
+template <int W>
+__device__ __forceinline__ const NmAtom& pick_atom(const NmTerm& tm) {
+  if constexpr (W == 0) return tm.lhs.a; else if constexpr (W == 1) return tm.lhs.b;
+  else if constexpr (W == 2) return tm.rhs.a; else return tm.rhs.b;
+}
+template <class S, int K, int W>
+__device__ __forceinline__ float atom_value_s(const NmTerm& tm, const VarTable& vt, int64_t b, int te, int de) {
+  using A = AtomS<S, K, W>;
+  const NmAtom& a = pick_atom<W>(tm);
+  if constexpr (A::VAR < 0) return a.offset;
+  else {
+    const int t = a.t_start + (A::TB ? 0 : te);
+    const int d = a.d_start + (A::DB ? 0 : de);
+    const float v = vt.base[A::VAR][(b * vt.T[A::VAR] + t) * vt.D[A::VAR] + d];
+    return fmaf(a.scale, v, a.offset);
+  }
+}
+template <class S, int K, int SIDE>
+__device__ __forceinline__ float side_value_s(const NmTerm& tm, const VarTable& vt, int64_t b, int te, int de) {
+  constexpr int OP = S::t_op(K, SIDE);
+  const float a = atom_value_s<S, K, 2 * SIDE>(tm, vt, b, te, de);
+  if constexpr (OP == NM_OP_NONE) return a;
+  else {
+    const float c = atom_value_s<S, K, 2 * SIDE + 1>(tm, vt, b, te, de);
+    if constexpr (OP == NM_OP_ADD) return a + c; else if constexpr (OP == NM_OP_SUB) return a - c; else return a * c;
+  }
+}
+template <class S, int K>
+__device__ __forceinline__ float term_value_s(const NmTerm& tm, const VarTable& vt, int64_t b, int te, int de) {
+  const float l = side_value_s<S, K, 0>(tm, vt, b, te, de);
+  const float r = side_value_s<S, K, 1>(tm, vt, b, te, de);
+  if constexpr (S::t_cmp(K) == NM_CMP_GT) return r - l; else return l - r;
+}
+template <class S, int K>
+__device__ __forceinline__ float term_penalty_s(float v) {
+  if constexpr (S::t_cmp(K) == NM_CMP_EQ) { if constexpr (S::t_norm(K) == 1) return fabsf(v); else return v * v; }
+  else { const float p = v > 0.f ? v : 0.f; if constexpr (S::t_norm(K) == 1) return p; else return p * p; }
+}
+template <class S, int K>
+__device__ __forceinline__ float term_dpenalty_s(float v) {
+  if constexpr (S::t_cmp(K) == NM_CMP_EQ) {
+    if constexpr (S::t_norm(K) == 1) return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); else return 2.f * v;
+  } else {
+    if constexpr (S::t_norm(K) == 1) return v > 0.f ? 1.f : 0.f; else return v > 0.f ? 2.f * v : 0.f;
+  }
+}
+
+// add this trajectory's penalty sums to tsum[k]
+template <class S>
+__device__ __forceinline__ void score_traj_s(const NmPlan& p, const VarTable& vt, int64_t b,
+                                             float (&tsum)[S::NTERMS > 0 ? S::NTERMS : 1]) {
+  static_for<0, S::NTERMS>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    const NmTerm& tm = p.terms[K];
+    float s0 = 0.f, s1 = 0.f;
+    const int tl = tm.t_len, dl = tm.d_len;
+    int te = 0;
+    for (; te + 1 < tl; te += 2) {                      // two independent chains: loads overlap
+      for (int de = 0; de < dl; ++de) {
+        s0 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+        s1 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 1, de));
+      }
+    }
+    if (te < tl)
+      for (int de = 0; de < dl; ++de) s0 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+    tsum[K] += s0 + s1;
+  });
+}
+
+// d(sum_k coef_k * penalty sums)/d VAR[b, t_idx, 0..DIM)  accumulated into g
+template <class S, int VAR, int DIM, int DIMA>
+__device__ __forceinline__ void term_grad_s(const NmPlan& p, const VarTable& vt, const float* __restrict__ coef,
+                                            int64_t b, int t_idx, float (&g)[DIMA]) {
+  static_for<0, S::NTERMS>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    static_for<0, 4>([&](auto wc) {
+      constexpr int W = decltype(wc)::value;
+      using A = AtomS<S, K, W>;
+      if constexpr (A::VAR == VAR) {
+        const NmTerm& tm = p.terms[K];
+        const NmAtom& at = pick_atom<W>(tm);
+        int te_lo, te_hi;
+        if constexpr (A::TB) {
+          if (t_idx != at.t_start) return;
+          te_lo = 0; te_hi = tm.t_len;
+        } else {
+          const int te = t_idx - at.t_start;
+          if (te < 0 || te >= at.t_len) return;
+          te_lo = te; te_hi = te + 1;
+        }
+        constexpr float side_sign = (W < 2) ? (S::t_cmp(K) == NM_CMP_GT ? -1.f : 1.f) : (S::t_cmp(K) == NM_CMP_GT ? 1.f : -1.f);
+        constexpr int OP = S::t_op(K, W / 2);
+        const float ck = coef[K] * at.scale * side_sign * ((OP == NM_OP_SUB && (W & 1)) ? -1.f : 1.f);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          int de_lo, de_hi;
+          if constexpr (A::DB) { if (d != at.d_start) continue; de_lo = 0; de_hi = tm.d_len; }
+          else { const int de = d - at.d_start; if (de < 0 || de >= at.d_len) continue; de_lo = de; de_hi = de + 1; }
+          float acc = 0.f;
+          for (int te = te_lo; te < te_hi; ++te)
+            for (int de = de_lo; de < de_hi; ++de) {
+              float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+              if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te, de);
+              acc += dv;
+            }
+          g[d] = fmaf(ck, acc, g[d]);
+        }
+      }
+    });
+  });
+}
+
+// out-of-line generic (runtime descriptor) fallbacks: keep them out of the sweeps' register budget
+template <int MAXD, int MODE>
+__device__ __noinline__ void term_grad_accum_ool(const NmPlan& p, const VarTable& vt, const float* __restrict__ coef,
+                                                 int64_t b, int var, int t_idx, int dim, float* g) {
+  float tmp[MAXD];
+#pragma unroll
+  for (int d = 0; d < MAXD; ++d) tmp[d] = 0.f;
+  term_grad_accum<MAXD, MODE>(p, vt, coef, b, var, t_idx, dim, tmp);
+#pragma unroll
+  for (int d = 0; d < MAXD; ++d) if (d < dim) g[d] += tmp[d];
+}
+
 // coefficient of term k in the scalar being differentiated:
 //   (d term_k + d objective|penalty + d loss) * weight / (global element count)
 __device__ __forceinline__ float term_coef(const NmPlan& p, int k, const float* __restrict__ grad_scalars, int64_t b_total) {

@@ -78,9 +78,9 @@ def test_native_library_is_loaded_and_counts_launches():
     lib = _lib.load()
     case = H.make_case("c2", DEV)
     out = case.problem(to_dev(case.make_batch(64, "cpu", 0)))
-    assert lib.nm_last_launch_count() == 4      # weight prep, rollout, term scoring, loss finalise
+    assert lib.nm_last_launch_count() == 3      # weight prep, rollout (+fused scoring), loss finalise
     out["train_loss"].backward()
-    assert lib.nm_last_launch_count() == 4      # weight prep, term gradients, adjoint, gradient finalise
+    assert lib.nm_last_launch_count() == 3      # weight prep, adjoint (+fused term gradients), gradient finalise
     maps = open("/proc/self/maps").read()
     assert "libnm_rollout.so" in maps
 
