@@ -177,6 +177,11 @@ struct GemmCfg {
   static_assert(TILE % TG == 0 && TM % TMB == 0, "tile shape");
 };
 
+#ifndef NM_TUNE_GEMM_UNROLL
+#define NM_TUNE_GEMM_UNROLL 4
+#endif
+constexpr int kGemmUnroll = NM_TUNE_GEMM_UNROLL;   // k-loop unroll of the layer GEMMs (tuning knob)
+
 // epi(ng, traj0, acc[TMB][TN]) is invoked once per register block; output j of the thread is
 // n = ng + NG*j, stored weight column ng*TN + j.
 template <int KC, int N, int TILE, int THREADS, int LD, class Epi>
@@ -195,7 +200,7 @@ __device__ __forceinline__ void gemm_phase(const float* __restrict__ W, const fl
     for (int i = 0; i < G::TMB; ++i)
 #pragma unroll
       for (int j = 0; j < G::TN; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
+#pragma unroll kGemmUnroll
     for (int c = 0; c < KC; ++c) {
       float w[G::TN], a[G::TMB];
       ld_vec<G::TN>(w, wp + c * G::NP);

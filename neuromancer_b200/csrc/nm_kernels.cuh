@@ -691,8 +691,13 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
     const int64_t b = b_raw < args.B ? b_raw : args.B - 1;
 
     float lam[NX];                                              // dL/dx_{t+1}
+    float x_pre[NX];                                            // x_t fetched one step ahead (L2 latency hidden)
 #pragma unroll
-    for (int i = 0; i < NX; ++i) lam[i] = 0.f;
+    for (int i = 0; i < NX; ++i) { lam[i] = 0.f; x_pre[i] = 0.f; }
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + (T - 1)) * NX + i);
+    }
     if (valid) {
       if (pre) {
 #pragma unroll
@@ -718,7 +723,11 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
       for (int i = 0; i < NX; ++i) { x[i] = 0.f; gx[i] = 0.f; }
       if (owner) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = __ldg(args.x_traj + (b * (T + 1) + t) * NX + i);
+        for (int i = 0; i < NX; ++i) x[i] = x_pre[i];
+        if (t > 0) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
+        }
         if constexpr (S::HAS_OUTPUT) {
 #pragma unroll
           for (int j = 0; j < NY; ++j) {
