@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NM_ABI_VERSION 3
+#define NM_ABI_VERSION 4
 
 #define NM_MAX_LAYERS 8   /* linear layers per MLP                                   */
 #define NM_MAX_SEGS   8   /* concatenated inputs of the policy (blocks.py:39-43)     */
@@ -60,6 +60,15 @@ extern "C" {
 #define NM_SEG_STATE  0   /* x_i  (pre-update state)            */
 #define NM_SEG_OUTPUT 1   /* y_i  (same-step output of y = Cx)  */
 #define NM_SEG_EXO    2   /* exo[index][:, i, :]                */
+#define NM_SEG_PREVIEW 3  /* exo[index][:, i : i+1+preview_len, :] flattened time-major, right-padded
+                           * by NmPlan.pad_mode when the window runs past the signal (SystemPreview,
+                           * reference system.py:325-367)                                       */
+
+/* torch.nn.functional.pad modes of SystemPreview (system.py:297,341-345) */
+#define NM_PAD_CONSTANT  0
+#define NM_PAD_REPLICATE 1
+#define NM_PAD_CIRCULAR  2
+#define NM_PAD_REFLECT   3
 
 /* dynamics */
 #define NM_DYN_SSM 0      /* discrete x+ = A x + B u [+ E d]            (ode.py:7-51)        */
@@ -109,8 +118,8 @@ typedef struct NmMlp {
 typedef struct NmSegment {
   int32_t kind;    /* NM_SEG_*                    */
   int32_t index;   /* exo index for NM_SEG_EXO    */
-  int32_t width;
-  int32_t _pad;
+  int32_t width;         /* columns this segment contributes to the policy input         */
+  int32_t preview_len;   /* NM_SEG_PREVIEW: L (window = L+1 time entries), else 0        */
 } NmSegment;
 
 typedef struct NmExo {
@@ -170,6 +179,8 @@ typedef struct NmPlan {
   int32_t n_terms;
   NmTerm  terms[NM_MAX_TERMS];
   int64_t n_params;          /* total floats in params_flat                    */
+  int32_t pad_mode;          /* NM_PAD_* for NM_SEG_PREVIEW segments           */
+  float   pad_value;         /* NM_PAD_CONSTANT fill value                     */
 } NmPlan;
 
 /* Library / build identification. */

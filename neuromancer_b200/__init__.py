@@ -12,6 +12,6 @@ from .constraint import Constraint, Objective, Variable, variable  # noqa: F401
 from .dataset import DictDataset  # noqa: F401
 from .loss import PenaltyLoss  # noqa: F401
 from .problem import Problem  # noqa: F401
-from .system import Node, System  # noqa: F401
+from .system import Node, System, SystemPreview  # noqa: F401
 
 __version__ = "0.1.0"

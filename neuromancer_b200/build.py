@@ -59,6 +59,9 @@ def signature_of(p: L.NmPlan) -> str:
         parts = []
         for i in range(p.n_segs):
             g = p.segs[i]
+            if g.kind == L.NM_SEG_PREVIEW:
+                parts.append(f"p{g.index}.{g.width}.{p.exo[g.index].width}")
+                continue
             ch = {L.NM_SEG_STATE: "x", L.NM_SEG_OUTPUT: "y"}.get(g.kind, "e")
             parts.append(f"{ch}{g.index if g.kind == L.NM_SEG_EXO else 0}.{g.width}")
         s += ",".join(parts)
@@ -171,6 +174,7 @@ def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
            _table("seg_kind", [s.kind for s in segs]),
            _table("seg_index", [s.index for s in segs]),
            _table("seg_width", [s.width for s in segs]),
+           _table("seg_sub", [(p.exo[s.index].width if s.kind in (L.NM_SEG_EXO, L.NM_SEG_PREVIEW) else s.width) for s in segs]),
            f"  static constexpr int DYN = {p.dyn_kind}, INTEG = {integ}, RHS = {p.rhs_kind}, DIST_EXO = {p.dist_exo};\n",
            f"  static constexpr const char* signature() {{ return \"{sig}\"; }}\n", _term_tables(p), "};\n"]
     return "".join(out)

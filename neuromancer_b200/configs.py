@@ -26,7 +26,7 @@ from .loss import PenaltyLoss
 from .modules import blocks
 from .modules.activations import activations
 from .problem import Problem
-from .system import Node, System
+from .system import Node, System, SystemPreview
 
 
 @dataclass
@@ -339,14 +339,71 @@ def t_node_policy_euler(seed=0, nsteps=6) -> Case:
     return Case("t_node_policy_euler", problem, system, nsteps, 150, make_batch, 0, 0)
 
 
+def _t_preview(pad_mode, seed=0, nsteps=9) -> Case:
+    """TwoTank tracking with a previewing policy (examples/control/Part_3_ref_tracking_ODE.py:93-105)."""
+    torch.manual_seed(seed)
+    plant = ode.TwoTankParam()
+    plant.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
+    plant.c2 = nn.Parameter(torch.tensor(0.04), requires_grad=False)
+    model = Node(integrators.RK4(plant, h=1.0), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=2 + 2 * 6 + 1 * 3, outsize=2, hsizes=[16], nonlin=activations["gelu"], min=0., max=1.)
+    policy = Node(net, ["x", "r", "p"], ["u"], name="policy")
+    system = SystemPreview([policy, model], name="sys", nsteps=nsteps, preview_keys_map={"r": ["policy"], "p": ["policy"]},
+                           preview_length={"r": 5, "p": 2}, pad_mode=pad_mode, pad_constant=0.25)
+    x, rr = variable("x"), variable("r")
+    track = 5. * ((x[:, 1:, :] == rr[:, :nsteps, :]) ^ 2)
+    lo = 10. * (x > 0.)
+    track.name, lo.name = "track", "lo"
+    problem = Problem([system], PenaltyLoss([track], [lo]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 9700 + s)
+        return {"x": torch.rand(Bn, 1, 2, generator=g).to(device), "r": torch.rand(Bn, nsteps + 2, 2, generator=g).to(device),
+                "p": torch.rand(Bn, nsteps, 1, generator=g).to(device), "name": "train"}
+    return Case(f"t_preview_{pad_mode}", problem, system, nsteps, 140, make_batch, 0, 0)
+
+
+def t_preview_replicate(seed=0, **kw): return _t_preview("replicate", seed, **kw)
+def t_preview_circular(seed=0, **kw): return _t_preview("circular", seed, **kw)
+def t_preview_constant(seed=0, **kw): return _t_preview("constant", seed, **kw)
+def t_preview_reflect(seed=0, **kw): return _t_preview("reflect", seed, **kw)
+
+
+def t_preview_index(seed=0, nsteps=7, pad_mode="replicate") -> Case:
+    """Indexing probe: a bias-free one-layer policy whose weight rows are one-hot, feeding x+ = u.  The
+    state trajectory then consists of *copies* of preview-window entries, so the window / padding index
+    arithmetic can be checked bit-exactly (tests/test_parity_gpu.py)."""
+    torch.manual_seed(seed)
+    nx = nu = 2
+    L_s, d_s = 3, 2                                    # signal `s`: window 4, width 2 -> 8 policy inputs
+    net = blocks.MLP(insize=(L_s + 1) * d_s, outsize=nu, hsizes=[], bias=False, linear_map=nn.Linear, nonlin=nn.ReLU)
+    ssm = ode.SSM(_frozen_linear(torch.zeros(nx, nx)), _frozen_linear(torch.eye(nx)), nx, nu)
+    system = SystemPreview([Node(net, ["s"], ["u"], name="policy"), Node(ssm, ["x", "u"], ["x"], name="plant")],
+                           name="sys", nsteps=nsteps, preview_keys_map={"s": ["policy"]}, preview_length={"s": L_s},
+                           pad_mode=pad_mode, pad_constant=-7.5)
+    obj = (variable("x") == 0.) ^ 2
+    obj.name = "obj"
+    problem = Problem([system], PenaltyLoss([obj], []))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 9900 + s)
+        return {"x": torch.zeros(Bn, 1, nx, device=device), "s": torch.randn(Bn, nsteps, d_s, generator=g).to(device),
+                "name": "train"}
+    return Case("t_preview_index", problem, system, nsteps, 64, make_batch, 0, 0)
+
+
 CASES: Dict[str, Callable[..., Case]] = {
     "c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
     "t_vdp_rk4_tanh_clamp": t_vdp_rk4_tanh_clamp, "t_vdp_euler_elu": t_vdp_euler_elu,
     "t_twotank_rk2_sigmoid": t_twotank_rk2_sigmoid, "t_ssm_softplus": t_ssm_softplus,
     "t_node_policy_euler": t_node_policy_euler,
+    "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
+    "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
 }
-AOT_CASES = list(CASES)
+# shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
+EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index}
+AOT_CASES = list(CASES) + list(EXTRA_CASES)
 
 
 def build_case(name: str, batch=None, device="cpu", seed=0, **kw) -> Case:
-    return CASES[name](seed=seed, **kw)
+    return {**CASES, **EXTRA_CASES}[name](seed=seed, **kw)

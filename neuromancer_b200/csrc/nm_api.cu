@@ -51,6 +51,11 @@ int validate(const NmPlan* p) {
   for (int i = 0; i < p->n_segs; ++i) {
     const NmSegment& s = p->segs[i];
     if (s.kind == NM_SEG_EXO && (s.index < 0 || s.index >= p->n_exo || p->exo[s.index].width != s.width)) { nm_set_error("policy segment refers to a bad exo input"); return NM_ERR_BAD_PLAN; }
+    if (s.kind == NM_SEG_PREVIEW) {
+      if (s.index < 0 || s.index >= p->n_exo || s.preview_len < 0 || p->exo[s.index].width * (s.preview_len + 1) != s.width) { nm_set_error("preview segment shape mismatch"); return NM_ERR_BAD_PLAN; }
+      if (p->pad_mode < NM_PAD_CONSTANT || p->pad_mode > NM_PAD_REFLECT) { nm_set_error("bad pad_mode"); return NM_ERR_BAD_PLAN; }
+      if (p->pad_mode == NM_PAD_REFLECT && s.preview_len >= p->exo[s.index].steps) { nm_set_error("reflect padding needs preview_len < signal length"); return NM_ERR_BAD_PLAN; }
+    }
   }
   for (int e = 0; e < p->n_exo; ++e)
     if (p->exo[e].width < 1 || p->exo[e].steps < 1) { nm_set_error("exo shape invalid"); return NM_ERR_BAD_PLAN; }
@@ -113,7 +118,8 @@ std::string make_signature(const NmPlan* p) {
     s += "_seg";
     for (int i = 0; i < p->n_segs; ++i) {
       const NmSegment& g = p->segs[i];
-      std::snprintf(buf, sizeof(buf), "%s%c%d.%d", i ? "," : "", g.kind == NM_SEG_STATE ? 'x' : (g.kind == NM_SEG_OUTPUT ? 'y' : 'e'), g.kind == NM_SEG_EXO ? g.index : 0, g.width);
+      if (g.kind == NM_SEG_PREVIEW) std::snprintf(buf, sizeof(buf), "%sp%d.%d.%d", i ? "," : "", g.index, g.width, p->exo[g.index].width);
+      else std::snprintf(buf, sizeof(buf), "%s%c%d.%d", i ? "," : "", g.kind == NM_SEG_STATE ? 'x' : (g.kind == NM_SEG_OUTPUT ? 'y' : 'e'), g.kind == NM_SEG_EXO ? g.index : 0, g.width);
       s += buf;
     }
   }

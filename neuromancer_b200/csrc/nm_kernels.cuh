@@ -81,7 +81,7 @@ struct KCfg {
   // gradient is needed for the policy inputs up to the end of the last state/output segment
   static constexpr int pol_gw0() {
     int off = 0, gw = 0;
-    for (int i = 0; i < S::NSEG; ++i) { off += S::seg_width(i); if (S::seg_kind(i) != NM_SEG_EXO) gw = off; }
+    for (int i = 0; i < S::NSEG; ++i) { off += S::seg_width(i); if (S::seg_kind(i) == NM_SEG_STATE || S::seg_kind(i) == NM_SEG_OUTPUT) gw = off; }
     return gw;
   }
   using PolCfg = std::conditional_t<HAS_POL, MlpCfg<typename S::Pol, TILE, THREADS, pol_gw0()>, NoMlpCfg<TILE, THREADS>>;
@@ -401,6 +401,27 @@ __device__ __forceinline__ void build_policy_input(const NmPlan& p, const float*
     } else if constexpr (S::seg_kind(s) == NM_SEG_OUTPUT) {
 #pragma unroll
       for (int i = 0; i < W; ++i) a0[(off + i) * LD + tid] = y[i];
+    } else if constexpr (S::seg_kind(s) == NM_SEG_PREVIEW) {
+      // SystemPreview window  exo[e][:, t : t+1+L, :]  flattened time-major; entries past the signal are
+      // right-padding of the FULL signal by torch.nn.functional.pad(mode) (reference system.py:341-345)
+      constexpr int e = S::seg_index(s);
+      constexpr int D = S::seg_sub(s);
+      const int Tk = p.exo[e].steps;
+      const float* __restrict__ base = exo[e] + b * Tk * D;
+#pragma unroll 4
+      for (int j = 0; j < W / D; ++j) {
+        int ts = t + j;
+        bool fill = false;
+        if (ts >= Tk) {
+          if (p.pad_mode == NM_PAD_REPLICATE) ts = Tk - 1;
+          else if (p.pad_mode == NM_PAD_CIRCULAR) ts -= Tk;            // pad length L <= ... one wrap (ts < Tk + L)
+          else if (p.pad_mode == NM_PAD_REFLECT) ts = 2 * (Tk - 1) - ts;
+          else fill = true;
+          if (p.pad_mode == NM_PAD_CIRCULAR) ts %= Tk;
+        }
+#pragma unroll
+        for (int dd = 0; dd < D; ++dd) a0[(off + j * D + dd) * LD + tid] = fill ? p.pad_value : __ldg(base + ts * D + dd);
+      }
     } else {
       constexpr int e = S::seg_index(s);
       const float* __restrict__ src = exo[e] + (b * p.exo[e].steps + t) * W;

@@ -296,6 +296,9 @@ class SystemLayout:
     policy: Optional[_blocks.MLP] = None
     rhs_mlp: Optional[_blocks.MLP] = None
     policy_inputs: List[str] = field(default_factory=list)
+    policy_preview: Dict[str, int] = field(default_factory=dict)   # input key -> preview length L
+    pad_mode: int = 0
+    pad_value: float = 0.0
     dynamics: object = None
     output_map: object = None
     nx: int = 0
@@ -320,7 +323,11 @@ def _classify(node):
         "linear output map). neuromancer_b200 has no eager fallback for System.forward.")
 
 
-def recognise(nodes) -> SystemLayout:
+_PAD_MODES = {"constant": L.NM_PAD_CONSTANT, "replicate": L.NM_PAD_REPLICATE, "circular": L.NM_PAD_CIRCULAR,
+              "reflect": L.NM_PAD_REFLECT}
+
+
+def recognise(nodes, preview=None) -> SystemLayout:
     kinds = [_classify(n) for n in nodes]
     if kinds.count("dynamics") != 1:
         raise PlanError(f"a fused System needs exactly one dynamics node, found {kinds.count('dynamics')}")
@@ -369,6 +376,23 @@ def recognise(nodes) -> SystemLayout:
             raise PlanError(f"integrator dynamics with extra inputs {extra} are not fused")
         if isinstance(fn.block, _blocks.MLP):
             lay.rhs_mlp = fn.block
+
+    if preview is not None:
+        keys_map, lengths, mode, constant = preview
+        if mode not in _PAD_MODES:
+            raise PlanError(f"pad_mode '{mode}' is not one of {sorted(_PAD_MODES)}")
+        lay.pad_mode, lay.pad_value = _PAD_MODES[mode], float(constant or 0.0)
+        for key, names in keys_map.items():
+            for node in nodes:
+                if node.name not in names or key not in node.input_keys:
+                    continue
+                if node is not pol:
+                    raise PlanError(f"preview of '{key}' by node '{node.name}': only the policy node may preview")
+                if key in (lay.state_key, lay.output_key, lay.action_key):
+                    raise PlanError(f"'{key}' is produced by the rollout and cannot be previewed")
+                if lengths.get(key) is None:
+                    raise PlanError(f"preview_length['{key}'] is not set")
+                lay.policy_preview[key] = int(lengths[key])
 
     def add_exo(key):
         if key not in lay.exo_keys:
@@ -419,7 +443,7 @@ class RolloutPlan:
             shp = shapes[k]
             if len(shp) != 3:
                 raise PlanError(f"input '{k}' must be [batch, time, dim], got {shp}")
-            if shp[1] < self.nsteps:
+            if shp[1] < self.nsteps:     # previewed signals too: the window at step i starts at entry i
                 raise PlanError(f"input '{k}' has {shp[1]} time entries < nsteps={self.nsteps}")
             p.exo[i].width, p.exo[i].steps = shp[2], shp[1]
 
@@ -439,6 +463,16 @@ class RolloutPlan:
                     seg.kind, seg.index, seg.width = L.NM_SEG_STATE, 0, lay.nx
                 elif k == lay.output_key:
                     seg.kind, seg.index, seg.width = L.NM_SEG_OUTPUT, 0, lay.ny
+                elif k in lay.policy_preview:
+                    j = lay.exo_keys.index(k)
+                    plen = lay.policy_preview[k]
+                    if plen < 0:
+                        raise PlanError("preview length must be >= 0")
+                    if lay.pad_mode == L.NM_PAD_REFLECT and plen >= p.exo[j].steps:
+                        raise PlanError("reflect padding needs preview_length < signal length")
+                    if lay.pad_mode == L.NM_PAD_CIRCULAR and plen > p.exo[j].steps:
+                        raise PlanError("circular padding needs preview_length <= signal length")
+                    seg.kind, seg.index, seg.width, seg.preview_len = L.NM_SEG_PREVIEW, j, p.exo[j].width * (plen + 1), plen
                 else:
                     j = lay.exo_keys.index(k)
                     seg.kind, seg.index, seg.width = L.NM_SEG_EXO, j, p.exo[j].width
@@ -494,6 +528,7 @@ class RolloutPlan:
             else:
                 raise PlanError(f"right-hand side {type(rhs).__name__} has no fused implementation")
         p.n_params = offset
+        p.pad_mode, p.pad_value = lay.pad_mode, lay.pad_value
 
         # loss terms --------------------------------------------------------------------
         self.var_ids: Dict[str, int] = {lay.state_key: L.NM_VAR_X}

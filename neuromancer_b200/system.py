@@ -84,9 +84,13 @@ class System(nn.Module):
         return data
 
     # -- lowering -------------------------------------------------------------------------
+    def _preview_spec(self):
+        """``(preview_keys_map, preview_length, pad_mode, pad_constant)`` -- None for a plain System."""
+        return None
+
     def layout(self) -> _plan.SystemLayout:
         if self._layout is None:
-            self._layout = _plan.recognise(list(self.nodes))
+            self._layout = _plan.recognise(list(self.nodes), preview=self._preview_spec())
         return self._layout
 
     def resolve_nsteps(self, data):
@@ -131,3 +135,25 @@ class System(nn.Module):
 
     def show(self, figname=None):
         raise NotImplementedError("graph drawing (pydot) is outside the hot-path scope")
+
+
+class SystemPreview(System):
+    """``System`` whose nodes may read a *window* of future values of known signals
+    (reference system.py:293-367): for every key ``k`` in ``preview_keys_map`` and every node named in
+    ``preview_keys_map[k]`` the node receives ``data[k][:, i : i+1+L_k, :]`` flattened time-major to
+    ``[batch, (L_k+1)*d]``; where the window runs past the signal it is right-padded the way
+    ``torch.nn.functional.pad(mode=pad_mode)`` pads the whole signal (replicate / circular / constant /
+    reflect).  The fused rollout gathers the window inside the kernel (pure indexing, bit-exact) instead
+    of materialising look-ahead tensors, which cuts the exogenous HBM traffic by the window length."""
+
+    def __init__(self, nodes, preview_keys_map: dict = {}, preview_length: dict = None, pad_mode: str = "circular",
+                 pad_constant=0.0, name=None, nstep_key="X", init_func=None, nsteps=None):
+        super().__init__(nodes=nodes, name=name, nstep_key=nstep_key, init_func=init_func, nsteps=nsteps)
+        self.preview_keys_map = preview_keys_map
+        self.pad_mode = pad_mode
+        self.pad_constant = pad_constant if pad_mode == "constant" else None
+        self.preview_length = (preview_length if preview_length is not None
+                               else {k: nsteps for k in preview_keys_map})
+
+    def _preview_spec(self):
+        return self.preview_keys_map, self.preview_length, self.pad_mode, self.pad_constant

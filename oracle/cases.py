@@ -165,10 +165,34 @@ def t_node_policy_euler(params, nsteps=6) -> dict:
     return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
 
 
+def _t_preview(params, nsteps, pad_mode):
+    """examples/control/Part_3_ref_tracking_ODE.py:93-105 shape: TwoTank + RK4 with a policy that previews the
+    reference `r` (2 signals, window L+1 = 6) and a 1-d price signal `p` (window 3); `r` is SHORTER than
+    nsteps + L so the window runs into the padding."""
+    c1_, c2_ = _t(0.08, params[0]), _t(0.04, params[0])
+    rhs = lambda x, u: O.rhs_twotank(x, u, c1_, c2_)
+    nodes = [dict(name="policy", fn=lambda x, r, pz: O.bounds_scaling(O.mlp_forward(params, torch.cat([x, r, pz], dim=-1), "gelu"), 0., 1.),
+                  inputs=["x", "r", "p"], outputs=["u"]),
+             dict(name="model", fn=lambda x, u: O.rk4_step(rhs, x, 1.0, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("track", True, "eq", 2, 5., lambda d: d["x"][:, 1:, :], lambda d: d["r"][:, :nsteps, :]),
+             _term("lo", False, "gt", 1, 10., lambda d: d["x"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"],
+                preview=dict(keys_map={"r": ["policy"], "p": ["policy"]}, length={"r": 5, "p": 2}, pad_mode=pad_mode,
+                             pad_constant=0.25 if pad_mode == "constant" else None))
+
+
+def t_preview_replicate(params, nsteps=9): return _t_preview(params, nsteps, "replicate")
+def t_preview_circular(params, nsteps=9): return _t_preview(params, nsteps, "circular")
+def t_preview_constant(params, nsteps=9): return _t_preview(params, nsteps, "constant")
+def t_preview_reflect(params, nsteps=9): return _t_preview(params, nsteps, "reflect")
+
+
 CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_vdp_rk4_tanh_clamp": t_vdp_rk4_tanh_clamp, "t_vdp_euler_elu": t_vdp_euler_elu,
          "t_twotank_rk2_sigmoid": t_twotank_rk2_sigmoid, "t_ssm_softplus": t_ssm_softplus,
-         "t_node_policy_euler": t_node_policy_euler}
+         "t_node_policy_euler": t_node_policy_euler,
+         "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
+         "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect}
 
 
 def build(name: str, params: List[torch.Tensor], **kw) -> dict:

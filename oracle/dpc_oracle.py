@@ -156,6 +156,40 @@ def system_forward(nodes: List[dict], data: Dict[str, torch.Tensor], nsteps: int
     return data
 
 
+def preview_window(sig: torch.Tensor, i: int, length: int, pad_mode: str, pad_constant=None) -> torch.Tensor:
+    """``SystemPreview.get_data_with_preview`` (reference system.py:325-345): the window
+    ``sig[:, i : i+1+length, :]``; if it is short, the FULL signal is right-padded by ``length`` samples
+    with ``torch.nn.functional.pad(mode=pad_mode)`` and the window is taken from that."""
+    data = sig[:, i:i + 1 + length, :]
+    if data.shape[1] < length + 1:
+        data = F.pad(sig, (0, 0, 0, length), mode=pad_mode, value=pad_constant)[:, i:i + 1 + length, :]
+    return data
+
+
+def system_preview_forward(nodes: List[dict], data: Dict[str, torch.Tensor], nsteps: int, preview_keys_map: dict,
+                           preview_length: dict, pad_mode: str, pad_constant=None) -> Dict[str, torch.Tensor]:
+    """``SystemPreview.forward`` (reference system.py:348-367).  ``nodes`` entries carry a ``name``."""
+    data = dict(data)
+    for i in range(nsteps):
+        for node in nodes:
+            args = []
+            for k in node["inputs"]:
+                if k in preview_keys_map and node["name"] in preview_keys_map[k]:
+                    win = preview_window(data[k], i, preview_length[k], pad_mode, pad_constant)
+                    args.append(win.reshape(data[k].size(0), -1))
+                else:
+                    args.append(data[k][:, i])
+            out = node["fn"](*args)
+            if not isinstance(out, tuple):
+                out = (out,)
+            for k, v in zip(node["outputs"], out):
+                if k not in data:
+                    data[k] = v[:, None, :]
+                else:
+                    data[k] = torch.cat([data[k], v[:, None, :]], dim=1)
+    return data
+
+
 # ------------------------------------------------------------------------------------------ loss
 def compare(cmp: str, norm: int, left: torch.Tensor, right: torch.Tensor):
     """``LT/GT/Eq.forward`` (reference constraint.py:85-98, 122-134, 157-173) -> (loss, value, violation)"""
@@ -209,7 +243,12 @@ def penalty_loss(terms: List[dict], data: Dict[str, torch.Tensor]) -> Dict[str, 
 def run_case(spec: dict, data: Dict[str, torch.Tensor], want_grad: bool = True) -> Dict[str, object]:
     """Forward (+ backward) of one problem.  ``spec`` = {nodes, terms, nsteps, params (list of leaf
     tensors), traj_keys}.  Returns trajectories, per-term scalars, loss and parameter gradients."""
-    traj = system_forward(spec["nodes"], data, spec["nsteps"])
+    if "preview" in spec:
+        pv = spec["preview"]
+        traj = system_preview_forward(spec["nodes"], data, spec["nsteps"], pv["keys_map"], pv["length"], pv["pad_mode"],
+                                      pv.get("pad_constant"))
+    else:
+        traj = system_forward(spec["nodes"], data, spec["nsteps"])
     scored = penalty_loss(spec["terms"], traj)
     res = {"traj": {k: traj[k] for k in spec["traj_keys"]},
            "terms": {t["name"]: scored[t["name"]] for t in spec["terms"]},

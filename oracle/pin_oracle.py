@@ -278,11 +278,39 @@ def ref_t_node_policy_euler(ns, nsteps=6):
     return problem, _mlp_params(net) + _mlp_params(rhs), data, ["x", "u"], ["obj", "eff"]
 
 
+def _ref_t_preview(ns, pad_mode, nsteps=9):
+    ode = ns.ode.TwoTankParam()
+    ode.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
+    ode.c2 = nn.Parameter(torch.tensor(0.04), requires_grad=False)
+    model = ns.system.Node(ns.integrators.RK4(ode, h=1.0), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=2 + 2 * 6 + 1 * 3, outsize=2, hsizes=[16], nonlin=ns.activations.activations["gelu"], min=0., max=1.)
+    policy = ns.system.Node(net, ["x", "r", "p"], ["u"], name="policy")
+    system = ns.system.SystemPreview([policy, model], name="sys", nsteps=nsteps, preview_keys_map={"r": ["policy"], "p": ["policy"]},
+                                     preview_length={"r": 5, "p": 2}, pad_mode=pad_mode, pad_constant=0.25)
+    v = ns.constraint.variable
+    x, rr = v("x"), v("r")
+    track = 5. * ((x[:, 1:, :] == rr[:, :nsteps, :]) ^ 2)
+    lo = 10. * (x > 0.)
+    _name([(track, "track"), (lo, "lo")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([track], [lo]))
+    data = lambda B_, g: {"x": torch.rand(B_, 1, 2, generator=g), "r": torch.rand(B_, nsteps + 2, 2, generator=g),
+                          "p": torch.rand(B_, nsteps, 1, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u"], ["track", "lo"]
+
+
+def ref_t_preview_replicate(ns): return _ref_t_preview(ns, "replicate")
+def ref_t_preview_circular(ns): return _ref_t_preview(ns, "circular")
+def ref_t_preview_constant(ns): return _ref_t_preview(ns, "constant")
+def ref_t_preview_reflect(ns): return _ref_t_preview(ns, "reflect")
+
+
 REF_BUILDERS = {
     "c1": (ref_c1, 16), "c2": (ref_c2, 16), "c3": (ref_c3, 12), "c4": (ref_c4, 6), "c5": (ref_c5, 6),
     "t_vdp_rk4_tanh_clamp": (ref_t_vdp_rk4_tanh_clamp, 16), "t_vdp_euler_elu": (ref_t_vdp_euler_elu, 16),
     "t_twotank_rk2_sigmoid": (ref_t_twotank_rk2_sigmoid, 16), "t_ssm_softplus": (ref_t_ssm_softplus, 16),
     "t_node_policy_euler": (ref_t_node_policy_euler, 16),
+    "t_preview_replicate": (ref_t_preview_replicate, 12), "t_preview_circular": (ref_t_preview_circular, 12),
+    "t_preview_constant": (ref_t_preview_constant, 12), "t_preview_reflect": (ref_t_preview_reflect, 12),
 }
 
 

@@ -205,3 +205,34 @@ def test_mask_conventions_bit_exact():
     v2 = torch.nn.functional.l1_loss(xr[:, [0], :], torch.full_like(xr[:, [0], :], 2.0))
     (v1 + v2).backward()
     assert torch.equal(x0.grad.cpu(), xr.grad), (x0.grad, xr.grad)
+
+
+@pytest.mark.parametrize("pad_mode", ["replicate", "circular", "constant", "reflect"])
+def test_preview_window_indexing_bit_exact(pad_mode):
+    """SystemPreview (reference system.py:325-367) is pure indexing: with a one-hot linear policy and
+    x+ = u the state trajectory must equal, bit for bit, the entries torch.nn.functional.pad + slicing
+    select -- including windows that run past the end of the signal."""
+    import torch.nn.functional as F
+    case = H.make_case("t_preview_index", DEV, pad_mode=pad_mode)
+    T, L, d = case.nsteps, 3, 2
+    batch_cpu = case.make_batch(37, "cpu", 1)
+    net = case.system.nodes[0].callable
+    for pick in [(0, 1), (5, 2), (7, 6)]:                     # which flattened window entry feeds u_0 / u_1
+        with torch.no_grad():
+            w = torch.zeros(2, (L + 1) * d)
+            w[0, pick[0]] = 1.0
+            w[1, pick[1]] = 1.0
+            net.linear[0].weight.copy_(w.to(DEV))
+        with torch.no_grad():
+            out = case.system({k: v.to(DEV) for k, v in batch_cpu.items() if k != "name"})
+        sig = batch_cpu["s"]
+        padded = F.pad(sig, (0, 0, 0, L), mode=pad_mode, value=-7.5 if pad_mode == "constant" else None)
+        want = torch.zeros(37, T + 1, 2)
+        for i in range(T):
+            win = sig[:, i:i + 1 + L, :]
+            if win.shape[1] < L + 1:
+                win = padded[:, i:i + 1 + L, :]
+            flat = win.reshape(37, -1)
+            want[:, i + 1, 0] = flat[:, pick[0]]
+            want[:, i + 1, 1] = flat[:, pick[1]]
+        assert torch.equal(out["x"].cpu(), want), (pad_mode, pick)
