@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NM_ABI_VERSION 4
+#define NM_ABI_VERSION 5
 
 #define NM_MAX_LAYERS 8   /* linear layers per MLP                                   */
 #define NM_MAX_SEGS   8   /* concatenated inputs of the policy (blocks.py:39-43)     */
@@ -77,6 +77,10 @@ extern "C" {
 #define NM_INT_EULER 0    /* integrators.py:144-156 */
 #define NM_INT_RK4   1    /* integrators.py:196-211 */
 #define NM_INT_RK2   2    /* integrators.py:180-193 */
+#define NM_INT_EULER_TRAP 3 /* integrators.py:159-177  predictor Euler, corrector trapezoid            */
+#define NM_INT_RK4_TRAP   4 /* integrators.py:214-235  predictor RK4, corrector trapezoid              */
+#define NM_INT_LUTHER     5 /* integrators.py:238-264  Luther's 6th-order 7-stage method               */
+#define NM_INT_RKF        6 /* integrators.py:267-301  Runge-Kutta-Fehlberg, 5th-order output          */
 
 #define NM_RHS_NONE     0
 #define NM_RHS_TWOTANK  1 /* ode.py:216-237; rhs_const = {c1, c2}                            */
@@ -84,6 +88,12 @@ extern "C" {
 #define NM_RHS_CVDP     3 /* ring of nx/2 coupled VanDerPolControl; rhs_const = {mu, kappa}  */
 #define NM_RHS_MLP      4 /* blocks.MLP as the right-hand side (neural ODE)                  */
 #define NM_RHS_LINEAR   5 /* dx = A x + B u                                                  */
+#define NM_RHS_LORENZ_CTRL 6 /* ode.py:393-414; rhs_const = {rho, sigma, beta}; nu = 2               */
+#define NM_RHS_CSTR     7 /* ode.py:417-461; rhs_const = {q/V, Caf, Tf, k0, E/R, mdelH/(rho Cp), UA/V/rho/Cp} */
+#define NM_RHS_DUFFING  8 /* ode.py:240-262; rhs_const = {alpha, beta, delta, gamma, omega}; input = time */
+#define NM_RHS_BRUSSELATOR 9 /* ode.py:265-281; rhs_const = {alpha, beta}; autonomous                */
+#define NM_RHS_LOTKA_VOLTERRA 10 /* ode.py:333-349; rhs_const = {alpha}; autonomous                  */
+#define NM_RHS_LORENZ   11 /* ode.py:371-391; rhs_const = {rho, sigma, beta}; autonomous             */
 
 /* variables a loss-term atom can refer to */
 #define NM_VAR_CONST (-1)
@@ -167,6 +177,7 @@ typedef struct NmPlan {
   int32_t integrator;        /* NM_INT_*                                       */
   int32_t rhs_kind;          /* NM_RHS_*                                       */
   int32_t dist_exo;          /* exo index of the disturbance d of an SSM, or -1 */
+  int32_t act_exo;           /* open loop: exo index the action u_i is read from (no policy), or -1 */
   float   h;                 /* integration step                               */
   float   rhs_const[8];
   NmMlp   rhs_mlp;

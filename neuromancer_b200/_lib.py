@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-NM_ABI_VERSION = 4
+NM_ABI_VERSION = 5
 NM_MAX_LAYERS, NM_MAX_SEGS, NM_MAX_EXO, NM_MAX_TERMS, NM_MAX_DIM = 8, 8, 8, 16, 16
 
 NM_OK, NM_ERR_BAD_PLAN, NM_ERR_NO_KERNEL, NM_ERR_CUDA, NM_ERR_WORKSPACE, NM_ERR_ABI = 0, -1, -2, -3, -4, -5
@@ -19,7 +19,7 @@ NM_BOUNDS_NONE, NM_BOUNDS_SIGMOID_SCALE, NM_BOUNDS_RELU_CLAMP = 0, 1, 2
 NM_SEG_STATE, NM_SEG_OUTPUT, NM_SEG_EXO, NM_SEG_PREVIEW = 0, 1, 2, 3
 NM_PAD_CONSTANT, NM_PAD_REPLICATE, NM_PAD_CIRCULAR, NM_PAD_REFLECT = 0, 1, 2, 3
 NM_DYN_SSM, NM_DYN_ODE = 0, 1
-NM_INT_EULER, NM_INT_RK4, NM_INT_RK2 = 0, 1, 2
+NM_INT_EULER, NM_INT_RK4, NM_INT_RK2, NM_INT_EULER_TRAP, NM_INT_RK4_TRAP, NM_INT_LUTHER, NM_INT_RKF = 0, 1, 2, 3, 4, 5, 6
 NM_RHS_NONE, NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 0, 1, 2, 3, 4, 5
 NM_VAR_CONST, NM_VAR_X, NM_VAR_U, NM_VAR_Y, NM_VAR_EXO0 = -1, 0, 1, 2, 3
 NM_OP_NONE, NM_OP_ADD, NM_OP_SUB, NM_OP_MUL = 0, 1, 2, 3
@@ -65,7 +65,7 @@ class NmPlan(C.Structure):
                 ("nsteps", C.c_int32), ("has_policy", C.c_int32), ("has_output", C.c_int32),
                 ("n_segs", C.c_int32), ("segs", NmSegment * NM_MAX_SEGS), ("policy", NmMlp),
                 ("dyn_kind", C.c_int32), ("integrator", C.c_int32), ("rhs_kind", C.c_int32),
-                ("dist_exo", C.c_int32), ("h", C.c_float), ("rhs_const", C.c_float * 8),
+                ("dist_exo", C.c_int32), ("act_exo", C.c_int32), ("h", C.c_float), ("rhs_const", C.c_float * 8),
                 ("rhs_mlp", NmMlp), ("A", _MAT), ("Bm", _MAT), ("E", _MAT), ("C", _MAT),
                 ("n_exo", C.c_int32), ("exo", NmExo * NM_MAX_EXO), ("n_terms", C.c_int32),
                 ("terms", NmTerm * NM_MAX_TERMS), ("n_params", C.c_int64),

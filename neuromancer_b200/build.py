@@ -70,7 +70,7 @@ def signature_of(p: L.NmPlan) -> str:
     if p.rhs_kind == L.NM_RHS_MLP:
         s += _mlp_sig(p.rhs_mlp)
     nd = p.exo[p.dist_exo].width if p.dist_exo >= 0 else 0
-    s += f"_dist{p.dist_exo}.{nd}"
+    s += f"_dist{p.dist_exo}.{nd}_act{p.act_exo}"
     return s
 
 
@@ -175,7 +175,7 @@ def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
            _table("seg_index", [s.index for s in segs]),
            _table("seg_width", [s.width for s in segs]),
            _table("seg_sub", [(p.exo[s.index].width if s.kind in (L.NM_SEG_EXO, L.NM_SEG_PREVIEW) else s.width) for s in segs]),
-           f"  static constexpr int DYN = {p.dyn_kind}, INTEG = {integ}, RHS = {p.rhs_kind}, DIST_EXO = {p.dist_exo};\n",
+           f"  static constexpr int DYN = {p.dyn_kind}, INTEG = {integ}, RHS = {p.rhs_kind}, DIST_EXO = {p.dist_exo}, ACT_EXO = {p.act_exo};\n",
            f"  static constexpr const char* signature() {{ return \"{sig}\"; }}\n", _term_tables(p), "};\n"]
     return "".join(out)
 

@@ -339,6 +339,122 @@ def t_node_policy_euler(seed=0, nsteps=6) -> Case:
     return Case("t_node_policy_euler", problem, system, nsteps, 150, make_batch, 0, 0)
 
 
+# ---- remaining explicit integrators and white-box right-hand sides --------------
+def _freeze(module):
+    for q in module.parameters():
+        q.requires_grad_(False)
+    return module
+
+
+def t_int_euler_trap_lorenz(seed=0, nsteps=8) -> Case:
+    torch.manual_seed(seed)
+    model = Node(integrators.Euler_Trap(_freeze(ode.LorenzControl()), h=0.01), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=3, outsize=2, hsizes=[12], nonlin=nn.Tanh, min=-2., max=2., method="relu_clamp")
+    system = System([Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    obj = (variable("x") == 0.) ^ 2
+    eff = 0.1 * ((variable("u") == 0.) ^ 2)
+    obj.name, eff.name = "obj", "eff"
+    problem = Problem([system], PenaltyLoss([obj, eff], []))
+    mb = lambda Bn, device, s=0: {"x": (2.0 * torch.randn(Bn, 1, 3, generator=_gen(device, 9100 + s))).to(device), "name": "train"}
+    return Case("t_int_euler_trap_lorenz", problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_int_rk4_trap_cstr(seed=0, nsteps=6) -> Case:
+    torch.manual_seed(seed)
+    model = Node(integrators.RK4_Trap(_freeze(ode.CSTR_Param()), h=0.02), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP_bounds(insize=3, outsize=1, hsizes=[10, 10], nonlin=activations["gelu"], min=280., max=320.)
+    system = System([Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    x, r = variable("x"), variable("r")
+    obj = (x[:, :, [1]] == r) ^ 2
+    cmax = 5. * (x[:, :, [0]] < 0.9)
+    obj.name, cmax.name = "obj", "cmax"
+    problem = Problem([system], PenaltyLoss([obj], [cmax]))
+
+    def mb(Bn, device, s=0):
+        g = _gen(device, 9200 + s)
+        x0 = torch.cat([0.8 + 0.2 * torch.rand(Bn, 1, 1, generator=g), 300. + 20. * torch.rand(Bn, 1, 1, generator=g)], dim=-1)
+        return {"x": x0.to(device), "r": (305. + 10. * torch.rand(Bn, nsteps + 1, 1, generator=g)).to(device), "name": "train"}
+    return Case("t_int_rk4_trap_cstr", problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_int_luther_vdp(seed=0, nsteps=7) -> Case:
+    torch.manual_seed(seed)
+    plant = ode.VanDerPolControl()
+    plant.mu = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+    model = Node(integrators.Luther(plant, h=0.1), ["x", "u"], ["x"], name="model")
+    net = blocks.MLP(insize=2, outsize=1, hsizes=[8, 8], nonlin=nn.ReLU)
+    system = System([Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    obj = (variable("x") == 0.) ^ 2
+    obj.name = "obj"
+    problem = Problem([system], PenaltyLoss([obj], []))
+    mb = lambda Bn, device, s=0: {"x": torch.randn(Bn, 1, 2, generator=_gen(device, 9300 + s)).to(device), "name": "train"}
+    return Case("t_int_luther_vdp", problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_int_rkf_node(seed=0, nsteps=6) -> Case:
+    """Open-loop neural ODE with a measured input read from the data (Part_4a_nonauto_NODE shape)."""
+    torch.manual_seed(seed)
+    fx = blocks.MLP(3, 2, bias=True, linear_map=nn.Linear, nonlin=nn.Tanh, hsizes=[16, 16])
+    model = Node(integrators.Runge_Kutta_Fehlberg(fx, h=0.1), ["xn", "U"], ["xn"], name="NODE")
+    system = System([model], name="system")                       # nsteps from data['X']
+    ref = (variable("xn")[:, :-1, :] == variable("X")) ^ 2
+    ref.name = "ref"
+    problem = Problem([system], PenaltyLoss([ref], []))
+
+    def mb(Bn, device, s=0):
+        g = _gen(device, 9400 + s)
+        X = torch.randn(Bn, nsteps, 2, generator=g)
+        return {"X": X.to(device), "xn": X[:, 0:1, :].contiguous().to(device), "U": torch.randn(Bn, nsteps, 1, generator=g).to(device),
+                "name": "train"}
+    return Case("t_int_rkf_node", problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_open_duffing(seed=0, nsteps=9) -> Case:
+    torch.manual_seed(seed)
+    model = Node(integrators.RK4(_freeze(ode.DuffingParam()), h=0.05), ["x", "t"], ["x"], name="model")
+    system = System([model], nsteps=nsteps, name="sys")
+    obj = (variable("x") == 0.) ^ 2
+    obj.name = "obj"
+    problem = Problem([system], PenaltyLoss([obj], []))
+
+    def mb(Bn, device, s=0):
+        g = _gen(device, 9500 + s)
+        t = (0.05 * torch.arange(nsteps, dtype=torch.float32)).reshape(1, nsteps, 1).repeat(Bn, 1, 1)
+        return {"x": torch.randn(Bn, 1, 2, generator=g).to(device), "t": t.to(device), "name": "train"}
+    return Case("t_open_duffing", problem, system, nsteps, 100, mb, 0, 0)
+
+
+def _t_auto(name, plant, integ, h, nsteps, norm, target, seed, scale, shift):
+    torch.manual_seed(seed)
+    model = Node(integ(_freeze(plant), h=h), ["x"], ["x"], name="model")
+    system = System([model], nsteps=nsteps, name="sys")
+    obj = (variable("x") == target) ^ norm
+    obj.name = "obj"
+    problem = Problem([system], PenaltyLoss([obj], []))
+    nx = plant.out_features
+    mb = lambda Bn, device, s=0: {"x": (shift + scale * torch.rand(Bn, 1, nx, generator=_gen(device, 9600 + s))).to(device), "name": "train"}
+    return Case(name, problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_auto_brusselator(seed=0, nsteps=8) -> Case:
+    plant = ode.BrusselatorParam()
+    plant.alpha = nn.Parameter(torch.tensor([1.0]), requires_grad=False)
+    plant.beta = nn.Parameter(torch.tensor([3.0]), requires_grad=False)
+    return _t_auto("t_auto_brusselator", plant, integrators.RK2, 0.05, nsteps, 1, 1., seed, 2.0, 0.5)
+
+
+def t_auto_lotka(seed=0, nsteps=8) -> Case:
+    return _t_auto("t_auto_lotka", ode.LotkaVolterraParam(), integrators.Euler, 0.1, nsteps, 2, 1., seed, 3.0, 0.5)
+
+
+def t_auto_lorenz(seed=0, nsteps=8) -> Case:
+    plant = ode.LorenzParam()
+    plant.rho = nn.Parameter(torch.tensor([28.0]), requires_grad=False)
+    plant.sigma = nn.Parameter(torch.tensor([10.0]), requires_grad=False)
+    plant.beta = nn.Parameter(torch.tensor([2.66667]), requires_grad=False)
+    return _t_auto("t_auto_lorenz", plant, integrators.RK4, 0.01, nsteps, 2, 0., seed, 10.0, -5.0)
+
+
 def _t_preview(pad_mode, seed=0, nsteps=9) -> Case:
     """TwoTank tracking with a previewing policy (examples/control/Part_3_ref_tracking_ODE.py:93-105)."""
     torch.manual_seed(seed)
@@ -397,6 +513,9 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_vdp_rk4_tanh_clamp": t_vdp_rk4_tanh_clamp, "t_vdp_euler_elu": t_vdp_euler_elu,
     "t_twotank_rk2_sigmoid": t_twotank_rk2_sigmoid, "t_ssm_softplus": t_ssm_softplus,
     "t_node_policy_euler": t_node_policy_euler,
+    "t_int_euler_trap_lorenz": t_int_euler_trap_lorenz, "t_int_rk4_trap_cstr": t_int_rk4_trap_cstr,
+    "t_int_luther_vdp": t_int_luther_vdp, "t_int_rkf_node": t_int_rkf_node, "t_open_duffing": t_open_duffing,
+    "t_auto_brusselator": t_auto_brusselator, "t_auto_lotka": t_auto_lotka, "t_auto_lorenz": t_auto_lorenz,
     "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
     "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
 }

@@ -60,6 +60,7 @@ int validate(const NmPlan* p) {
   for (int e = 0; e < p->n_exo; ++e)
     if (p->exo[e].width < 1 || p->exo[e].steps < 1) { nm_set_error("exo shape invalid"); return NM_ERR_BAD_PLAN; }
   if (p->dist_exo >= p->n_exo) { nm_set_error("dist_exo out of range"); return NM_ERR_BAD_PLAN; }
+  if (p->act_exo >= p->n_exo || (p->act_exo >= 0 && (p->has_policy || p->exo[p->act_exo].width != p->nu))) { nm_set_error("act_exo invalid"); return NM_ERR_BAD_PLAN; }
   const int T[3] = {p->nsteps + 1, p->nsteps, p->nsteps};
   const int D[3] = {p->nx, p->nu, p->ny};
   for (int k = 0; k < p->n_terms; ++k) {
@@ -127,7 +128,7 @@ std::string make_signature(const NmPlan* p) {
   s += buf;
   if (p->rhs_kind == NM_RHS_MLP) append_mlp(s, p->rhs_mlp);
   const int nd = p->dist_exo >= 0 ? p->exo[p->dist_exo].width : 0;
-  std::snprintf(buf, sizeof(buf), "_dist%d.%d", p->dist_exo, nd);
+  std::snprintf(buf, sizeof(buf), "_dist%d.%d_act%d", p->dist_exo, nd, p->act_exo);
   s += buf;
   return s;
 }

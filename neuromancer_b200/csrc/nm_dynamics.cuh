@@ -42,6 +42,31 @@ struct Rhs {
         dx[2 * j] = vel;
         dx[2 * j + 1] = mu * (1.f - pos * pos) * vel - pos + u[j] + kappa * (nxt - pos);
       }
+    } else if constexpr (S::RHS == NM_RHS_LORENZ_CTRL || S::RHS == NM_RHS_LORENZ) {   // ode.py:371-414
+      const float rho = p.rhs_const[0], sigma = p.rhs_const[1], beta = p.rhs_const[2];
+      dx[0] = sigma * (x[1] - x[0]);
+      dx[1] = x[0] * (rho - x[2]) - x[1];
+      dx[2] = x[0] * x[1] - beta * x[2];
+      if constexpr (S::RHS == NM_RHS_LORENZ_CTRL) { dx[0] += u[0]; dx[2] -= u[1]; }
+    } else if constexpr (S::RHS == NM_RHS_CSTR) {              // ode.py:449-461
+      const float qV = p.rhs_const[0], Caf = p.rhs_const[1], Tf = p.rhs_const[2], k0 = p.rhs_const[3];
+      const float EoverR = p.rhs_const[4], cH = p.rhs_const[5], cU = p.rhs_const[6];
+      const float rA = k0 * expf(-EoverR / x[1]) * x[0];
+      dx[0] = qV * (Caf - x[0]) - rA;
+      dx[1] = qV * (Tf - x[1]) + cH * rA + cU * (u[0] - x[1]);
+    } else if constexpr (S::RHS == NM_RHS_DUFFING) {           // ode.py:254-262 (input is time)
+      const float alpha = p.rhs_const[0], beta = p.rhs_const[1], delta = p.rhs_const[2], gamma = p.rhs_const[3], omega = p.rhs_const[4];
+      dx[0] = x[1];
+      dx[1] = -delta * x[1] - alpha * x[0] - beta * (x[0] * x[0] * x[0]) + gamma * cosf(omega * u[0]);
+    } else if constexpr (S::RHS == NM_RHS_BRUSSELATOR) {       // ode.py:276-281
+      const float alpha = p.rhs_const[0], beta = p.rhs_const[1];
+      const float q = x[1] * (x[0] * x[0]);
+      dx[0] = alpha + q - beta * x[0] - x[0];
+      dx[1] = beta * x[0] - q;
+    } else if constexpr (S::RHS == NM_RHS_LOTKA_VOLTERRA) {    // ode.py:344-349
+      const float alpha = p.rhs_const[0];
+      dx[0] = alpha * x[0] - 0.4f * x[0] * x[1];
+      dx[1] = 0.1f * x[0] * x[1] - 0.4f * x[1];
     } else if constexpr (S::RHS == NM_RHS_LINEAR) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
@@ -90,6 +115,33 @@ struct Rhs {
         gx[2 * ((j + 1) % NO)] += wa * kappa;
         gu[j] += wa;
       }
+    } else if constexpr (S::RHS == NM_RHS_LORENZ_CTRL || S::RHS == NM_RHS_LORENZ) {
+      const float rho = p.rhs_const[0], sigma = p.rhs_const[1], beta = p.rhs_const[2];
+      gx[0] += -sigma * w[0] + (rho - x[2]) * w[1] + x[1] * w[2];
+      gx[1] += sigma * w[0] - w[1] + x[0] * w[2];
+      gx[2] += -x[0] * w[1] - beta * w[2];
+      if constexpr (S::RHS == NM_RHS_LORENZ_CTRL) { gu[0] += w[0]; gu[1] -= w[2]; }
+    } else if constexpr (S::RHS == NM_RHS_CSTR) {
+      const float qV = p.rhs_const[0], k0 = p.rhs_const[3], EoverR = p.rhs_const[4], cH = p.rhs_const[5], cU = p.rhs_const[6];
+      const float e = k0 * expf(-EoverR / x[1]);
+      const float g_rA = -w[0] + cH * w[1];                 // cotangent of rA = e * Ca
+      gx[0] += -qV * w[0] + g_rA * e;
+      gx[1] += (-qV - cU) * w[1] + g_rA * x[0] * e * (EoverR / (x[1] * x[1]));
+      gu[0] += cU * w[1];
+    } else if constexpr (S::RHS == NM_RHS_DUFFING) {
+      const float alpha = p.rhs_const[0], beta = p.rhs_const[1], delta = p.rhs_const[2], gamma = p.rhs_const[3], omega = p.rhs_const[4];
+      gx[0] += w[1] * (-alpha - 3.f * beta * x[0] * x[0]);
+      gx[1] += w[0] - delta * w[1];
+      gu[0] += -w[1] * gamma * omega * sinf(omega * u[0]);
+    } else if constexpr (S::RHS == NM_RHS_BRUSSELATOR) {
+      const float beta = p.rhs_const[1];
+      const float dq0 = 2.f * x[1] * x[0], dq1 = x[0] * x[0];   // d(x2*x1^2)/dx1, /dx2
+      gx[0] += w[0] * (dq0 - beta - 1.f) + w[1] * (beta - dq0);
+      gx[1] += (w[0] - w[1]) * dq1;
+    } else if constexpr (S::RHS == NM_RHS_LOTKA_VOLTERRA) {
+      const float alpha = p.rhs_const[0];
+      gx[0] += w[0] * (alpha - 0.4f * x[1]) + w[1] * 0.1f * x[1];
+      gx[1] += -w[0] * 0.4f * x[0] + w[1] * (0.1f * x[0] - 0.4f);
     } else if constexpr (S::RHS == NM_RHS_LINEAR) {
 #pragma unroll
       for (int j = 0; j < NX; ++j) {
@@ -110,47 +162,142 @@ struct Rhs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// explicit one-step schemes whose stage s reads only stage s-1:  xs = x + a_s*h*k_{s-1}
+// explicit Runge-Kutta schemes as Butcher tableaux:  xs_s = x + h * sum_{j<s} a(s,j) k_j ,  k_s = f(xs_s, u),
+// x+ = x + h * sum_s b(s) k_s.  Euler / RK2 / RK4 evaluate their stages in the reference's exact operation
+// order (below); the other schemes use the generic tableau arithmetic (same values to ~1 ulp per stage).
+constexpr int NM_MAX_STAGES = 7;
+constexpr double kQ21 = 4.58257569495584000658804719372800848898445657676797;   // sqrt(21), Luther
 template <int INTEG> struct Tableau;
-template <> struct Tableau<NM_INT_EULER> { static constexpr int NS = 1; };
-template <> struct Tableau<NM_INT_RK2> { static constexpr int NS = 2; };
-template <> struct Tableau<NM_INT_RK4> { static constexpr int NS = 4; };
+template <> struct Tableau<NM_INT_EULER> {
+  static constexpr int NS = 1;
+  static constexpr double a(int, int) { return 0.0; }
+  static constexpr double b(int) { return 1.0; }
+};
+template <> struct Tableau<NM_INT_RK2> {
+  static constexpr int NS = 2;
+  static constexpr double a(int s, int j) { return (s == 1 && j == 0) ? 0.5 : 0.0; }
+  static constexpr double b(int s) { return s == 1 ? 1.0 : 0.0; }
+};
+template <> struct Tableau<NM_INT_RK4> {
+  static constexpr int NS = 4;
+  static constexpr double a(int s, int j) { return (j == s - 1) ? (s == 3 ? 1.0 : 0.5) : 0.0; }
+  static constexpr double b(int s) { return (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0; }
+};
+template <> struct Tableau<NM_INT_EULER_TRAP> {              // pred = x + h k1 ; corr = x + 0.5 h (k1 + f(pred))
+  static constexpr int NS = 2;
+  static constexpr double a(int s, int j) { return (s == 1 && j == 0) ? 1.0 : 0.0; }
+  static constexpr double b(int) { return 0.5; }
+};
+template <> struct Tableau<NM_INT_RK4_TRAP> {                // RK4 predictor, trapezoidal corrector
+  static constexpr int NS = 5;
+  static constexpr double a(int s, int j) {
+    if (s < 4) return Tableau<NM_INT_RK4>::a(s, j);
+    return Tableau<NM_INT_RK4>::b(j);
+  }
+  static constexpr double b(int s) { return (s == 0 || s == 4) ? 0.5 : 0.0; }
+};
+template <> struct Tableau<NM_INT_LUTHER> {                  // integrators.py:247-264
+  static constexpr int NS = 7;
+  static constexpr double a(int s, int j) {
+    constexpr double q = kQ21;
+    const double A[7][6] = {
+        {0, 0, 0, 0, 0, 0},
+        {1, 0, 0, 0, 0, 0},
+        {3.0 / 8, 1.0 / 8, 0, 0, 0, 0},
+        {8.0 / 27, 2.0 / 27, 8.0 / 27, 0, 0, 0},
+        {(-21 + 9 * q) / 392, (-56 + 8 * q) / 392, (336 - 48 * q) / 392, (-63 + 3 * q) / 392, 0, 0},
+        {(-1155 - 255 * q) / 1960, (-280 - 40 * q) / 1960, -320 * q / 1960, (63 + 363 * q) / 1960, (2352 + 392 * q) / 1960, 0},
+        {(330 + 105 * q) / 180, 120.0 / 180, (-200 + 280 * q) / 180, (126 - 189 * q) / 180, (-686 - 126 * q) / 180, (490 - 70 * q) / 180}};
+    return j < s ? A[s][j] : 0.0;
+  }
+  static constexpr double b(int s) {
+    const double B[7] = {1.0 / 20, 0, 16.0 / 45, 0, 49.0 / 180, 49.0 / 180, 1.0 / 20};
+    return B[s];
+  }
+};
+template <> struct Tableau<NM_INT_RKF> {                     // integrators.py:287-301 (5th-order output)
+  static constexpr int NS = 6;
+  static constexpr double a(int s, int j) {
+    const double A[6][5] = {
+        {0, 0, 0, 0, 0},
+        {1.0 / 4, 0, 0, 0, 0},
+        {3.0 / 32, 9.0 / 32, 0, 0, 0},
+        {1932.0 / 2197, -7200.0 / 2197, 7296.0 / 2197, 0, 0},
+        {439.0 / 216, -8.0, 3680.0 / 513, -845.0 / 4104, 0},
+        {-8.0 / 27, 2.0, -3544.0 / 2565, 1859.0 / 4104, -11.0 / 40}};
+    return j < s ? A[s][j] : 0.0;
+  }
+  static constexpr double b(int s) {
+    const double B[6] = {16.0 / 135, 0, 6656.0 / 12825, 28561.0 / 56430, -9.0 / 50, 2.0 / 55};
+    return B[s];
+  }
+};
 
-// stage input, in the reference's operation order
-template <int INTEG, int NX>
-__device__ __forceinline__ void stage_input(int s, float h, const float (&x)[NX], const float (&kprev)[NX],
-                                            float (&xs)[NX]) {
+// stage input xs_S from x and the earlier stage derivatives k[0..S-1]
+template <int INTEG, int S_, int NX>
+__device__ __forceinline__ void stage_input(float h, const float (&x)[NX], const float (&k)[NM_MAX_STAGES][NX], float (&xs)[NX]) {
+  if constexpr (S_ == 0) {
 #pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    if (s == 0) xs[i] = x[i];
-    else if (INTEG == NM_INT_RK4 && s == 3) xs[i] = x[i] + h * kprev[i];
-    else xs[i] = x[i] + h * kprev[i] / 2.0f;
+    for (int i = 0; i < NX; ++i) xs[i] = x[i];
+  } else if constexpr (INTEG == NM_INT_RK2 || INTEG == NM_INT_RK4) {
+    // reference order:  x + h*k/2.0   (RK4 last stage:  x + h*k)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      if constexpr (INTEG == NM_INT_RK4 && S_ == 3) xs[i] = x[i] + h * k[S_ - 1][i];
+      else xs[i] = x[i] + h * k[S_ - 1][i] / 2.0f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      float acc = 0.f;
+      static_for<0, S_>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        constexpr float A = static_cast<float>(Tableau<INTEG>::a(S_, J));
+        if constexpr (A != 0.f) acc = fmaf(A, k[J][i], acc);
+      });
+      xs[i] = fmaf(h, acc, x[i]);
+    }
   }
 }
-// d xs / d k_{s-1}
-template <int INTEG>
-__device__ __forceinline__ float stage_coupling(int s, float h) {
-  if (s == 0) return 0.f;
-  if (INTEG == NM_INT_RK4 && s == 3) return h;
-  return h * 0.5f;
-}
-// d x+ / d k_s
-template <int INTEG>
-__device__ __forceinline__ float stage_weight(int s, float h) {
-  if (INTEG == NM_INT_EULER) return h;
-  if (INTEG == NM_INT_RK2) return s == 1 ? h : 0.f;
-  return (s == 0 || s == 3) ? h / 6.0f : h / 3.0f;
-}
-// x+ from the stage derivatives, reference operation order
+// x+ from the stage derivatives
 template <int INTEG, int NX>
-__device__ __forceinline__ void combine_stages(float h, const float (&x)[NX], const float (&k)[4][NX],
-                                               float (&xn)[NX]) {
+__device__ __forceinline__ void combine_stages(float h, const float (&x)[NX], const float (&k)[NM_MAX_STAGES][NX], float (&xn)[NX]) {
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
-    if (INTEG == NM_INT_EULER) xn[i] = x[i] + h * k[0][i];
-    else if (INTEG == NM_INT_RK2) xn[i] = x[i] + h * k[1][i];
-    else xn[i] = x[i] + h * (k[0][i] / 6.0f + k[1][i] / 3.0f + k[2][i] / 3.0f + k[3][i] / 6.0f);
+    if constexpr (INTEG == NM_INT_EULER) xn[i] = x[i] + h * k[0][i];
+    else if constexpr (INTEG == NM_INT_RK2) xn[i] = x[i] + h * k[1][i];
+    else if constexpr (INTEG == NM_INT_RK4) xn[i] = x[i] + h * (k[0][i] / 6.0f + k[1][i] / 3.0f + k[2][i] / 3.0f + k[3][i] / 6.0f);
+    else {
+      float acc = 0.f;
+      static_for<0, Tableau<INTEG>::NS>([&](auto sc) {
+        constexpr int Sx = decltype(sc)::value;
+        constexpr float Bv = static_cast<float>(Tableau<INTEG>::b(Sx));
+        if constexpr (Bv != 0.f) acc = fmaf(Bv, k[Sx][i], acc);
+      });
+      xn[i] = fmaf(h, acc, x[i]);
+    }
   }
+}
+// adjoint bookkeeping of stage S:  w = h*b(S)*lam + gk[S]  is the cotangent of k_S; after the RHS vjp gave
+// gxs (cotangent of xs_S) it is pushed to x and to the earlier stages:  gk[j] += h*a(S,j)*gxs
+template <int INTEG, int S_, int NX>
+__device__ __forceinline__ void stage_cotangent(float h, const float (&lam)[NX], const float (&gk)[NM_MAX_STAGES][NX], float (&w)[NX]) {
+  constexpr float Bv = static_cast<float>(Tableau<INTEG>::b(S_));
+#pragma unroll
+  for (int i = 0; i < NX; ++i) w[i] = fmaf(h * Bv, lam[i], gk[S_][i]);
+}
+template <int INTEG, int S_, int NX>
+__device__ __forceinline__ void stage_push(float h, const float (&gxs)[NX], float (&gx)[NX], float (&gk)[NM_MAX_STAGES][NX]) {
+#pragma unroll
+  for (int i = 0; i < NX; ++i) gx[i] += gxs[i];
+  static_for<0, S_>([&](auto jc) {
+    constexpr int J = decltype(jc)::value;
+    constexpr float A = static_cast<float>(Tableau<INTEG>::a(S_, J));
+    if constexpr (A != 0.f) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) gk[J][i] = fmaf(h * A, gxs[i], gk[J][i]);
+    }
+  });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,13 +328,13 @@ struct Dyn {
       }
     } else {
       constexpr int NS = Tableau<S::INTEG>::NS;
-      float k[4][NX];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
+      float k[NM_MAX_STAGES][NX];
+      static_for<0, NS>([&](auto sc) {
+        constexpr int St = decltype(sc)::value;
         float xs[NX];
-        stage_input<S::INTEG, NX>(s, p.h, x, k[s > 0 ? s - 1 : 0], xs);
-        Rhs<S>::eval(p, xs, u, k[s]);
-      }
+        stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
+        Rhs<S>::eval(p, xs, u, k[St]);
+      });
       combine_stages<S::INTEG, NX>(p.h, x, k, xn);
     }
   }
@@ -215,28 +362,25 @@ struct Dyn {
     } else {
       constexpr int NS = Tableau<S::INTEG>::NS;
       const float h = p.h;
-      float k[4][NX], xs[4][NX];
+      float k[NM_MAX_STAGES][NX], xs[NM_MAX_STAGES][NX], gk[NM_MAX_STAGES][NX];
+      static_for<0, NS>([&](auto sc) {                   // recompute the stage inputs
+        constexpr int St = decltype(sc)::value;
+        stage_input<S::INTEG, St, NX>(h, x, k, xs[St]);
+        if constexpr (St + 1 < NS) Rhs<S>::eval(p, xs[St], u, k[St]);
 #pragma unroll
-      for (int s = 0; s < NS; ++s) {                     // recompute the stage inputs
-        stage_input<S::INTEG, NX>(s, h, x, k[s > 0 ? s - 1 : 0], xs[s]);
-        if (s + 1 < NS) Rhs<S>::eval(p, xs[s], u, k[s]);
-      }
+        for (int i = 0; i < NX; ++i) gk[St][i] = 0.f;
+      });
 #pragma unroll
       for (int i = 0; i < NX; ++i) gx[i] = lam[i];
-      float carry[NX];                                    // cotangent reaching k_s from stage s+1's input
-#pragma unroll
-      for (int i = 0; i < NX; ++i) carry[i] = 0.f;
-#pragma unroll
-      for (int s = NS - 1; s >= 0; --s) {
+      static_for_rev<0, NS>([&](auto sc) {
+        constexpr int St = decltype(sc)::value;
         float w[NX], gxs[NX];
-        const float bw = stage_weight<S::INTEG>(s, h);
+        stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { w[i] = fmaf(bw, lam[i], carry[i]); gxs[i] = 0.f; }
-        Rhs<S>::vjp(p, xs[s], u, w, gxs, gu);
-        const float cp = stage_coupling<S::INTEG>(s, h);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { gx[i] += gxs[i]; carry[i] = cp * gxs[i]; }
-      }
+        for (int i = 0; i < NX; ++i) gxs[i] = 0.f;
+        Rhs<S>::vjp(p, xs[St], u, w, gxs, gu);
+        stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
+      });
     }
   }
 };

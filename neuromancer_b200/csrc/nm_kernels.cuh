@@ -564,18 +564,25 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
           for (int j = 0; j < ND; ++j) d[j] = __ldg(src + j);
         }
       }
+      if constexpr (!KC::HAS_POL && S::ACT_EXO >= 0) {       // open loop: the action comes from the data
+        if (owner) {
+          const float* src = args.exo[S::ACT_EXO] + (b * p.exo[S::ACT_EXO].steps + t) * NU;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) { u[j] = __ldg(src + j); if (valid) args.u_traj[(b * T + t) * NU + j] = u[j]; }
+        }
+      }
       float xn[NX];
       if constexpr (!KC::HAS_RHS_MLP) {
         if (owner) Dyn<S>::step(p, x, u, d, xn);
       } else {
         // neural right-hand side: every stage is a CTA-cooperative MLP evaluation
         constexpr int NS = Tableau<S::INTEG>::NS;
-        float k[4][NX];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
+        float k[NM_MAX_STAGES][NX];
+        static_for<0, NS>([&](auto sc) {
+          constexpr int St = decltype(sc)::value;
           if (owner) {
             float xs[NX];
-            stage_input<S::INTEG, NX>(s, p.h, x, k[s > 0 ? s - 1 : 0], xs);
+            stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
 #pragma unroll
             for (int i = 0; i < NX; ++i) pp0[i * LD + tid] = xs[i];
 #pragma unroll
@@ -586,11 +593,11 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
           if (owner) {
             const float* outp = (RhsCfg::NL & 1) ? pp1 : pp0;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) k[s][i] = outp[i * LD + tid];
+            for (int i = 0; i < NX; ++i) k[St][i] = outp[i * LD + tid];
           }
           // the next writer of pp0/pp1 is this same thread's own column (stage input) or, behind a
           // barrier, the next layer GEMM: no extra barrier needed here
-        }
+        });
         if (owner) combine_stages<S::INTEG, NX>(p.h, x, k, xn);
       }
       if (owner) {
@@ -771,41 +778,51 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
           }
         }
       }
+      if constexpr (!KC::HAS_POL && S::ACT_EXO >= 0) {       // open loop: the action comes from the data
+        if (owner) {
+          const float* src = args.exo[S::ACT_EXO] + (b * p.exo[S::ACT_EXO].steps + t) * NU;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) u[j] = __ldg(src + j);
+        }
+      }
       // ---- dynamics adjoint: (gx, gu) = (d x_{t+1} / d (x_t, u_t))^T lam
       if constexpr (!KC::HAS_RHS_MLP) {
         if (owner) Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
       } else {
         constexpr int NS = Tableau<S::INTEG>::NS;
         const float h = p.h;
-        float k[4][NX];
+        float k[NM_MAX_STAGES][NX], gk[NM_MAX_STAGES][NX];
         // pass 1: stage derivatives k_0 .. k_{NS-2}
+        static_for<0, NS>([&](auto sc) {
+          constexpr int St = decltype(sc)::value;
 #pragma unroll
-        for (int s = 0; s + 1 < NS; ++s) {
-          if (owner) {
-            float xs[NX];
-            stage_input<S::INTEG, NX>(s, h, x, k[s > 0 ? s - 1 : 0], xs);
+          for (int i = 0; i < NX; ++i) gk[St][i] = 0.f;
+          if constexpr (St + 1 < NS) {
+            if (owner) {
+              float xs[NX];
+              stage_input<S::INTEG, St, NX>(h, x, k, xs);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
+              for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
 #pragma unroll
-            for (int j = 0; j < NU; ++j) keep_rhs[(NX + j) * LD + tid] = u[j];
+              for (int j = 0; j < NU; ++j) keep_rhs[(NX + j) * LD + tid] = u[j];
+            }
+            __syncthreads();
+            mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
+            if (owner) {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) k[St][i] = dbuf0[i * LD + tid];
+            }
+            __syncthreads();                                     // dbuf0 is rewritten by the next stage
           }
-          __syncthreads();
-          mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
-          if (owner) {
-#pragma unroll
-            for (int i = 0; i < NX; ++i) k[s][i] = dbuf0[i * LD + tid];
-          }
-          __syncthreads();                                       // dbuf0 is rewritten by the next stage
-        }
+        });
         // pass 2: stages in reverse, recomputing each stage's activations
-        float carry[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { carry[i] = 0.f; gx[i] = lam[i]; }
-#pragma unroll
-        for (int s = NS - 1; s >= 0; --s) {
+        for (int i = 0; i < NX; ++i) gx[i] = lam[i];
+        static_for_rev<0, NS>([&](auto sc) {
+          constexpr int St = decltype(sc)::value;
           if (owner) {
             float xs[NX];
-            stage_input<S::INTEG, NX>(s, h, x, k[s > 0 ? s - 1 : 0], xs);
+            stage_input<S::INTEG, St, NX>(h, x, k, xs);
 #pragma unroll
             for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
 #pragma unroll
@@ -814,23 +831,25 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
           __syncthreads();
           mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
           if (owner) {
-            const float bw = stage_weight<S::INTEG>(s, h);
+            float w[NX];
+            stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) dbuf0[i * LD + tid] = valid ? fmaf(bw, lam[i], carry[i]) : 0.f;
+            for (int i = 0; i < NX; ++i) dbuf0[i * LD + tid] = valid ? w[i] : 0.f;
           }
           __syncthreads();
           mlp_backward<RhsCfg, typename S::RhsM, TILE, THREADS, SPILL>(Wrhs, keep_rhs, dbuf0, dbuf1, rhs_dw, grhs,
                                                                         p.rhs_mlp.has_bias, rhs_train, p.rhs_mlp.act_param, tid);
           if (owner) {
             const float* gin = (RhsCfg::NL & 1) ? dbuf1 : dbuf0;
-            const float cp = stage_coupling<S::INTEG>(s, h);
+            float gxs[NX];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) { const float g = gin[i * LD + tid]; gx[i] += g; carry[i] = cp * g; }
+            for (int i = 0; i < NX; ++i) gxs[i] = gin[i * LD + tid];
+            stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
 #pragma unroll
             for (int j = 0; j < NU; ++j) gu[j] += gin[(NX + j) * LD + tid];
           }
           __syncthreads();                                       // gin buffer is rewritten by the next stage
-        }
+        });
       }
       // ---- loss-term gradients w.r.t. u_t and y_t
       if (valid) {

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 1, 2, 3, 4, 5
+NM_RHS_LORENZ_CTRL, NM_RHS_CSTR, NM_RHS_DUFFING, NM_RHS_BRUSSELATOR, NM_RHS_LOTKA_VOLTERRA, NM_RHS_LORENZ = 6, 7, 8, 9, 10, 11
 
 
 class SSM(nn.Module):
@@ -126,5 +127,120 @@ class CoupledVanDerPolControl(ODESystem):
         return torch.stack([vel, acc], dim=-1).reshape(x.shape[0], -1)
 
 
-ode = {"TwoTankParam": TwoTankParam, "VanDerPolControl": VanDerPolControl,
+class LorenzControl(ODESystem):
+    """Controlled Lorenz system, two inputs (reference ode.py:393-414)."""
+    nm_rhs_id = NM_RHS_LORENZ_CTRL
+
+    def __init__(self, insize=5, outsize=3):
+        super().__init__(insize=insize, outsize=outsize)
+        self.rho = nn.Parameter(torch.tensor([28.0]), requires_grad=True)
+        self.sigma = nn.Parameter(torch.tensor([10.0]), requires_grad=True)
+        self.beta = nn.Parameter(torch.tensor([2.66667]), requires_grad=True)
+
+    def rhs_constants(self):
+        return [float(self.rho), float(self.sigma), float(self.beta)]
+
+    def ode_equations(self, x, u):
+        a, b, c = x[:, 0:1], x[:, 1:2], x[:, 2:3]
+        return torch.cat([self.sigma * (b - a) + u[:, 0:1], a * (self.rho - c) - b, a * b - self.beta * c - u[:, 1:2]], dim=-1)
+
+
+class LorenzParam(ODESystem):
+    """Autonomous Lorenz system (reference ode.py:371-391)."""
+    nm_rhs_id = NM_RHS_LORENZ
+
+    def __init__(self, insize=3, outsize=3):
+        super().__init__(insize=insize, outsize=outsize)
+        self.rho = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+        self.sigma = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+        self.beta = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+
+    def rhs_constants(self):
+        return [float(self.rho), float(self.sigma), float(self.beta)]
+
+    def ode_equations(self, x):
+        a, b, c = x[:, 0:1], x[:, 1:2], x[:, 2:3]
+        return torch.cat([self.sigma * (b - a), a * (self.rho - c) - b, a * b - self.beta * c], dim=-1)
+
+
+class CSTR_Param(ODESystem):
+    """Exothermic CSTR with cooling-jacket temperature as input (reference ode.py:417-461)."""
+    nm_rhs_id = NM_RHS_CSTR
+
+    def __init__(self, insize=3, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        mk = lambda v, g: nn.Parameter(torch.tensor([v]), requires_grad=g)
+        self.q, self.V, self.rho, self.Cp = mk(100.0, True), mk(100.0, False), mk(1000.0, True), mk(0.239, True)
+        self.mdelH, self.EoverR, self.k0 = mk(5e4, False), mk(8750.0, False), mk(7.2e10, False)
+        self.UA, self.Tf, self.Caf = mk(5e4, False), mk(350.0, False), mk(1.0, False)
+
+    def rhs_constants(self):
+        f = lambda t: float(t.detach())
+        # the coefficient groups are formed in fp32 exactly as the reference forms them per call
+        qV = f(self.q / self.V)
+        cH = f(self.mdelH / (self.rho * self.Cp))
+        cU = f(self.UA / self.V / self.rho / self.Cp)
+        return [qV, f(self.Caf), f(self.Tf), f(self.k0), f(self.EoverR), cH, cU]
+
+    def ode_equations(self, x, u):
+        conc, temp = x[:, 0:1], x[:, 1:2]
+        rate = self.k0 * torch.exp(-self.EoverR / temp) * conc
+        d_conc = self.q / self.V * (self.Caf - conc) - rate
+        d_temp = (self.q / self.V * (self.Tf - temp) + self.mdelH / (self.rho * self.Cp) * rate
+                  + self.UA / self.V / self.rho / self.Cp * (u - temp))
+        return torch.cat([d_conc, d_temp], dim=-1)
+
+
+class DuffingParam(ODESystem):
+    """Forced Duffing oscillator; the input is time (reference ode.py:240-262)."""
+    nm_rhs_id = NM_RHS_DUFFING
+
+    def __init__(self, insize=3, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        mk = lambda v, g: nn.Parameter(torch.tensor([v]), requires_grad=g)
+        self.alpha, self.beta, self.delta, self.gamma, self.omega = mk(1.0, False), mk(5.0, False), mk(0.02, False), mk(8.0, False), mk(0.5, True)
+
+    def rhs_constants(self):
+        return [float(v) for v in (self.alpha, self.beta, self.delta, self.gamma, self.omega)]
+
+    def ode_equations(self, x, u):
+        pos, vel = x[:, 0:1], x[:, 1:2]
+        return torch.cat([vel, -self.delta * vel - self.alpha * pos - self.beta * pos ** 3 + self.gamma * torch.cos(self.omega * u)], dim=-1)
+
+
+class BrusselatorParam(ODESystem):
+    """Autonomous Brusselator (reference ode.py:265-281)."""
+    nm_rhs_id = NM_RHS_BRUSSELATOR
+
+    def __init__(self, insize=2, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        self.alpha = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+        self.beta = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+
+    def rhs_constants(self):
+        return [float(self.alpha), float(self.beta)]
+
+    def ode_equations(self, x):
+        a, b = x[:, 0:1], x[:, 1:2]
+        return torch.cat([self.alpha + b * a ** 2 - self.beta * a - a, self.beta * a - b * a ** 2], dim=-1)
+
+
+class LotkaVolterraParam(ODESystem):
+    """Autonomous predator-prey model (reference ode.py:333-349)."""
+    nm_rhs_id = NM_RHS_LOTKA_VOLTERRA
+
+    def __init__(self, insize=2, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        self.alpha = nn.Parameter(torch.tensor([1.0]), requires_grad=True)
+
+    def rhs_constants(self):
+        return [float(self.alpha)]
+
+    def ode_equations(self, x):
+        a, b = x[:, 0:1], x[:, 1:2]
+        return torch.cat([self.alpha * a - 0.4 * a * b, 0.1 * a * b - 0.4 * b], dim=-1)
+
+
+ode = {"TwoTankParam": TwoTankParam, "LorenzControl": LorenzControl, "LorenzParam": LorenzParam, "CSTR_Param": CSTR_Param,
+       "DuffingParam": DuffingParam, "BrusselatorParam": BrusselatorParam, "LotkaVolterraParam": LotkaVolterraParam, "VanDerPolControl": VanDerPolControl,
        "CoupledVanDerPolControl": CoupledVanDerPolControl}

@@ -293,6 +293,7 @@ class SystemLayout:
     output_key: Optional[str] = None
     exo_keys: List[str] = field(default_factory=list)
     dist_key: Optional[str] = None
+    act_exo_key: Optional[str] = None      # open loop: the action is read from this data key (no policy)
     policy: Optional[_blocks.MLP] = None
     rhs_mlp: Optional[_blocks.MLP] = None
     policy_inputs: List[str] = field(default_factory=list)
@@ -372,6 +373,11 @@ def recognise(nodes, preview=None) -> SystemLayout:
         if lay.action_key is None:
             raise PlanError("SSM dynamics need an action input produced by a policy node")
     else:
+        if extra and lay.action_key is None and len(extra) == 1:
+            # open-loop rollout: the control input of the integrator comes straight from the data
+            lay.act_exo_key = extra[0]
+            lay.action_key = None
+            extra = []
         if extra:
             raise PlanError(f"integrator dynamics with extra inputs {extra} are not fused")
         if isinstance(fn.block, _blocks.MLP):
@@ -404,6 +410,8 @@ def recognise(nodes, preview=None) -> SystemLayout:
             add_exo(k)
     if lay.dist_key is not None:
         add_exo(lay.dist_key)
+    if lay.act_exo_key is not None:
+        add_exo(lay.act_exo_key)
     return lay
 
 
@@ -490,6 +498,11 @@ class RolloutPlan:
         # dynamics ----------------------------------------------------------------------
         fn = lay.dynamics
         p.dist_exo = -1
+        p.act_exo = -1
+        if lay.act_exo_key is not None:
+            j = lay.exo_keys.index(lay.act_exo_key)
+            p.act_exo = j
+            lay.nu = p.nu = p.exo[j].width
         if isinstance(fn, _ode.SSM):
             p.dyn_kind, p.integrator, p.rhs_kind, p.h = L.NM_DYN_SSM, 0, L.NM_RHS_NONE, 1.0
             _fill_matrix(p.A, _dense_matrix(fn.fx, "SSM.fx"), lay.nx, lay.nx)

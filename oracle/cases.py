@@ -165,6 +165,82 @@ def t_node_policy_euler(params, nsteps=6) -> dict:
     return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
 
 
+# ---- remaining explicit integrators and white-box right-hand sides --------------
+def _cstr_consts(like):
+    vals = dict(q=100.0, V=100.0, rho=1000.0, Cp=0.239, mdelH=5e4, EoverR=8750.0, k0=7.2e10, UA=5e4, Tf=350.0, Caf=1.0)
+    return {k: _t([v], like) for k, v in vals.items()}
+
+
+def t_int_euler_trap_lorenz(params, nsteps=8) -> dict:
+    rho, sigma, beta = (_t([v], params[0]) for v in (28.0, 10.0, 2.66667))
+    rhs = lambda x, u: O.rhs_lorenz_control(x, u, rho, sigma, beta)
+    nodes = [dict(fn=lambda x: O.bounds_clamp(O.mlp_forward(params, x, "tanh"), -2., 2.), inputs=["x"], outputs=["u"]),
+             dict(fn=lambda x, u: O.euler_trap_step(rhs, x, 0.01, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.),
+             _term("eff", True, "eq", 2, 0.1, lambda d: d["u"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+def t_int_rk4_trap_cstr(params, nsteps=6) -> dict:
+    cc = _cstr_consts(params[0])
+    rhs = lambda x, u: O.rhs_cstr(x, u, cc)
+    nodes = [dict(fn=lambda x, r: O.bounds_scaling(O.mlp_forward(params, torch.cat([x, r], dim=-1), "gelu"), 280., 320.),
+                  inputs=["x", "r"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk4_trap_step(rhs, x, 0.02, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"][:, :, [1]], lambda d: d["r"]),
+             _term("cmax", False, "lt", 1, 5., lambda d: d["x"][:, :, [0]], lambda d: 0.9)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+def t_int_luther_vdp(params, nsteps=7) -> dict:
+    mu = _t(1.0, params[0])
+    rhs = lambda x, u: O.rhs_vdp(x, u, mu)
+    nodes = [dict(fn=lambda x: O.mlp_forward(params, x, "relu"), inputs=["x"], outputs=["u"]),
+             dict(fn=lambda x, u: O.luther_step(rhs, x, 0.1, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
+def t_int_rkf_node(params, nsteps=6) -> dict:
+    """open-loop neural ODE with a measured input (examples/ODEs/Part_4a_nonauto_NODE.py:79-111 shape)"""
+    f = lambda x, u: O.mlp_forward(params, torch.cat([x, u], dim=-1), "tanh")
+    nodes = [dict(fn=lambda x, u: O.rkf_step(f, x, 0.1, u), inputs=["xn", "U"], outputs=["xn"])]
+    terms = [_term("ref", True, "eq", 2, 1.0, lambda d: d["xn"][:, :-1, :], lambda d: d["X"])]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["xn"])
+
+
+def t_open_duffing(params, nsteps=9) -> dict:
+    a, b, dl, g, w = (_t([v], torch.zeros(1)) for v in (1.0, 5.0, 0.02, 8.0, 0.5))
+    rhs = lambda x, t: O.rhs_duffing(x, t, a, b, dl, g, w)
+    nodes = [dict(fn=lambda x, t: O.rk4_step(rhs, x, 0.05, t), inputs=["x", "t"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x"])
+
+
+def t_auto_brusselator(params, nsteps=8) -> dict:
+    al, be = _t([1.0], torch.zeros(1)), _t([3.0], torch.zeros(1))
+    rhs = lambda x: O.rhs_brusselator(x, al, be)
+    nodes = [dict(fn=lambda x: O.rk2_step(rhs, x, 0.05), inputs=["x"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 1, 1.0, lambda d: d["x"], lambda d: 1.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x"])
+
+
+def t_auto_lotka(params, nsteps=8) -> dict:
+    al = _t([1.0], torch.zeros(1))
+    rhs = lambda x: O.rhs_lotka_volterra(x, al)
+    nodes = [dict(fn=lambda x: O.euler_step(rhs, x, 0.1), inputs=["x"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 1.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x"])
+
+
+def t_auto_lorenz(params, nsteps=8) -> dict:
+    rho, sigma, beta = (_t([v], torch.zeros(1)) for v in (28.0, 10.0, 2.66667))
+    rhs = lambda x: O.rhs_lorenz(x, rho, sigma, beta)
+    nodes = [dict(fn=lambda x: O.rk4_step(rhs, x, 0.01), inputs=["x"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x"])
+
+
 def _t_preview(params, nsteps, pad_mode):
     """examples/control/Part_3_ref_tracking_ODE.py:93-105 shape: TwoTank + RK4 with a policy that previews the
     reference `r` (2 signals, window L+1 = 6) and a 1-d price signal `p` (window 3); `r` is SHORTER than
@@ -191,6 +267,9 @@ CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_vdp_rk4_tanh_clamp": t_vdp_rk4_tanh_clamp, "t_vdp_euler_elu": t_vdp_euler_elu,
          "t_twotank_rk2_sigmoid": t_twotank_rk2_sigmoid, "t_ssm_softplus": t_ssm_softplus,
          "t_node_policy_euler": t_node_policy_euler,
+         "t_int_euler_trap_lorenz": t_int_euler_trap_lorenz, "t_int_rk4_trap_cstr": t_int_rk4_trap_cstr,
+         "t_int_luther_vdp": t_int_luther_vdp, "t_int_rkf_node": t_int_rkf_node, "t_open_duffing": t_open_duffing,
+         "t_auto_brusselator": t_auto_brusselator, "t_auto_lotka": t_auto_lotka, "t_auto_lorenz": t_auto_lorenz,
          "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
          "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect}
 

@@ -102,6 +102,49 @@ def rhs_cvdp(x, u, mu, kappa):
     return torch.stack([vel, acc], dim=-1).reshape(x.shape[0], -1)
 
 
+def rhs_lorenz_control(x, u, rho, sigma, beta):
+    """``LorenzControl.ode_equations`` (reference dynamics/ode.py:404-414)"""
+    x1, x2, x3 = x[:, [0]], x[:, [1]], x[:, [2]]
+    u1, u2 = u[:, [0]], u[:, [1]]
+    dx1 = sigma * (x2 - x1) + u1
+    dx2 = x1 * (rho - x3) - x2
+    dx3 = x1 * x2 - beta * x3 - u2
+    return torch.cat([dx1, dx2, dx3], dim=-1)
+
+
+def rhs_lorenz(x, rho, sigma, beta):
+    """``LorenzParam.ode_equations`` (reference dynamics/ode.py:383-391)"""
+    x1, x2, x3 = x[:, [0]], x[:, [1]], x[:, [-1]]
+    return torch.cat([sigma * (x2 - x1), x1 * (rho - x3) - x2, x1 * x2 - beta * x3], dim=-1)
+
+
+def rhs_cstr(x, u, c):
+    """``CSTR_Param.ode_equations`` (reference dynamics/ode.py:449-461); ``c`` = dict of its constants"""
+    Ca, T, Tc = x[:, [0]], x[:, [1]], u
+    rA = c["k0"] * torch.exp(-c["EoverR"] / T) * Ca
+    dCadt = c["q"] / c["V"] * (c["Caf"] - Ca) - rA
+    dTdt = c["q"] / c["V"] * (c["Tf"] - T) + c["mdelH"] / (c["rho"] * c["Cp"]) * rA + c["UA"] / c["V"] / c["rho"] / c["Cp"] * (Tc - T)
+    return torch.cat([dCadt, dTdt], dim=-1)
+
+
+def rhs_duffing(x, u, alpha, beta, delta, gamma, omega):
+    """``DuffingParam.ode_equations`` (reference dynamics/ode.py:254-262); the input is time"""
+    x0, x1, t = x[:, [0]], x[:, [1]], u
+    return torch.cat([x1, -delta * x1 - alpha * x0 - beta * x0 ** 3 + gamma * torch.cos(omega * t)], dim=-1)
+
+
+def rhs_brusselator(x, alpha, beta):
+    """``BrusselatorParam.ode_equations`` (reference dynamics/ode.py:276-281)"""
+    x1, x2 = x[:, [0]], x[:, [-1]]
+    return torch.cat([alpha + x2 * x1 ** 2 - beta * x1 - x1, beta * x1 - x2 * x1 ** 2], dim=-1)
+
+
+def rhs_lotka_volterra(x, alpha):
+    """``LotkaVolterraParam.ode_equations`` (reference dynamics/ode.py:344-349)"""
+    x1, x2 = x[:, [0]], x[:, [-1]]
+    return torch.cat([alpha * x1 - 0.4 * x1 * x2, 0.1 * x1 * x2 - 0.4 * x2], dim=-1)
+
+
 def euler_step(f, x, h, *args):
     """``Euler.integrate`` (reference dynamics/integrators.py:153-156)"""
     k1 = f(x, *args)
@@ -124,7 +167,52 @@ def rk4_step(f, x, h, *args):
     return x + h * (k1 / 6.0 + k2 / 3.0 + k3 / 3.0 + k4 / 6.0)
 
 
-INTEGRATORS = {"euler": euler_step, "rk2": rk2_step, "rk4": rk4_step}
+def euler_trap_step(f, x, h, *args):
+    """``Euler_Trap.integrate`` (reference dynamics/integrators.py:169-177)"""
+    pred = x + h * f(x, *args)
+    corr = x + 0.5 * h * (f(x, *args) + f(pred, *args))
+    return corr
+
+
+def rk4_trap_step(f, x, h, *args):
+    """``RK4_Trap.integrate`` (reference dynamics/integrators.py:229-235)"""
+    k1 = f(x, *args)
+    k2 = f(x + h * k1 / 2.0, *args)
+    k3 = f(x + h * k2 / 2.0, *args)
+    k4 = f(x + h * k3, *args)
+    pred = x + h * (k1 / 6.0 + k2 / 3.0 + k3 / 3.0 + k4 / 6.0)
+    corr = x + 0.5 * h * (f(x, *args) + f(pred, *args))
+    return corr
+
+
+def luther_step(f, x, h, *args):
+    """``Luther.integrate`` (reference dynamics/integrators.py:247-264)"""
+    q = 21 ** 0.5
+    k1 = f(x, *args)
+    k2 = f(x + h * k1, *args)
+    k3 = f(x + h * (3 / 8 * k1 + 1 / 8 * k2), *args)
+    k4 = f(x + h * (8 / 27 * k1 + 2 / 27 * k2 + 8 / 27 * k3), *args)
+    k5 = f(x + h * ((-21 + 9 * q) / 392 * k1 + (-56 + 8 * q) / 392 * k2 + (336 - 48 * q) / 392 * k3 + (-63 + 3 * q) / 392 * k4), *args)
+    k6 = f(x + h * ((-1155 - 255 * q) / 1960 * k1 + (-280 - 40 * q) / 1960 * k2 - 320 * q / 1960 * k3 + (63 + 363 * q) / 1960 * k4
+                    + (2352 + 392 * q) / 1960 * k5), *args)
+    k7 = f(x + h * ((330 + 105 * q) / 180 * k1 + 120 / 180 * k2 + (-200 + 280 * q) / 180 * k3 + (126 - 189 * q) / 180 * k4
+                    + (-686 - 126 * q) / 180 * k5 + (490 - 70 * q) / 180 * k6), *args)
+    return x + h * (1 / 20 * k1 + 16 / 45 * k3 + 49 / 180 * k5 + 49 / 180 * k6 + 1 / 20 * k7)
+
+
+def rkf_step(f, x, h, *args):
+    """``Runge_Kutta_Fehlberg.integrate`` (reference dynamics/integrators.py:287-301), 5th-order output"""
+    k1 = f(x, *args)
+    k2 = f(x + h * k1 / 4, *args)
+    k3 = f(x + 3 * h * k1 / 32 + 9 * h * k2 / 32, *args)
+    k4 = f(x + h * k1 * 1932 / 2197 - 7200 / 2197 * h * k2 + 7296 / 2197 * h * k3, *args)
+    k5 = f(x + h * k1 * 439 / 216 - 8 * h * k2 + 3680 / 513 * h * k3 - 845 / 4104 * h * k4, *args)
+    k6 = f(x - 8 / 27 * h * k1 + 2 * h * k2 - 3544 / 2565 * h * k3 + 1859 / 4104 * h * k4 - 11 / 40 * h * k5, *args)
+    return x + h * (k1 * 16 / 135 + k3 * 6656 / 12825 + k4 * 28561 / 56430 - 9 / 50 * k5 + k6 * 2 / 55)
+
+
+INTEGRATORS = {"euler": euler_step, "rk2": rk2_step, "rk4": rk4_step, "euler_trap": euler_trap_step,
+               "rk4_trap": rk4_trap_step, "luther": luther_step, "rkf": rkf_step}
 
 
 def ssm_step(x, u, d, A, B, E=None):
@@ -256,6 +344,6 @@ def run_case(spec: dict, data: Dict[str, torch.Tensor], want_grad: bool = True) 
            "loss": scored["loss"]}
     if want_grad:
         leaves = [p for p in spec["params"] if p.requires_grad]
-        grads = torch.autograd.grad(scored["loss"], leaves, allow_unused=True)
+        grads = torch.autograd.grad(scored["loss"], leaves, allow_unused=True) if leaves else []
         res["grads"] = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, leaves)]
     return res

@@ -278,6 +278,111 @@ def ref_t_node_policy_euler(ns, nsteps=6):
     return problem, _mlp_params(net) + _mlp_params(rhs), data, ["x", "u"], ["obj", "eff"]
 
 
+def _frz(m):
+    for q in m.parameters():
+        q.requires_grad_(False)
+    return m
+
+
+def ref_t_int_euler_trap_lorenz(ns, nsteps=8):
+    model = ns.system.Node(ns.integrators.Euler_Trap(_frz(ns.ode.LorenzControl()), h=0.01), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=3, outsize=2, hsizes=[12], nonlin=torch.nn.Tanh, min=-2., max=2., method="relu_clamp")
+    system = ns.system.System([ns.system.Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    obj = (v("x") == 0.) ^ 2
+    eff = 0.1 * ((v("u") == 0.) ^ 2)
+    _name([(obj, "obj"), (eff, "eff")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj, eff], []))
+    data = lambda B_, g: {"x": 2.0 * torch.randn(B_, 1, 3, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u"], ["obj", "eff"]
+
+
+def ref_t_int_rk4_trap_cstr(ns, nsteps=6):
+    model = ns.system.Node(ns.integrators.RK4_Trap(_frz(ns.ode.CSTR_Param()), h=0.02), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP_bounds(insize=3, outsize=1, hsizes=[10, 10], nonlin=ns.activations.activations["gelu"], min=280., max=320.)
+    system = ns.system.System([ns.system.Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    v = ns.constraint.variable
+    x, r = v("x"), v("r")
+    obj = (x[:, :, [1]] == r) ^ 2
+    cmax = 5. * (x[:, :, [0]] < 0.9)
+    _name([(obj, "obj"), (cmax, "cmax")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], [cmax]))
+
+    def data(B_, g):
+        x0 = torch.cat([0.8 + 0.2 * torch.rand(B_, 1, 1, generator=g), 300. + 20. * torch.rand(B_, 1, 1, generator=g)], dim=-1)
+        return {"x": x0, "r": 305. + 10. * torch.rand(B_, nsteps + 1, 1, generator=g)}
+    return problem, _mlp_params(net), data, ["x", "u"], ["obj", "cmax"]
+
+
+def ref_t_int_luther_vdp(ns, nsteps=7):
+    ode = ns.ode.VanDerPolControl()
+    ode.mu = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+    model = ns.system.Node(ns.integrators.Luther(ode, h=0.1), ["x", "u"], ["x"], name="model")
+    net = ns.blocks.MLP(insize=2, outsize=1, hsizes=[8, 8], nonlin=torch.nn.ReLU)
+    system = ns.system.System([ns.system.Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    obj = (ns.constraint.variable("x") == 0.) ^ 2
+    _name([(obj, "obj")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], []))
+    return problem, _mlp_params(net), (lambda B_, g: {"x": torch.randn(B_, 1, 2, generator=g)}), ["x", "u"], ["obj"]
+
+
+def ref_t_int_rkf_node(ns, nsteps=6):
+    fx = ns.blocks.MLP(3, 2, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh, hsizes=[16, 16])
+    model = ns.system.Node(ns.integrators.Runge_Kutta_Fehlberg(fx, h=0.1), ["xn", "U"], ["xn"], name="NODE")
+    system = ns.system.System([model], name="system")
+    v = ns.constraint.variable
+    ref = (v("xn")[:, :-1, :] == v("X")) ^ 2
+    _name([(ref, "ref")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([ref], []))
+
+    def data(B_, g):
+        X = torch.randn(B_, nsteps, 2, generator=g)
+        return {"X": X, "xn": X[:, 0:1, :].contiguous(), "U": torch.randn(B_, nsteps, 1, generator=g)}
+    return problem, _mlp_params(fx), data, ["xn"], ["ref"]
+
+
+def ref_t_open_duffing(ns, nsteps=9):
+    model = ns.system.Node(ns.integrators.RK4(_frz(ns.ode.DuffingParam()), h=0.05), ["x", "t"], ["x"], name="model")
+    system = ns.system.System([model], nsteps=nsteps, name="sys")
+    obj = (ns.constraint.variable("x") == 0.) ^ 2
+    _name([(obj, "obj")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], []))
+
+    def data(B_, g):
+        t = (0.05 * torch.arange(nsteps, dtype=torch.float32)).reshape(1, nsteps, 1).repeat(B_, 1, 1)
+        return {"x": torch.randn(B_, 1, 2, generator=g), "t": t}
+    return problem, [], data, ["x"], ["obj"]
+
+
+def _ref_t_auto(ns, plant, integ, h, nsteps, norm, target, scale, shift):
+    model = ns.system.Node(integ(_frz(plant), h=h), ["x"], ["x"], name="model")
+    system = ns.system.System([model], nsteps=nsteps, name="sys")
+    obj = (ns.constraint.variable("x") == target) ^ norm
+    _name([(obj, "obj")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], []))
+    nx = plant.out_features
+    return problem, [], (lambda B_, g: {"x": shift + scale * torch.rand(B_, 1, nx, generator=g)}), ["x"], ["obj"]
+
+
+def ref_t_auto_brusselator(ns, nsteps=8):
+    plant = ns.ode.BrusselatorParam()
+    plant.alpha = nn.Parameter(torch.tensor([1.0]), requires_grad=False)
+    plant.beta = nn.Parameter(torch.tensor([3.0]), requires_grad=False)
+    return _ref_t_auto(ns, plant, ns.integrators.RK2, 0.05, nsteps, 1, 1., 2.0, 0.5)
+
+
+def ref_t_auto_lotka(ns, nsteps=8):
+    return _ref_t_auto(ns, ns.ode.LotkaVolterraParam(), ns.integrators.Euler, 0.1, nsteps, 2, 1., 3.0, 0.5)
+
+
+def ref_t_auto_lorenz(ns, nsteps=8):
+    plant = ns.ode.LorenzParam()
+    plant.rho = nn.Parameter(torch.tensor([28.0]), requires_grad=False)
+    plant.sigma = nn.Parameter(torch.tensor([10.0]), requires_grad=False)
+    plant.beta = nn.Parameter(torch.tensor([2.66667]), requires_grad=False)
+    return _ref_t_auto(ns, plant, ns.integrators.RK4, 0.01, nsteps, 2, 0., 10.0, -5.0)
+
+
 def _ref_t_preview(ns, pad_mode, nsteps=9):
     ode = ns.ode.TwoTankParam()
     ode.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
@@ -309,6 +414,10 @@ REF_BUILDERS = {
     "t_vdp_rk4_tanh_clamp": (ref_t_vdp_rk4_tanh_clamp, 16), "t_vdp_euler_elu": (ref_t_vdp_euler_elu, 16),
     "t_twotank_rk2_sigmoid": (ref_t_twotank_rk2_sigmoid, 16), "t_ssm_softplus": (ref_t_ssm_softplus, 16),
     "t_node_policy_euler": (ref_t_node_policy_euler, 16),
+    "t_int_euler_trap_lorenz": (ref_t_int_euler_trap_lorenz, 12), "t_int_rk4_trap_cstr": (ref_t_int_rk4_trap_cstr, 12),
+    "t_int_luther_vdp": (ref_t_int_luther_vdp, 12), "t_int_rkf_node": (ref_t_int_rkf_node, 12),
+    "t_open_duffing": (ref_t_open_duffing, 12), "t_auto_brusselator": (ref_t_auto_brusselator, 12),
+    "t_auto_lotka": (ref_t_auto_lotka, 12), "t_auto_lorenz": (ref_t_auto_lorenz, 12),
     "t_preview_replicate": (ref_t_preview_replicate, 12), "t_preview_circular": (ref_t_preview_circular, 12),
     "t_preview_constant": (ref_t_preview_constant, 12), "t_preview_reflect": (ref_t_preview_reflect, 12),
 }
@@ -318,7 +427,8 @@ def run_reference(problem, params, batch, traj_keys, term_names):
     for p in params:
         p.grad = None
     out = problem({**batch, "name": "train"})
-    out["train_loss"].backward()
+    if params:
+        out["train_loss"].backward()
     return {"traj": {k: out[f"train_{k}"].detach() for k in traj_keys},
             "terms": {n: out[f"train_{n}"].detach() for n in term_names},
             "objective_loss": torch.as_tensor(out["train_objective_loss"]).detach(),
@@ -339,6 +449,8 @@ def main() -> int:
         ref = run_reference(problem, params, batch, traj_keys, term_names)
         plist = [p.detach().clone().requires_grad_(True) for p in params]
         spec = ocases.build(name, plist)
+        if not plist:
+            spec["params"] = []
         ora = dpc_oracle.run_case(spec, batch)
         checks = {}
         for k in traj_keys:

@@ -36,13 +36,16 @@ def product_run(case, batch, backward=True):
         params = [p for p in case.plan_params if p.requires_grad]
         for p in params:
             p.grad = None
-        out["train_loss"].backward()
+        if params:                                   # simulation-only cases have nothing to differentiate
+            out["train_loss"].backward()
         res["grads"] = [p.grad.detach().cpu().clone() for p in params]
     return res
 
 
 def oracle_run(name, params_cpu, batch_cpu, dtype=torch.float32, backward=True, **kw):
     params = [p.detach().to(dtype).clone().requires_grad_(True) for p in params_cpu]
+    if not params:
+        params = []
     data = {k: (v.to(dtype) if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
     spec = ocases.build(name, params, **kw)
     return dpc_oracle.run_case(spec, data, want_grad=backward)
