@@ -29,7 +29,7 @@ for p_ in (ROOT, os.path.join(ROOT, "tests")):
 
 METRIC = "DPC train-step trajectory-steps/sec (fwd+bwd)"
 UNIT = "trajectory-steps/s"
-CPU_SAMPLE_BATCH = {"c1": 3333, "c2": 8192, "c3": 2048, "c4": 2048, "c5": 256}
+CPU_SAMPLE_BATCH = {"c1": 3333, "c2": 8192, "c3": 2048, "c4": 2048, "c4p": 2048, "c5": 256}
 
 
 def read_peaks():
@@ -146,6 +146,7 @@ def main():
                            "c2": "DPC reference tracking, TwoTank ODE + RK4, MLP_bounds 4-32-32-2 GELU",
                            "c3": "neural-ODE system ID, RK4 over MLP RHS 2-60-60-60-2 ReLU",
                            "c4": "building thermal DPC, linear SSM nx=4, 48-step preview, MLP_bounds 193-32-32-1",
+                           "c4p": "c4 with SystemPreview windows over the raw signals (in-kernel gather)",
                            "c5": "parametric nonlinear DPC, 12-state coupled VdP + RK4, MLP 24-128x4-6 GELU"}.get(args.workload, args.workload)}
 
     # ------------------------------------------------------------------ reference arm (CPU)

@@ -200,6 +200,47 @@ def c4(seed=0, nsteps=96, horizon=48) -> Case:
     return Case("c4", problem, system, nsteps, 131072, make_batch, 43.7e3, 1600.0)
 
 
+def c4p(seed=0, nsteps=96, horizon=48) -> Case:
+    """C4 written with ``SystemPreview``: the policy previews the RAW disturbance / comfort-band / price
+    signals (window = horizon) instead of reading materialised look-ahead tensors.  Same arithmetic as c4 --
+    look-ahead column j*D+d at step t IS signal entry t+j -- with 1/48 of the exogenous HBM traffic."""
+    torch.manual_seed(seed)
+    nx, nu, nd, ny = 4, 1, 3, 1
+    A, Bm, E, Cm = (torch.tensor(m) for m in (C4_A, C4_B, C4_E, C4_C))
+    ssm = ode.SSM(_frozen_linear(A), _frozen_linear(Bm), nx, nu, fd=_frozen_linear(E), nd=nd)
+    state_model = Node(ssm, ["x", "u", "d"], ["x"], name="SSM")
+    obs_model = Node(_frozen_linear(Cm), ["x"], ["y"], name="y=Cx")
+    raw = ["d_obs", "ymin", "ymax", "price"]
+    net = blocks.MLP_bounds(insize=ny + horizon * 4, outsize=nu, hsizes=[32, 32], nonlin=nn.LeakyReLU,
+                            min=torch.tensor([0.0]), max=torch.tensor([5000.0]))
+    policy = Node(net, ["y"] + raw, ["u"], name="policy")
+    system = SystemPreview([obs_model, policy, state_model], nsteps=nsteps, name="cl_system",
+                           preview_keys_map={k: ["policy"] for k in raw}, preview_length={k: horizon - 1 for k in raw},
+                           pad_mode="replicate")
+    y_var, u_var = variable("y"), variable("u")
+    price_loss = 1 * ((u_var * variable("price")[:, :nsteps, 0:1]) == torch.zeros_like(u_var)) ^ 2
+    comfort_lower = 5e06 * (y_var > variable("ymin")[:, :nsteps, 0:1])
+    comfort_upper = 5e06 * (y_var < variable("ymax")[:, :nsteps, 0:1])
+    price_loss.name, comfort_lower.name, comfort_upper.name = "price_loss", "y_min", "y_max"
+    problem = Problem([system], PenaltyLoss([price_loss], [comfort_lower, comfort_upper]))
+
+    def make_batch(Bn, device, s=0):
+        g = _gen(device, 4000 + s)                       # same stream as c4.make_batch -> same signals
+        Tn = nsteps + horizon
+        ymin = (18.0 + 4.5 * torch.rand(Bn, 1, ny, generator=g)).repeat(1, Tn, 1)
+        ymax = (22.5 + 4.5 * torch.rand(Bn, 1, ny, generator=g)).repeat(1, Tn, 1)
+        dist = torch.randn(Bn, Tn, nd, generator=g)
+        dist[:, :, 0] = 5.0 + 8.0 * dist[:, :, 0]
+        price = 0.05 + 0.2 * torch.rand(Bn, Tn, 1, generator=g)
+        x0 = 20.0 + torch.randn(Bn, 1, nx, generator=g)
+        batch = {"x": x0, "d": dist[:, :nsteps, :].contiguous(), "d_obs": dist[:, :, 0:1].contiguous(),
+                 "ymin": ymin.contiguous(), "ymax": ymax.contiguous(), "price": price.contiguous()}
+        out = {k: v.to(device) for k, v in batch.items()}
+        out["name"] = "train"
+        return out
+    return Case("c4p", problem, system, nsteps, 131072, make_batch, 43.7e3, 100.0)
+
+
 # ------------------------------------------------------------------------------------------- C5
 def c5(seed=0, nsteps=200) -> Case:
     torch.manual_seed(seed)
@@ -520,7 +561,7 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
 }
 # shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
-EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index}
+EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index, "c4p": c4p}
 AOT_CASES = list(CASES) + list(EXTRA_CASES)
 
 

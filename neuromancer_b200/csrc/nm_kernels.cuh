@@ -408,19 +408,25 @@ __device__ __forceinline__ void build_policy_input(const NmPlan& p, const float*
       constexpr int D = S::seg_sub(s);
       const int Tk = p.exo[e].steps;
       const float* __restrict__ base = exo[e] + b * Tk * D;
-#pragma unroll 4
-      for (int j = 0; j < W / D; ++j) {
-        int ts = t + j;
-        bool fill = false;
-        if (ts >= Tk) {
-          if (p.pad_mode == NM_PAD_REPLICATE) ts = Tk - 1;
-          else if (p.pad_mode == NM_PAD_CIRCULAR) ts -= Tk;            // pad length L <= ... one wrap (ts < Tk + L)
-          else if (p.pad_mode == NM_PAD_REFLECT) ts = 2 * (Tk - 1) - ts;
-          else fill = true;
-          if (p.pad_mode == NM_PAD_CIRCULAR) ts %= Tk;
-        }
+      if (t + W / D <= Tk) {
+        // whole window inside the signal: W contiguous floats starting at entry t (time-major flatten)
+        const float* __restrict__ src = base + t * D;
+#pragma unroll 8
+        for (int i = 0; i < W; ++i) a0[(off + i) * LD + tid] = __ldg(src + i);
+      } else {
+#pragma unroll 2
+        for (int j = 0; j < W / D; ++j) {
+          int ts = t + j;
+          bool fill = false;
+          if (ts >= Tk) {
+            if (p.pad_mode == NM_PAD_REPLICATE) ts = Tk - 1;
+            else if (p.pad_mode == NM_PAD_CIRCULAR) ts = (ts - Tk) % Tk;
+            else if (p.pad_mode == NM_PAD_REFLECT) ts = 2 * (Tk - 1) - ts;
+            else fill = true;
+          }
 #pragma unroll
-        for (int dd = 0; dd < D; ++dd) a0[(off + j * D + dd) * LD + tid] = fill ? p.pad_value : __ldg(base + ts * D + dd);
+          for (int dd = 0; dd < D; ++dd) a0[(off + j * D + dd) * LD + tid] = fill ? p.pad_value : __ldg(base + ts * D + dd);
+        }
       }
     } else {
       constexpr int e = S::seg_index(s);

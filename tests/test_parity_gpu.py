@@ -236,3 +236,21 @@ def test_preview_window_indexing_bit_exact(pad_mode):
             want[:, i + 1, 0] = flat[:, pick[0]]
             want[:, i + 1, 1] = flat[:, pick[1]]
         assert torch.equal(out["x"].cpu(), want), (pad_mode, pick)
+
+
+def test_c4_preview_formulation_equals_materialised_lookahead():
+    """C4 with SystemPreview windows over the raw signals reproduces C4 with materialised look-ahead
+    tensors (grid_response.ipynb) -- identical arithmetic, so trajectories agree bitwise and gradients to
+    round-off of the (differently split) weight-gradient partial sums."""
+    a = H.make_case("c4", DEV, seed=2)
+    b = H.make_case("c4p", DEV, seed=2)
+    with torch.no_grad():
+        for q, src in zip(b.plan_params, a.plan_params):
+            q.copy_(src)
+    ra = H.product_run(a, to_dev(a.make_batch(150, "cpu", 3)))
+    rb = H.product_run(b, to_dev(b.make_batch(150, "cpu", 3)))
+    for k in ("x", "u", "y"):
+        assert torch.equal(ra["traj"][k], rb["traj"][k]), k
+    assert_rel(rb["loss"], ra["loss"], 1e-6, "loss")
+    for ga, gb in zip(ra["grads"], rb["grads"]):
+        assert_rel(gb, ga, 1e-5, "grad")

@@ -1,6 +1,6 @@
 #!/bin/bash
 # bench every workload once (kernel path only) and print a one-line summary each
-for spec in "c1 3333" "c2 65536" "c3 262144" "c4 131072" "c5 16384"; do
+for spec in "c1 3333" "c2 65536" "c3 262144" "c4 131072" "c4p 131072" "c5 16384"; do
   set -- $spec
   python bench.py --workload $1 --batch $2 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
