@@ -102,7 +102,7 @@ struct KCfg {
   static constexpr size_t FWD_SMEM_BYTES = size_t(FWD_SMEM_FLOATS) * 4, BWD_SMEM_BYTES = size_t(BWD_SMEM_FLOATS) * 4;
   static constexpr bool DW_SPILL = (PolCfg::dw_regs() + RhsCfg::dw_regs()) > 112;   // accumulators do not fit the RF
   static constexpr int N_PARAMS = PolCfg::N_PARAMS + RhsCfg::N_PARAMS;
-  static constexpr bool FITS = FWD_SMEM_BYTES <= 227 * 1024 && BWD_SMEM_BYTES <= 227 * 1024;
+  static constexpr bool FITS_FWD = FWD_SMEM_BYTES <= 227 * 1024, FITS_BWD = BWD_SMEM_BYTES <= 227 * 1024;
 };
 
 struct FwdArgs {

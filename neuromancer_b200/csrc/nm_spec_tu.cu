@@ -26,7 +26,9 @@ struct Tiled : Shape {
   static constexpr int MINB_FWD = NM_TUNE_MINB_FWD, MINB_BWD = NM_TUNE_MINB_BWD;   // __launch_bounds__ min CTAs / SM
 };
 
-// widest layer decides the CTA size; the largest batch tile whose buffers fit in 227 KB wins
+// widest layer decides the CTA size; the forward and the adjoint kernel are tiled independently (the
+// trajectory layout in HBM does not depend on the tile): each takes the largest batch tile whose buffers fit
+// in 227 KB, preferring weights staged in shared memory over weights streamed from L2.
 constexpr int shape_max_width() {
   int m = 1;
   for (int l = 0; l <= NM_SPEC_NAME::Pol::NL; ++l) m = cmax(m, NM_SPEC_NAME::Pol::sz(l));
@@ -34,25 +36,44 @@ constexpr int shape_max_width() {
   return m;
 }
 #ifdef NM_TUNE_THREADS
-constexpr int kThreads = NM_TUNE_THREADS;
+constexpr int kThreadsF = NM_TUNE_THREADS, kThreadsB = NM_TUNE_THREADS;
 #else
-constexpr int kThreads = shape_max_width() >= 96 ? 256 : 128;
+// adjoint kernel: 256 threads for wide layers, and whenever the keep-all activation buffers leave room for only
+// ONE resident CTA per SM (measured on c3: 8 warps/SM instead of 4 -> adjoint 57 ms instead of 69 ms)
+constexpr bool kOneCtaPerSm = KCfg<Tiled<NM_SPEC_NAME, 128, 128, true>>::BWD_SMEM_BYTES > 113 * 1024 + 512;
+constexpr int kThreadsB = (shape_max_width() >= 96 || kOneCtaPerSm) ? 256 : 128;
+#ifdef NM_TUNE_THREADS_FWD
+constexpr int kThreadsF = NM_TUNE_THREADS_FWD;
+#else
+constexpr int kThreadsF = shape_max_width() >= 96 ? 256 : 128;
 #endif
-template <int TILE, bool WS> constexpr bool fits() { return KCfg<Tiled<NM_SPEC_NAME, TILE, kThreads, WS>>::FITS; }
-// preference: weights staged in shared memory with the largest tile; else weights streamed from L2
+#endif
+template <int TILE, int THREADS, bool WS> constexpr bool fits_f() { return KCfg<Tiled<NM_SPEC_NAME, TILE, THREADS, WS>>::FITS_FWD; }
+template <int TILE, int THREADS, bool WS> constexpr bool fits_b() { return KCfg<Tiled<NM_SPEC_NAME, TILE, THREADS, WS>>::FITS_BWD; }
 #ifdef NM_TUNE_TILE
-constexpr bool kWSmem = fits<NM_TUNE_TILE, true>();
+constexpr bool kWSmemF = fits_f<NM_TUNE_TILE, kThreadsF, true>(), kWSmemB = fits_b<NM_TUNE_TILE, kThreadsB, true>();
+constexpr int kTileF = NM_TUNE_TILE, kTileB = NM_TUNE_TILE;
 #else
-constexpr bool kWSmem = fits<128, true>() || fits<64, true>();
-#endif
-#ifdef NM_TUNE_TILE
-constexpr int kTile = NM_TUNE_TILE;
+#ifdef NM_TUNE_TILE_FWD
+constexpr bool kWSmemF = fits_f<NM_TUNE_TILE_FWD, kThreadsF, true>();
+constexpr int kTileF = NM_TUNE_TILE_FWD;
 #else
-constexpr int kTile = kWSmem ? (fits<128, true>() ? 128 : 64) : (fits<128, false>() ? 128 : (fits<64, false>() ? 64 : 32));
+constexpr bool kWSmemF = fits_f<128, kThreadsF, true>() || fits_f<64, kThreadsF, true>();
+// weights streamed from L2 (they do not fit): measured on c5, a 64-trajectory forward tile with more resident
+// CTAs hides the L2 latency better than one 128-trajectory tile (13.4 vs 17.3 ms)
+constexpr int kTileF = kWSmemF ? (fits_f<128, kThreadsF, true>() ? 128 : 64)
+                               : (fits_f<64, kThreadsF, false>() ? 64 : 32);
 #endif
-using S = Tiled<NM_SPEC_NAME, kTile, kThreads, kWSmem>;
-using KC = KCfg<S>;
-static_assert(KC::FITS, "shape class does not fit in shared memory even with a 32-trajectory tile");
+constexpr bool kWSmemB = fits_b<128, kThreadsB, true>() || fits_b<64, kThreadsB, true>();
+constexpr int kTileB = kWSmemB ? (fits_b<128, kThreadsB, true>() ? 128 : 64)
+                               : (fits_b<128, kThreadsB, false>() ? 128 : (fits_b<64, kThreadsB, false>() ? 64 : 32));
+#endif
+using SF = Tiled<NM_SPEC_NAME, kTileF, kThreadsF, kWSmemF>;     // forward (rollout) kernel
+using SB = Tiled<NM_SPEC_NAME, kTileB, kThreadsB, kWSmemB>;     // adjoint kernel
+using S = SB;
+using KCF = KCfg<SF>;
+using KC = KCfg<SB>;
+static_assert(KCF::FITS_FWD && KC::FITS_BWD, "shape class does not fit in shared memory even with a 32-trajectory tile");
 
 struct DeviceInfo { int sms = 0; int occ_fwd = 0; int occ_bwd = 0; bool ready = false; };
 DeviceInfo g_dev[64];
@@ -65,9 +86,9 @@ int device_info(DeviceInfo** out) {
   DeviceInfo& d = g_dev[dev];
   if (!d.ready) {
     cudaError_t e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::FWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_fwd_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KCF::FWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::BWD_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fwd, nm_fwd_kernel<S>, S::THREADS, KC::FWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fwd, nm_fwd_kernel<SF>, SF::THREADS, KCF::FWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_bwd, nm_bwd_kernel<S>, S::THREADS, KC::BWD_SMEM_BYTES);
     if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
     if (d.occ_fwd < 1 || d.occ_bwd < 1) { nm_set_error("kernel does not fit on an SM (occupancy 0)"); return NM_ERR_CUDA; }
@@ -97,9 +118,9 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   int sms = 148, occf = 8, occb = 8, ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && device_info(&d) == NM_OK) { sms = d->sms; occf = d->occ_fwd; occb = d->occ_bwd; }
   else { (void)cudaGetLastError(); }
-  const int64_t tiles = (B + S::TILE - 1) / S::TILE;
-  const int64_t gf = tiles < int64_t(sms) * occf ? tiles : int64_t(sms) * occf;
-  const int64_t gb = tiles < int64_t(sms) * occb ? tiles : int64_t(sms) * occb;
+  const int64_t tiles_f = (B + SF::TILE - 1) / SF::TILE, tiles_b = (B + SB::TILE - 1) / SB::TILE;
+  const int64_t gf = tiles_f < int64_t(sms) * occf ? tiles_f : int64_t(sms) * occf;
+  const int64_t gb = tiles_b < int64_t(sms) * occb ? tiles_b : int64_t(sms) * occb;
   *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
   *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float));
   return NM_OK;
@@ -119,7 +140,7 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   DeviceInfo* d = nullptr; rc = device_info(&d); if (rc != NM_OK) return rc;
   size_t need_f = 0, need_b = 0; workspace_fn(p, c->B, &need_f, &need_b);
   if (c->workspace_bytes < need_f || (reinterpret_cast<uintptr_t>(c->workspace) & 255)) { nm_set_error("forward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
-  const int tiles = int((c->B + S::TILE - 1) / S::TILE);
+  const int tiles = int((c->B + SF::TILE - 1) / SF::TILE);
   int grid = d->sms * d->occ_fwd; if (grid > tiles) grid = tiles; if (grid < 1) grid = 1;
   char* ws = static_cast<char*>(c->workspace);
   float* wprep = reinterpret_cast<float*>(ws);
@@ -132,7 +153,7 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
   a.B = c->B; a.num_tiles = tiles;
-  nm_fwd_kernel<S><<<grid, S::THREADS, KC::FWD_SMEM_BYTES, c->stream>>>(*p, a);
+  nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
   return NM_OK;
@@ -170,8 +191,9 @@ NmKernelEntry g_entry;
 
 struct Registrar {
   Registrar() {
-    std::snprintf(g_info, sizeof(g_info), "tile=%d threads=%d minb=%d/%d compiled_terms=%d w_smem=%d smem_fwd=%zu smem_bwd=%zu dw_spill=%d wprep_floats=%d",
-                  S::TILE, S::THREADS, S::MINB_FWD, S::MINB_BWD, S::NTERMS, int(S::W_SMEM), KC::FWD_SMEM_BYTES, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), KC::W_FLOATS_ALL);
+    std::snprintf(g_info, sizeof(g_info), "fwd[tile=%d threads=%d w_smem=%d smem=%zu] bwd[tile=%d threads=%d w_smem=%d smem=%zu dw_spill=%d] minb=%d/%d compiled_terms=%d wprep_floats=%d",
+                  SF::TILE, SF::THREADS, int(SF::W_SMEM), KCF::FWD_SMEM_BYTES, SB::TILE, SB::THREADS, int(SB::W_SMEM), KC::BWD_SMEM_BYTES,
+                  int(KC::DW_SPILL), S::MINB_FWD, S::MINB_BWD, S::NTERMS, KC::W_FLOATS_ALL);
     g_entry.signature = NM_SPEC_NAME::signature();
     g_entry.term_signature = NM_SPEC_NAME::term_signature();
     g_entry.workspace = workspace_fn;
