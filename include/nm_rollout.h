@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NM_ABI_VERSION 5
+#define NM_ABI_VERSION 6
 
 #define NM_MAX_LAYERS 8   /* linear layers per MLP                                   */
 #define NM_MAX_SEGS   8   /* concatenated inputs of the policy (blocks.py:39-43)     */
@@ -224,6 +224,12 @@ int nm_struct_sizes(int* out, int cap);
  * for a plan whose shape class was not compiled ahead of time).  Returns NM_OK or NM_ERR_*. */
 int nm_load_plugin(const char* path);
 
+/* Size in bytes of the optional checkpoint buffer for a batch of B trajectories (0 when the plan has none).
+ * The emitted x trajectory is always the per-step checkpoint of the adjoint; plans with an MLP right-hand
+ * side can additionally keep the stage derivatives k_0..k_{NS-2} of every integrator step
+ * ([B, nsteps, (NS-1)*nx] fp32) so that the adjoint skips its first recompute pass. */
+int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes);
+
 /* Device workspace sizes in bytes for a batch of B trajectories. */
 int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes, size_t* bwd_bytes);
 
@@ -247,8 +253,8 @@ int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes,
  */
 int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
                        const float* const* exo, float* x_traj, float* u_traj, float* y_traj,
-                       float* scalars, void* workspace, size_t workspace_bytes, int64_t B,
-                       void* stream);
+                       float* scalars, float* checkpoints /* nm_rollout_checkpoint_bytes, or NULL */,
+                       void* workspace, size_t workspace_bytes, int64_t B, void* stream);
 
 /*
  * Adjoint / backward-through-time pass.
@@ -264,6 +270,7 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
  */
 int nm_rollout_backward(const NmPlan* plan, const float* params, const float* const* exo,
                         const float* x_traj, const float* u_traj, const float* y_traj,
+                        const float* checkpoints /* written by the forward call, or NULL: recompute */,
                         const float* grad_scalars, const float* grad_x_ext, const float* grad_u_ext,
                         const float* grad_y_ext, float* grad_params, float* grad_x0,
                         void* workspace, size_t workspace_bytes, int64_t B, int64_t b_total,

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-NM_ABI_VERSION = 5
+NM_ABI_VERSION = 6
 NM_MAX_LAYERS, NM_MAX_SEGS, NM_MAX_EXO, NM_MAX_TERMS, NM_MAX_DIM = 8, 8, 8, 16, 16
 
 NM_OK, NM_ERR_BAD_PLAN, NM_ERR_NO_KERNEL, NM_ERR_CUDA, NM_ERR_WORKSPACE, NM_ERR_ABI = 0, -1, -2, -3, -4, -5
@@ -101,10 +101,12 @@ def _declare(lib):
     lib.nm_load_plugin.restype = C.c_int
     lib.nm_rollout_workspace_bytes.argtypes = [P(NmPlan), C.c_int64, P(C.c_size_t), P(C.c_size_t)]
     lib.nm_rollout_workspace_bytes.restype = C.c_int
-    lib.nm_rollout_forward.argtypes = [P(NmPlan), fp, fp, P(C.c_void_p), fp, fp, fp, fp, vp,
+    lib.nm_rollout_checkpoint_bytes.argtypes = [P(NmPlan), C.c_int64, P(C.c_size_t)]
+    lib.nm_rollout_checkpoint_bytes.restype = C.c_int
+    lib.nm_rollout_forward.argtypes = [P(NmPlan), fp, fp, P(C.c_void_p), fp, fp, fp, fp, fp, vp,
                                        C.c_size_t, C.c_int64, vp]
     lib.nm_rollout_forward.restype = C.c_int
-    lib.nm_rollout_backward.argtypes = [P(NmPlan), fp, P(C.c_void_p), fp, fp, fp, fp, fp, fp, fp,
+    lib.nm_rollout_backward.argtypes = [P(NmPlan), fp, P(C.c_void_p), fp, fp, fp, fp, fp, fp, fp, fp,
                                         fp, fp, vp, C.c_size_t, C.c_int64, C.c_int64, vp]
     lib.nm_rollout_backward.restype = C.c_int
     lib.nm_last_launch_count.restype = C.c_int
@@ -118,7 +120,7 @@ EXPORTED_SYMBOLS = [
     "nm_abi_version", "nm_last_error", "nm_plan_signature", "nm_has_kernel", "nm_num_kernels",
     "nm_kernel_signature", "nm_load_plugin", "nm_rollout_workspace_bytes", "nm_rollout_forward",
     "nm_rollout_backward", "nm_last_launch_count", "nm_kernel_info", "nm_struct_sizes",
-    "nm_plan_term_signature",
+    "nm_plan_term_signature", "nm_rollout_checkpoint_bytes",
 ]
 
 

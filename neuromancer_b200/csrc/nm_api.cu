@@ -357,6 +357,23 @@ int nm_load_plugin(const char* path) {
   return NM_OK;                                     // the plugin's static registrar ran during dlopen
 }
 
+// stage derivatives kept per integrator step for MLP right-hand sides
+static int integrator_stages(int integ) {
+  switch (integ) { case NM_INT_EULER: return 1; case NM_INT_RK2: case NM_INT_EULER_TRAP: return 2; case NM_INT_RK4: return 4;
+                   case NM_INT_RK4_TRAP: return 5; case NM_INT_RKF: return 6; case NM_INT_LUTHER: return 7; default: return 1; }
+}
+int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes) {
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  if (!bytes || B < 1) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
+  *bytes = 0;
+  if (plan->dyn_kind == NM_DYN_ODE && plan->rhs_kind == NM_RHS_MLP) {
+    const int ns = integrator_stages(plan->integrator);
+    *bytes = size_t(B) * size_t(plan->nsteps) * size_t(ns - 1) * size_t(plan->nx) * sizeof(float);
+  }
+  return NM_OK;
+}
+
 int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes, size_t* bwd_bytes) {
   int rc = validate(plan);
   if (rc != NM_OK) return rc;
@@ -372,8 +389,8 @@ int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes,
 }
 
 int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0, const float* const* exo,
-                       float* x_traj, float* u_traj, float* y_traj, float* scalars, void* workspace,
-                       size_t workspace_bytes, int64_t B, void* stream) {
+                       float* x_traj, float* u_traj, float* y_traj, float* scalars, float* checkpoints,
+                       void* workspace, size_t workspace_bytes, int64_t B, void* stream) {
   g_launches = 0;
   int rc = validate(plan);
   if (rc != NM_OK) return rc;
@@ -389,7 +406,7 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   const size_t need = align256(spec_f) + align256(size_t(sgrid) * NM_MAX_TERMS * sizeof(double));
   if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) { nm_set_error("forward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
   NmFwdCall c{};
-  c.params = params; c.x0 = x0; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
+  c.params = params; c.x0 = x0; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj; c.checkpoints = checkpoints;
   c.workspace = workspace; c.workspace_bytes = align256(spec_f); c.B = B; c.stream = static_cast<cudaStream_t>(stream);
   c.fused_terms = fused;
   rc = e->forward(plan, &c);
@@ -410,7 +427,8 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
 }
 
 int nm_rollout_backward(const NmPlan* plan, const float* params, const float* const* exo, const float* x_traj,
-                        const float* u_traj, const float* y_traj, const float* grad_scalars, const float* grad_x_ext,
+                        const float* u_traj, const float* y_traj, const float* checkpoints, const float* grad_scalars,
+                        const float* grad_x_ext,
                         const float* grad_u_ext, const float* grad_y_ext, float* grad_params, float* grad_x0,
                         void* workspace, size_t workspace_bytes, int64_t B, int64_t b_total, void* stream) {
   g_launches = 0;
@@ -428,7 +446,7 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
   const size_t need = align256(spec_b) + (pre ? align256(gbuf_floats(plan, B) * sizeof(float)) : 0);
   if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255)) { nm_set_error("backward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
   NmBwdCall c{};
-  c.params = params; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj;
+  c.params = params; c.exo = exo; c.x_traj = x_traj; c.u_traj = u_traj; c.y_traj = y_traj; c.checkpoints = checkpoints;
   c.grad_scalars = grad_scalars; c.gx_ext = grad_x_ext; c.gu_ext = grad_u_ext; c.gy_ext = grad_y_ext;
   c.grad_x0 = grad_x0; c.workspace = workspace; c.workspace_bytes = align256(spec_b); c.B = B; c.b_total = b_total;
   c.stream = static_cast<cudaStream_t>(stream);

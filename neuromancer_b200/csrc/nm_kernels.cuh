@@ -109,6 +109,7 @@ struct FwdArgs {
   const float* params; const float* wprep; const float* x0;
   const float* exo[NM_MAX_EXO];
   float* x_traj; float* u_traj; float* y_traj;
+  float* chk;                       // stage-derivative checkpoints [B][T][(NS-1)*NX] (MLP right-hand side), or null
   double* term_partials;            // [grid][NM_MAX_TERMS], written when fused_terms
   int fused_terms;                  // the plan's terms match the compiled term structure of S
   int64_t B; int num_tiles;
@@ -117,6 +118,7 @@ struct BwdArgs {
   const float* params; const float* wprep;
   const float* exo[NM_MAX_EXO];
   const float* x_traj; const float* u_traj; const float* y_traj;
+  const float* chk;                 // stage-derivative checkpoints written by the forward kernel, or null
   const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
   // loss-term gradients precomputed by nm_term_grad_kernel (already include the *_ext gradients);
   // when null they are evaluated inline in the sweep
@@ -600,6 +602,13 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
             const float* outp = (RhsCfg::NL & 1) ? pp1 : pp0;
 #pragma unroll
             for (int i = 0; i < NX; ++i) k[St][i] = outp[i * LD + tid];
+            if constexpr (St + 1 < NS) {
+              if (valid && args.chk != nullptr) {
+                float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) cp[i] = k[St][i];
+              }
+            }
           }
           // the next writer of pp0/pp1 is this same thread's own column (stage input) or, behind a
           // barrier, the next layer GEMM: no extra barrier needed here
@@ -804,6 +813,13 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
 #pragma unroll
           for (int i = 0; i < NX; ++i) gk[St][i] = 0.f;
           if constexpr (St + 1 < NS) {
+           if (args.chk != nullptr) {                           // kept by the forward kernel: no recompute
+            if (owner) {
+              const float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
+#pragma unroll
+              for (int i = 0; i < NX; ++i) k[St][i] = __ldg(cp + i);
+            }
+           } else {
             if (owner) {
               float xs[NX];
               stage_input<S::INTEG, St, NX>(h, x, k, xs);
@@ -819,6 +835,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
               for (int i = 0; i < NX; ++i) k[St][i] = dbuf0[i * LD + tid];
             }
             __syncthreads();                                     // dbuf0 is rewritten by the next stage
+           }
           }
         });
         // pass 2: stages in reverse, recomputing each stage's activations

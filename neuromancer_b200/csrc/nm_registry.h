@@ -6,14 +6,14 @@
 
 struct NmFwdCall {
   const float* params; const float* x0; const float* const* exo;
-  float* x_traj; float* u_traj; float* y_traj;
+  float* x_traj; float* u_traj; float* y_traj; float* checkpoints;
   void* workspace; size_t workspace_bytes; int64_t B; cudaStream_t stream;
   int fused_terms;                                 // in: plan terms match the entry's compiled term structure
   double* term_partials; int grid;                 // out: per-CTA term sums (fused), CTAs launched
 };
 struct NmBwdCall {
   const float* params; const float* const* exo;
-  const float* x_traj; const float* u_traj; const float* y_traj;
+  const float* x_traj; const float* u_traj; const float* y_traj; const float* checkpoints;
   const float* grad_scalars; const float* gx_ext; const float* gu_ext; const float* gy_ext;
   float* grad_x0;
   const float* G_x; const float* G_u; const float* G_y;   // precomputed term gradients or null

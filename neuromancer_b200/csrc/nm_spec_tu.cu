@@ -151,7 +151,7 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   a.term_partials = c->term_partials; a.fused_terms = c->fused_terms;
   a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
-  a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
+  a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj; a.chk = c->checkpoints;
   a.B = c->B; a.num_tiles = tiles;
   nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
@@ -175,7 +175,7 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   BwdArgs a{};
   a.params = c->params; a.wprep = wprep;
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
-  a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj;
+  a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj; a.chk = c->checkpoints;
   a.grad_scalars = c->grad_scalars; a.gx_ext = c->gx_ext; a.gu_ext = c->gu_ext; a.gy_ext = c->gy_ext;
   a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y; a.fused_terms = c->fused_terms;
   a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;

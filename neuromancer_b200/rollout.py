@@ -98,9 +98,15 @@ class FusedRollout(torch.autograd.Function):
         ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
         exo_ptrs = (C.c_void_p * max(n_exo, 1))(*[e.data_ptr() for e in exo])
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        chk = None
+        if any(ctx.needs_input_grad):                 # a backward pass may follow: keep stage checkpoints
+            cb = C.c_size_t()
+            L.check(lib.nm_rollout_checkpoint_bytes(C.byref(p), B, C.byref(cb)), "nm_rollout_checkpoint_bytes")
+            if cb.value:
+                chk = torch.empty(cb.value // 4, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             L.check(lib.nm_rollout_forward(C.byref(p), _ptr(runner.arena.flat), _ptr(x0), exo_ptrs,
-                                           _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(scalars),
+                                           _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(scalars), _ptr(chk),
                                            _ptr(ws), ws.numel(), B, stream), "nm_rollout_forward")
         runner.launches += lib.nm_last_launch_count()
         ctx.runner, ctx.B = runner, B
@@ -108,7 +114,8 @@ class FusedRollout(torch.autograd.Function):
         ctx.n_tensors = len(tensors)
         outs = [x_traj, u_traj if u_traj is not None else x_traj.new_empty(0),
                 y_traj if y_traj is not None else x_traj.new_empty(0), scalars]
-        ctx.save_for_backward(outs[0], outs[1], outs[2], *exo)
+        ctx.has_chk = chk is not None
+        ctx.save_for_backward(outs[0], outs[1], outs[2], chk if chk is not None else x_traj.new_empty(0), *exo)
         ctx.mark_non_differentiable(*[o for o in outs[1:3] if o.numel() == 0])
         return tuple(outs)
 
@@ -122,7 +129,8 @@ class FusedRollout(torch.autograd.Function):
         x_traj = saved[0]
         u_traj = saved[1] if saved[1].numel() else None
         y_traj = saved[2] if saved[2].numel() else None
-        exo = saved[3:]
+        chk = saved[3] if ctx.has_chk else None
+        exo = saved[4:]
         dev = x_traj.device
         B = ctx.B
 
@@ -146,7 +154,7 @@ class FusedRollout(torch.autograd.Function):
         gx0 = torch.empty(B, p.nx, dtype=torch.float32, device=dev) if want_x0 else None
         with torch.cuda.device(dev):
             L.check(lib.nm_rollout_backward(
-                C.byref(p), _ptr(runner.arena.flat), exo_ptrs, _ptr(x_traj), _ptr(u_traj), _ptr(y_traj),
+                C.byref(p), _ptr(runner.arena.flat), exo_ptrs, _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(chk),
                 _ptr(gs), _ptr(gx), _ptr(gu), _ptr(gy), _ptr(gflat), _ptr(gx0), _ptr(ws), ws.numel(),
                 B, B * _WORLD["size"], stream), "nm_rollout_backward")
         runner.launches += lib.nm_last_launch_count()
@@ -306,6 +314,9 @@ class RawTrainStep:
         L.check(self.lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
                 "nm_rollout_workspace_bytes")
         self.ws = torch.empty(max(fwd_b.value, bwd_b.value, 256), dtype=torch.uint8, device=dev)
+        cb = C.c_size_t()
+        L.check(self.lib.nm_rollout_checkpoint_bytes(C.byref(p), B, C.byref(cb)), "nm_rollout_checkpoint_bytes")
+        self.chk = torch.empty(cb.value // 4, dtype=torch.float32, device=dev) if cb.value else None
         self.exo_ptrs = (C.c_void_p * max(len(self.exo), 1))(*[e.data_ptr() for e in self.exo])
         self.launches = 0
 
@@ -316,7 +327,7 @@ class RawTrainStep:
         p = self.plan.c
         L.check(self.lib.nm_rollout_forward(
             C.byref(p), _ptr(self.runner.arena.flat), _ptr(self.x0), self.exo_ptrs, _ptr(self.x_traj),
-            _ptr(self.u_traj), _ptr(self.y_traj), C.c_void_p(self.scalars.data_ptr()), _ptr(self.ws),
+            _ptr(self.u_traj), _ptr(self.y_traj), C.c_void_p(self.scalars.data_ptr()), _ptr(self.chk), _ptr(self.ws),
             self.ws.numel(), self.B, self._stream()), "nm_rollout_forward")
         self.launches += self.lib.nm_last_launch_count()
 
@@ -324,7 +335,7 @@ class RawTrainStep:
         p = self.plan.c
         L.check(self.lib.nm_rollout_backward(
             C.byref(p), _ptr(self.runner.arena.flat), self.exo_ptrs, _ptr(self.x_traj), _ptr(self.u_traj),
-            _ptr(self.y_traj), None, None, None, None, C.c_void_p(self.grad.data_ptr()), None,
+            _ptr(self.y_traj), _ptr(self.chk), None, None, None, None, C.c_void_p(self.grad.data_ptr()), None,
             _ptr(self.ws), self.ws.numel(), self.B, self.B * self.world_size, self._stream()),
             "nm_rollout_backward")
         self.launches += self.lib.nm_last_launch_count()

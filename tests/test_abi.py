@@ -65,5 +65,5 @@ def test_bad_plans_are_rejected(nm_lib):
 
 def test_null_arguments_fail_without_touching_the_device(nm_lib):
     plan = configs.build_case("c1").plan()
-    rc = nm_lib.nm_rollout_forward(C.byref(plan.c), None, None, None, None, None, None, None, None, 0, 8, None)
+    rc = nm_lib.nm_rollout_forward(C.byref(plan.c), None, None, None, None, None, None, None, None, None, 0, 8, None)
     assert rc == L.NM_ERR_BAD_PLAN
