@@ -4,6 +4,7 @@
 #include <cstring>
 #include <mutex>
 #include "nm_kernels.cuh"
+#include "nm_tc_kernels.cuh"
 #include "nm_registry.h"
 
 #include NM_SPEC_HEADER   // defines struct NM_SPEC_NAME (the "Shape")
@@ -75,6 +76,33 @@ using KCF = KCfg<SF>;
 using KC = KCfg<SB>;
 static_assert(KCF::FITS_FWD && KC::FITS_BWD, "shape class does not fit in shared memory even with a 32-trajectory tile");
 
+// tensor-core (tcgen05) forward kernel for neural-ODE shape classes whose hidden layers are wide enough for the
+// tensor pipe to pay (one M=128 MMA costs >= 44 cycles whatever its N: measured, profiles/r01_tcgen05_findings.md)
+using TK = TcKCfg<NM_SPEC_NAME>;
+#ifdef NM_TUNE_TC
+constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && (NM_TUNE_TC != 0);
+#else
+constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && TK::C::max_hidden() >= 48;
+#endif
+
+// launch helpers as class templates so that the tensor-core kernels are only instantiated for eligible classes
+template <class Sp, bool ON> struct TcFwd {
+  static cudaError_t setup(int*) { return cudaSuccess; }
+  static void launch(const NmPlan&, const FwdArgs&, const float*, float*, int, cudaStream_t) {}
+};
+template <class Sp> struct TcFwd<Sp, true> {
+  static cudaError_t setup(int* occ) {
+    cudaError_t e = cudaFuncSetAttribute(nm_tc_fwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcKCfg<Sp>::FWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, nm_tc_fwd_kernel<Sp>, 128, TcKCfg<Sp>::FWD_SMEM_BYTES);
+    if (*occ > TcKCfg<Sp>::MAX_CTAS) *occ = TcKCfg<Sp>::MAX_CTAS;
+    return e;
+  }
+  static void launch(const NmPlan& p, const FwdArgs& a, const float* params, float* wprep, int grid, cudaStream_t st) {
+    nm_tc_prep_fwd_kernel<Sp><<<8, 256, 0, st>>>(p, params, wprep);
+    nm_tc_fwd_kernel<Sp><<<grid, 128, TcKCfg<Sp>::FWD_SMEM_BYTES, st>>>(p, a);
+  }
+};
+
 struct DeviceInfo { int sms = 0; int occ_fwd = 0; int occ_bwd = 0; bool ready = false; };
 DeviceInfo g_dev[64];
 std::mutex g_mu;
@@ -89,6 +117,7 @@ int device_info(DeviceInfo** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_fwd_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KCF::FWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::BWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fwd, nm_fwd_kernel<SF>, SF::THREADS, KCF::FWD_SMEM_BYTES);
+    if (kTcFwd && e == cudaSuccess) e = TcFwd<NM_SPEC_NAME, kTcFwd>::setup(&d.occ_fwd);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_bwd, nm_bwd_kernel<S>, S::THREADS, KC::BWD_SMEM_BYTES);
     if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
     if (d.occ_fwd < 1 || d.occ_bwd < 1) { nm_set_error("kernel does not fit on an SM (occupancy 0)"); return NM_ERR_CUDA; }
@@ -99,7 +128,9 @@ int device_info(DeviceInfo** out) {
 }
 
 constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
-constexpr size_t kWprepBytes = align256(size_t(KC::W_FLOATS_ALL > 0 ? KC::W_FLOATS_ALL : 4) * 4);
+constexpr size_t kWprepFfma = size_t(KC::W_FLOATS_ALL > 0 ? KC::W_FLOATS_ALL : 4) * 4;
+constexpr size_t kWprepBytes = align256(kTcFwd && TK::FWD_W_BYTES > kWprepFfma ? TK::FWD_W_BYTES : kWprepFfma);
+constexpr int kFwdTile = kTcFwd ? 128 : SF::TILE;
 
 int check_plan(const NmPlan* p) {
   if (p->n_params < KC::N_PARAMS) { nm_set_error("plan.n_params smaller than the shape class expects"); return NM_ERR_BAD_PLAN; }
@@ -118,7 +149,7 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   int sms = 148, occf = 8, occb = 8, ndev = 0;
   if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && device_info(&d) == NM_OK) { sms = d->sms; occf = d->occ_fwd; occb = d->occ_bwd; }
   else { (void)cudaGetLastError(); }
-  const int64_t tiles_f = (B + SF::TILE - 1) / SF::TILE, tiles_b = (B + SB::TILE - 1) / SB::TILE;
+  const int64_t tiles_f = (B + kFwdTile - 1) / kFwdTile, tiles_b = (B + SB::TILE - 1) / SB::TILE;
   const int64_t gf = tiles_f < int64_t(sms) * occf ? tiles_f : int64_t(sms) * occf;
   const int64_t gb = tiles_b < int64_t(sms) * occb ? tiles_b : int64_t(sms) * occb;
   *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
@@ -140,20 +171,21 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   DeviceInfo* d = nullptr; rc = device_info(&d); if (rc != NM_OK) return rc;
   size_t need_f = 0, need_b = 0; workspace_fn(p, c->B, &need_f, &need_b);
   if (c->workspace_bytes < need_f || (reinterpret_cast<uintptr_t>(c->workspace) & 255)) { nm_set_error("forward workspace too small or misaligned"); return NM_ERR_WORKSPACE; }
-  const int tiles = int((c->B + SF::TILE - 1) / SF::TILE);
+  const int tiles = int((c->B + kFwdTile - 1) / kFwdTile);
   int grid = d->sms * d->occ_fwd; if (grid > tiles) grid = tiles; if (grid < 1) grid = 1;
   char* ws = static_cast<char*>(c->workspace);
   float* wprep = reinterpret_cast<float*>(ws);
   c->grid = grid;
   c->term_partials = reinterpret_cast<double*>(ws + kWprepBytes);
-  launch_prep(p, c->params, wprep, c->stream);
+  if (!kTcFwd) launch_prep(p, c->params, wprep, c->stream);
   FwdArgs a{};
   a.term_partials = c->term_partials; a.fused_terms = c->fused_terms;
   a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj; a.chk = c->checkpoints;
   a.B = c->B; a.num_tiles = tiles;
-  nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
+  if (kTcFwd) TcFwd<NM_SPEC_NAME, kTcFwd>::launch(*p, a, c->params, wprep, grid, c->stream);
+  else nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
   return NM_OK;
@@ -186,11 +218,16 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   return NM_OK;
 }
 
-char g_info[256];
+char g_info[512];
 NmKernelEntry g_entry;
 
 struct Registrar {
   Registrar() {
+    if (kTcFwd)
+      std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tile=%d threads=%d w_smem=%d smem=%zu dw_spill=%d] minb=%d/%d compiled_terms=%d wprep_floats=%d",
+                    TK::C::FWD_COLS, TK::FWD_SMEM_BYTES, TK::MAX_CTAS, SB::TILE, SB::THREADS, int(SB::W_SMEM), KC::BWD_SMEM_BYTES,
+                    int(KC::DW_SPILL), S::MINB_FWD, S::MINB_BWD, S::NTERMS, KC::W_FLOATS_ALL);
+    else
     std::snprintf(g_info, sizeof(g_info), "fwd[tile=%d threads=%d w_smem=%d smem=%zu] bwd[tile=%d threads=%d w_smem=%d smem=%zu dw_spill=%d] minb=%d/%d compiled_terms=%d wprep_floats=%d",
                   SF::TILE, SF::THREADS, int(SF::W_SMEM), KCF::FWD_SMEM_BYTES, SB::TILE, SB::THREADS, int(SB::W_SMEM), KC::BWD_SMEM_BYTES,
                   int(KC::DW_SPILL), S::MINB_FWD, S::MINB_BWD, S::NTERMS, KC::W_FLOATS_ALL);
