@@ -1,13 +1,13 @@
 // nm_spec_tu.cu -- compiled once per shape class:  nvcc -DNM_SPEC_HEADER='"specs/<name>.h"' ...
 // Instantiates the fused kernels for the generated spec and registers their launchers.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include NM_SPEC_HEADER   // defines struct NM_SPEC_NAME (the "Shape") and the NM_TUNE_* knobs: before the kernel headers
 #include "nm_kernels.cuh"
 #include "nm_tc_kernels.cuh"
 #include "nm_registry.h"
-
-#include NM_SPEC_HEADER   // defines struct NM_SPEC_NAME (the "Shape")
 
 namespace {
 
@@ -94,7 +94,22 @@ template <class Sp> struct TcFwd<Sp, true> {
   static cudaError_t setup(int* occ) {
     cudaError_t e = cudaFuncSetAttribute(nm_tc_fwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcKCfg<Sp>::FWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, nm_tc_fwd_kernel<Sp>, 128, TcKCfg<Sp>::FWD_SMEM_BYTES);
+    if (e == cudaSuccess) {
+      // the occupancy query is conservative for kernels that allocate tensor memory (it answered 1 where two
+      // CTAs fit): recompute from shared memory and registers, then cap by the 512 TMEM columns
+      cudaFuncAttributes fa{};
+      e = cudaFuncGetAttributes(&fa, nm_tc_fwd_kernel<Sp>);
+      if (e == cudaSuccess) {
+        const int by_smem = int((227 * 1024) / (TcKCfg<Sp>::FWD_SMEM_BYTES + 1024));
+        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
+        const int by_regs = regs_per_cta > 0 ? 65536 / regs_per_cta : 1;
+        int manual = by_smem < by_regs ? by_smem : by_regs;
+        if (getenv("NM_DEBUG")) fprintf(stderr, "[nm] tc fwd occupancy: api %d, smem %d, regs %d (numRegs %d)\n", *occ, by_smem, by_regs, fa.numRegs);
+        if (manual > *occ) *occ = manual;
+      }
+    }
     if (*occ > TcKCfg<Sp>::MAX_CTAS) *occ = TcKCfg<Sp>::MAX_CTAS;
+    if (*occ < 1) *occ = 1;
     return e;
   }
   static void launch(const NmPlan& p, const FwdArgs& a, const float* params, float* wprep, int grid, cudaStream_t st) {
@@ -102,6 +117,26 @@ template <class Sp> struct TcFwd<Sp, true> {
     nm_tc_fwd_kernel<Sp><<<grid, 128, TcKCfg<Sp>::FWD_SMEM_BYTES, st>>>(p, a);
   }
 };
+
+template <class Sp, bool ON> struct TcBwd {
+  static constexpr size_t W_BYTES = 0;
+  static cudaError_t setup() { return cudaSuccess; }
+  static void launch(const NmPlan&, const BwdArgs&, const float*, float*, int, cudaStream_t) {}
+};
+template <class Sp> struct TcBwd<Sp, true> {
+  static constexpr size_t W_BYTES = TcBKCfg<Sp>::W_BYTES;
+  static cudaError_t setup() {
+    return cudaFuncSetAttribute(nm_tc_bwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcBKCfg<Sp>::SMEM_BYTES);
+  }
+  static void launch(const NmPlan& p, const BwdArgs& a, const float* params, float* wprep, int grid, cudaStream_t st) {
+    nm_tc_prep_bwd_kernel<Sp><<<16, 256, 0, st>>>(p, params, wprep);
+    nm_tc_bwd_kernel<Sp><<<grid, TcBKCfg<Sp>::THREADS, TcBKCfg<Sp>::SMEM_BYTES, st>>>(p, a);
+  }
+};
+template <class Sp, bool EL> struct TcBwdEligible { static constexpr bool value = false; };
+template <class Sp> struct TcBwdEligible<Sp, true> { static constexpr bool value = TcBKCfg<Sp>::ELIGIBLE; };
+// the tensor-core adjoint needs the stage checkpoints written by the forward kernel; without them the FFMA adjoint runs
+constexpr bool kTcBwd = kTcFwd && TcBwdEligible<NM_SPEC_NAME, kTcFwd>::value;
 
 struct DeviceInfo { int sms = 0; int occ_fwd = 0; int occ_bwd = 0; bool ready = false; };
 DeviceInfo g_dev[64];
@@ -118,6 +153,7 @@ int device_info(DeviceInfo** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::BWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fwd, nm_fwd_kernel<SF>, SF::THREADS, KCF::FWD_SMEM_BYTES);
     if (kTcFwd && e == cudaSuccess) e = TcFwd<NM_SPEC_NAME, kTcFwd>::setup(&d.occ_fwd);
+    if (kTcBwd && e == cudaSuccess) e = TcBwd<NM_SPEC_NAME, kTcBwd>::setup();
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_bwd, nm_bwd_kernel<S>, S::THREADS, KC::BWD_SMEM_BYTES);
     if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
     if (d.occ_fwd < 1 || d.occ_bwd < 1) { nm_set_error("kernel does not fit on an SM (occupancy 0)"); return NM_ERR_CUDA; }
@@ -129,7 +165,8 @@ int device_info(DeviceInfo** out) {
 
 constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 constexpr size_t kWprepFfma = size_t(KC::W_FLOATS_ALL > 0 ? KC::W_FLOATS_ALL : 4) * 4;
-constexpr size_t kWprepBytes = align256(kTcFwd && TK::FWD_W_BYTES > kWprepFfma ? TK::FWD_W_BYTES : kWprepFfma);
+constexpr size_t kWprepTc = TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES > (kTcFwd ? TK::FWD_W_BYTES : 0) ? TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES : (kTcFwd ? TK::FWD_W_BYTES : 0);
+constexpr size_t kWprepBytes = align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
 constexpr int kFwdTile = kTcFwd ? 128 : SF::TILE;
 
 int check_plan(const NmPlan* p) {
@@ -203,7 +240,9 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   float* wprep = reinterpret_cast<float*>(ws);
   c->grad_partials = reinterpret_cast<float*>(ws + kWprepBytes);
   c->grid = grid;
-  launch_prep(p, c->params, wprep, c->stream);
+  const bool tc_bwd = kTcBwd && c->checkpoints != nullptr;
+  if (tc_bwd) { grid = d->sms; if (grid > int((c->B + 127) / 128)) grid = int((c->B + 127) / 128); if (grid < 1) grid = 1; c->grid = grid; }
+  else launch_prep(p, c->params, wprep, c->stream);
   BwdArgs a{};
   a.params = c->params; a.wprep = wprep;
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
@@ -211,8 +250,9 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   a.grad_scalars = c->grad_scalars; a.gx_ext = c->gx_ext; a.gu_ext = c->gu_ext; a.gy_ext = c->gy_ext;
   a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y; a.fused_terms = c->fused_terms;
   a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;
-  a.B = c->B; a.b_total = c->b_total; a.num_tiles = tiles;
-  nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
+  a.B = c->B; a.b_total = c->b_total; a.num_tiles = tc_bwd ? int((c->B + 127) / 128) : tiles;
+  if (tc_bwd) TcBwd<NM_SPEC_NAME, kTcBwd>::launch(*p, a, c->params, wprep, grid, c->stream);
+  else nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
   return NM_OK;

@@ -50,6 +50,24 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// compile-time accumulate flag (no setp in the issue loop)
+template <bool ACC>
+__device__ __forceinline__ void mma_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
+}
+// descriptor of the same tile family `byte_off` bytes further (the start-address field holds address >> 4)
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + uint64_t(byte_off >> 4); }
+__device__ __forceinline__ void st_shared(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
+// one lane of a converged warp (the tensor-core instructions live on the uniform datapath: issuing them from
+// `if (tid == k)` makes the compiler wrap each one in a per-thread vote loop -- measured 94 instead of 46 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -140,6 +158,7 @@ __device__ __forceinline__ float tf32_hi(float v) {
 
 constexpr int pow2_ceil(int v) { int p = 32; while (p < v) p *= 2; return p; }
 constexpr int chunk_of(int w) { return w % 32 == 0 ? 32 : (w % 16 == 0 ? 16 : 8); }
+constexpr int chunk16_of(int w) { return w % 16 == 0 ? 16 : 8; }     // adjoint kernel: smaller register footprint
 
 // ------------------------------------------------------------------------------------------------
 // Static layout of one MLP on the tensor-core path
@@ -223,6 +242,139 @@ __device__ void prep_tc_fwd(const float* __restrict__ params, float* __restrict_
       if (n < Nl) v = k < Kl ? W[n * Kl + k] : ((k == Kl && C::BIAS) ? b[n] : 0.f);
       const float h = tf32_hi(v);
       hi[idx] = h; lo[idx] = v - h;
+    }
+  });
+}
+
+}  // namespace tc
+}  // namespace nm
+
+// ================================================================================================
+// adjoint kernel support
+namespace nm {
+namespace tc {
+
+// K-major SWIZZLE_128B descriptor (tiles [feature row][128 trajectories], 128-byte rows, 4 blocks of 32 trajectories)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t(1) << 16;                                   // leading byte offset: unused for swizzled K-major
+  d |= uint64_t(1024 >> 4) << 32;                           // stride between 8-row groups
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;                                   // SWIZZLE_128B
+  return d;
+}
+// byte offset of element (row f, trajectory m) in such a tile with R rows
+__host__ __device__ constexpr uint32_t sw128_off(int f, int m, int R) {
+  return uint32_t((m >> 5) * (R * 128) + f * 128 + ((((m & 31) >> 2) ^ (f & 7)) << 4) + (m & 3) * 4);
+}
+
+template <int ACT> constexpr bool act_is_mask() { return ACT == NM_ACT_RELU || ACT == NM_ACT_LEAKY || ACT == NM_ACT_IDENTITY; }
+// activation and derivative from the pre-activation
+template <int ACT>
+__device__ __forceinline__ void act_ad(float z, float prm, float& a, float& d) {
+  if constexpr (act_needs_dbuf<ACT>()) act_pair_z<ACT>(z, prm, a, d);
+  else { a = act_fwd<ACT>(z, prm); d = act_deriv_a<ACT>(a, prm); }
+}
+
+template <class M>
+struct TcBwdCfg {
+  using C = TcCfg<M>;
+  static constexpr int NL = C::NL;
+  static constexpr int NI = 2 * (NL - 2);                                  // streamed weight images per MLP evaluation
+  // data-gradient GEMM of tensor-core layer l:  dA[m][k] = sum_n dZ[m][n] W[n][k]
+  static constexpr int dnp(int l) { return round_up(C::K(l), 16); }        // MMA N (rows of the transposed image)
+  static constexpr int dkp(int l) { return round_up(C::N(l), 8); }         // contraction extent
+  static constexpr int dimg_floats(int l) { return dnp(l) * dkp(l); }
+  static constexpr int slot_floats() {
+    int m = 256;
+    for (int l = 1; l <= NL - 2; ++l) m = cmax(m, cmax(2 * C::img_floats(l), 2 * dimg_floats(l)));
+    return round_up(m, 256);
+  }
+  // image i of the per-evaluation sequence: forward layers 1..NL-2, then data-gradient layers NL-2..1
+  static constexpr int img_layer(int i) { return i < NL - 2 ? i + 1 : (NL - 2) - (i - (NL - 2)); }
+  static constexpr bool img_is_fwd(int i) { return i < NL - 2; }
+  static constexpr int img_pair_floats(int i) { return img_is_fwd(i) ? 2 * C::img_floats(img_layer(i)) : 2 * dimg_floats(img_layer(i)); }
+  // prepared global block: [first rows | last rows | last bias] (same offsets as the forward block) then the images
+  static constexpr int SMALL = round_up(C::lastb_off() + round_up(C::N(NL - 1), 4), 32);
+  static constexpr int gimg_off(int i) { int o = SMALL; for (int j = 0; j < i; ++j) o += img_pair_floats(j); return o; }
+  static constexpr int BWD_W = gimg_off(NI);
+  // tensor-memory columns
+  static constexpr int opw() { int m = C::kp_max(); for (int l = 1; l <= NL - 2; ++l) m = cmax(m, dkp(l)); return m; }
+  static constexpr int accw() { int m = cmax(C::np_max(), C::kp_max()); for (int l = 1; l <= NL - 2; ++l) m = cmax(m, dnp(l)); return m; }
+  static constexpr int OPH = 0, OPL = opw(), ACC = 2 * opw();
+  static constexpr int wgc(int l) { return round_up(C::kaug(l), 16); }     // weight-gradient accumulator of layer l: lanes n, columns k (+ bias)
+  static constexpr int wg_off(int l) { int o = ACC + accw(); for (int i = 0; i < l; ++i) o += wgc(i); return o; }
+  static constexpr bool MASK = act_is_mask<M::ACT>();
+  // derivative stash for hidden layers 1 .. NL-2 (the last hidden layer's derivative is used on the spot)
+  static constexpr int der_w(int j) { return C::kp(j); }                   // j = index of the activation a_j (operand width: whole chunks)
+  static constexpr int der_off(int j) { int o = wg_off(NL); for (int i = 1; i < j; ++i) o += der_w(i); return o; }
+  static constexpr int COLS_USED = MASK ? wg_off(NL) : der_off(NL - 1);
+  static constexpr int COLS = pow2_ceil(COLS_USED);
+  // shared memory (bytes): DT | DTL | AT[0..NL-1] | ring (2 slots) | small | barriers
+  static constexpr int max_hidden() { return C::max_hidden(); }
+  static constexpr int RD = round_up(max_hidden(), 8);
+  static constexpr int ra(int l) { return round_up(C::kaug(l), 8); }
+  static constexpr int DT_OFF = 0, DTL_OFF = RD * 512;
+  static constexpr int at_off(int l) { int o = DTL_OFF + 8 * 512; for (int i = 0; i < l; ++i) o += ra(i) * 512; return o; }
+  static constexpr int RING_OFF = at_off(NL);
+  static constexpr int SMALL_OFF = RING_OFF + 2 * slot_floats() * 4;
+  static constexpr int BAR_OFF = SMALL_OFF + SMALL * 4;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512;
+  static constexpr bool FITS = SMEM_BYTES + 1024 <= 227 * 1024 && COLS_USED <= 512 && C::N(NL - 1) <= 8 && max_hidden() <= 128;
+};
+
+// weight preparation for the adjoint kernel
+template <class M>
+__device__ void prep_tc_bwd(const float* __restrict__ params, float* __restrict__ dst, int gtid, int gthreads) {
+  using C = TcCfg<M>;
+  using B = TcBwdCfg<M>;
+  auto p_off = [](int l) { int o = 0; for (int i = 0; i < l; ++i) o += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0); return o; };
+  {
+    const float* W = params + p_off(0);
+    const float* b = W + C::N(0) * C::K(0);
+    for (int idx = gtid; idx < C::N(0) * C::R0; idx += gthreads) {
+      const int n = idx / C::R0, c = idx % C::R0;
+      dst[C::first_off() + idx] = c < C::K(0) ? W[n * C::K(0) + c] : (c == C::K(0) && C::BIAS ? b[n] : 0.f);
+    }
+  }
+  {
+    constexpr int l = C::NL - 1;
+    const float* W = params + p_off(l);
+    const float* b = W + C::N(l) * C::K(l);
+    for (int idx = gtid; idx < C::N(l) * C::RL; idx += gthreads) {
+      const int n = idx / C::RL, c = idx % C::RL;
+      dst[C::last_off() + idx] = c < C::K(l) ? W[n * C::K(l) + c] : 0.f;
+    }
+    for (int idx = gtid; idx < round_up(C::N(l), 4); idx += gthreads) dst[C::lastb_off() + idx] = (idx < C::N(l) && C::BIAS) ? b[idx] : 0.f;
+  }
+  static_for<0, B::NI>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    constexpr int l = B::img_layer(i);
+    constexpr int Kl = C::K(l), Nl = C::N(l);
+    const float* W = params + p_off(l);
+    const float* b = W + Nl * Kl;
+    float* hi = dst + B::gimg_off(i);
+    if constexpr (B::img_is_fwd(i)) {
+      constexpr int KP = C::kp(l), NP = C::np(l);
+      float* lo = hi + C::img_floats(l);
+      for (int idx = gtid; idx < NP * KP; idx += gthreads) {
+        const int kc = idx / (NP * 4), n = (idx / 4) % NP, k = kc * 4 + (idx & 3);
+        float v = 0.f;
+        if (n < Nl) v = k < Kl ? W[n * Kl + k] : ((k == Kl && C::BIAS) ? b[n] : 0.f);
+        const float h = tf32_hi(v);
+        hi[idx] = h; lo[idx] = v - h;
+      }
+    } else {
+      // transposed image: rows k (MMA N), contraction n:  T[n/4][k][n%4] = W[n][k]
+      constexpr int NPd = B::dnp(l), KPd = B::dkp(l);
+      float* lo = hi + B::dimg_floats(l);
+      for (int idx = gtid; idx < NPd * KPd; idx += gthreads) {
+        const int nc = idx / (NPd * 4), k = (idx / 4) % NPd, n = nc * 4 + (idx & 3);
+        const float v = (k < Kl && n < Nl) ? W[n * Kl + k] : 0.f;
+        const float h = tf32_hi(v);
+        hi[idx] = h; lo[idx] = v - h;
+      }
     }
   });
 }

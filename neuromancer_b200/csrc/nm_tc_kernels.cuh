@@ -84,21 +84,26 @@ __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint
     tc::wait_st();
     tc::fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {                                       // warp 0, converged: one elected lane issues
       tc::fence_after();
-      const uint32_t wh = smem_u32(W + C::img_off(l)), wl = wh + C::img_floats(l) * 4;
       constexpr uint32_t idesc = tc::idesc_tf32(128, NP);
       constexpr uint32_t LBO = NP * 16, SBO = 128, KSTEP = 2 * NP * 16;
-      // the two small products first: the accumulator truncates on every accumulate (see nm_tc.cuh)
-#pragma unroll
-      for (int ks = 0; ks < KP / 8; ++ks) {
-        tc::mma_ts(tmem + C::ACC, tmem + C::OPL + ks * 8, tc::smem_desc(wh + ks * KSTEP, LBO, SBO), idesc, ks > 0);
-        tc::mma_ts(tmem + C::ACC, tmem + C::OPH + ks * 8, tc::smem_desc(wl + ks * KSTEP, LBO, SBO), idesc, 1);
+      const uint64_t wh = tc::smem_desc(smem_u32(W + C::img_off(l)), LBO, SBO);
+      const uint64_t wl = tc::desc_add(wh, C::img_floats(l) * 4);
+      if (tc::elect_one()) {
+        // the two small products first: the accumulator truncates on every accumulate (see nm_tc.cuh)
+        static_for<0, KP / 8>([&](auto kc) {
+          constexpr int ks = decltype(kc)::value;
+          tc::mma_ts_c<(ks > 0)>(tmem + C::ACC, tmem + C::OPL + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+          tc::mma_ts_c<true>(tmem + C::ACC, tmem + C::OPH + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+        });
+        static_for<0, KP / 8>([&](auto kc) {
+          constexpr int ks = decltype(kc)::value;
+          tc::mma_ts_c<true>(tmem + C::ACC, tmem + C::OPH + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+        });
+        tc::commit(mma_bar);
       }
-#pragma unroll
-      for (int ks = 0; ks < KP / 8; ++ks)
-        tc::mma_ts(tmem + C::ACC, tmem + C::OPH + ks * 8, tc::smem_desc(wh + ks * KSTEP, LBO, SBO), idesc, 1);
-      tc::commit(mma_bar);
+      __syncwarp();
     }
     mbar_wait(mma_bar, phase);
     phase ^= 1;
@@ -274,4 +279,601 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
   if (warp == 0) tc::tmem_dealloc<C::FWD_COLS>(tmem);
 }
 
+
+
+// ================================================================================================
+// adjoint (BPTT) kernel, tensor-core variant
+//
+// 128 owner threads (thread m = trajectory m of the tile = TMEM lane m) + one control warp whose lane 0 streams
+// the weight images of the hidden layers through a two-slot shared-memory ring (bulk TMA from the L2-resident
+// prepared block) and issues every MMA.  Per integrator stage, in reverse stage order:
+//   recompute     layer 0 on CUDA cores, hidden layers on the tensor cores (A = activations in TMEM, 3-product
+//                 split); every layer's input is also written TRANSPOSED (tf32-rounded) into a swizzled shared
+//                 memory tile  AT_l[feature][trajectory]  for the weight-gradient GEMM
+//   backward      output layer on CUDA cores; data gradients of the hidden layers on the tensor cores
+//                 (A = dZ in TMEM, B = transposed weight image); weight gradients
+//                 dW_l[n][k] = sum_m dZ_{l+1}[m][n] a_l[m][k]  as M=128 (n) x N=k MMAs contracting over the 128
+//                 trajectories, single-pass TF32 on round-to-nearest operands (gradient tolerance 1e-4; measured
+//                 error <= 2e-5 at B = 127 and falling with B), bias gradient through a constant-one row of AT_l
+//   accumulation  the TMEM accumulator truncates, so weight-gradient accumulators only run for FLUSH steps and are
+//                 then added (fp32, round-to-nearest) to this CTA's private gradient block in L2
+#ifdef NM_TUNE_TCPROF
+#define TCP_DECL(n) long long n = 0
+#define TCP_T0() const long long tcp_t0 = clock64()
+#define TCP_ADD(n) n += clock64() - tcp_t0
+#else
+#define TCP_DECL(n)
+#define TCP_T0()
+#define TCP_ADD(n)
+#endif
+template <class S>
+struct TcBKCfg {
+  using M = typename S::RhsM;
+  using C = tc::TcCfg<M>;
+  using B = tc::TcBwdCfg<M>;
+  static constexpr bool ELIGIBLE = TcKCfg<S>::ELIGIBLE && B::FITS;
+  static constexpr int THREADS = 160, FLUSH = 8;
+  static constexpr size_t SMEM_BYTES = size_t(B::SMEM_BYTES) + 1024;      // + alignment slack
+  static constexpr size_t W_BYTES = size_t(B::BWD_W) * 4;
+};
+
+template <class S>
+__global__ void nm_tc_prep_bwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, float* __restrict__ wprep) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  tc::prep_tc_bwd<typename S::RhsM>(params + plan.rhs_mlp.param_offset, wprep, gtid, gthreads);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class S>
+__global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
+  using M = typename S::RhsM;
+  using C = tc::TcCfg<M>;
+  using B = tc::TcBwdCfg<M>;
+  using BK = TcBKCfg<S>;
+  constexpr int NX = S::NX, NU = S::NU, NUA = NU > 0 ? NU : 1, K0 = C::K(0), N0 = C::N(0), NL = C::NL;
+  constexpr int TILE = 128, NS = Tableau<S::INTEG>::NS, NI = B::NI, FLUSH = BK::FLUSH;
+  constexpr int NLAST = C::N(NL - 1);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the swizzled tiles need a 1024-byte aligned base; the dynamic window starts right after the driver's 1 KB
+  // (checked, not re-aligned: pointer arithmetic on an integer would turn every access into a generic one)
+  uint8_t* sm = smem_raw;
+  if ((smem_u32(sm) & 1023u) != 0u) __trap();
+  const float* Wsm = reinterpret_cast<const float*>(sm + B::SMALL_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + B::BAR_OFF);
+  // bars: 0 small-weights TMA, 1 ops_full (128 arrivals), 2 mma done, 3 wgrad done, 4/5 ring slot full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* coef = reinterpret_cast<float*>(bars + 10);                       // [NM_MAX_TERMS]
+  VarTable& vt = *reinterpret_cast<VarTable*>(bars + 20);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const NmPlan& p = plan;
+  const int T = p.nsteps;
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  const bool pre = !fused && args.G_x != nullptr;
+  const int g_row = (T + 1) * NX + T * NU;
+  int tb_mask = 0;
+  for (int k = 0; k < p.n_terms; ++k) {
+    const NmTerm& tm = p.terms[k];
+    const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
+    const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (live[i] && at[i]->var >= 0 && at[i]->var <= NM_VAR_Y && atom_is_tbcast(*at[i], tm)) tb_mask |= 1 << at[i]->var;
+  }
+  if (tid < NM_MAX_TERMS) coef[tid] = tid < p.n_terms ? term_coef(p, tid, args.grad_scalars, args.b_total) : 0.f;
+  float* gblock = args.grad_partials + size_t(blockIdx.x) * size_t(p.n_params > 0 ? p.n_params : 1);
+  for (int i = tid; i < p.n_params; i += BK::THREADS) gblock[i] = 0.f;
+  float* grhs = gblock + p.rhs_mlp.param_offset;
+  if (tid == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = 0;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 128); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  // constant rows of the transposed tiles: zero everything, then the constant-one (bias) row of every AT_l
+  for (int i = tid; i < B::RING_OFF / 4; i += BK::THREADS) reinterpret_cast<float*>(sm)[i] = 0.f;
+  __syncthreads();
+  if (C::BIAS && tid < 128) {
+    static_for<0, NL>([&](auto lc) {
+      constexpr int l = decltype(lc)::value;
+      *reinterpret_cast<float*>(sm + B::at_off(l) + tc::sw128_off(C::K(l), tid, B::ra(l))) = 1.f;
+    });
+  }
+  if (warp == 0) tc::tmem_alloc<B::COLS>(tmem_slot);
+  tc::fence_before();
+  tc::fence_async_smem();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], uint32_t(B::SMALL * 4));
+    tma_bulk_g2s(sm + B::SMALL_OFF, args.wprep, uint32_t(B::SMALL * 4), &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+
+  // number of MLP evaluations this CTA runs (both roles count the same way)
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) ++my_tiles;
+
+  if (warp == 4) {
+    // =============================================================== control thread: TMA producer + MMA issuer
+    {
+      const uint32_t sbase = smem_u32(sm);
+      const uint64_t d_sw0 = tc::smem_desc_sw128(sbase);
+      const long long total_imgs = (long long)my_tiles * T * NS * NI;
+      long long img_issued = 0;
+      uint32_t ph_ops = 0, ph_slot[2] = {0, 0};
+      TCP_DECL(c_wait_ops); TCP_DECL(c_wait_slot); TCP_DECL(c_issue); TCP_DECL(c_total);
+#ifdef NM_TUNE_TCPROF
+      const long long c_begin = clock64();
+#endif
+      auto issue_img = [&](int i) {                     // image i of the per-evaluation sequence -> ring slot i % 2
+        static_for<0, NI>([&](auto ic) {
+          constexpr int I = decltype(ic)::value;
+          if (i == I) {
+            constexpr uint32_t bytes = uint32_t(B::img_pair_floats(I)) * 4;
+            if (tc::elect_one()) {
+              mbar_expect_tx(&bars[4 + (I & 1)], bytes);
+              tma_bulk_g2s(sm + B::RING_OFF + (I & 1) * B::slot_floats() * 4, args.wprep + B::gimg_off(I), bytes, &bars[4 + (I & 1)]);
+            }
+            __syncwarp();
+          }
+        });
+        ++img_issued;
+      };
+      if (total_imgs > 0) issue_img(0);
+      int step_cnt = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int t = T - 1; t >= 0; --t) {
+          bool fresh = (step_cnt % FLUSH) == 0;         // accumulators were flushed before this step
+          ++step_cnt;
+          for (int st = NS - 1; st >= 0; --st) {
+            // one wgrad GEMM: D'[n][k] (+)= sum_m DT[n][m] AT_l[k][m]
+            auto wgrad = [&](auto lc, auto dtoff_c, auto dtrows_c) {
+              constexpr int l = decltype(lc)::value;
+              constexpr uint32_t dt_off = decltype(dtoff_c)::value, dt_rows = decltype(dtrows_c)::value;
+              constexpr uint32_t idesc = tc::idesc_tf32(128, B::wgc(l));
+              const uint64_t da = tc::desc_add(d_sw0, dt_off), db = tc::desc_add(d_sw0, B::at_off(l));
+              if (tc::elect_one()) {
+                tc::mma_ss(tmem + B::wg_off(l), da, db, idesc, fresh ? 0u : 1u);
+                static_for<1, 16>([&](auto sc) {
+                  constexpr uint32_t s = decltype(sc)::value;
+                  tc::mma_ss(tmem + B::wg_off(l), tc::desc_add(da, (s >> 2) * (dt_rows * 128) + (s & 3) * 32),
+                             tc::desc_add(db, (s >> 2) * (B::ra(l) * 128) + (s & 3) * 32), idesc, 1u);
+                });
+              }
+              __syncwarp();
+            };
+            // ---- forward hidden layers
+            static_for<1, NL - 1>([&](auto lc) {
+              constexpr int l = decltype(lc)::value;
+              constexpr int I = l - 1;
+              { TCP_T0(); mbar_wait(&bars[1], ph_ops); ph_ops ^= 1; TCP_ADD(c_wait_ops); }
+              tc::fence_after();
+              if (img_issued < total_imgs) issue_img((I + 1) % NI);
+              { TCP_T0(); mbar_wait(&bars[4 + (I & 1)], ph_slot[I & 1]); ph_slot[I & 1] ^= 1; TCP_ADD(c_wait_slot); }
+              TCP_T0();
+              constexpr int KP = C::kp(l), NP = C::np(l);
+              constexpr uint32_t idesc = tc::idesc_tf32(128, NP);
+              constexpr uint32_t LBO = NP * 16, SBO = 128, KSTEP = 2 * NP * 16;
+              const uint64_t wh = tc::smem_desc(sbase + B::RING_OFF + (I & 1) * B::slot_floats() * 4, LBO, SBO);
+              const uint64_t wl = tc::desc_add(wh, C::img_floats(l) * 4);
+              if (tc::elect_one()) {
+                static_for<0, KP / 8>([&](auto kc) {
+                  constexpr int ks = decltype(kc)::value;
+                  tc::mma_ts_c<(ks > 0)>(tmem + B::ACC, tmem + B::OPL + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+                  tc::mma_ts_c<true>(tmem + B::ACC, tmem + B::OPH + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+                });
+                static_for<0, KP / 8>([&](auto kc) {
+                  constexpr int ks = decltype(kc)::value;
+                  tc::mma_ts_c<true>(tmem + B::ACC, tmem + B::OPH + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+                });
+                tc::commit(&bars[2]);
+              }
+              __syncwarp();
+              TCP_ADD(c_issue);
+            });
+            // ---- backward hidden layers
+            static_for_rev<1, NL - 1>([&](auto lc) {
+              constexpr int l = decltype(lc)::value;
+              constexpr int I = (NL - 2) + (NL - 2 - l);
+              { TCP_T0(); mbar_wait(&bars[1], ph_ops); ph_ops ^= 1; TCP_ADD(c_wait_ops); }
+              tc::fence_after();
+              if (img_issued < total_imgs) issue_img((I + 1) % NI);
+              { TCP_T0(); mbar_wait(&bars[4 + (I & 1)], ph_slot[I & 1]); ph_slot[I & 1] ^= 1; TCP_ADD(c_wait_slot); }
+              TCP_T0();
+              constexpr int KPd = B::dkp(l), NPd = B::dnp(l);
+              constexpr uint32_t idesc = tc::idesc_tf32(128, NPd);
+              constexpr uint32_t LBO = NPd * 16, SBO = 128, KSTEP = 2 * NPd * 16;
+              const uint64_t wh = tc::smem_desc(sbase + B::RING_OFF + (I & 1) * B::slot_floats() * 4, LBO, SBO);
+              const uint64_t wl = tc::desc_add(wh, B::dimg_floats(l) * 4);
+              if (tc::elect_one()) {
+                static_for<0, KPd / 8>([&](auto kc) {
+                  constexpr int ks = decltype(kc)::value;
+                  tc::mma_ts_c<(ks > 0)>(tmem + B::ACC, tmem + B::OPL + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+                  tc::mma_ts_c<true>(tmem + B::ACC, tmem + B::OPH + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+                });
+                static_for<0, KPd / 8>([&](auto kc) {
+                  constexpr int ks = decltype(kc)::value;
+                  tc::mma_ts_c<true>(tmem + B::ACC, tmem + B::OPH + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+                });
+                tc::commit(&bars[2]);
+              }
+              __syncwarp();
+              if constexpr (l == NL - 2) wgrad(IC<NL - 1>{}, IC<B::DTL_OFF>{}, IC<8>{});
+              wgrad(IC<l>{}, IC<B::DT_OFF>{}, IC<B::RD>{});
+              if (tc::elect_one()) tc::commit(&bars[3]);
+              __syncwarp();
+              TCP_ADD(c_issue);
+            });
+            // ---- weight gradient of layer 0
+            { TCP_T0(); mbar_wait(&bars[1], ph_ops); ph_ops ^= 1; TCP_ADD(c_wait_ops); }
+            tc::fence_after();
+            { TCP_T0(); wgrad(IC<0>{}, IC<B::DT_OFF>{}, IC<B::RD>{});
+            if (tc::elect_one()) tc::commit(&bars[3]);
+            __syncwarp(); TCP_ADD(c_issue); }
+            fresh = false;
+          }
+        }
+      }
+#ifdef NM_TUNE_TCPROF
+      c_total = clock64() - c_begin;
+      if (blockIdx.x == 0 && tid == 128) printf("[tcprof control] total %lld  wait_ops %lld  wait_slot %lld  issue %lld  (stages %lld)\n", c_total, c_wait_ops, c_wait_slot, c_issue, (long long)my_tiles * T * NS);
+#endif
+    }
+  } else {
+    // =============================================================== owners
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const uint32_t t_oph = tmem + lane_base + B::OPH, t_opl = tmem + lane_base + B::OPL, t_acc = tmem + lane_base + B::ACC;
+    uint32_t ph_mma = 0, ph_wg = 0;
+    bool wg_pending = false;
+    TCP_DECL(o_wait_mma); TCP_DECL(o_wait_wg); TCP_DECL(o_arrive); TCP_DECL(o_flush);
+#ifdef NM_TUNE_TCPROF
+    const long long o_begin = clock64();
+#endif
+    int step_cnt = 0;
+    const float act_prm = p.rhs_mlp.act_param;
+    const float* __restrict__ W0 = Wsm + C::first_off();
+    const float* __restrict__ WL = Wsm + C::last_off();
+    // per-thread pieces of the swizzled transposed-tile address: element (f, tid) sits at
+    //   block(tid) * R*128 + f*128 + ((chunk ^ (f & 7)) << 4) + (tid & 3)*4
+    const uint32_t t_blk = uint32_t(tid >> 5), t_chunk = uint32_t((tid & 31) >> 2), t_in = uint32_t(tid & 3) * 4;
+    const uint32_t sm_u32 = smem_u32(sm);
+    uint32_t t_x[8];                                                       // (chunk ^ r) << 4 for the 8 row residues
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t_x[r] = sm_u32 + ((t_chunk ^ uint32_t(r)) << 4) + t_in;
+    auto tstore = [&](uint32_t tile_off, int R, int f, float v) {
+      tc::st_shared(t_x[f & 7] + tile_off + t_blk * uint32_t(R * 128) + uint32_t(f * 128), v);
+    };
+    auto arrive_ops = [&]() {
+      TCP_T0();
+      tc::wait_st();
+      tc::fence_async_smem();
+      tc::fence_before();
+      mbar_arrive(&bars[1]);
+      TCP_ADD(o_arrive);
+    };
+    // add this CTA's TMEM weight-gradient accumulators to its gradient block (fp32, round to nearest)
+    auto flush = [&]() {
+      static_for<0, NL>([&](auto lc) {
+        constexpr int l = decltype(lc)::value;
+        constexpr int Kl = C::K(l), Nl = C::N(l), KA = C::kaug(l), CH = 8;
+        int off = 0;
+        for (int i = 0; i < l; ++i) off += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0);
+        float* dst = grhs + off;
+        // tcgen05.ld is warp-collective (.sync.aligned): every owner executes it, rows n >= N(l) are dropped
+#pragma unroll 1
+        for (int c0 = 0; c0 < KA; c0 += CH) {
+          float v[CH];
+          tc::tmem_ld<CH>(tmem + lane_base + B::wg_off(l) + c0, v);
+          if (tid < Nl) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const int k = c0 + i;
+              if (k < Kl) atomicAdd(dst + tid * Kl + k, v[i]);              // result unused: RED, no round trip
+              else if (k == Kl && C::BIAS) atomicAdd(dst + Nl * Kl + tid, v[i]);
+            }
+          }
+        }
+      });
+    };
+    uint32_t masks[NL][4];
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) masks[i][j] = 0u;
+
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      const int64_t b_raw = int64_t(tile) * TILE + tid;
+      const bool valid = b_raw < args.B;
+      const int64_t b = valid ? b_raw : args.B - 1;
+      float lam[NX], x_pre[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { lam[i] = 0.f; x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + (T - 1)) * NX + i); }
+      if (valid) {
+        if (pre) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
+          if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+        } else {
+          if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, T, lam); }
+          else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+          if (args.gx_ext != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
+          }
+        }
+      }
+#pragma unroll 1
+      for (int t = T - 1; t >= 0; --t) {
+        // flush point (mirrored by the control thread's `fresh`)
+        if (step_cnt > 0 && (step_cnt % FLUSH) == 0) {
+          if (wg_pending) { mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; wg_pending = false; tc::fence_after(); }
+          { TCP_T0(); flush(); TCP_ADD(o_flush); }
+        }
+        ++step_cnt;
+        float x[NX], u[NUA], gx[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = x_pre[i];
+        if (t > 0) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
+        }
+#pragma unroll
+        for (int j = 0; j < NUA; ++j) u[j] = 0.f;
+        if constexpr (NU > 0 && S::ACT_EXO >= 0) {
+          const float* src = args.exo[S::ACT_EXO] + (b * p.exo[S::ACT_EXO].steps + t) * NU;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) u[j] = __ldg(src + j);
+        }
+        const float h = p.h;
+        float k[NM_MAX_STAGES][NX], gk[NM_MAX_STAGES][NX];
+        static_for<0, NS>([&](auto sc) {
+          constexpr int St = decltype(sc)::value;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { gk[St][i] = 0.f; k[St][i] = 0.f; }
+          if constexpr (St + 1 < NS) {
+            const float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) k[St][i] = __ldg(cp + i);
+          }
+        });
+#pragma unroll
+        for (int i = 0; i < NX; ++i) gx[i] = lam[i];
+#pragma unroll 1
+        for (int st = NS - 1; st >= 0; --st) {
+          float in[K0], xs[NX], w_cot[NX];
+          static_for<0, NS>([&](auto sc) {                       // only the tableau arithmetic is per-stage code
+            constexpr int St = decltype(sc)::value;
+            if (st == St) {
+              stage_input<S::INTEG, St, NX>(h, x, k, xs);
+              stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w_cot);
+            }
+          });
+#pragma unroll
+          for (int i = 0; i < NX; ++i) in[i] = xs[i];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) in[NX + j] = u[j];
+          // the previous evaluation's last weight-gradient GEMM still reads AT_0 / DT
+          if (wg_pending) { TCP_T0(); mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; wg_pending = false; TCP_ADD(o_wait_wg); }
+          // ---- layer 0 (CUDA cores): a_1, its derivative, operand of layer 1, transposed tiles AT_0 / AT_1
+#pragma unroll
+          for (int i = 0; i < K0; ++i) tstore(B::at_off(0), B::ra(0), i, tc::tf32_hi(in[i]));
+          {
+            constexpr int KP1 = C::kp(1), CH = tc::chunk16_of(KP1);
+#pragma unroll
+            for (int c0 = 0; c0 < KP1; c0 += CH) {
+              float hi[CH], lo[CH], dv[CH];
+#pragma unroll
+              for (int i = 0; i < CH; ++i) {
+                const int n = c0 + i;
+                float a = 0.f, d = 0.f;
+                if (n < N0) {
+                  float w[C::R0];
+                  ld_vec<C::R0>(w, W0 + n * C::R0);
+                  float z = C::BIAS ? w[K0] : 0.f;
+#pragma unroll
+                  for (int q = 0; q < K0; ++q) z = fmaf(w[q], in[q], z);
+                  tc::act_ad<M::ACT>(z, act_prm, a, d);
+                } else if (n == N0 && C::BIAS) a = 1.f;
+                hi[i] = tc::tf32_hi(a);
+                lo[i] = a - hi[i];
+                dv[i] = d;
+                if (n < N0) {
+                  tstore(B::at_off(1), B::ra(1), n, hi[i]);
+                  if constexpr (B::MASK) masks[1][n >> 5] = (masks[1][n >> 5] & ~(1u << (n & 31))) | (a > 0.f ? (1u << (n & 31)) : 0u);
+                }
+              }
+              tc::tmem_st<CH>(t_oph + c0, hi);
+              tc::tmem_st<CH>(t_opl + c0, lo);
+              if constexpr (!B::MASK) {
+                if (c0 < B::der_w(1)) tc::tmem_st<CH>(tmem + lane_base + B::der_off(1) + c0, dv);
+              }
+              (void)dv;
+            }
+          }
+          arrive_ops();
+          // ---- hidden layers forward (tensor cores) and, after the last one, the output layer backward
+#pragma unroll
+          for (int i = 0; i < NX; ++i) w_cot[i] = valid ? w_cot[i] : 0.f;
+          static_for<1, NL - 1>([&](auto lc) {
+            constexpr int l = decltype(lc)::value;
+            constexpr int Nl = C::N(l);
+            { TCP_T0(); mbar_wait(&bars[2], ph_mma); ph_mma ^= 1; TCP_ADD(o_wait_mma); }
+            tc::fence_after();
+            if constexpr (l < NL - 2) {
+              constexpr int KPN = C::kp(l + 1), CH = tc::chunk16_of(KPN);
+#pragma unroll
+              for (int c0 = 0; c0 < KPN; c0 += CH) {
+                float v[CH], hi[CH], lo[CH], dv[CH];
+                tc::tmem_ld<CH>(t_acc + c0, v);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  const int n = c0 + i;
+                  float a = 0.f, d = 0.f;
+                  if (n < Nl) tc::act_ad<M::ACT>(v[i], act_prm, a, d);
+                  else if (n == Nl && C::BIAS) a = 1.f;
+                  hi[i] = tc::tf32_hi(a);
+                  lo[i] = a - hi[i];
+                  dv[i] = d;
+                  if (n < Nl) {
+                    tstore(B::at_off(l + 1), B::ra(l + 1), n, hi[i]);
+                    if constexpr (B::MASK) masks[l + 1][n >> 5] = (masks[l + 1][n >> 5] & ~(1u << (n & 31))) | (a > 0.f ? (1u << (n & 31)) : 0u);
+                  }
+                }
+                tc::tmem_st<CH>(t_oph + c0, hi);
+                tc::tmem_st<CH>(t_opl + c0, lo);
+                if constexpr (!B::MASK) {
+                  if (c0 < B::der_w(l + 1)) tc::tmem_st<CH>(tmem + lane_base + B::der_off(l + 1) + c0, dv);
+                }
+                (void)dv;
+              }
+              arrive_ops();
+            } else {
+              // last hidden layer: a_{NL-1} (transposed tile only), then straight into the backward pass:
+              // output layer on CUDA cores  dA[k] = sum_j w[j] WL[j][k],  dZ = dA * act'
+#pragma unroll
+              for (int j = 0; j < NLAST; ++j) tstore(B::DTL_OFF, 8, j, tc::tf32_hi(w_cot[j]));
+              constexpr int KPD = B::dkp(l), CH = tc::chunk16_of(KPD);      // operand width of the data-gradient GEMM of layer l
+#pragma unroll
+              for (int c0 = 0; c0 < KPD; c0 += CH) {
+                float v[CH], hi[CH], lo[CH];
+                tc::tmem_ld<CH>(t_acc + c0, v);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  const int n = c0 + i;
+                  float dz = 0.f;
+                  if (n < Nl) {
+                    float a, d;
+                    tc::act_ad<M::ACT>(v[i], act_prm, a, d);
+                    tstore(B::at_off(NL - 1), B::ra(NL - 1), n, tc::tf32_hi(a));
+                    float da = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NLAST; ++j) da = fmaf(w_cot[j], WL[j * C::RL + n], da);
+                    dz = da * d;
+                  }
+                  hi[i] = tc::tf32_hi(dz);
+                  lo[i] = dz - hi[i];
+                  if (n < Nl) tstore(B::DT_OFF, B::RD, n, hi[i]);
+                }
+                tc::tmem_st<CH>(t_oph + c0, hi);
+                tc::tmem_st<CH>(t_opl + c0, lo);
+              }
+              arrive_ops();
+            }
+          });
+          // ---- hidden layers backward
+          float d_in[K0];
+#pragma unroll
+          for (int i = 0; i < K0; ++i) d_in[i] = 0.f;
+          static_for_rev<1, NL - 1>([&](auto lc) {
+            constexpr int l = decltype(lc)::value;
+            constexpr int Kl = C::K(l);                                    // width of dA_l = hidden width of a_l
+            { TCP_T0(); mbar_wait(&bars[2], ph_mma); ph_mma ^= 1; TCP_ADD(o_wait_mma); }
+            tc::fence_after();
+            { TCP_T0(); mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; TCP_ADD(o_wait_wg); }  // weight-gradient GEMMs reading DT are done
+            if constexpr (l > 1) {
+              constexpr int KPD = B::dkp(l - 1), CH = tc::chunk16_of(KPD);
+#pragma unroll
+              for (int c0 = 0; c0 < KPD; c0 += CH) {
+                float v[CH], hi[CH], lo[CH], dv[CH];
+                tc::tmem_ld<CH>(t_acc + c0, v);
+                if constexpr (!B::MASK) tc::tmem_ld<CH>(tmem + lane_base + B::der_off(l) + c0, dv);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  const int n = c0 + i;
+                  float dz = 0.f;
+                  if (n < Kl) {
+                    float d;
+                    if constexpr (B::MASK) d = M::ACT == NM_ACT_IDENTITY ? 1.f : (((masks[l][n >> 5] >> (n & 31)) & 1u) ? 1.f : (M::ACT == NM_ACT_LEAKY ? act_prm : 0.f));
+                    else d = dv[i];
+                    dz = v[i] * d;
+                  }
+                  hi[i] = tc::tf32_hi(dz);
+                  lo[i] = dz - hi[i];
+                  if (n < Kl) tstore(B::DT_OFF, B::RD, n, hi[i]);
+                }
+                tc::tmem_st<CH>(t_oph + c0, hi);
+                tc::tmem_st<CH>(t_opl + c0, lo);
+              }
+              arrive_ops();
+            } else {
+              // l == 1: dZ_1, then layer 0 backward on CUDA cores
+              constexpr int CH = tc::chunk16_of(round_up(Kl, 8));
+#pragma unroll
+              for (int c0 = 0; c0 < round_up(Kl, 8); c0 += CH) {
+                float v[CH], dv[CH];
+                tc::tmem_ld<CH>(t_acc + c0, v);
+                if constexpr (!B::MASK) tc::tmem_ld<CH>(tmem + lane_base + B::der_off(1) + c0, dv);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  const int n = c0 + i;
+                  if (n < Kl) {
+                    float d;
+                    if constexpr (B::MASK) d = M::ACT == NM_ACT_IDENTITY ? 1.f : (((masks[1][n >> 5] >> (n & 31)) & 1u) ? 1.f : (M::ACT == NM_ACT_LEAKY ? act_prm : 0.f));
+                    else d = dv[i];
+                    const float dz = v[i] * d;
+                    tstore(B::DT_OFF, B::RD, n, tc::tf32_hi(dz));
+                    float w[C::R0];
+                    ld_vec<C::R0>(w, W0 + n * C::R0);
+#pragma unroll
+                    for (int q = 0; q < K0; ++q) d_in[q] = fmaf(dz, w[q], d_in[q]);
+                  }
+                }
+              }
+              arrive_ops();
+              wg_pending = true;
+            }
+          });
+          float gxs[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) gxs[i] = d_in[i];
+          static_for<0, NS>([&](auto sc) {
+            constexpr int St = decltype(sc)::value;
+            if (st == St) stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
+          });
+        }
+        // ---- loss-term gradient w.r.t. x_t
+        if (valid) {
+          if (pre) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
+            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+          } else {
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, t, gx); }
+            else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+            if (args.gx_ext != nullptr) {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] : 0.f;
+      }
+      if (valid && args.grad_x0 != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) args.grad_x0[b * NX + i] = lam[i];
+      }
+    }
+    if (step_cnt > 0) {
+      if (wg_pending) { mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; wg_pending = false; tc::fence_after(); }
+      flush();
+    }
+#ifdef NM_TUNE_TCPROF
+    if (blockIdx.x == 0 && tid == 0)
+      printf("[tcprof owner0] total %lld  wait_mma %lld  wait_wg %lld  arrive %lld  flush %lld\n", clock64() - o_begin, o_wait_mma, o_wait_wg, o_arrive, o_flush);
+#endif
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<B::COLS>(tmem);
+}
 }  // namespace nm
