@@ -317,9 +317,16 @@ struct TcBwdCfg {
   static constexpr int ra(int l) { return round_up(C::kaug(l), 8); }
   static constexpr int DT_OFF = 0, DTL_OFF = RD * 512;
   static constexpr int at_off(int l) { int o = DTL_OFF + 8 * 512; for (int i = 0; i < l; ++i) o += ra(i) * 512; return o; }
-  static constexpr int RING_OFF = at_off(NL);
+  // weight-gradient GEMMs: 3-product split (needs the remainder tiles: a second copy of the tile region) when it
+  // fits, else single-pass TF32 on round-to-nearest operands (noise ~ 2^-12 / sqrt(#products): large batches only)
+  static constexpr int TILES_BYTES = at_off(NL);
+  static constexpr int TAIL_BYTES = 2 * slot_floats() * 4 + SMALL * 4 + 2 * 128 * 8 * 4 + 512;
+  static constexpr bool WG3 = 2 * TILES_BYTES + TAIL_BYTES + 1024 <= 227 * 1024;
+  static constexpr int LO_OFF = TILES_BYTES;                              // remainder tile = same offset + LO_OFF
+  static constexpr int RING_OFF = (WG3 ? 2 : 1) * TILES_BYTES;
   static constexpr int SMALL_OFF = RING_OFF + 2 * slot_floats() * 4;
-  static constexpr int BAR_OFF = SMALL_OFF + SMALL * 4;
+  static constexpr int XCH_OFF = SMALL_OFF + SMALL * 4;                   // [2][128][8] floats: partial input gradients of a thread pair
+  static constexpr int BAR_OFF = XCH_OFF + 2 * 128 * 8 * 4;
   static constexpr int SMEM_BYTES = BAR_OFF + 512;
   static constexpr bool FITS = SMEM_BYTES + 1024 <= 227 * 1024 && COLS_USED <= 512 && C::N(NL - 1) <= 8 && max_hidden() <= 128;
 };

@@ -306,13 +306,21 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
 #define TCP_T0()
 #define TCP_ADD(n)
 #endif
+// column blocks of 16 alternate between the two threads of a trajectory; position of chunk `ci` (chunk size CH in
+// {8, 16}) among the chunks its thread owns, and how many chunks a thread can own out of NCH
+constexpr int own_idx(int ci, int CH) { return CH == 16 ? ci / 2 : (ci / 4) * 2 + (ci & 1); }
+constexpr int own_cnt(int NCH, int CH) { return CH == 16 ? (NCH + 1) / 2 : ((NCH + 3) / 4) * 2; }
 template <class S>
 struct TcBKCfg {
   using M = typename S::RhsM;
   using C = tc::TcCfg<M>;
   using B = tc::TcBwdCfg<M>;
   static constexpr bool ELIGIBLE = TcKCfg<S>::ELIGIBLE && B::FITS;
-  static constexpr int THREADS = 160, FLUSH = 8;
+  static constexpr int THREADS = 288;                                       // 2 owner warpgroups + the control warp
+  // weight-gradient accumulators live in tensor memory, whose accumulate truncates: bound the chain to ~320 accumulations
+  static constexpr int MMAS_PER_WG = B::WG3 ? 48 : 16;
+  static constexpr int FLUSH = (320 / (Tableau<S::INTEG>::NS * MMAS_PER_WG)) > 1 ? 320 / (Tableau<S::INTEG>::NS * MMAS_PER_WG) : 1;
+  static constexpr bool WG3 = B::WG3;
   static constexpr size_t SMEM_BYTES = size_t(B::SMEM_BYTES) + 1024;      // + alignment slack
   static constexpr size_t W_BYTES = size_t(B::BWD_W) * 4;
 };
@@ -328,7 +336,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <class S>
-__global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
+__global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
   using M = typename S::RhsM;
   using C = tc::TcCfg<M>;
   using B = tc::TcBwdCfg<M>;
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
     for (int e = 0; e < NM_MAX_EXO; ++e) {
       vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
     }
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 128); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 256); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
     mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -402,7 +410,8 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
   int my_tiles = 0;
   for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) ++my_tiles;
 
-  if (warp == 4) {
+  if (warp >= 8) {
+   if (warp == 8) {
     // =============================================================== control thread: TMA producer + MMA issuer
     {
       const uint32_t sbase = smem_u32(sm);
@@ -442,12 +451,27 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
               constexpr uint32_t idesc = tc::idesc_tf32(128, B::wgc(l));
               const uint64_t da = tc::desc_add(d_sw0, dt_off), db = tc::desc_add(d_sw0, B::at_off(l));
               if (tc::elect_one()) {
-                tc::mma_ss(tmem + B::wg_off(l), da, db, idesc, fresh ? 0u : 1u);
-                static_for<1, 16>([&](auto sc) {
-                  constexpr uint32_t s = decltype(sc)::value;
-                  tc::mma_ss(tmem + B::wg_off(l), tc::desc_add(da, (s >> 2) * (dt_rows * 128) + (s & 3) * 32),
-                             tc::desc_add(db, (s >> 2) * (B::ra(l) * 128) + (s & 3) * 32), idesc, 1u);
-                });
+                if constexpr (B::WG3) {
+                  // remainder products first (see nm_tc.cuh: the accumulator truncates)
+                  static_for<0, 16>([&](auto sc) {
+                    constexpr uint32_t s = decltype(sc)::value;
+                    constexpr uint32_t ao = (s >> 2) * (dt_rows * 128) + (s & 3) * 32, bo = (s >> 2) * (B::ra(l) * 128) + (s & 3) * 32;
+                    tc::mma_ss(tmem + B::wg_off(l), tc::desc_add(da, ao + B::LO_OFF), tc::desc_add(db, bo), idesc, (s == 0 && fresh) ? 0u : 1u);
+                    tc::mma_ss(tmem + B::wg_off(l), tc::desc_add(da, ao), tc::desc_add(db, bo + B::LO_OFF), idesc, 1u);
+                  });
+                  static_for<0, 16>([&](auto sc) {
+                    constexpr uint32_t s = decltype(sc)::value;
+                    tc::mma_ss(tmem + B::wg_off(l), tc::desc_add(da, (s >> 2) * (dt_rows * 128) + (s & 3) * 32),
+                               tc::desc_add(db, (s >> 2) * (B::ra(l) * 128) + (s & 3) * 32), idesc, 1u);
+                  });
+                } else {
+                  tc::mma_ss(tmem + B::wg_off(l), da, db, idesc, fresh ? 0u : 1u);
+                  static_for<1, 16>([&](auto sc) {
+                    constexpr uint32_t s = decltype(sc)::value;
+                    tc::mma_ss(tmem + B::wg_off(l), tc::desc_add(da, (s >> 2) * (dt_rows * 128) + (s & 3) * 32),
+                               tc::desc_add(db, (s >> 2) * (B::ra(l) * 128) + (s & 3) * 32), idesc, 1u);
+                  });
+                }
               }
               __syncwarp();
             };
@@ -525,16 +549,22 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
       }
 #ifdef NM_TUNE_TCPROF
       c_total = clock64() - c_begin;
-      if (blockIdx.x == 0 && tid == 128) printf("[tcprof control] total %lld  wait_ops %lld  wait_slot %lld  issue %lld  (stages %lld)\n", c_total, c_wait_ops, c_wait_slot, c_issue, (long long)my_tiles * T * NS);
+      if (blockIdx.x == 0 && tid == 256) printf("[tcprof control] total %lld  wait_ops %lld  wait_slot %lld  issue %lld  (stages %lld)\n", c_total, c_wait_ops, c_wait_slot, c_issue, (long long)my_tiles * T * NS);
 #endif
     }
+   }
   } else {
     // =============================================================== owners
-    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    // two threads per trajectory: thread (m, hf) with m = tid & 127 owns TMEM lane m and the 16-column blocks of
+    // every layer whose index has parity hf (two warps per scheduler instead of one: the epilogues are
+    // latency-bound); per-trajectory scalars (state, stage derivatives, co-state) are kept by both
+    const int m_ = tid & 127, hf = tid >> 7;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t t_oph = tmem + lane_base + B::OPH, t_opl = tmem + lane_base + B::OPL, t_acc = tmem + lane_base + B::ACC;
     uint32_t ph_mma = 0, ph_wg = 0;
     bool wg_pending = false;
     TCP_DECL(o_wait_mma); TCP_DECL(o_wait_wg); TCP_DECL(o_arrive); TCP_DECL(o_flush);
+    TCP_DECL(o_l0); TCP_DECL(o_fwd); TCP_DECL(o_last); TCP_DECL(o_bwd); TCP_DECL(o_l1); TCP_DECL(o_xch);
 #ifdef NM_TUNE_TCPROF
     const long long o_begin = clock64();
 #endif
@@ -542,15 +572,19 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
     const float act_prm = p.rhs_mlp.act_param;
     const float* __restrict__ W0 = Wsm + C::first_off();
     const float* __restrict__ WL = Wsm + C::last_off();
-    // per-thread pieces of the swizzled transposed-tile address: element (f, tid) sits at
-    //   block(tid) * R*128 + f*128 + ((chunk ^ (f & 7)) << 4) + (tid & 3)*4
-    const uint32_t t_blk = uint32_t(tid >> 5), t_chunk = uint32_t((tid & 31) >> 2), t_in = uint32_t(tid & 3) * 4;
+    float* xch = reinterpret_cast<float*>(sm + B::XCH_OFF);                 // [2][128][8] partial input gradients of the pair
+    auto mine = [&](int c0) { return ((c0 >> 4) & 1) == hf; };
+    // per-thread pieces of the swizzled transposed-tile address: element (f, m) sits at
+    //   block(m) * R*128 + f*128 + ((chunk ^ (f & 7)) << 4) + (m & 3)*4
+    const uint32_t t_blk = uint32_t(m_ >> 5), t_chunk = uint32_t((m_ & 31) >> 2), t_in = uint32_t(m_ & 3) * 4;
     const uint32_t sm_u32 = smem_u32(sm);
     uint32_t t_x[8];                                                       // (chunk ^ r) << 4 for the 8 row residues
 #pragma unroll
     for (int r = 0; r < 8; ++r) t_x[r] = sm_u32 + ((t_chunk ^ uint32_t(r)) << 4) + t_in;
-    auto tstore = [&](uint32_t tile_off, int R, int f, float v) {
-      tc::st_shared(t_x[f & 7] + tile_off + t_blk * uint32_t(R * 128) + uint32_t(f * 128), v);
+    auto tstore = [&](uint32_t tile_off, int R, int f, float v_hi, float v_lo) {
+      const uint32_t a = t_x[f & 7] + tile_off + t_blk * uint32_t(R * 128) + uint32_t(f * 128);
+      tc::st_shared(a, v_hi);
+      if constexpr (B::WG3) tc::st_shared(a + uint32_t(B::LO_OFF), v_lo);
     };
     auto arrive_ops = [&]() {
       TCP_T0();
@@ -560,6 +594,7 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
       mbar_arrive(&bars[1]);
       TCP_ADD(o_arrive);
     };
+    auto wait_wg = [&]() { TCP_T0(); mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; TCP_ADD(o_wait_wg); };
     // add this CTA's TMEM weight-gradient accumulators to its gradient block (fp32, round to nearest)
     auto flush = [&]() {
       static_for<0, NL>([&](auto lc) {
@@ -568,30 +603,41 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
         int off = 0;
         for (int i = 0; i < l; ++i) off += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0);
         float* dst = grhs + off;
-        // tcgen05.ld is warp-collective (.sync.aligned): every owner executes it, rows n >= N(l) are dropped
+        // tcgen05.ld is warp-collective (.sync.aligned): every owner of the half executes it, rows n >= N(l) are dropped
 #pragma unroll 1
         for (int c0 = 0; c0 < KA; c0 += CH) {
+          if (!mine(c0)) continue;
           float v[CH];
           tc::tmem_ld<CH>(tmem + lane_base + B::wg_off(l) + c0, v);
-          if (tid < Nl) {
+          if (m_ < Nl) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const int k = c0 + i;
-              if (k < Kl) atomicAdd(dst + tid * Kl + k, v[i]);              // result unused: RED, no round trip
-              else if (k == Kl && C::BIAS) atomicAdd(dst + Nl * Kl + tid, v[i]);
+              if (k < Kl) atomicAdd(dst + m_ * Kl + k, v[i]);              // result unused: RED, no round trip
+              else if (k == Kl && C::BIAS) atomicAdd(dst + Nl * Kl + m_, v[i]);
             }
           }
         }
       });
     };
+    // derivative of hidden activation a_j at column n (this thread's columns only)
     uint32_t masks[NL][4];
 #pragma unroll
     for (int i = 0; i < NL; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) masks[i][j] = 0u;
+    auto mask_set = [&](auto jc, int n, float a) {
+      constexpr int j = decltype(jc)::value;
+      masks[j][n >> 5] = (masks[j][n >> 5] & ~(1u << (n & 31))) | (a > 0.f ? (1u << (n & 31)) : 0u);
+    };
+    auto mask_d = [&](auto jc, int n) -> float {
+      constexpr int j = decltype(jc)::value;
+      if constexpr (M::ACT == NM_ACT_IDENTITY) return 1.f;
+      return ((masks[j][n >> 5] >> (n & 31)) & 1u) ? 1.f : (M::ACT == NM_ACT_LEAKY ? act_prm : 0.f);
+    };
 
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-      const int64_t b_raw = int64_t(tile) * TILE + tid;
+      const int64_t b_raw = int64_t(tile) * TILE + m_;
       const bool valid = b_raw < args.B;
       const int64_t b = valid ? b_raw : args.B - 1;
       float lam[NX], x_pre[NX];
@@ -613,9 +659,9 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
       }
 #pragma unroll 1
       for (int t = T - 1; t >= 0; --t) {
-        // flush point (mirrored by the control thread's `fresh`)
+        // flush point (mirrored by the control warp's `fresh`)
         if (step_cnt > 0 && (step_cnt % FLUSH) == 0) {
-          if (wg_pending) { mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; wg_pending = false; tc::fence_after(); }
+          if (wg_pending) { wait_wg(); wg_pending = false; tc::fence_after(); }
           { TCP_T0(); flush(); TCP_ADD(o_flush); }
         }
         ++step_cnt;
@@ -658,114 +704,135 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
             }
           });
 #pragma unroll
-          for (int i = 0; i < NX; ++i) in[i] = xs[i];
+          for (int i = 0; i < NX; ++i) { in[i] = xs[i]; w_cot[i] = valid ? w_cot[i] : 0.f; }
 #pragma unroll
           for (int j = 0; j < NU; ++j) in[NX + j] = u[j];
           // the previous evaluation's last weight-gradient GEMM still reads AT_0 / DT
-          if (wg_pending) { TCP_T0(); mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; wg_pending = false; TCP_ADD(o_wait_wg); }
+          if (wg_pending) { wait_wg(); wg_pending = false; }
           // ---- layer 0 (CUDA cores): a_1, its derivative, operand of layer 1, transposed tiles AT_0 / AT_1
+          if (hf == 0) {
 #pragma unroll
-          for (int i = 0; i < K0; ++i) tstore(B::at_off(0), B::ra(0), i, tc::tf32_hi(in[i]));
+            for (int i = 0; i < K0; ++i) { const float ih = tc::tf32_hi(in[i]); tstore(B::at_off(0), B::ra(0), i, ih, in[i] - ih); }
+          }
           {
+            TCP_T0();
             constexpr int KP1 = C::kp(1), CH = tc::chunk16_of(KP1);
+            static_for<0, KP1 / CH>([&](auto cc) {
+              constexpr int c0 = decltype(cc)::value * CH;
+              if (mine(c0)) {
+                float hi[CH], lo[CH], dv[CH];
 #pragma unroll
-            for (int c0 = 0; c0 < KP1; c0 += CH) {
-              float hi[CH], lo[CH], dv[CH];
+                for (int i = 0; i < CH; ++i) {
+                  const int n = c0 + i;
+                  float a = 0.f, d = 0.f;
+                  if (n < N0) {
+                    float w[C::R0];
+                    ld_vec<C::R0>(w, W0 + n * C::R0);
+                    float z = C::BIAS ? w[K0] : 0.f;
 #pragma unroll
-              for (int i = 0; i < CH; ++i) {
-                const int n = c0 + i;
-                float a = 0.f, d = 0.f;
-                if (n < N0) {
-                  float w[C::R0];
-                  ld_vec<C::R0>(w, W0 + n * C::R0);
-                  float z = C::BIAS ? w[K0] : 0.f;
-#pragma unroll
-                  for (int q = 0; q < K0; ++q) z = fmaf(w[q], in[q], z);
-                  tc::act_ad<M::ACT>(z, act_prm, a, d);
-                } else if (n == N0 && C::BIAS) a = 1.f;
-                hi[i] = tc::tf32_hi(a);
-                lo[i] = a - hi[i];
-                dv[i] = d;
-                if (n < N0) {
-                  tstore(B::at_off(1), B::ra(1), n, hi[i]);
-                  if constexpr (B::MASK) masks[1][n >> 5] = (masks[1][n >> 5] & ~(1u << (n & 31))) | (a > 0.f ? (1u << (n & 31)) : 0u);
+                    for (int q = 0; q < K0; ++q) z = fmaf(w[q], in[q], z);
+                    tc::act_ad<M::ACT>(z, act_prm, a, d);
+                  } else if (n == N0 && C::BIAS) a = 1.f;
+                  hi[i] = tc::tf32_hi(a);
+                  lo[i] = a - hi[i];
+                  dv[i] = d;
+                  if (n < N0) {
+                    tstore(B::at_off(1), B::ra(1), n, hi[i], lo[i]);
+                    if constexpr (B::MASK) mask_set(IC<1>{}, n, a);
+                  }
                 }
+                tc::tmem_st<CH>(t_oph + c0, hi);
+                tc::tmem_st<CH>(t_opl + c0, lo);
+                if constexpr (!B::MASK) {
+                  if constexpr (c0 < B::der_w(1)) tc::tmem_st<CH>(tmem + lane_base + B::der_off(1) + c0, dv);
+                }
+                (void)dv;
               }
-              tc::tmem_st<CH>(t_oph + c0, hi);
-              tc::tmem_st<CH>(t_opl + c0, lo);
-              if constexpr (!B::MASK) {
-                if (c0 < B::der_w(1)) tc::tmem_st<CH>(tmem + lane_base + B::der_off(1) + c0, dv);
-              }
-              (void)dv;
-            }
+            });
+            TCP_ADD(o_l0);
           }
           arrive_ops();
           // ---- hidden layers forward (tensor cores) and, after the last one, the output layer backward
-#pragma unroll
-          for (int i = 0; i < NX; ++i) w_cot[i] = valid ? w_cot[i] : 0.f;
           static_for<1, NL - 1>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
             constexpr int Nl = C::N(l);
             { TCP_T0(); mbar_wait(&bars[2], ph_mma); ph_mma ^= 1; TCP_ADD(o_wait_mma); }
             tc::fence_after();
             if constexpr (l < NL - 2) {
+              TCP_T0();
               constexpr int KPN = C::kp(l + 1), CH = tc::chunk16_of(KPN);
+              static_for<0, KPN / CH>([&](auto cc) {
+                constexpr int c0 = decltype(cc)::value * CH;
+                if (mine(c0)) {
+                  float v[CH], hi[CH], lo[CH], dv[CH];
+                  tc::tmem_ld<CH>(t_acc + c0, v);
 #pragma unroll
-              for (int c0 = 0; c0 < KPN; c0 += CH) {
-                float v[CH], hi[CH], lo[CH], dv[CH];
-                tc::tmem_ld<CH>(t_acc + c0, v);
-#pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                  const int n = c0 + i;
-                  float a = 0.f, d = 0.f;
-                  if (n < Nl) tc::act_ad<M::ACT>(v[i], act_prm, a, d);
-                  else if (n == Nl && C::BIAS) a = 1.f;
-                  hi[i] = tc::tf32_hi(a);
-                  lo[i] = a - hi[i];
-                  dv[i] = d;
-                  if (n < Nl) {
-                    tstore(B::at_off(l + 1), B::ra(l + 1), n, hi[i]);
-                    if constexpr (B::MASK) masks[l + 1][n >> 5] = (masks[l + 1][n >> 5] & ~(1u << (n & 31))) | (a > 0.f ? (1u << (n & 31)) : 0u);
+                  for (int i = 0; i < CH; ++i) {
+                    const int n = c0 + i;
+                    float a = 0.f, d = 0.f;
+                    if (n < Nl) tc::act_ad<M::ACT>(v[i], act_prm, a, d);
+                    else if (n == Nl && C::BIAS) a = 1.f;
+                    hi[i] = tc::tf32_hi(a);
+                    lo[i] = a - hi[i];
+                    dv[i] = d;
+                    if (n < Nl) {
+                      tstore(B::at_off(l + 1), B::ra(l + 1), n, hi[i], lo[i]);
+                      if constexpr (B::MASK) mask_set(IC<l + 1>{}, n, a);
+                    }
                   }
+                  tc::tmem_st<CH>(t_oph + c0, hi);
+                  tc::tmem_st<CH>(t_opl + c0, lo);
+                  if constexpr (!B::MASK) {
+                    if constexpr (c0 < B::der_w(l + 1)) tc::tmem_st<CH>(tmem + lane_base + B::der_off(l + 1) + c0, dv);
+                  }
+                  (void)dv;
                 }
-                tc::tmem_st<CH>(t_oph + c0, hi);
-                tc::tmem_st<CH>(t_opl + c0, lo);
-                if constexpr (!B::MASK) {
-                  if (c0 < B::der_w(l + 1)) tc::tmem_st<CH>(tmem + lane_base + B::der_off(l + 1) + c0, dv);
-                }
-                (void)dv;
-              }
+              });
+              TCP_ADD(o_fwd);
               arrive_ops();
             } else {
+              TCP_T0();
               // last hidden layer: a_{NL-1} (transposed tile only), then straight into the backward pass:
               // output layer on CUDA cores  dA[k] = sum_j w[j] WL[j][k],  dZ = dA * act'
+              if (hf == 0) {
 #pragma unroll
-              for (int j = 0; j < NLAST; ++j) tstore(B::DTL_OFF, 8, j, tc::tf32_hi(w_cot[j]));
-              constexpr int KPD = B::dkp(l), CH = tc::chunk16_of(KPD);      // operand width of the data-gradient GEMM of layer l
-#pragma unroll
-              for (int c0 = 0; c0 < KPD; c0 += CH) {
-                float v[CH], hi[CH], lo[CH];
-                tc::tmem_ld<CH>(t_acc + c0, v);
-#pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                  const int n = c0 + i;
-                  float dz = 0.f;
-                  if (n < Nl) {
-                    float a, d;
-                    tc::act_ad<M::ACT>(v[i], act_prm, a, d);
-                    tstore(B::at_off(NL - 1), B::ra(NL - 1), n, tc::tf32_hi(a));
-                    float da = 0.f;
-#pragma unroll
-                    for (int j = 0; j < NLAST; ++j) da = fmaf(w_cot[j], WL[j * C::RL + n], da);
-                    dz = da * d;
-                  }
-                  hi[i] = tc::tf32_hi(dz);
-                  lo[i] = dz - hi[i];
-                  if (n < Nl) tstore(B::DT_OFF, B::RD, n, hi[i]);
-                }
-                tc::tmem_st<CH>(t_oph + c0, hi);
-                tc::tmem_st<CH>(t_opl + c0, lo);
+                for (int j = 0; j < NLAST; ++j) { const float wh_ = tc::tf32_hi(w_cot[j]); tstore(B::DTL_OFF, 8, j, wh_, w_cot[j] - wh_); }
               }
+              constexpr int KPD = B::dkp(l), CH = tc::chunk16_of(KPD);      // operand width of the data-gradient GEMM of layer l
+              static_for<0, KPD / CH>([&](auto cc) {
+                constexpr int c0 = decltype(cc)::value * CH;
+                if (mine(c0)) {
+                  float v[CH], hi[CH], lo[CH];
+                  float wl4[NLAST][4];
+                  tc::tmem_ld<CH>(t_acc + c0, v);
+#pragma unroll
+                  for (int i = 0; i < CH; ++i) {
+                    const int n = c0 + i;
+                    float dz = 0.f;
+                    if ((i & 3) == 0) {                                      // output-layer weights of 4 columns: one LDS.128 per row
+#pragma unroll
+                      for (int j = 0; j < NLAST; ++j) {
+                        if (n < C::RL) ld_vec<4>(wl4[j], WL + j * C::RL + n);
+                      }
+                    }
+                    if (n < Nl) {
+                      float a, d;
+                      tc::act_ad<M::ACT>(v[i], act_prm, a, d);
+                      { const float ah_ = tc::tf32_hi(a); tstore(B::at_off(NL - 1), B::ra(NL - 1), n, ah_, a - ah_); }
+                      float da = 0.f;
+#pragma unroll
+                      for (int j = 0; j < NLAST; ++j) da = fmaf(w_cot[j], wl4[j][i & 3], da);
+                      dz = da * d;
+                    }
+                    hi[i] = tc::tf32_hi(dz);
+                    lo[i] = dz - hi[i];
+                    if (n < Nl) tstore(B::DT_OFF, B::RD, n, hi[i], lo[i]);
+                  }
+                  tc::tmem_st<CH>(t_oph + c0, hi);
+                  tc::tmem_st<CH>(t_opl + c0, lo);
+                }
+              });
+              TCP_ADD(o_last);
               arrive_ops();
             }
           });
@@ -778,63 +845,103 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
             constexpr int Kl = C::K(l);                                    // width of dA_l = hidden width of a_l
             { TCP_T0(); mbar_wait(&bars[2], ph_mma); ph_mma ^= 1; TCP_ADD(o_wait_mma); }
             tc::fence_after();
-            { TCP_T0(); mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; TCP_ADD(o_wait_wg); }  // weight-gradient GEMMs reading DT are done
             if constexpr (l > 1) {
-              constexpr int KPD = B::dkp(l - 1), CH = tc::chunk16_of(KPD);
+              TCP_T0();
+              constexpr int KPD = B::dkp(l - 1), CH = tc::chunk16_of(KPD), NCH = KPD / CH;
+              // this thread's dZ_l columns: operand (tensor memory) first, the transposed copy only after the
+              // weight-gradient GEMMs that still read DT have completed
+              float keep_hi[own_cnt(NCH, CH)][CH], keep_lo[B::WG3 ? own_cnt(NCH, CH) : 1][CH];
+              static_for<0, NCH>([&](auto cc) {
+                constexpr int ci = decltype(cc)::value, c0 = ci * CH;
+                if (mine(c0)) {
+                  float v[CH], hi[CH], lo[CH], dv[CH];
+                  tc::tmem_ld<CH>(t_acc + c0, v);
+                  if constexpr (!B::MASK) tc::tmem_ld<CH>(tmem + lane_base + B::der_off(l) + c0, dv);
 #pragma unroll
-              for (int c0 = 0; c0 < KPD; c0 += CH) {
-                float v[CH], hi[CH], lo[CH], dv[CH];
-                tc::tmem_ld<CH>(t_acc + c0, v);
-                if constexpr (!B::MASK) tc::tmem_ld<CH>(tmem + lane_base + B::der_off(l) + c0, dv);
-#pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                  const int n = c0 + i;
-                  float dz = 0.f;
-                  if (n < Kl) {
-                    float d;
-                    if constexpr (B::MASK) d = M::ACT == NM_ACT_IDENTITY ? 1.f : (((masks[l][n >> 5] >> (n & 31)) & 1u) ? 1.f : (M::ACT == NM_ACT_LEAKY ? act_prm : 0.f));
-                    else d = dv[i];
-                    dz = v[i] * d;
+                  for (int i = 0; i < CH; ++i) {
+                    const int n = c0 + i;
+                    float dz = 0.f;
+                    if (n < Kl) {
+                      float d;
+                      if constexpr (B::MASK) d = mask_d(IC<l>{}, n); else d = dv[i];
+                      dz = v[i] * d;
+                    }
+                    hi[i] = tc::tf32_hi(dz);
+                    lo[i] = dz - hi[i];
+                    keep_hi[own_idx(ci, CH)][i] = hi[i];
+                    if constexpr (B::WG3) keep_lo[own_idx(ci, CH)][i] = lo[i];
                   }
-                  hi[i] = tc::tf32_hi(dz);
-                  lo[i] = dz - hi[i];
-                  if (n < Kl) tstore(B::DT_OFF, B::RD, n, hi[i]);
+                  tc::tmem_st<CH>(t_oph + c0, hi);
+                  tc::tmem_st<CH>(t_opl + c0, lo);
                 }
-                tc::tmem_st<CH>(t_oph + c0, hi);
-                tc::tmem_st<CH>(t_opl + c0, lo);
-              }
+              });
+              TCP_ADD(o_bwd);
+              wait_wg();                                                   // weight-gradient GEMMs reading DT are done
+              static_for<0, NCH>([&](auto cc) {
+                constexpr int ci = decltype(cc)::value, c0 = ci * CH;
+                if (mine(c0)) {
+#pragma unroll
+                  for (int i = 0; i < CH; ++i) {
+                    const int n = c0 + i;
+                    if (n < Kl) tstore(B::DT_OFF, B::RD, n, keep_hi[own_idx(ci, CH)][i], B::WG3 ? keep_lo[own_idx(ci, CH)][i] : 0.f);
+                  }
+                }
+              });
               arrive_ops();
             } else {
               // l == 1: dZ_1, then layer 0 backward on CUDA cores
-              constexpr int CH = tc::chunk16_of(round_up(Kl, 8));
+              TCP_T0();
+              constexpr int CH = tc::chunk16_of(round_up(Kl, 8)), NCH = round_up(Kl, 8) / CH;
+              float keep_dz[own_cnt(NCH, CH)][CH];
+              static_for<0, NCH>([&](auto cc) {
+                constexpr int ci = decltype(cc)::value, c0 = ci * CH;
+                if (mine(c0)) {
+                  float v[CH], dv[CH];
+                  tc::tmem_ld<CH>(t_acc + c0, v);
+                  if constexpr (!B::MASK) tc::tmem_ld<CH>(tmem + lane_base + B::der_off(1) + c0, dv);
 #pragma unroll
-              for (int c0 = 0; c0 < round_up(Kl, 8); c0 += CH) {
-                float v[CH], dv[CH];
-                tc::tmem_ld<CH>(t_acc + c0, v);
-                if constexpr (!B::MASK) tc::tmem_ld<CH>(tmem + lane_base + B::der_off(1) + c0, dv);
+                  for (int i = 0; i < CH; ++i) {
+                    const int n = c0 + i;
+                    float dz = 0.f;
+                    if (n < Kl) {
+                      float d;
+                      if constexpr (B::MASK) d = mask_d(IC<1>{}, n); else d = dv[i];
+                      dz = v[i] * d;
+                      float w[C::R0];
+                      ld_vec<C::R0>(w, W0 + n * C::R0);
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                  const int n = c0 + i;
-                  if (n < Kl) {
-                    float d;
-                    if constexpr (B::MASK) d = M::ACT == NM_ACT_IDENTITY ? 1.f : (((masks[1][n >> 5] >> (n & 31)) & 1u) ? 1.f : (M::ACT == NM_ACT_LEAKY ? act_prm : 0.f));
-                    else d = dv[i];
-                    const float dz = v[i] * d;
-                    tstore(B::DT_OFF, B::RD, n, tc::tf32_hi(dz));
-                    float w[C::R0];
-                    ld_vec<C::R0>(w, W0 + n * C::R0);
+                      for (int q = 0; q < K0; ++q) d_in[q] = fmaf(dz, w[q], d_in[q]);
+                    }
+                    keep_dz[own_idx(ci, CH)][i] = dz;
+                  }
+                  (void)dv;
+                }
+              });
+              TCP_ADD(o_l1);
+              wait_wg();                                                   // weight-gradient GEMMs reading DT are done
+              static_for<0, NCH>([&](auto cc) {
+                constexpr int ci = decltype(cc)::value, c0 = ci * CH;
+                if (mine(c0)) {
 #pragma unroll
-                    for (int q = 0; q < K0; ++q) d_in[q] = fmaf(dz, w[q], d_in[q]);
+                  for (int i = 0; i < CH; ++i) {
+                    const int n = c0 + i;
+                    if (n < Kl) { const float dz = keep_dz[own_idx(ci, CH)][i]; const float dh_ = tc::tf32_hi(dz); tstore(B::DT_OFF, B::RD, n, dh_, dz - dh_); }
                   }
                 }
-              }
+              });
               arrive_ops();
               wg_pending = true;
             }
           });
+          // the pair's partial input gradients meet in shared memory
+          TCP_T0();
+#pragma unroll
+          for (int q = 0; q < K0; ++q) xch[(hf * 128 + m_) * 8 + q] = d_in[q];
+          asm volatile("bar.sync %0, 64;\n" ::"r"(1 + (warp & 3)) : "memory");
           float gxs[NX];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) gxs[i] = d_in[i];
+          for (int i = 0; i < NX; ++i) gxs[i] = xch[m_ * 8 + i] + xch[(128 + m_) * 8 + i];
+          TCP_ADD(o_xch);
           static_for<0, NS>([&](auto sc) {
             constexpr int St = decltype(sc)::value;
             if (st == St) stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
@@ -858,18 +965,18 @@ __global__ void __launch_bounds__(160, 1) nm_tc_bwd_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] : 0.f;
       }
-      if (valid && args.grad_x0 != nullptr) {
+      if (valid && hf == 0 && args.grad_x0 != nullptr) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) args.grad_x0[b * NX + i] = lam[i];
       }
     }
     if (step_cnt > 0) {
-      if (wg_pending) { mbar_wait(&bars[3], ph_wg); ph_wg ^= 1; wg_pending = false; tc::fence_after(); }
+      if (wg_pending) { wait_wg(); wg_pending = false; tc::fence_after(); }
       flush();
     }
 #ifdef NM_TUNE_TCPROF
     if (blockIdx.x == 0 && tid == 0)
-      printf("[tcprof owner0] total %lld  wait_mma %lld  wait_wg %lld  arrive %lld  flush %lld\n", clock64() - o_begin, o_wait_mma, o_wait_wg, o_arrive, o_flush);
+      printf("[tcprof owner0] total %lld  wait_mma %lld  wait_wg %lld  arrive %lld  flush %lld | l0 %lld fwd %lld last %lld bwd %lld l1 %lld xch %lld\n", clock64() - o_begin, o_wait_mma, o_wait_wg, o_arrive, o_flush, o_l0, o_fwd, o_last, o_bwd, o_l1, o_xch);
 #endif
   }
   tc::fence_before();
