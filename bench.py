@@ -284,8 +284,12 @@ def main():
     tf32x3_peak = peaks["bf16_tflops"] / 2.0 / 3.0             # fp32-accurate tensor-pipe peak (3xTF32 split)
     achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
     traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    traffic = json.load(open(traffic_path)).get("bwd_dram_bytes_per_launch") if os.path.exists(traffic_path) else None
-    roofline = {"bound": "tensor", "kernel": "nm_bwd_kernel", "achieved": achieved, "peak": tf32x3_peak,
+    traffic = None
+    if os.path.exists(traffic_path):                           # one ncu --set full capture, scaled to this batch
+        tj = json.load(open(traffic_path))
+        traffic = tj["bwd_dram_bytes_per_launch"] * (B / tj["batch"])
+    bwd_kernel = "nm_tc_bwd_kernel" if "bwd[tcgen05" in kernel_info else "nm_bwd_kernel"
+    roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": tf32x3_peak,
                 "unit": "TFLOP/s", "frac": achieved / tf32x3_peak, "traffic": traffic,
                 "peak_source": f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 2 (tf32) / 3 (3xTF32 fp32-accurate split)",
                 "ffma_peak_tflops": 72.2, "ffma_frac": achieved / 72.2,

@@ -277,7 +277,11 @@ NmKernelEntry g_entry;
 
 struct Registrar {
   Registrar() {
-    if (kTcFwd)
+    if (kTcFwd && kTcBwd)
+      std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tcgen05 tile=128 threads=288 wgrad=%s; below 2^20 products or without checkpoints: ffma tile=%d threads=%d smem=%zu] compiled_terms=%d",
+                    TK::C::FWD_COLS, TK::FWD_SMEM_BYTES, TK::MAX_CTAS, TcBwd<NM_SPEC_NAME, kTcBwd>::WG3 ? "3xTF32" : "1xTF32-rn", SB::TILE, SB::THREADS,
+                    KC::BWD_SMEM_BYTES, S::NTERMS);
+    else if (kTcFwd)
       std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tile=%d threads=%d w_smem=%d smem=%zu dw_spill=%d] minb=%d/%d compiled_terms=%d wprep_floats=%d",
                     TK::C::FWD_COLS, TK::FWD_SMEM_BYTES, TK::MAX_CTAS, SB::TILE, SB::THREADS, int(SB::W_SMEM), KC::BWD_SMEM_BYTES,
                     int(KC::DW_SPILL), S::MINB_FWD, S::MINB_BWD, S::NTERMS, KC::W_FLOATS_ALL);
