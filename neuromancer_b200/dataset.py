@@ -26,3 +26,48 @@ class DictDataset(Dataset):
 def move_batch_to_device(batch, device="cpu"):
     return {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v)
             for k, v in batch.items()}
+
+
+class DevicePrefetcher:
+    """Iterate over host batches (dicts of pinned CPU tensors) and hand them out as device batches, with the
+    host->device copy of batch i+1 running on a side stream while batch i is being computed.
+
+    The trainer's ``for batch in train_data: move_batch_to_device(...)`` loop (reference trainer.py:240-243)
+    serialises copy and compute; on B200 the copy of one C2 batch (16.8 MB) is 0.31 ms next to a 1.3 ms step.
+    The prefetcher keeps the order of batches and makes the compute stream wait for the copy it consumes, so
+    results are unchanged."""
+
+    def __init__(self, batches, device="cuda", depth=2):
+        self.batches, self.device = batches, torch.device(device)
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.depth = max(int(depth), 1)
+
+    def _issue(self, batch):
+        if self.stream is None:
+            return move_batch_to_device(batch, self.device), None
+        with torch.cuda.stream(self.stream):
+            dev = move_batch_to_device(batch, self.device)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def __iter__(self):
+        it = iter(self.batches)
+        queue = []
+        try:
+            for _ in range(self.depth):
+                queue.append(self._issue(next(it)))
+        except StopIteration:
+            pass
+        while queue:
+            dev, ev = queue.pop(0)
+            try:
+                queue.append(self._issue(next(it)))          # next copy goes out before this batch is consumed
+            except StopIteration:
+                pass
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                for v in dev.values():                        # the caching allocator must not recycle the buffers early
+                    if isinstance(v, torch.Tensor):
+                        v.record_stream(torch.cuda.current_stream(self.device))
+            yield dev

@@ -13,7 +13,37 @@ from copy import deepcopy
 import numpy as np
 import torch
 
-from .dataset import move_batch_to_device
+from .dataset import DevicePrefetcher, move_batch_to_device
+
+
+class LaggedScalarReader:
+    """Per-step device->host read of a scalar (the loss) that does not stall the launch pipeline: step k's value is
+    copied into pinned host memory asynchronously and collected while step k+1 is already queued.  Every step's
+    value reaches the host; `read()` returns the values in order (one step late), `drain()` the rest."""
+
+    def __init__(self, device, depth=2):
+        self.buf = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ev = [torch.cuda.Event() for _ in range(depth)]
+        self.pending, self.k, self.depth = [], 0, depth
+
+    def push(self, scalar):
+        out = []
+        if len(self.pending) == self.depth:
+            out.append(self._pop())
+        slot = self.k % self.depth
+        self.buf[slot].copy_(scalar.detach().reshape(1), non_blocking=True)
+        self.ev[slot].record()
+        self.pending.append(slot)
+        self.k += 1
+        return out
+
+    def _pop(self):
+        slot = self.pending.pop(0)
+        self.ev[slot].synchronize()
+        return float(self.buf[slot])
+
+    def drain(self):
+        return [self._pop() for _ in range(len(self.pending))]
 
 
 class Trainer:
@@ -50,9 +80,9 @@ class Trainer:
         for i in range(self.current_epoch, self.current_epoch + self.epochs):
             self.model.train()
             losses = []
-            for batch in self.train_data:
+            for batch in DevicePrefetcher(self.train_data, self.device):     # copy of batch k+1 overlaps step k
                 batch["epoch"] = i
-                output = self.train_step(move_batch_to_device(batch, self.device))
+                output = self.train_step(batch)
                 losses.append(output[self.train_metric].detach())
             output[f"mean_{self.train_metric}"] = torch.mean(torch.stack(losses))
             if self.lr_scheduler is not None:

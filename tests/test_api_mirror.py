@@ -106,3 +106,14 @@ def test_node_key_handling():
     assert not any(p.requires_grad for p in net.parameters())
     node.unfreeze()
     assert all(p.requires_grad for p in net.parameters())
+
+
+def test_device_prefetcher_keeps_order_and_content_on_cpu():
+    import torch
+    from neuromancer_b200.dataset import DevicePrefetcher
+    batches = [{"x": torch.full((2, 3), float(i)), "name": "train"} for i in range(5)]
+    got = list(DevicePrefetcher(iter(batches), device="cpu", depth=2))
+    assert len(got) == 5
+    for i, b in enumerate(got):
+        assert b["name"] == "train" and torch.equal(b["x"], batches[i]["x"])
+    assert list(DevicePrefetcher(iter([]), device="cpu")) == []

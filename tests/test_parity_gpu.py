@@ -301,3 +301,12 @@ def test_tensor_core_adjoint_is_deterministic():
     b = _grads_with(case, batch, "1")
     for x, y in zip(a["grads"], b["grads"]):
         assert torch.equal(x, y)
+
+
+def test_device_prefetcher_feeds_the_same_batches():
+    from neuromancer_b200.dataset import DevicePrefetcher
+    case = H.make_case("c2", DEV)
+    host = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.make_batch(256, "cpu", s).items()} for s in range(4)]
+    want = [float(case.problem(to_dev(b))["train_loss"]) for b in host]
+    got = [float(case.problem(b)["train_loss"]) for b in DevicePrefetcher(iter(host), DEV)]
+    assert got == want
