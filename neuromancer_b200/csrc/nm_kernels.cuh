@@ -242,21 +242,26 @@ struct DwStore<MC, TILE, THREADS, L, false> {
 };
 struct DwNone { __device__ __forceinline__ void zero() {} };
 
-// add the thread's tile of layer L to  dst[n*K + k]  (atomic: split groups share entries)
+// add the thread's tile of layer L to  dst[n*K + k].  With a trajectory split (SPLIT > 1) several thread groups
+// hold partial sums of the same entries: they are added one group after the other, a barrier apart, so that the
+// result does not depend on scheduling (bitwise reproducible gradients).  Called by every thread of the CTA.
 template <class D, int N, int K>
-__device__ __forceinline__ void dw_flush_tile(const float (&acc)[D::RJ][D::RK], float* __restrict__ dst, int unit, bool atomic) {
+__device__ __forceinline__ void dw_flush_tile(const float (&acc)[D::RJ][D::RK], float* __restrict__ dst, int unit) {
   const int tile = unit % D::TILES, grp = unit / D::TILES;
-  if (grp >= D::SPLIT) return;
   const int kt = tile % D::NKT, jt = tile / D::NKT;
+#pragma unroll 1
+  for (int g = 0; g < D::SPLIT; ++g) {
+    if (grp == g) {
 #pragma unroll
-  for (int i = 0; i < D::RJ; ++i)
+      for (int i = 0; i < D::RJ; ++i)
 #pragma unroll
-    for (int j = 0; j < D::RK; ++j) {
-      const int n = jt + D::NJ * i, k = kt + D::NKT * j;
-      if (n < N && k < K) {
-        if (atomic) atomicAdd(dst + n * K + k, acc[i][j]); else dst[n * K + k] += acc[i][j];
-      }
+        for (int j = 0; j < D::RK; ++j) {
+          const int n = jt + D::NJ * i, k = kt + D::NKT * j;
+          if (n < N && k < K) dst[n * K + k] += acc[i][j];
+        }
     }
+    if constexpr (D::SPLIT > 1) __syncthreads();
+  }
 }
 
 // MLP backward on the tile.  delta_{NL} (cotangent of the raw output) must be in dbuf0 and visible.
@@ -328,7 +333,7 @@ __device__ __forceinline__ void mlp_backward(const float* __restrict__ W, const 
 #pragma unroll
             for (int j = 0; j < D::RK; ++j) t[i][j] = 0.f;
           dw_tile<N, K, TILE, THREADS, LD>(t, dl, al, s * THREADS + tid);
-          dw_flush_tile<D, N, K>(t, gw_dst, s * THREADS + tid, D::SPLIT > 1);
+          dw_flush_tile<D, N, K>(t, gw_dst, s * THREADS + tid);
         }
         if (has_bias && tid < N) {
           const float* row = dl + tid * LD;
@@ -356,7 +361,7 @@ __device__ __forceinline__ void dw_writeout(Store& store, float* __restrict__ gd
     auto& st = store.template at<l>();
     float* dst = gdst + MC::p_off(l);
 #pragma unroll
-    for (int s = 0; s < D::SLOTS; ++s) dw_flush_tile<D, N, K>(st.acc[s], dst, s * THREADS + tid, D::SPLIT > 1);
+    for (int s = 0; s < D::SLOTS; ++s) dw_flush_tile<D, N, K>(st.acc[s], dst, s * THREADS + tid);
     if (has_bias && tid < N) dst[N * K + tid] += st.db;
   });
 }

@@ -307,6 +307,38 @@ def test_device_prefetcher_feeds_the_same_batches():
     from neuromancer_b200.dataset import DevicePrefetcher
     case = H.make_case("c2", DEV)
     host = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in case.make_batch(256, "cpu", s).items()} for s in range(4)]
-    want = [float(case.problem(to_dev(b))["train_loss"]) for b in host]
-    got = [float(case.problem(b)["train_loss"]) for b in DevicePrefetcher(iter(host), DEV)]
+    want = [float(case.problem(to_dev(b))["train_loss"].detach()) for b in host]
+    got = [float(case.problem(b)["train_loss"].detach()) for b in DevicePrefetcher(iter(host), DEV)]
     assert got == want
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-size runs through size-independent properties (the oracle cannot run these sizes in seconds)
+FULL_SIZE = [("c1", 3333), ("c2", 65536), ("c3", 65536), ("c4p", 32768), ("c5", 4096)]
+
+
+@pytest.mark.parametrize("name,B", FULL_SIZE)
+def test_full_size_shard_additivity_and_determinism(name, B):
+    """Trajectories are independent given the weights and every loss term is a mean: the loss and the gradient of a
+    batch must equal the average over its two halves (this is also what the data-parallel all-reduce relies on),
+    rows of the trajectories must not depend on which launch / tile / wave produced them, and a repeat must be
+    bitwise identical.  Runs the persistent kernels over many waves of tiles at the benchmark batch sizes."""
+    case = H.make_case(name, DEV, seed=2)
+    full = to_dev(case.make_batch(B, "cpu", 21))
+    half = B // 2
+    lo = {k: (v[:half].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
+    hi = {k: (v[half:2 * half].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
+    both = {k: (v[:2 * half].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
+    r_all = H.product_run(case, both)
+    r_again = H.product_run(case, both)
+    r_lo, r_hi = H.product_run(case, lo), H.product_run(case, hi)
+    for k in r_all["traj"]:
+        assert torch.equal(r_all["traj"][k], r_again["traj"][k])
+        assert torch.equal(r_all["traj"][k][:half], r_lo["traj"][k]), f"{name}: trajectory rows depend on the launch ({k})"
+        assert torch.equal(r_all["traj"][k][half:], r_hi["traj"][k])
+        assert torch.isfinite(r_all["traj"][k]).all()
+    assert torch.equal(r_all["loss"], r_again["loss"])
+    assert_rel(r_all["loss"], 0.5 * (r_lo["loss"] + r_hi["loss"]), 1e-5, f"{name} B={B} loss additivity")
+    for i, (g, a, b) in enumerate(zip(r_all["grads"], r_lo["grads"], r_hi["grads"])):
+        assert torch.equal(g, r_again["grads"][i])
+        assert_rel(g, 0.5 * (a + b), 2e-5, f"{name} B={B} gradient additivity, grad {i}")
