@@ -67,3 +67,20 @@ def test_null_arguments_fail_without_touching_the_device(nm_lib):
     plan = configs.build_case("c1").plan()
     rc = nm_lib.nm_rollout_forward(C.byref(plan.c), None, None, None, None, None, None, None, None, None, 0, 8, None)
     assert rc == L.NM_ERR_BAD_PLAN
+
+
+def test_neural_ode_classes_are_served_by_the_tensor_core_kernels(nm_lib):
+    """The c3 shape class (60-wide hidden layers) is compiled onto the tcgen05 kernels, the small RKF test shape is
+    forced onto them (build.TUNING_RULES) so that the parity suite covers a second class; narrow policies stay on
+    the FFMA kernels.  Checkpoint buffer: stage derivatives k_0..k_{NS-2} of every step."""
+    info = nm_lib.nm_kernel_info(C.byref(configs.build_case("c3").plan().c)).decode()
+    assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "1xTF32-rn" in info
+    info = nm_lib.nm_kernel_info(C.byref(configs.build_case("t_int_rkf_node").plan().c)).decode()
+    assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "3xTF32" in info
+    assert "tcgen05" not in nm_lib.nm_kernel_info(C.byref(configs.build_case("c2").plan().c)).decode()
+    plan = configs.build_case("c3").plan()
+    nbytes = C.c_size_t()
+    assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(plan.c), 1000, C.byref(nbytes)) == L.NM_OK
+    assert nbytes.value == 1000 * plan.c.nsteps * 3 * plan.c.nx * 4          # RK4: 3 kept stages
+    assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c2").plan().c), 1000, C.byref(nbytes)) == L.NM_OK
+    assert nbytes.value == 0
