@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -224,7 +224,6 @@ def main():
         ev[i][3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
     step_ms = [e[0].elapsed_time(e[3]) for e in ev]
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
@@ -286,6 +285,8 @@ def main():
                "d2h_bytes_per_step": 4, "ms_per_step": float(dt) / args.steps * 1e3,
                "api": "DevicePrefetcher (Trainer.train loop) -> Problem.forward + loss.backward; every batch copied from pinned host memory inside the timed region, every step's loss read back on the host (asynchronously, one step late)"}
 
+    # clocks / throttle reasons sampled every 20 ms over both timed regions (device-resident steps and end-to-end steps)
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
