@@ -367,6 +367,12 @@ int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes) {
   if (rc != NM_OK) return rc;
   if (!bytes || B < 1) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
   *bytes = 0;
+  // a shape class on the tensor-core path states what its kernels keep (policy mode: the raw policy output o_t)
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  if (e != nullptr && e->chk_floats_per_step >= 0) {
+    *bytes = size_t(B) * size_t(plan->nsteps) * size_t(e->chk_floats_per_step) * sizeof(float);
+    return NM_OK;
+  }
   if (plan->dyn_kind == NM_DYN_ODE && plan->rhs_kind == NM_RHS_MLP) {
     const int ns = integrator_stages(plan->integrator);
     *bytes = size_t(B) * size_t(plan->nsteps) * size_t(ns - 1) * size_t(plan->nx) * sizeof(float);

@@ -29,6 +29,8 @@ struct NmKernelEntry {
   int (*forward)(const NmPlan*, NmFwdCall*);      // prep + rollout kernel; returns NM_OK / NM_ERR_*
   int (*backward)(const NmPlan*, NmBwdCall*);     // prep + adjoint kernel
   const char* info;                               // tile / threads / smem, for diagnostics
+  int chk_floats_per_step;                        // checkpoint floats per trajectory-step the kernels of this entry keep
+                                                  // (-1: generic rule -- stage derivatives for MLP right-hand sides)
   NmKernelEntry* next;
 };
 

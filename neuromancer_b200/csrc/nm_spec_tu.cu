@@ -82,7 +82,10 @@ using TK = TcKCfg<NM_SPEC_NAME>;
 #ifdef NM_TUNE_TC
 constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && (NM_TUNE_TC != 0);
 #else
-constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && TK::C::max_hidden() >= 48;
+// right-hand-side mode: from ~48 hidden units up (below, the 44-cycle MMA floor loses to FFMA over the 4+ evaluations
+// of a step); policy mode: from 16 up -- one evaluation per step, and what the tensor pipe removes is not pipe time
+// but issue slots (FFMA + LDS are ~60 % of the FFMA kernels' instructions on the narrow policies)
+constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && TK::C::max_hidden() >= (TK::MD::POLICY ? 16 : 48);
 #endif
 
 // launch helpers as class templates so that the tensor-core kernels are only instantiated for eligible classes
@@ -121,14 +124,14 @@ template <class Sp> struct TcFwd<Sp, true> {
 template <class Sp, bool ON> struct TcBwd {
   static constexpr size_t W_BYTES = 0;
   static constexpr bool WG3 = false;
-  static constexpr int NS = 1;
+  static constexpr int EVALS = 1, CTAS = 1, THREADS = 0;
   static cudaError_t setup() { return cudaSuccess; }
   static void launch(const NmPlan&, const BwdArgs&, const float*, float*, int, cudaStream_t) {}
 };
 template <class Sp> struct TcBwd<Sp, true> {
   static constexpr size_t W_BYTES = TcBKCfg<Sp>::W_BYTES;
   static constexpr bool WG3 = TcBKCfg<Sp>::WG3;
-  static constexpr int NS = Tableau<Sp::INTEG>::NS;
+  static constexpr int EVALS = TcMode<Sp>::EVALS, CTAS = TcBKCfg<Sp>::CTAS_PER_SM, THREADS = TcBKCfg<Sp>::THREADS;
   static cudaError_t setup() {
     return cudaFuncSetAttribute(nm_tc_bwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcBKCfg<Sp>::SMEM_BYTES);
   }
@@ -192,7 +195,12 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   else { (void)cudaGetLastError(); }
   const int64_t tiles_f = (B + kFwdTile - 1) / kFwdTile, tiles_b = (B + SB::TILE - 1) / SB::TILE;
   const int64_t gf = tiles_f < int64_t(sms) * occf ? tiles_f : int64_t(sms) * occf;
-  const int64_t gb = tiles_b < int64_t(sms) * occb ? tiles_b : int64_t(sms) * occb;
+  int64_t gb = tiles_b < int64_t(sms) * occb ? tiles_b : int64_t(sms) * occb;
+  if (kTcBwd) {                                     // the tensor-core adjoint launches its own grid (128-trajectory tiles)
+    const int64_t tiles_tc = (B + 127) / 128, slots = int64_t(sms) * TcBwd<NM_SPEC_NAME, kTcBwd>::CTAS;
+    const int64_t gtc = tiles_tc < slots ? tiles_tc : slots;
+    if (gtc > gb) gb = gtc;
+  }
   *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
   *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float));
   return NM_OK;
@@ -253,9 +261,9 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
     using TB = TcBwd<NM_SPEC_NAME, kTcBwd>;
     const char* force = getenv("NM_TC_BWD");
     if (force != nullptr) tc_bwd = force[0] != '0';
-    else if (!TB::WG3) tc_bwd = double(c->B) * double(p->nsteps) * double(TB::NS) >= 1048576.0;
+    else if (!TB::WG3) tc_bwd = double(c->B) * double(p->nsteps) * double(TB::EVALS) >= 1048576.0;
   }
-  if (tc_bwd) { grid = d->sms; if (grid > int((c->B + 127) / 128)) grid = int((c->B + 127) / 128); if (grid < 1) grid = 1; c->grid = grid; }
+  if (tc_bwd) { grid = d->sms * TcBwd<NM_SPEC_NAME, kTcBwd>::CTAS; if (grid > int((c->B + 127) / 128)) grid = int((c->B + 127) / 128); if (grid < 1) grid = 1; c->grid = grid; }
   else launch_prep(p, c->params, wprep, c->stream);
   BwdArgs a{};
   a.params = c->params; a.wprep = wprep;
@@ -278,8 +286,9 @@ NmKernelEntry g_entry;
 struct Registrar {
   Registrar() {
     if (kTcFwd && kTcBwd)
-      std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tcgen05 tile=128 threads=288 wgrad=%s; below 2^20 products or without checkpoints: ffma tile=%d threads=%d smem=%zu] compiled_terms=%d",
-                    TK::C::FWD_COLS, TK::FWD_SMEM_BYTES, TK::MAX_CTAS, TcBwd<NM_SPEC_NAME, kTcBwd>::WG3 ? "3xTF32" : "1xTF32-rn", SB::TILE, SB::THREADS,
+      std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tcgen05 tile=128 threads=%d ctas/sm=%d wgrad=%s; below 2^20 products or without checkpoints: ffma tile=%d threads=%d smem=%zu] compiled_terms=%d",
+                    TK::C::FWD_COLS, TK::FWD_SMEM_BYTES, TK::MAX_CTAS, TcBwd<NM_SPEC_NAME, kTcBwd>::THREADS, TcBwd<NM_SPEC_NAME, kTcBwd>::CTAS,
+                    TcBwd<NM_SPEC_NAME, kTcBwd>::WG3 ? "3xTF32" : "1xTF32-rn", SB::TILE, SB::THREADS,
                     KC::BWD_SMEM_BYTES, S::NTERMS);
     else if (kTcFwd)
       std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tile=%d threads=%d w_smem=%d smem=%zu dw_spill=%d] minb=%d/%d compiled_terms=%d wprep_floats=%d",
@@ -295,6 +304,7 @@ struct Registrar {
     g_entry.forward = forward_fn;
     g_entry.backward = backward_fn;
     g_entry.info = g_info;
+    g_entry.chk_floats_per_step = kTcFwd ? TcMode<NM_SPEC_NAME>::CHK : -1;   // -1: the generic rule of nm_api.cu
     g_entry.next = nullptr;
     nm_register_kernel(&g_entry);
   }

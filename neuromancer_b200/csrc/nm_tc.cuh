@@ -270,7 +270,7 @@ __device__ __forceinline__ void act_ad(float z, float prm, float& a, float& d) {
   else { a = act_fwd<ACT>(z, prm); d = act_deriv_a<ACT>(a, prm); }
 }
 
-template <class M>
+template <class M, bool ALLOW_WG3 = true>
 struct TcBwdCfg {
   using C = TcCfg<M>;
   static constexpr int NL = C::NL;
@@ -294,13 +294,14 @@ struct TcBwdCfg {
   static constexpr int BWD_W = gimg_off(NI);
   // tensor-memory columns
   static constexpr int opw() { int m = C::kp_max(); for (int l = 1; l <= NL - 2; ++l) m = cmax(m, dkp(l)); return m; }
-  static constexpr int accw() { int m = cmax(C::np_max(), C::kp_max()); for (int l = 1; l <= NL - 2; ++l) m = cmax(m, dnp(l)); return m; }
+  // accumulator width: read back as the next layer's operand (kp wide) only when there is a next tensor-core layer
+  static constexpr int accw() { int m = NL > 3 ? cmax(C::np_max(), C::kp_max()) : C::np_max(); for (int l = 1; l <= NL - 2; ++l) m = cmax(m, cmax(dnp(l), dkp(l))); return m; }
   static constexpr int OPH = 0, OPL = opw(), ACC = 2 * opw();
   static constexpr int wgc(int l) { return round_up(C::kaug(l), 16); }     // weight-gradient accumulator of layer l: lanes n, columns k (+ bias)
   static constexpr int wg_off(int l) { int o = ACC + accw(); for (int i = 0; i < l; ++i) o += wgc(i); return o; }
   static constexpr bool MASK = act_is_mask<M::ACT>();
   // derivative stash for hidden layers 1 .. NL-2 (the last hidden layer's derivative is used on the spot)
-  static constexpr int der_w(int j) { return C::kp(j); }                   // j = index of the activation a_j (operand width: whole chunks)
+  static constexpr int der_w(int j) { return round_up(C::K(j), chunk16_of(C::kp(j))); }   // j = index of the activation a_j (whole store chunks)
   static constexpr int der_off(int j) { int o = wg_off(NL); for (int i = 1; i < j; ++i) o += der_w(i); return o; }
   static constexpr int COLS_USED = MASK ? wg_off(NL) : der_off(NL - 1);
   static constexpr int COLS = pow2_ceil(COLS_USED);
@@ -314,7 +315,7 @@ struct TcBwdCfg {
   // fits, else single-pass TF32 on round-to-nearest operands (noise ~ 2^-12 / sqrt(#products): large batches only)
   static constexpr int TILES_BYTES = at_off(NL);
   static constexpr int TAIL_BYTES = 2 * slot_floats() * 4 + SMALL * 4 + 2 * 128 * 8 * 4 + 512;
-  static constexpr bool WG3 = 2 * TILES_BYTES + TAIL_BYTES + 1024 <= 227 * 1024;
+  static constexpr bool WG3 = ALLOW_WG3 && 2 * TILES_BYTES + TAIL_BYTES + 1024 <= 227 * 1024;
   static constexpr int LO_OFF = TILES_BYTES;                              // remainder tile = same offset + LO_OFF
   static constexpr int RING_OFF = (WG3 ? 2 : 1) * TILES_BYTES;
   static constexpr int SMALL_OFF = RING_OFF + 2 * slot_floats() * 4;
@@ -328,7 +329,7 @@ struct TcBwdCfg {
 template <class M>
 __device__ void prep_tc_bwd(const float* __restrict__ params, float* __restrict__ dst, int gtid, int gthreads) {
   using C = TcCfg<M>;
-  using B = TcBwdCfg<M>;
+  using B = TcBwdCfg<M>;                       // the prepared block does not depend on the weight-gradient mode
   auto p_off = [](int l) { int o = 0; for (int i = 0; i < l; ++i) o += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0); return o; };
   {
     const float* W = params + p_off(0);

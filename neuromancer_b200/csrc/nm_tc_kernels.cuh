@@ -15,12 +15,43 @@
 
 namespace nm {
 
+// Two kinds of systems run on this path:
+//   RHS mode     System([Node(integrator(MLP))]): the MLP is the right-hand side, evaluated once per integrator stage
+//   POLICY mode  System([Node(MLP policy), Node(integrator(white-box RHS) | SSM)]): the MLP is the closed-loop policy
+//                (inputs: state and exogenous segments, output through MLP_bounds), evaluated once per step; the
+//                dynamics are thread-per-trajectory register math (Dyn<S>).  The forward kernel keeps the RAW policy
+//                output o_t as the checkpoint, so that the adjoint knows u_t = bounds(o_t) and the cotangent of o_t
+//                before it starts the step's only MLP evaluation.
+template <class S>
+struct TcMode {
+  static constexpr bool POLICY = S::RHS != NM_RHS_MLP && S::Pol::NL >= 3;
+  using M = std::conditional_t<POLICY, typename S::Pol, typename S::RhsM>;
+  static constexpr int NOUT = POLICY ? S::NU : S::NX;                       // width of the MLP output
+  static constexpr int EVALS = POLICY ? 1 : Tableau<S::INTEG>::NS;          // MLP evaluations per step
+  static constexpr int CHK = POLICY ? S::NU : (Tableau<S::INTEG>::NS - 1) * S::NX;   // checkpoint floats per trajectory-step
+  static __device__ __forceinline__ const NmMlp& mlp(const NmPlan& p) { if constexpr (POLICY) return p.policy; else return p.rhs_mlp; }
+  // policy input = state and exogenous segments only (no output / preview windows on this path)
+  static constexpr bool segs_ok() {
+    int w = 0;
+    for (int i = 0; i < S::NSEG; ++i) {
+      if (S::seg_kind(i) != NM_SEG_STATE && S::seg_kind(i) != NM_SEG_EXO) return false;
+      if (S::seg_kind(i) == NM_SEG_STATE && S::seg_width(i) != S::NX) return false;
+      w += S::seg_width(i);
+    }
+    return w == M::sz(0);
+  }
+};
+
 template <class S>
 struct TcKCfg {
-  using C = tc::TcCfg<typename S::RhsM>;
+  using MD = TcMode<S>;
+  using C = tc::TcCfg<typename MD::M>;
   static constexpr int NX = S::NX, NU = S::NU;
-  static constexpr bool ELIGIBLE = S::RHS == NM_RHS_MLP && S::Pol::NL == 0 && !S::HAS_OUTPUT && S::ND == 0 && C::shape_ok() &&
-                                   C::K(0) == NX + NU && C::N(C::NL - 1) == NX;
+  static constexpr bool ELIGIBLE_RHS = S::RHS == NM_RHS_MLP && S::Pol::NL == 0 && !S::HAS_OUTPUT && S::ND == 0 && C::shape_ok() &&
+                                       C::K(0) == NX + NU && C::N(C::NL - 1) == NX;
+  static constexpr bool ELIGIBLE_POL = MD::POLICY && !S::HAS_OUTPUT && S::ND == 0 && S::ACT_EXO < 0 && NU > 0 && C::shape_ok() &&
+                                       MD::segs_ok() && C::N(C::NL - 1) == NU;
+  static constexpr bool ELIGIBLE = MD::POLICY ? ELIGIBLE_POL : ELIGIBLE_RHS;
   // shared memory of the forward kernel: weight block + barriers/slots; padded so that no more CTAs become
   // resident than tensor memory has room for (512 columns per SM)
   static constexpr int MAX_CTAS = 512 / C::FWD_COLS;
@@ -31,20 +62,40 @@ struct TcKCfg {
   static constexpr bool FITS_FWD = FWD_SMEM_RAW <= 227 * 1024;
 };
 
+// policy input of trajectory b at step t: [x | exo[e][b, t, :] ...] in segment order (reference blocks.py:32-43)
+template <class S, int K0>
+__device__ __forceinline__ void tc_policy_input(const NmPlan& p, const float* const* exo, int64_t b, int t, const float (&x)[S::NX], float (&in)[K0]) {
+  int off = 0;
+  static_for<0, S::NSEG>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    constexpr int W = S::seg_width(s);
+    if constexpr (S::seg_kind(s) == NM_SEG_STATE) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) in[off + i] = x[i];
+    } else {
+      constexpr int e = S::seg_index(s);
+      const float* __restrict__ src = exo[e] + (b * p.exo[e].steps + t) * W;
+#pragma unroll
+      for (int i = 0; i < W; ++i) in[off + i] = __ldg(src + i);
+    }
+    off += W;
+  });
+}
+
 template <class S>
 __global__ void nm_tc_prep_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, float* __restrict__ wprep) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  tc::prep_tc_fwd<typename S::RhsM>(params + plan.rhs_mlp.param_offset, wprep, gtid, gthreads);
+  tc::prep_tc_fwd<typename TcMode<S>::M>(params + TcMode<S>::mlp(plan).param_offset, wprep, gtid, gthreads);
 }
 
-// One MLP evaluation on the tile: in[K0] (registers) -> out[NX] (registers).  All 128 threads call it.
+// One MLP evaluation on the tile: in[K0] (registers) -> out[NOUT] (registers).  All 128 threads call it.
 //   `phase` is the parity of the MMA-completion mbarrier (flipped per tensor-core layer).
-template <class S>
+template <class M, int NOUT>
 __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint32_t tmem, uint32_t lane_base, uint64_t* mma_bar,
-                                               uint32_t& phase, float act_prm, const float (&in)[tc::TcCfg<typename S::RhsM>::K(0)],
-                                               float (&out)[S::NX], int tid) {
-  using M = typename S::RhsM;
+                                               uint32_t& phase, float act_prm, const float (&in)[tc::TcCfg<M>::K(0)],
+                                               float (&out)[NOUT], int tid) {
   using C = tc::TcCfg<M>;
+  static_assert(NOUT == C::N(C::NL - 1), "output width");
   constexpr int K0 = C::K(0), N0 = C::N(0), NL = C::NL;
   const uint32_t t_oph = tmem + lane_base + C::OPH, t_opl = tmem + lane_base + C::OPL, t_acc = tmem + lane_base + C::ACC;
 
@@ -75,7 +126,7 @@ __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint
     }
   }
 #pragma unroll
-  for (int i = 0; i < S::NX; ++i) out[i] = 0.f;
+  for (int i = 0; i < NOUT; ++i) out[i] = 0.f;
 
   // ---- hidden layers on the tensor cores
   static_for<1, NL - 1>([&](auto lc) {
@@ -160,7 +211,9 @@ __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint
 // forward (rollout) kernel, tensor-core variant
 template <class S>
 __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
-  using C = tc::TcCfg<typename S::RhsM>;
+  using MD = TcMode<S>;
+  using M = typename MD::M;
+  using C = tc::TcCfg<M>;
   using TK = TcKCfg<S>;
   constexpr int NX = S::NX, NU = S::NU, NUA = NU > 0 ? NU : 1, K0 = C::K(0);
   constexpr int TILE = 128, THREADS = 128;
@@ -200,9 +253,9 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
   float tsum[NT];
 #pragma unroll
   for (int q = 0; q < NT; ++q) tsum[q] = 0.f;
+  const float act_prm = MD::mlp(p).act_param;
 
   const int T = p.nsteps;
-  constexpr int NS = Tableau<S::INTEG>::NS;
   for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
     const int64_t b_raw = int64_t(tile) * TILE + tid;
     const bool valid = b_raw < args.B;
@@ -219,31 +272,50 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
       float u[NUA];
 #pragma unroll
       for (int j = 0; j < NUA; ++j) u[j] = 0.f;
-      if constexpr (NU > 0 && S::ACT_EXO >= 0) {               // open loop: the action comes from the data
-        const float* src = args.exo[S::ACT_EXO] + (b * p.exo[S::ACT_EXO].steps + t) * NU;
+      float xn[NX];
+      if constexpr (MD::POLICY) {
+        // closed loop: u_t = bounds(policy([x_t | exo_t])), x_{t+1} = dynamics(x_t, u_t) in registers
+        float in[K0], o[NUA], dnone[1] = {0.f};
+        tc_policy_input<S, K0>(p, args.exo, b, t, x, in);
+        tc_mlp_forward<M, MD::NOUT>(sm_w, tmem, lane_base, &bars[1], phase, act_prm, in, o, tid);
 #pragma unroll
-        for (int j = 0; j < NU; ++j) { u[j] = __ldg(src + j); if (valid) args.u_traj[(b * T + t) * NU + j] = u[j]; }
-      }
-      float k[NM_MAX_STAGES][NX];
-      static_for<0, NS>([&](auto sc) {
-        constexpr int St = decltype(sc)::value;
-        float in[K0], xs[NX];
-        stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
+        for (int j = 0; j < NU; ++j) u[j] = bounds_fwd<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]);
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) in[i] = xs[i];
+          for (int j = 0; j < NU; ++j) args.u_traj[(b * T + t) * NU + j] = u[j];
+          if (args.chk != nullptr) {
 #pragma unroll
-        for (int j = 0; j < NU; ++j) in[NX + j] = u[j];
-        tc_mlp_forward<S>(sm_w, tmem, lane_base, &bars[1], phase, p.rhs_mlp.act_param, in, k[St], tid);
-        if constexpr (St + 1 < NS) {
-          if (valid && args.chk != nullptr) {
-            float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) cp[i] = k[St][i];
+            for (int j = 0; j < NU; ++j) args.chk[(b * T + t) * NU + j] = o[j];
           }
         }
-      });
-      float xn[NX];
-      combine_stages<S::INTEG, NX>(p.h, x, k, xn);
+        Dyn<S>::step(p, x, u, dnone, xn);
+      } else {
+        constexpr int NS = Tableau<S::INTEG>::NS;
+        if constexpr (NU > 0 && S::ACT_EXO >= 0) {               // open loop: the action comes from the data
+          const float* src = args.exo[S::ACT_EXO] + (b * p.exo[S::ACT_EXO].steps + t) * NU;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) { u[j] = __ldg(src + j); if (valid) args.u_traj[(b * T + t) * NU + j] = u[j]; }
+        }
+        float k[NM_MAX_STAGES][NX];
+        static_for<0, NS>([&](auto sc) {
+          constexpr int St = decltype(sc)::value;
+          float in[K0], xs[NX];
+          stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) in[i] = xs[i];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) in[NX + j] = u[j];
+          tc_mlp_forward<M, MD::NOUT>(sm_w, tmem, lane_base, &bars[1], phase, act_prm, in, k[St], tid);
+          if constexpr (St + 1 < NS) {
+            if (valid && args.chk != nullptr) {
+              float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
+#pragma unroll
+              for (int i = 0; i < NX; ++i) cp[i] = k[St][i];
+            }
+          }
+        });
+        combine_stages<S::INTEG, NX>(p.h, x, k, xn);
+      }
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
       if (valid) {
@@ -308,18 +380,34 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
 #endif
 // column blocks of 16 alternate between the two threads of a trajectory; position of chunk `ci` (chunk size CH in
 // {8, 16}) among the chunks its thread owns, and how many chunks a thread can own out of NCH
-constexpr int own_idx(int ci, int CH) { return CH == 16 ? ci / 2 : (ci / 4) * 2 + (ci & 1); }
-constexpr int own_cnt(int NCH, int CH) { return CH == 16 ? (NCH + 1) / 2 : ((NCH + 3) / 4) * 2; }
+// (SOLO: one thread per trajectory owns every chunk)
+constexpr int own_idx(int ci, int CH, bool SOLO) { return SOLO ? ci : (CH == 16 ? ci / 2 : (ci / 4) * 2 + (ci & 1)); }
+constexpr int own_cnt(int NCH, int CH, bool SOLO) { return SOLO ? NCH : (CH == 16 ? (NCH + 1) / 2 : ((NCH + 3) / 4) * 2); }
 template <class S>
 struct TcBKCfg {
-  using M = typename S::RhsM;
+  using MD = TcMode<S>;
+  using M = typename MD::M;
   using C = tc::TcCfg<M>;
-  using B = tc::TcBwdCfg<M>;
+  // policy mode always runs the weight-gradient GEMMs single-pass (one evaluation per step: with the 3-product
+  // split the 48 weight-gradient MMAs per layer would outweigh everything else the step does)
+  using B = tc::TcBwdCfg<M, !MD::POLICY>;
   static constexpr bool ELIGIBLE = TcKCfg<S>::ELIGIBLE && B::FITS;
-  static constexpr int THREADS = 288;                                       // 2 owner warpgroups + the control warp
+  // Owner layout.  PAIR: two threads per trajectory (alternating 16-column blocks), one CTA per SM -- for classes whose
+  // tiles fill the SM's shared memory (c3).  SOLO: one thread per trajectory and TWO CTAs per SM when shared memory
+  // (<= 113 KB) and tensor memory (<= 256 columns) allow: the per-step phases are latency-bound and serialised by the
+  // MMA round trips, so a second independent tile per SM nearly doubles the throughput, and the per-trajectory
+  // scalar work (dynamics adjoint, loss-term gradients) is no longer duplicated across a thread pair.
+#ifdef NM_TUNE_TCSOLO
+  static constexpr bool SOLO = (NM_TUNE_TCSOLO != 0) && B::SMEM_BYTES + 2048 <= (227 * 1024) / 2 && B::COLS <= 256;
+#else
+  static constexpr bool SOLO = B::SMEM_BYTES + 2048 <= (227 * 1024) / 2 && B::COLS <= 256;
+#endif
+  static constexpr int OWNER_WARPS = SOLO ? 4 : 8;
+  static constexpr int THREADS = OWNER_WARPS * 32 + 32;                    // owners + the control warp
+  static constexpr int CTAS_PER_SM = SOLO ? 2 : 1;
   // weight-gradient accumulators live in tensor memory, whose accumulate truncates: bound the chain to ~320 accumulations
   static constexpr int MMAS_PER_WG = B::WG3 ? 48 : 16;
-  static constexpr int FLUSH = (320 / (Tableau<S::INTEG>::NS * MMAS_PER_WG)) > 1 ? 320 / (Tableau<S::INTEG>::NS * MMAS_PER_WG) : 1;
+  static constexpr int FLUSH = (320 / (MD::EVALS * MMAS_PER_WG)) > 1 ? 320 / (MD::EVALS * MMAS_PER_WG) : 1;
   static constexpr bool WG3 = B::WG3;
   static constexpr size_t SMEM_BYTES = size_t(B::SMEM_BYTES) + 1024;      // + alignment slack
   static constexpr size_t W_BYTES = size_t(B::BWD_W) * 4;
@@ -328,7 +416,7 @@ struct TcBKCfg {
 template <class S>
 __global__ void nm_tc_prep_bwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, float* __restrict__ wprep) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  tc::prep_tc_bwd<typename S::RhsM>(params + plan.rhs_mlp.param_offset, wprep, gtid, gthreads);
+  tc::prep_tc_bwd<typename TcMode<S>::M>(params + TcMode<S>::mlp(plan).param_offset, wprep, gtid, gthreads);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -336,13 +424,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <class S>
-__global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
-  using M = typename S::RhsM;
-  using C = tc::TcCfg<M>;
-  using B = tc::TcBwdCfg<M>;
+__global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
   using BK = TcBKCfg<S>;
+  using MD = typename BK::MD;
+  using M = typename BK::M;
+  using C = typename BK::C;
+  using B = typename BK::B;
+  constexpr bool POLICY = MD::POLICY, SOLO = BK::SOLO;
+  constexpr int NOW = BK::OWNER_WARPS;
   constexpr int NX = S::NX, NU = S::NU, NUA = NU > 0 ? NU : 1, K0 = C::K(0), N0 = C::N(0), NL = C::NL;
-  constexpr int TILE = 128, NS = Tableau<S::INTEG>::NS, NI = B::NI, FLUSH = BK::FLUSH;
+  constexpr int TILE = 128, NS = Tableau<S::INTEG>::NS, NEV = MD::EVALS, NI = B::NI, FLUSH = BK::FLUSH;
   constexpr int NLAST = C::N(NL - 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the swizzled tiles need a 1024-byte aligned base; the dynamic window starts right after the driver's 1 KB
@@ -373,7 +464,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
   if (tid < NM_MAX_TERMS) coef[tid] = tid < p.n_terms ? term_coef(p, tid, args.grad_scalars, args.b_total) : 0.f;
   float* gblock = args.grad_partials + size_t(blockIdx.x) * size_t(p.n_params > 0 ? p.n_params : 1);
   for (int i = tid; i < p.n_params; i += BK::THREADS) gblock[i] = 0.f;
-  float* grhs = gblock + p.rhs_mlp.param_offset;
+  float* grhs = gblock + MD::mlp(p).param_offset;
   if (tid == 0) {
     vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
     vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
@@ -381,7 +472,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
     for (int e = 0; e < NM_MAX_EXO; ++e) {
       vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
     }
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 256); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], NOW * 32); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
     mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -410,13 +501,13 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
   int my_tiles = 0;
   for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) ++my_tiles;
 
-  if (warp >= 8) {
-   if (warp == 8) {
+  if (warp >= NOW) {
+   if (warp == NOW) {
     // =============================================================== control thread: TMA producer + MMA issuer
     {
       const uint32_t sbase = smem_u32(sm);
       const uint64_t d_sw0 = tc::smem_desc_sw128(sbase);
-      const long long total_imgs = (long long)my_tiles * T * NS * NI;
+      const long long total_imgs = (long long)my_tiles * T * NEV * NI;
       long long img_issued = 0;
       uint32_t ph_ops = 0, ph_slot[2] = {0, 0};
       TCP_DECL(c_wait_ops); TCP_DECL(c_wait_slot); TCP_DECL(c_issue); TCP_DECL(c_total);
@@ -443,7 +534,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
         for (int t = T - 1; t >= 0; --t) {
           bool fresh = (step_cnt % FLUSH) == 0;         // accumulators were flushed before this step
           ++step_cnt;
-          for (int st = NS - 1; st >= 0; --st) {
+          for (int st = NEV - 1; st >= 0; --st) {
             // one wgrad GEMM: D'[n][k] (+)= sum_m DT[n][m] AT_l[k][m]
             auto wgrad = [&](auto lc, auto dtoff_c, auto dtrows_c) {
               constexpr int l = decltype(lc)::value;
@@ -549,7 +640,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
       }
 #ifdef NM_TUNE_TCPROF
       c_total = clock64() - c_begin;
-      if (blockIdx.x == 0 && tid == 256) printf("[tcprof control] total %lld  wait_ops %lld  wait_slot %lld  issue %lld  (stages %lld)\n", c_total, c_wait_ops, c_wait_slot, c_issue, (long long)my_tiles * T * NS);
+      if (blockIdx.x == 0 && tid == NOW * 32) printf("[tcprof control] total %lld  wait_ops %lld  wait_slot %lld  issue %lld  (stages %lld)\n", c_total, c_wait_ops, c_wait_slot, c_issue, (long long)my_tiles * T * NEV);
 #endif
     }
    }
@@ -558,22 +649,23 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
     // two threads per trajectory: thread (m, hf) with m = tid & 127 owns TMEM lane m and the 16-column blocks of
     // every layer whose index has parity hf (two warps per scheduler instead of one: the epilogues are
     // latency-bound); per-trajectory scalars (state, stage derivatives, co-state) are kept by both
-    const int m_ = tid & 127, hf = tid >> 7;
+    const int m_ = tid & 127, hf = SOLO ? 0 : (tid >> 7);
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t t_oph = tmem + lane_base + B::OPH, t_opl = tmem + lane_base + B::OPL, t_acc = tmem + lane_base + B::ACC;
     uint32_t ph_mma = 0, ph_wg = 0;
     bool wg_pending = false;
     TCP_DECL(o_wait_mma); TCP_DECL(o_wait_wg); TCP_DECL(o_arrive); TCP_DECL(o_flush);
     TCP_DECL(o_l0); TCP_DECL(o_fwd); TCP_DECL(o_last); TCP_DECL(o_bwd); TCP_DECL(o_l1); TCP_DECL(o_xch);
+    TCP_DECL(o_dyn); TCP_DECL(o_tu); TCP_DECL(o_pin); TCP_DECL(o_tx);
 #ifdef NM_TUNE_TCPROF
     const long long o_begin = clock64();
 #endif
     int step_cnt = 0;
-    const float act_prm = p.rhs_mlp.act_param;
+    const float act_prm = MD::mlp(p).act_param;
     const float* __restrict__ W0 = Wsm + C::first_off();
     const float* __restrict__ WL = Wsm + C::last_off();
     float* xch = reinterpret_cast<float*>(sm + B::XCH_OFF);                 // [2][128][8] partial input gradients of the pair
-    auto mine = [&](int c0) { return ((c0 >> 4) & 1) == hf; };
+    auto mine = [&](int c0) { return SOLO || ((c0 >> 4) & 1) == hf; };
     // per-thread pieces of the swizzled transposed-tile address: element (f, m) sits at
     //   block(m) * R*128 + f*128 + ((chunk ^ (f & 7)) << 4) + (m & 3)*4
     const uint32_t t_blk = uint32_t(m_ >> 5), t_chunk = uint32_t((m_ & 31) >> 2), t_in = uint32_t(m_ & 3) * 4;
@@ -674,39 +766,84 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
         }
 #pragma unroll
         for (int j = 0; j < NUA; ++j) u[j] = 0.f;
-        if constexpr (NU > 0 && S::ACT_EXO >= 0) {
+        if constexpr (!POLICY && NU > 0 && S::ACT_EXO >= 0) {
           const float* src = args.exo[S::ACT_EXO] + (b * p.exo[S::ACT_EXO].steps + t) * NU;
 #pragma unroll
           for (int j = 0; j < NU; ++j) u[j] = __ldg(src + j);
         }
         const float h = p.h;
-        float k[NM_MAX_STAGES][NX], gk[NM_MAX_STAGES][NX];
-        static_for<0, NS>([&](auto sc) {
-          constexpr int St = decltype(sc)::value;
+        float k[POLICY ? 1 : NM_MAX_STAGES][NX], gk[POLICY ? 1 : NM_MAX_STAGES][NX];
+        float pol_cot[NLAST];                                    // policy mode: cotangent of the raw policy output o_t
 #pragma unroll
-          for (int i = 0; i < NX; ++i) { gk[St][i] = 0.f; k[St][i] = 0.f; }
-          if constexpr (St + 1 < NS) {
-            const float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
+        for (int j = 0; j < NLAST; ++j) pol_cot[j] = 0.f;
+        if constexpr (POLICY) {
+          // u_t = bounds(o_t) from the checkpointed raw output; dynamics adjoint and the loss-term gradient of u_t
+          // are known before the step's MLP evaluation starts
+          float o[NUA], gu[NUA];
+          { TCP_T0();
 #pragma unroll
-            for (int i = 0; i < NX; ++i) k[St][i] = __ldg(cp + i);
+          for (int j = 0; j < NU; ++j) {
+            o[j] = __ldg(args.chk + (b * T + t) * NU + j);
+            u[j] = bounds_fwd<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]);
           }
-        });
+          Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
+          TCP_ADD(o_dyn); }
+          TCP_T0();
+          if (valid) {
+            if (pre) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) gx[i] = lam[i];
-#pragma unroll 1
-        for (int st = NS - 1; st >= 0; --st) {
-          float in[K0], xs[NX], w_cot[NX];
-          static_for<0, NS>([&](auto sc) {                       // only the tableau arithmetic is per-stage code
+              for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.G_x + b * g_row + (T + 1) * NX + t * NU + j);
+              if (tb_mask & 2) term_grad_accum_ool<NUA, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+            } else {
+              if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_U, NU, NUA>(p, vt, coef, b, t, gu); }
+              else term_grad_accum_ool<NUA, 0>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+              if (args.gu_ext != nullptr) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NU; ++j) pol_cot[j] = valid ? gu[j] * bounds_deriv<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]) : 0.f;
+          TCP_ADD(o_tu);
+          (void)k; (void)gk;
+        } else {
+          static_for<0, NS>([&](auto sc) {
             constexpr int St = decltype(sc)::value;
-            if (st == St) {
-              stage_input<S::INTEG, St, NX>(h, x, k, xs);
-              stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w_cot);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { gk[St][i] = 0.f; k[St][i] = 0.f; }
+            if constexpr (St + 1 < NS) {
+              const float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
+#pragma unroll
+              for (int i = 0; i < NX; ++i) k[St][i] = __ldg(cp + i);
             }
           });
 #pragma unroll
-          for (int i = 0; i < NX; ++i) { in[i] = xs[i]; w_cot[i] = valid ? w_cot[i] : 0.f; }
+          for (int i = 0; i < NX; ++i) gx[i] = lam[i];
+        }
+#pragma unroll 1
+        for (int st = NEV - 1; st >= 0; --st) {
+          float in[K0], w_cot[NLAST];
+          if constexpr (POLICY) {
+            TCP_T0();
+            tc_policy_input<S, K0>(p, args.exo, b, t, x, in);
 #pragma unroll
-          for (int j = 0; j < NU; ++j) in[NX + j] = u[j];
+            for (int j = 0; j < NLAST; ++j) w_cot[j] = pol_cot[j];
+            TCP_ADD(o_pin);
+          } else {
+            float xs[NX];
+            static_for<0, NS>([&](auto sc) {                       // only the tableau arithmetic is per-stage code
+              constexpr int St = decltype(sc)::value;
+              if (st == St) {
+                stage_input<S::INTEG, St, NX>(h, x, k, xs);
+                stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w_cot);
+              }
+            });
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { in[i] = xs[i]; w_cot[i] = valid ? w_cot[i] : 0.f; }
+#pragma unroll
+            for (int j = 0; j < NU; ++j) in[NX + j] = u[j];
+          }
           // the previous evaluation's last weight-gradient GEMM still reads AT_0 / DT
           if (wg_pending) { wait_wg(); wg_pending = false; }
           // ---- layer 0 (CUDA cores): a_1, its derivative, operand of layer 1, transposed tiles AT_0 / AT_1
@@ -850,7 +987,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
               constexpr int KPD = B::dkp(l - 1), CH = tc::chunk16_of(KPD), NCH = KPD / CH;
               // this thread's dZ_l columns: operand (tensor memory) first, the transposed copy only after the
               // weight-gradient GEMMs that still read DT have completed
-              float keep_hi[own_cnt(NCH, CH)][CH], keep_lo[B::WG3 ? own_cnt(NCH, CH) : 1][CH];
+              float keep_hi[own_cnt(NCH, CH, SOLO)][CH], keep_lo[B::WG3 ? own_cnt(NCH, CH, SOLO) : 1][CH];
               static_for<0, NCH>([&](auto cc) {
                 constexpr int ci = decltype(cc)::value, c0 = ci * CH;
                 if (mine(c0)) {
@@ -868,8 +1005,8 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
                     }
                     hi[i] = tc::tf32_hi(dz);
                     lo[i] = dz - hi[i];
-                    keep_hi[own_idx(ci, CH)][i] = hi[i];
-                    if constexpr (B::WG3) keep_lo[own_idx(ci, CH)][i] = lo[i];
+                    keep_hi[own_idx(ci, CH, SOLO)][i] = hi[i];
+                    if constexpr (B::WG3) keep_lo[own_idx(ci, CH, SOLO)][i] = lo[i];
                   }
                   tc::tmem_st<CH>(t_oph + c0, hi);
                   tc::tmem_st<CH>(t_opl + c0, lo);
@@ -883,7 +1020,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
                     const int n = c0 + i;
-                    if (n < Kl) tstore(B::DT_OFF, B::RD, n, keep_hi[own_idx(ci, CH)][i], B::WG3 ? keep_lo[own_idx(ci, CH)][i] : 0.f);
+                    if (n < Kl) tstore(B::DT_OFF, B::RD, n, keep_hi[own_idx(ci, CH, SOLO)][i], B::WG3 ? keep_lo[own_idx(ci, CH, SOLO)][i] : 0.f);
                   }
                 }
               });
@@ -892,7 +1029,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
               // l == 1: dZ_1, then layer 0 backward on CUDA cores
               TCP_T0();
               constexpr int CH = tc::chunk16_of(round_up(Kl, 8)), NCH = round_up(Kl, 8) / CH;
-              float keep_dz[own_cnt(NCH, CH)][CH];
+              float keep_dz[own_cnt(NCH, CH, SOLO)][CH];
               static_for<0, NCH>([&](auto cc) {
                 constexpr int ci = decltype(cc)::value, c0 = ci * CH;
                 if (mine(c0)) {
@@ -912,7 +1049,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
 #pragma unroll
                       for (int q = 0; q < K0; ++q) d_in[q] = fmaf(dz, w[q], d_in[q]);
                     }
-                    keep_dz[own_idx(ci, CH)][i] = dz;
+                    keep_dz[own_idx(ci, CH, SOLO)][i] = dz;
                   }
                   (void)dv;
                 }
@@ -925,7 +1062,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
                     const int n = c0 + i;
-                    if (n < Kl) { const float dz = keep_dz[own_idx(ci, CH)][i]; const float dh_ = tc::tf32_hi(dz); tstore(B::DT_OFF, B::RD, n, dh_, dz - dh_); }
+                    if (n < Kl) { const float dz = keep_dz[own_idx(ci, CH, SOLO)][i]; const float dh_ = tc::tf32_hi(dz); tstore(B::DT_OFF, B::RD, n, dh_, dz - dh_); }
                   }
                 }
               });
@@ -935,19 +1072,42 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
           });
           // the pair's partial input gradients meet in shared memory
           TCP_T0();
+          float gin[K0];
+          if constexpr (SOLO) {
 #pragma unroll
-          for (int q = 0; q < K0; ++q) xch[(hf * 128 + m_) * 8 + q] = d_in[q];
-          asm volatile("bar.sync %0, 64;\n" ::"r"(1 + (warp & 3)) : "memory");
-          float gxs[NX];
+            for (int q = 0; q < K0; ++q) gin[q] = d_in[q];
+          } else {
 #pragma unroll
-          for (int i = 0; i < NX; ++i) gxs[i] = xch[m_ * 8 + i] + xch[(128 + m_) * 8 + i];
-          TCP_ADD(o_xch);
-          static_for<0, NS>([&](auto sc) {
-            constexpr int St = decltype(sc)::value;
-            if (st == St) stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
-          });
+            for (int q = 0; q < K0; ++q) xch[(hf * 128 + m_) * 8 + q] = d_in[q];
+            asm volatile("bar.sync %0, 64;\n" ::"r"(1 + (warp & 3)) : "memory");
+#pragma unroll
+            for (int q = 0; q < K0; ++q) gin[q] = xch[m_ * 8 + q] + xch[(128 + m_) * 8 + q];
+          }
+          if constexpr (POLICY) {
+            // gradient of the policy input: the state segment feeds back into the co-state
+            TCP_ADD(o_xch);
+            int off = 0;
+            static_for<0, S::NSEG>([&](auto sc) {
+              constexpr int sg = decltype(sc)::value;
+              if constexpr (S::seg_kind(sg) == NM_SEG_STATE) {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) gx[i] += gin[off + i];
+              }
+              off += S::seg_width(sg);
+            });
+          } else {
+            float gxs[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) gxs[i] = gin[i];
+            TCP_ADD(o_xch);
+            static_for<0, NS>([&](auto sc) {
+              constexpr int St = decltype(sc)::value;
+              if (st == St) stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
+            });
+          }
         }
         // ---- loss-term gradient w.r.t. x_t
+        TCP_T0();
         if (valid) {
           if (pre) {
 #pragma unroll
@@ -964,6 +1124,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] : 0.f;
+        TCP_ADD(o_tx);
       }
       if (valid && hf == 0 && args.grad_x0 != nullptr) {
 #pragma unroll
@@ -976,7 +1137,7 @@ __global__ void __launch_bounds__(288, 1) nm_tc_bwd_kernel(const __grid_constant
     }
 #ifdef NM_TUNE_TCPROF
     if (blockIdx.x == 0 && tid == 0)
-      printf("[tcprof owner0] total %lld  wait_mma %lld  wait_wg %lld  arrive %lld  flush %lld | l0 %lld fwd %lld last %lld bwd %lld l1 %lld xch %lld\n", clock64() - o_begin, o_wait_mma, o_wait_wg, o_arrive, o_flush, o_l0, o_fwd, o_last, o_bwd, o_l1, o_xch);
+      printf("[tcprof owner0] total %lld  wait_mma %lld  wait_wg %lld  arrive %lld  flush %lld | l0 %lld fwd %lld last %lld bwd %lld l1 %lld xch %lld | dyn %lld terms_u %lld pol_in %lld terms_x %lld\n", clock64() - o_begin, o_wait_mma, o_wait_wg, o_arrive, o_flush, o_l0, o_fwd, o_last, o_bwd, o_l1, o_xch, o_dyn, o_tu, o_pin, o_tx);
 #endif
   }
   tc::fence_before();

@@ -303,6 +303,31 @@ def test_tensor_core_adjoint_is_deterministic():
         assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("name,B_scale", [("c2", 4096), ("c1", 4096), ("t_vdp_rk4_tanh_clamp", 4096)])
+def test_tensor_core_policy_adjoint(name, B_scale):
+    """Policy mode of the tcgen05 kernels (closed-loop MLP policy evaluated once per step, white-box dynamics in
+    registers, raw policy output as the checkpoint): the forward kernel is the 3xTF32 one at every batch size (pinned to
+    the goldens / oracle by the tests above); its adjoint runs single-pass TF32 weight-gradient GEMMs, so it is
+    compared with the exact FFMA adjoint at scale and with the oracle at a small batch."""
+    case = H.make_case(name, DEV, seed=5)
+    batch = to_dev(case.make_batch(B_scale, "cpu", 11))
+    exact = _grads_with(case, batch, "0")
+    tcore = _grads_with(case, batch, "1")
+    for k in exact["traj"]:
+        assert torch.equal(exact["traj"][k], tcore["traj"][k])           # same forward kernel
+    for i, (a, b) in enumerate(zip(tcore["grads"], exact["grads"])):
+        assert_rel(a, b, 3e-5, f"{name} B={B_scale} tensor-core vs exact adjoint, grad {i}")
+    again = _grads_with(case, batch, "1")
+    for x, y in zip(tcore["grads"], again["grads"]):
+        assert torch.equal(x, y)                                         # fixed-order accumulation
+    for B in (129, 300):          # (single-pass TF32 noise ~ 2^-12 / sqrt(#products): the dispatcher never picks it this low)
+        small_cpu = case.make_batch(B, "cpu", 12)
+        params_cpu = [p.detach().cpu().clone() for p in case.plan_params]
+        got = _grads_with(case, to_dev(small_cpu), "1")
+        ref = H.oracle_run(name, params_cpu, small_cpu)
+        compare(got, ref, f"{name} B={B} tensor-core policy adjoint vs oracle")
+
+
 def test_device_prefetcher_feeds_the_same_batches():
     from neuromancer_b200.dataset import DevicePrefetcher
     case = H.make_case("c2", DEV)
