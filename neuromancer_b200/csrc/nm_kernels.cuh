@@ -491,6 +491,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
   VarTable& vt = *reinterpret_cast<VarTable*>(pp1 + KC::FWD_PP1 + 16);
   const int tid = threadIdx.x;
   const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, NX, NU, NY);      // compiled term code (see nm_terms.cuh)
   constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   if (tid == 0) {
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
     // PenaltyLoss scoring of this thread's trajectory with the compiled term structure (its entries
     // were stored by this same thread; plain loads are coherent)
     if constexpr (S::NTERMS > 0) {
-      if (fused && valid) score_traj_s<S>(p, vt, b, tsum);
+      if (fused && valid) score_traj_s<S>(p, vtc, b, tsum);
     }
   }
 
@@ -681,6 +682,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
   VarTable& vt = *reinterpret_cast<VarTable*>(coef + 48);
   const int tid = threadIdx.x;
   const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, NX, NU, NY);      // compiled term code (see nm_terms.cuh)
   const int T = p.nsteps;
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   const bool pre = !fused && args.G_x != nullptr;
@@ -752,7 +754,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
         for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
         if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
       } else {
-        if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, T, lam); }
+        if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, T, lam); }
         else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
         if (args.gx_ext != nullptr) {
 #pragma unroll
@@ -890,7 +892,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
           if constexpr (NY > 0) { if (tb_mask & 4) term_grad_accum_ool<NYA, 2>(p, vt, coef, b, NM_VAR_Y, t, NY, gy); }
         } else {
           if constexpr (NU > 0) {
-            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_U, NU, NUA>(p, vt, coef, b, t, gu); }
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_U, NU, NUA>(p, vtc, coef, b, t, gu); }
             else term_grad_accum_ool<NUA, 0>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
             if (args.gu_ext != nullptr) {
 #pragma unroll
@@ -898,7 +900,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             }
           }
           if constexpr (NY > 0) {
-            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_Y, NY, NYA>(p, vt, coef, b, t, gy); }
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_Y, NY, NYA>(p, vtc, coef, b, t, gy); }
             else term_grad_accum_ool<NYA, 0>(p, vt, coef, b, NM_VAR_Y, t, NY, gy);
             if (args.gy_ext != nullptr) {
 #pragma unroll
@@ -952,7 +954,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
             if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
           } else {
-            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, t, gx); }
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, t, gx); }
             else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
             if (args.gx_ext != nullptr) {
 #pragma unroll

@@ -82,6 +82,20 @@ __device__ __forceinline__ void tc_policy_input(const NmPlan& p, const float* co
   });
 }
 
+// overwrite the state segment(s) of a policy input whose exogenous entries were fetched one step ahead
+template <class S, int K0>
+__device__ __forceinline__ void tc_policy_state(const float (&x)[S::NX], float (&in)[K0]) {
+  int off = 0;
+  static_for<0, S::NSEG>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    if constexpr (S::seg_kind(s) == NM_SEG_STATE) {
+#pragma unroll
+      for (int i = 0; i < S::seg_width(s); ++i) in[off + i] = x[i];
+    }
+    off += S::seg_width(s);
+  });
+}
+
 template <class S>
 __global__ void nm_tc_prep_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, float* __restrict__ wprep) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -209,8 +223,14 @@ __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint
 
 // ================================================================================================
 // forward (rollout) kernel, tensor-core variant
+// as many resident CTAs as tensor memory allows (<= 4: 128 registers per thread -- measured on c2: forward 0.28 -> 0.23 ms)
+#ifdef NM_TUNE_TCMINB
+template <class S> constexpr int tc_fwd_minb() { return NM_TUNE_TCMINB; }
+#else
+template <class S> constexpr int tc_fwd_minb() { return TcKCfg<S>::MAX_CTAS < 4 ? TcKCfg<S>::MAX_CTAS : 4; }
+#endif
 template <class S>
-__global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
+__global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
   using MD = TcMode<S>;
   using M = typename MD::M;
   using C = tc::TcCfg<M>;
@@ -225,6 +245,7 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
   double* red = reinterpret_cast<double*>(smem);                                      // end-of-kernel reduction scratch (weights dead)
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, 0);
   constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   if (tid == 0) {
@@ -267,6 +288,8 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
 #pragma unroll
       for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1)) * NX + i] = x[i];
     }
+    float in_pre[MD::POLICY ? K0 : 1];
+    if constexpr (MD::POLICY) tc_policy_input<S, K0>(p, args.exo, b, 0, x, in_pre);
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       float u[NUA];
@@ -276,7 +299,10 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
       if constexpr (MD::POLICY) {
         // closed loop: u_t = bounds(policy([x_t | exo_t])), x_{t+1} = dynamics(x_t, u_t) in registers
         float in[K0], o[NUA], dnone[1] = {0.f};
-        tc_policy_input<S, K0>(p, args.exo, b, t, x, in);
+#pragma unroll
+        for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
+        tc_policy_state<S, K0>(x, in);
+        if (t + 1 < T) tc_policy_input<S, K0>(p, args.exo, b, t + 1, x, in_pre);   // exogenous inputs one step ahead
         tc_mlp_forward<M, MD::NOUT>(sm_w, tmem, lane_base, &bars[1], phase, act_prm, in, o, tid);
 #pragma unroll
         for (int j = 0; j < NU; ++j) u[j] = bounds_fwd<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]);
@@ -324,7 +350,7 @@ __global__ void __launch_bounds__(128, 1) nm_tc_fwd_kernel(const __grid_constant
       }
     }
     if constexpr (S::NTERMS > 0) {
-      if (fused && valid) score_traj_s<S>(p, vt, b, tsum);
+      if (fused && valid) score_traj_s<S>(p, vtc, b, tsum);
     }
   }
 
@@ -404,7 +430,11 @@ struct TcBKCfg {
 #endif
   static constexpr int OWNER_WARPS = SOLO ? 4 : 8;
   static constexpr int THREADS = OWNER_WARPS * 32 + 32;                    // owners + the control warp
+#ifdef NM_TUNE_TCPAIR2
+  static constexpr int CTAS_PER_SM = (SOLO || (NM_TUNE_TCPAIR2 != 0 && B::SMEM_BYTES + 2048 <= (227 * 1024) / 2 && B::COLS <= 256)) ? 2 : 1;
+#else
   static constexpr int CTAS_PER_SM = SOLO ? 2 : 1;
+#endif
   // weight-gradient accumulators live in tensor memory, whose accumulate truncates: bound the chain to ~320 accumulations
   static constexpr int MMAS_PER_WG = B::WG3 ? 48 : 16;
   static constexpr int FLUSH = (320 / (MD::EVALS * MMAS_PER_WG)) > 1 ? 320 / (MD::EVALS * MMAS_PER_WG) : 1;
@@ -448,6 +478,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
   VarTable& vt = *reinterpret_cast<VarTable*>(bars + 20);
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, 0);
   const int T = p.nsteps;
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   const bool pre = !fused && args.G_x != nullptr;
@@ -735,13 +766,20 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
       float lam[NX], x_pre[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) { lam[i] = 0.f; x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + (T - 1)) * NX + i); }
+      // policy mode: the raw policy output (checkpoint) and the exogenous policy inputs are fetched one step ahead too
+      float o_pre[POLICY ? NUA : 1], in_pre[POLICY ? K0 : 1];
+      if constexpr (POLICY) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + (T - 1)) * NU + j);
+        tc_policy_input<S, K0>(p, args.exo, b, T - 1, x_pre, in_pre);
+      }
       if (valid) {
         if (pre) {
 #pragma unroll
           for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
           if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
         } else {
-          if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, T, lam); }
+          if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, T, lam); }
           else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
           if (args.gx_ext != nullptr) {
 #pragma unroll
@@ -757,12 +795,25 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           { TCP_T0(); flush(); TCP_ADD(o_flush); }
         }
         ++step_cnt;
-        float x[NX], u[NUA], gx[NX];
+        float x[NX], u[NUA], gx[NX], gtx[NX];
+        float o_cur[POLICY ? NUA : 1], in_cur[POLICY ? K0 : 1];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = x_pre[i];
+        for (int i = 0; i < NX; ++i) { x[i] = x_pre[i]; gtx[i] = 0.f; }
+        if constexpr (POLICY) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j) o_cur[j] = o_pre[j];
+#pragma unroll
+          for (int q = 0; q < K0; ++q) in_cur[q] = in_pre[q];
+          tc_policy_state<S, K0>(x, in_cur);
+        }
         if (t > 0) {
 #pragma unroll
           for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
+          if constexpr (POLICY) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + t - 1) * NU + j);
+            tc_policy_input<S, K0>(p, args.exo, b, t - 1, x, in_pre);     // (state entries are placeholders)
+          }
         }
 #pragma unroll
         for (int j = 0; j < NUA; ++j) u[j] = 0.f;
@@ -776,14 +827,14 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
         float pol_cot[NLAST];                                    // policy mode: cotangent of the raw policy output o_t
 #pragma unroll
         for (int j = 0; j < NLAST; ++j) pol_cot[j] = 0.f;
-        if constexpr (POLICY) {
-          // u_t = bounds(o_t) from the checkpointed raw output; dynamics adjoint and the loss-term gradient of u_t
-          // are known before the step's MLP evaluation starts
+        // policy mode: dynamics adjoint and the loss-term gradient of u_t (-> co-state part gx and the cotangent of the raw
+        // policy output).  Needs nothing from the step's MLP evaluation: runs while the first MMA batch is in flight.
+        auto policy_dyn = [&](auto) {                           // generic: only instantiated in policy mode
           float o[NUA], gu[NUA];
           { TCP_T0();
 #pragma unroll
           for (int j = 0; j < NU; ++j) {
-            o[j] = __ldg(args.chk + (b * T + t) * NU + j);
+            o[j] = o_cur[j];
             u[j] = bounds_fwd<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]);
           }
           Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
@@ -795,7 +846,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
               for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.G_x + b * g_row + (T + 1) * NX + t * NU + j);
               if (tb_mask & 2) term_grad_accum_ool<NUA, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
             } else {
-              if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_U, NU, NUA>(p, vt, coef, b, t, gu); }
+              if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_U, NU, NUA>(p, vtc, coef, b, t, gu); }
               else term_grad_accum_ool<NUA, 0>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
               if (args.gu_ext != nullptr) {
 #pragma unroll
@@ -806,6 +857,8 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
 #pragma unroll
           for (int j = 0; j < NU; ++j) pol_cot[j] = valid ? gu[j] * bounds_deriv<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]) : 0.f;
           TCP_ADD(o_tu);
+        };
+        if constexpr (POLICY) {
           (void)k; (void)gk;
         } else {
           static_for<0, NS>([&](auto sc) {
@@ -826,9 +879,10 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           float in[K0], w_cot[NLAST];
           if constexpr (POLICY) {
             TCP_T0();
-            tc_policy_input<S, K0>(p, args.exo, b, t, x, in);
 #pragma unroll
-            for (int j = 0; j < NLAST; ++j) w_cot[j] = pol_cot[j];
+            for (int q = 0; q < K0; ++q) in[q] = in_cur[q];
+#pragma unroll
+            for (int j = 0; j < NLAST; ++j) w_cot[j] = 0.f;
             TCP_ADD(o_pin);
           } else {
             float xs[NX];
@@ -893,6 +947,33 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           static_for<1, NL - 1>([&](auto lc) {
             constexpr int l = decltype(lc)::value;
             constexpr int Nl = C::N(l);
+            if constexpr (l == 1) {
+              // loss-term gradient w.r.t. x_t: depends on the stored trajectories only -- evaluated here, while the
+              // step's first MMA batch is in flight
+              if constexpr (POLICY) {
+                policy_dyn(0);
+#pragma unroll
+                for (int j = 0; j < NLAST; ++j) w_cot[j] = pol_cot[j];
+              }
+              if (st == NEV - 1) {
+                TCP_T0();
+            if (valid) {
+              if (pre) {
+    #pragma unroll
+                for (int i = 0; i < NX; ++i) gtx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
+                if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gtx);
+              } else {
+                if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, t, gtx); }
+                else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gtx);
+                if (args.gx_ext != nullptr) {
+    #pragma unroll
+                  for (int i = 0; i < NX; ++i) gtx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+                }
+              }
+            }
+                TCP_ADD(o_tx);
+              }
+            }
             { TCP_T0(); mbar_wait(&bars[2], ph_mma); ph_mma ^= 1; TCP_ADD(o_wait_mma); }
             tc::fence_after();
             if constexpr (l < NL - 2) {
@@ -1106,25 +1187,9 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
             });
           }
         }
-        // ---- loss-term gradient w.r.t. x_t
-        TCP_T0();
-        if (valid) {
-          if (pre) {
+        // ---- co-state of step t: dynamics / policy part + the loss-term gradient computed in the MMA wait window
 #pragma unroll
-            for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
-            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
-          } else {
-            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vt, coef, b, t, gx); }
-            else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
-            if (args.gx_ext != nullptr) {
-#pragma unroll
-              for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] : 0.f;
-        TCP_ADD(o_tx);
+        for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] + gtx[i] : 0.f;
       }
       if (valid && hf == 0 && args.grad_x0 != nullptr) {
 #pragma unroll

@@ -16,6 +16,22 @@ struct VarTable {                       // trajectory variables a term atom can 
   int D[NM_VAR_EXO0 + NM_MAX_EXO];      // last dim
 };
 
+// The same table by value, for the compile-time-structured term code: with constant indices the struct is scalarised
+// and every entry becomes a kernel-parameter (constant bank) operand or an immediate -- no shared-memory pointer
+// loads in front of the trajectory loads (those chains were 11 % of the adjoint's stall samples on c2).
+template <class Args>
+__device__ __forceinline__ VarTable make_vartable_regs(const NmPlan& p, const Args& a, int nx, int nu, int ny) {
+  VarTable vt;
+  vt.base[NM_VAR_X] = a.x_traj; vt.T[NM_VAR_X] = p.nsteps + 1; vt.D[NM_VAR_X] = nx;
+  vt.base[NM_VAR_U] = a.u_traj; vt.T[NM_VAR_U] = p.nsteps; vt.D[NM_VAR_U] = nu;
+  vt.base[NM_VAR_Y] = a.y_traj; vt.T[NM_VAR_Y] = p.nsteps; vt.D[NM_VAR_Y] = ny;
+#pragma unroll
+  for (int e = 0; e < NM_MAX_EXO; ++e) {
+    vt.base[NM_VAR_EXO0 + e] = a.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+  }
+  return vt;
+}
+
 __device__ __forceinline__ float atom_value(const NmAtom& a, const VarTable& vt, int64_t b, int te, int de) {
   if (a.var < 0) return a.offset;
   const int t = a.t_start + (a.t_len == 1 ? 0 : te);
@@ -263,17 +279,20 @@ __device__ __forceinline__ void score_traj_s(const NmPlan& p, const VarTable& vt
   static_for<0, S::NTERMS>([&](auto kc) {
     constexpr int K = decltype(kc)::value;
     const NmTerm& tm = p.terms[K];
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     const int tl = tm.t_len, dl = tm.d_len;
     int te = 0;
-    for (; te + 1 < tl; te += 2) {                      // two independent chains: loads overlap
+    for (; te + 3 < tl; te += 4) {                      // four independent chains: the (L2-latency) loads overlap
       for (int de = 0; de < dl; ++de) {
         s0 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
         s1 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 1, de));
+        s2 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 2, de));
+        s3 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 3, de));
       }
     }
-    if (te < tl)
+    for (; te < tl; ++te)
       for (int de = 0; de < dl; ++de) s0 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+    s0 += s2; s1 += s3;
     tsum[K] += s0 + s1;
   });
 }
@@ -290,31 +309,48 @@ __device__ __forceinline__ void term_grad_s(const NmPlan& p, const VarTable& vt,
       if constexpr (A::VAR == VAR) {
         const NmTerm& tm = p.terms[K];
         const NmAtom& at = pick_atom<W>(tm);
-        int te_lo, te_hi;
-        if constexpr (A::TB) {
-          if (t_idx != at.t_start) return;
-          te_lo = 0; te_hi = tm.t_len;
-        } else {
-          const int te = t_idx - at.t_start;
-          if (te < 0 || te >= at.t_len) return;
-          te_lo = te; te_hi = te + 1;
-        }
         constexpr float side_sign = (W < 2) ? (S::t_cmp(K) == NM_CMP_GT ? -1.f : 1.f) : (S::t_cmp(K) == NM_CMP_GT ? 1.f : -1.f);
         constexpr int OP = S::t_op(K, W / 2);
         const float ck = coef[K] * at.scale * side_sign * ((OP == NM_OP_SUB && (W & 1)) ? -1.f : 1.f);
+        if constexpr (!A::TB && !A::DB) {
+          // one element per (t_idx, d): branch-free -- the element index is clamped into the term's range and the
+          // contribution selected afterwards, so the loads of all terms are independent and issue back to back
+          const int te = t_idx - at.t_start;
+          const bool act_t = te >= 0 && te < at.t_len;
+          const int te_c = act_t ? te : 0;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          int de_lo, de_hi;
-          if constexpr (A::DB) { if (d != at.d_start) continue; de_lo = 0; de_hi = tm.d_len; }
-          else { const int de = d - at.d_start; if (de < 0 || de >= at.d_len) continue; de_lo = de; de_hi = de + 1; }
-          float acc = 0.f;
-          for (int te = te_lo; te < te_hi; ++te)
-            for (int de = de_lo; de < de_hi; ++de) {
-              float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
-              if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te, de);
-              acc += dv;
-            }
-          g[d] = fmaf(ck, acc, g[d]);
+          for (int d = 0; d < DIM; ++d) {
+            const int de = d - at.d_start;
+            const bool in_d = de >= 0 && de < at.d_len;
+            const int de_c = in_d ? de : 0;
+            float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te_c, de_c));
+            if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te_c, de_c);
+            g[d] = (act_t && in_d) ? fmaf(ck, dv, g[d]) : g[d];
+          }
+        } else {
+          int te_lo, te_hi;
+          if constexpr (A::TB) {
+            if (t_idx != at.t_start) return;
+            te_lo = 0; te_hi = tm.t_len;
+          } else {
+            const int te = t_idx - at.t_start;
+            if (te < 0 || te >= at.t_len) return;
+            te_lo = te; te_hi = te + 1;
+          }
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            int de_lo, de_hi;
+            if constexpr (A::DB) { if (d != at.d_start) continue; de_lo = 0; de_hi = tm.d_len; }
+            else { const int de = d - at.d_start; if (de < 0 || de >= at.d_len) continue; de_lo = de; de_hi = de + 1; }
+            float acc = 0.f;
+            for (int te = te_lo; te < te_hi; ++te)
+              for (int de = de_lo; de < de_hi; ++de) {
+                float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+                if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te, de);
+                acc += dv;
+              }
+            g[d] = fmaf(ck, acc, g[d]);
+          }
         }
       }
     });
