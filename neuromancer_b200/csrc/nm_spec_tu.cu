@@ -36,13 +36,25 @@ constexpr int shape_max_width() {
   for (int l = 0; l <= NM_SPEC_NAME::RhsM::NL; ++l) m = cmax(m, NM_SPEC_NAME::RhsM::sz(l));
   return m;
 }
+constexpr int shape_max_out() {                     // widest layer OUTPUT (the fan-in of the first layer does not count)
+  int m = 1;
+  for (int l = 1; l <= NM_SPEC_NAME::Pol::NL; ++l) m = cmax(m, NM_SPEC_NAME::Pol::sz(l));
+  for (int l = 1; l <= NM_SPEC_NAME::RhsM::NL; ++l) m = cmax(m, NM_SPEC_NAME::RhsM::sz(l));
+  return m;
+}
 #ifdef NM_TUNE_THREADS
 constexpr int kThreadsF = NM_TUNE_THREADS, kThreadsB = NM_TUNE_THREADS;
 #else
 // adjoint kernel: 256 threads for wide layers, and whenever the keep-all activation buffers leave room for only
 // ONE resident CTA per SM (measured on c3: 8 warps/SM instead of 4 -> adjoint 57 ms instead of 69 ms)
 constexpr bool kOneCtaPerSm = KCfg<Tiled<NM_SPEC_NAME, 128, 128, true>>::BWD_SMEM_BYTES > 113 * 1024 + 512;
-constexpr int kThreadsB = (shape_max_width() >= 96 || kOneCtaPerSm) ? 256 : 128;
+#ifdef NM_TUNE_THREADS_BWD
+constexpr int kThreadsB = NM_TUNE_THREADS_BWD;
+#else
+// 128-wide layers with weights streamed from L2 (c5): 512 threads hide the L2 latency of the weight rows (measured:
+// adjoint 95 -> 76 ms)
+constexpr int kThreadsB = shape_max_out() >= 128 ? 512 : ((shape_max_width() >= 96 || kOneCtaPerSm) ? 256 : 128);
+#endif
 #ifdef NM_TUNE_THREADS_FWD
 constexpr int kThreadsF = NM_TUNE_THREADS_FWD;
 #else
