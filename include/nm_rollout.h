@@ -225,9 +225,12 @@ int nm_struct_sizes(int* out, int cap);
 int nm_load_plugin(const char* path);
 
 /* Size in bytes of the optional checkpoint buffer for a batch of B trajectories (0 when the plan has none).
- * The emitted x trajectory is always the per-step checkpoint of the adjoint; plans with an MLP right-hand
- * side can additionally keep the stage derivatives k_0..k_{NS-2} of every integrator step
- * ([B, nsteps, (NS-1)*nx] fp32) so that the adjoint skips its first recompute pass. */
+ * The emitted x trajectory is always the per-step checkpoint of the adjoint.  Additionally:
+ *   - plans with an MLP right-hand side keep the stage derivatives k_0..k_{NS-2} of every integrator step
+ *     ([B, nsteps, (NS-1)*nx] fp32) so that the adjoint skips its first recompute pass;
+ *   - closed-loop plans whose policy runs on the tensor-core kernels keep the raw policy output o_t (before
+ *     MLP_bounds) of every step ([B, nsteps, nu] fp32).
+ * The buffer is filled by nm_rollout_forward and read by nm_rollout_backward; NULL is always accepted. */
 int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes);
 
 /* Device workspace sizes in bytes for a batch of B trajectories. */
