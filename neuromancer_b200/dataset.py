@@ -37,9 +37,19 @@ class DevicePrefetcher:
     The prefetcher keeps the order of batches and makes the compute stream wait for the copy it consumes, so
     results are unchanged."""
 
+    # One copy stream per device, shared by every prefetcher: the caching allocator keeps a block pool PER STREAM, so a
+    # fresh stream per epoch would start from an empty pool and pay cudaMalloc (measured: 2-4 ms/step instead of 1.05
+    # for the first ~40 steps of every new prefetcher).
+    _copy_streams = {}
+
     def __init__(self, batches, device="cuda", depth=2):
         self.batches, self.device = batches, torch.device(device)
-        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.stream = None
+        if self.device.type == "cuda":
+            key = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            if key not in DevicePrefetcher._copy_streams:
+                DevicePrefetcher._copy_streams[key] = torch.cuda.Stream(self.device)
+            self.stream = DevicePrefetcher._copy_streams[key]
         self.depth = max(int(depth), 1)
 
     def _issue(self, batch):
