@@ -428,7 +428,7 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   nm_loss_finalize_kernel<<<1, 256, 0, c.stream>>>(*plan, partials, pgrid, B, scalars);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
-  g_launches = (!fused && plan->n_terms > 0) ? 4 : 3;   // weight prep + rollout [+ term scoring] + loss finalise
+  g_launches = ((!fused && plan->n_terms > 0) ? 4 : 3) + c.extra_launches;   // weight prep + rollout [+ term scoring] + loss finalise
   return NM_OK;
 }
 
@@ -472,6 +472,7 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
   }
   rc = e->backward(plan, &c);
   if (rc != NM_OK) return rc;
+  extra += c.extra_launches;
   g_launches = 2 + extra;
   if (plan->n_params > 0) {
     const int blocks = int((plan->n_params + 31) / 32);

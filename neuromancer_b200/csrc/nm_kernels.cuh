@@ -22,6 +22,22 @@
 namespace nm {
 
 // ------------------------------------------------------------------------------------------------
+// Exogenous first-layer hoist (policy MLPs whose inputs are [state / output segments | exogenous segments]):
+//   z_1 = b + W[:, :KS] s_t + W[:, KS:] e_t     where e_t does not depend on the rollout,
+// so  E[b, t, :] = b + W[:, KS:] e[b, t, :]  is ONE plain GEMM over all (b, t) rows before the horizon loop
+// (nm_exo_gemm_fwd_kernel), the loop contracts the first layer over its KS leading inputs only and adds E as a
+// per-step pre-activation, the adjoint stores dZ_1[b, t, :], and  dW[:, KS:] = sum_{b,t} dZ_1 (x) e  is one GEMM
+// after it (nm_exo_gemm_bwd_kernel).  C4: 193 -> 1 contracted inputs per step.
+// HoistedMlp<M, KS> is M with its first layer restricted to the KS leading inputs; KW0 keeps the fan-in of the
+// parameter layout (row stride of W_0, offsets of the following layers).
+template <class M, int KS>
+struct HoistedMlp : M {
+  static constexpr int sz(int i) { return i == 0 ? KS : M::sz(i); }
+  static constexpr int KW0 = M::sz(0);
+};
+template <class M, class = void> struct KW0Of { static constexpr int value = M::sz(0); };
+template <class M> struct KW0Of<M, std::void_t<decltype(M::KW0)>> { static constexpr int value = M::KW0; };
+
 // Static description of one MLP's staging buffers.
 //   GW0 = number of leading input features whose gradient is needed (state / output segments).
 template <class M, int TILE, int THREADS, int GW0>
@@ -30,6 +46,7 @@ struct MlpCfg {
   static constexpr int LD = TILE + 4;
   static constexpr int K(int l) { return M::sz(l); }
   static constexpr int N(int l) { return M::sz(l + 1); }
+  static constexpr int KW(int l) { return l == 0 ? KW0Of<M>::value : M::sz(l); }   // fan-in in the parameter layout
   static constexpr int gw(int l) { return l == 0 ? GW0 : K(l); }       // width of the data gradient of layer l
   // permuted weight block (floats): per layer  Wf[K][NPf] , bias[NPf] ; then per layer Wb[N][NPb]
   static constexpr int npf(int l) { return g_np(N(l)); }
@@ -40,7 +57,7 @@ struct MlpCfg {
   static constexpr int wb_off(int l) { int o = FWD_W; for (int i = 0; i < l; ++i) o += N(i) * npb(i); return o; }
   static constexpr int ALL_W = wb_off(NL);
   // number of parameters of layer l in the reference's flat order (W [N][K] then b [N])
-  static constexpr int p_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += N(i) * K(i) + (M::BIAS ? N(i) : 0); return o; }
+  static constexpr int p_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += N(i) * KW(i) + (M::BIAS ? N(i) : 0); return o; }
   static constexpr int N_PARAMS = p_off(NL);
   static constexpr int max_width() { int m = 1; for (int l = 0; l <= NL; ++l) m = cmax(m, M::sz(l)); return m; }
   // forward-only activation buffers: layer inputs alternate between two buffers
@@ -84,12 +101,32 @@ struct KCfg {
     for (int i = 0; i < S::NSEG; ++i) { off += S::seg_width(i); if (S::seg_kind(i) == NM_SEG_STATE || S::seg_kind(i) == NM_SEG_OUTPUT) gw = off; }
     return gw;
   }
-  using PolCfg = std::conditional_t<HAS_POL, MlpCfg<typename S::Pol, TILE, THREADS, pol_gw0()>, NoMlpCfg<TILE, THREADS>>;
+  // exogenous first-layer hoist: every exogenous segment follows the last state / output segment, no preview windows
+  static constexpr bool hoist_ok() {
+    if (!HAS_POL || S::Pol::NL < 2 || S::Pol::sz(1) % 4 != 0 || S::Pol::sz(1) > 128) return false;
+    int ks = 0, seen_exo = 0;
+    for (int i = 0; i < S::NSEG; ++i) {
+      if (S::seg_kind(i) == NM_SEG_PREVIEW) return false;
+      if (S::seg_kind(i) == NM_SEG_EXO) { seen_exo = 1; if (S::seg_width(i) % 4 != 0) return false; }
+      else { if (seen_exo) return false; ks += S::seg_width(i); }
+    }
+    return seen_exo && ks >= 1 && ks == pol_gw0();
+  }
+  static constexpr bool HOIST = S::HOIST && hoist_ok();
+  static constexpr int KS = pol_gw0();                                     // contracted fan-in of the first layer when hoisted
+  static constexpr int KE = HAS_POL ? S::Pol::sz(0) - KS : 0;              // hoisted (exogenous) fan-in
+  static constexpr int N0 = HAS_POL ? S::Pol::sz(1) : 1;
+  using PolM = std::conditional_t<HOIST, HoistedMlp<typename S::Pol, pol_gw0()>, typename S::Pol>;
+  using PolCfg = std::conditional_t<HAS_POL, MlpCfg<PolM, TILE, THREADS, pol_gw0()>, NoMlpCfg<TILE, THREADS>>;
+  // prepared exogenous block of the hoist GEMMs: rows [KE exogenous inputs | bias][NPf] in the forward image layout
+  static constexpr int EXO_NP = g_np(N0);
+  static constexpr int EXO_W_FLOATS = HOIST ? round_up((KE + 1) * EXO_NP, 4) : 0;
   using RhsCfg = std::conditional_t<HAS_RHS_MLP, MlpCfg<typename S::RhsM, TILE, THREADS, NX + NU>, NoMlpCfg<TILE, THREADS>>;
   static constexpr int W_FLOATS_FWD = round_up(PolCfg::FWD_W, 4) + round_up(RhsCfg::FWD_W, 4);
   static constexpr int RHS_WF_OFF = round_up(PolCfg::FWD_W, 4);                     // forward-kernel smem offset
   static constexpr int W_FLOATS_ALL = round_up(PolCfg::ALL_W, 4) + round_up(RhsCfg::ALL_W, 4);
   static constexpr int POL_W_OFF = 0, RHS_W_OFF = round_up(PolCfg::ALL_W, 4);       // in the prepared global block
+  static constexpr int EXO_W_OFF = W_FLOATS_ALL;                                     // (hoist) after the staged part
   // forward kernel shared memory (floats)
   static constexpr int FWD_PP0 = cmax(cmax(PolCfg::pp_rows(0), RhsCfg::pp_rows(0)), 4) * LD;   // >= 256 floats: reused by the loss reduction
   static constexpr int FWD_PP1 = cmax(PolCfg::pp_rows(1), RhsCfg::pp_rows(1)) * LD;
@@ -113,6 +150,7 @@ struct FwdArgs {
   double* term_partials;            // [grid][NM_MAX_TERMS], written when fused_terms
   int fused_terms;                  // the plan's terms match the compiled term structure of S
   int64_t B; int num_tiles;
+  const float* pre;                 // (hoist) E[B][T][N0] = bias + exogenous part of the first layer
 };
 struct BwdArgs {
   const float* params; const float* wprep;
@@ -127,6 +165,8 @@ struct BwdArgs {
   float* grad_x0;
   int fused_terms;                  // evaluate term gradients with the compiled term structure of S
   int64_t B; int64_t b_total; int num_tiles;
+  const float* pre;                 // (hoist) E[B][T][N0]
+  float* dz1;                       // (hoist) dZ_1[B][T][N0], may alias `pre` (each entry is read before it is written)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -135,16 +175,16 @@ template <class MC>
 __device__ void prep_mlp(const float* __restrict__ params, float* __restrict__ dst, bool has_bias, int gtid, int gthreads) {
   static_for<0, MC::NL>([&](auto lc) {
     constexpr int l = decltype(lc)::value;
-    constexpr int K = MC::K(l), N = MC::N(l), NPF = MC::npf(l), GW = MC::gw(l), NPB = MC::npb(l);
+    constexpr int K = MC::K(l), KW = MC::KW(l), N = MC::N(l), NPF = MC::npf(l), GW = MC::gw(l), NPB = MC::npb(l);
     const float* __restrict__ Wg = params + MC::p_off(l);
-    const float* __restrict__ bg = Wg + N * K;
+    const float* __restrict__ bg = Wg + N * KW;
     float* __restrict__ wf = dst + MC::wf_off(l);
     for (int idx = gtid; idx < (K + 1) * NPF; idx += gthreads) {
       const int c = idx / NPF, col = idx % NPF;
       const int ng = col / g_tn(N), j = col % g_tn(N);
       const int n = ng + g_ng(N) * j;
       float v = 0.f;
-      if (ng < g_ng(N) && n < N) v = c < K ? Wg[n * K + c] : (has_bias ? bg[n] : 0.f);
+      if (ng < g_ng(N) && n < N) v = c < K ? Wg[n * KW + c] : (has_bias ? bg[n] : 0.f);
       wf[idx] = v;
     }
     if constexpr (GW > 0) {
@@ -153,7 +193,7 @@ __device__ void prep_mlp(const float* __restrict__ params, float* __restrict__ d
         const int n = idx / NPB, col = idx % NPB;
         const int kg = col / g_tn(GW), j = col % g_tn(GW);
         const int k = kg + g_ng(GW) * j;
-        wb[idx] = (kg < g_ng(GW) && k < GW) ? Wg[n * K + k] : 0.f;
+        wb[idx] = (kg < g_ng(GW) && k < GW) ? Wg[n * KW + k] : 0.f;
       }
     }
   });
@@ -167,17 +207,43 @@ __global__ void nm_prep_kernel(const __grid_constant__ NmPlan plan, const float*
     prep_mlp<typename KC::PolCfg>(params + plan.policy.param_offset, wprep + KC::POL_W_OFF, plan.policy.has_bias, gtid, gthreads);
   if constexpr (KC::HAS_RHS_MLP)
     prep_mlp<typename KC::RhsCfg>(params + plan.rhs_mlp.param_offset, wprep + KC::RHS_W_OFF, plan.rhs_mlp.has_bias, gtid, gthreads);
+  if constexpr (KC::HOIST) {
+    // exogenous rows of the first layer (+ its bias as the last row) in the forward image layout of the hoist GEMMs
+    constexpr int N = KC::N0, NP = KC::EXO_NP, KW = S::Pol::sz(0), KS = KC::KS, KE = KC::KE;
+    const float* __restrict__ Wg = params + plan.policy.param_offset;
+    const float* __restrict__ bg = Wg + N * KW;
+    float* __restrict__ we = wprep + KC::EXO_W_OFF;
+    for (int idx = gtid; idx < (KE + 1) * NP; idx += gthreads) {
+      const int c = idx / NP, col = idx % NP;
+      const int ng = col / g_tn(N), j = col % g_tn(N);
+      const int n = ng + g_ng(N) * j;
+      float v = 0.f;
+      if (ng < g_ng(N) && n < N) v = c < KE ? Wg[n * KW + KS + c] : (plan.policy.has_bias ? bg[n] : 0.f);
+      we[idx] = v;
+    }
+  }
 }
+
+// hoisted first-layer pre-activation of the tile's trajectories at step t:  E[(b * T + t) * N0 + n]   (b clamped to B-1)
+struct PreAct {
+  const float* base; int64_t b0, B; int T, t;
+  __device__ __forceinline__ const float* row(int traj, int n0) const {
+    const int64_t b = b0 + traj < B ? b0 + traj : B - 1;
+    return base + (b * T + t) * int64_t(n0);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // MLP forward on the tile.  Inputs a_0 must be in place and visible (caller synchronised).
+//   HOIST        : layer 0 contracts over its leading inputs only; `pre` supplies bias + exogenous part (see HoistedMlp)
 //   KEEP = false : layer inputs ping-pong between pp0/pp1; raw output of the last layer is left in
 //                  the buffer of parity NL.
 //   KEEP = true  : a_l kept at keep + a_off(l) (and act' at keep + d_off(l)); raw output -> out_raw.
 // Ends with a __syncthreads().
-template <class MC, class M, int TILE, int THREADS, bool KEEP>
+template <class MC, class M, int TILE, int THREADS, bool KEEP, bool HOIST = false>
 __device__ __forceinline__ void mlp_forward(const float* __restrict__ W, float* __restrict__ pp0, float* __restrict__ pp1,
-                                            float* __restrict__ keep, float* __restrict__ out_raw, float act_prm, int tid) {
+                                            float* __restrict__ keep, float* __restrict__ out_raw, float act_prm, int tid,
+                                            const PreAct pre = PreAct{}) {
   constexpr int LD = TILE + 4;
   static_for<0, MC::NL>([&](auto lc) {
     constexpr int l = decltype(lc)::value;
@@ -192,10 +258,15 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ W, float* 
       for (int j = 0; j < G::TN; ++j) {
         const int n = ng + G::NG * j;
         if (n < N) {
-          const float bj = bias[ng * G::TN + j];
           float v[G::TMB];
+          if constexpr (HOIST && l == 0) {
 #pragma unroll
-          for (int i = 0; i < G::TMB; ++i) v[i] = acc[i][j] + bj;
+            for (int i = 0; i < G::TMB; ++i) v[i] = acc[i][j] + __ldg(pre.row(traj0 + i, N) + n);
+          } else {
+            const float bj = bias[ng * G::TN + j];
+#pragma unroll
+            for (int i = 0; i < G::TMB; ++i) v[i] = acc[i][j] + bj;
+          }
           if constexpr (!LAST) {
             if constexpr (KEEP && MC::DBUF) {
               float dv[G::TMB];
@@ -245,7 +316,7 @@ struct DwNone { __device__ __forceinline__ void zero() {} };
 // add the thread's tile of layer L to  dst[n*K + k].  With a trajectory split (SPLIT > 1) several thread groups
 // hold partial sums of the same entries: they are added one group after the other, a barrier apart, so that the
 // result does not depend on scheduling (bitwise reproducible gradients).  Called by every thread of the CTA.
-template <class D, int N, int K>
+template <class D, int N, int K, int KW = K>
 __device__ __forceinline__ void dw_flush_tile(const float (&acc)[D::RJ][D::RK], float* __restrict__ dst, int unit) {
   const int tile = unit % D::TILES, grp = unit / D::TILES;
   const int kt = tile % D::NKT, jt = tile / D::NKT;
@@ -257,7 +328,7 @@ __device__ __forceinline__ void dw_flush_tile(const float (&acc)[D::RJ][D::RK], 
 #pragma unroll
         for (int j = 0; j < D::RK; ++j) {
           const int n = jt + D::NJ * i, k = kt + D::NKT * j;
-          if (n < N && k < K) dst[n * K + k] += acc[i][j];
+          if (n < N && k < K) dst[n * KW + k] += acc[i][j];
         }
     }
     if constexpr (D::SPLIT > 1) __syncthreads();
@@ -268,11 +339,12 @@ __device__ __forceinline__ void dw_flush_tile(const float (&acc)[D::RJ][D::RK], 
 // Leaves the gradient w.r.t. the first gw(0) inputs in the delta buffer of parity NL (dbuf0 if NL even
 // else dbuf1).  `gscratch` != nullptr selects spill mode: per-step tiles are added to the CTA's private
 // global gradient block instead of persistent registers.  Ends with a __syncthreads().
-template <class MC, class M, int TILE, int THREADS, bool SPILL, class Store>
+//   HOIST: dZ_1 of the tile's trajectories is also written to `dz1` (PreAct addressing) for nm_exo_gemm_bwd_kernel.
+template <class MC, class M, int TILE, int THREADS, bool SPILL, bool HOIST = false, class Store>
 __device__ __forceinline__ void mlp_backward(const float* __restrict__ W, const float* __restrict__ keep,
                                              float* __restrict__ dbuf0, float* __restrict__ dbuf1, Store& store,
                                              float* __restrict__ gscratch, bool has_bias, bool trainable,
-                                             float act_prm, int tid) {
+                                             float act_prm, int tid, const PreAct dz1 = PreAct{}) {
   constexpr int LD = TILE + 4;
   static_for_rev<0, MC::NL>([&](auto lc) {
     constexpr int l = decltype(lc)::value;
@@ -281,6 +353,14 @@ __device__ __forceinline__ void mlp_backward(const float* __restrict__ W, const 
     const float* dl = (step & 1) ? dbuf1 : dbuf0;              // delta_{l+1}  [N][LD]
     float* dout = (step & 1) ? dbuf0 : dbuf1;                  // delta_l      [GW][LD]
     const float* al = keep + MC::a_off(l);
+    if constexpr (HOIST && l == 0) {
+      // consecutive threads -> consecutive outputs of one trajectory: coalesced rows of N floats
+      float* __restrict__ gdst = const_cast<float*>(dz1.base);
+      for (int idx = tid; idx < N * TILE; idx += THREADS) {
+        const int traj = idx / N, n = idx - traj * N;
+        if (dz1.b0 + traj < dz1.B) gdst[((dz1.b0 + traj) * dz1.T + dz1.t) * int64_t(N) + n] = dl[n * LD + traj];
+      }
+    }
     if constexpr (GW > 0) {
       using G = GemmCfg<GW, TILE, THREADS>;
       gemm_phase<N, GW, TILE, THREADS, LD>(W + MC::wb_off(l), dl, tid, [&](int kg, int traj0, float (&acc)[G::TMB][G::TN]) {
@@ -333,7 +413,7 @@ __device__ __forceinline__ void mlp_backward(const float* __restrict__ W, const 
 #pragma unroll
             for (int j = 0; j < D::RK; ++j) t[i][j] = 0.f;
           dw_tile<N, K, TILE, THREADS, LD>(t, dl, al, s * THREADS + tid);
-          dw_flush_tile<D, N, K>(t, gw_dst, s * THREADS + tid);
+          dw_flush_tile<D, N, K, MC::KW(l)>(t, gw_dst, s * THREADS + tid);
         }
         if (has_bias && tid < N) {
           const float* row = dl + tid * LD;
@@ -343,7 +423,7 @@ __device__ __forceinline__ void mlp_backward(const float* __restrict__ W, const 
             const float4 v = *reinterpret_cast<const float4*>(row + t4);
             s += (v.x + v.y) + (v.z + v.w);
           }
-          gw_dst[N * K + tid] += s;
+          gw_dst[N * MC::KW(l) + tid] += s;
         }
       }
     }
@@ -361,8 +441,8 @@ __device__ __forceinline__ void dw_writeout(Store& store, float* __restrict__ gd
     auto& st = store.template at<l>();
     float* dst = gdst + MC::p_off(l);
 #pragma unroll
-    for (int s = 0; s < D::SLOTS; ++s) dw_flush_tile<D, N, K>(st.acc[s], dst, s * THREADS + tid);
-    if (has_bias && tid < N) dst[N * K + tid] += st.db;
+    for (int s = 0; s < D::SLOTS; ++s) dw_flush_tile<D, N, K, MC::KW(l)>(st.acc[s], dst, s * THREADS + tid);
+    if (has_bias && tid < N) dst[N * MC::KW(l) + tid] += st.db;
   });
 }
 
@@ -435,7 +515,7 @@ __device__ __forceinline__ void build_policy_input(const NmPlan& p, const float*
           for (int dd = 0; dd < D; ++dd) a0[(off + j * D + dd) * LD + tid] = fill ? p.pad_value : __ldg(base + ts * D + dd);
         }
       }
-    } else {
+    } else if constexpr (!S::HOIST) {                         // (hoisted: the exogenous segments enter through E)
       constexpr int e = S::seg_index(s);
       const float* __restrict__ src = exo[e] + (b * p.exo[e].steps + t) * W;
       if constexpr (W % 4 == 0) {
@@ -560,7 +640,8 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
       }
       if constexpr (KC::HAS_POL) {
         __syncthreads();
-        mlp_forward<PolCfg, typename S::Pol, TILE, THREADS, false>(Wpol, pp0, pp1, nullptr, nullptr, p.policy.act_param, tid);
+        mlp_forward<PolCfg, typename S::Pol, TILE, THREADS, false, KC::HOIST>(Wpol, pp0, pp1, nullptr, nullptr, p.policy.act_param, tid,
+                                                                              PreAct{args.pre, int64_t(tile) * TILE, args.B, T, t});
         if (owner) {
           const float* outp = (PolCfg::NL & 1) ? pp1 : pp0;
 #pragma unroll
@@ -791,7 +872,8 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
       }
       if constexpr (KC::HAS_POL) {
         __syncthreads();
-        mlp_forward<PolCfg, typename S::Pol, TILE, THREADS, true>(Wpol, nullptr, nullptr, keep_pol, dbuf0, p.policy.act_param, tid);
+        mlp_forward<PolCfg, typename S::Pol, TILE, THREADS, true, KC::HOIST>(Wpol, nullptr, nullptr, keep_pol, dbuf0, p.policy.act_param, tid,
+                                                                             PreAct{args.pre, int64_t(tile) * TILE, args.B, T, t});
         if (owner) {
 #pragma unroll
           for (int j = 0; j < NU; ++j) {
@@ -917,8 +999,9 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             dbuf0[j * LD + tid] = valid ? gu[j] * bounds_deriv<S::Pol::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]) : 0.f;
         }
         __syncthreads();
-        mlp_backward<PolCfg, typename S::Pol, TILE, THREADS, SPILL>(Wpol, keep_pol, dbuf0, dbuf1, pol_dw, gpol,
-                                                                     p.policy.has_bias, pol_train, p.policy.act_param, tid);
+        mlp_backward<PolCfg, typename S::Pol, TILE, THREADS, SPILL, KC::HOIST>(Wpol, keep_pol, dbuf0, dbuf1, pol_dw, gpol,
+                                                                     p.policy.has_bias, pol_train, p.policy.act_param, tid,
+                                                                     PreAct{args.dz1, int64_t(tile) * TILE, args.B, T, t});
         if (owner) {
           const float* gin = (PolCfg::NL & 1) ? dbuf1 : dbuf0;
           int off = 0;
@@ -979,5 +1062,136 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
   }
   (void)ND; (void)Wrhs; (void)Wpol; (void)keep_rhs;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Hoist GEMMs (see HoistedMlp).  Rows r = b * T + t over the whole batch and horizon; a CTA takes tiles of TILE rows.
+struct ExoPtrs { const float* p[NM_MAX_EXO]; };
+template <class S> constexpr int exo_seg_off(int s) {        // offset of segment s within the exogenous part
+  int o = 0;
+  for (int i = 0; i < s; ++i) if (S::seg_kind(i) == NM_SEG_EXO) o += S::seg_width(i);
+  return o;
+}
+template <class S> constexpr int exo_seg_wmax() {
+  int m = 4;
+  for (int i = 0; i < S::NSEG; ++i) if (S::seg_kind(i) == NM_SEG_EXO) m = cmax(m, S::seg_width(i));
+  return m;
+}
+template <class S> constexpr size_t exo_gemm_smem_bytes() { return size_t(exo_seg_wmax<S>() + KCfg<S>::N0) * (S::TILE + 4) * 4; }
+
+// gather rows r0 .. r0+TILE of exogenous segment `s` (width W) into in[c][row]
+template <class S, int s>
+__device__ __forceinline__ void exo_gather(const NmPlan& p, const ExoPtrs& exo, float* __restrict__ in, int tid, int64_t r0, int64_t R) {
+  constexpr int W = S::seg_width(s), e = S::seg_index(s), LD = S::TILE + 4;
+  if (tid < S::TILE) {
+    const int64_t r = r0 + tid < R ? r0 + tid : R - 1;
+    const int64_t b = r / p.nsteps;
+    const int t = int(r - b * p.nsteps);
+    const float* __restrict__ src = exo.p[e] + (b * p.exo[e].steps + t) * W;
+#pragma unroll 4
+    for (int i = 0; i < W; i += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+      in[(i + 0) * LD + tid] = v.x; in[(i + 1) * LD + tid] = v.y; in[(i + 2) * LD + tid] = v.z; in[(i + 3) * LD + tid] = v.w;
+    }
+  }
+}
+
+// E[r][n] = bias[n] + sum over exogenous segments, k:  W_0[n][KS + off + k] * exo_seg[r][k]
+template <class S>
+__global__ void __launch_bounds__(S::THREADS) nm_exo_gemm_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ wprep,
+                                                                     const __grid_constant__ ExoPtrs exo, float* __restrict__ E, int64_t B) {
+  using KC = KCfg<S>;
+  constexpr int TILE = S::TILE, THREADS = S::THREADS, LD = TILE + 4, N0 = KC::N0, NP = KC::EXO_NP;
+  using G = GemmCfg<N0, TILE, THREADS>;
+  extern __shared__ __align__(128) float smem[];
+  float* in = smem;                                          // [wmax][LD]
+  float* out = smem + exo_seg_wmax<S>() * LD;                // [N0][LD]
+  const int tid = threadIdx.x;
+  const NmPlan& p = plan;
+  const float* __restrict__ wexo = wprep + KC::EXO_W_OFF;
+  const int64_t R = B * p.nsteps;
+  const int64_t tiles = (R + TILE - 1) / TILE;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * TILE;
+    static_for<0, S::NSEG>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+        constexpr int W = S::seg_width(s), OFF = exo_seg_off<S>(s);
+        __syncthreads();                                     // the previous GEMM has finished reading `in`
+        exo_gather<S, s>(p, exo, in, tid, r0, R);
+        __syncthreads();
+        gemm_phase<W, N0, TILE, THREADS, LD>(wexo + OFF * NP, in, tid, [&](int ng, int traj0, float (&acc)[G::TMB][G::TN]) {
+#pragma unroll
+          for (int j = 0; j < G::TN; ++j) {
+            const int n = ng + G::NG * j;
+            if (n < N0) {
+              float v[G::TMB];
+              if constexpr (OFF == 0) {
+#pragma unroll
+                for (int i = 0; i < G::TMB; ++i) v[i] = acc[i][j];
+              } else {
+                ld_vec<G::TMB>(v, out + n * LD + traj0);    // same thread wrote it for the previous segment
+#pragma unroll
+                for (int i = 0; i < G::TMB; ++i) v[i] += acc[i][j];
+              }
+              st_vec<G::TMB>(out + n * LD + traj0, v);
+            }
+          }
+        });
+      }
+    });
+    __syncthreads();
+    // consecutive threads -> consecutive outputs of one row: coalesced rows of N0 floats
+    for (int idx = tid; idx < N0 * TILE; idx += THREADS) {
+      const int row = idx / N0, n = idx - row * N0;
+      if (r0 + row < R) E[(r0 + row) * N0 + n] = out[n * LD + row] + wexo[KC::KE * NP + g_col(N0, n)];
+    }
+  }
+}
+
+// dW_0[n][KS + off + k] += sum_r dZ_1[r][n] * exo_seg[r][k]   into this CTA's gradient block (after the adjoint kernel)
+template <class S>
+__global__ void __launch_bounds__(S::THREADS) nm_exo_gemm_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ ExoPtrs exo,
+                                                                     const float* __restrict__ dZ1, float* __restrict__ grad_partials, int64_t B) {
+  using KC = KCfg<S>;
+  constexpr int TILE = S::TILE, THREADS = S::THREADS, LD = TILE + 4, N0 = KC::N0, KW = S::Pol::sz(0);
+  extern __shared__ __align__(128) float smem[];
+  float* in = smem;                                          // [wmax][LD]   exogenous rows, transposed
+  float* delta = smem + exo_seg_wmax<S>() * LD;              // [N0][LD]     dZ_1 rows, transposed
+  const int tid = threadIdx.x;
+  const NmPlan& p = plan;
+  const int64_t R = B * p.nsteps;
+  const int64_t tiles = (R + TILE - 1) / TILE;
+  float* gpol = grad_partials + size_t(blockIdx.x) * size_t(p.n_params) + p.policy.param_offset;
+  static_for<0, S::NSEG>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+      constexpr int W = S::seg_width(s), OFF = exo_seg_off<S>(s);
+      using D = DwCfg<N0, W, TILE, THREADS>;
+      float acc[D::SLOTS][D::RJ][D::RK];
+#pragma unroll
+      for (int q = 0; q < D::SLOTS; ++q)
+#pragma unroll
+        for (int i = 0; i < D::RJ; ++i)
+#pragma unroll
+          for (int j = 0; j < D::RK; ++j) acc[q][i][j] = 0.f;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t r0 = tile * TILE;
+        __syncthreads();                                     // the previous tile's products are done
+        exo_gather<S, s>(p, exo, in, tid, r0, R);
+        for (int idx = tid; idx < N0 * TILE; idx += THREADS) {
+          const int row = idx / N0, n = idx - row * N0;
+          delta[n * LD + row] = r0 + row < R ? __ldg(dZ1 + (r0 + row) * N0 + n) : 0.f;   // rows past the end contribute nothing
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < D::SLOTS; ++q) dw_tile<N0, W, TILE, THREADS, LD>(acc[q], delta, in, q * THREADS + tid);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < D::SLOTS; ++q) dw_flush_tile<D, N0, W, KW>(acc[q], gpol + KC::KS + OFF, q * THREADS + tid);
+    }
+  });
+}
+
 
 }  // namespace nm

@@ -10,6 +10,7 @@ struct NmFwdCall {
   void* workspace; size_t workspace_bytes; int64_t B; cudaStream_t stream;
   int fused_terms;                                 // in: plan terms match the entry's compiled term structure
   double* term_partials; int grid;                 // out: per-CTA term sums (fused), CTAs launched
+  int extra_launches;                              // out: kernels launched besides weight prep + rollout
 };
 struct NmBwdCall {
   const float* params; const float* const* exo;
@@ -20,6 +21,7 @@ struct NmBwdCall {
   int fused_terms;
   void* workspace; size_t workspace_bytes; int64_t B; int64_t b_total; cudaStream_t stream;
   float* grad_partials; int grid;                  // out: per-CTA gradient blocks, CTAs launched
+  int extra_launches;                              // out: kernels launched besides weight prep + adjoint
 };
 
 struct NmKernelEntry {

@@ -20,10 +20,17 @@ using namespace nm;
 #ifndef NM_TUNE_MINB_BWD
 #define NM_TUNE_MINB_BWD 1
 #endif
+// exogenous first-layer hoist (nm_kernels.cuh, HoistedMlp): compiled in with NM_TUNE_HOIST=1.  Written without GPU access
+// at the end of round 1 -- it compiles, the kernels of every class built without the flag are unchanged (identical SASS),
+// and it has NOT run on a GPU yet: off by default until the parity suite has seen it.
+#ifndef NM_TUNE_HOIST
+#define NM_TUNE_HOIST 0
+#endif
 template <class Shape, int TILE_, int THREADS_, bool W_SMEM_>
 struct Tiled : Shape {
   static constexpr int TILE = TILE_, THREADS = THREADS_;
   static constexpr bool W_SMEM = W_SMEM_;
+  static constexpr bool HOIST = NM_TUNE_HOIST != 0;
   static constexpr int MINB_FWD = NM_TUNE_MINB_FWD, MINB_BWD = NM_TUNE_MINB_BWD;   // __launch_bounds__ min CTAs / SM
 };
 
@@ -157,6 +164,10 @@ template <class Sp> struct TcBwdEligible<Sp, true> { static constexpr bool value
 // the tensor-core adjoint needs the stage checkpoints written by the forward kernel; without them the FFMA adjoint runs
 constexpr bool kTcBwd = kTcFwd && TcBwdEligible<NM_SPEC_NAME, kTcFwd>::value;
 
+constexpr bool kHoist = KC::HOIST && KCF::HOIST && !kTcFwd;
+constexpr size_t hoist_bytes(const NmPlan* p, int64_t B) { return kHoist ? ((size_t(B) * size_t(p->nsteps) * size_t(KC::N0) * sizeof(float) + 255) & ~size_t(255)) : 0; }
+constexpr size_t kExoSmem = exo_gemm_smem_bytes<SB>();
+
 struct DeviceInfo { int sms = 0; int occ_fwd = 0; int occ_bwd = 0; bool ready = false; };
 DeviceInfo g_dev[64];
 std::mutex g_mu;
@@ -174,6 +185,10 @@ int device_info(DeviceInfo** out) {
     if (kTcFwd && e == cudaSuccess) e = TcFwd<NM_SPEC_NAME, kTcFwd>::setup(&d.occ_fwd);
     if (kTcBwd && e == cudaSuccess) e = TcBwd<NM_SPEC_NAME, kTcBwd>::setup();
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_bwd, nm_bwd_kernel<S>, S::THREADS, KC::BWD_SMEM_BYTES);
+    if constexpr (kHoist) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_fwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExoSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_bwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExoSmem);
+    }
     if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
     if (d.occ_fwd < 1 || d.occ_bwd < 1) { nm_set_error("kernel does not fit on an SM (occupancy 0)"); return NM_ERR_CUDA; }
     d.ready = true;
@@ -183,7 +198,7 @@ int device_info(DeviceInfo** out) {
 }
 
 constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
-constexpr size_t kWprepFfma = size_t(KC::W_FLOATS_ALL > 0 ? KC::W_FLOATS_ALL : 4) * 4;
+constexpr size_t kWprepFfma = size_t(KC::W_FLOATS_ALL + KC::EXO_W_FLOATS > 0 ? KC::W_FLOATS_ALL + KC::EXO_W_FLOATS : 4) * 4;
 constexpr size_t kWprepTc = TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES > (kTcFwd ? TK::FWD_W_BYTES : 0) ? TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES : (kTcFwd ? TK::FWD_W_BYTES : 0);
 constexpr size_t kWprepBytes = align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
 constexpr int kFwdTile = kTcFwd ? 128 : SF::TILE;
@@ -213,14 +228,15 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
     const int64_t gtc = tiles_tc < slots ? tiles_tc : slots;
     if (gtc > gb) gb = gtc;
   }
-  *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double));
-  *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float));
+  // (hoist: E[B][T][N0] in the forward workspace when the caller gives no checkpoint buffer; E recomputed / dZ_1 in the backward one)
+  *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double)) + hoist_bytes(p, B);
+  *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float)) + hoist_bytes(p, B);
   return NM_OK;
 }
 
 int launch_prep(const NmPlan* p, const float* params, float* wprep, cudaStream_t st) {
-  if constexpr (KC::W_FLOATS_ALL > 0) {
-    const int blocks = (KC::W_FLOATS_ALL + 4 * 256 - 1) / (4 * 256);
+  if constexpr (KC::W_FLOATS_ALL + KC::EXO_W_FLOATS > 0) {
+    const int blocks = (KC::W_FLOATS_ALL + KC::EXO_W_FLOATS + 4 * 256 - 1) / (4 * 256);
     nm_prep_kernel<S><<<blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks), 256, 0, st>>>(*p, params, wprep);
   }
   return NM_OK;
@@ -245,6 +261,19 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
   a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj; a.chk = c->checkpoints;
   a.B = c->B; a.num_tiles = tiles;
+  if constexpr (kHoist) {
+    // E = bias + exogenous part of the first layer for every (trajectory, step): into the caller's checkpoint buffer
+    // when there is one (the adjoint then reads it back), else into the workspace tail
+    float* E = c->checkpoints != nullptr ? c->checkpoints
+                                         : reinterpret_cast<float*>(ws + (need_f - hoist_bytes(p, c->B)));
+    ExoPtrs ep{};
+    for (int e = 0; e < NM_MAX_EXO; ++e) ep.p[e] = a.exo[e];
+    const int64_t row_tiles = (c->B * p->nsteps + SB::TILE - 1) / SB::TILE;
+    int ggrid = d->sms * 2; if (ggrid > row_tiles) ggrid = int(row_tiles); if (ggrid < 1) ggrid = 1;
+    nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep, ep, E, c->B);
+    a.pre = E;
+    c->extra_launches = 1;
+  }
   if (kTcFwd) TcFwd<NM_SPEC_NAME, kTcFwd>::launch(*p, a, c->params, wprep, grid, c->stream);
   else nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
@@ -285,8 +314,30 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y; a.fused_terms = c->fused_terms;
   a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;
   a.B = c->B; a.b_total = c->b_total; a.num_tiles = tc_bwd ? int((c->B + 127) / 128) : tiles;
+  ExoPtrs ep{};
+  for (int e = 0; e < NM_MAX_EXO; ++e) ep.p[e] = a.exo[e];
+  if constexpr (kHoist) {
+    // workspace tail G1[B][T][N0]: dZ_1 written by the adjoint; without a checkpoint buffer E is recomputed into it first
+    // (the adjoint reads each entry of E before it overwrites it with dZ_1)
+    float* G1 = reinterpret_cast<float*>(ws + (need_b - hoist_bytes(p, c->B)));
+    if (c->checkpoints != nullptr) a.pre = c->checkpoints;
+    else {
+      const int64_t row_tiles = (c->B * p->nsteps + SB::TILE - 1) / SB::TILE;
+      int ggrid = d->sms * 2; if (ggrid > row_tiles) ggrid = int(row_tiles); if (ggrid < 1) ggrid = 1;
+      nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep, ep, G1, c->B);
+      a.pre = G1;
+      c->extra_launches += 1;
+    }
+    a.dz1 = G1;
+  }
   if (tc_bwd) TcBwd<NM_SPEC_NAME, kTcBwd>::launch(*p, a, c->params, wprep, grid, c->stream);
   else nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
+  if constexpr (kHoist) {
+    if (p->policy.trainable) {
+      nm_exo_gemm_bwd_kernel<SB><<<grid, SB::THREADS, kExoSmem, c->stream>>>(*p, ep, a.dz1, c->grad_partials, c->B);
+      c->extra_launches += 1;
+    }
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
   return NM_OK;
@@ -316,7 +367,7 @@ struct Registrar {
     g_entry.forward = forward_fn;
     g_entry.backward = backward_fn;
     g_entry.info = g_info;
-    g_entry.chk_floats_per_step = kTcFwd ? TcMode<NM_SPEC_NAME>::CHK : -1;   // -1: the generic rule of nm_api.cu
+    g_entry.chk_floats_per_step = kTcFwd ? TcMode<NM_SPEC_NAME>::CHK : (kHoist ? KC::N0 : -1);   // -1: the generic rule of nm_api.cu
     g_entry.next = nullptr;
     nm_register_kernel(&g_entry);
   }
