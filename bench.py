@@ -140,8 +140,12 @@ def main():
     import helpers as H
     case0 = H.configs.build_case(args.workload)
     nsteps = case0.nsteps
-    cfg = {"workload": args.workload, "nsteps": nsteps, "batch_per_gpu": args.batch or case0.default_batch,
-           "global_batch": (args.batch or case0.default_batch) * max(world, 1), "parallelism": f"dp{world}",
+    # c5 is quoted at a fixed GLOBAL batch (4M trajectories at 1/2/4/8 GPUs: strong scaling); every other config at a
+    # fixed batch per GPU (weak scaling)
+    strong = args.workload == "c5" and not args.batch
+    per_gpu = args.batch or (case0.default_batch // max(world, 1) if strong else case0.default_batch)
+    cfg = {"workload": args.workload, "nsteps": nsteps, "batch_per_gpu": per_gpu,
+           "global_batch": per_gpu * max(world, 1), "parallelism": f"dp{world}",
            "description": {"c1": "DPC double integrator, MLP 2-20-20-20-20-1 ReLU, linear SSM",
                            "c2": "DPC reference tracking, TwoTank ODE + RK4, MLP_bounds 4-32-32-2 GELU",
                            "c3": "neural-ODE system ID, RK4 over MLP RHS 2-60-60-60-2 ReLU",
@@ -333,7 +337,7 @@ def main():
         cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {**cfg, "l2": "flushed between timed steps (256 MiB memset)", "loss": loss_val,
                        "kernel_info": kernel_info},
