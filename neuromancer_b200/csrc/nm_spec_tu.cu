@@ -168,14 +168,15 @@ constexpr bool kHoist = KC::HOIST && KCF::HOIST && !kTcFwd;
 constexpr size_t hoist_bytes(const NmPlan* p, int64_t B) { return kHoist ? ((size_t(B) * size_t(p->nsteps) * size_t(KC::N0) * sizeof(float) + 255) & ~size_t(255)) : 0; }
 constexpr size_t kExoSmem = exo_gemm_smem_bytes<SB>();
 // the hoisted configuration addresses the same parameter block as the plain one
-template <bool ON> constexpr bool hoist_layout_ok() {
-  if constexpr (ON) {
-    using Full = MlpCfg<NM_SPEC_NAME::Pol, SB::TILE, SB::THREADS, KC::pol_gw0()>;
-    return KC::PolCfg::N_PARAMS == Full::N_PARAMS && KC::KS + KC::KE == NM_SPEC_NAME::Pol::sz(0) && KC::KS >= 1 && KC::KE >= 4 &&
-           KC::PolCfg::p_off(1) == Full::p_off(1) && KC::PolCfg::K(0) == KC::KS && KC::PolCfg::KW(0) == NM_SPEC_NAME::Pol::sz(0);
+template <class K_, class Tl> constexpr bool hoist_layout_ok() {       // (dependent on K_: only instantiated for hoisted classes)
+  if constexpr (K_::HOIST) {
+    using Full = MlpCfg<NM_SPEC_NAME::Pol, Tl::TILE, Tl::THREADS, K_::pol_gw0()>;
+    using Pc = typename K_::PolCfg;
+    return Pc::N_PARAMS == Full::N_PARAMS && K_::KS + K_::KE == NM_SPEC_NAME::Pol::sz(0) && K_::KS >= 1 && K_::KE >= 4 &&
+           Pc::p_off(1) == Full::p_off(1) && Pc::K(0) == K_::KS && Pc::KW(0) == NM_SPEC_NAME::Pol::sz(0);
   } else return true;
 }
-static_assert(hoist_layout_ok<kHoist>(), "hoist: parameter layout of the restricted first layer");
+static_assert(hoist_layout_ok<KC, SB>() && hoist_layout_ok<KCF, SF>(), "hoist: parameter layout of the restricted first layer");
 static_assert(!kHoist || kExoSmem <= 200 * 1024, "hoist: GEMM tiles do not fit in shared memory");
 
 struct DeviceInfo { int sms = 0; int occ_fwd = 0; int occ_bwd = 0; bool ready = false; };
