@@ -1,0 +1,101 @@
+"""The FFMA kernel templates (neuromancer_b200/csrc/nm_kernels.cuh) compiled for the HOST and run against the oracle.
+
+tests/emu/cuda_emu.h emulates the CUDA execution model with one OS thread per CUDA thread of one block at a time
+(std::barrier for __syncthreads); tests/emu/ffma_emu.cpp launches weight preparation, rollout and adjoint kernels the
+way nm_spec_tu.cu does and writes trajectories, term sums and the parameter gradient.  What this checks without a GPU
+is the kernels' LOGIC -- index math, staging layouts, barrier placement (a missing barrier is a data race between the
+OS threads too), the persistent tile loop, the per-CTA gradient blocks -- not their performance and not the
+tensor-core kernels (inline PTX).  It is how the flag-guarded first-layer hoist (HoistedMlp, nm_exo_gemm_*_kernel) was
+validated at the end of round 1, after the GPU budget was spent."""
+import os
+import shutil
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from neuromancer_b200 import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20)")
+
+
+def compile_emulator(name, out, defines=()):
+    hdr = build.write_spec(H.configs.build_case(name).plan().c)
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-fpermissive", "-DNM_HOST_EMU", "-I", os.path.join(ROOT, "tests", "emu"),
+           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "neuromancer_b200", "csrc"),
+           "-I", "/usr/local/cuda/include", f'-DNM_SPEC_HEADER="{hdr}"', *[f"-D{d}" for d in defines],
+           os.path.join(ROOT, "tests", "emu", "ffma_emu.cpp"), "-o", out, "-lpthread"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout[-4000:]
+
+
+def run_emulated(name, B, exe, tmp):
+    case = H.configs.build_case(name, seed=3)
+    batch = case.make_batch(B, "cpu", 7)
+    x_in = case.system.init(dict(batch))
+    plan = case.system.plan_for(x_in, loss=case.problem.loss)
+    p = plan.c
+    flat = np.zeros(int(p.n_params), np.float32)
+    for q, (off, n) in zip(plan.params, plan.param_slices):
+        flat[off:off + n] = q.detach().numpy().reshape(-1)
+    lay = case.system.layout()
+    fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("q", B))
+        f.write(bytes(p))
+        f.write(flat.tobytes())
+        f.write(x_in[lay.state_key][:, 0, :].contiguous().numpy().astype(np.float32).tobytes())
+        for k in plan.exo_keys:
+            f.write(x_in[k].contiguous().numpy().astype(np.float32).tobytes())
+    subprocess.run([exe, fin, fout], check=True, timeout=600)
+    raw = open(fout, "rb").read()
+    T, nx, nu, ny, pos = p.nsteps, p.nx, p.nu, p.ny, 0
+
+    def take(n, dt=np.float32):
+        nonlocal pos
+        a = np.frombuffer(raw, dt, n, pos).copy()
+        pos += n * np.dtype(dt).itemsize
+        return a
+    traj = {lay.state_key: take(B * (T + 1) * nx).reshape(B, T + 1, nx), lay.action_key: take(B * T * nu).reshape(B, T, nu),
+            lay.output_key: take(B * T * ny).reshape(B, T, ny)}
+    tsum, grad = take(p.n_terms, np.float64), take(int(p.n_params))
+    ref = H.oracle_run(name, [q.detach().clone() for q in plan.params], batch)
+    for k, v in ref["traj"].items():
+        assert H.rel_err(torch.from_numpy(traj[k]), v) <= 1e-5, (name, B, k)
+    loss = sum(p.terms[k].weight * tsum[k] / (B * p.terms[k].t_len * p.terms[k].d_len) for k in range(p.n_terms))
+    assert abs(loss - float(ref["loss"].detach())) <= 1e-4 * abs(float(ref["loss"].detach())), (name, B, loss)
+    trainable = [q for q in plan.params if q.requires_grad]
+    for q, (off, n) in zip(plan.params, plan.param_slices):
+        if q.requires_grad:
+            g = torch.from_numpy(grad[off:off + n]).view(q.shape)
+            r = ref["grads"][[id(z) for z in trainable].index(id(q))]
+            assert H.rel_err(g, r) <= 1e-4, (name, B, tuple(q.shape), H.rel_err(g, r))
+
+
+# (case, defines): tile / thread shapes as nm_spec_tu.cu picks them, weights read from the prepared global block
+PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256")),                 # y = Cx node, disturbance, LeakyReLU, sigmoid bounds, 193-wide fan-in
+         ("c2", ("EMU_TILE=128", "EMU_THREADS=128")),                 # exact FFMA fallback of the tensor-core class: GELU, TwoTank RK4, 5 terms
+         ("t_ssm_softplus", ("EMU_TILE=64", "EMU_THREADS=128"))]      # state after the exogenous segment, softplus derivative buffers
+
+
+@pytest.mark.parametrize("name,defines", PLAIN)
+def test_ffma_kernels_on_the_host_match_the_oracle(name, defines, tmp_path):
+    exe = str(tmp_path / "emu")
+    compile_emulator(name, exe, defines)
+    for B in (1, 150):                                                 # ragged single tile; two or three tiles on two CTAs
+        run_emulated(name, B, exe, str(tmp_path))
+
+
+@pytest.mark.parametrize("alias", [False, True])
+def test_first_layer_hoist_on_the_host_matches_the_oracle(alias, tmp_path):
+    """c4 with the exogenous part of its first layer hoisted into the two GEMM kernels (NM_TUNE_HOIST=1); `alias`:
+    dZ_1 overwrites E in place, the no-checkpoint configuration of nm_spec_tu.cu."""
+    exe = str(tmp_path / "emu_hoist")
+    compile_emulator("c4", exe, ("EMU_TILE=128", "EMU_THREADS=256", "NM_TUNE_HOIST=1") + (("EMU_ALIAS_DZ1",) if alias else ()))
+    for B in (1, 70, 300):
+        run_emulated("c4", B, exe, str(tmp_path))
