@@ -78,16 +78,21 @@ def run_emulated(name, B, exe, tmp):
 
 
 # (case, defines): tile / thread shapes as nm_spec_tu.cu picks them, weights read from the prepared global block
-PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256")),                 # y = Cx node, disturbance, LeakyReLU, sigmoid bounds, 193-wide fan-in
-         ("c2", ("EMU_TILE=128", "EMU_THREADS=128")),                 # exact FFMA fallback of the tensor-core class: GELU, TwoTank RK4, 5 terms
-         ("t_ssm_softplus", ("EMU_TILE=64", "EMU_THREADS=128"))]      # state after the exogenous segment, softplus derivative buffers
+PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256"), (1, 150)),      # y = Cx node, disturbance, LeakyReLU, sigmoid bounds, 193-wide fan-in
+         ("c2", ("EMU_TILE=128", "EMU_THREADS=128"), (1, 150)),      # exact FFMA fallback of the tensor-core class: GELU, TwoTank RK4, 5 terms
+         ("c1", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),        # linear SSM, ReLU masks, 4 hidden layers
+         ("c3", ("EMU_TILE=64", "EMU_THREADS=256"), (70,)),          # neural ODE: MLP right-hand side inside RK4, adjoint recomputing its stages
+         ("c5", ("EMU_TILE=32", "EMU_THREADS=256"), (40,)),          # 128-wide layers, weight gradients spilled to the CTA's gradient block, coupled VdP ring
+         ("t_ssm_softplus", ("EMU_TILE=64", "EMU_THREADS=128"), (1, 150)),     # state after the exogenous segment, softplus derivative buffers
+         ("t_preview_reflect", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),   # SystemPreview window gather with reflect padding
+         ("t_node_policy_euler", ("EMU_TILE=64", "EMU_THREADS=128"), (100,))]  # MLP policy AND MLP right-hand side
 
 
-@pytest.mark.parametrize("name,defines", PLAIN)
-def test_ffma_kernels_on_the_host_match_the_oracle(name, defines, tmp_path):
+@pytest.mark.parametrize("name,defines,batches", PLAIN, ids=[c[0] for c in PLAIN])
+def test_ffma_kernels_on_the_host_match_the_oracle(name, defines, batches, tmp_path):
     exe = str(tmp_path / "emu")
     compile_emulator(name, exe, defines)
-    for B in (1, 150):                                                 # ragged single tile; two or three tiles on two CTAs
+    for B in batches:                                                  # ragged single tile / several tiles on two CTAs
         run_emulated(name, B, exe, str(tmp_path))
 
 
