@@ -10,7 +10,7 @@ signatures so a DPC / system-ID script switches by changing its imports.
 from . import constraint, dataset, dynamics, loss, modules, problem, slim, system  # noqa: F401
 from .constraint import Constraint, Objective, Variable, variable  # noqa: F401
 from .dataset import DictDataset  # noqa: F401
-from .loss import PenaltyLoss  # noqa: F401
+from .loss import BarrierLoss, PenaltyLoss  # noqa: F401
 from .problem import Problem  # noqa: F401
 from .system import Node, System, SystemPreview  # noqa: F401
 

@@ -116,3 +116,49 @@ class PenaltyLoss(AggregateLoss):
         merged.update(pens)
         merged["loss"] = objs["objective_loss"] + pens["penalty_loss"]
         return merged
+
+
+class BarrierLoss(PenaltyLoss):
+    """Barrier method (reference loss.py:184-257): a satisfied constraint (value < 0) contributes
+    ``weight * mean(barrier(value))``, clamped to ``[0, upper_bound]``, a violated one its penalty.
+
+    Not lowered to the fused term kernels: inside a ``Problem`` the ``System`` rollout runs on the fused forward
+    kernel, this loss is evaluated with torch ops on the CUDA trajectories it wrote, and its gradient enters the
+    fused adjoint kernel through ``grad_*_ext`` (the path of every Python-evaluated term)."""
+
+    def __init__(self, objectives, constraints, barrier="log10", upper_bound=1., shift=1., alpha=0.5):
+        super().__init__(objectives, constraints)
+        self.shift, self.alpha = shift, alpha
+        self.barriers = {"log10": lambda value: -torch.log10(-value),
+                         "log": lambda value: -torch.log(-value),
+                         "inverse": lambda value: 1 / (-value),
+                         "softexp": lambda value: (torch.exp(self.alpha * value) - 1) / self.alpha + self.alpha,
+                         "softlog": lambda value: -torch.log(1 + self.alpha * (-value - self.alpha)) / self.alpha,
+                         "expshift": lambda value: torch.exp(value + self.shift)}
+        if barrier in self.barriers:
+            self.barrier = self.barriers[barrier]
+        else:
+            assert callable(barrier), f"The barrier, {barrier} must be a key in {self.barriers} or a callable."
+            self.barrier = barrier
+        self.upper_bound = upper_bound
+
+    def calculate_constraints(self, input_dict):
+        loss, b_loss = 0.0, 0.0
+        out = super().calculate_constraints(input_dict)
+        for c in self.constraints:
+            cvalue, cviolation = out[c.output_keys[1]], out[c.output_keys[2]]
+            penalty_mask = cvalue >= 0
+            cbarrier = self.barrier(cvalue)
+            cbarrier[cbarrier != cbarrier] = 0.0               # nan -> 0: infeasible entries
+            cbarrier[cbarrier == float("Inf")] = 0.0           # inf -> 0: active constraints
+            cbarrier = torch.clamp(cbarrier, min=0.0, max=self.upper_bound)
+            out[f"{c.name}_barrier"] = cbarrier
+            if penalty_mask.any():
+                loss = loss + c.weight * torch.mean(penalty_mask * cviolation)
+            if (~penalty_mask).any():
+                barrier_loss = c.weight * torch.mean(~penalty_mask * cbarrier)
+                b_loss = b_loss + barrier_loss
+                loss = loss + barrier_loss
+        out["barrier_loss"] = b_loss
+        out["penalty_loss"] = loss
+        return out

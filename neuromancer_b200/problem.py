@@ -78,8 +78,10 @@ class Problem(nn.Module):
             seen |= set(node.output_keys)
 
     def _fusable(self):
+        # (exactly PenaltyLoss: subclasses such as BarrierLoss redefine how constraints enter the loss and are
+        # evaluated with torch ops on the trajectories the fused rollout wrote)
         return (len(self.nodes) == 1 and isinstance(self.nodes[0], System)
-                and isinstance(self.loss, PenaltyLoss))
+                and type(self.loss) is PenaltyLoss)
 
     def step(self, input_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Run the nodes (each a fused ``System``) and merge their outputs."""

@@ -117,3 +117,34 @@ def test_device_prefetcher_keeps_order_and_content_on_cpu():
     for i, b in enumerate(got):
         assert b["name"] == "train" and torch.equal(b["x"], batches[i]["x"])
     assert list(DevicePrefetcher(iter([]), device="cpu")) == []
+
+
+@pytest.mark.parametrize("barrier", ["log10", "log", "inverse", "softexp", "softlog", "expshift"])
+def test_barrier_loss_matches_reference_golden(barrier):
+    """BarrierLoss (reference loss.py:184-257) against vectors recorded from the unmodified reference
+    (oracle/pin_barrier.py): same torch ops in the same order, so equality is exact."""
+    import os
+    import numpy as np
+    from neuromancer_b200 import constraint as nb_constraint, loss as nb_loss
+    from oracle.pin_barrier import build
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "barrier.npz"))
+    data = {"x": torch.from_numpy(g["in_x"]), "u": torch.from_numpy(g["in_u"])}
+    res = build(nb_constraint, nb_loss, barrier)(data)
+    for k in ("loss", "objective_loss", "penalty_loss", "barrier_loss", "x_hi_barrier", "x_lo_barrier"):
+        want = torch.from_numpy(g[f"{barrier}/{k}"])
+        got = torch.as_tensor(res[k]).detach()
+        assert got.shape == want.shape and torch.equal(got, want), (barrier, k, got, want)
+    assert float(res["loss"]) == float(res["objective_loss"] + res["penalty_loss"])
+
+
+def test_problem_fuses_only_plain_penalty_loss():
+    from neuromancer_b200 import BarrierLoss, Problem, System
+    from neuromancer_b200.dynamics import integrators, ode
+    from neuromancer_b200.modules import blocks
+    net = blocks.MLP(2, 1, hsizes=[8], nonlin=nn.ReLU)
+    system = System([Node(net, ["x"], ["u"], name="policy"),
+                     Node(integrators.Euler(ode.VanDerPolControl(), h=0.1), ["x", "u"], ["x"], name="model")], nsteps=4)
+    x = variable("x")
+    con = (x < 1.0)
+    assert Problem([system], PenaltyLoss([], [con]))._fusable()
+    assert not Problem([system], BarrierLoss([], [con], barrier="softexp"))._fusable()
