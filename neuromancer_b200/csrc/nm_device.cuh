@@ -277,15 +277,25 @@ __device__ __forceinline__ void dw_tile(float (&acc)[DwCfg<N, K, TILE, THREADS>:
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1-D bulk TMA copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+// PTX helpers: mbarriers, 1-D bulk TMA copy global -> shared with completion on an mbarrier (SASS: UBLKCP), named
+// barriers.  (NM_HOST_EMU: tests/emu replaces them with host models to run the kernel templates without a GPU.)
+#ifdef NM_HOST_EMU
+}  // namespace nm
+#include "ptx_emu.h"
+namespace nm {
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   asm volatile(
@@ -303,5 +313,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                    "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// bar.sync <id>, 64: the two warps of a thread pair in the PAIR owner layout of the tensor-core adjoint
+__device__ __forceinline__ void named_bar_sync64(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+#endif
 
 }  // namespace nm

@@ -542,7 +542,7 @@ __device__ __forceinline__ void stage_weights(float* __restrict__ dst_a, const f
   if constexpr (FLOATS_A + FLOATS_B > 0) {
     if (tid == 0) {
       mbar_init(bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {

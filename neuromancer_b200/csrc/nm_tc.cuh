@@ -36,6 +36,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);   // D f32, A/B tf32, both K-major
 }
+// descriptor of the same tile family `byte_off` bytes further (the start-address field holds address >> 4)
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + uint64_t(byte_off >> 4); }
+// (NM_HOST_EMU: tests/emu/tc_ptx_emu.h models tensor memory, the MMAs and the barriers on the host)
+#ifdef NM_HOST_EMU
+}  // namespace tc
+}  // namespace nm
+#include "tc_ptx_emu.h"
+namespace nm {
+namespace tc {
+#else
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -51,8 +61,6 @@ __device__ __forceinline__ void mma_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint6
   else
     asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
 }
-// descriptor of the same tile family `byte_off` bytes further (the start-address field holds address >> 4)
-__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + uint64_t(byte_off >> 4); }
 __device__ __forceinline__ void st_shared(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
 // one lane of a converged warp (the tensor-core instructions live on the uniform datapath: issuing them from
 // `if (tid == k)` makes the compiler wrap each one in a per-thread vote loop -- measured 94 instead of 46 cycles per MMA)
@@ -148,6 +156,8 @@ __device__ __forceinline__ float tf32_hi(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
   return __uint_as_float(u);
 }
+
+#endif
 
 constexpr int pow2_ceil(int v) { int p = 32; while (p < v) p *= 2; return p; }
 constexpr int chunk_of(int w) { return w % 32 == 0 ? 32 : (w % 16 == 0 ? 16 : 8); }

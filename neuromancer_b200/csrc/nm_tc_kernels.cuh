@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const 
     }
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 0) tc::tmem_alloc<C::FWD_COLS>(tmem_slot);
   tc::fence_before();
@@ -449,9 +449,6 @@ __global__ void nm_tc_prep_bwd_kernel(const __grid_constant__ NmPlan plan, const
   tc::prep_tc_bwd<typename TcMode<S>::M>(params + TcMode<S>::mlp(plan).param_offset, wprep, gtid, gthreads);
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <class S>
 __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
@@ -505,7 +502,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
     }
     mbar_init(&bars[0], 1); mbar_init(&bars[1], NOW * 32); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
     mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    mbar_fence_init();
   }
   // constant rows of the transposed tiles: zero everything, then the constant-one (bias) row of every AT_l
   for (int i = tid; i < B::RING_OFF / 4; i += BK::THREADS) reinterpret_cast<float*>(sm)[i] = 0.f;
@@ -1160,7 +1157,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           } else {
 #pragma unroll
             for (int q = 0; q < K0; ++q) xch[(hf * 128 + m_) * 8 + q] = d_in[q];
-            asm volatile("bar.sync %0, 64;\n" ::"r"(1 + (warp & 3)) : "memory");
+            named_bar_sync64(1 + (warp & 3));
 #pragma unroll
             for (int q = 0; q < K0; ++q) gin[q] = xch[m_ * 8 + q] + xch[(128 + m_) * 8 + q];
           }
