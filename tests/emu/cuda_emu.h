@@ -3,7 +3,9 @@
 // neuromancer_b200/csrc/nm_kernels.cuh can be compiled with g++ and their LOGIC (index math, layouts, staging order)
 // checked on a machine without a GPU.  Nothing in the product imports, links or ships this.
 #pragma once
+#include <atomic>
 #include <barrier>
+#include <mutex>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -41,6 +43,14 @@ struct Idx { unsigned x = 0, y = 0, z = 0; };
 inline thread_local Idx t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 inline std::barrier<>* g_block_barrier = nullptr;
 inline double g_xchg[2048];
+inline std::unique_ptr<std::barrier<>> g_warp_bar[64];
+inline std::mutex g_named_mu;
+inline std::unique_ptr<std::barrier<>> g_named[16];
+inline std::barrier<>* named_barrier(int id, int n) {                  // bar.sync id, n
+  std::lock_guard<std::mutex> l(g_named_mu);
+  if (!g_named[id]) g_named[id] = std::make_unique<std::barrier<>>(n);
+  return g_named[id].get();
+}
 }  // namespace emu
 #define threadIdx emu::t_threadIdx
 #define blockIdx emu::t_blockIdx
@@ -49,7 +59,13 @@ inline double g_xchg[2048];
 
 // the dynamic shared memory window of the (single) running block: the kernels declare `extern __shared__ float smem[]`
 // at function scope inside namespace nm, which here is an ordinary extern declaration of this array
-namespace nm { alignas(1024) inline float smem[64 * 1024]; }
+namespace nm { extern float smem[]; }
+#define EMU_DEFINE_SMEM                                                                                  \
+  namespace nm {                                                                                         \
+  alignas(1024) float smem[64 * 1024];                                                                   \
+  /* the tensor-core adjoint declares its window as `uint8_t smem_raw[]`: the same memory */             \
+  extern uint8_t smem_raw[] __attribute__((alias("_ZN2nm4smemE")));                                      \
+  }
 
 inline void __syncthreads() { emu::g_block_barrier->arrive_and_wait(); }
 template <class T> inline T __ldg(const T* p) { return *p; }
@@ -64,6 +80,13 @@ inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
   emu::g_block_barrier->arrive_and_wait();
   return r;
 }
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
+// a real barrier among the 32 threads of the warp: on the hardware the lanes of a converged warp advance in lockstep; here
+// it keeps the non-elected lanes of a control warp within one step of the elected one (otherwise a slow lane can miss
+// two phase flips of an mbarrier and wait forever)
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::g_warp_bar[emu::t_threadIdx.x >> 5]->arrive_and_wait(); }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 using std::min;
 using std::max;
 
@@ -74,6 +97,8 @@ void launch(int grid, int threads, F&& fn) {
   for (int b = 0; b < grid; ++b) {
     std::barrier<> bar(threads);
     g_block_barrier = &bar;
+    for (auto& nb : g_named) nb.reset();
+    for (int w = 0; w < (threads + 31) / 32; ++w) g_warp_bar[w] = std::make_unique<std::barrier<>>(std::min(32, threads - 32 * w));
     std::vector<std::thread> th;
     th.reserve(threads);
     for (int t = 0; t < threads; ++t)

@@ -6,6 +6,7 @@
 // in.bin : int64 B | NmPlan bytes | params[n_params] | x0[B*nx] | exo_e[B*steps_e*width_e] ...
 // out.bin: x[B*(T+1)*nx] | u[B*T*nu] | y[B*T*ny] | term_sums[n_terms] (double) | grad[n_params]
 #include "cuda_emu.h"
+EMU_DEFINE_SMEM
 #include NM_SPEC_HEADER
 #include "nm_kernels.cuh"
 

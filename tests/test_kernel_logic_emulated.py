@@ -24,12 +24,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20)")
 
 
-def compile_emulator(name, out, defines=(), tsan=False):
+def compile_emulator(name, out, defines=(), tsan=False, src="ffma_emu.cpp"):
     hdr = build.write_spec(H.configs.build_case(name).plan().c)
     cmd = ["g++", "-std=c++20", "-O1", "-w", "-fpermissive", "-DNM_HOST_EMU", *(["-g", "-fsanitize=thread"] if tsan else []), "-I", os.path.join(ROOT, "tests", "emu"),
            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "neuromancer_b200", "csrc"),
            "-I", "/usr/local/cuda/include", f'-DNM_SPEC_HEADER="{hdr}"', *[f"-D{d}" for d in defines],
-           os.path.join(ROOT, "tests", "emu", "ffma_emu.cpp"), "-o", out, "-lpthread"]
+           os.path.join(ROOT, "tests", "emu", src), "-o", out, "-lpthread"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if tsan and res.returncode != 0 and "tsan" in res.stdout.lower():
         pytest.skip("libtsan not available")
@@ -122,4 +122,24 @@ def test_ffma_kernels_have_no_data_races_under_thread_sanitizer(name, defines, B
     once; three stay in the suite."""
     exe = str(tmp_path / "emu_tsan")
     compile_emulator(name, exe, defines, tsan=True)
+    run_emulated(name, B, exe, str(tmp_path))
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core kernels (nm_tc_kernels.cuh) on the host: tests/emu/tc_ptx_emu.h models tensor memory (128 lanes x 512
+# columns), tcgen05.mma on tf32-truncated operands read through the real shared-memory descriptors (interleaved K-major
+# and SWIZZLE_128B), tcgen05.ld/st, mbarriers with transaction counts, bulk TMA copies and elect.sync; the warps of a
+# block are OS threads, __syncwarp is a real 32-thread barrier.  Owner / control-warp protocol, operand and
+# transposed-tile layouts, ring-slot hand-over, weight-gradient flushes -- all of it runs, forward and adjoint.
+TC = [("c2", 130),                      # policy mode, SOLO owners (two tiles on two CTAs), GELU derivative stash, single-pass TF32 weight gradients
+      ("c1", 130),                      # policy mode, three tensor-core layers through the two-slot weight ring, ReLU masks
+      ("t_vdp_rk4_tanh_clamp", 130),    # policy mode, tanh, relu-clamp bounds
+      ("t_int_rkf_node", 130),          # right-hand-side mode, six stages per step, 3xTF32 weight gradients
+      ("c3", 60)]                       # right-hand-side mode, PAIR owners (named barriers), 60-wide layers
+
+
+@pytest.mark.parametrize("name,B", TC, ids=[c[0] for c in TC])
+def test_tensor_core_kernels_on_the_host_match_the_oracle(name, B, tmp_path):
+    exe = str(tmp_path / "emu_tc")
+    compile_emulator(name, exe, src="tc_emu.cpp")
     run_emulated(name, B, exe, str(tmp_path))
