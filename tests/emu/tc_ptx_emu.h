@@ -67,7 +67,7 @@ inline void fence_after() {}
 inline void wait_ld() {}
 inline void wait_st() {}
 inline void fence_async_smem() {}
-template <int COLS> inline void tmem_alloc(uint32_t* slot_smem) { *slot_smem = 0u; }
+template <int COLS> inline void tmem_alloc(uint32_t* slot_smem) { if ((threadIdx.x & 31u) == 0u) *slot_smem = 0u; }   // warp-collective: one write
 template <int COLS> inline void tmem_dealloc(uint32_t) {}
 // 32x32b shapes: thread i of the warp accesses lane (lane base of the address) + i
 template <int CH> inline void tmem_ld(uint32_t taddr, float (&v)[CH]) {

@@ -143,3 +143,13 @@ def test_tensor_core_kernels_on_the_host_match_the_oracle(name, B, tmp_path):
     exe = str(tmp_path / "emu_tc")
     compile_emulator(name, exe, src="tc_emu.cpp")
     run_emulated(name, B, exe, str(tmp_path))
+
+
+def test_tensor_core_kernels_have_no_data_races_under_thread_sanitizer(tmp_path):
+    """Owner <-> control-warp hand-overs of the tcgen05 kernels (operands in tensor memory, transposed tiles and the
+    weight ring in shared memory) under -fsanitize=thread.  The emulated MMA runs when it is issued, so what this sees
+    are read-after-write hazards (an MMA issued before the owners' stores are ordered by the mbarrier); write-after-read
+    hazards against a still-running asynchronous MMA are outside this model."""
+    exe = str(tmp_path / "emu_tc_tsan")
+    compile_emulator("c2", exe, ("EMU_DEADLOCK_SECONDS=120",), tsan=True, src="tc_emu.cpp")
+    run_emulated("c2", 130, exe, str(tmp_path))
