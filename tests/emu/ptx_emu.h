@@ -6,7 +6,7 @@
 #include <mutex>
 #include <thread>
 #ifndef EMU_DEADLOCK_SECONDS
-#define EMU_DEADLOCK_SECONDS 20
+#define EMU_DEADLOCK_SECONDS 90
 #endif
 
 namespace nm {
