@@ -30,12 +30,13 @@ struct TcMode {
   static constexpr int EVALS = POLICY ? 1 : Tableau<S::INTEG>::NS;          // MLP evaluations per step
   static constexpr int CHK = POLICY ? S::NU : (Tableau<S::INTEG>::NS - 1) * S::NX;   // checkpoint floats per trajectory-step
   static __device__ __forceinline__ const NmMlp& mlp(const NmPlan& p) { if constexpr (POLICY) return p.policy; else return p.rhs_mlp; }
-  // policy input = state and exogenous segments only (no output / preview windows on this path)
+  // policy input = state, output and exogenous segments (no preview windows on this path)
   static constexpr bool segs_ok() {
     int w = 0;
     for (int i = 0; i < S::NSEG; ++i) {
-      if (S::seg_kind(i) != NM_SEG_STATE && S::seg_kind(i) != NM_SEG_EXO) return false;
+      if (S::seg_kind(i) == NM_SEG_PREVIEW) return false;
       if (S::seg_kind(i) == NM_SEG_STATE && S::seg_width(i) != S::NX) return false;
+      if (S::seg_kind(i) == NM_SEG_OUTPUT && (!S::HAS_OUTPUT || S::seg_width(i) != S::NY)) return false;
       w += S::seg_width(i);
     }
     return w == M::sz(0);
@@ -49,7 +50,9 @@ struct TcKCfg {
   static constexpr int NX = S::NX, NU = S::NU;
   static constexpr bool ELIGIBLE_RHS = S::RHS == NM_RHS_MLP && S::Pol::NL == 0 && !S::HAS_OUTPUT && S::ND == 0 && C::shape_ok() &&
                                        C::K(0) == NX + NU && C::N(C::NL - 1) == NX;
-  static constexpr bool ELIGIBLE_POL = MD::POLICY && !S::HAS_OUTPUT && S::ND == 0 && S::ACT_EXO < 0 && NU > 0 && C::shape_ok() &&
+  // (policy mode also carries an output node y = C x and an additive disturbance: both are register math of the
+  // trajectory's thread)
+  static constexpr bool ELIGIBLE_POL = MD::POLICY && S::ACT_EXO < 0 && NU > 0 && C::shape_ok() &&
                                        MD::segs_ok() && C::N(C::NL - 1) == NU;
   static constexpr bool ELIGIBLE = MD::POLICY ? ELIGIBLE_POL : ELIGIBLE_RHS;
   // shared memory of the forward kernel: weight block + barriers/slots; padded so that no more CTAs become
@@ -72,6 +75,9 @@ __device__ __forceinline__ void tc_policy_input(const NmPlan& p, const float* co
     if constexpr (S::seg_kind(s) == NM_SEG_STATE) {
 #pragma unroll
       for (int i = 0; i < W; ++i) in[off + i] = x[i];
+    } else if constexpr (S::seg_kind(s) == NM_SEG_OUTPUT) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) in[off + i] = 0.f;                 // filled by tc_policy_state
     } else {
       constexpr int e = S::seg_index(s);
       const float* __restrict__ src = exo[e] + (b * p.exo[e].steps + t) * W;
@@ -82,18 +88,36 @@ __device__ __forceinline__ void tc_policy_input(const NmPlan& p, const float* co
   });
 }
 
-// overwrite the state segment(s) of a policy input whose exogenous entries were fetched one step ahead
+// overwrite the state / output segment(s) of a policy input whose exogenous entries were fetched one step ahead
 template <class S, int K0>
-__device__ __forceinline__ void tc_policy_state(const float (&x)[S::NX], float (&in)[K0]) {
+__device__ __forceinline__ void tc_policy_state(const float (&x)[S::NX], const float (&y)[S::NY > 0 ? S::NY : 1], float (&in)[K0]) {
   int off = 0;
   static_for<0, S::NSEG>([&](auto sc) {
     constexpr int s = decltype(sc)::value;
     if constexpr (S::seg_kind(s) == NM_SEG_STATE) {
 #pragma unroll
       for (int i = 0; i < S::seg_width(s); ++i) in[off + i] = x[i];
+    } else if constexpr (S::seg_kind(s) == NM_SEG_OUTPUT) {
+#pragma unroll
+      for (int i = 0; i < S::seg_width(s); ++i) in[off + i] = y[i];
     }
     off += S::seg_width(s);
   });
+}
+// y = C x (reference: the output node of grid_response.ipynb cell 7)
+template <class S>
+__device__ __forceinline__ void tc_output(const NmPlan& p, const float (&x)[S::NX], float (&y)[S::NY > 0 ? S::NY : 1]) {
+#pragma unroll
+  for (int j = 0; j < (S::NY > 0 ? S::NY : 1); ++j) y[j] = 0.f;
+  if constexpr (S::HAS_OUTPUT) {
+#pragma unroll
+    for (int j = 0; j < S::NY; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < S::NX; ++i) s = fmaf(x[i], p.C[j * S::NX + i], s);
+      y[j] = s;
+    }
+  }
 }
 
 template <class S>
@@ -245,13 +269,13 @@ __global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const 
   double* red = reinterpret_cast<double*>(smem);                                      // end-of-kernel reduction scratch (weights dead)
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
-  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, 0);
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
   constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   if (tid == 0) {
     vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = p.nsteps + 1; vt.D[NM_VAR_X] = NX;
     vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = p.nsteps; vt.D[NM_VAR_U] = NU;
-    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = p.nsteps; vt.D[NM_VAR_Y] = 0;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = p.nsteps; vt.D[NM_VAR_Y] = S::NY;
     for (int e = 0; e < NM_MAX_EXO; ++e) {
       vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
     }
@@ -298,10 +322,24 @@ __global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const 
       float xn[NX];
       if constexpr (MD::POLICY) {
         // closed loop: u_t = bounds(policy([x_t | exo_t])), x_{t+1} = dynamics(x_t, u_t) in registers
-        float in[K0], o[NUA], dnone[1] = {0.f};
+        float in[K0], o[NUA], yv[S::NY > 0 ? S::NY : 1], dv_[S::ND > 0 ? S::ND : 1];
+        tc_output<S>(p, x, yv);
+        if constexpr (S::HAS_OUTPUT) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < S::NY; ++j) args.y_traj[(b * T + t) * S::NY + j] = yv[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < (S::ND > 0 ? S::ND : 1); ++j) dv_[j] = 0.f;
+        if constexpr (S::ND > 0) {
+          const float* dsrc = args.exo[S::DIST_EXO] + (b * p.exo[S::DIST_EXO].steps + t) * S::ND;
+#pragma unroll
+          for (int j = 0; j < S::ND; ++j) dv_[j] = __ldg(dsrc + j);
+        }
 #pragma unroll
         for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
-        tc_policy_state<S, K0>(x, in);
+        tc_policy_state<S, K0>(x, yv, in);
         if (t + 1 < T) tc_policy_input<S, K0>(p, args.exo, b, t + 1, x, in_pre);   // exogenous inputs one step ahead
         tc_mlp_forward<M, MD::NOUT>(sm_w, tmem, lane_base, &bars[1], phase, act_prm, in, o, tid);
 #pragma unroll
@@ -314,7 +352,7 @@ __global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const 
             for (int j = 0; j < NU; ++j) args.chk[(b * T + t) * NU + j] = o[j];
           }
         }
-        Dyn<S>::step(p, x, u, dnone, xn);
+        Dyn<S>::step(p, x, u, dv_, xn);
       } else {
         constexpr int NS = Tableau<S::INTEG>::NS;
         if constexpr (NU > 0 && S::ACT_EXO >= 0) {               // open loop: the action comes from the data
@@ -475,11 +513,11 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
   VarTable& vt = *reinterpret_cast<VarTable*>(bars + 20);
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
-  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, 0);
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
   const int T = p.nsteps;
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   const bool pre = !fused && args.G_x != nullptr;
-  const int g_row = (T + 1) * NX + T * NU;
+  const int g_row = (T + 1) * NX + T * (NU + S::NY), g_yoff = (T + 1) * NX + T * NU;
   int tb_mask = 0;
   for (int k = 0; k < p.n_terms; ++k) {
     const NmTerm& tm = p.terms[k];
@@ -496,7 +534,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
   if (tid == 0) {
     vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
     vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
-    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = 0;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = S::NY;
     for (int e = 0; e < NM_MAX_EXO; ++e) {
       vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
     }
@@ -792,16 +830,20 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           { TCP_T0(); flush(); TCP_ADD(o_flush); }
         }
         ++step_cnt;
-        float x[NX], u[NUA], gx[NX], gtx[NX];
+        constexpr int NYA = S::NY > 0 ? S::NY : 1;
+        float x[NX], u[NUA], gx[NX], gtx[NX], yv[NYA], gty[NYA];
         float o_cur[POLICY ? NUA : 1], in_cur[POLICY ? K0 : 1];
 #pragma unroll
         for (int i = 0; i < NX; ++i) { x[i] = x_pre[i]; gtx[i] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < NYA; ++j) { yv[j] = 0.f; gty[j] = 0.f; }
         if constexpr (POLICY) {
 #pragma unroll
           for (int j = 0; j < NU; ++j) o_cur[j] = o_pre[j];
 #pragma unroll
           for (int q = 0; q < K0; ++q) in_cur[q] = in_pre[q];
-          tc_policy_state<S, K0>(x, in_cur);
+          tc_output<S>(p, x, yv);
+          tc_policy_state<S, K0>(x, yv, in_cur);
         }
         if (t > 0) {
 #pragma unroll
@@ -968,6 +1010,22 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
                 }
               }
             }
+                if constexpr (S::NY > 0) {                    // loss-term gradient w.r.t. y_t (output node y = C x)
+                  if (valid) {
+                    if (pre) {
+#pragma unroll
+                      for (int j = 0; j < S::NY; ++j) gty[j] += __ldg(args.G_x + b * g_row + g_yoff + t * S::NY + j);
+                      if (tb_mask & 4) term_grad_accum_ool<NYA, 2>(p, vt, coef, b, NM_VAR_Y, t, S::NY, gty);
+                    } else {
+                      if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_Y, S::NY, NYA>(p, vtc, coef, b, t, gty); }
+                      else term_grad_accum_ool<NYA, 0>(p, vt, coef, b, NM_VAR_Y, t, S::NY, gty);
+                      if (args.gy_ext != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < S::NY; ++j) gty[j] += __ldg(args.gy_ext + (b * T + t) * S::NY + j);
+                      }
+                    }
+                  }
+                }
                 TCP_ADD(o_tx);
               }
             }
@@ -1170,6 +1228,9 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
               if constexpr (S::seg_kind(sg) == NM_SEG_STATE) {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) gx[i] += gin[off + i];
+              } else if constexpr (S::seg_kind(sg) == NM_SEG_OUTPUT) {
+#pragma unroll
+                for (int i = 0; i < S::NY; ++i) gty[i] += gin[off + i];
               }
               off += S::seg_width(sg);
             });
@@ -1185,6 +1246,15 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           }
         }
         // ---- co-state of step t: dynamics / policy part + the loss-term gradient computed in the MMA wait window
+        if constexpr (S::HAS_OUTPUT) {                                     // y_t = C x_t
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            float sC = 0.f;
+#pragma unroll
+            for (int j = 0; j < S::NY; ++j) sC = fmaf(p.C[j * NX + i], gty[j], sC);
+            gx[i] += sC;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] + gtx[i] : 0.f;
       }

@@ -135,6 +135,7 @@ TC = [("c2", 130),                      # policy mode, SOLO owners (two tiles on
       ("c1", 130),                      # policy mode, three tensor-core layers through the two-slot weight ring, ReLU masks
       ("t_vdp_rk4_tanh_clamp", 130),    # policy mode, tanh, relu-clamp bounds
       ("t_int_rkf_node", 130),          # right-hand-side mode, six stages per step, 3xTF32 weight gradients
+      ("t_ssm_softplus", 130),          # policy mode with an output node y = C x, a disturbance and [y | exo | x] inputs (FFMA by default: 10-wide)
       ("c3", 60)]                       # right-hand-side mode, PAIR owners (named barriers), 60-wide layers
 
 
