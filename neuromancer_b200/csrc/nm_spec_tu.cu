@@ -99,12 +99,13 @@ static_assert(KCF::FITS_FWD && KC::FITS_BWD, "shape class does not fit in shared
 // tensor pipe to pay (one M=128 MMA costs >= 44 cycles whatever its N: measured, profiles/r01_tcgen05_findings.md)
 using TK = TcKCfg<NM_SPEC_NAME>;
 #ifdef NM_TUNE_TC
-constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && (NM_TUNE_TC != 0);
+constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && (NM_TUNE_TC != 0) && (KC::HOIST == TK::MD::HOIST);
 #else
 // right-hand-side mode: from ~48 hidden units up (below, the 44-cycle MMA floor loses to FFMA over the 4+ evaluations
 // of a step); policy mode: from 16 up -- one evaluation per step, and what the tensor pipe removes is not pipe time
 // but issue slots (FFMA + LDS are ~60 % of the FFMA kernels' instructions on the narrow policies)
-constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && TK::C::max_hidden() >= (TK::MD::POLICY ? 16 : 48);
+// (with the first-layer hoist compiled in, both kernel families have to agree on it: the FFMA adjoint is the fallback)
+constexpr bool kTcFwd = TK::ELIGIBLE && TK::FITS_FWD && TK::C::max_hidden() >= (TK::MD::POLICY ? 16 : 48) && (KC::HOIST == TK::MD::HOIST);
 #endif
 
 // launch helpers as class templates so that the tensor-core kernels are only instantiated for eligible classes
@@ -164,7 +165,7 @@ template <class Sp> struct TcBwdEligible<Sp, true> { static constexpr bool value
 // the tensor-core adjoint needs the stage checkpoints written by the forward kernel; without them the FFMA adjoint runs
 constexpr bool kTcBwd = kTcFwd && TcBwdEligible<NM_SPEC_NAME, kTcFwd>::value;
 
-constexpr bool kHoist = KC::HOIST && KCF::HOIST && !kTcFwd;
+constexpr bool kHoist = KC::HOIST && KCF::HOIST;
 constexpr size_t hoist_bytes(const NmPlan* p, int64_t B) { return kHoist ? ((size_t(B) * size_t(p->nsteps) * size_t(KC::N0) * sizeof(float) + 255) & ~size_t(255)) : 0; }
 constexpr size_t kExoSmem = exo_gemm_smem_bytes<SB>();
 // the hoisted configuration addresses the same parameter block as the plain one
@@ -211,7 +212,10 @@ int device_info(DeviceInfo** out) {
 constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 constexpr size_t kWprepFfma = size_t(KC::W_FLOATS_ALL + KC::EXO_W_FLOATS > 0 ? KC::W_FLOATS_ALL + KC::EXO_W_FLOATS : 4) * 4;
 constexpr size_t kWprepTc = TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES > (kTcFwd ? TK::FWD_W_BYTES : 0) ? TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES : (kTcFwd ? TK::FWD_W_BYTES : 0);
-constexpr size_t kWprepBytes = align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
+// tensor-core class with the hoist: the FFMA-layout block (exogenous rows for the hoist GEMM) lives BEHIND the
+// tensor-core images while the tensor-core kernels run; every other class keeps one region
+constexpr size_t kFfmaRegionOff = (kHoist && kTcFwd) ? align256(kWprepTc) : 0;
+constexpr size_t kWprepBytes = (kHoist && kTcFwd) ? align256(kWprepTc) + align256(kWprepFfma) : align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
 constexpr int kFwdTile = kTcFwd ? 128 : SF::TILE;
 
 int check_plan(const NmPlan* p) {
@@ -265,7 +269,8 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   float* wprep = reinterpret_cast<float*>(ws);
   c->grid = grid;
   c->term_partials = reinterpret_cast<double*>(ws + kWprepBytes);
-  if (!kTcFwd) launch_prep(p, c->params, wprep, c->stream);
+  float* wprep_ffma = reinterpret_cast<float*>(ws + kFfmaRegionOff);
+  if (!kTcFwd || kHoist) launch_prep(p, c->params, wprep_ffma, c->stream);
   FwdArgs a{};
   a.term_partials = c->term_partials; a.fused_terms = c->fused_terms;
   a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
@@ -281,7 +286,7 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
     for (int e = 0; e < NM_MAX_EXO; ++e) ep.p[e] = a.exo[e];
     const int64_t row_tiles = (c->B * p->nsteps + SB::TILE - 1) / SB::TILE;
     int ggrid = d->sms * 2; if (ggrid > row_tiles) ggrid = int(row_tiles); if (ggrid < 1) ggrid = 1;
-    nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep, ep, E, c->B);
+    nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep_ffma, ep, E, c->B);
     a.pre = E;
     c->extra_launches = 1;
   }

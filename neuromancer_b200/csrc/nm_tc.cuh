@@ -171,6 +171,7 @@ struct TcCfg {
   static constexpr bool BIAS = M::BIAS;
   static constexpr int K(int l) { return M::sz(l); }
   static constexpr int N(int l) { return M::sz(l + 1); }
+  static constexpr int KW(int l) { return l == 0 ? KW0Of<M>::value : M::sz(l); }   // fan-in in the parameter layout (HoistedMlp)
   static constexpr bool is_tc(int l) { return l >= 1 && l <= NL - 2; }
   static constexpr int kaug(int l) { return K(l) + (BIAS ? 1 : 0); }      // + constant-one column carrying the bias
   static constexpr int kp(int l) { return round_up(kaug(l), 8); }          // MMA K steps of 8
@@ -212,13 +213,13 @@ struct TcCfg {
 template <class M>
 __device__ void prep_tc_fwd(const float* __restrict__ params, float* __restrict__ dst, int gtid, int gthreads) {
   using C = TcCfg<M>;
-  auto p_off = [](int l) { int o = 0; for (int i = 0; i < l; ++i) o += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0); return o; };
+  auto p_off = [](int l) { int o = 0; for (int i = 0; i < l; ++i) o += C::N(i) * C::KW(i) + (C::BIAS ? C::N(i) : 0); return o; };
   {   // first layer
     const float* W = params + p_off(0);
-    const float* b = W + C::N(0) * C::K(0);
+    const float* b = W + C::N(0) * C::KW(0);
     for (int idx = gtid; idx < C::N(0) * C::R0; idx += gthreads) {
       const int n = idx / C::R0, c = idx % C::R0;
-      dst[C::first_off() + idx] = c < C::K(0) ? W[n * C::K(0) + c] : (c == C::K(0) && C::BIAS ? b[n] : 0.f);
+      dst[C::first_off() + idx] = c < C::K(0) ? W[n * C::KW(0) + c] : (c == C::K(0) && C::BIAS ? b[n] : 0.f);
     }
   }
   {   // last layer
@@ -340,13 +341,13 @@ template <class M>
 __device__ void prep_tc_bwd(const float* __restrict__ params, float* __restrict__ dst, int gtid, int gthreads) {
   using C = TcCfg<M>;
   using B = TcBwdCfg<M>;                       // the prepared block does not depend on the weight-gradient mode
-  auto p_off = [](int l) { int o = 0; for (int i = 0; i < l; ++i) o += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0); return o; };
+  auto p_off = [](int l) { int o = 0; for (int i = 0; i < l; ++i) o += C::N(i) * C::KW(i) + (C::BIAS ? C::N(i) : 0); return o; };
   {
     const float* W = params + p_off(0);
-    const float* b = W + C::N(0) * C::K(0);
+    const float* b = W + C::N(0) * C::KW(0);
     for (int idx = gtid; idx < C::N(0) * C::R0; idx += gthreads) {
       const int n = idx / C::R0, c = idx % C::R0;
-      dst[C::first_off() + idx] = c < C::K(0) ? W[n * C::K(0) + c] : (c == C::K(0) && C::BIAS ? b[n] : 0.f);
+      dst[C::first_off() + idx] = c < C::K(0) ? W[n * C::KW(0) + c] : (c == C::K(0) && C::BIAS ? b[n] : 0.f);
     }
   }
   {

@@ -22,13 +22,35 @@ namespace nm {
 //                dynamics are thread-per-trajectory register math (Dyn<S>).  The forward kernel keeps the RAW policy
 //                output o_t as the checkpoint, so that the adjoint knows u_t = bounds(o_t) and the cotangent of o_t
 //                before it starts the step's only MLP evaluation.
+#ifndef NM_TUNE_HOIST
+#define NM_TUNE_HOIST 0
+#endif
+// exogenous first-layer hoist (nm_kernels.cuh, HoistedMlp) for a policy: every exogenous segment follows the last
+// state / output segment; returns the width of the leading (contracted) part, or 0 when the class is not eligible
+template <class S>
+constexpr int tc_hoist_ks() {
+  if (S::Pol::NL < 2 || S::Pol::sz(1) % 4 != 0) return 0;
+  int ks = 0, seen_exo = 0;
+  for (int i = 0; i < S::NSEG; ++i) {
+    if (S::seg_kind(i) == NM_SEG_PREVIEW) return 0;
+    if (S::seg_kind(i) == NM_SEG_EXO) { seen_exo = 1; if (S::seg_width(i) % 4 != 0) return 0; }
+    else { if (seen_exo) return 0; ks += S::seg_width(i); }
+  }
+  return (seen_exo && ks >= 1) ? ks : 0;
+}
 template <class S>
 struct TcMode {
   static constexpr bool POLICY = S::RHS != NM_RHS_MLP && S::Pol::NL >= 3;
-  using M = std::conditional_t<POLICY, typename S::Pol, typename S::RhsM>;
+  static constexpr bool HOIST = POLICY && (NM_TUNE_HOIST != 0) && tc_hoist_ks<S>() > 0;
+  using PolM = std::conditional_t<HOIST, HoistedMlp<typename S::Pol, (tc_hoist_ks<S>() > 0 ? tc_hoist_ks<S>() : 1)>, typename S::Pol>;
+  using M = std::conditional_t<POLICY, PolM, typename S::RhsM>;
+  static constexpr int N0 = M::sz(1);                                        // width of the first hidden layer (rows of E / dZ_1)
   static constexpr int NOUT = POLICY ? S::NU : S::NX;                       // width of the MLP output
   static constexpr int EVALS = POLICY ? 1 : Tableau<S::INTEG>::NS;          // MLP evaluations per step
-  static constexpr int CHK = POLICY ? S::NU : (Tableau<S::INTEG>::NS - 1) * S::NX;   // checkpoint floats per trajectory-step
+  // checkpoint floats per trajectory-step; policy mode: [B*T rows of E (hoist only, N0 floats) | B*T raw outputs o_t (NU floats)]
+  static constexpr int E_ROW = HOIST ? N0 : 0;
+  static constexpr int CHK = POLICY ? S::NU + E_ROW : (Tableau<S::INTEG>::NS - 1) * S::NX;
+  template <class T_> static __device__ __forceinline__ T_* o_base(T_* chk, int64_t B, int T) { return chk + int64_t(E_ROW) * B * T; }
   static __device__ __forceinline__ const NmMlp& mlp(const NmPlan& p) { if constexpr (POLICY) return p.policy; else return p.rhs_mlp; }
   // policy input = state, output and exogenous segments (no preview windows on this path)
   static constexpr bool segs_ok() {
@@ -39,7 +61,7 @@ struct TcMode {
       if (S::seg_kind(i) == NM_SEG_OUTPUT && (!S::HAS_OUTPUT || S::seg_width(i) != S::NY)) return false;
       w += S::seg_width(i);
     }
-    return w == M::sz(0);
+    return w == (POLICY ? S::Pol::sz(0) : M::sz(0));
   }
 };
 
@@ -78,7 +100,7 @@ __device__ __forceinline__ void tc_policy_input(const NmPlan& p, const float* co
     } else if constexpr (S::seg_kind(s) == NM_SEG_OUTPUT) {
 #pragma unroll
       for (int i = 0; i < W; ++i) in[off + i] = 0.f;                 // filled by tc_policy_state
-    } else {
+    } else if constexpr (!TcMode<S>::HOIST) {                         // (hoisted: the exogenous segments enter through E)
       constexpr int e = S::seg_index(s);
       const float* __restrict__ src = exo[e] + (b * p.exo[e].steps + t) * W;
 #pragma unroll
@@ -128,10 +150,11 @@ __global__ void nm_tc_prep_fwd_kernel(const __grid_constant__ NmPlan plan, const
 
 // One MLP evaluation on the tile: in[K0] (registers) -> out[NOUT] (registers).  All 128 threads call it.
 //   `phase` is the parity of the MMA-completion mbarrier (flipped per tensor-core layer).
+//   `pre` != nullptr (hoisted first layer): z_1 = pre[n] + W[:, :K0] in   (pre = E row: bias + exogenous part)
 template <class M, int NOUT>
 __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint32_t tmem, uint32_t lane_base, uint64_t* mma_bar,
                                                uint32_t& phase, float act_prm, const float (&in)[tc::TcCfg<M>::K(0)],
-                                               float (&out)[NOUT], int tid) {
+                                               float (&out)[NOUT], int tid, const float* __restrict__ pre = nullptr) {
   using C = tc::TcCfg<M>;
   static_assert(NOUT == C::N(C::NL - 1), "output width");
   constexpr int K0 = C::K(0), N0 = C::N(0), NL = C::NL;
@@ -151,7 +174,7 @@ __device__ __forceinline__ void tc_mlp_forward(const float* __restrict__ W, uint
         if (n < N0) {
           float w[C::R0];
           ld_vec<C::R0>(w, W0 + n * C::R0);
-          float z = C::BIAS ? w[K0] : 0.f;
+          float z = pre != nullptr ? __ldg(pre + n) : (C::BIAS ? w[K0] : 0.f);
 #pragma unroll
           for (int q = 0; q < K0; ++q) z = fmaf(w[q], in[q], z);
           a = act_fwd<M::ACT>(z, act_prm);
@@ -341,7 +364,8 @@ __global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const 
         for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
         tc_policy_state<S, K0>(x, yv, in);
         if (t + 1 < T) tc_policy_input<S, K0>(p, args.exo, b, t + 1, x, in_pre);   // exogenous inputs one step ahead
-        tc_mlp_forward<M, MD::NOUT>(sm_w, tmem, lane_base, &bars[1], phase, act_prm, in, o, tid);
+        tc_mlp_forward<M, MD::NOUT>(sm_w, tmem, lane_base, &bars[1], phase, act_prm, in, o, tid,
+                                    MD::HOIST ? args.pre + (b * T + t) * int64_t(MD::N0) : nullptr);
 #pragma unroll
         for (int j = 0; j < NU; ++j) u[j] = bounds_fwd<M::BOUNDS>(o[j], p.policy.bmin[j], p.policy.bmax[j]);
         if (valid) {
@@ -349,7 +373,7 @@ __global__ void __launch_bounds__(128, tc_fwd_minb<S>()) nm_tc_fwd_kernel(const 
           for (int j = 0; j < NU; ++j) args.u_traj[(b * T + t) * NU + j] = u[j];
           if (args.chk != nullptr) {
 #pragma unroll
-            for (int j = 0; j < NU; ++j) args.chk[(b * T + t) * NU + j] = o[j];
+            for (int j = 0; j < NU; ++j) MD::o_base(args.chk, args.B, T)[(b * T + t) * NU + j] = o[j];
           }
         }
         Dyn<S>::step(p, x, u, dv_, xn);
@@ -759,7 +783,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
         constexpr int l = decltype(lc)::value;
         constexpr int Kl = C::K(l), Nl = C::N(l), KA = C::kaug(l), CH = 8;
         int off = 0;
-        for (int i = 0; i < l; ++i) off += C::N(i) * C::K(i) + (C::BIAS ? C::N(i) : 0);
+        for (int i = 0; i < l; ++i) off += C::N(i) * C::KW(i) + (C::BIAS ? C::N(i) : 0);
         float* dst = grhs + off;
         // tcgen05.ld is warp-collective (.sync.aligned): every owner of the half executes it, rows n >= N(l) are dropped
 #pragma unroll 1
@@ -771,8 +795,8 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const int k = c0 + i;
-              if (k < Kl) atomicAdd(dst + m_ * Kl + k, v[i]);              // result unused: RED, no round trip
-              else if (k == Kl && C::BIAS) atomicAdd(dst + Nl * Kl + m_, v[i]);
+              if (k < Kl) atomicAdd(dst + m_ * C::KW(l) + k, v[i]);        // result unused: RED, no round trip
+              else if (k == Kl && C::BIAS) atomicAdd(dst + Nl * C::KW(l) + m_, v[i]);
             }
           }
         }
@@ -805,7 +829,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
       float o_pre[POLICY ? NUA : 1], in_pre[POLICY ? K0 : 1];
       if constexpr (POLICY) {
 #pragma unroll
-        for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + (T - 1)) * NU + j);
+        for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(MD::o_base(args.chk, args.B, T) + (b * T + (T - 1)) * NU + j);
         tc_policy_input<S, K0>(p, args.exo, b, T - 1, x_pre, in_pre);
       }
       if (valid) {
@@ -850,7 +874,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
           for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
           if constexpr (POLICY) {
 #pragma unroll
-            for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + t - 1) * NU + j);
+            for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(MD::o_base(args.chk, args.B, T) + (b * T + t - 1) * NU + j);
             tc_policy_input<S, K0>(p, args.exo, b, t - 1, x, in_pre);     // (state entries are placeholders)
           }
         }
@@ -958,7 +982,7 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
                   if (n < N0) {
                     float w[C::R0];
                     ld_vec<C::R0>(w, W0 + n * C::R0);
-                    float z = C::BIAS ? w[K0] : 0.f;
+                    float z = MD::HOIST ? __ldg(args.pre + (b * T + t) * int64_t(MD::N0) + n) : (C::BIAS ? w[K0] : 0.f);
 #pragma unroll
                     for (int q = 0; q < K0; ++q) z = fmaf(w[q], in[q], z);
                     tc::act_ad<M::ACT>(z, act_prm, a, d);
@@ -1198,7 +1222,10 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
                     const int n = c0 + i;
-                    if (n < Kl) { const float dz = keep_dz[own_idx(ci, CH, SOLO)][i]; const float dh_ = tc::tf32_hi(dz); tstore(B::DT_OFF, B::RD, n, dh_, dz - dh_); }
+                    if (n < Kl) {
+                      const float dz = keep_dz[own_idx(ci, CH, SOLO)][i]; const float dh_ = tc::tf32_hi(dz); tstore(B::DT_OFF, B::RD, n, dh_, dz - dh_);
+                      if constexpr (MD::HOIST) { if (valid) args.dz1[(b * T + t) * int64_t(MD::N0) + n] = dz; }
+                    }
                   }
                 }
               });

@@ -10,13 +10,27 @@ EMU_DEFINE_SMEM
 #ifndef EMU_GRID
 #define EMU_GRID 2
 #endif
+#ifndef NM_TUNE_HOIST
+#define NM_TUNE_HOIST 0
+#endif
 
 using namespace nm;
 using S = NM_SPEC_NAME;
+// FFMA-side view of the class (weight preparation and the hoist GEMMs run through it, as in nm_spec_tu.cu)
+template <class Shape>
+struct Tiled : Shape {
+  static constexpr int TILE = 128, THREADS = 256;
+  static constexpr bool W_SMEM = false;
+  static constexpr int MINB_FWD = 1, MINB_BWD = 1;
+  static constexpr bool HOIST = NM_TUNE_HOIST != 0;
+};
+using SB = Tiled<NM_SPEC_NAME>;
+using KC = KCfg<SB>;
 using TK = TcKCfg<S>;
 using BK = TcBKCfg<S>;
 using MD = TcMode<S>;
 static_assert(TK::ELIGIBLE && TK::FITS_FWD && BK::ELIGIBLE, "shape class is not on the tensor-core path");
+static_assert(KC::HOIST == MD::HOIST, "the FFMA and the tensor-core kernels disagree on the first-layer hoist");
 static_assert(BK::SMEM_BYTES <= 4 * 64 * 1024 && TK::FWD_SMEM_BYTES <= 4 * 64 * 1024, "emulated shared memory window too small");
 
 template <class T> static std::vector<T> read_vec(FILE* f, size_t n) {
@@ -49,7 +63,17 @@ int main(int argc, char** argv) {
   std::vector<double> partials(size_t(grid) * NM_MAX_TERMS, 0.0);
   std::vector<float> gpart(size_t(grid) * std::max<int64_t>(plan.n_params, 1), 0.f);
 
+  // first-layer hoist: E = bias + exogenous part, for every (trajectory, step), into the head of the checkpoint buffer
+  std::vector<float> wprep_ffma(size_t(KC::W_FLOATS_ALL + KC::EXO_W_FLOATS) + 16, 0.f), G1(MD::HOIST ? size_t(B) * T * MD::N0 : 1, 0.f);
+  ExoPtrs ep{};
+  for (int e = 0; e < plan.n_exo; ++e) ep.p[e] = exo[e].data();
+  if constexpr (MD::HOIST) {
+    emu::launch(2, 256, [&] { nm_prep_kernel<SB>(plan, params.data(), wprep_ffma.data()); });
+    emu::launch(grid, SB::THREADS, [&] { nm_exo_gemm_fwd_kernel<SB>(plan, wprep_ffma.data(), ep, chk.data(), B); });
+  }
+
   FwdArgs fa{};
+  fa.pre = chk.data();
   fa.params = params.data(); fa.wprep = wprep.data(); fa.x0 = x0.data();
   for (int e = 0; e < plan.n_exo; ++e) fa.exo[e] = exo[e].data();
   fa.x_traj = x.data(); fa.u_traj = u.data(); fa.y_traj = y.data(); fa.chk = chk.data();
@@ -63,8 +87,10 @@ int main(int argc, char** argv) {
   ba.x_traj = x.data(); ba.u_traj = u.data(); ba.y_traj = y.data(); ba.chk = chk.data();
   ba.grad_scalars = nullptr; ba.grad_partials = gpart.data(); ba.grad_x0 = nullptr; ba.fused_terms = 1;
   ba.B = B; ba.b_total = B; ba.num_tiles = tiles;
+  ba.pre = chk.data(); ba.dz1 = G1.data();
   emu::launch(16, 256, [&] { nm_tc_prep_bwd_kernel<S>(plan, params.data(), wprep.data()); });
   emu::launch(grid, BK::THREADS, [&] { nm_tc_bwd_kernel<S>(plan, ba); });
+  if constexpr (MD::HOIST) emu::launch(grid, SB::THREADS, [&] { nm_exo_gemm_bwd_kernel<SB>(plan, ep, G1.data(), gpart.data(), B); });
 
   std::vector<double> tsum(std::max<int>(plan.n_terms, 1), 0.0);
   for (int k = 0; k < plan.n_terms; ++k)

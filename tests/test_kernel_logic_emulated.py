@@ -154,3 +154,13 @@ def test_tensor_core_kernels_have_no_data_races_under_thread_sanitizer(tmp_path)
     exe = str(tmp_path / "emu_tc_tsan")
     compile_emulator("c2", exe, ("EMU_DEADLOCK_SECONDS=120",), tsan=True, src="tc_emu.cpp")
     run_emulated("c2", 130, exe, str(tmp_path))
+
+
+def test_first_layer_hoist_on_the_tensor_core_kernels_matches_the_oracle(tmp_path):
+    """c4 with NM_TUNE_HOIST=1 is a policy-mode tensor-core class: E from nm_exo_gemm_fwd_kernel at the head of the
+    checkpoint buffer, a 1-input 32-wide policy with E as per-step pre-activation, y = C x and the disturbance as register
+    math, dZ_1 stored by the adjoint's layer-1 epilogue, dW_0[:, exo] from nm_exo_gemm_bwd_kernel."""
+    exe = str(tmp_path / "emu_tc_hoist")
+    compile_emulator("c4", exe, ("NM_TUNE_HOIST=1",), src="tc_emu.cpp")
+    for B in (1, 130):
+        run_emulated("c4", B, exe, str(tmp_path))
