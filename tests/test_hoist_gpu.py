@@ -37,6 +37,18 @@ for B in (1, 127, 300):
     assert H.rel_err(got["loss"], ref["loss"].detach()) <= 1e-4, (name, B)
     for i, (a, b) in enumerate(zip(got["grads"], ref["grads"])):
         assert H.rel_err(a, b) <= 1e-4, (name, B, i, H.rel_err(a, b))
+# the tensor-core adjoint of the hoisted class (c4: policy mode + E pre-activation + dZ_1 store), forced at a small batch
+import os
+if "bwd[tcgen05" in info:
+    os.environ["NM_TC_BWD"] = "1"
+    case = H.make_case(name, "cuda:0", seed=3)
+    batch_cpu = case.make_batch(300, "cpu", 9)
+    params_cpu = [p.detach().cpu().clone() for p in case.plan_params]
+    batch = {{k: (v.to("cuda:0") if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}}
+    got = H.product_run(case, batch)
+    ref = H.oracle_run(name, params_cpu, batch_cpu)
+    for i, (a, b) in enumerate(zip(got["grads"], ref["grads"])):
+        assert H.rel_err(a, b) <= 1e-4, (name, "tensor-core adjoint", i, H.rel_err(a, b))
 print("hoist parity ok", name)
 """
 
