@@ -167,6 +167,15 @@ constexpr bool kTcBwd = kTcFwd && TcBwdEligible<NM_SPEC_NAME, kTcFwd>::value;
 
 constexpr bool kHoist = KC::HOIST && KCF::HOIST;
 constexpr size_t hoist_bytes(const NmPlan* p, int64_t B) { return kHoist ? ((size_t(B) * size_t(p->nsteps) * size_t(KC::N0) * sizeof(float) + 255) & ~size_t(255)) : 0; }
+// forward hoist GEMM on the tensor cores (nm_exo_gemm_tc_fwd_kernel) when the class allows it; its weight images
+// live behind the other prepared blocks
+#ifndef NM_TUNE_HOIST_TCGEMM
+#define NM_TUNE_HOIST_TCGEMM 1
+#endif
+template <bool ON> constexpr bool exo_tc_ok() { if constexpr (ON) return ExoTcCfg<SB>::OK; else return false; }
+constexpr bool kExoTc = exo_tc_ok<kHoist>() && (NM_TUNE_HOIST_TCGEMM != 0);
+template <bool ON> constexpr size_t exo_tc_wbytes() { if constexpr (ON) return (size_t(ExoTcCfg<SB>::W_FLOATS) * 4 + 255) & ~size_t(255); else return 0; }
+template <bool ON> constexpr size_t exo_tc_smem() { if constexpr (ON) return ExoTcCfg<SB>::SMEM_BYTES; else return 0; }
 constexpr size_t kExoSmem = exo_gemm_smem_bytes<SB>();
 // the hoisted configuration addresses the same parameter block as the plain one
 template <class K_, class Tl> constexpr bool hoist_layout_ok() {       // (dependent on K_: only instantiated for hoisted classes)
@@ -200,6 +209,9 @@ int device_info(DeviceInfo** out) {
     if constexpr (kHoist) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_fwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExoSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_bwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExoSmem);
+      if constexpr (kExoTc) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_tc_fwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exo_tc_smem<kExoTc>());
+      }
     }
     if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
     if (d.occ_fwd < 1 || d.occ_bwd < 1) { nm_set_error("kernel does not fit on an SM (occupancy 0)"); return NM_ERR_CUDA; }
@@ -215,7 +227,9 @@ constexpr size_t kWprepTc = TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES > (kTcFwd ? TK:
 // tensor-core class with the hoist: the FFMA-layout block (exogenous rows for the hoist GEMM) lives BEHIND the
 // tensor-core images while the tensor-core kernels run; every other class keeps one region
 constexpr size_t kFfmaRegionOff = (kHoist && kTcFwd) ? align256(kWprepTc) : 0;
-constexpr size_t kWprepBytes = (kHoist && kTcFwd) ? align256(kWprepTc) + align256(kWprepFfma) : align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
+constexpr size_t kBaseWprepBytes = (kHoist && kTcFwd) ? align256(kWprepTc) + align256(kWprepFfma) : align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
+constexpr size_t kExoTcOff = kBaseWprepBytes;
+constexpr size_t kWprepBytes = kBaseWprepBytes + exo_tc_wbytes<kExoTc>();
 constexpr int kFwdTile = kTcFwd ? 128 : SF::TILE;
 
 int check_plan(const NmPlan* p) {
@@ -286,9 +300,18 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
     for (int e = 0; e < NM_MAX_EXO; ++e) ep.p[e] = a.exo[e];
     const int64_t row_tiles = (c->B * p->nsteps + SB::TILE - 1) / SB::TILE;
     int ggrid = d->sms * 2; if (ggrid > row_tiles) ggrid = int(row_tiles); if (ggrid < 1) ggrid = 1;
-    nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep_ffma, ep, E, c->B);
+    if constexpr (kExoTc) {
+      float* wexo = reinterpret_cast<float*>(ws + kExoTcOff);
+      const int64_t tiles128 = (c->B * p->nsteps + 127) / 128;
+      int tgrid = d->sms * 2; if (tgrid > tiles128) tgrid = int(tiles128); if (tgrid < 1) tgrid = 1;
+      nm_exo_tc_prep_kernel<SB><<<8, 256, 0, c->stream>>>(*p, c->params, wexo);
+      nm_exo_gemm_tc_fwd_kernel<SB><<<tgrid, 128, exo_tc_smem<kExoTc>(), c->stream>>>(*p, wexo, ep, E, c->B);
+      c->extra_launches = 2;
+    } else {
+      nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep_ffma, ep, E, c->B);
+      c->extra_launches = 1;
+    }
     a.pre = E;
-    c->extra_launches = 1;
   }
   if (kTcFwd) TcFwd<NM_SPEC_NAME, kTcFwd>::launch(*p, a, c->params, wprep, grid, c->stream);
   else nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);

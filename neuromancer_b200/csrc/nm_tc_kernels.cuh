@@ -1303,4 +1303,143 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<B::COLS>(tmem);
 }
+
+// ================================================================================================
+// First-layer hoist GEMM on the tensor cores:  E[r][n] = bias[n] + sum_k exo_cat[r][k] * W_0[n][KS + k]
+// (rows r = b * T + t over the whole batch and horizon; see HoistedMlp in nm_kernels.cuh).  A plain GEMM that streams
+// the exogenous rows once: per exogenous segment the 128 row-owning threads copy their row slice into a K-major
+// interleaved operand tile  A[k/4][row][k%4]  (raw fp32 = the tf32 "hi" part once the tensor core has truncated it)
+// and its exact remainder tile, one elected lane issues the 3-product MMAs (remainder products first) into a
+// 32-column accumulator, and the epilogue writes the row back with the bias added.
+template <class S>
+struct ExoTcCfg {
+  using KC = KCfg<S>;
+  static constexpr int N0 = KC::N0, NP = round_up(N0, 16), KE = KC::KE;
+  static constexpr int wmax() { return round_up(exo_seg_wmax<S>(), 8); }
+  static constexpr int IMG_FLOATS = round_up(KE, 8) * NP;                 // one weight image [k/4][NP][4]
+  static constexpr int W_FLOATS = 2 * IMG_FLOATS + round_up(NP, 32);      // hi | lo | bias
+  static constexpr int A_FLOATS = wmax() * 128;                           // one operand tile [k/4][128][4]
+  static constexpr size_t SMEM_BYTES = size_t(W_FLOATS + 2 * A_FLOATS) * 4 + 256;
+  static constexpr bool OK = KC::HOIST && NP <= 256 && SMEM_BYTES <= 227 * 1024 && KE % 8 == 0;
+};
+
+template <class S>
+__global__ void nm_exo_tc_prep_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, float* __restrict__ wexo) {
+  using X = ExoTcCfg<S>;
+  using KC = KCfg<S>;
+  constexpr int KW = S::Pol::sz(0), KS = KC::KS;
+  const float* __restrict__ Wg = params + plan.policy.param_offset;
+  const float* __restrict__ bg = Wg + X::N0 * KW;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  for (int idx = gtid; idx < X::IMG_FLOATS; idx += gthreads) {
+    const int kc = idx / (X::NP * 4), n = (idx / 4) % X::NP, k = kc * 4 + (idx & 3);
+    const float v = (n < X::N0 && k < X::KE) ? Wg[n * KW + KS + k] : 0.f;
+    const float h = tc::tf32_hi(v);
+    wexo[idx] = h; wexo[X::IMG_FLOATS + idx] = v - h;
+  }
+  for (int idx = gtid; idx < round_up(X::NP, 32); idx += gthreads) wexo[2 * X::IMG_FLOATS + idx] = (idx < X::N0 && plan.policy.has_bias) ? bg[idx] : 0.f;
+}
+
+template <class S>
+__global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ wexo,
+                                                                    const __grid_constant__ ExoPtrs exo, float* __restrict__ E, int64_t B) {
+  using X = ExoTcCfg<S>;
+  constexpr int N0 = X::N0, NP = X::NP;
+  extern __shared__ __align__(128) float smem[];
+  float* sm_w = smem;                                           // hi | lo | bias
+  float* a_hi = smem + X::W_FLOATS;
+  float* a_lo = a_hi + X::A_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_lo + X::A_FLOATS);      // [0] weight TMA, [1] MMA completion
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const NmPlan& p = plan;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc<32>(tmem_slot);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], uint32_t(X::W_FLOATS) * 4);
+    tma_bulk_g2s(sm_w, wexo, uint32_t(X::W_FLOATS) * 4, &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  uint32_t phase = 0;
+  const int64_t R = B * p.nsteps;
+  const int64_t tiles = (R + 127) / 128;
+  constexpr uint32_t idesc = tc::idesc_tf32(128, NP);
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t r = tile * 128 + tid < R ? tile * 128 + tid : R - 1;
+    const int64_t b = r / p.nsteps;
+    const int t = int(r - b * p.nsteps);
+    static_for<0, S::NSEG>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+        constexpr int W = S::seg_width(s), e = S::seg_index(s), OFF = exo_seg_off<S>(s), WP = round_up(W, 8);
+        const float* __restrict__ src = exo.p[e] + (b * p.exo[e].steps + t) * W;
+#pragma unroll 4
+        for (int k4 = 0; k4 < WP / 4; ++k4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k4 * 4 < W) v = __ldg(reinterpret_cast<const float4*>(src + k4 * 4));
+          // the tensor core reads the hi tile truncated to tf32: the remainder is taken against the truncated value
+          float4 l;
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          *reinterpret_cast<float4*>(a_hi + (k4 * 128 + tid) * 4) = v;
+          *reinterpret_cast<float4*>(a_lo + (k4 * 128 + tid) * 4) = l;
+        }
+        tc::fence_async_smem();
+        tc::fence_before();
+        __syncthreads();
+        if (tid < 32) {
+          tc::fence_after();
+          constexpr uint32_t A_LBO = 128 * 16, A_KSTEP = 2 * 128 * 16, B_LBO = NP * 16, B_KSTEP = 2 * NP * 16;
+          const uint64_t ah = tc::smem_desc(smem_u32(a_hi), A_LBO, 128), al = tc::smem_desc(smem_u32(a_lo), A_LBO, 128);
+          const uint64_t wh = tc::smem_desc(smem_u32(sm_w) + (OFF / 4) * NP * 16, B_LBO, 128);
+          const uint64_t wl = tc::desc_add(wh, X::IMG_FLOATS * 4);
+          if (tc::elect_one()) {
+            static_for<0, WP / 8>([&](auto kc) {
+              constexpr int ks = decltype(kc)::value;
+              tc::mma_ss(tmem, tc::desc_add(al, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, (OFF == 0 && ks == 0) ? 0u : 1u);
+              tc::mma_ss(tmem, tc::desc_add(ah, ks * A_KSTEP), tc::desc_add(wl, ks * B_KSTEP), idesc, 1u);
+            });
+            static_for<0, WP / 8>([&](auto kc) {
+              constexpr int ks = decltype(kc)::value;
+              tc::mma_ss(tmem, tc::desc_add(ah, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, 1u);
+            });
+            tc::commit(&bars[1]);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&bars[1], phase);                             // the operand tiles are free again
+        phase ^= 1;
+        tc::fence_after();
+      }
+    });
+    // epilogue: this thread's row of the accumulator + bias -> E
+    const bool valid = tile * 128 + tid < R;
+    static_for<0, NP / 16>([&](auto cc) {
+      constexpr int c0 = decltype(cc)::value * 16;
+      float v[16];
+      tc::tmem_ld<16>(tmem + lane_base + c0, v);
+      if (valid) {
+#pragma unroll
+        for (int i4 = 0; i4 < 16; i4 += 4) {
+          if (c0 + i4 < N0) {
+            const float4 bb = *reinterpret_cast<const float4*>(sm_w + 2 * X::IMG_FLOATS + c0 + i4);
+            *reinterpret_cast<float4*>(E + r * N0 + c0 + i4) = make_float4(v[i4] + bb.x, v[i4 + 1] + bb.y, v[i4 + 2] + bb.z, v[i4 + 3] + bb.w);
+          }
+        }
+      }
+    });
+    tc::fence_before();
+    __syncthreads();                                            // every row has been read before the next tile's first MMA overwrites the accumulator
+    tc::fence_after();
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<32>(tmem);
+}
+
 }  // namespace nm
