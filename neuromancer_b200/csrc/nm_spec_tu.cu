@@ -176,6 +176,9 @@ template <bool ON> constexpr bool exo_tc_ok() { if constexpr (ON) return ExoTcCf
 constexpr bool kExoTc = exo_tc_ok<kHoist>() && (NM_TUNE_HOIST_TCGEMM != 0);
 template <bool ON> constexpr size_t exo_tc_wbytes() { if constexpr (ON) return (size_t(ExoTcCfg<SB>::W_FLOATS) * 4 + 255) & ~size_t(255); else return 0; }
 template <bool ON> constexpr size_t exo_tc_smem() { if constexpr (ON) return ExoTcCfg<SB>::SMEM_BYTES; else return 0; }
+template <bool ON> constexpr bool exo_tc_bwd_ok() { if constexpr (ON) return ExoTcBwdCfg<SB>::OK; else return false; }
+constexpr bool kExoTcBwd = exo_tc_bwd_ok<kHoist>() && (NM_TUNE_HOIST_TCGEMM != 0);
+template <bool ON> constexpr size_t exo_tc_bwd_smem() { if constexpr (ON) return ExoTcBwdCfg<SB>::SMEM_BYTES; else return 0; }
 constexpr size_t kExoSmem = exo_gemm_smem_bytes<SB>();
 // the hoisted configuration addresses the same parameter block as the plain one
 template <class K_, class Tl> constexpr bool hoist_layout_ok() {       // (dependent on K_: only instantiated for hoisted classes)
@@ -211,6 +214,9 @@ int device_info(DeviceInfo** out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_bwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExoSmem);
       if constexpr (kExoTc) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_tc_fwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exo_tc_smem<kExoTc>());
+      }
+      if constexpr (kExoTcBwd) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_tc_bwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exo_tc_bwd_smem<kExoTcBwd>());
       }
     }
     if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
@@ -373,7 +379,14 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
   else nm_bwd_kernel<S><<<grid, S::THREADS, KC::BWD_SMEM_BYTES, c->stream>>>(*p, a);
   if constexpr (kHoist) {
     if (p->policy.trainable) {
-      nm_exo_gemm_bwd_kernel<SB><<<grid, SB::THREADS, kExoSmem, c->stream>>>(*p, ep, a.dz1, c->grad_partials, c->B);
+      // single-pass TF32 on the tensor cores from 2^20 rows up (unbiased rounding noise, averaged over the rows of every
+      // entry -- the rule of the tensor-core adjoint's weight gradients); the exact FFMA GEMM below that.  NM_TC_BWD forces.
+      bool tc_gemm = kExoTcBwd && double(c->B) * double(p->nsteps) >= 1048576.0;
+      if (kExoTcBwd) { const char* force = getenv("NM_TC_BWD"); if (force != nullptr) tc_gemm = force[0] != '0'; }
+      if constexpr (kExoTcBwd) {
+        if (tc_gemm) nm_exo_gemm_tc_bwd_kernel<SB><<<grid, 128, exo_tc_bwd_smem<kExoTcBwd>(), c->stream>>>(*p, ep, a.dz1, c->grad_partials, c->B);
+      }
+      if (!tc_gemm) nm_exo_gemm_bwd_kernel<SB><<<grid, SB::THREADS, kExoSmem, c->stream>>>(*p, ep, a.dz1, c->grad_partials, c->B);
       c->extra_launches += 1;
     }
   }

@@ -1442,4 +1442,136 @@ __global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_fwd_kernel(const __grid
   if (warp == 0) tc::tmem_dealloc<32>(tmem);
 }
 
+
+// ================================================================================================
+// First-layer hoist, backward GEMM on the tensor cores:  dW_0[n][KS + k] += sum_r dZ_1[r][n] * exo_cat[r][k]
+// A contraction over ROWS (r = b * T + t), i.e. the weight-gradient form of nm_tc_bwd_kernel: both operands are
+// "K-major in rows" -- transposed, tf32-rounded (round to nearest: unbiased, averages out over the rows) tiles
+// DT[n][row] and XT[k][row] in the 128-byte swizzle, written by the row-owning threads; M = 128 accumulator lanes = n
+// (the first N0 are real), N = segment width, 16 MMAs per 128-row tile and segment.  The tensor-memory accumulator
+// truncates, so it is flushed (RED.ADD into this CTA's gradient block, fp32 round-to-nearest) every 20 tiles.
+// Single-pass TF32: the dispatcher uses it from 2^20 rows up, the exact FFMA GEMM below that.
+template <class S>
+struct ExoTcBwdCfg {
+  using KC = KCfg<S>;
+  static constexpr int N0 = KC::N0, KE = KC::KE;
+  static constexpr int RD = round_up(N0, 8);                                // rows of DT
+  static constexpr int rx() { return round_up(exo_seg_wmax<S>(), 8); }      // rows of XT (widest segment)
+  static constexpr int DT_BYTES = RD * 512, XT_BYTES = rx() * 512;
+  // the MMA reads 128 rows of the A operand: the window has to cover them (rows >= RD are garbage lanes, dropped at the flush)
+  static constexpr int A_SPAN = 3 * RD * 128 + 16 * 1024;
+  static constexpr int TILE_BYTES = cmax(DT_BYTES + XT_BYTES, A_SPAN);
+  static constexpr size_t SMEM_BYTES = size_t(TILE_BYTES) + 256 + 1024;
+  static constexpr int acc_cols(int w) { return round_up(w, 16); }
+  static constexpr int acc_off(int s) { int o = 0; for (int i = 0; i < s; ++i) if (S::seg_kind(i) == NM_SEG_EXO) o += acc_cols(S::seg_width(i)); return o; }
+  static constexpr int COLS = tc::pow2_ceil(acc_off(S::NSEG));
+  static constexpr int FLUSH_TILES = 20;                                    // 20 tiles x 16 MMAs = 320 accumulations
+  static constexpr bool OK = KC::HOIST && N0 <= 128 && COLS <= 512 && SMEM_BYTES <= 227 * 1024;
+};
+
+template <class S>
+__global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ ExoPtrs exo,
+                                                                    const float* __restrict__ dZ1, float* __restrict__ grad_partials, int64_t B) {
+  using X = ExoTcBwdCfg<S>;
+  using KC = KCfg<S>;
+  constexpr int N0 = X::N0, KW = S::Pol::sz(0);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw;
+  if ((smem_u32(sm) & 1023u) != 0u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + X::TILE_BYTES);         // [0] MMA completion
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const NmPlan& p = plan;
+  for (int i = tid; i < X::TILE_BYTES / 4; i += 128) reinterpret_cast<float*>(sm)[i] = 0.f;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc<X::COLS>(tmem_slot);
+  tc::fence_before();
+  tc::fence_async_smem();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  const uint32_t sbase = smem_u32(sm);
+  const uint64_t d_sw0 = tc::smem_desc_sw128(sbase);
+  float* gpol = grad_partials + size_t(blockIdx.x) * size_t(p.n_params) + p.policy.param_offset;
+  uint32_t phase = 0;
+  const int64_t R = B * p.nsteps;
+  const int64_t tiles = (R + 127) / 128;
+  // per-thread pieces of the swizzled address of element (row f, trajectory-slot tid) -- see tc::sw128_off
+  const uint32_t t_blk = uint32_t(tid >> 5), t_chunk = uint32_t((tid & 31) >> 2), t_in = uint32_t(tid & 3) * 4;
+  auto tstore = [&](uint32_t tile_off, int Rr, int f, float v) {
+    tc::st_shared(sbase + tile_off + t_blk * uint32_t(Rr * 128) + uint32_t(f * 128) + ((t_chunk ^ uint32_t(f & 7)) << 4) + t_in, tc::tf32_hi(v));
+  };
+  auto flush = [&]() {                                                    // lane n of the accumulators -> row n of dW_0[:, exo]
+    static_for<0, S::NSEG>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+        constexpr int W = S::seg_width(s), OFF = exo_seg_off<S>(s);
+#pragma unroll 1
+        for (int c0 = 0; c0 < X::acc_cols(W); c0 += 8) {
+          float v[8];
+          tc::tmem_ld<8>(tmem + lane_base + X::acc_off(s) + c0, v);
+          if (tid < N0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (c0 + i < W) atomicAdd(gpol + tid * KW + KC::KS + OFF + c0 + i, v[i]);
+          }
+        }
+      }
+    });
+  };
+  int since_flush = 0;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const bool valid = tile * 128 + tid < R;
+    const int64_t r = valid ? tile * 128 + tid : R - 1;
+    const int64_t b = r / p.nsteps;
+    const int t = int(r - b * p.nsteps);
+    const bool fresh = since_flush == 0;
+    // DT <- dZ_1 rows (zero for rows past the end: they contribute nothing)
+#pragma unroll 2
+    for (int n4 = 0; n4 < N0; n4 += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) v = __ldg(reinterpret_cast<const float4*>(dZ1 + r * N0 + n4));
+      tstore(0, X::RD, n4 + 0, v.x); tstore(0, X::RD, n4 + 1, v.y); tstore(0, X::RD, n4 + 2, v.z); tstore(0, X::RD, n4 + 3, v.w);
+    }
+    static_for<0, S::NSEG>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+        constexpr int W = S::seg_width(s), e = S::seg_index(s), RX = X::rx();
+        const float* __restrict__ src = exo.p[e] + (b * p.exo[e].steps + t) * W;
+#pragma unroll 2
+        for (int k4 = 0; k4 < W; k4 += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + k4));
+          tstore(X::DT_BYTES, RX, k4 + 0, v.x); tstore(X::DT_BYTES, RX, k4 + 1, v.y); tstore(X::DT_BYTES, RX, k4 + 2, v.z); tstore(X::DT_BYTES, RX, k4 + 3, v.w);
+        }
+        tc::fence_async_smem();
+        tc::fence_before();
+        __syncthreads();
+        if (tid < 32) {
+          tc::fence_after();
+          constexpr uint32_t idesc = tc::idesc_tf32(128, X::acc_cols(W));
+          const uint64_t da = d_sw0, db = tc::desc_add(d_sw0, X::DT_BYTES);
+          if (tc::elect_one()) {
+            static_for<0, 16>([&](auto kc) {
+              constexpr uint32_t q = decltype(kc)::value;
+              tc::mma_ss(tmem + X::acc_off(s), tc::desc_add(da, (q >> 2) * (X::RD * 128) + (q & 3) * 32),
+                         tc::desc_add(db, (q >> 2) * (RX * 128) + (q & 3) * 32), idesc, (q == 0 && fresh) ? 0u : 1u);
+            });
+            tc::commit(&bars[0]);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&bars[0], phase);                             // XT (and, after the last segment, DT) may be overwritten
+        phase ^= 1;
+        tc::fence_after();
+      }
+    });
+    if (++since_flush == X::FLUSH_TILES) { flush(); since_flush = 0; tc::fence_before(); __syncthreads(); tc::fence_after(); }
+  }
+  if (since_flush > 0) flush();
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<X::COLS>(tmem);
+}
+
 }  // namespace nm

@@ -99,7 +99,14 @@ int main(int argc, char** argv) {
   ba.pre = chk.data(); ba.dz1 = G1.data();
   emu::launch(16, 256, [&] { nm_tc_prep_bwd_kernel<S>(plan, params.data(), wprep.data()); });
   emu::launch(grid, BK::THREADS, [&] { nm_tc_bwd_kernel<S>(plan, ba); });
+#ifdef EMU_TC_GEMM
+  if constexpr (MD::HOIST) {
+    static_assert(ExoTcBwdCfg<SB>::OK, "tensor-core backward hoist GEMM not available for this class");
+    emu::launch(grid, 128, [&] { nm_exo_gemm_tc_bwd_kernel<SB>(plan, ep, G1.data(), gpart.data(), B); });
+  }
+#else
   if constexpr (MD::HOIST) emu::launch(grid, SB::THREADS, [&] { nm_exo_gemm_bwd_kernel<SB>(plan, ep, G1.data(), gpart.data(), B); });
+#endif
 
   std::vector<double> tsum(std::max<int>(plan.n_terms, 1), 0.0);
   for (int k = 0; k < plan.n_terms; ++k)

@@ -164,8 +164,10 @@ def test_first_layer_hoist_on_the_tensor_core_kernels_matches_the_oracle(tmp_pat
     compile_emulator("c4", exe, ("NM_TUNE_HOIST=1",), src="tc_emu.cpp")
     for B in (1, 130):
         run_emulated("c4", B, exe, str(tmp_path))
-    # ... and with E from the tensor-core version of the forward hoist GEMM (nm_exo_gemm_tc_fwd_kernel: row slices as
-    # K-major operand tiles + remainder tiles in shared memory, 3-product MMAs, bias in the epilogue)
+    # ... and with both hoist GEMMs on the tensor cores: E from nm_exo_gemm_tc_fwd_kernel (row slices as K-major operand
+    # + remainder tiles in shared memory, 3-product MMAs, bias in the epilogue), dW_0[:, exo] from
+    # nm_exo_gemm_tc_bwd_kernel (transposed tf32 tiles in the 128-byte swizzle, contraction over rows, accumulators
+    # flushed every 20 tiles; single-pass TF32 like the adjoint's weight gradients)
     exe2 = str(tmp_path / "emu_tc_hoist_tcgemm")
     compile_emulator("c4", exe2, ("NM_TUNE_HOIST=1", "EMU_TC_GEMM"), src="tc_emu.cpp")
     for B in (1, 130):
