@@ -7,7 +7,9 @@
 #include NM_SPEC_HEADER   // defines struct NM_SPEC_NAME (the "Shape") and the NM_TUNE_* knobs: before the kernel headers
 #include "nm_kernels.cuh"
 #include "nm_tc_kernels.cuh"
+#include "nm_wide_kernels.cuh"
 #include "nm_registry.h"
+#include <cmath>
 
 namespace {
 
@@ -165,6 +167,99 @@ template <class Sp> struct TcBwdEligible<Sp, true> { static constexpr bool value
 // the tensor-core adjoint needs the stage checkpoints written by the forward kernel; without them the FFMA adjoint runs
 constexpr bool kTcBwd = kTcFwd && TcBwdEligible<NM_SPEC_NAME, kTcFwd>::value;
 
+// ------------------------------------------------------------------------------------------------
+// wide-policy tensor-core family (nm_wide_kernels.cuh): fp16 3-product MMAs, weights resident in shared memory,
+// weight gradients as a separate streaming GEMM over a staging buffer, horizon swept in chunks
+template <class Sp, bool ON> struct Wide {
+  static constexpr size_t W_BYTES = 0;
+  static cudaError_t setup() { return cudaSuccess; }
+  static int chunk_steps(int64_t, int) { return 1; }
+  static size_t bwd_extra(int64_t, int, int) { return 0; }
+  static void launch_fwd(const NmPlan&, const FwdArgs&, const float*, void*, int, cudaStream_t) {}
+  static int launch_bwd(const NmPlan&, const BwdArgs&, const float*, void*, char*, int, int, cudaStream_t) { return 0; }
+  static void info(char*, size_t, int, int, size_t, int, int) {}
+};
+template <class Sp> struct Wide<Sp, true> {
+  using C = wd::WideCfg<Sp>;
+  static constexpr size_t W_BYTES = C::W_BYTES;
+  static cudaError_t setup() {
+    cudaError_t e = cudaFuncSetAttribute(nm_wide_fwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_wide_bwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_wide_wgrad_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::WG_SMEM_BYTES);
+    return e;
+  }
+  // steps per adjoint launch: the staging buffer (tiles * CS items of ITEM_BYTES) is capped at NM_WIDE_STAGING_GB (default 16)
+  static int chunk_steps(int64_t B, int T) {
+    double cap_gb = 16.0;
+    if (const char* s = getenv("NM_WIDE_STAGING_GB")) { const double v = atof(s); if (v > 0.0) cap_gb = v; }
+    const double per_step = double((B + 127) / 128) * double(C::ITEM_BYTES);
+    int64_t cs = int64_t(cap_gb * 1073741824.0 / per_step);
+    if (cs < 1) cs = 1;
+    if (cs > T) cs = T;
+    return int(cs);
+  }
+  static void info(char* buf, size_t cap, int tile, int threads, size_t smem, int spill, int nterms) {
+    std::snprintf(buf, cap, "fwd[tcgen05 3xFP16 wide tile=2x128 threads=%d smem=%d weights-resident] bwd[tcgen05 3xFP16 wide threads=%d + wgrad GEMM 1xFP16-rn item=%d B; below 2^20 products or without checkpoints: ffma tile=%d threads=%d smem=%zu dw_spill=%d] compiled_terms=%d",
+                  C::THREADS, C::SMEM_BYTES, C::THREADS, C::ITEM_BYTES, tile, threads, smem, spill, nterms);
+  }
+  static constexpr size_t a256(size_t v) { return (v + 255) & ~size_t(255); }
+  static size_t staging_bytes(int64_t B, int T) { return a256(size_t((B + 127) / 128) * size_t(chunk_steps(B, T)) * size_t(C::ITEM_BYTES)); }
+  static size_t stash_bytes(int sms) { return a256(size_t(sms) * 2 * size_t(C::STASH_SLOT_BYTES)); }
+  static size_t carry_bytes(int64_t B) { return a256(size_t(B) * Sp::NX * sizeof(float)); }
+  // [scale state 256 B | co-state carry | derivative stash | staging]
+  static size_t bwd_extra(int64_t B, int T, int sms) { return 256 + carry_bytes(B) + stash_bytes(sms) + staging_bytes(B, T); }
+  static int grid_for(int64_t B, int sms) { const int64_t pairs = ((B + 127) / 128 + 1) / 2; return int(pairs < sms ? pairs : sms); }
+  static void launch_fwd(const NmPlan& p, const FwdArgs& a, const float* params, void* wprep, int sms, cudaStream_t st) {
+    wd::nm_wide_prep_kernel<Sp><<<32, 256, 0, st>>>(p, params, static_cast<uint8_t*>(wprep));
+    nm_wide_fwd_kernel<Sp><<<grid_for(a.B, sms), C::THREADS, C::SMEM_BYTES, st>>>(p, a);
+  }
+  // returns the number of kernels launched; `extra` is the wide region of the backward workspace, `nblocks` gradient blocks are zeroed
+  static int launch_bwd(const NmPlan& p, const BwdArgs& a, const float* params, void* wprep, char* extra, int sms, int nblocks, cudaStream_t st) {
+    const int T = p.nsteps;
+    const int CS = chunk_steps(a.B, T);
+    const int64_t tiles = (a.B + 127) / 128;
+    wd::ScaleState* scale = reinterpret_cast<wd::ScaleState*>(extra);
+    float* carry = reinterpret_cast<float*>(extra + 256);
+    float* stash = reinterpret_cast<float*>(extra + 256 + carry_bytes(a.B));
+    uint8_t* staging = reinterpret_cast<uint8_t*>(extra + 256 + carry_bytes(a.B) + stash_bytes(sms));
+    // initial cotangent scale: the largest term coefficient w / (B_total * t_len * d_len) goes to ~2^4
+    double cmax = 0.0;
+    for (int k = 0; k < p.n_terms; ++k) {
+      const double c = std::fabs(double(p.terms[k].weight)) / (double(a.b_total) * double(p.terms[k].t_len) * double(p.terms[k].d_len));
+      if (c > cmax) cmax = c;
+    }
+    int e0 = cmax > 0.0 ? 4 - int(std::floor(std::log2(cmax))) : int(std::floor(std::log2(double(a.b_total)))) + 10;
+    if (const char* s = getenv("NM_WIDE_GS0_LOG2")) e0 = atoi(s);
+    if (e0 > 100) e0 = 100;
+    if (e0 < -100) e0 = -100;
+    cudaMemsetAsync(a.grad_partials, 0, size_t(nblocks) * size_t(p.n_params) * sizeof(float), st);
+    nm_wide_scale_init_kernel<<<1, 32, 0, st>>>(scale, float(std::ldexp(1.0, e0)));
+    wd::nm_wide_prep_kernel<Sp><<<32, 256, 0, st>>>(p, params, static_cast<uint8_t*>(wprep));
+    int launches = 3;
+    const int grid = grid_for(a.B, sms);
+    for (int t_hi = T; t_hi > 0; t_hi -= CS) {
+      const int t_lo = t_hi - CS > 0 ? t_hi - CS : 0;
+      WideBwdArgs w{};
+      w.b = a; w.staging = staging; w.stash = stash; w.lam_carry = carry; w.scale = scale; w.t_lo = t_lo; w.t_hi = t_hi;
+      nm_wide_bwd_kernel<Sp><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(p, w);
+      const int64_t n_items = tiles * int64_t(t_hi - t_lo);
+      const int wgrid = int(n_items < sms ? n_items : sms);
+      nm_wide_wgrad_kernel<Sp><<<wgrid, C::WG_THREADS, C::WG_SMEM_BYTES, st>>>(p, staging, n_items, scale, a.grad_partials);
+      nm_wide_scale_update_kernel<<<1, 32, 0, st>>>(scale);
+      launches += 3;
+    }
+    return launches;
+  }
+};
+template <class Sp, bool EL> struct WideEligible { static constexpr bool value = false; };
+template <class Sp> struct WideEligible<Sp, true> { static constexpr bool value = wd::WideCfg<Sp>::ELIGIBLE && wd::WideCfg<Sp>::FITS && wd::WideCfg<Sp>::WG_OK; };
+#ifndef NM_TUNE_WIDE
+#define NM_TUNE_WIDE 1
+#endif
+constexpr bool kWide = !kTcFwd && (NM_TUNE_WIDE != 0) && !KC::HOIST && NM_SPEC_NAME::RHS != NM_RHS_MLP && NM_SPEC_NAME::Pol::NL >= 3 &&
+                       WideEligible<NM_SPEC_NAME, (NM_SPEC_NAME::RHS != NM_RHS_MLP && NM_SPEC_NAME::Pol::NL >= 3)>::value;
+using WD = Wide<NM_SPEC_NAME, kWide>;
+
 constexpr bool kHoist = KC::HOIST && KCF::HOIST;
 constexpr size_t hoist_bytes(const NmPlan* p, int64_t B) { return kHoist ? ((size_t(B) * size_t(p->nsteps) * size_t(KC::N0) * sizeof(float) + 255) & ~size_t(255)) : 0; }
 // forward hoist GEMM on the tensor cores (nm_exo_gemm_tc_fwd_kernel) when the class allows it; its weight images
@@ -208,6 +303,7 @@ int device_info(DeviceInfo** out) {
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fwd, nm_fwd_kernel<SF>, SF::THREADS, KCF::FWD_SMEM_BYTES);
     if (kTcFwd && e == cudaSuccess) e = TcFwd<NM_SPEC_NAME, kTcFwd>::setup(&d.occ_fwd);
     if (kTcBwd && e == cudaSuccess) e = TcBwd<NM_SPEC_NAME, kTcBwd>::setup();
+    if (kWide && e == cudaSuccess) e = WD::setup();
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_bwd, nm_bwd_kernel<S>, S::THREADS, KC::BWD_SMEM_BYTES);
     if constexpr (kHoist) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_exo_gemm_fwd_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExoSmem);
@@ -229,14 +325,15 @@ int device_info(DeviceInfo** out) {
 
 constexpr size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 constexpr size_t kWprepFfma = size_t(KC::W_FLOATS_ALL + KC::EXO_W_FLOATS > 0 ? KC::W_FLOATS_ALL + KC::EXO_W_FLOATS : 4) * 4;
-constexpr size_t kWprepTc = TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES > (kTcFwd ? TK::FWD_W_BYTES : 0) ? TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES : (kTcFwd ? TK::FWD_W_BYTES : 0);
+constexpr size_t kWprepTc0 = TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES > (kTcFwd ? TK::FWD_W_BYTES : 0) ? TcBwd<NM_SPEC_NAME, kTcBwd>::W_BYTES : (kTcFwd ? TK::FWD_W_BYTES : 0);
+constexpr size_t kWprepTc = kWprepTc0 > WD::W_BYTES ? kWprepTc0 : WD::W_BYTES;
 // tensor-core class with the hoist: the FFMA-layout block (exogenous rows for the hoist GEMM) lives BEHIND the
 // tensor-core images while the tensor-core kernels run; every other class keeps one region
 constexpr size_t kFfmaRegionOff = (kHoist && kTcFwd) ? align256(kWprepTc) : 0;
 constexpr size_t kBaseWprepBytes = (kHoist && kTcFwd) ? align256(kWprepTc) + align256(kWprepFfma) : align256(kWprepTc > kWprepFfma ? kWprepTc : kWprepFfma);
 constexpr size_t kExoTcOff = kBaseWprepBytes;
 constexpr size_t kWprepBytes = kBaseWprepBytes + exo_tc_wbytes<kExoTc>();
-constexpr int kFwdTile = kTcFwd ? 128 : SF::TILE;
+constexpr int kFwdTile = (kTcFwd || kWide) ? 128 : SF::TILE;
 
 int check_plan(const NmPlan* p) {
   if (p->n_params < KC::N_PARAMS) { nm_set_error("plan.n_params smaller than the shape class expects"); return NM_ERR_BAD_PLAN; }
@@ -264,8 +361,10 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
     if (gtc > gb) gb = gtc;
   }
   // (hoist: E[B][T][N0] in the forward workspace when the caller gives no checkpoint buffer; E recomputed / dZ_1 in the backward one)
+  if (kWide && gb < sms) gb = sms;                   // the wide adjoint / weight-gradient GEMM own one gradient block per SM
   *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double)) + hoist_bytes(p, B);
   *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float)) + hoist_bytes(p, B);
+  if (kWide) *bwd = align256(*bwd) + WD::bwd_extra(B, p->nsteps, sms);
   return NM_OK;
 }
 
@@ -290,7 +389,8 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
   c->grid = grid;
   c->term_partials = reinterpret_cast<double*>(ws + kWprepBytes);
   float* wprep_ffma = reinterpret_cast<float*>(ws + kFfmaRegionOff);
-  if (!kTcFwd || kHoist) launch_prep(p, c->params, wprep_ffma, c->stream);
+  if (kWide) { grid = d->sms; if (grid > (tiles + 1) / 2) grid = (tiles + 1) / 2; if (grid < 1) grid = 1; c->grid = grid; }
+  if ((!kTcFwd && !kWide) || kHoist) launch_prep(p, c->params, wprep_ffma, c->stream);
   FwdArgs a{};
   a.term_partials = c->term_partials; a.fused_terms = c->fused_terms;
   a.params = c->params; a.wprep = wprep; a.x0 = c->x0;
@@ -319,7 +419,8 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
     }
     a.pre = E;
   }
-  if (kTcFwd) TcFwd<NM_SPEC_NAME, kTcFwd>::launch(*p, a, c->params, wprep, grid, c->stream);
+  if (kWide) WD::launch_fwd(*p, a, c->params, wprep, d->sms, c->stream);
+  else if (kTcFwd) TcFwd<NM_SPEC_NAME, kTcFwd>::launch(*p, a, c->params, wprep, grid, c->stream);
   else nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
@@ -348,6 +449,30 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
     const char* force = getenv("NM_TC_BWD");
     if (force != nullptr) tc_bwd = force[0] != '0';
     else if (!TB::WG3) tc_bwd = double(c->B) * double(p->nsteps) * double(TB::EVALS) >= 1048576.0;
+  }
+  // wide-policy classes: same rule (single-pass fp16 weight-gradient operands), NM_TC_BWD forces
+  bool wide_bwd = kWide && c->checkpoints != nullptr;
+  if (wide_bwd) {
+    const char* force = getenv("NM_TC_BWD");
+    if (force != nullptr) wide_bwd = force[0] != '0';
+    else wide_bwd = double(c->B) * double(p->nsteps) >= 1048576.0;
+  }
+  if (wide_bwd) {
+    BwdArgs a{};
+    a.params = c->params; a.wprep = wprep;
+    for (int e = 0; e < NM_MAX_EXO; ++e) a.exo[e] = e < p->n_exo ? c->exo[e] : nullptr;
+    a.x_traj = c->x_traj; a.u_traj = c->u_traj; a.y_traj = c->y_traj; a.chk = c->checkpoints;
+    a.grad_scalars = c->grad_scalars; a.gx_ext = c->gx_ext; a.gu_ext = c->gu_ext; a.gy_ext = c->gy_ext;
+    a.G_x = c->G_x; a.G_u = c->G_u; a.G_y = c->G_y; a.fused_terms = c->fused_terms;
+    a.grad_partials = c->grad_partials; a.grad_x0 = c->grad_x0;
+    a.B = c->B; a.b_total = c->b_total; a.num_tiles = int((c->B + 127) / 128);
+    char* extra = ws + (need_b - WD::bwd_extra(c->B, p->nsteps, d->sms));
+    c->grid = d->sms;
+    const int n = WD::launch_bwd(*p, a, c->params, wprep, extra, d->sms, d->sms, c->stream);
+    c->extra_launches += n - 2;                      // the caller counts weight prep + adjoint
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { nm_set_error(cudaGetErrorString(e)); return NM_ERR_CUDA; }
+    return NM_OK;
   }
   if (tc_bwd) { grid = d->sms * TcBwd<NM_SPEC_NAME, kTcBwd>::CTAS; if (grid > int((c->B + 127) / 128)) grid = int((c->B + 127) / 128); if (grid < 1) grid = 1; c->grid = grid; }
   else launch_prep(p, c->params, wprep, c->stream);
@@ -400,7 +525,9 @@ NmKernelEntry g_entry;
 
 struct Registrar {
   Registrar() {
-    if (kTcFwd && kTcBwd)
+    if (kWide)
+      WD::info(g_info, sizeof(g_info), SB::TILE, SB::THREADS, KC::BWD_SMEM_BYTES, int(KC::DW_SPILL), S::NTERMS);
+    else if (kTcFwd && kTcBwd)
       std::snprintf(g_info, sizeof(g_info), "fwd[tcgen05 3xTF32 tile=128 threads=128 tmem_cols=%d smem=%zu ctas/sm<=%d] bwd[tcgen05 tile=128 threads=%d ctas/sm=%d wgrad=%s; below 2^20 products or without checkpoints: ffma tile=%d threads=%d smem=%zu] compiled_terms=%d",
                     TK::C::FWD_COLS, TK::FWD_SMEM_BYTES, TK::MAX_CTAS, TcBwd<NM_SPEC_NAME, kTcBwd>::THREADS, TcBwd<NM_SPEC_NAME, kTcBwd>::CTAS,
                     TcBwd<NM_SPEC_NAME, kTcBwd>::WG3 ? "3xTF32" : "1xTF32-rn", SB::TILE, SB::THREADS,
@@ -419,7 +546,7 @@ struct Registrar {
     g_entry.forward = forward_fn;
     g_entry.backward = backward_fn;
     g_entry.info = g_info;
-    g_entry.chk_floats_per_step = kTcFwd ? TcMode<NM_SPEC_NAME>::CHK : (kHoist ? KC::N0 : -1);   // -1: the generic rule of nm_api.cu
+    g_entry.chk_floats_per_step = kWide ? NM_SPEC_NAME::NU : (kTcFwd ? TcMode<NM_SPEC_NAME>::CHK : (kHoist ? KC::N0 : -1));   // -1: the generic rule of nm_api.cu
     g_entry.next = nullptr;
     nm_register_kernel(&g_entry);
   }

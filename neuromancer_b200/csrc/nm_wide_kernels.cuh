@@ -1,0 +1,960 @@
+// nm_wide_kernels.cuh -- tcgen05 kernels for closed-loop systems with a WIDE policy MLP (C5: 24-128-128-128-128-6 in
+// front of a 12-state RK4 plant; reference blocks.py:169-177, 611-619, system.py:261-277, integrators.py:196-211).
+//
+// Why a second tensor-core family (measured, profiles/r02_probes_fp16_tcgen05_l2stream.txt):
+//   * three 128x128 hidden layers as tf32 hi/lo images are 418 KB -- they do not fit an SM.  As FP16 hi/lo images they
+//     are 192 KB and stay RESIDENT in shared memory; kind::f16 MMAs cost the same cycles as kind::tf32 ones but
+//     contract K = 16 per instruction, and fp16 has the same 11-bit significand as tf32: the 3-product split
+//     A_lo*W_hi + A_hi*W_lo + A_hi*W_hi keeps 22 bits (the remainders are stored scaled by 2^11 so they stay in the
+//     normal range, their two products are accumulated first and folded in by the first main product through
+//     scale-input-d = 2^-11).  Range: |activation|, |weight| < 65504 (beyond that the result is inf/NaN, never wrong).
+//   * fp16 operands may be K-major or MN-major: ONE weight image serves the forward contraction (K-major) and the
+//     data-gradient contraction (the same bytes read MN-major) -- no transposed copies.
+//   * every layer of the policy runs on the tensor pipe (layer 0: K padded to 16, output layer: N padded to 16); the
+//     CUDA cores only do activations, operand splitting, dynamics and loss terms.
+// Thread = trajectory = TMEM lane (as in nm_tc_kernels.cuh); one CTA per SM holds TWO 128-trajectory tiles in
+// tensor memory (2 x [A_hi 64 | A_lo 64 | D 128] columns) that ping-pong between the tensor pipe and their owner
+// warps; a ninth warp issues every MMA.
+//
+// Adjoint: recompute (3-product) + data gradients (3-product, cotangents carried scaled by a power of two `gs` so that
+// they sit in fp16 range) in nm_wide_bwd_kernel; the WEIGHT gradients are a separate streaming GEMM
+// (nm_wide_wgrad_kernel): the adjoint writes the fp16 "hi" halves of every layer input a_l and every scaled
+// pre-activation cotangent dZ_l -- the very words it hands to the tensor pipe -- into a staging buffer laid out as
+// MN-major operand tiles X[feature/8][trajectory][8], and the GEMM contracts them over trajectories with TMEM
+// accumulators (432 + 64 columns: they cannot share tensor memory with the rollout pipeline).  Single-pass fp16 =
+// 11-bit operands, unbiased rounding noise that averages out over the B*nsteps products of every entry -- the rule of
+// nm_tc_kernels.cuh: the dispatcher runs the exact FFMA adjoint below 2^20 products.  The horizon is swept in chunks
+// of CS steps (staging = tiles * CS * 268 KB), the co-state crossing chunk boundaries through a [B, nx] buffer.
+#pragma once
+#include "nm_tc_kernels.cuh"
+#ifndef NM_HOST_EMU
+#include <cuda_fp16.h>
+
+namespace nm {
+namespace wd {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);   // D f32, A/B f16
+}
+// MODE 0: D = A*B   1: D += A*B   2: D = A*B + D * 2^-11
+template <int MODE>
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc) {
+  if constexpr (MODE == 0)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc) : "memory");
+  else if constexpr (MODE == 1)
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n}\n" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+               "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+// fp16 split of two values: hi = rn16(a), lo = rn16((a - hi) * 2^11), packed (first value in the low half)
+__device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a0 - hf.x) * 2048.f, (a1 - hf.y) * 2048.f);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ------------------------------------------------------------------------------------------------ static layout
+struct ScaleState { float gs; float inv_gs; unsigned int max_bits; unsigned int pad; };
+
+template <class S>
+struct WideCfg {
+  using MD = TcMode<S>;
+  using M = typename S::Pol;
+  static constexpr int NL = M::NL;
+  static constexpr int K0 = M::sz(0), H = M::sz(1), NOUT = M::sz(NL > 0 ? NL : 0);
+  static constexpr int K0P = round_up(K0, 16), NOP = 16;
+  static constexpr bool BIAS = M::BIAS;
+  static constexpr int NX = S::NX, NU = S::NU;
+  // gradient is needed for the policy inputs up to the end of the last state segment
+  static constexpr int gw0() {
+    int off = 0, gw = 0;
+    for (int i = 0; i < S::NSEG; ++i) { off += S::seg_width(i); if (S::seg_kind(i) == NM_SEG_STATE) gw = off; }
+    return gw;
+  }
+  static constexpr int GWP = round_up(gw0() > 0 ? gw0() : 1, 16);
+  static constexpr bool uniform() { for (int l = 1; l < NL; ++l) if (M::sz(l) != H) return false; return true; }
+  static constexpr bool ELIGIBLE = MD::POLICY && !MD::HOIST && NL >= 3 && NL <= 6 && uniform() && H == 128 && K0 > 8 && K0P <= 64 && GWP <= K0P &&
+                                   NOUT <= NOP && NOUT == NU && !S::HAS_OUTPUT && S::ND == 0 && S::ACT_EXO < 0 && MD::segs_ok();
+  static constexpr int NHID = NL - 2;                                      // H x H layers (1 .. NL-2)
+  // ---- prepared weight block = shared-memory image (bytes); every fp16 image is [k/8][rows][8], hi then lo (x 2^11)
+  static constexpr int IMG0_BYTES = K0P * H * 2, IMGH_BYTES = H * H * 2, IMGO_BYTES = H * NOP * 2;
+  static constexpr int img0_off() { return 0; }
+  static constexpr int imgh_off(int l) { return 2 * IMG0_BYTES + (l - 1) * 2 * IMGH_BYTES; }   // l = 1 .. NL-2
+  static constexpr int imgo_off() { return 2 * IMG0_BYTES + NHID * 2 * IMGH_BYTES; }
+  static constexpr int F32_OFF = imgo_off() + 2 * IMGO_BYTES;
+  // fp32 tail: bias[l][H] for l = 0..NL-2, bias_out[NOP], W_out[NOUT][H] (output layer backward on the CUDA cores)
+  static constexpr int bias_off(int l) { return F32_OFF + l * H * 4; }
+  static constexpr int biaso_off() { return F32_OFF + (NL - 1) * H * 4; }
+  static constexpr int wout_off() { return biaso_off() + NOP * 4; }
+  static constexpr int W_BYTES = round_up(wout_off() + NOUT * H * 4, 128);
+  static constexpr int BAR_OFF = W_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 1024;
+  static constexpr bool FITS = SMEM_BYTES + 1024 <= 227 * 1024;
+  // parameter layout of the policy (reference nn.Linear: W[out][in] then bias[out])
+  static constexpr int kin(int l) { return l == 0 ? K0 : H; }
+  static constexpr int nout(int l) { return l == NL - 1 ? NOUT : H; }
+  static constexpr int p_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += nout(i) * kin(i) + (BIAS ? nout(i) : 0); return o; }
+  // ---- tensor memory: two tile slots of [A_hi H/2 | A_lo H/2 | D H] columns
+  static constexpr int SLOT_COLS = 2 * H, A_HI = 0, A_LO = H / 2, DCOL = H;
+  // ---- launch shape
+  static constexpr int THREADS = 288;
+  // ---- adjoint: staging item (one tile-step), byte offsets of the operand tiles X[feature/8][128][8] halves
+  static constexpr int GRP = 128 * 16;                                    // one 8-feature group of a tile
+  static constexpr int a_off(int l) { return l == 0 ? 0 : (K0P / 8) * GRP + (l - 1) * (H / 8) * GRP; }       // a_l, l = 0..NL-1
+  static constexpr int z_off(int l) { return a_off(NL - 1) + (H / 8) * GRP + l * (H / 8) * GRP; }             // dZ_l, l = 0..NL-2
+  static constexpr int c_off() { return z_off(NL - 2) + (H / 8) * GRP; }                                      // cotangent of the raw output
+  static constexpr int ITEM_BYTES = c_off() + (NOP / 8) * GRP;
+  // derivative stash of one tile slot: act'(z_l) for l = 0..NL-3, [l][k/4][128][4] floats
+  static constexpr int STASH_SLOT_BYTES = (NL - 2) * H * 128 * 4;
+  // ---- weight-gradient GEMM: tensor-memory columns
+  static constexpr int wg_col(int l) { return l == 0 ? 0 : (l < NL - 1 ? K0P + (l - 1) * H : K0P + NHID * H); }
+  static constexpr int wgb_col(int l) { return K0P + NHID * H + NOP + 16 * l; }                              // bias sums of layer l < NL-1
+  static constexpr int WG_COLS = wgb_col(NL - 1);
+  static constexpr int WG_RING = 3, WG_SLOT_BYTES = 2 * (H / 8) * GRP;
+  static constexpr int WG_ONES_OFF = WG_RING * WG_SLOT_BYTES, WG_BAR_OFF = WG_ONES_OFF + 2 * GRP;
+  static constexpr int WG_SMEM_BYTES = WG_BAR_OFF + 256;
+  static constexpr int WG_THREADS = 192, WG_FLUSH_ITEMS = 16;
+  static constexpr bool WG_OK = WG_COLS <= 512 && WG_SMEM_BYTES + 1024 <= 227 * 1024;
+};
+
+// ------------------------------------------------------------------------------------------------ weight preparation
+template <class S>
+__global__ void nm_wide_prep_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ params, uint8_t* __restrict__ wprep) {
+  using C = WideCfg<S>;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const float* P = params + plan.policy.param_offset;
+  auto image = [&](int l, int off, int rows, int kp) {               // [kp/8][rows][8]: element (n, k) = W_l[n][k]
+    const int Kr = C::kin(l), Nr = C::nout(l);
+    const float* W = P + C::p_off(l);
+    __half* hi = reinterpret_cast<__half*>(wprep + off);
+    __half* lo = hi + rows * kp;
+    for (int idx = gtid; idx < rows * kp; idx += gthreads) {
+      const int kc = idx / (rows * 8), n = (idx / 8) % rows, k = kc * 8 + (idx & 7);
+      const float v = (n < Nr && k < Kr) ? W[n * Kr + k] : 0.f;
+      const __half h = __float2half_rn(v);
+      hi[idx] = h;
+      lo[idx] = __float2half_rn((v - __half2float(h)) * 2048.f);
+    }
+  };
+  image(0, C::img0_off(), C::H, C::K0P);
+  for (int l = 1; l <= C::NL - 2; ++l) image(l, C::imgh_off(l), C::H, C::H);
+  image(C::NL - 1, C::imgo_off(), C::NOP, C::H);
+  for (int l = 0; l <= C::NL - 2; ++l) {
+    float* b = reinterpret_cast<float*>(wprep + C::bias_off(l));
+    const float* src = P + C::p_off(l) + C::nout(l) * C::kin(l);
+    for (int i = gtid; i < C::H; i += gthreads) b[i] = C::BIAS ? src[i] : 0.f;
+  }
+  {
+    float* b = reinterpret_cast<float*>(wprep + C::biaso_off());
+    const float* src = P + C::p_off(C::NL - 1) + C::NOUT * C::H;
+    for (int i = gtid; i < C::NOP; i += gthreads) b[i] = (C::BIAS && i < C::NOUT) ? src[i] : 0.f;
+    float* w = reinterpret_cast<float*>(wprep + C::wout_off());
+    const float* ws = P + C::p_off(C::NL - 1);
+    for (int i = gtid; i < C::NOUT * C::H; i += gthreads) w[i] = ws[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MMA batches (issuer lane)
+// D[128][N] = A[128][KP] * W^T, K-major image [KP/8][ROWS = N][8]: hi at `img`, lo at `img + ROWS*KP*2`
+template <int KP, int N>
+__device__ __forceinline__ void issue_kmajor(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t img) {
+  constexpr uint32_t idesc = idesc_f16(128, N, 0, 0);
+  constexpr uint32_t LBO = N * 16, SBO = 128, KSTEP = 2 * N * 16;
+  const uint64_t wh = tc::smem_desc(img, LBO, SBO);
+  const uint64_t wl = tc::desc_add(wh, N * KP * 2);
+  static_for<0, KP / 16>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    mma_ts<(ks > 0 ? 1 : 0)>(d, a_lo + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+    mma_ts<1>(d, a_hi + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+  });
+  static_for<0, KP / 16>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    mma_ts<(ks > 0 ? 1 : 2)>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+  });
+}
+// D[128][NP] = A[128][ROWS] * W[:, 0:NP]: the same image [KPI/8][ROWS][8] read MN-major (contraction over its rows)
+template <int ROWS, int KPI, int NP>
+__device__ __forceinline__ void issue_mnmajor(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t img) {
+  constexpr uint32_t idesc = idesc_f16(128, NP, 0, 1);
+  constexpr uint32_t LBO = 128, SBO = ROWS * 16, KSTEP = 256;
+  const uint64_t wh = tc::smem_desc(img, LBO, SBO);
+  const uint64_t wl = tc::desc_add(wh, ROWS * KPI * 2);
+  static_for<0, ROWS / 16>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    mma_ts<(ks > 0 ? 1 : 0)>(d, a_lo + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+    mma_ts<1>(d, a_hi + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+  });
+  static_for<0, ROWS / 16>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    mma_ts<(ks > 0 ? 1 : 2)>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+  });
+}
+
+// policy input -> the thread's TMEM lane (hi | lo, K0P halves each); returns the packed hi words for staging
+template <class C>
+__device__ __forceinline__ void put_input(uint32_t t_hi, uint32_t t_lo, const float (&in)[C::K0], uint32_t (&hi)[C::K0P / 2]) {
+  uint32_t lo[C::K0P / 2];
+#pragma unroll
+  for (int i = 0; i < C::K0P / 2; ++i) {
+    const float a0 = 2 * i < C::K0 ? in[2 * i < C::K0 ? 2 * i : 0] : 0.f;
+    const float a1 = 2 * i + 1 < C::K0 ? in[2 * i + 1 < C::K0 ? 2 * i + 1 : 0] : 0.f;
+    split2(a0, a1, hi[i], lo[i]);
+  }
+#pragma unroll
+  for (int c = 0; c < C::K0P / 2; c += 8) {
+    uint32_t h8[8], l8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h8[i] = hi[c + i]; l8[i] = lo[c + i]; }
+    tmem_st8u(t_hi + c, h8);
+    tmem_st8u(t_lo + c, l8);
+  }
+}
+
+// number of tiles slot `slot` of this CTA processes
+__device__ __forceinline__ int slot_rounds(int num_tiles, int slot) {
+  int n = 0;
+  for (int r = 0;; ++r) { if ((r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot >= num_tiles) break; ++n; }
+  return n;
+}
+
+}  // namespace wd
+
+// ================================================================================================ forward
+template <class S>
+__global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
+  using C = wd::WideCfg<S>;
+  using M = typename C::M;
+  constexpr int NX = S::NX, NU = S::NU, K0 = C::K0, H = C::H, NL = C::NL, TILE = 128;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);           // 0 weights, 1/2 operands ready (slot), 3/4 MMAs done (slot)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  double* red = reinterpret_cast<double*>(sm);                              // end-of-kernel reduction scratch (weights dead)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
+  constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 128); mbar_init(&bars[2], 128);
+    mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], uint32_t(C::W_BYTES));
+    tma_bulk_g2s(sm, args.wprep, uint32_t(C::W_BYTES), &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  const int T = p.nsteps;
+  float tsum[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) tsum[q] = 0.f;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    const int n0 = wd::slot_rounds(args.num_tiles, 0), n1 = wd::slot_rounds(args.num_tiles, 1);
+    const uint32_t sbase = smem_u32(sm);
+    uint32_t ph[2] = {0, 0};
+    for (int r = 0; r < n0; ++r) {
+      const bool two = r < n1;
+      for (int t = 0; t < T; ++t) {
+        static_for<0, NL>([&](auto lc) {
+          constexpr int l = decltype(lc)::value;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s == 1 && !two) continue;
+            mbar_wait(&bars[1 + s], ph[s]); ph[s] ^= 1;
+            tc::fence_after();
+            const uint32_t cb = tmem + s * C::SLOT_COLS;
+            if (tc::elect_one()) {
+              if constexpr (l == 0) wd::issue_kmajor<C::K0P, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::img0_off());
+              else if constexpr (l < NL - 1) wd::issue_kmajor<H, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgh_off(l));
+              else wd::issue_kmajor<H, C::NOP>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgo_off());
+              tc::commit(&bars[3 + s]);
+            }
+            __syncwarp();
+          }
+        });
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ owners: thread = trajectory = TMEM lane
+    const int slot = warp >> 2, m_ = tid & 127;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t cb = tmem + lane_base + slot * C::SLOT_COLS;
+    const uint32_t t_hi = cb + C::A_HI, t_lo = cb + C::A_LO, t_d = cb + C::DCOL;
+    uint64_t* bar_ops = &bars[1 + slot];
+    uint64_t* bar_done = &bars[3 + slot];
+    uint32_t ph_done = 0;
+    const float act_prm = p.policy.act_param;
+    auto arrive_ops = [&]() { tc::wait_st(); tc::fence_before(); mbar_arrive(bar_ops); };
+    for (int r = 0;; ++r) {
+      const int tile = (r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot;
+      if (tile >= args.num_tiles) break;
+      const int64_t b_raw = int64_t(tile) * TILE + m_;
+      const bool valid = b_raw < args.B;
+      const int64_t b = valid ? b_raw : args.B - 1;
+      float x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = __ldg(args.x0 + b * NX + i);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1)) * NX + i] = x[i];
+      }
+      float in_pre[K0];
+      tc_policy_input<S, K0>(p, args.exo, b, 0, x, in_pre);
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        float in[K0], yv[1] = {0.f};
+#pragma unroll
+        for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
+        tc_policy_state<S, K0>(x, yv, in);
+        { uint32_t hi0[C::K0P / 2]; wd::put_input<C>(t_hi, t_lo, in, hi0); (void)hi0; }
+        arrive_ops();
+        if (t + 1 < T) tc_policy_input<S, K0>(p, args.exo, b, t + 1, x, in_pre);     // exogenous inputs one step ahead
+        // hidden activations a_1 .. a_{NL-1}
+#pragma unroll 1
+        for (int l = 0; l < NL - 1; ++l) {
+          const float* __restrict__ bias = reinterpret_cast<const float*>(sm + C::bias_off(0)) + l * H;
+          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          tc::fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < H; c0 += 32) {
+            float v[32];
+            uint32_t hi[16], lo[16];
+            tc::tmem_ld<32>(t_d + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
+              v[i] = act_fwd<M::ACT>(v[i] + bv.x, act_prm); v[i + 1] = act_fwd<M::ACT>(v[i + 1] + bv.y, act_prm);
+              v[i + 2] = act_fwd<M::ACT>(v[i + 2] + bv.z, act_prm); v[i + 3] = act_fwd<M::ACT>(v[i + 3] + bv.w, act_prm);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            wd::tmem_st16u(t_hi + c0 / 2, hi);
+            wd::tmem_st16u(t_lo + c0 / 2, lo);
+          }
+          arrive_ops();
+        }
+        // output layer
+        mbar_wait(bar_done, ph_done); ph_done ^= 1;
+        tc::fence_after();
+        float o16[16], u[NU];
+        tc::tmem_ld<16>(t_d, o16);
+        const float* __restrict__ bo = reinterpret_cast<const float*>(sm + C::biaso_off());
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          o16[j] += bo[j];
+          u[j] = bounds_fwd<M::BOUNDS>(o16[j], p.policy.bmin[j], p.policy.bmax[j]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j) args.u_traj[(b * T + t) * NU + j] = u[j];
+          if (args.chk != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) args.chk[(b * T + t) * NU + j] = o16[j];
+          }
+        }
+        float xn[NX], dv_[1] = {0.f};
+        Dyn<S>::step(p, x, u, dv_, xn);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = xn[i];
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1) + t + 1) * NX + i] = x[i];
+        }
+      }
+      if constexpr (S::NTERMS > 0) {
+        if (fused && valid) score_traj_s<S>(p, vtc, b, tsum);
+      }
+    }
+  }
+
+  if constexpr (S::NTERMS > 0) {
+    if (fused) {
+      __syncthreads();
+      static_for<0, S::NTERMS>([&](auto kc) {
+        constexpr int Kq = decltype(kc)::value;
+        double v = static_cast<double>(tsum[Kq]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[Kq * (C::THREADS / 32) + (tid >> 5)] = v;
+      });
+      __syncthreads();
+      if (tid < S::NTERMS) {
+        double v = 0.0;
+        for (int w = 0; w < C::THREADS / 32; ++w) v += red[tid * (C::THREADS / 32) + w];
+        args.term_partials[size_t(blockIdx.x) * NM_MAX_TERMS + tid] = v;
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// ================================================================================================ adjoint
+struct WideBwdArgs {
+  BwdArgs b;
+  uint8_t* staging;              // [tile][step in chunk] items of WideCfg::ITEM_BYTES
+  float* stash;                  // [grid * 2] slots of WideCfg::STASH_SLOT_BYTES
+  float* lam_carry;              // [B][NX] co-state at the chunk boundary
+  wd::ScaleState* scale;         // cotangent scale of this chunk (read), largest scaled cotangent seen (atomic max)
+  int t_lo, t_hi;                // this launch sweeps steps t_hi-1 .. t_lo  (t_hi == nsteps: the first chunk of the pass)
+};
+
+template <class S>
+__global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ WideBwdArgs wargs) {
+  using C = wd::WideCfg<S>;
+  using M = typename C::M;
+  constexpr int NX = S::NX, NU = S::NU, K0 = C::K0, H = C::H, NL = C::NL, TILE = 128, NOUT = C::NOUT;
+  const BwdArgs& args = wargs.b;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);           // 0 weights, 1/2 operands ready (slot), 3/4 MMAs done (slot)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* coef = reinterpret_cast<float*>(bars + 10);                        // [NM_MAX_TERMS]
+  float* dbred = coef + NM_MAX_TERMS;                                       // [8 warps][NOP] output-bias gradient partials
+  VarTable& vt = *reinterpret_cast<VarTable*>(dbred + 8 * C::NOP);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
+  const int T = p.nsteps;
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  const bool pre = !fused && args.G_x != nullptr;
+  const int g_row = (T + 1) * NX + T * (NU + S::NY);
+  int tb_mask = 0;
+  for (int k = 0; k < p.n_terms; ++k) {
+    const NmTerm& tm = p.terms[k];
+    const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
+    const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (live[i] && at[i]->var >= 0 && at[i]->var <= NM_VAR_Y && atom_is_tbcast(*at[i], tm)) tb_mask |= 1 << at[i]->var;
+  }
+  if (tid < NM_MAX_TERMS) coef[tid] = tid < p.n_terms ? term_coef(p, tid, args.grad_scalars, args.b_total) : 0.f;
+  if (tid == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = S::NY;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 128); mbar_init(&bars[2], 128);
+    mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], uint32_t(C::W_BYTES));
+    tma_bulk_g2s(sm, args.wprep, uint32_t(C::W_BYTES), &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  const int t_lo = wargs.t_lo, t_hi = wargs.t_hi, CSn = t_hi - t_lo;
+  const float gs = wargs.scale->gs, inv_gs = wargs.scale->inv_gs;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    const int n0 = wd::slot_rounds(args.num_tiles, 0), n1 = wd::slot_rounds(args.num_tiles, 1);
+    const uint32_t sbase = smem_u32(sm);
+    uint32_t ph[2] = {0, 0};
+    constexpr int NB = 2 * (NL - 1);                 // MMA batches per step: recompute L0..L(NL-2), data gradients L(NL-2)..L0
+    for (int r = 0; r < n0; ++r) {
+      const bool two = r < n1;
+      for (int t = t_hi - 1; t >= t_lo; --t) {
+        static_for<0, NB>([&](auto bc) {
+          constexpr int bi = decltype(bc)::value;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s == 1 && !two) continue;
+            mbar_wait(&bars[1 + s], ph[s]); ph[s] ^= 1;
+            tc::fence_after();
+            const uint32_t cb = tmem + s * C::SLOT_COLS;
+            if (tc::elect_one()) {
+              if constexpr (bi == 0) wd::issue_kmajor<C::K0P, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::img0_off());
+              else if constexpr (bi < NL - 1) wd::issue_kmajor<H, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgh_off(bi));
+              else if constexpr (bi < NB - 1) {      // data gradient of hidden layer l = NL-2 .. 1:  dA_l = dZ_l W_l
+                constexpr int l = (NL - 2) - (bi - (NL - 1));
+                wd::issue_mnmajor<H, H, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgh_off(l));
+              } else wd::issue_mnmajor<H, C::K0P, C::GWP>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::img0_off());
+              tc::commit(&bars[3 + s]);
+            }
+            __syncwarp();
+          }
+        });
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ owners
+    const int slot = warp >> 2, m_ = tid & 127;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t cb = tmem + lane_base + slot * C::SLOT_COLS;
+    const uint32_t t_hi_ = cb + C::A_HI, t_lo_ = cb + C::A_LO, t_d = cb + C::DCOL;
+    uint64_t* bar_ops = &bars[1 + slot];
+    uint64_t* bar_done = &bars[3 + slot];
+    uint32_t ph_done = 0;
+    const float act_prm = p.policy.act_param;
+    auto arrive_ops = [&]() { tc::wait_st(); tc::fence_before(); mbar_arrive(bar_ops); };
+    float4* stash = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(wargs.stash) + size_t(blockIdx.x * 2 + slot) * C::STASH_SLOT_BYTES) + m_;
+    const float* __restrict__ Wout = reinterpret_cast<const float*>(sm + C::wout_off());
+    float dbo[NOUT];                                  // output-bias gradient (scaled), summed over this thread's trajectory-steps
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) dbo[j] = 0.f;
+    float dzmax = 0.f;
+    // staging store of 32 consecutive features (16 packed words) of operand tile `toff`
+    auto stage32 = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[16]) {
+      uint8_t* q = item + toff + (c0 / 8) * C::GRP + m_ * 16;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+    };
+
+    for (int r = 0;; ++r) {
+      const int tile = (r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot;
+      if (tile >= args.num_tiles) break;
+      const int64_t b_raw = int64_t(tile) * TILE + m_;
+      const bool valid = b_raw < args.B;
+      const int64_t b = valid ? b_raw : args.B - 1;
+      float lam[NX], x_pre[NX], o_pre[NU], in_pre[K0];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { lam[i] = 0.f; x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + (t_hi - 1)) * NX + i); }
+#pragma unroll
+      for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + (t_hi - 1)) * NU + j);
+      tc_policy_input<S, K0>(p, args.exo, b, t_hi - 1, x_pre, in_pre);
+      if (t_hi == T) {
+        if (valid) {
+          if (pre) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
+            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+          } else {
+            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, T, lam); }
+            else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
+            if (args.gx_ext != nullptr) {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam[i] = valid ? wargs.lam_carry[b * NX + i] : 0.f;
+      }
+#pragma unroll 1
+      for (int t = t_hi - 1; t >= t_lo; --t) {
+        uint8_t* item = wargs.staging + (size_t(tile) * CSn + size_t(t - t_lo)) * C::ITEM_BYTES;
+        float x[NX], o_cur[NU], in[K0], yv[1] = {0.f};
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = x_pre[i];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) o_cur[j] = o_pre[j];
+#pragma unroll
+        for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
+        tc_policy_state<S, K0>(x, yv, in);
+        {
+          uint32_t hi0[C::K0P / 2];
+          wd::put_input<C>(t_hi_, t_lo_, in, hi0);
+          uint8_t* q = item + C::a_off(0) + m_ * 16;
+#pragma unroll
+          for (int g = 0; g < C::K0P / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi0[4 * g], hi0[4 * g + 1], hi0[4 * g + 2], hi0[4 * g + 3]);
+        }
+        arrive_ops();                                 // -> recompute of layer 0
+        if (t > 0) {                                  // next step's inputs (also across the chunk boundary: harmless)
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
+#pragma unroll
+          for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + t - 1) * NU + j);
+          tc_policy_input<S, K0>(p, args.exo, b, t - 1, x, in_pre);
+        }
+        // ---- dynamics adjoint, loss-term gradients, cotangent of the raw policy output (all while the MMAs run)
+        float u[NU], gx[NX], gu[NU], gtx[NX], cot[NOUT];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) gtx[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) u[j] = bounds_fwd<M::BOUNDS>(o_cur[j], p.policy.bmin[j], p.policy.bmax[j]);
+        Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
+        if (valid) {
+          if (pre) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.G_x + b * g_row + (T + 1) * NX + t * NU + j);
+            if (tb_mask & 2) term_grad_accum_ool<NU, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) gtx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
+            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gtx);
+          } else {
+            if (fused) {
+              if constexpr (S::NTERMS > 0) {
+                term_grad_s<S, NM_VAR_U, NU, NU>(p, vtc, coef, b, t, gu);
+                term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, t, gtx);
+              }
+            } else {
+              term_grad_accum_ool<NU, 0>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+              term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gtx);
+            }
+            if (args.gu_ext != nullptr) {
+#pragma unroll
+              for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
+            }
+            if (args.gx_ext != nullptr) {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) gtx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) {
+          cot[j] = valid ? gu[j] * bounds_deriv<M::BOUNDS>(o_cur[j], p.policy.bmin[j], p.policy.bmax[j]) * gs : 0.f;
+          dbo[j] += cot[j];
+          dzmax = fmaxf(dzmax, fabsf(cot[j]));
+        }
+        {                                             // cotangent tile (NOP halves): weight gradient of the output layer
+          uint32_t ch[C::NOP / 2];
+#pragma unroll
+          for (int i = 0; i < C::NOP / 2; ++i) {
+            const float c0 = 2 * i < NOUT ? cot[2 * i < NOUT ? 2 * i : 0] : 0.f, c1 = 2 * i + 1 < NOUT ? cot[2 * i + 1 < NOUT ? 2 * i + 1 : 0] : 0.f;
+            const __half2 h2 = __floats2half2_rn(c0, c1);
+            ch[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          uint8_t* q = item + C::c_off() + m_ * 16;
+#pragma unroll
+          for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3]);
+        }
+        // ---- recompute: a_{l+1} = act(z_l), derivative stash; the last one goes straight into the backward pass
+#pragma unroll 1
+        for (int l = 0; l < NL - 1; ++l) {
+          const float* __restrict__ bias = reinterpret_cast<const float*>(sm + C::bias_off(0)) + l * H;
+          const bool last = l == NL - 2;
+          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          tc::fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < H; c0 += 32) {
+            float v[32], d[32];
+            uint32_t hi[16], lo[16];
+            tc::tmem_ld<32>(t_d + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
+              tc::act_ad<M::ACT>(v[i] + bv.x, act_prm, v[i], d[i]); tc::act_ad<M::ACT>(v[i + 1] + bv.y, act_prm, v[i + 1], d[i + 1]);
+              tc::act_ad<M::ACT>(v[i + 2] + bv.z, act_prm, v[i + 2], d[i + 2]); tc::act_ad<M::ACT>(v[i + 3] + bv.w, act_prm, v[i + 3], d[i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            stage32(item, C::a_off(1) + l * (H / 8) * C::GRP, c0, hi);                    // a_{l+1}
+            if (!last) {
+              wd::tmem_st16u(t_hi_ + c0 / 2, hi);
+              wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) stash[(l * (H / 4) + (c0 + i) / 4) * 128] = make_float4(d[i], d[i + 1], d[i + 2], d[i + 3]);
+            } else {
+              // output layer backward on the CUDA cores: dA[k] = sum_j cot[j] W_out[j][k];  dZ_{NL-2} = dA * act'
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float da0 = 0.f, da1 = 0.f, da2 = 0.f, da3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < NOUT; ++j) {
+                  const float4 w = *reinterpret_cast<const float4*>(Wout + j * H + c0 + i);
+                  da0 = fmaf(cot[j], w.x, da0); da1 = fmaf(cot[j], w.y, da1); da2 = fmaf(cot[j], w.z, da2); da3 = fmaf(cot[j], w.w, da3);
+                }
+                v[i] = da0 * d[i]; v[i + 1] = da1 * d[i + 1]; v[i + 2] = da2 * d[i + 2]; v[i + 3] = da3 * d[i + 3];
+              }
+              if (c0 == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+              stage32(item, C::z_off(NL - 2), c0, hi);                                   // dZ_{NL-2}
+              wd::tmem_st16u(t_hi_ + c0 / 2, hi);
+              wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+            }
+          }
+          arrive_ops();                               // -> recompute of layer l+1, or (last) data gradient of layer NL-2
+        }
+        // ---- data gradients: D = dA_l (cotangent of a_l), l = NL-2 .. 1;  dZ_{l-1} = dA_l * act'(z_{l-1})
+#pragma unroll 1
+        for (int l = NL - 2; l >= 1; --l) {
+          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          tc::fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < H; c0 += 32) {
+            float v[32];
+            uint32_t hi[16], lo[16];
+            float4 dq[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dq[i] = stash[((l - 1) * (H / 4) + c0 / 4 + i) * 128];
+            tc::tmem_ld<32>(t_d + c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[4 * i] *= dq[i].x; v[4 * i + 1] *= dq[i].y; v[4 * i + 2] *= dq[i].z; v[4 * i + 3] *= dq[i].w; }
+            if (c0 == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            stage32(item, C::z_off(l - 1), c0, hi);                                       // dZ_{l-1}
+            wd::tmem_st16u(t_hi_ + c0 / 2, hi);
+            wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+          }
+          arrive_ops();                               // -> data gradient of layer l-1
+        }
+        // ---- gradient of the policy input (state segment) closes the loop
+        mbar_wait(bar_done, ph_done); ph_done ^= 1;
+        tc::fence_after();
+        {
+          float gin[C::GWP];
+#pragma unroll
+          for (int c0 = 0; c0 < C::GWP; c0 += 16) {
+            float g16[16];
+            tc::tmem_ld<16>(t_d + c0, g16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gin[c0 + i] = g16[i] * inv_gs;
+          }
+          int off = 0;
+          static_for<0, S::NSEG>([&](auto sc) {
+            constexpr int sg = decltype(sc)::value;
+            if constexpr (S::seg_kind(sg) == NM_SEG_STATE) {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) gx[i] += gin[off + i];
+            }
+            off += S::seg_width(sg);
+          });
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] + gtx[i] : 0.f;
+      }
+      if (valid) {
+        if (t_lo == 0) {
+          if (args.grad_x0 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) args.grad_x0[b * NX + i] = lam[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) wargs.lam_carry[b * NX + i] = lam[i];
+        }
+      }
+    }
+    // ---- output-bias gradient and the scale statistics of this launch (fixed order: deterministic)
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+      float v = dbo[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) dbred[warp * C::NOP + j] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dzmax = fmaxf(dzmax, __shfl_xor_sync(0xffffffffu, dzmax, o));
+    if ((tid & 31) == 0) atomicMax(&wargs.scale->max_bits, __float_as_uint(dzmax));
+    wd::named_bar_sync(1, 256);
+    if (tid < NOUT && C::BIAS && p.policy.trainable) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += dbred[w * C::NOP + tid];
+      float* gb = args.grad_partials + size_t(blockIdx.x) * size_t(p.n_params) + p.policy.param_offset + C::p_off(NL - 1) + NOUT * H + tid;
+      *gb += s * inv_gs;
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// next chunk's cotangent scale: the largest scaled cotangent seen goes to ~2^6 (fp16 overflows at 2^16)
+static __global__ void nm_wide_scale_update_kernel(wd::ScaleState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float m = __uint_as_float(st->max_bits);
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);                                  // m = f * 2^e, f in [0.5, 1)
+      int shift = 6 - e;
+      shift = shift > 40 ? 40 : (shift < -40 ? -40 : shift);
+      const float g = ldexpf(st->gs, shift);
+      if (g > 1e-30f && g < 1e30f) { st->gs = g; st->inv_gs = 1.f / g; }
+    }
+    st->max_bits = 0u;
+  }
+}
+static __global__ void nm_wide_scale_init_kernel(wd::ScaleState* st, float gs0) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { st->gs = gs0; st->inv_gs = 1.f / gs0; st->max_bits = 0u; st->pad = 0u; }
+}
+
+// ================================================================================================ weight-gradient GEMM
+// One work item = one staged tile-step.  warp 0: bulk-TMA producer (per layer unit: the dZ tile and the input tile into a
+// 3-slot ring); warp 1: MMA issuer, D_l[n][k] += sum_m dZ_l[m][n] a_l[m][k] (both operands MN-major, contraction over the
+// 128 trajectories, 8 MMAs of K = 16) plus the bias sums against a constant tile whose feature 0 is 1; warps 2..5: every
+// WG_FLUSH_ITEMS items (the TMEM accumulator truncates: chains stay short) add the accumulators, un-scaled, to this
+// CTA's private gradient block (plain read-modify-write: nobody else touches it).
+template <class S>
+__global__ void __launch_bounds__(wd::WideCfg<S>::WG_THREADS, 1) nm_wide_wgrad_kernel(const __grid_constant__ NmPlan plan, const uint8_t* __restrict__ staging,
+                                                                                      int64_t n_items, const wd::ScaleState* __restrict__ scale,
+                                                                                      float* __restrict__ grad_partials) {
+  using C = wd::WideCfg<S>;
+  constexpr int NL = C::NL, H = C::H, FL = C::WG_FLUSH_ITEMS;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::WG_BAR_OFF);        // 0..2 full, 3..5 empty, 6 accumulators ready, 7 accumulators free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const NmPlan& p = plan;
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[3 + i], 1); }
+    mbar_init(&bars[6], 1); mbar_init(&bars[7], 128);
+    mbar_fence_init();
+  }
+  // constant tile [2 groups][128][8] halves: feature 0 = 1
+  for (int i = tid; i < 2 * C::GRP / 4; i += C::WG_THREADS) reinterpret_cast<uint32_t*>(sm + C::WG_ONES_OFF)[i] = 0u;
+  __syncthreads();
+  if (tid < 128) *reinterpret_cast<__half*>(sm + C::WG_ONES_OFF + tid * 16) = __float2half_rn(1.f);
+  if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+  tc::fence_async_smem();
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
+  int64_t my_items = 0;
+  for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) ++my_items;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    uint32_t ph_empty[3] = {0, 0, 0};
+    int64_t q = 0;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const uint8_t* item = staging + size_t(it) * C::ITEM_BYTES;
+      static_for<0, NL>([&](auto lc) {
+        constexpr int l = decltype(lc)::value;
+        const int slot = int(q % 3);
+        if (q >= 3) { mbar_wait(&bars[3 + slot], ph_empty[slot]); ph_empty[slot] ^= 1; }
+        uint8_t* dst = sm + slot * C::WG_SLOT_BYTES;
+        if (tc::elect_one()) {
+          if constexpr (l < NL - 1) {
+            constexpr uint32_t za = (H / 8) * C::GRP, ab = (l == 0 ? C::K0P / 8 : H / 8) * C::GRP;
+            mbar_expect_tx(&bars[slot], za + ab);
+            tma_bulk_g2s(dst, item + C::z_off(l), za, &bars[slot]);
+            tma_bulk_g2s(dst + (H / 8) * C::GRP, item + C::a_off(l), ab, &bars[slot]);
+          } else {
+            constexpr uint32_t aa = (H / 8) * C::GRP, cb = (C::NOP / 8) * C::GRP;
+            mbar_expect_tx(&bars[slot], aa + cb);
+            tma_bulk_g2s(dst, item + C::a_off(NL - 1), aa, &bars[slot]);
+            tma_bulk_g2s(dst + (H / 8) * C::GRP, item + C::c_off(), cb, &bars[slot]);
+          }
+        }
+        __syncwarp();
+        ++q;
+      });
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    uint32_t ph_full[3] = {0, 0, 0}, ph_free = 0;
+    int64_t q = 0, done = 0;
+    const uint32_t sbase = smem_u32(sm);
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const uint32_t fresh = (done % FL) == 0 ? 0u : 1u;
+      static_for<0, NL>([&](auto lc) {
+        constexpr int l = decltype(lc)::value;
+        const int slot = int(q % 3);
+        mbar_wait(&bars[slot], ph_full[slot]); ph_full[slot] ^= 1;
+        tc::fence_after();
+        const uint32_t a0 = sbase + slot * C::WG_SLOT_BYTES, b0 = a0 + (H / 8) * C::GRP;
+        // MN-major tiles X[f/8][128][8]: 8-feature groups GRP apart (SBO), 8-trajectory groups 128 B apart (LBO); K step = 16 trajectories = 256 B
+        const uint64_t da = tc::smem_desc(a0, 128, C::GRP), db = tc::smem_desc(b0, 128, C::GRP);
+        const uint64_t dones = tc::smem_desc(sbase + C::WG_ONES_OFF, 128, C::GRP);
+        if (tc::elect_one()) {
+          constexpr int N = l == 0 ? C::K0P : (l < NL - 1 ? H : C::NOP);
+          constexpr uint32_t idesc = wd::idesc_f16(128, N, 1, 1), idesc_b = wd::idesc_f16(128, 16, 1, 1);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) wd::mma_ss(tmem + C::wg_col(l), tc::desc_add(da, ks * 256), tc::desc_add(db, ks * 256), idesc, ks > 0 ? 1u : fresh);
+          if constexpr (l < NL - 1 && C::BIAS) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) wd::mma_ss(tmem + C::wgb_col(l), tc::desc_add(da, ks * 256), tc::desc_add(dones, ks * 256), idesc_b, ks > 0 ? 1u : fresh);
+          }
+          tc::commit(&bars[3 + slot]);
+        }
+        __syncwarp();
+        ++q;
+      });
+      ++done;
+      if ((done % FL) == 0 || done == my_items) {
+        if (tc::elect_one()) tc::commit(&bars[6]);
+        __syncwarp();
+        mbar_wait(&bars[7], ph_free); ph_free ^= 1;
+        tc::fence_after();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ flush warps: thread = accumulator lane
+    const int q4 = warp & 3, lane_n = q4 * 32 + (tid & 31);
+    const uint32_t lane_base = uint32_t(q4 * 32) << 16;
+    uint32_t ph_rdy = 0;
+    const float inv_gs = scale->inv_gs;
+    float* gblock = grad_partials + size_t(blockIdx.x) * size_t(p.n_params) + p.policy.param_offset;
+    const bool train = p.policy.trainable != 0;
+    int64_t done = 0;
+    while (done < my_items) {
+      done = done + FL < my_items ? done + FL : my_items;
+      mbar_wait(&bars[6], ph_rdy); ph_rdy ^= 1;
+      tc::fence_after();
+      if (train) {
+        static_for<0, NL - 1>([&](auto lc) {
+          constexpr int l = decltype(lc)::value;
+          constexpr int Kl = C::kin(l);
+          float* dst = gblock + C::p_off(l) + lane_n * Kl;
+#pragma unroll 1
+          for (int c0 = 0; c0 < Kl; c0 += 8) {
+            float v[8];
+            tc::tmem_ld<8>(tmem + lane_base + C::wg_col(l) + c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c0 + i < Kl) dst[c0 + i] += v[i] * inv_gs;
+          }
+          if constexpr (C::BIAS) {
+            float v[8];
+            tc::tmem_ld<8>(tmem + lane_base + C::wgb_col(l), v);
+            gblock[C::p_off(l) + H * Kl + lane_n] += v[0] * inv_gs;
+          }
+        });
+        {   // output layer: accumulator lanes = input features k, columns = outputs j
+          float v[16];
+          tc::tmem_ld<16>(tmem + lane_base + C::wg_col(NL - 1), v);
+          float* dst = gblock + C::p_off(NL - 1);
+#pragma unroll
+          for (int j = 0; j < C::NOUT; ++j) dst[j * H + lane_n] += v[j] * inv_gs;
+        }
+      }
+      tc::fence_before();
+      mbar_arrive(&bars[7]);
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace nm
+#endif  // NM_HOST_EMU
