@@ -419,7 +419,8 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   if (rc != NM_OK) return rc;
   const double* partials = c.term_partials;            // written by the rollout kernel when fused
   int pgrid = c.grid;
-  if (!fused && plan->n_terms > 0) {
+  const bool api_scores = plan->n_terms > 0 && !(fused && c.scored);
+  if (api_scores) {
     double* sp = reinterpret_cast<double*>(static_cast<char*>(workspace) + align256(spec_f));
     const nm::VarTable vt = make_vartable(plan, x_traj, u_traj, y_traj, exo);
     nm_term_score_kernel<<<sgrid, kScoreThreads, 0, c.stream>>>(*plan, vt, B, max_term_steps(plan), sp);
@@ -428,7 +429,7 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   nm_loss_finalize_kernel<<<1, 256, 0, c.stream>>>(*plan, partials, pgrid, B, scalars);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
-  g_launches = ((!fused && plan->n_terms > 0) ? 4 : 3) + c.extra_launches;   // weight prep + rollout [+ term scoring] + loss finalise
+  g_launches = (api_scores ? 4 : 3) + c.extra_launches;   // weight prep + rollout [+ term scoring] + loss finalise
   return NM_OK;
 }
 

@@ -11,6 +11,7 @@ struct NmFwdCall {
   int fused_terms;                                 // in: plan terms match the entry's compiled term structure
   double* term_partials; int grid;                 // out: per-CTA term sums (fused), CTAs launched
   int extra_launches;                              // out: kernels launched besides weight prep + rollout
+  int scored;                                      // out: the rollout kernel wrote term_partials (else the API scores the terms)
 };
 struct NmBwdCall {
   const float* params; const float* const* exo;

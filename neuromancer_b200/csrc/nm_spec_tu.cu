@@ -175,7 +175,7 @@ template <class Sp, bool ON> struct Wide {
   static cudaError_t setup() { return cudaSuccess; }
   static int chunk_steps(int64_t, int) { return 1; }
   static size_t bwd_extra(int64_t, int, int) { return 0; }
-  static void launch_fwd(const NmPlan&, const FwdArgs&, const float*, void*, int, cudaStream_t) {}
+  static int launch_fwd(const NmPlan&, const FwdArgs&, const float*, void*, int, cudaStream_t) { return 0; }
   static int launch_bwd(const NmPlan&, const BwdArgs&, const float*, void*, char*, int, int, cudaStream_t) { return 0; }
   static void info(char*, size_t, int, int, size_t, int, int) {}
 };
@@ -186,6 +186,12 @@ template <class Sp> struct Wide<Sp, true> {
     cudaError_t e = cudaFuncSetAttribute(nm_wide_fwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_wide_bwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_wide_wgrad_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::WG_SMEM_BYTES);
+    if (e == cudaSuccess) {                          // L2 set-aside for the evict_last derivative stash (57 MB on 148 SMs)
+      int dev = 0, maxp = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && maxp > 0)
+        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(maxp));
+      (void)cudaGetLastError();
+    }
     return e;
   }
   // steps per adjoint launch: the staging buffer (tiles * CS items of ITEM_BYTES) is capped at NM_WIDE_STAGING_GB (default 16)
@@ -206,12 +212,28 @@ template <class Sp> struct Wide<Sp, true> {
   static size_t staging_bytes(int64_t B, int T) { return a256(size_t((B + 127) / 128) * size_t(chunk_steps(B, T)) * size_t(C::ITEM_BYTES)); }
   static size_t stash_bytes(int sms) { return a256(size_t(sms) * 2 * size_t(C::STASH_SLOT_BYTES)); }
   static size_t carry_bytes(int64_t B) { return a256(size_t(B) * Sp::NX * sizeof(float)); }
-  // [scale state 256 B | co-state carry | derivative stash | staging]
-  static size_t bwd_extra(int64_t B, int T, int sms) { return 256 + carry_bytes(B) + stash_bytes(sms) + staging_bytes(B, T); }
+  static size_t g_bytes(int64_t B, int T) { return a256(size_t(B) * size_t(chunk_steps(B, T) + 1) * size_t(Sp::NX + Sp::NU) * sizeof(float)); }
+  // [scale state 256 B | co-state carry | derivative stash | chunk term gradients | staging]
+  static size_t bwd_extra(int64_t B, int T, int sms) { return 256 + carry_bytes(B) + stash_bytes(sms) + g_bytes(B, T) + staging_bytes(B, T); }
   static int grid_for(int64_t B, int sms) { const int64_t pairs = ((B + 127) / 128 + 1) / 2; return int(pairs < sms ? pairs : sms); }
-  static void launch_fwd(const NmPlan& p, const FwdArgs& a, const float* params, void* wprep, int sms, cudaStream_t st) {
+  static int score_grid(const NmPlan& p, int64_t B, int sms) {
+    int tmax = 1;
+    for (int k = 0; k < p.n_terms; ++k) tmax = p.terms[k].t_len > tmax ? p.terms[k].t_len : tmax;
+    const int64_t g = (B * tmax + 255) / 256;
+    return int(g < int64_t(sms) * 8 ? (g < 1 ? 1 : g) : int64_t(sms) * 8);
+  }
+  // returns the number of blocks that wrote term partials (0: the caller scores the terms)
+  static int launch_fwd(const NmPlan& p, const FwdArgs& a, const float* params, void* wprep, int sms, cudaStream_t st) {
     wd::nm_wide_prep_kernel<Sp><<<32, 256, 0, st>>>(p, params, static_cast<uint8_t*>(wprep));
     nm_wide_fwd_kernel<Sp><<<grid_for(a.B, sms), C::THREADS, C::SMEM_BYTES, st>>>(p, a);
+    if (Sp::NTERMS > 0 && a.fused_terms) {
+      int tmax = 1;
+      for (int k = 0; k < p.n_terms; ++k) tmax = p.terms[k].t_len > tmax ? p.terms[k].t_len : tmax;
+      const int g = score_grid(p, a.B, sms);
+      nm_wide_score_kernel<Sp><<<g, 256, 0, st>>>(p, a, tmax);
+      return g;
+    }
+    return 0;
   }
   // returns the number of kernels launched; `extra` is the wide region of the backward workspace, `nblocks` gradient blocks are zeroed
   static int launch_bwd(const NmPlan& p, const BwdArgs& a, const float* params, void* wprep, char* extra, int sms, int nblocks, cudaStream_t st) {
@@ -221,7 +243,8 @@ template <class Sp> struct Wide<Sp, true> {
     wd::ScaleState* scale = reinterpret_cast<wd::ScaleState*>(extra);
     float* carry = reinterpret_cast<float*>(extra + 256);
     float* stash = reinterpret_cast<float*>(extra + 256 + carry_bytes(a.B));
-    uint8_t* staging = reinterpret_cast<uint8_t*>(extra + 256 + carry_bytes(a.B) + stash_bytes(sms));
+    float* G = reinterpret_cast<float*>(extra + 256 + carry_bytes(a.B) + stash_bytes(sms));
+    uint8_t* staging = reinterpret_cast<uint8_t*>(extra + 256 + carry_bytes(a.B) + stash_bytes(sms) + g_bytes(a.B, T));
     // initial cotangent scale: the largest term coefficient w / (B_total * t_len * d_len) goes to ~2^4
     double cmax = 0.0;
     for (int k = 0; k < p.n_terms; ++k) {
@@ -240,13 +263,40 @@ template <class Sp> struct Wide<Sp, true> {
     for (int t_hi = T; t_hi > 0; t_hi -= CS) {
       const int t_lo = t_hi - CS > 0 ? t_hi - CS : 0;
       WideBwdArgs w{};
-      w.b = a; w.staging = staging; w.stash = stash; w.lam_carry = carry; w.scale = scale; w.t_lo = t_lo; w.t_hi = t_hi;
+      w.b = a; w.staging = staging; w.stash = stash; w.lam_carry = carry; w.scale = scale; w.G = G; w.t_lo = t_lo; w.t_hi = t_hi;
+      {
+        const int64_t n = a.B * int64_t(t_hi - t_lo + 1);
+        int64_t g = (n + 255) / 256;
+        if (g > int64_t(sms) * 16) g = int64_t(sms) * 16;
+        nm_wide_termgrad_kernel<Sp><<<int(g), 256, 0, st>>>(p, a, G, t_lo, t_hi);
+        // time-broadcast atoms anchored inside this chunk: one warp per trajectory sums the range
+        WideTbAnchors an{};
+        for (int k = 0; k < p.n_terms && an.n < 8; ++k) {
+          const NmTerm& tm = p.terms[k];
+          const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
+          const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
+          for (int i = 0; i < 4 && an.n < 8; ++i) {
+            if (!live[i] || !(at[i]->var == NM_VAR_X || at[i]->var == NM_VAR_U) || !(at[i]->t_len == 1 && tm.t_len > 1)) continue;
+            const int t0 = at[i]->t_start;
+            const bool in_chunk = at[i]->var == NM_VAR_X ? (t0 >= t_lo && (t0 < t_hi || (t0 == t_hi && t_hi == T))) : (t0 >= t_lo && t0 < t_hi);
+            bool seen = false;
+            for (int q = 0; q < an.n; ++q) seen = seen || (an.var[q] == at[i]->var && an.t[q] == t0);
+            if (in_chunk && !seen) { an.var[an.n] = at[i]->var; an.t[an.n] = t0; ++an.n; }
+          }
+        }
+        if (an.n > 0) {
+          int64_t gw = (a.B * 32 + 255) / 256;
+          if (gw > int64_t(sms) * 16) gw = int64_t(sms) * 16;
+          nm_wide_termgrad_tb_kernel<Sp><<<int(gw), 256, 0, st>>>(p, a, an, G, t_lo, t_hi);
+          ++launches;
+        }
+      }
       nm_wide_bwd_kernel<Sp><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(p, w);
       const int64_t n_items = tiles * int64_t(t_hi - t_lo);
       const int wgrid = int(n_items < sms ? n_items : sms);
       nm_wide_wgrad_kernel<Sp><<<wgrid, C::WG_THREADS, C::WG_SMEM_BYTES, st>>>(p, staging, n_items, scale, a.grad_partials);
       nm_wide_scale_update_kernel<<<1, 32, 0, st>>>(scale);
-      launches += 3;
+      launches += 4;
     }
     return launches;
   }
@@ -362,7 +412,9 @@ int workspace_fn(const NmPlan* p, int64_t B, size_t* fwd, size_t* bwd) {
   }
   // (hoist: E[B][T][N0] in the forward workspace when the caller gives no checkpoint buffer; E recomputed / dZ_1 in the backward one)
   if (kWide && gb < sms) gb = sms;                   // the wide adjoint / weight-gradient GEMM own one gradient block per SM
-  *fwd = kWprepBytes + align256(size_t(gf > 0 ? gf : 1) * NM_MAX_TERMS * sizeof(double)) + hoist_bytes(p, B);
+  int64_t gfw = gf;
+  if (kWide && gfw < int64_t(sms) * 8) gfw = int64_t(sms) * 8;   // blocks of the streaming scoring kernel
+  *fwd = kWprepBytes + align256(size_t(gfw > 0 ? gfw : 1) * NM_MAX_TERMS * sizeof(double)) + hoist_bytes(p, B);
   *bwd = kWprepBytes + align256(size_t(gb > 0 ? gb : 1) * size_t(p->n_params > 0 ? p->n_params : 1) * sizeof(float)) + hoist_bytes(p, B);
   if (kWide) *bwd = align256(*bwd) + WD::bwd_extra(B, p->nsteps, sms);
   return NM_OK;
@@ -419,7 +471,12 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
     }
     a.pre = E;
   }
-  if (kWide) WD::launch_fwd(*p, a, c->params, wprep, d->sms, c->stream);
+  c->scored = c->fused_terms ? 1 : 0;
+  if (kWide) {                                       // scoring: a streaming kernel behind the rollout (compiled term structure), else the API's
+    const int sg = WD::launch_fwd(*p, a, c->params, wprep, d->sms, c->stream);
+    c->scored = sg > 0 ? 1 : 0;
+    if (sg > 0) { c->grid = sg; c->extra_launches += 1; }
+  }
   else if (kTcFwd) TcFwd<NM_SPEC_NAME, kTcFwd>::launch(*p, a, c->params, wprep, grid, c->stream);
   else nm_fwd_kernel<SF><<<grid, SF::THREADS, KCF::FWD_SMEM_BYTES, c->stream>>>(*p, a);
   cudaError_t e = cudaGetLastError();

@@ -134,6 +134,50 @@ __device__ __forceinline__ void term_grad_accum(const NmPlan& p, const VarTable&
   }
 }
 
+// Time-broadcast atoms only (MODE 2 of term_grad_accum), evaluated by a whole WARP for one trajectory entry row: the
+// range of time elements the anchored entry participates in is strided over the lanes; the caller sums g over the lanes.
+template <int MAXD>
+__device__ __forceinline__ void term_grad_accum_tb_lanes(const NmPlan& p, const VarTable& vt, const float* __restrict__ coef,
+                                                         int64_t b, int var, int t_idx, int dim, int lane, float (&g)[MAXD]) {
+  for (int k = 0; k < p.n_terms; ++k) {
+    const NmTerm& tm = p.terms[k];
+    const float ck = coef[k];
+    if (ck == 0.f) continue;
+#pragma unroll
+    for (int which = 0; which < 4; ++which) {
+      const NmSide& side = which < 2 ? tm.lhs : tm.rhs;
+      const bool second = which & 1;
+      if (second && side.op == NM_OP_NONE) continue;
+      const NmAtom& at = second ? side.b : side.a;
+      if (at.var != var || !atom_is_tbcast(at, tm) || t_idx != at.t_start) continue;
+      const float side_sign = (which < 2) ? (tm.cmp == NM_CMP_GT ? -1.f : 1.f) : (tm.cmp == NM_CMP_GT ? 1.f : -1.f);
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) {
+        if (d >= dim) break;
+        int de_lo, de_hi;
+        if (at.d_len == 1) {
+          if (d != at.d_start) continue;
+          de_lo = 0; de_hi = tm.d_len;
+        } else {
+          const int de = d - at.d_start;
+          if (de < 0 || de >= at.d_len) continue;
+          de_lo = de; de_hi = de + 1;
+        }
+        float acc = 0.f;
+        for (int te = lane; te < tm.t_len; te += 32)
+          for (int de = de_lo; de < de_hi; ++de) {
+            const float v = term_value(tm, vt, b, te, de);
+            float dv = term_dpenalty(tm, v) * side_sign;
+            if (side.op == NM_OP_SUB && second) dv = -dv;
+            else if (side.op == NM_OP_MUL) dv *= atom_value(second ? side.a : side.b, vt, b, te, de);
+            acc += dv;
+          }
+        g[d] = fmaf(ck * at.scale, acc, g[d]);
+      }
+    }
+  }
+}
+
 // ---- pre-resolved atoms: hoist the (b, te) addressing out of the per-dimension loop -------------
 struct AtomRef { const float* p; int dstep; float scale, offset; };
 __device__ __forceinline__ AtomRef atom_ref(const NmAtom& a, const VarTable& vt, int64_t b, int te) {
@@ -298,15 +342,17 @@ __device__ __forceinline__ void score_traj_s(const NmPlan& p, const VarTable& vt
 }
 
 // d(sum_k coef_k * penalty sums)/d VAR[b, t_idx, 0..DIM)  accumulated into g
-template <class S, int VAR, int DIM, int DIMA>
+// MODE 0: every atom; 1: skip time-broadcast atoms; 2: time-broadcast atoms only (see term_grad_entry)
+// (te0, te_stride): the time range of a time-broadcast atom may be strided over the lanes of a warp (the caller sums)
+template <class S, int VAR, int DIM, int DIMA, int MODE = 0>
 __device__ __forceinline__ void term_grad_s(const NmPlan& p, const VarTable& vt, const float* __restrict__ coef,
-                                            int64_t b, int t_idx, float (&g)[DIMA]) {
+                                            int64_t b, int t_idx, float (&g)[DIMA], int te0 = 0, int te_stride = 1) {
   static_for<0, S::NTERMS>([&](auto kc) {
     constexpr int K = decltype(kc)::value;
     static_for<0, 4>([&](auto wc) {
       constexpr int W = decltype(wc)::value;
       using A = AtomS<S, K, W>;
-      if constexpr (A::VAR == VAR) {
+      if constexpr (A::VAR == VAR && !(MODE == 1 && A::TB) && !(MODE == 2 && !A::TB)) {
         const NmTerm& tm = p.terms[K];
         const NmAtom& at = pick_atom<W>(tm);
         constexpr float side_sign = (W < 2) ? (S::t_cmp(K) == NM_CMP_GT ? -1.f : 1.f) : (S::t_cmp(K) == NM_CMP_GT ? 1.f : -1.f);
@@ -343,7 +389,7 @@ __device__ __forceinline__ void term_grad_s(const NmPlan& p, const VarTable& vt,
             if constexpr (A::DB) { if (d != at.d_start) continue; de_lo = 0; de_hi = tm.d_len; }
             else { const int de = d - at.d_start; if (de < 0 || de >= at.d_len) continue; de_lo = de; de_hi = de + 1; }
             float acc = 0.f;
-            for (int te = te_lo; te < te_hi; ++te)
+            for (int te = te_lo + (A::TB ? te0 : 0); te < te_hi; te += (A::TB ? te_stride : 1))
               for (int de = de_lo; de < de_hi; ++de) {
                 float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
                 if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te, de);

@@ -14,7 +14,8 @@
 //     CUDA cores only do activations, operand splitting, dynamics and loss terms.
 // Thread = trajectory = TMEM lane (as in nm_tc_kernels.cuh); one CTA per SM holds TWO 128-trajectory tiles in
 // tensor memory (2 x [A_hi 64 | A_lo 64 | D 128] columns) that ping-pong between the tensor pipe and their owner
-// warps; a ninth warp issues every MMA.
+// warps; the first warp of each slot issues the slot's MMAs once all 128 operand rows have arrived (a ninth warp
+// would cost every thread 56 registers: the register file is allocated per 4 warps).
 //
 // Adjoint: recompute (3-product) + data gradients (3-product, cotangents carried scaled by a power of two `gs` so that
 // they sit in fp16 range) in nm_wide_bwd_kernel; the WEIGHT gradients are a separate streaming GEMM
@@ -61,8 +62,20 @@ __device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// L2 residency: the derivative stash is rewritten and re-read every step (evict_last keeps it out of DRAM); the staging
+// tiles are written once and read by a later kernel (evict_first: they must not push the stash out)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol)); return pol; }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol)); return pol; }
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_global_f4(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld_global_f4(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+  return v;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
@@ -119,7 +132,7 @@ struct WideCfg {
   // ---- tensor memory: two tile slots of [A_hi H/2 | A_lo H/2 | D H] columns
   static constexpr int SLOT_COLS = 2 * H, A_HI = 0, A_LO = H / 2, DCOL = H;
   // ---- launch shape
-  static constexpr int THREADS = 288;
+  static constexpr int THREADS = 256;                                     // 2 tile slots x 4 owner warps (register file: allocation is per 4 warps)
   // ---- adjoint: staging item (one tile-step), byte offsets of the operand tiles X[feature/8][128][8] halves
   static constexpr int GRP = 128 * 16;                                    // one 8-feature group of a tile
   static constexpr int a_off(int l) { return l == 0 ? 0 : (K0P / 8) * GRP + (l - 1) * (H / 8) * GRP; }       // a_l, l = 0..NL-1
@@ -242,6 +255,8 @@ __device__ __forceinline__ int slot_rounds(int num_tiles, int slot) {
 }  // namespace wd
 
 // ================================================================================================ forward
+// (PenaltyLoss scoring is NOT fused here: read back per trajectory it is a chain of L2-latency loads during which both
+// tile slots and the tensor pipe idle -- measured 45 % of this kernel; the streaming nm_term_score_kernel does it at HBM rate)
 template <class S>
 __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
   using C = wd::WideCfg<S>;
@@ -250,12 +265,8 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
   extern __shared__ __align__(1024) uint8_t sm[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);           // 0 weights, 1/2 operands ready (slot), 3/4 MMAs done (slot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  double* red = reinterpret_cast<double*>(sm);                              // end-of-kernel reduction scratch (weights dead)
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
-  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
-  constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
-  const bool fused = S::NTERMS > 0 && args.fused_terms;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 128); mbar_init(&bars[2], 128);
@@ -273,38 +284,8 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
   }
   mbar_wait(&bars[0], 0);
   const int T = p.nsteps;
-  float tsum[NT];
-#pragma unroll
-  for (int q = 0; q < NT; ++q) tsum[q] = 0.f;
 
-  if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    const int n0 = wd::slot_rounds(args.num_tiles, 0), n1 = wd::slot_rounds(args.num_tiles, 1);
-    const uint32_t sbase = smem_u32(sm);
-    uint32_t ph[2] = {0, 0};
-    for (int r = 0; r < n0; ++r) {
-      const bool two = r < n1;
-      for (int t = 0; t < T; ++t) {
-        static_for<0, NL>([&](auto lc) {
-          constexpr int l = decltype(lc)::value;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (s == 1 && !two) continue;
-            mbar_wait(&bars[1 + s], ph[s]); ph[s] ^= 1;
-            tc::fence_after();
-            const uint32_t cb = tmem + s * C::SLOT_COLS;
-            if (tc::elect_one()) {
-              if constexpr (l == 0) wd::issue_kmajor<C::K0P, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::img0_off());
-              else if constexpr (l < NL - 1) wd::issue_kmajor<H, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgh_off(l));
-              else wd::issue_kmajor<H, C::NOP>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgo_off());
-              tc::commit(&bars[3 + s]);
-            }
-            __syncwarp();
-          }
-        });
-      }
-    }
-  } else {
+  {
     // ------------------------------------------------------------------ owners: thread = trajectory = TMEM lane
     const int slot = warp >> 2, m_ = tid & 127;
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -312,9 +293,26 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
     const uint32_t t_hi = cb + C::A_HI, t_lo = cb + C::A_LO, t_d = cb + C::DCOL;
     uint64_t* bar_ops = &bars[1 + slot];
     uint64_t* bar_done = &bars[3 + slot];
-    uint32_t ph_done = 0;
+    uint32_t ph_done = 0, ph_ops = 0;
     const float act_prm = p.policy.act_param;
-    auto arrive_ops = [&]() { tc::wait_st(); tc::fence_before(); mbar_arrive(bar_ops); };
+    const bool issuer = (warp & 3) == 0;
+    const uint32_t sbase = smem_u32(sm), cbs = tmem + slot * C::SLOT_COLS;
+    // operands of this thread are in tensor memory; the slot's first warp waits for all 128 rows and issues MMA batch `bi`
+    // (0: layer 0, 1 .. NL-2: hidden layer, NL-1: output layer)
+    auto arrive_ops = [&](int bi) {
+      tc::wait_st(); tc::fence_before(); mbar_arrive(bar_ops);
+      if (issuer) {
+        mbar_wait(bar_ops, ph_ops); ph_ops ^= 1;
+        tc::fence_after();
+        if (tc::elect_one()) {
+          if (bi == 0) wd::issue_kmajor<C::K0P, H>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::img0_off());
+          else if (bi < NL - 1) wd::issue_kmajor<H, H>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::imgh_off(1) + (bi - 1) * 2 * C::IMGH_BYTES);
+          else wd::issue_kmajor<H, C::NOP>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::imgo_off());
+          tc::commit(bar_done);
+        }
+        __syncwarp();
+      }
+    };
     for (int r = 0;; ++r) {
       const int tile = (r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot;
       if (tile >= args.num_tiles) break;
@@ -337,7 +335,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
         for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
         tc_policy_state<S, K0>(x, yv, in);
         { uint32_t hi0[C::K0P / 2]; wd::put_input<C>(t_hi, t_lo, in, hi0); (void)hi0; }
-        arrive_ops();
+        arrive_ops(0);
         if (t + 1 < T) tc_policy_input<S, K0>(p, args.exo, b, t + 1, x, in_pre);     // exogenous inputs one step ahead
         // hidden activations a_1 .. a_{NL-1}
 #pragma unroll 1
@@ -361,7 +359,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
             wd::tmem_st16u(t_hi + c0 / 2, hi);
             wd::tmem_st16u(t_lo + c0 / 2, lo);
           }
-          arrive_ops();
+          arrive_ops(l + 1);
         }
         // output layer
         mbar_wait(bar_done, ph_done); ph_done ^= 1;
@@ -391,33 +389,51 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
           for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1) + t + 1) * NX + i] = x[i];
         }
       }
-      if constexpr (S::NTERMS > 0) {
-        if (fused && valid) score_traj_s<S>(p, vtc, b, tsum);
-      }
-    }
-  }
-
-  if constexpr (S::NTERMS > 0) {
-    if (fused) {
-      __syncthreads();
-      static_for<0, S::NTERMS>([&](auto kc) {
-        constexpr int Kq = decltype(kc)::value;
-        double v = static_cast<double>(tsum[Kq]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) red[Kq * (C::THREADS / 32) + (tid >> 5)] = v;
-      });
-      __syncthreads();
-      if (tid < S::NTERMS) {
-        double v = 0.0;
-        for (int w = 0; w < C::THREADS / 32; ++w) v += red[tid * (C::THREADS / 32) + w];
-        args.term_partials[size_t(blockIdx.x) * NM_MAX_TERMS + tid] = v;
-      }
     }
   }
   tc::fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// PenaltyLoss scoring with the compiled term structure, thread per (trajectory, time element): streams the
+// trajectories once at HBM rate (block partial sums in double, same layout as nm_term_score_kernel's)
+template <class S>
+__global__ void __launch_bounds__(256) nm_wide_score_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args, int tmax) {
+  constexpr int NT = S::NTERMS > 0 ? S::NTERMS : 1;
+  __shared__ double red[NT][8];
+  const NmPlan& p = plan;
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
+  float ts[NT];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) ts[k] = 0.f;
+  const int64_t n = args.B * tmax;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / tmax;
+    const int te = int(idx - b * tmax);
+    static_for<0, S::NTERMS>([&](auto kc) {
+      constexpr int K = decltype(kc)::value;
+      const NmTerm& tm = p.terms[K];
+      if (te < tm.t_len) {
+        float s = 0.f;
+        for (int de = 0; de < tm.d_len; ++de) s += term_penalty_s<S, K>(term_value_s<S, K>(tm, vtc, b, te, de));
+        ts[K] += s;
+      }
+    });
+  }
+  static_for<0, S::NTERMS>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    double v = static_cast<double>(ts[K]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[K][threadIdx.x >> 5] = v;
+  });
+  __syncthreads();
+  if (threadIdx.x < S::NTERMS) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    args.term_partials[size_t(blockIdx.x) * NM_MAX_TERMS + threadIdx.x] = v;
+  }
 }
 
 // ================================================================================================ adjoint
@@ -427,8 +443,120 @@ struct WideBwdArgs {
   float* stash;                  // [grid * 2] slots of WideCfg::STASH_SLOT_BYTES
   float* lam_carry;              // [B][NX] co-state at the chunk boundary
   wd::ScaleState* scale;         // cotangent scale of this chunk (read), largest scaled cotangent seen (atomic max)
+  const float* G;                // loss-term gradients of this chunk [B][t_hi - t_lo + 1][NX + NU] (nm_wide_termgrad_kernel)
   int t_lo, t_hi;                // this launch sweeps steps t_hi-1 .. t_lo  (t_hi == nsteps: the first chunk of the pass)
 };
+
+// Loss-term gradients of one chunk, thread per (trajectory, time): G[b][tt][0:NX] = d loss / d x[b, t_lo + tt, :] for
+// tt <= t_hi - t_lo (the last row only matters when t_hi == nsteps), G[b][tt][NX:] = d loss / d u[b, t_lo + tt, :] for
+// tt < t_hi - t_lo.  Time-broadcast atoms (x[:, [-1], :] against a whole range) are left to the adjoint sweep, where all
+// lanes sit at the same time index (see term_grad_entry).  External gradients (Python-evaluated terms) are added here.
+template <class S>
+__global__ void __launch_bounds__(256) nm_wide_termgrad_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args,
+                                                               float* __restrict__ G, int t_lo, int t_hi) {
+  constexpr int NX = S::NX, NU = S::NU, RW = NX + NU;
+  __shared__ float coef[NM_MAX_TERMS];
+  __shared__ VarTable vt;
+  const NmPlan& p = plan;
+  const int T = p.nsteps;
+  if (threadIdx.x < NM_MAX_TERMS) coef[threadIdx.x] = threadIdx.x < p.n_terms ? term_coef(p, threadIdx.x, args.grad_scalars, args.b_total) : 0.f;
+  if (threadIdx.x == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = S::NY;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+  }
+  __syncthreads();
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  const int NT = t_hi - t_lo + 1;
+  const int64_t n = args.B * NT;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / NT;
+    const int tt = int(idx - b * NT), t = t_lo + tt;
+    float gx[NX], gu[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) gx[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) gu[j] = 0.f;
+    const bool want_x = t < t_hi || t_hi == T, want_u = t < t_hi;
+    if (fused) {
+      if constexpr (S::NTERMS > 0) {
+        if (want_x) term_grad_s<S, NM_VAR_X, NX, NX, 1>(p, vtc, coef, b, t, gx);
+        if (want_u) term_grad_s<S, NM_VAR_U, NU, NU, 1>(p, vtc, coef, b, t, gu);
+      }
+    } else {
+      if (want_x) term_grad_accum<NX, 1>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
+      if (want_u) term_grad_accum<NU, 1>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+    }
+    if (want_x && args.gx_ext != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) gx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
+    }
+    if (want_u && args.gu_ext != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
+    }
+    float* dst = G + idx * RW;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dst[i] = gx[i];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) dst[NX + j] = gu[j];
+  }
+}
+
+// Time-broadcast atoms (a single time entry compared against a whole range, e.g. x[:, [-1], :] > r - 0.01): the
+// gradient of the anchored entry is a sum over the range -- one warp per trajectory, range strided over the lanes, fixed
+// shuffle order (deterministic), added to the rows nm_wide_termgrad_kernel wrote.  `anchor` lists the anchored times.
+struct WideTbAnchors { int n; int var[8]; int t[8]; };
+template <class S>
+__global__ void __launch_bounds__(256) nm_wide_termgrad_tb_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args,
+                                                                  const __grid_constant__ WideTbAnchors anchors, float* __restrict__ G, int t_lo, int t_hi) {
+  constexpr int NX = S::NX, NU = S::NU, RW = NX + NU, MAXD = NX > NU ? NX : NU;
+  __shared__ float coef[NM_MAX_TERMS];
+  __shared__ VarTable vt;
+  const NmPlan& p = plan;
+  const int T = p.nsteps;
+  if (threadIdx.x < NM_MAX_TERMS) coef[threadIdx.x] = threadIdx.x < p.n_terms ? term_coef(p, threadIdx.x, args.grad_scalars, args.b_total) : 0.f;
+  if (threadIdx.x == 0) {
+    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
+    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
+    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = S::NY;
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, NT = t_hi - t_lo + 1;
+  const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
+  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  for (int64_t b = warp0; b < args.B; b += nwarps) {
+    for (int a = 0; a < anchors.n; ++a) {
+      const int var = anchors.var[a], t = anchors.t[a], dim = var == NM_VAR_X ? NX : NU;
+      float g[MAXD];
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) g[d] = 0.f;
+      if (fused) {
+        if constexpr (S::NTERMS > 0) {
+          if (var == NM_VAR_X) term_grad_s<S, NM_VAR_X, NX, MAXD, 2>(p, vtc, coef, b, t, g, lane, 32);
+          else term_grad_s<S, NM_VAR_U, NU, MAXD, 2>(p, vtc, coef, b, t, g, lane, 32);
+        }
+      } else term_grad_accum_tb_lanes<MAXD>(p, vt, coef, b, var, t, dim, lane, g);
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g[d] += __shfl_xor_sync(0xffffffffu, g[d], o);
+      }
+      if (lane == 0) {
+        float* dst = G + (b * NT + (t - t_lo)) * RW + (var == NM_VAR_X ? 0 : NX);
+        for (int d = 0; d < dim; ++d) dst[d] += g[d];
+      }
+    }
+  }
+}
 
 template <class S>
 __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ WideBwdArgs wargs) {
@@ -439,33 +567,12 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
   extern __shared__ __align__(1024) uint8_t sm[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);           // 0 weights, 1/2 operands ready (slot), 3/4 MMAs done (slot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* coef = reinterpret_cast<float*>(bars + 10);                        // [NM_MAX_TERMS]
-  float* dbred = coef + NM_MAX_TERMS;                                       // [8 warps][NOP] output-bias gradient partials
-  VarTable& vt = *reinterpret_cast<VarTable*>(dbred + 8 * C::NOP);
+  float* dbred = reinterpret_cast<float*>(bars + 10);                       // [8 warps][NOP] output-bias gradient partials
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
-  const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
   const int T = p.nsteps;
-  const bool fused = S::NTERMS > 0 && args.fused_terms;
-  const bool pre = !fused && args.G_x != nullptr;
-  const int g_row = (T + 1) * NX + T * (NU + S::NY);
-  int tb_mask = 0;
-  for (int k = 0; k < p.n_terms; ++k) {
-    const NmTerm& tm = p.terms[k];
-    const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
-    const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (live[i] && at[i]->var >= 0 && at[i]->var <= NM_VAR_Y && atom_is_tbcast(*at[i], tm)) tb_mask |= 1 << at[i]->var;
-  }
-  if (tid < NM_MAX_TERMS) coef[tid] = tid < p.n_terms ? term_coef(p, tid, args.grad_scalars, args.b_total) : 0.f;
+  constexpr int RW = NX + NU;
   if (tid == 0) {
-    vt.base[NM_VAR_X] = args.x_traj; vt.T[NM_VAR_X] = T + 1; vt.D[NM_VAR_X] = NX;
-    vt.base[NM_VAR_U] = args.u_traj; vt.T[NM_VAR_U] = T; vt.D[NM_VAR_U] = NU;
-    vt.base[NM_VAR_Y] = args.y_traj; vt.T[NM_VAR_Y] = T; vt.D[NM_VAR_Y] = S::NY;
-    for (int e = 0; e < NM_MAX_EXO; ++e) {
-      vt.base[NM_VAR_EXO0 + e] = args.exo[e]; vt.T[NM_VAR_EXO0 + e] = p.exo[e].steps; vt.D[NM_VAR_EXO0 + e] = p.exo[e].width;
-    }
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 128); mbar_init(&bars[2], 128);
     mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
@@ -484,38 +591,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
   const int t_lo = wargs.t_lo, t_hi = wargs.t_hi, CSn = t_hi - t_lo;
   const float gs = wargs.scale->gs, inv_gs = wargs.scale->inv_gs;
 
-  if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    const int n0 = wd::slot_rounds(args.num_tiles, 0), n1 = wd::slot_rounds(args.num_tiles, 1);
-    const uint32_t sbase = smem_u32(sm);
-    uint32_t ph[2] = {0, 0};
-    constexpr int NB = 2 * (NL - 1);                 // MMA batches per step: recompute L0..L(NL-2), data gradients L(NL-2)..L0
-    for (int r = 0; r < n0; ++r) {
-      const bool two = r < n1;
-      for (int t = t_hi - 1; t >= t_lo; --t) {
-        static_for<0, NB>([&](auto bc) {
-          constexpr int bi = decltype(bc)::value;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (s == 1 && !two) continue;
-            mbar_wait(&bars[1 + s], ph[s]); ph[s] ^= 1;
-            tc::fence_after();
-            const uint32_t cb = tmem + s * C::SLOT_COLS;
-            if (tc::elect_one()) {
-              if constexpr (bi == 0) wd::issue_kmajor<C::K0P, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::img0_off());
-              else if constexpr (bi < NL - 1) wd::issue_kmajor<H, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgh_off(bi));
-              else if constexpr (bi < NB - 1) {      // data gradient of hidden layer l = NL-2 .. 1:  dA_l = dZ_l W_l
-                constexpr int l = (NL - 2) - (bi - (NL - 1));
-                wd::issue_mnmajor<H, H, H>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::imgh_off(l));
-              } else wd::issue_mnmajor<H, C::K0P, C::GWP>(cb + C::DCOL, cb + C::A_HI, cb + C::A_LO, sbase + C::img0_off());
-              tc::commit(&bars[3 + s]);
-            }
-            __syncwarp();
-          }
-        });
-      }
-    }
-  } else {
+  {
     // ------------------------------------------------------------------ owners
     const int slot = warp >> 2, m_ = tid & 127;
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -523,20 +599,40 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
     const uint32_t t_hi_ = cb + C::A_HI, t_lo_ = cb + C::A_LO, t_d = cb + C::DCOL;
     uint64_t* bar_ops = &bars[1 + slot];
     uint64_t* bar_done = &bars[3 + slot];
-    uint32_t ph_done = 0;
+    uint32_t ph_done = 0, ph_ops = 0;
     const float act_prm = p.policy.act_param;
-    auto arrive_ops = [&]() { tc::wait_st(); tc::fence_before(); mbar_arrive(bar_ops); };
+    const bool issuer = (warp & 3) == 0;
+    const uint32_t sbase = smem_u32(sm), cbs = tmem + slot * C::SLOT_COLS;
+    // operands of this thread are in tensor memory; the slot's first warp waits for all 128 rows and issues MMA batch `bi`:
+    //   0: recompute layer 0    1 .. NL-2: recompute hidden layer bi    NL-1 .. 2NL-4: data gradient of hidden layer
+    //   l = 2NL-3-bi (dA_l = dZ_l W_l, the forward image read MN-major)    2NL-3: data gradient of layer 0 (state columns)
+    auto arrive_ops = [&](int bi) {
+      tc::wait_st(); tc::fence_before(); mbar_arrive(bar_ops);
+      if (issuer) {
+        mbar_wait(bar_ops, ph_ops); ph_ops ^= 1;
+        tc::fence_after();
+        if (tc::elect_one()) {
+          if (bi == 0) wd::issue_kmajor<C::K0P, H>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::img0_off());
+          else if (bi < NL - 1) wd::issue_kmajor<H, H>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::imgh_off(1) + (bi - 1) * 2 * C::IMGH_BYTES);
+          else if (bi < 2 * NL - 3) wd::issue_mnmajor<H, H, H>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::imgh_off(1) + (2 * NL - 3 - bi - 1) * 2 * C::IMGH_BYTES);
+          else wd::issue_mnmajor<H, C::K0P, C::GWP>(cbs + C::DCOL, cbs + C::A_HI, cbs + C::A_LO, sbase + C::img0_off());
+          tc::commit(bar_done);
+        }
+        __syncwarp();
+      }
+    };
     float4* stash = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(wargs.stash) + size_t(blockIdx.x * 2 + slot) * C::STASH_SLOT_BYTES) + m_;
     const float* __restrict__ Wout = reinterpret_cast<const float*>(sm + C::wout_off());
     float dbo[NOUT];                                  // output-bias gradient (scaled), summed over this thread's trajectory-steps
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) dbo[j] = 0.f;
     float dzmax = 0.f;
+    const uint64_t pol_stage = wd::l2_policy_evict_first(), pol_stash = wd::l2_policy_evict_last();
     // staging store of 32 consecutive features (16 packed words) of operand tile `toff`
     auto stage32 = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[16]) {
       uint8_t* q = item + toff + (c0 / 8) * C::GRP + m_ * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3], pol_stage);
     };
 
     for (int r = 0;; ++r) {
@@ -545,26 +641,19 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
       const int64_t b_raw = int64_t(tile) * TILE + m_;
       const bool valid = b_raw < args.B;
       const int64_t b = valid ? b_raw : args.B - 1;
-      float lam[NX], x_pre[NX], o_pre[NU], in_pre[K0];
+      float lam[NX], x_pre[NX], o_pre[NU], in_pre[K0], g_pre[RW];
+      const float* __restrict__ Gb = wargs.G + b * int64_t(CSn + 1) * RW;
 #pragma unroll
       for (int i = 0; i < NX; ++i) { lam[i] = 0.f; x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + (t_hi - 1)) * NX + i); }
 #pragma unroll
       for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + (t_hi - 1)) * NU + j);
+#pragma unroll
+      for (int q = 0; q < RW; ++q) g_pre[q] = __ldg(Gb + (CSn - 1) * RW + q);
       tc_policy_input<S, K0>(p, args.exo, b, t_hi - 1, x_pre, in_pre);
       if (t_hi == T) {
         if (valid) {
-          if (pre) {
 #pragma unroll
-            for (int i = 0; i < NX; ++i) lam[i] = __ldg(args.G_x + b * g_row + T * NX + i);
-            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
-          } else {
-            if (fused) { if constexpr (S::NTERMS > 0) term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, T, lam); }
-            else term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, T, NX, lam);
-            if (args.gx_ext != nullptr) {
-#pragma unroll
-              for (int i = 0; i < NX; ++i) lam[i] += __ldg(args.gx_ext + (b * (T + 1) + T) * NX + i);
-            }
-          }
+          for (int i = 0; i < NX; ++i) lam[i] = __ldg(Gb + CSn * RW + i);
         }
       } else {
 #pragma unroll
@@ -573,64 +662,44 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll 1
       for (int t = t_hi - 1; t >= t_lo; --t) {
         uint8_t* item = wargs.staging + (size_t(tile) * CSn + size_t(t - t_lo)) * C::ITEM_BYTES;
-        float x[NX], o_cur[NU], in[K0], yv[1] = {0.f};
+        float x[NX], o_cur[NU], in[K0], g_cur[RW], yv[1] = {0.f};
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = x_pre[i];
 #pragma unroll
         for (int j = 0; j < NU; ++j) o_cur[j] = o_pre[j];
 #pragma unroll
         for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
+#pragma unroll
+        for (int q = 0; q < RW; ++q) g_cur[q] = g_pre[q];
         tc_policy_state<S, K0>(x, yv, in);
         {
           uint32_t hi0[C::K0P / 2];
           wd::put_input<C>(t_hi_, t_lo_, in, hi0);
           uint8_t* q = item + C::a_off(0) + m_ * 16;
 #pragma unroll
-          for (int g = 0; g < C::K0P / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi0[4 * g], hi0[4 * g + 1], hi0[4 * g + 2], hi0[4 * g + 3]);
+          for (int g = 0; g < C::K0P / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi0[4 * g], hi0[4 * g + 1], hi0[4 * g + 2], hi0[4 * g + 3], pol_stage);
         }
-        arrive_ops();                                 // -> recompute of layer 0
+        arrive_ops(0);                                // -> recompute of layer 0
         if (t > 0) {                                  // next step's inputs (also across the chunk boundary: harmless)
 #pragma unroll
           for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
 #pragma unroll
           for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + t - 1) * NU + j);
           tc_policy_input<S, K0>(p, args.exo, b, t - 1, x, in_pre);
+          if (t > t_lo) {
+#pragma unroll
+            for (int q = 0; q < RW; ++q) g_pre[q] = __ldg(Gb + (t - 1 - t_lo) * RW + q);
+          }
         }
         // ---- dynamics adjoint, loss-term gradients, cotangent of the raw policy output (all while the MMAs run)
         float u[NU], gx[NX], gu[NU], gtx[NX], cot[NOUT];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) gtx[i] = 0.f;
-#pragma unroll
         for (int j = 0; j < NU; ++j) u[j] = bounds_fwd<M::BOUNDS>(o_cur[j], p.policy.bmin[j], p.policy.bmax[j]);
         Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
-        if (valid) {
-          if (pre) {
 #pragma unroll
-            for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.G_x + b * g_row + (T + 1) * NX + t * NU + j);
-            if (tb_mask & 2) term_grad_accum_ool<NU, 2>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
+        for (int i = 0; i < NX; ++i) gtx[i] = g_cur[i];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) gtx[i] += __ldg(args.G_x + b * g_row + t * NX + i);
-            if (tb_mask & 1) term_grad_accum_ool<NX, 2>(p, vt, coef, b, NM_VAR_X, t, NX, gtx);
-          } else {
-            if (fused) {
-              if constexpr (S::NTERMS > 0) {
-                term_grad_s<S, NM_VAR_U, NU, NU>(p, vtc, coef, b, t, gu);
-                term_grad_s<S, NM_VAR_X, NX, NX>(p, vtc, coef, b, t, gtx);
-              }
-            } else {
-              term_grad_accum_ool<NU, 0>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
-              term_grad_accum_ool<NX, 0>(p, vt, coef, b, NM_VAR_X, t, NX, gtx);
-            }
-            if (args.gu_ext != nullptr) {
-#pragma unroll
-              for (int j = 0; j < NU; ++j) gu[j] += __ldg(args.gu_ext + (b * T + t) * NU + j);
-            }
-            if (args.gx_ext != nullptr) {
-#pragma unroll
-              for (int i = 0; i < NX; ++i) gtx[i] += __ldg(args.gx_ext + (b * (T + 1) + t) * NX + i);
-            }
-          }
-        }
+        for (int j = 0; j < NU; ++j) gu[j] += g_cur[NX + j];
 #pragma unroll
         for (int j = 0; j < NOUT; ++j) {
           cot[j] = valid ? gu[j] * bounds_deriv<M::BOUNDS>(o_cur[j], p.policy.bmin[j], p.policy.bmax[j]) * gs : 0.f;
@@ -647,7 +716,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
           }
           uint8_t* q = item + C::c_off() + m_ * 16;
 #pragma unroll
-          for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3]);
+          for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3], pol_stage);
         }
         // ---- recompute: a_{l+1} = act(z_l), derivative stash; the last one goes straight into the backward pass
 #pragma unroll 1
@@ -674,7 +743,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
               wd::tmem_st16u(t_hi_ + c0 / 2, hi);
               wd::tmem_st16u(t_lo_ + c0 / 2, lo);
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) stash[(l * (H / 4) + (c0 + i) / 4) * 128] = make_float4(d[i], d[i + 1], d[i + 2], d[i + 3]);
+              for (int i = 0; i < 32; i += 4) wd::st_global_f4(stash + (l * (H / 4) + (c0 + i) / 4) * 128, make_float4(d[i], d[i + 1], d[i + 2], d[i + 3]), pol_stash);
             } else {
               // output layer backward on the CUDA cores: dA[k] = sum_j cot[j] W_out[j][k];  dZ_{NL-2} = dA * act'
 #pragma unroll
@@ -698,20 +767,26 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
               wd::tmem_st16u(t_lo_ + c0 / 2, lo);
             }
           }
-          arrive_ops();                               // -> recompute of layer l+1, or (last) data gradient of layer NL-2
+          arrive_ops(l + 1);                          // -> recompute of layer l+1, or (last: bi = NL-1) data gradient of layer NL-2
         }
         // ---- data gradients: D = dA_l (cotangent of a_l), l = NL-2 .. 1;  dZ_{l-1} = dA_l * act'(z_{l-1})
 #pragma unroll 1
         for (int l = NL - 2; l >= 1; --l) {
+          // the stashed derivatives come from L2: the first chunk is requested before the wait, chunk c+1 while chunk c is processed
+          float4 dq[8], dn[8];
+          const float4* __restrict__ sl = stash + (l - 1) * (H / 4) * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dq[i] = wd::ld_global_f4(sl + i * 128, pol_stash);
           mbar_wait(bar_done, ph_done); ph_done ^= 1;
           tc::fence_after();
 #pragma unroll 1
           for (int c0 = 0; c0 < H; c0 += 32) {
             float v[32];
             uint32_t hi[16], lo[16];
-            float4 dq[8];
+            if (c0 + 32 < H) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dq[i] = stash[((l - 1) * (H / 4) + c0 / 4 + i) * 128];
+              for (int i = 0; i < 8; ++i) dn[i] = wd::ld_global_f4(sl + ((c0 + 32) / 4 + i) * 128, pol_stash);
+            }
             tc::tmem_ld<32>(t_d + c0, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[4 * i] *= dq[i].x; v[4 * i + 1] *= dq[i].y; v[4 * i + 2] *= dq[i].z; v[4 * i + 3] *= dq[i].w; }
@@ -724,8 +799,10 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
             stage32(item, C::z_off(l - 1), c0, hi);                                       // dZ_{l-1}
             wd::tmem_st16u(t_hi_ + c0 / 2, hi);
             wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dq[i] = dn[i];
           }
-          arrive_ops();                               // -> data gradient of layer l-1
+          arrive_ops(2 * NL - 2 - l);                 // -> data gradient of layer l-1
         }
         // ---- gradient of the policy input (state segment) closes the loop
         mbar_wait(bar_done, ph_done); ph_done ^= 1;
