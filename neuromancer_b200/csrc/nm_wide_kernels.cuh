@@ -31,6 +31,15 @@
 #ifndef NM_HOST_EMU
 #include <cuda_fp16.h>
 
+#ifdef NM_TUNE_WPROF
+#define WP_DECL(n) long long n = 0
+#define WP_T0() const long long wp_t0 = clock64()
+#define WP_ADD(n) n += clock64() - wp_t0
+#else
+#define WP_DECL(n)
+#define WP_T0()
+#define WP_ADD(n)
+#endif
 namespace nm {
 namespace wd {
 
@@ -86,6 +95,48 @@ __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_
   const __half2 l = __floats2half2_rn((a0 - hf.x) * 2048.f, (a1 - hf.y) * 2048.f);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Activation epilogue on an accumulator entry `acc` (= z - bias).  GELU (exact erf form, nn.GELU()) works on
+// x = z / sqrt(2) = fma(acc, 1/sqrt2, bias/sqrt2) -- the bias comes pre-scaled, its add is free -- with the erfc fit of
+// nm_device.cuh (erfc(t) = 2^(-t Q(t)), |t| <= 4.2):   e = erfc(|x|) / sqrt2 = 2^(-t Q - 1/2),
+//   gelu(z)  = z Phi(z)         = x / sqrt2 + |x| (1/sqrt2 - e)
+//   gelu'(z) = Phi(z) + z phi(z) = 1/2 + sign(x) (1/sqrt2 - e) / sqrt2 + x exp(-x^2) / sqrt(pi)
+template <int ACT> constexpr float bias_scale() { return ACT == NM_ACT_GELU ? 0.70710678118654752440f : 1.f; }
+__device__ __forceinline__ float gelu_core(float x, float& ax) {          // returns s = 1/sqrt2 - e
+  ax = fabsf(x);
+  const float t = fminf(ax, 4.2f);
+  float q = -1.476634237e-05f;
+  q = fmaf(q, t, 1.797868946e-04f);
+  q = fmaf(q, t, -9.401043775e-04f);
+  q = fmaf(q, t, 2.438597105e-03f);
+  q = fmaf(q, t, -2.483013238e-04f);
+  q = fmaf(q, t, -2.763307886e-02f);
+  q = fmaf(q, t, 1.482808647e-01f);
+  q = fmaf(q, t, 9.184465932e-01f);
+  q = fmaf(q, t, 1.627907100e+00f);
+  return 0.70710678118654752440f - ex2_approx(fmaf(-q, t, -0.5f));
+}
+template <int ACT>
+__device__ __forceinline__ float act_acc(float acc, float bs, float prm) {
+  if constexpr (ACT == NM_ACT_GELU) {
+    const float x = fmaf(acc, 0.70710678118654752440f, bs);
+    float ax;
+    const float s = gelu_core(x, ax);
+    return fmaf(ax, s, x * 0.70710678118654752440f);
+  } else return act_fwd<ACT>(acc + bs, prm);
+}
+template <int ACT>
+__device__ __forceinline__ void act_acc_pair(float acc, float bs, float prm, float& a, float& d) {
+  if constexpr (ACT == NM_ACT_GELU) {
+    const float x = fmaf(acc, 0.70710678118654752440f, bs);
+    float ax;
+    const float s = gelu_core(x, ax);
+    a = fmaf(ax, s, x * 0.70710678118654752440f);
+    const float g = ex2_approx(x * (x * -1.44269504088896340736f));        // exp(-x^2)
+    const float cdf = fmaf(copysignf(0.70710678118654752440f, x), s, 0.5f);
+    d = fmaf(x * 0.56418958354775628695f, g, cdf);
+  } else tc::act_ad<ACT>(acc + bs, prm, a, d);
 }
 
 // ------------------------------------------------------------------------------------------------ static layout
@@ -177,7 +228,7 @@ __global__ void nm_wide_prep_kernel(const __grid_constant__ NmPlan plan, const f
   for (int l = 0; l <= C::NL - 2; ++l) {
     float* b = reinterpret_cast<float*>(wprep + C::bias_off(l));
     const float* src = P + C::p_off(l) + C::nout(l) * C::kin(l);
-    for (int i = gtid; i < C::H; i += gthreads) b[i] = C::BIAS ? src[i] : 0.f;
+    for (int i = gtid; i < C::H; i += gthreads) b[i] = C::BIAS ? src[i] * bias_scale<C::M::ACT>() : 0.f;
   }
   {
     float* b = reinterpret_cast<float*>(wprep + C::biaso_off());
@@ -222,6 +273,38 @@ __device__ __forceinline__ void issue_mnmajor(uint32_t d, uint32_t a_hi, uint32_
   static_for<0, ROWS / 16>([&](auto kc) {
     constexpr int ks = decltype(kc)::value;
     mma_ts<(ks > 0 ? 1 : 2)>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+  });
+}
+
+// N contiguous floats of a row whose start is aligned like its length (N % 4 == 0: 16 B, N % 2 == 0: 8 B)
+template <int N>
+__device__ __forceinline__ void ld_row(float (&dst)[N], const float* __restrict__ src) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) { const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i); dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) { const float2 v = __ldg(reinterpret_cast<const float2*>(src) + i); dst[2 * i] = v.x; dst[2 * i + 1] = v.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = __ldg(src + i);
+  }
+}
+// exogenous segments of the policy input of trajectory b at step t (state entries of `in` are left untouched)
+template <class S, int K0>
+__device__ __forceinline__ void policy_exo(const NmPlan& p, const float* const* exo, int64_t b, int t, float (&in)[K0]) {
+  int off = 0;
+  static_for<0, S::NSEG>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    constexpr int W = S::seg_width(s);
+    if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+      constexpr int e = S::seg_index(s);
+      float row[W];
+      ld_row<W>(row, exo[e] + (b * p.exo[e].steps + t) * W);
+#pragma unroll
+      for (int i = 0; i < W; ++i) in[off + i] = row[i];
+    }
+    off += W;
   });
 }
 
@@ -327,7 +410,9 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
         for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1)) * NX + i] = x[i];
       }
       float in_pre[K0];
-      tc_policy_input<S, K0>(p, args.exo, b, 0, x, in_pre);
+#pragma unroll
+      for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
+      wd::policy_exo<S, K0>(p, args.exo, b, 0, in_pre);
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
         float in[K0], yv[1] = {0.f};
@@ -336,7 +421,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
         tc_policy_state<S, K0>(x, yv, in);
         { uint32_t hi0[C::K0P / 2]; wd::put_input<C>(t_hi, t_lo, in, hi0); (void)hi0; }
         arrive_ops(0);
-        if (t + 1 < T) tc_policy_input<S, K0>(p, args.exo, b, t + 1, x, in_pre);     // exogenous inputs one step ahead
+        if (t + 1 < T) wd::policy_exo<S, K0>(p, args.exo, b, t + 1, in_pre);     // exogenous inputs one step ahead
         // hidden activations a_1 .. a_{NL-1}
 #pragma unroll 1
         for (int l = 0; l < NL - 1; ++l) {
@@ -351,8 +436,8 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
-              v[i] = act_fwd<M::ACT>(v[i] + bv.x, act_prm); v[i + 1] = act_fwd<M::ACT>(v[i + 1] + bv.y, act_prm);
-              v[i + 2] = act_fwd<M::ACT>(v[i + 2] + bv.z, act_prm); v[i + 3] = act_fwd<M::ACT>(v[i + 3] + bv.w, act_prm);
+              v[i] = wd::act_acc<M::ACT>(v[i], bv.x, act_prm); v[i + 1] = wd::act_acc<M::ACT>(v[i + 1], bv.y, act_prm);
+              v[i + 2] = wd::act_acc<M::ACT>(v[i + 2], bv.z, act_prm); v[i + 3] = wd::act_acc<M::ACT>(v[i + 3], bv.w, act_prm);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -627,6 +712,10 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) dbo[j] = 0.f;
     float dzmax = 0.f;
+    WP_DECL(w_in); WP_DECL(w_dyn); WP_DECL(w_wait_rc); WP_DECL(w_epi_rc); WP_DECL(w_wait_dg); WP_DECL(w_epi_dg); WP_DECL(w_wait_in); WP_DECL(w_arr); WP_DECL(w_tile);
+#ifdef NM_TUNE_WPROF
+    const long long w_begin = clock64();
+#endif
     const uint64_t pol_stage = wd::l2_policy_evict_first(), pol_stash = wd::l2_policy_evict_last();
     // staging store of 32 consecutive features (16 packed words) of operand tile `toff`
     auto stage32 = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[16]) {
@@ -644,16 +733,18 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
       float lam[NX], x_pre[NX], o_pre[NU], in_pre[K0], g_pre[RW];
       const float* __restrict__ Gb = wargs.G + b * int64_t(CSn + 1) * RW;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { lam[i] = 0.f; x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + (t_hi - 1)) * NX + i); }
+      for (int i = 0; i < NX; ++i) lam[i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + (t_hi - 1)) * NU + j);
-#pragma unroll
-      for (int q = 0; q < RW; ++q) g_pre[q] = __ldg(Gb + (CSn - 1) * RW + q);
-      tc_policy_input<S, K0>(p, args.exo, b, t_hi - 1, x_pre, in_pre);
+      for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
+      wd::ld_row<NX>(x_pre, args.x_traj + (b * (T + 1) + (t_hi - 1)) * NX);
+      wd::ld_row<NU>(o_pre, args.chk + (b * T + (t_hi - 1)) * NU);
+      wd::ld_row<RW>(g_pre, Gb + (CSn - 1) * RW);
+      wd::policy_exo<S, K0>(p, args.exo, b, t_hi - 1, in_pre);
       if (t_hi == T) {
         if (valid) {
+          { float gT[RW]; wd::ld_row<RW>(gT, Gb + CSn * RW);
 #pragma unroll
-          for (int i = 0; i < NX; ++i) lam[i] = __ldg(Gb + CSn * RW + i);
+            for (int i = 0; i < NX; ++i) lam[i] = gT[i]; }
         }
       } else {
 #pragma unroll
@@ -679,17 +770,13 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
           for (int g = 0; g < C::K0P / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi0[4 * g], hi0[4 * g + 1], hi0[4 * g + 2], hi0[4 * g + 3], pol_stage);
         }
-        arrive_ops(0);                                // -> recompute of layer 0
+        { WP_T0(); arrive_ops(0); WP_ADD(w_arr); }   // -> recompute of layer 0
+        WP_T0();
         if (t > 0) {                                  // next step's inputs (also across the chunk boundary: harmless)
-#pragma unroll
-          for (int i = 0; i < NX; ++i) x_pre[i] = __ldg(args.x_traj + (b * (T + 1) + t - 1) * NX + i);
-#pragma unroll
-          for (int j = 0; j < NU; ++j) o_pre[j] = __ldg(args.chk + (b * T + t - 1) * NU + j);
-          tc_policy_input<S, K0>(p, args.exo, b, t - 1, x, in_pre);
-          if (t > t_lo) {
-#pragma unroll
-            for (int q = 0; q < RW; ++q) g_pre[q] = __ldg(Gb + (t - 1 - t_lo) * RW + q);
-          }
+          wd::ld_row<NX>(x_pre, args.x_traj + (b * (T + 1) + t - 1) * NX);
+          wd::ld_row<NU>(o_pre, args.chk + (b * T + t - 1) * NU);
+          wd::policy_exo<S, K0>(p, args.exo, b, t - 1, in_pre);
+          if (t > t_lo) wd::ld_row<RW>(g_pre, Gb + (t - 1 - t_lo) * RW);
         }
         // ---- dynamics adjoint, loss-term gradients, cotangent of the raw policy output (all while the MMAs run)
         float u[NU], gx[NX], gu[NU], gtx[NX], cot[NOUT];
@@ -718,13 +805,15 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
           for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3], pol_stage);
         }
+        WP_ADD(w_dyn);
         // ---- recompute: a_{l+1} = act(z_l), derivative stash; the last one goes straight into the backward pass
 #pragma unroll 1
         for (int l = 0; l < NL - 1; ++l) {
           const float* __restrict__ bias = reinterpret_cast<const float*>(sm + C::bias_off(0)) + l * H;
           const bool last = l == NL - 2;
-          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait_rc); }
           tc::fence_after();
+          WP_T0();
 #pragma unroll 1
           for (int c0 = 0; c0 < H; c0 += 32) {
             float v[32], d[32];
@@ -733,8 +822,8 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
-              tc::act_ad<M::ACT>(v[i] + bv.x, act_prm, v[i], d[i]); tc::act_ad<M::ACT>(v[i + 1] + bv.y, act_prm, v[i + 1], d[i + 1]);
-              tc::act_ad<M::ACT>(v[i + 2] + bv.z, act_prm, v[i + 2], d[i + 2]); tc::act_ad<M::ACT>(v[i + 3] + bv.w, act_prm, v[i + 3], d[i + 3]);
+              wd::act_acc_pair<M::ACT>(v[i], bv.x, act_prm, v[i], d[i]); wd::act_acc_pair<M::ACT>(v[i + 1], bv.y, act_prm, v[i + 1], d[i + 1]);
+              wd::act_acc_pair<M::ACT>(v[i + 2], bv.z, act_prm, v[i + 2], d[i + 2]); wd::act_acc_pair<M::ACT>(v[i + 3], bv.w, act_prm, v[i + 3], d[i + 3]);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -767,45 +856,53 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
               wd::tmem_st16u(t_lo_ + c0 / 2, lo);
             }
           }
-          arrive_ops(l + 1);                          // -> recompute of layer l+1, or (last: bi = NL-1) data gradient of layer NL-2
+          WP_ADD(w_epi_rc);
+          { WP_T0(); arrive_ops(l + 1); WP_ADD(w_arr); }   // -> recompute of layer l+1, or (last: bi = NL-1) data gradient of layer NL-2
         }
         // ---- data gradients: D = dA_l (cotangent of a_l), l = NL-2 .. 1;  dZ_{l-1} = dA_l * act'(z_{l-1})
 #pragma unroll 1
         for (int l = NL - 2; l >= 1; --l) {
-          // the stashed derivatives come from L2: the first chunk is requested before the wait, chunk c+1 while chunk c is processed
-          float4 dq[8], dn[8];
+          // the stashed derivatives come from L2: two 32-column chunks are always in flight -- chunks 0 and 1 are
+          // requested before the wait for the MMAs, chunk c+2 when chunk c has been consumed
+          float4 dq[2][8];
           const float4* __restrict__ sl = stash + (l - 1) * (H / 4) * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dq[i] = wd::ld_global_f4(sl + i * 128, pol_stash);
-          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          for (int i = 0; i < 8; ++i) dq[0][i] = wd::ld_global_f4(sl + i * 128, pol_stash);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dq[1][i] = wd::ld_global_f4(sl + (8 + i) * 128, pol_stash);
+          { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait_dg); }
           tc::fence_after();
+          WP_T0();
 #pragma unroll 1
-          for (int c0 = 0; c0 < H; c0 += 32) {
-            float v[32];
-            uint32_t hi[16], lo[16];
-            if (c0 + 32 < H) {
+          for (int c2 = 0; c2 < H; c2 += 64) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dn[i] = wd::ld_global_f4(sl + ((c0 + 32) / 4 + i) * 128, pol_stash);
+            for (int hb = 0; hb < 2; ++hb) {
+              const int c0 = c2 + hb * 32;
+              float v[32];
+              uint32_t hi[16], lo[16];
+              tc::tmem_ld<32>(t_d + c0, v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[4 * i] *= dq[hb][i].x; v[4 * i + 1] *= dq[hb][i].y; v[4 * i + 2] *= dq[hb][i].z; v[4 * i + 3] *= dq[hb][i].w; }
+              if (c0 + 64 < H) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dq[hb][i] = wd::ld_global_f4(sl + ((c0 + 64) / 4 + i) * 128, pol_stash);
+              }
+              if (c0 == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+              stage32(item, C::z_off(l - 1), c0, hi);                                     // dZ_{l-1}
+              wd::tmem_st16u(t_hi_ + c0 / 2, hi);
+              wd::tmem_st16u(t_lo_ + c0 / 2, lo);
             }
-            tc::tmem_ld<32>(t_d + c0, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { v[4 * i] *= dq[i].x; v[4 * i + 1] *= dq[i].y; v[4 * i + 2] *= dq[i].z; v[4 * i + 3] *= dq[i].w; }
-            if (c0 == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-            stage32(item, C::z_off(l - 1), c0, hi);                                       // dZ_{l-1}
-            wd::tmem_st16u(t_hi_ + c0 / 2, hi);
-            wd::tmem_st16u(t_lo_ + c0 / 2, lo);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dq[i] = dn[i];
           }
-          arrive_ops(2 * NL - 2 - l);                 // -> data gradient of layer l-1
+          WP_ADD(w_epi_dg);
+          { WP_T0(); arrive_ops(2 * NL - 2 - l); WP_ADD(w_arr); }   // -> data gradient of layer l-1
         }
         // ---- gradient of the policy input (state segment) closes the loop
-        mbar_wait(bar_done, ph_done); ph_done ^= 1;
+        { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait_in); }
         tc::fence_after();
         {
           float gin[C::GWP];
@@ -841,6 +938,11 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
         }
       }
     }
+#ifdef NM_TUNE_WPROF
+    if (blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 32))
+      printf("[wprof bwd tid %d] total %lld | arrive+issue %lld  dyn/terms %lld  wait_rc %lld  epi_rc %lld  wait_dg %lld  epi_dg %lld  wait_in %lld (steps %d)\n", tid,
+             clock64() - w_begin, w_arr, w_dyn, w_wait_rc, w_epi_rc, w_wait_dg, w_epi_dg, w_wait_in, CSn);
+#endif
     // ---- output-bias gradient and the scale statistics of this launch (fixed order: deterministic)
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) {
