@@ -2,15 +2,17 @@
 """
 bench.py -- DPC train-step throughput of the fused rollout (forward + adjoint [+ gradient all-reduce]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--batch B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--batch B] [--impl reference]
 
-Contract (see the task statement): rank 0 prints ONE JSON line.  A "step" is one pass of the hot path
-over one batch of synthetic input: nm_rollout_forward + nm_rollout_backward on device-resident
-buffers (`value`), timed with CUDA events, L2 flushed between timed steps, max over ranks.  `e2e` is the
-same metric through the public API (`Problem.forward` + `.backward()`) with the batch coming from pinned
-HOST memory and the loss read back every step.  `--impl reference` times the reference's CPU
-implementation of the path (the oracle port: the same torch ops the reference executes, pinned
-bit-exactly to it) on the host cores.
+Contract (see the task statement): rank 0 prints ONE JSON line.  A "step" is one pass of the hot path over one batch of
+synthetic input: nm_rollout_forward + nm_rollout_backward on device-resident buffers (`value`), timed with CUDA events,
+L2 flushed between timed steps, max over ranks.  The default workload is the headline configuration of BASELINE.json:
+**C5** (24-128x4-6 GELU policy, 12-state coupled Van der Pol + RK4, nsteps 200) at a GLOBAL batch of 4,194,304
+trajectories -- strong scaling over 1/2/4/8 GPUs.  `e2e` is the same metric through the public API
+(`Problem.forward` + `.backward()`) with every batch copied from pinned HOST memory inside the timed region and the
+loss read back every step.  `--impl reference` times the reference's own CPU implementation of the path on the host
+cores: the UNMODIFIED reference modules (oracle/_ref, see oracle/make_ref.py) when they are present, else the oracle
+port (pinned bit-exactly to the reference).
 """
 from __future__ import annotations
 
@@ -23,13 +25,21 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p_ in (ROOT, os.path.join(ROOT, "tests")):
-    if p_ not in sys.path:
-        sys.path.insert(0, p_)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 METRIC = "DPC train-step trajectory-steps/sec (fwd+bwd)"
 UNIT = "trajectory-steps/s"
-CPU_SAMPLE_BATCH = {"c1": 3333, "c2": 8192, "c3": 2048, "c4": 2048, "c4p": 2048, "c5": 256}
+# CPU arm: batch per workload (the largest the eager reference holds an autograd tape for)
+CPU_REF_BATCH = {"c1": 3333, "c2": 65536, "c3": 8192, "c4": 16384, "c4p": 16384, "c5": 4096}
+CPU_PORT_BATCH = {"c1": 3333, "c2": 8192, "c3": 2048, "c4": 2048, "c4p": 2048, "c5": 256}
+E2E_MAX_BATCH = 1048576          # per GPU: the public-API leg double-buffers its host batches (c5: 10 GB of `r` each)
+DESCRIPTION = {"c1": "DPC double integrator, MLP 2-20-20-20-20-1 ReLU, linear SSM",
+               "c2": "DPC reference tracking, TwoTank ODE + RK4, MLP_bounds 4-32-32-2 GELU",
+               "c3": "neural-ODE system ID, RK4 over MLP RHS 2-60-60-60-2 ReLU",
+               "c4": "building thermal DPC, linear SSM nx=4, 48-step preview, MLP_bounds 193-32-32-1",
+               "c4p": "c4 with SystemPreview windows over the raw signals (in-kernel gather)",
+               "c5": "parametric nonlinear DPC, 12-state coupled VdP + RK4, MLP_bounds 24-128x4-6 GELU, box + terminal constraints"}
 
 
 def read_peaks():
@@ -53,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", os.environ.get("NM_CLOCK_MS", "20"), "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", os.environ.get("NM_CLOCK_MS", "50"), "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -87,48 +97,117 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_cpu_step(name, batch_cpu, params_cpu):
-    """One fwd+bwd of the reference's CPU path (oracle port) -- the thing `--impl reference` times."""
-    import helpers as H
-    res = H.oracle_run(name, params_cpu, batch_cpu)
-    return float(res["loss"])
+# ------------------------------------------------------------------------------------------- CPU arm
+def _reference_src():
+    """Unmodified reference modules: the build container's /root/reference, else the copy oracle/make_ref.py leaves
+    under oracle/_ref (git-ignored, travels to the GPU box with the snapshot)."""
+    for cand in (os.environ.get("NM_REFERENCE_SRC"), os.path.join(ROOT, "oracle", "_ref", "src"), "/root/reference/src"):
+        if cand and os.path.isdir(os.path.join(cand, "neuromancer")):
+            return cand
+    return None
 
 
-def time_cpu_reference(name, steps, warmup, nsteps, budget_s=25.0):
+def time_cpu_reference(name, steps, warmup, nsteps, budget_s=45.0):
+    """fwd+bwd of the reference's CPU path on all host cores, on a bounded sample of the workload."""
     import torch
-    import helpers as H
     torch.set_num_threads(os.cpu_count() or 1)
-    case = H.make_case(name, "cpu")
-    B = CPU_SAMPLE_BATCH.get(name, 1024)
-    batch = case.make_batch(B, "cpu", 0)
-    params = [p.detach().clone() for p in case.plan_params]
-    for _ in range(max(warmup, 1)):
-        oracle_cpu_step(name, batch, params)
-    times = []
+    src = _reference_src()
+    kind = "reference" if src is not None else "port"
+    if kind == "reference":
+        os.environ["NM_REFERENCE_SRC"] = src
+        from oracle import pin_oracle, ref_shim
+        ref_shim.REFERENCE_SRC = src
+        ns = ref_shim.load()
+        torch.manual_seed(0)
+        builder = pin_oracle.REF_BUILDERS[name][0]
+        problem, params, data_fn, _, _ = builder(ns)
+        B = CPU_REF_BATCH.get(name, 1024)
+        g = torch.Generator(device="cpu"); g.manual_seed(4321)
+        batch = {**data_fn(B, g), "name": "train"}
+
+        def one():
+            for q in params:
+                q.grad = None
+            out = problem(batch)
+            out["train_loss"].backward()
+            return float(out["train_loss"])
+        what = (f"UNMODIFIED reference modules (pnnl/neuromancer System/Node/MLP_bounds/RK4/PenaltyLoss/Problem from {os.path.relpath(src, ROOT) if src.startswith(ROOT) else src}, "
+                f"loaded through oracle/ref_shim.py), Problem.forward + loss.backward on torch CPU fp32")
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as H
+        case = H.make_case(name, "cpu")
+        B = CPU_PORT_BATCH.get(name, 1024)
+        batch = case.make_batch(B, "cpu", 0)
+        params = [p.detach().clone() for p in case.plan_params]
+
+        def one():
+            return float(H.oracle_run(name, params, batch)["loss"])
+        what = "oracle port (same torch CPU ops as the reference, pinned bit-exactly to it; oracle/_ref absent)"
     t_begin = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(max(min(warmup, 1), 1)):
+        one()
+    times = []
+    for _ in range(max(steps, 1)):
         t0 = time.perf_counter()
-        oracle_cpu_step(name, batch, params)
+        one()
         times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
             break
-    per = sum(times) / len(times)
-    return {"value": B * nsteps / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{name} at batch {B} (full horizon {nsteps}), {len(times)} timed fwd+bwd passes of the "
-                      f"oracle port (same torch CPU ops as the reference, pinned bit-exact to it)",
+    per = sorted(times)[len(times) // 2]
+    return {"value": B * nsteps / per, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{name} at batch {B} (full horizon {nsteps}), median of {len(times)} timed fwd+bwd passes of the {what}",
             "ms_per_step": per * 1e3, "batch": B, "steps_timed": len(times)}
+
+
+# ------------------------------------------------------------------------------------------- helpers of the B200 arm
+def make_inputs(case, B, dev, seed):
+    """Synthetic batch of SURVEY 8(d2) resident on `dev` (tensors a config creates with torch.zeros are made on the device)."""
+    import torch
+    batch = case.make_batch(B, dev, seed)
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+def quick_raw(name, dev, steps=5, warmup=3, batch=None):
+    """Kernel-path throughput of another config (extra.per_config): the config's own batch, device-resident."""
+    import ctypes
+    import torch
+    from neuromancer_b200 import _lib, configs, rollout as nr
+    case = configs.make_case(name, dev)
+    B = batch or case.default_batch
+    data = make_inputs(case, B, dev, 0)
+    plan = case.system.plan_for(case.system.init(dict(data)), loss=case.problem.loss)
+    raw = nr.RawTrainStep(plan, data)
+    for _ in range(warmup):
+        raw.forward(); raw.backward()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        raw.forward(); raw.backward()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    info = _lib.load().nm_kernel_info(ctypes.byref(plan.c)).decode()
+    out = {"batch": B, "nsteps": case.nsteps, "ms_per_step": ms, "value": B * case.nsteps / (ms * 1e-3), "unit": UNIT,
+           "loss": float(raw.scalars[-1]), "kernel_info": info.split(" compiled_terms")[0],
+           "note": "device-resident forward + adjoint, back to back (no L2 flush), CUDA events"}
+    del raw, data, plan, case
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c5")
     ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -137,8 +216,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     import torch
-    import helpers as H
-    case0 = H.configs.build_case(args.workload)
+    from neuromancer_b200 import configs
+    case0 = configs.build_case(args.workload)
     nsteps = case0.nsteps
     # c5 is quoted at a fixed GLOBAL batch (4M trajectories at 1/2/4/8 GPUs: strong scaling); every other config at a
     # fixed batch per GPU (weak scaling)
@@ -146,21 +225,16 @@ def main():
     per_gpu = args.batch or (case0.default_batch // max(world, 1) if strong else case0.default_batch)
     cfg = {"workload": args.workload, "nsteps": nsteps, "batch_per_gpu": per_gpu,
            "global_batch": per_gpu * max(world, 1), "parallelism": f"dp{world}",
-           "description": {"c1": "DPC double integrator, MLP 2-20-20-20-20-1 ReLU, linear SSM",
-                           "c2": "DPC reference tracking, TwoTank ODE + RK4, MLP_bounds 4-32-32-2 GELU",
-                           "c3": "neural-ODE system ID, RK4 over MLP RHS 2-60-60-60-2 ReLU",
-                           "c4": "building thermal DPC, linear SSM nx=4, 48-step preview, MLP_bounds 193-32-32-1",
-                           "c4p": "c4 with SystemPreview windows over the raw signals (in-kernel gather)",
-                           "c5": "parametric nonlinear DPC, 12-state coupled VdP + RK4, MLP 24-128x4-6 GELU"}.get(args.workload, args.workload)}
+           "description": DESCRIPTION.get(args.workload, args.workload)}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = time_cpu_reference(args.workload, max(args.steps, 1), args.warmup, nsteps)
+        res = time_cpu_reference(args.workload, max(min(args.steps, 5), 1), args.warmup, nsteps)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": res["steps_timed"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "steps": res["steps_timed"], "warmup": 1, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {**cfg, "cpu_sample_batch": res["batch"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -186,10 +260,8 @@ def main():
     from neuromancer_b200.distributed import GradientSync
 
     B = cfg["batch_per_gpu"]
-    case = H.make_case(args.workload, dev)                    # same seed on every rank: replicated weights
-    batch_cpu = case.make_batch(B, "cpu", rank)               # per-rank shard of the sampled batch
-    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
-    batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()}
+    case = configs.make_case(args.workload, dev)              # same seed on every rank: replicated weights
+    batch = make_inputs(case, B, dev, rank)                   # per-rank shard of the sampled batch, resident in HBM
     sync = GradientSync() if world > 1 else None
     plan = case.system.plan_for(case.system.init(dict(batch)), loss=case.problem.loss)
     raw = nr.RawTrainStep(plan, batch, world_size=world)
@@ -241,16 +313,22 @@ def main():
     import ctypes
     from neuromancer_b200 import _lib
     kernel_info = _lib.load().nm_kernel_info(ctypes.byref(plan.c)).decode()
+    wide = "wide" in kernel_info
+    del raw, batch, plan
+    torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ end-to-end through the public API
     e2e = None
     if not args.no_e2e:
+        Be = min(B, E2E_MAX_BATCH)
         params = [q for q in case.plan_params if q.requires_grad]
+        batch_cpu = case.make_batch(Be, "cpu", rank)
+        pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in batch_cpu.items()}
+        del batch_cpu
         tensors = [k for k, v in pinned.items() if isinstance(v, torch.Tensor)]
         h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in tensors)
 
         from neuromancer_b200.dataset import DevicePrefetcher
-
         from neuromancer_b200.trainer import LaggedScalarReader
         reader = LaggedScalarReader(dev)                      # every step's loss is read on the host, one step late
         losses_seen = []
@@ -267,63 +345,76 @@ def main():
         def host_batches(n):                                  # every step copies its inputs from pinned host memory
             for _ in range(n):
                 yield dict(pinned)
-        # the caching allocator needs a few dozen steps to stop growing its pool (measured: host time per
-        # step falls from ~4 ms to ~0.4 ms over the first ~100 steps, tools/e2e_probe.py) -- warm it up
-        for b in DevicePrefetcher(host_batches(max(args.warmup, 100)), dev):
+        # a step of the headline workload takes ~0.1-1 s: two warm-up steps settle the caching allocator; small
+        # workloads (ms per step) keep the long warm-up of round 1 (the allocator needs ~100 steps to stop growing)
+        slow = ms_per_step * (Be / B) > 50.0
+        n_warm = 2 if slow else max(args.warmup, 100)
+        n_timed = max(2, min(args.steps, 5)) if slow else args.steps
+        n_rep = 1 if slow else 3
+        for b in DevicePrefetcher(host_batches(n_warm), dev):
             step_api(b)
         losses_seen.extend(reader.drain())
         losses_seen.clear()
-        # the public training loop (Trainer.train) iterates a DevicePrefetcher: the copy of step k+1's inputs is in
-        # flight while step k computes; all `steps` copies happen inside the timed region.  The region is only
-        # ~20 ms long, so one host hiccup (allocator, GC, a driver lock taken by nvidia-smi) can dominate it: the
-        # K-step region is repeated three times and the MEDIAN repetition is reported (all three are listed).
         import gc
         reps = []
-        for _ in range(3):
+        for _ in range(n_rep):
             gc.collect()
             gc.disable()
             barrier()
             t0 = time.perf_counter()
-            for b in DevicePrefetcher(host_batches(args.steps), dev):
+            for b in DevicePrefetcher(host_batches(n_timed), dev):
                 step_api(b)
             losses_seen.extend(reader.drain())                # the last steps' losses: still inside the timed region
             barrier()
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             gc.enable()
-            assert len(losses_seen) == args.steps, "every timed step's loss must have reached the host"
+            assert len(losses_seen) == n_timed, "every timed step's loss must have reached the host"
             losses_seen.clear()
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             reps.append(float(dt))
-        dt_med = sorted(reps)[1]
-        e2e = {"value": world * B * nsteps * args.steps / dt_med, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4, "ms_per_step": dt_med / args.steps * 1e3,
-               "ms_per_step_repetitions": [r / args.steps * 1e3 for r in reps],
-               "api": "DevicePrefetcher (Trainer.train loop) -> Problem.forward + loss.backward; every batch copied from pinned host memory inside the timed region, every step's loss read back on the host (asynchronously, one step late); median of 3 repetitions of the K-step region"}
+        dt_med = sorted(reps)[len(reps) // 2]
+        e2e = {"value": world * Be * nsteps * n_timed / dt_med, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": dt_med / n_timed * 1e3, "steps": n_timed, "batch_per_gpu": Be,
+               "ms_per_step_repetitions": [r / n_timed * 1e3 for r in reps],
+               "api": "DevicePrefetcher (Trainer.train loop) -> Problem.forward + loss.backward; every batch copied from pinned host memory "
+                      "inside the timed region (the copy of step k+1 overlaps step k), every step's loss read back on the host "
+                      "(asynchronously, one step late)" + ("" if Be == B else f"; per-GPU batch capped at {Be} (host batches are double-buffered on the device)")}
+        del pinned
+        torch.cuda.empty_cache()
 
-    # clocks / throttle reasons sampled every 20 ms over both timed regions (device-resident steps and end-to-end steps)
+    # clocks / throttle reasons sampled over both timed regions (device-resident steps and end-to-end steps)
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ------------------------------------------------------------------ roofline of the dominant kernel (adjoint)
+    # ------------------------------------------------------------------ roofline of the dominant kernel group (adjoint)
     peaks = read_peaks()
     flop_step = case.flop_per_traj_step                        # fwd+bwd algorithmic FLOP per trajectory-step
-    bwd_flops = (2.0 / 3.0) * flop_step * B * nsteps          # the adjoint launch's share (2 of 3 passes)
+    bwd_flops = (2.0 / 3.0) * flop_step * B * nsteps          # the adjoint launches' share (2 of 3 passes)
     fwd_flops = (1.0 / 3.0) * flop_step * B * nsteps
-    tf32x3_peak = peaks["bf16_tflops"] / 2.0 / 3.0             # fp32-accurate tensor-pipe peak (3xTF32 split)
+    tf32x3_peak = peaks["bf16_tflops"] / 2.0 / 3.0             # fp32-accurate peak of a 3xTF32 split (BASELINE.md ceilings)
+    fp16x3_peak = peaks["bf16_tflops"] / 3.0                   # fp32-accurate peak of the 3xFP16 split the wide kernels run
+    peak = fp16x3_peak if wide else tf32x3_peak
     achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
     traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     traffic = None
-    if os.path.exists(traffic_path):                           # one ncu --set full capture, scaled to this batch
+    if os.path.exists(traffic_path):                           # ncu capture of the adjoint launches, scaled to this batch
         tj = json.load(open(traffic_path))
         traffic = tj["bwd_dram_bytes_per_launch"] * (B / tj["batch"])
-    bwd_kernel = "nm_tc_bwd_kernel" if "bwd[tcgen05" in kernel_info else "nm_bwd_kernel"
-    roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": tf32x3_peak,
-                "unit": "TFLOP/s", "frac": achieved / tf32x3_peak, "traffic": traffic,
-                "peak_source": f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 2 (tf32) / 3 (3xTF32 fp32-accurate split)",
+    if wide:
+        bwd_kernel = "nm_wide_bwd_kernel + nm_wide_wgrad_kernel + term-gradient kernels (the whole adjoint window)"
+    else:
+        bwd_kernel = "nm_tc_bwd_kernel" if "bwd[tcgen05" in kernel_info else "nm_bwd_kernel"
+    roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": (f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 3 (3-product fp16 split, fp32-accurate)" if wide else
+                                f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 2 (tf32) / 3 (3xTF32 fp32-accurate split)"),
+                "frac_of_3xtf32_peak": achieved / tf32x3_peak, "tf32x3_peak": tf32x3_peak,
+                "step_achieved_tflops": flop_step * B * nsteps / ((fwd_ms + bwd_ms) * 1e-3) / 1e12,
+                "step_frac": flop_step * B * nsteps / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak,
                 "ffma_peak_tflops": 72.2, "ffma_frac": achieved / 72.2,
                 "ffma_peak_source": "measured, profiles/r01_pipe_rates_microbench.txt",
                 "kernel_ms": bwd_ms, "fwd_kernel_ms": fwd_ms,
@@ -333,16 +424,29 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        res = time_cpu_reference(args.workload, 3, 1, nsteps)
+        res = time_cpu_reference(args.workload, 2, 1, nsteps, budget_s=30.0)
         cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    extra = None
+    if world == 1 and not args.no_per_config:
+        extra = {"per_config": {}}
+        for name in ("c1", "c2", "c3", "c4"):
+            if name == args.workload:
+                continue
+            try:
+                extra["per_config"][name] = quick_raw(name, dev)
+            except Exception as exc:                          # a failing side config must not lose the headline line
+                extra["per_config"][name] = {"error": repr(exc)[:300]}
+
+    dtype = "f32 (policy MMAs: 3-product fp16 split, 22-bit; weight-gradient operands 1xFP16-rn)" if wide else \
+            ("f32 (fwd 3xTF32, wgrad 1xTF32-rn)" if "1xTF32" in kernel_info else "f32")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {**cfg, "l2": "flushed between timed steps (256 MiB memset)", "loss": loss_val,
                        "kernel_info": kernel_info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "wall_s_timed_region": t_wall}
+            "cpu_baseline": cpu_baseline, "extra": extra, "wall_s_timed_region": t_wall}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)

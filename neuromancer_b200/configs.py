@@ -567,3 +567,13 @@ AOT_CASES = list(CASES) + list(EXTRA_CASES)
 
 def build_case(name: str, batch=None, device="cpu", seed=0, **kw) -> Case:
     return {**CASES, **EXTRA_CASES}[name](seed=seed, **kw)
+
+
+def make_case(name: str, device, seed=0, **kw) -> Case:
+    """``build_case`` moved to ``device`` with its lowered plan parameters attached (``case.plan_params``: the
+    parameters in the order of the flat arena) -- what bench.py and the parity tests run."""
+    case = build_case(name, seed=seed, **kw)
+    case.problem.to(device)
+    plan = case.plan()
+    case.plan_params = list(plan.params)
+    return case

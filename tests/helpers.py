@@ -52,11 +52,7 @@ def oracle_run(name, params_cpu, batch_cpu, dtype=torch.float32, backward=True, 
 
 
 def make_case(name, device, seed=0, **kw):
-    case = configs.build_case(name, seed=seed, **kw)
-    case.problem.to(device)
-    plan = case.plan()
-    case.plan_params = list(plan.params)
-    return case
+    return configs.make_case(name, device, seed=seed, **kw)
 
 
 def rel_err(a, b):
