@@ -194,9 +194,9 @@ template <class Sp> struct Wide<Sp, true> {
     }
     return e;
   }
-  // steps per adjoint launch: the staging buffer (tiles * CS items of ITEM_BYTES) is capped at NM_WIDE_STAGING_GB (default 16)
+  // steps per adjoint launch: the staging buffer (tiles * CS items of ITEM_BYTES) is capped at NM_WIDE_STAGING_GB (default 24)
   static int chunk_steps(int64_t B, int T) {
-    double cap_gb = 16.0;
+    double cap_gb = 24.0;
     if (const char* s = getenv("NM_WIDE_STAGING_GB")) { const double v = atof(s); if (v > 0.0) cap_gb = v; }
     const double per_step = double((B + 127) / 128) * double(C::ITEM_BYTES);
     int64_t cs = int64_t(cap_gb * 1073741824.0 / per_step);
@@ -225,7 +225,7 @@ template <class Sp> struct Wide<Sp, true> {
   // returns the number of blocks that wrote term partials (0: the caller scores the terms)
   static int launch_fwd(const NmPlan& p, const FwdArgs& a, const float* params, void* wprep, int sms, cudaStream_t st) {
     wd::nm_wide_prep_kernel<Sp><<<32, 256, 0, st>>>(p, params, static_cast<uint8_t*>(wprep));
-    nm_wide_fwd_kernel<Sp><<<grid_for(a.B, sms), C::THREADS, C::SMEM_BYTES, st>>>(p, a);
+    nm_wide_fwd_kernel<Sp><<<grid_for(a.B, sms), C::FWD_THREADS, C::SMEM_BYTES, st>>>(p, a);
     if (Sp::NTERMS > 0 && a.fused_terms) {
       int tmax = 1;
       for (int k = 0; k < p.n_terms; ++k) tmax = p.terms[k].t_len > tmax ? p.terms[k].t_len : tmax;

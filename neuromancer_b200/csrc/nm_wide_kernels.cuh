@@ -184,6 +184,12 @@ struct WideCfg {
   static constexpr int SLOT_COLS = 2 * H, A_HI = 0, A_LO = H / 2, DCOL = H;
   // ---- launch shape
   static constexpr int THREADS = 256;                                     // 2 tile slots x 4 owner warps (register file: allocation is per 4 warps)
+#ifdef NM_TUNE_WFT
+  static constexpr int FWD_TPT = NM_TUNE_WFT;
+#else
+  static constexpr int FWD_TPT = 2;                                       // forward kernel: threads per trajectory (16 warps: the epilogues hide each other's stalls)
+#endif
+  static constexpr int FWD_THREADS = 256 * FWD_TPT;
   // ---- adjoint: staging item (one tile-step), byte offsets of the operand tiles X[feature/8][128][8] halves
   static constexpr int GRP = 128 * 16;                                    // one 8-feature group of a tile
   static constexpr int a_off(int l) { return l == 0 ? 0 : (K0P / 8) * GRP + (l - 1) * (H / 8) * GRP; }       // a_l, l = 0..NL-1
@@ -341,10 +347,10 @@ __device__ __forceinline__ int slot_rounds(int num_tiles, int slot) {
 // (PenaltyLoss scoring is NOT fused here: read back per trajectory it is a chain of L2-latency loads during which both
 // tile slots and the tensor pipe idle -- measured 45 % of this kernel; the streaming nm_term_score_kernel does it at HBM rate)
 template <class S>
-__global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
+__global__ void __launch_bounds__(wd::WideCfg<S>::FWD_THREADS, 1) nm_wide_fwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ FwdArgs args) {
   using C = wd::WideCfg<S>;
   using M = typename C::M;
-  constexpr int NX = S::NX, NU = S::NU, K0 = C::K0, H = C::H, NL = C::NL, TILE = 128;
+  constexpr int NX = S::NX, NU = S::NU, K0 = C::K0, H = C::H, NL = C::NL, TILE = 128, TPT = C::FWD_TPT;
   extern __shared__ __align__(1024) uint8_t sm[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);           // 0 weights, 1/2 operands ready (slot), 3/4 MMAs done (slot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
   const NmPlan& p = plan;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 128); mbar_init(&bars[2], 128);
+    mbar_init(&bars[1], 128 * TPT); mbar_init(&bars[2], 128 * TPT);
     mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
     mbar_fence_init();
   }
@@ -369,8 +375,11 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
   const int T = p.nsteps;
 
   {
-    // ------------------------------------------------------------------ owners: thread = trajectory = TMEM lane
-    const int slot = warp >> 2, m_ = tid & 127;
+    // ------------------------------------------------------------------ owners: TPT threads per trajectory (= TMEM lane); thread
+    // `half` of a trajectory owns the columns [half * H / TPT, (half + 1) * H / TPT) of every layer.  The per-trajectory
+    // scalars (state, dynamics) are kept by every thread of the trajectory; thread 0 writes operands and trajectories.
+    const int slot = warp / (4 * TPT), half = (warp >> 2) % TPT, m_ = (warp & 3) * 32 + (tid & 31);
+    constexpr int HC = H / TPT;
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t cb = tmem + lane_base + slot * C::SLOT_COLS;
     const uint32_t t_hi = cb + C::A_HI, t_lo = cb + C::A_LO, t_d = cb + C::DCOL;
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
     uint64_t* bar_done = &bars[3 + slot];
     uint32_t ph_done = 0, ph_ops = 0;
     const float act_prm = p.policy.act_param;
-    const bool issuer = (warp & 3) == 0;
+    const bool issuer = (warp % (4 * TPT)) == 0;
     const uint32_t sbase = smem_u32(sm), cbs = tmem + slot * C::SLOT_COLS;
     // operands of this thread are in tensor memory; the slot's first warp waits for all 128 rows and issues MMA batch `bi`
     // (0: layer 0, 1 .. NL-2: hidden layer, NL-1: output layer)
@@ -405,10 +414,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
       float x[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = __ldg(args.x0 + b * NX + i);
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1)) * NX + i] = x[i];
-      }
+      if (valid && half == 0) st_vec<NX>(args.x_traj + (b * (T + 1)) * NX, x);
       float in_pre[K0];
 #pragma unroll
       for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
 #pragma unroll
         for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
         tc_policy_state<S, K0>(x, yv, in);
-        { uint32_t hi0[C::K0P / 2]; wd::put_input<C>(t_hi, t_lo, in, hi0); (void)hi0; }
+        if (half == 0) { uint32_t hi0[C::K0P / 2]; wd::put_input<C>(t_hi, t_lo, in, hi0); (void)hi0; }
         arrive_ops(0);
         if (t + 1 < T) wd::policy_exo<S, K0>(p, args.exo, b, t + 1, in_pre);     // exogenous inputs one step ahead
         // hidden activations a_1 .. a_{NL-1}
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
           mbar_wait(bar_done, ph_done); ph_done ^= 1;
           tc::fence_after();
 #pragma unroll 1
-          for (int c0 = 0; c0 < H; c0 += 32) {
+          for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
             float v[32];
             uint32_t hi[16], lo[16];
             tc::tmem_ld<32>(t_d + c0, v);
@@ -457,22 +463,20 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_fwd_kernel
           o16[j] += bo[j];
           u[j] = bounds_fwd<M::BOUNDS>(o16[j], p.policy.bmin[j], p.policy.bmax[j]);
         }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < NU; ++j) args.u_traj[(b * T + t) * NU + j] = u[j];
+        if (valid && half == 0) {
+          st_vec<NU>(args.u_traj + (b * T + t) * NU, u);
           if (args.chk != nullptr) {
+            float oc[NU];
 #pragma unroll
-            for (int j = 0; j < NU; ++j) args.chk[(b * T + t) * NU + j] = o16[j];
+            for (int j = 0; j < NU; ++j) oc[j] = o16[j];
+            st_vec<NU>(args.chk + (b * T + t) * NU, oc);
           }
         }
         float xn[NX], dv_[1] = {0.f};
         Dyn<S>::step(p, x, u, dv_, xn);
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < NX; ++i) args.x_traj[(b * (T + 1) + t + 1) * NX + i] = x[i];
-        }
+        if (valid && half == 0) st_vec<NX>(args.x_traj + (b * (T + 1) + t + 1) * NX, x);
       }
     }
   }
@@ -724,32 +728,39 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
       for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3], pol_stage);
     };
 
+    // Everything a step reads from HBM is requested one step ahead -- across tile boundaries too (with short chunks a
+    // tile is only CSn steps long): rows of step t-1 of this trajectory, or the first rows of the next tile's trajectory
+    float lam_pre[NX], x_pre[NX], o_pre[NU], in_pre[K0], g_pre[RW];
+#pragma unroll
+    for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
+    auto prefetch_rows = [&](int64_t bq, int tq) {
+      wd::ld_row<NX>(x_pre, args.x_traj + (bq * (T + 1) + tq) * NX);
+      wd::ld_row<NU>(o_pre, args.chk + (bq * T + tq) * NU);
+      wd::ld_row<RW>(g_pre, wargs.G + (bq * int64_t(CSn + 1) + (tq - t_lo)) * RW);
+      wd::policy_exo<S, K0>(p, args.exo, bq, tq, in_pre);
+    };
+    auto prefetch_tile = [&](int tile_q) {                 // first step of a tile + its incoming co-state
+      const int64_t bq_raw = int64_t(tile_q) * TILE + m_;
+      const int64_t bq = bq_raw < args.B ? bq_raw : args.B - 1;
+      prefetch_rows(bq, t_hi - 1);
+      if (t_hi == T) {
+        float gT[RW];
+        wd::ld_row<RW>(gT, wargs.G + (bq * int64_t(CSn + 1) + CSn) * RW);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam_pre[i] = gT[i];
+      } else wd::ld_row<NX>(lam_pre, wargs.lam_carry + bq * NX);
+    };
+    if (int(blockIdx.x) * 2 + slot < args.num_tiles) prefetch_tile(int(blockIdx.x) * 2 + slot);
     for (int r = 0;; ++r) {
       const int tile = (r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot;
       if (tile >= args.num_tiles) break;
+      const int tile_next = tile + 2 * int(gridDim.x);
       const int64_t b_raw = int64_t(tile) * TILE + m_;
       const bool valid = b_raw < args.B;
       const int64_t b = valid ? b_raw : args.B - 1;
-      float lam[NX], x_pre[NX], o_pre[NU], in_pre[K0], g_pre[RW];
-      const float* __restrict__ Gb = wargs.G + b * int64_t(CSn + 1) * RW;
+      float lam[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) lam[i] = 0.f;
-#pragma unroll
-      for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
-      wd::ld_row<NX>(x_pre, args.x_traj + (b * (T + 1) + (t_hi - 1)) * NX);
-      wd::ld_row<NU>(o_pre, args.chk + (b * T + (t_hi - 1)) * NU);
-      wd::ld_row<RW>(g_pre, Gb + (CSn - 1) * RW);
-      wd::policy_exo<S, K0>(p, args.exo, b, t_hi - 1, in_pre);
-      if (t_hi == T) {
-        if (valid) {
-          { float gT[RW]; wd::ld_row<RW>(gT, Gb + CSn * RW);
-#pragma unroll
-            for (int i = 0; i < NX; ++i) lam[i] = gT[i]; }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) lam[i] = valid ? wargs.lam_carry[b * NX + i] : 0.f;
-      }
+      for (int i = 0; i < NX; ++i) lam[i] = valid ? lam_pre[i] : 0.f;
 #pragma unroll 1
       for (int t = t_hi - 1; t >= t_lo; --t) {
         uint8_t* item = wargs.staging + (size_t(tile) * CSn + size_t(t - t_lo)) * C::ITEM_BYTES;
@@ -772,12 +783,8 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
         }
         { WP_T0(); arrive_ops(0); WP_ADD(w_arr); }   // -> recompute of layer 0
         WP_T0();
-        if (t > 0) {                                  // next step's inputs (also across the chunk boundary: harmless)
-          wd::ld_row<NX>(x_pre, args.x_traj + (b * (T + 1) + t - 1) * NX);
-          wd::ld_row<NU>(o_pre, args.chk + (b * T + t - 1) * NU);
-          wd::policy_exo<S, K0>(p, args.exo, b, t - 1, in_pre);
-          if (t > t_lo) wd::ld_row<RW>(g_pre, Gb + (t - 1 - t_lo) * RW);
-        }
+        if (t > t_lo) prefetch_rows(b, t - 1);
+        else if (tile_next < args.num_tiles) prefetch_tile(tile_next);
         // ---- dynamics adjoint, loss-term gradients, cotangent of the raw policy output (all while the MMAs run)
         float u[NU], gx[NX], gu[NU], gtx[NX], cot[NOUT];
 #pragma unroll
