@@ -423,14 +423,20 @@ REF_BUILDERS = {
 }
 
 
+# constraint matrices of AggregateLoss.calculate_constraints (reference loss.py:86-106): values, violations and their
+# eq / ineq column partitions -- stored in the goldens so that the product's lazily built C_* outputs are compared by content
+CMAT_KEYS = ("C_values", "C_violations", "C_eq_values", "C_ineq_values", "C_eq_violations", "C_ineq_violations")
+
+
 def run_reference(problem, params, batch, traj_keys, term_names):
     for p in params:
         p.grad = None
     out = problem({**batch, "name": "train"})
     if params:
         out["train_loss"].backward()
+    cmat = {k: out[f"train_{k}"].detach() for k in CMAT_KEYS if f"train_{k}" in out}
     return {"traj": {k: out[f"train_{k}"].detach() for k in traj_keys},
-            "terms": {n: out[f"train_{n}"].detach() for n in term_names},
+            "terms": {n: out[f"train_{n}"].detach() for n in term_names}, "cmat": cmat,
             "objective_loss": torch.as_tensor(out["train_objective_loss"]).detach(),
             "penalty_loss": torch.as_tensor(out["train_penalty_loss"]).detach(),
             "loss": out["train_loss"].detach(),
@@ -487,6 +493,8 @@ def main() -> int:
             arrays[k] = ref[k].numpy()
         for i, g in enumerate(ref["grads"]):
             arrays[f"grad_{i}"] = g.numpy()
+        for k, v in ref["cmat"].items():
+            arrays[f"cmat_{k}"] = v.numpy()
         arrays["term_names"] = np.array(term_names)
         arrays["traj_keys"] = np.array(traj_keys)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **arrays)

@@ -78,14 +78,21 @@ def test_neural_ode_classes_are_served_by_the_tensor_core_kernels(nm_lib):
     info = nm_lib.nm_kernel_info(C.byref(configs.build_case("t_int_rkf_node").plan().c)).decode()
     assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "3xTF32" in info
     # narrow closed-loop policies (tiny fan-in / fan-out, hidden layers >= 16 wide) run in policy mode; wide fan-in
-    # (c4: 193 inputs) and 128-wide policies (c5) stay on the FFMA kernels
+    # (c4: 193 inputs) stays on the FFMA kernels
     for name in ("c1", "c2", "t_vdp_rk4_tanh_clamp"):
         info = nm_lib.nm_kernel_info(C.byref(configs.build_case(name).plan().c)).decode()
         assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "1xTF32-rn" in info, (name, info)
-    for name in ("c4", "c5", "t_int_luther_vdp", "t_node_policy_euler"):
+    for name in ("c4", "t_int_luther_vdp", "t_node_policy_euler"):
         assert "tcgen05" not in nm_lib.nm_kernel_info(C.byref(configs.build_case(name).plan().c)).decode(), name
+    # the 128-wide policy of c5 runs on the wide-policy family (nm_wide_kernels.cuh): 3-product fp16 MMAs, weights
+    # resident in shared memory, raw policy output as the checkpoint
+    info = nm_lib.nm_kernel_info(C.byref(configs.build_case("c5").plan().c)).decode()
+    assert "fwd[tcgen05 3xFP16 wide" in info and "bwd[tcgen05 3xFP16 wide" in info and "wgrad GEMM 1xFP16-rn" in info, info
+    assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c5").plan().c), 1000, C.byref(C.c_size_t())) == L.NM_OK
     plan = configs.build_case("c3").plan()
     nbytes = C.c_size_t()
+    assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c5").plan().c), 1000, C.byref(nbytes)) == L.NM_OK
+    assert nbytes.value == 1000 * 200 * 6 * 4                                 # wide policy mode: o_t[6] per step
     assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(plan.c), 1000, C.byref(nbytes)) == L.NM_OK
     assert nbytes.value == 1000 * plan.c.nsteps * 3 * plan.c.nx * 4          # RK4: 3 kept stages
     # policy mode keeps the raw policy output o_t of every step

@@ -23,7 +23,8 @@ def load_golden(name):
     terms = {str(n): torch.from_numpy(z[f"term_{n}"]) for n in z["term_names"]}
     grads = [torch.from_numpy(z[f"grad_{i}"]) for i in range(len(params))]
     scal = {k: torch.from_numpy(z[k]) for k in ("objective_loss", "penalty_loss", "loss")}
-    return dict(params=params, inputs=inputs, traj=traj, terms=terms, grads=grads, **scal)
+    cmat = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("cmat_")}
+    return dict(params=params, inputs=inputs, traj=traj, terms=terms, grads=grads, cmat=cmat, **scal)
 
 
 def test_pin_report_says_bit_exact():
