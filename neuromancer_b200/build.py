@@ -145,7 +145,10 @@ def _table(fn: str, vals: List[int]) -> str:
 TUNING: Dict[str, Dict[str, int]] = {}
 # substring rules: the small RKF neural-ODE test shape is forced onto the tensor-core forward kernel so that the
 # parity suite covers it on a second shape class (its 16-wide layers would not pick it on throughput grounds)
-TUNING_RULES = [("rhs4[3-16-16-2]", {"tc": 1})]
+# c4 (193-wide fan-in, 192 of them exogenous look-ahead features): the exogenous part of the first layer is hoisted out of the
+# horizon loop into one GEMM before the rollout and one after the adjoint (nm_kernels.cuh, HoistedMlp) -- GPU parity
+# green since round 2 (tests/test_hoist_gpu.py, then the whole -m gpu suite with the rule on)
+TUNING_RULES = [("rhs4[3-16-16-2]", {"tc": 1}), ("pol[193-32-32-1]", {"hoist": 1})]
 
 
 def parse_tune(text: str) -> Dict[str, int]:

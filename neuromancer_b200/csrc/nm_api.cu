@@ -368,7 +368,9 @@ int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes) {
   if (!bytes || B < 1) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
   *bytes = 0;
   // a shape class on the tensor-core path states what its kernels keep (policy mode: the raw policy output o_t)
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  // (the same (shape, term) lookup as nm_rollout_forward / nm_rollout_backward: entries of one shape class may be
+  // compiled with different tuning, and with it different checkpoint layouts)
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str());
   if (e != nullptr && e->chk_floats_per_step >= 0) {
     *bytes = size_t(B) * size_t(plan->nsteps) * size_t(e->chk_floats_per_step) * sizeof(float);
     return NM_OK;
@@ -384,7 +386,7 @@ int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes,
   int rc = validate(plan);
   if (rc != NM_OK) return rc;
   if (B < 1 || !fwd_bytes || !bwd_bytes) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str());
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str());
   if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
   rc = e->workspace(plan, B, fwd_bytes, bwd_bytes);
   if (rc != NM_OK) return rc;

@@ -53,7 +53,22 @@ def _dense_matrix(module, what):
     return inner.weight
 
 
+# Tensors whose VALUES are baked into the POD plan (SSM / output-map matrices, white-box ODE constants, bounds, step
+# size).  RolloutPlan records (tensor, version counter) for each: an in-place change (optimizer step, load_state_dict,
+# .data assignment shows up as a new object) makes the cached plan stale and System.plan_for rebuilds it.
+_TRACK: Optional[list] = None
+
+
+def _track(t):
+    if _TRACK is not None and isinstance(t, torch.Tensor):
+        _TRACK.append((t, t._version))
+
+
 def _fill_matrix(dst, weight, rows, cols):
+    if weight.requires_grad:
+        raise PlanError("a trainable linear map (requires_grad=True) of the SSM / output node is not differentiated by "
+                        "the fused path: freeze it (requires_grad_(False)) -- its gradient would silently be zero")
+    _track(weight)
     w = weight.detach().to("cpu", torch.float32)
     assert w.shape == (rows, cols), (tuple(w.shape), rows, cols)
     if rows > L.NM_MAX_DIM or cols > L.NM_MAX_DIM:
@@ -93,6 +108,7 @@ def _mlp_descriptor(mlp: _blocks.MLP, what: str) -> Tuple[L.NmMlp, List[torch.nn
         for name, val, dst in (("min", bmin, d.bmin), ("max", bmax, d.bmax)):
             if val is None:
                 raise PlanError(f"{what}: bounds need both min and max")
+            _track(val)
             t = torch.as_tensor(val, dtype=torch.float32).detach().cpu().reshape(-1)
             if t.numel() == 1:
                 t = t.expand(nout)
@@ -422,6 +438,25 @@ class RolloutPlan:
                  loss=None):
         self.layout, self.nsteps, self.loss = layout, int(nsteps), loss
         lay = layout
+        global _TRACK
+        _TRACK = self._tracked = []
+        try:
+            self._build(lay, shapes, loss)
+        finally:
+            _TRACK = None
+        self._term_weights = self._current_term_weights()
+
+    def _current_term_weights(self):
+        return tuple(float(t.weight) for t, _ in getattr(self, "fused_terms", []))
+
+    def values_stale(self) -> bool:
+        """True when a tensor or term weight whose value the plan carries has changed since lowering."""
+        for t, v in self._tracked:
+            if t._version != v:
+                return True
+        return self._current_term_weights() != self._term_weights
+
+    def _build(self, lay, shapes, loss):
         p = L.NmPlan()
         p.abi_version = L.NM_ABI_VERSION
         p.nx, p.nu, p.ny, p.nsteps = lay.nx, lay.nu, lay.ny, self.nsteps
@@ -517,6 +552,7 @@ class RolloutPlan:
             if fn.nm_integrator_id is None:
                 raise PlanError(f"integrator {type(fn).__name__} is not fused (Euler, RK2, RK4 are)")
             p.dyn_kind, p.integrator, p.h = L.NM_DYN_ODE, fn.nm_integrator_id, fn.step_size()
+            _track(fn.h)
             rhs = fn.block
             if isinstance(rhs, _blocks.MLP):
                 p.rhs_kind = L.NM_RHS_MLP
@@ -529,6 +565,8 @@ class RolloutPlan:
                 p.rhs_mlp = desc
             elif isinstance(rhs, _ode.ODESystem) and rhs.nm_rhs_id is not None:
                 p.rhs_kind = rhs.nm_rhs_id
+                for q in rhs.parameters():
+                    _track(q)
                 consts = rhs.rhs_constants()
                 for i, v in enumerate(consts):
                     p.rhs_const[i] = v

@@ -135,9 +135,13 @@ class FusedRollout(torch.autograd.Function):
         B = ctx.B
 
         def ext(g, ref):
+            # gradients of torch-evaluated terms (python_terms, BarrierLoss, user losses on the trajectories) are LOCAL means;
+            # the fused terms are divided by the global trajectory count in the kernel, and the data-parallel all-reduce
+            # SUMS -- scale the external part by 1 / world_size so that both follow DDP-average semantics
             if g is None or ref is None or g.numel() == 0:
                 return None
-            return g.contiguous()
+            g = g.contiguous()
+            return g / _WORLD["size"] if _WORLD["size"] > 1 else g
         gx, gu, gy = ext(gx, x_traj), ext(gu, u_traj), ext(gy, y_traj)
         if gs is not None:
             gs = gs.contiguous()
@@ -163,6 +167,26 @@ class FusedRollout(torch.autograd.Function):
         for q, (off, n) in zip(plan.params, plan.param_slices):
             grads.append(gflat[off:off + n].view(q.shape) if q.requires_grad else None)
         return tuple(grads)
+
+
+def _checked_exo(plan: RolloutPlan, data, x_in) -> List[torch.Tensor]:
+    """Exogenous / loss-only inputs in plan order.  The kernels index them as ``[B, steps, width]`` with the batch of the
+    initial condition: a tensor on another device, with another batch size (incl. a broadcastable batch of 1) or with
+    another trailing shape than the plan was lowered for would be read out of bounds -- rejected here instead."""
+    out = []
+    B = x_in.shape[0]
+    for i, k in enumerate(plan.exo_keys):
+        t = data[k]
+        _require_cuda(t, k)
+        if t.device != x_in.device:
+            raise PlanError(f"'{k}' lives on {t.device}, the initial condition on {x_in.device}")
+        want = (B, int(plan.c.exo[i].steps), int(plan.c.exo[i].width))
+        if t.dim() == 3 and t.shape[0] == 1 and B > 1 and tuple(t.shape[1:]) == want[1:]:
+            t = t.expand(B, -1, -1)                      # the reference would broadcast a batch of one
+        if tuple(t.shape) != want:
+            raise PlanError(f"'{k}' must be {list(want)} ([batch, steps, width] of this plan), got {list(t.shape)}")
+        out.append(t.contiguous())
+    return out
 
 
 class RolloutRunner:
@@ -195,11 +219,7 @@ class RolloutRunner:
             if k is not None and k in data:
                 raise PlanError(f"key '{k}' is produced by the rollout but already present in the data")
         x0 = x_in[:, 0, :].contiguous()
-        exo = []
-        for k in plan.exo_keys:
-            t = data[k]
-            _require_cuda(t, k)
-            exo.append(t.contiguous())
+        exo = _checked_exo(plan, data, x_in)
         if not self.arena.in_sync(plan.params):
             self.arena.adopt(plan.params)
         x, u, y, scalars = FusedRollout.apply(self, x0, *exo, *plan.params)
@@ -299,9 +319,7 @@ class RawTrainStep:
         if not self.runner.arena.in_sync(plan.params):
             self.runner.arena.adopt(plan.params)
         self.x0 = x_in[:, 0, :].contiguous()
-        self.exo = [batch[k].contiguous() for k in plan.exo_keys]
-        for e, k in zip(self.exo, plan.exo_keys):
-            _require_cuda(e, k)
+        self.exo = _checked_exo(plan, batch, x_in)
         B = self.B
         self.x_traj = torch.empty(B, p.nsteps + 1, p.nx, dtype=torch.float32, device=dev)
         self.u_traj = torch.empty(B, p.nsteps, p.nu, dtype=torch.float32, device=dev) if p.nu else None

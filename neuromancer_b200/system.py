@@ -108,6 +108,8 @@ class System(nn.Module):
         shapes = {k: tuple(v.shape) for k, v in data.items() if isinstance(v, torch.Tensor)}
         key = (nsteps, id(loss), tuple(sorted((k, s[1:]) for k, s in shapes.items())))
         plan = self._plans.get(key)
+        if plan is not None and plan.values_stale():     # a matrix / constant / bound the plan carries by value has changed
+            plan = None
         if plan is None:
             plan = _plan.RolloutPlan(layout, nsteps, shapes, loss=loss)
             self._plans = {key: plan}        # keep one: shapes rarely change during training

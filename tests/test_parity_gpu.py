@@ -240,8 +240,9 @@ def test_preview_window_indexing_bit_exact(pad_mode):
 
 def test_c4_preview_formulation_equals_materialised_lookahead():
     """C4 with SystemPreview windows over the raw signals reproduces C4 with materialised look-ahead
-    tensors (grid_response.ipynb) -- identical arithmetic, so trajectories agree bitwise and gradients to
-    round-off of the (differently split) weight-gradient partial sums."""
+    tensors (grid_response.ipynb).  Since round 2 the materialised formulation runs with its exogenous first-layer
+    part hoisted into a GEMM in front of the rollout (tensor-core policy mode), the windowed one on the FFMA kernels:
+    different summation orders, so the two agree to the trajectory / gradient tolerances instead of bitwise."""
     a = H.make_case("c4", DEV, seed=2)
     b = H.make_case("c4p", DEV, seed=2)
     with torch.no_grad():
@@ -250,10 +251,10 @@ def test_c4_preview_formulation_equals_materialised_lookahead():
     ra = H.product_run(a, to_dev(a.make_batch(150, "cpu", 3)))
     rb = H.product_run(b, to_dev(b.make_batch(150, "cpu", 3)))
     for k in ("x", "u", "y"):
-        assert torch.equal(ra["traj"][k], rb["traj"][k]), k
-    assert_rel(rb["loss"], ra["loss"], 1e-6, "loss")
+        assert_rel(rb["traj"][k], ra["traj"][k], TRAJ_RTOL, f"trajectory {k}")
+    assert_rel(rb["loss"], ra["loss"], 1e-5, "loss")
     for ga, gb in zip(ra["grads"], rb["grads"]):
-        assert_rel(gb, ga, 1e-5, "grad")
+        assert_rel(gb, ga, GRAD_RTOL, "grad")
 
 
 # ------------------------------------------------------------------------------------------------
