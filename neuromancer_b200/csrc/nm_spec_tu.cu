@@ -291,7 +291,7 @@ template <class Sp> struct Wide<Sp, true> {
           ++launches;
         }
       }
-      nm_wide_bwd_kernel<Sp><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(p, w);
+      nm_wide_bwd_kernel<Sp><<<grid, C::BWD_THREADS, C::SMEM_BYTES, st>>>(p, w);
       const int64_t n_items = tiles * int64_t(t_hi - t_lo);
       const int wgrid = int(n_items < sms ? n_items : sms);
       nm_wide_wgrad_kernel<Sp><<<wgrid, C::WG_THREADS, C::WG_SMEM_BYTES, st>>>(p, staging, n_items, scale, a.grad_partials);

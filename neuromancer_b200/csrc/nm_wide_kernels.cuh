@@ -190,6 +190,12 @@ struct WideCfg {
   static constexpr int FWD_TPT = 2;                                       // forward kernel: threads per trajectory (16 warps: the epilogues hide each other's stalls)
 #endif
   static constexpr int FWD_THREADS = 256 * FWD_TPT;
+#ifdef NM_TUNE_WBT
+  static constexpr int BWD_TPT = NM_TUNE_WBT;
+#else
+  static constexpr int BWD_TPT = 1;                                       // adjoint kernel: threads per trajectory (2 measured SLOWER: 19.0 vs 15.6 ms at B = 37,888 -- 128 registers spill the dynamics adjoint, and the primary thread serialises the scalar work)
+#endif
+  static constexpr int BWD_THREADS = 256 * BWD_TPT;
   // ---- adjoint: staging item (one tile-step), byte offsets of the operand tiles X[feature/8][128][8] halves
   static constexpr int GRP = 128 * 16;                                    // one 8-feature group of a tile
   static constexpr int a_off(int l) { return l == 0 ? 0 : (K0P / 8) * GRP + (l - 1) * (H / 8) * GRP; }       // a_l, l = 0..NL-1
@@ -648,10 +654,10 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_tb_kernel(const __grid_c
 }
 
 template <class S>
-__global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ WideBwdArgs wargs) {
+__global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ WideBwdArgs wargs) {
   using C = wd::WideCfg<S>;
   using M = typename C::M;
-  constexpr int NX = S::NX, NU = S::NU, K0 = C::K0, H = C::H, NL = C::NL, TILE = 128, NOUT = C::NOUT;
+  constexpr int NX = S::NX, NU = S::NU, K0 = C::K0, H = C::H, NL = C::NL, TILE = 128, NOUT = C::NOUT, TPT = C::BWD_TPT, HC = H / TPT;
   const BwdArgs& args = wargs.b;
   extern __shared__ __align__(1024) uint8_t sm[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);           // 0 weights, 1/2 operands ready (slot), 3/4 MMAs done (slot)
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
   constexpr int RW = NX + NU;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 128); mbar_init(&bars[2], 128);
+    mbar_init(&bars[1], 128 * TPT); mbar_init(&bars[2], 128 * TPT);
     mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
     mbar_fence_init();
   }
@@ -681,8 +687,13 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
   const float gs = wargs.scale->gs, inv_gs = wargs.scale->inv_gs;
 
   {
-    // ------------------------------------------------------------------ owners
-    const int slot = warp >> 2, m_ = tid & 127;
+    // ------------------------------------------------------------------ owners: TPT threads per trajectory (= TMEM lane).  Thread
+    // `half` owns the columns [half * HC, (half + 1) * HC) of every layer epilogue; thread 0 ("primary") alone carries the
+    // trajectory's scalars: co-state, dynamics adjoint, loss-term gradients, the policy input operand and the cotangent of
+    // the raw policy output, which it hands to its partner through shared memory (the output-layer image region: unused here).
+    const int slot = warp / (4 * TPT), half = (warp >> 2) % TPT, m_ = (warp & 3) * 32 + (tid & 31);
+    const bool primary = half == 0;
+    float* cotx = reinterpret_cast<float*>(sm + C::imgo_off()) + (slot * 128 + m_) * 8;
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t cb = tmem + lane_base + slot * C::SLOT_COLS;
     const uint32_t t_hi_ = cb + C::A_HI, t_lo_ = cb + C::A_LO, t_d = cb + C::DCOL;
@@ -690,7 +701,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
     uint64_t* bar_done = &bars[3 + slot];
     uint32_t ph_done = 0, ph_ops = 0;
     const float act_prm = p.policy.act_param;
-    const bool issuer = (warp & 3) == 0;
+    const bool issuer = (warp % (4 * TPT)) == 0;
     const uint32_t sbase = smem_u32(sm), cbs = tmem + slot * C::SLOT_COLS;
     // operands of this thread are in tensor memory; the slot's first warp waits for all 128 rows and issues MMA batch `bi`:
     //   0: recompute layer 0    1 .. NL-2: recompute hidden layer bi    NL-1 .. 2NL-4: data gradient of hidden layer
@@ -730,9 +741,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 
     // Everything a step reads from HBM is requested one step ahead -- across tile boundaries too (with short chunks a
     // tile is only CSn steps long): rows of step t-1 of this trajectory, or the first rows of the next tile's trajectory
-    float lam_pre[NX], x_pre[NX], o_pre[NU], in_pre[K0], g_pre[RW];
-#pragma unroll
-    for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
+    float lam_pre[NX] = {}, x_pre[NX] = {}, o_pre[NU] = {}, in_pre[K0] = {}, g_pre[RW] = {};
     auto prefetch_rows = [&](int64_t bq, int tq) {
       wd::ld_row<NX>(x_pre, args.x_traj + (bq * (T + 1) + tq) * NX);
       wd::ld_row<NU>(o_pre, args.chk + (bq * T + tq) * NU);
@@ -750,7 +759,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
         for (int i = 0; i < NX; ++i) lam_pre[i] = gT[i];
       } else wd::ld_row<NX>(lam_pre, wargs.lam_carry + bq * NX);
     };
-    if (int(blockIdx.x) * 2 + slot < args.num_tiles) prefetch_tile(int(blockIdx.x) * 2 + slot);
+    if (primary && int(blockIdx.x) * 2 + slot < args.num_tiles) prefetch_tile(int(blockIdx.x) * 2 + slot);
     for (int r = 0;; ++r) {
       const int tile = (r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot;
       if (tile >= args.num_tiles) break;
@@ -774,7 +783,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
         for (int q = 0; q < RW; ++q) g_cur[q] = g_pre[q];
         tc_policy_state<S, K0>(x, yv, in);
-        {
+        if (primary) {
           uint32_t hi0[C::K0P / 2];
           wd::put_input<C>(t_hi_, t_lo_, in, hi0);
           uint8_t* q = item + C::a_off(0) + m_ * 16;
@@ -783,10 +792,16 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
         }
         { WP_T0(); arrive_ops(0); WP_ADD(w_arr); }   // -> recompute of layer 0
         WP_T0();
+        float gx[NX], gtx[NX], cot[NOUT];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { gx[i] = 0.f; gtx[i] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) cot[j] = 0.f;
+        if (primary) {
         if (t > t_lo) prefetch_rows(b, t - 1);
         else if (tile_next < args.num_tiles) prefetch_tile(tile_next);
         // ---- dynamics adjoint, loss-term gradients, cotangent of the raw policy output (all while the MMAs run)
-        float u[NU], gx[NX], gu[NU], gtx[NX], cot[NOUT];
+        float u[NU], gu[NU];
 #pragma unroll
         for (int j = 0; j < NU; ++j) u[j] = bounds_fwd<M::BOUNDS>(o_cur[j], p.policy.bmin[j], p.policy.bmax[j]);
         Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
@@ -812,6 +827,11 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
           for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3], pol_stage);
         }
+        if constexpr (TPT > 1) {                      // -> partner thread (read after the batch-1 arrivals: release / acquire through bar_ops)
+#pragma unroll
+          for (int j = 0; j < NOUT; ++j) cotx[j] = cot[j];
+        }
+        }
         WP_ADD(w_dyn);
         // ---- recompute: a_{l+1} = act(z_l), derivative stash; the last one goes straight into the backward pass
 #pragma unroll 1
@@ -822,7 +842,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
           tc::fence_after();
           WP_T0();
 #pragma unroll 1
-          for (int c0 = 0; c0 < H; c0 += 32) {
+          for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
             float v[32], d[32];
             uint32_t hi[16], lo[16];
             tc::tmem_ld<32>(t_d + c0, v);
@@ -852,7 +872,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
                 }
                 v[i] = da0 * d[i]; v[i + 1] = da1 * d[i + 1]; v[i + 2] = da2 * d[i + 2]; v[i + 3] = da3 * d[i + 3];
               }
-              if (c0 == 0) {
+              if (c0 == half * HC) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
               }
@@ -865,6 +885,13 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
           }
           WP_ADD(w_epi_rc);
           { WP_T0(); arrive_ops(l + 1); WP_ADD(w_arr); }   // -> recompute of layer l+1, or (last: bi = NL-1) data gradient of layer NL-2
+          if constexpr (TPT > 1) {
+            if (l == 0 && !primary) {                 // all arrivals of batch 1 (odd phase of bar_ops: 2 (NL - 1) batches per step) are in:
+              mbar_wait(bar_ops, 1);                  // the primary wrote the cotangent before it arrived
+#pragma unroll
+              for (int j = 0; j < NOUT; ++j) cot[j] = cotx[j];
+            }
+          }
         }
         // ---- data gradients: D = dA_l (cotangent of a_l), l = NL-2 .. 1;  dZ_{l-1} = dA_l * act'(z_{l-1})
 #pragma unroll 1
@@ -872,7 +899,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
           // the stashed derivatives come from L2: two 32-column chunks are always in flight -- chunks 0 and 1 are
           // requested before the wait for the MMAs, chunk c+2 when chunk c has been consumed
           float4 dq[2][8];
-          const float4* __restrict__ sl = stash + (l - 1) * (H / 4) * 128;
+          const float4* __restrict__ sl = stash + ((l - 1) * (H / 4) + half * (HC / 4)) * 128;
 #pragma unroll
           for (int i = 0; i < 8; ++i) dq[0][i] = wd::ld_global_f4(sl + i * 128, pol_stash);
 #pragma unroll
@@ -881,20 +908,20 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
           tc::fence_after();
           WP_T0();
 #pragma unroll 1
-          for (int c2 = 0; c2 < H; c2 += 64) {
+          for (int c2 = 0; c2 < HC; c2 += 64) {
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
-              const int c0 = c2 + hb * 32;
+              const int cl = c2 + hb * 32, c0 = half * HC + cl;      // column within this thread's range / within the layer
               float v[32];
               uint32_t hi[16], lo[16];
               tc::tmem_ld<32>(t_d + c0, v);
 #pragma unroll
               for (int i = 0; i < 8; ++i) { v[4 * i] *= dq[hb][i].x; v[4 * i + 1] *= dq[hb][i].y; v[4 * i + 2] *= dq[hb][i].z; v[4 * i + 3] *= dq[hb][i].w; }
-              if (c0 + 64 < H) {
+              if (cl + 64 < HC) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dq[hb][i] = wd::ld_global_f4(sl + ((c0 + 64) / 4 + i) * 128, pol_stash);
+                for (int i = 0; i < 8; ++i) dq[hb][i] = wd::ld_global_f4(sl + ((cl + 64) / 4 + i) * 128, pol_stash);
               }
-              if (c0 == 0) {
+              if (cl == 0) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
               }
@@ -911,7 +938,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
         // ---- gradient of the policy input (state segment) closes the loop
         { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait_in); }
         tc::fence_after();
-        {
+        if (primary) {
           float gin[C::GWP];
 #pragma unroll
           for (int c0 = 0; c0 < C::GWP; c0 += 16) {
@@ -933,7 +960,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam[i] = valid ? gx[i] + gtx[i] : 0.f;
       }
-      if (valid) {
+      if (valid && primary) {
         if (t_lo == 0) {
           if (args.grad_x0 != nullptr) {
 #pragma unroll
@@ -956,12 +983,12 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::THREADS, 1) nm_wide_bwd_kernel
       float v = dbo[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((tid & 31) == 0) dbred[warp * C::NOP + j] = v;
+      if ((tid & 31) == 0 && primary) dbred[(slot * 4 + (warp & 3)) * C::NOP + j] = v;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dzmax = fmaxf(dzmax, __shfl_xor_sync(0xffffffffu, dzmax, o));
     if ((tid & 31) == 0) atomicMax(&wargs.scale->max_bits, __float_as_uint(dzmax));
-    wd::named_bar_sync(1, 256);
+    wd::named_bar_sync(1, C::BWD_THREADS);
     if (tid < NOUT && C::BIAS && p.policy.trainable) {
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += dbred[w * C::NOP + tid];
