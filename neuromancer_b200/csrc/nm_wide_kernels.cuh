@@ -71,20 +71,20 @@ __device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// L2 residency: the derivative stash is rewritten and re-read every step (evict_last keeps it out of DRAM); the staging
-// tiles are written once and read by a later kernel (evict_first: they must not push the stash out)
-__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol)); return pol; }
-__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol)); return pol; }
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+// L2 residency: the derivative stash is rewritten and re-read every step (evict_last keeps it out of DRAM: 256-bit
+// accesses carry the priority as a qualifier -- a policy operand would cost two R2UR per access); the staging tiles are
+// written once and read by a later kernel (streaming stores: they must not push the stash out)
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void st_global_f4(float4* p, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+struct alignas(32) float8 { float v[8]; };
+__device__ __forceinline__ void st_stash8(float8* p, const float* v) {
+  asm volatile("st.global.L2::evict_last.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
-__device__ __forceinline__ float4 ld_global_f4(const float4* p, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
-  return v;
+__device__ __forceinline__ void ld_stash8(const float8* p, float* v) {
+  asm volatile("ld.global.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
+               "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
@@ -202,7 +202,7 @@ struct WideCfg {
   static constexpr int z_off(int l) { return a_off(NL - 1) + (H / 8) * GRP + l * (H / 8) * GRP; }             // dZ_l, l = 0..NL-2
   static constexpr int c_off() { return z_off(NL - 2) + (H / 8) * GRP; }                                      // cotangent of the raw output
   static constexpr int ITEM_BYTES = c_off() + (NOP / 8) * GRP;
-  // derivative stash of one tile slot: act'(z_l) for l = 0..NL-3, [l][k/4][128][4] floats
+  // derivative stash of one tile slot: act'(z_l) for l = 0..NL-3, [l][k/8][128][8] floats
   static constexpr int STASH_SLOT_BYTES = (NL - 2) * H * 128 * 4;
   // ---- weight-gradient GEMM: tensor-memory columns
   static constexpr int wg_col(int l) { return l == 0 ? 0 : (l < NL - 1 ? K0P + (l - 1) * H : K0P + NHID * H); }
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
         __syncwarp();
       }
     };
-    float4* stash = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(wargs.stash) + size_t(blockIdx.x * 2 + slot) * C::STASH_SLOT_BYTES) + m_;
+    wd::float8* stash = reinterpret_cast<wd::float8*>(reinterpret_cast<uint8_t*>(wargs.stash) + size_t(blockIdx.x * 2 + slot) * C::STASH_SLOT_BYTES) + m_;
     const float* __restrict__ Wout = reinterpret_cast<const float*>(sm + C::wout_off());
     float dbo[NOUT];                                  // output-bias gradient (scaled), summed over this thread's trajectory-steps
 #pragma unroll
@@ -731,12 +731,11 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
 #ifdef NM_TUNE_WPROF
     const long long w_begin = clock64();
 #endif
-    const uint64_t pol_stage = wd::l2_policy_evict_first(), pol_stash = wd::l2_policy_evict_last();
     // staging store of 32 consecutive features (16 packed words) of operand tile `toff`
     auto stage32 = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[16]) {
       uint8_t* q = item + toff + (c0 / 8) * C::GRP + m_ * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3], pol_stage);
+      for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
     };
 
     // Everything a step reads from HBM is requested one step ahead -- across tile boundaries too (with short chunks a
@@ -788,7 +787,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
           wd::put_input<C>(t_hi_, t_lo_, in, hi0);
           uint8_t* q = item + C::a_off(0) + m_ * 16;
 #pragma unroll
-          for (int g = 0; g < C::K0P / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi0[4 * g], hi0[4 * g + 1], hi0[4 * g + 2], hi0[4 * g + 3], pol_stage);
+          for (int g = 0; g < C::K0P / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi0[4 * g], hi0[4 * g + 1], hi0[4 * g + 2], hi0[4 * g + 3]);
         }
         { WP_T0(); arrive_ops(0); WP_ADD(w_arr); }   // -> recompute of layer 0
         WP_T0();
@@ -825,7 +824,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
           }
           uint8_t* q = item + C::c_off() + m_ * 16;
 #pragma unroll
-          for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3], pol_stage);
+          for (int g = 0; g < C::NOP / 8; ++g) wd::st_global_v4(q + g * C::GRP, ch[4 * g], ch[4 * g + 1], ch[4 * g + 2], ch[4 * g + 3]);
         }
         if constexpr (TPT > 1) {                      // -> partner thread (read after the batch-1 arrivals: release / acquire through bar_ops)
 #pragma unroll
@@ -859,7 +858,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
               wd::tmem_st16u(t_hi_ + c0 / 2, hi);
               wd::tmem_st16u(t_lo_ + c0 / 2, lo);
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) wd::st_global_f4(stash + (l * (H / 4) + (c0 + i) / 4) * 128, make_float4(d[i], d[i + 1], d[i + 2], d[i + 3]), pol_stash);
+              for (int i = 0; i < 32; i += 8) wd::st_stash8(stash + (l * (H / 8) + (c0 + i) / 8) * 128, d + i);
             } else {
               // output layer backward on the CUDA cores: dA[k] = sum_j cot[j] W_out[j][k];  dZ_{NL-2} = dA * act'
 #pragma unroll
@@ -898,12 +897,12 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
         for (int l = NL - 2; l >= 1; --l) {
           // the stashed derivatives come from L2: two 32-column chunks are always in flight -- chunks 0 and 1 are
           // requested before the wait for the MMAs, chunk c+2 when chunk c has been consumed
-          float4 dq[2][8];
-          const float4* __restrict__ sl = stash + ((l - 1) * (H / 4) + half * (HC / 4)) * 128;
+          float dq[2][32];
+          const wd::float8* __restrict__ sl = stash + ((l - 1) * (H / 8) + half * (HC / 8)) * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dq[0][i] = wd::ld_global_f4(sl + i * 128, pol_stash);
+          for (int i = 0; i < 4; ++i) wd::ld_stash8(sl + i * 128, dq[0] + 8 * i);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dq[1][i] = wd::ld_global_f4(sl + (8 + i) * 128, pol_stash);
+          for (int i = 0; i < 4; ++i) wd::ld_stash8(sl + (4 + i) * 128, dq[1] + 8 * i);
           { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait_dg); }
           tc::fence_after();
           WP_T0();
@@ -916,10 +915,10 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
               uint32_t hi[16], lo[16];
               tc::tmem_ld<32>(t_d + c0, v);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { v[4 * i] *= dq[hb][i].x; v[4 * i + 1] *= dq[hb][i].y; v[4 * i + 2] *= dq[hb][i].z; v[4 * i + 3] *= dq[hb][i].w; }
+              for (int i = 0; i < 32; ++i) v[i] *= dq[hb][i];
               if (cl + 64 < HC) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dq[hb][i] = wd::ld_global_f4(sl + ((cl + 64) / 4 + i) * 128, pol_stash);
+                for (int i = 0; i < 4; ++i) wd::ld_stash8(sl + ((cl + 64) / 8 + i) * 128, dq[hb] + 8 * i);
               }
               if (cl == 0) {
 #pragma unroll
