@@ -1,9 +1,10 @@
 """
 Bridge between the Python API and the C ABI (``libnm_rollout.so``).
 
-``FusedRollout`` is the ``torch.autograd.Function`` whose forward launches ``nm_rollout_forward``
-(one persistent kernel for the whole horizon + a tiny finalise kernel) and whose backward launches
-``nm_rollout_backward`` (the fused adjoint / BPTT kernel + gradient finalise).  PyTorch is used for
+The two entry points are registered with ``torch.library`` as the custom operators ``nmfused::rollout_fwd``
+(``nm_rollout_forward``: one persistent kernel for the whole horizon + a tiny finalise kernel) and
+``nmfused::rollout_bwd`` (``nm_rollout_backward``: the fused adjoint / BPTT kernels + gradient finalise), tied together
+by ``register_autograd``.  PyTorch is used for
 device memory, streams and autograd bookkeeping only; all arithmetic of the path happens in the
 sm_100a kernels under ``csrc/``.
 
@@ -12,7 +13,8 @@ No fallback: non-CUDA tensors or a missing extension raise immediately.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Tuple
+import weakref
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -77,96 +79,145 @@ class _Workspace:
         return self.buf
 
 
-class FusedRollout(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, runner, x0, *tensors):
-        # tensors = exo tensors (n_exo) followed by the parameters (views of the arena)
-        plan: RolloutPlan = runner.plan
-        p = plan.c
-        lib = L.load()
-        B = x0.shape[0]
-        dev = x0.device
-        n_exo = p.n_exo
-        exo = tensors[:n_exo]
-        x_traj = torch.empty(B, p.nsteps + 1, p.nx, dtype=torch.float32, device=dev)
-        u_traj = torch.empty(B, p.nsteps, p.nu, dtype=torch.float32, device=dev) if p.nu else None
-        y_traj = torch.empty(B, p.nsteps, p.ny, dtype=torch.float32, device=dev) if p.ny else None
-        scalars = torch.empty(plan.n_scalars, dtype=torch.float32, device=dev)
-        fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
-        L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
-                "nm_rollout_workspace_bytes")
-        ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
-        exo_ptrs = (C.c_void_p * max(n_exo, 1))(*[e.data_ptr() for e in exo])
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        chk = None
-        if any(ctx.needs_input_grad):                 # a backward pass may follow: keep stage checkpoints
-            cb = C.c_size_t()
-            L.check(lib.nm_rollout_checkpoint_bytes(C.byref(p), B, C.byref(cb)), "nm_rollout_checkpoint_bytes")
-            if cb.value:
-                chk = torch.empty(cb.value // 4, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            L.check(lib.nm_rollout_forward(C.byref(p), _ptr(runner.arena.flat), _ptr(x0), exo_ptrs,
-                                           _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(scalars), _ptr(chk),
-                                           _ptr(ws), ws.numel(), B, stream), "nm_rollout_forward")
-        runner.launches += lib.nm_last_launch_count()
-        ctx.runner, ctx.B = runner, B
-        ctx.n_exo = n_exo
-        ctx.n_tensors = len(tensors)
-        outs = [x_traj, u_traj if u_traj is not None else x_traj.new_empty(0),
-                y_traj if y_traj is not None else x_traj.new_empty(0), scalars]
-        ctx.has_chk = chk is not None
-        ctx.save_for_backward(outs[0], outs[1], outs[2], chk if chk is not None else x_traj.new_empty(0), *exo)
-        ctx.mark_non_differentiable(*[o for o in outs[1:3] if o.numel() == 0])
-        return tuple(outs)
+# ------------------------------------------------------------------------------------------------
+# PyTorch binding: the two C-ABI entry points as custom operators
+#   nmfused::rollout_fwd   nm_rollout_forward  (persistent rollout kernel + loss finalise)
+#   nmfused::rollout_bwd   nm_rollout_backward (adjoint / BPTT kernels + gradient finalise)
+# registered with torch.library, differentiable through register_autograd, launched on torch's current stream.  A plan
+# is not a tensor: the operators take the handle of its RolloutRunner (POD NmPlan + parameter arena + workspace).
+_RUNNERS: Dict[int, "weakref.ReferenceType"] = {}
 
-    @staticmethod
-    def backward(ctx, gx, gu, gy, gs):
-        runner = ctx.runner
-        plan: RolloutPlan = runner.plan
-        p = plan.c
-        lib = L.load()
-        saved = ctx.saved_tensors
-        x_traj = saved[0]
-        u_traj = saved[1] if saved[1].numel() else None
-        y_traj = saved[2] if saved[2].numel() else None
-        chk = saved[3] if ctx.has_chk else None
-        exo = saved[4:]
-        dev = x_traj.device
-        B = ctx.B
 
-        def ext(g, ref):
-            # gradients of torch-evaluated terms (python_terms, BarrierLoss, user losses on the trajectories) are LOCAL means;
-            # the fused terms are divided by the global trajectory count in the kernel, and the data-parallel all-reduce
-            # SUMS -- scale the external part by 1 / world_size so that both follow DDP-average semantics
-            if g is None or ref is None or g.numel() == 0:
-                return None
-            g = g.contiguous()
-            return g / _WORLD["size"] if _WORLD["size"] > 1 else g
-        gx, gu, gy = ext(gx, x_traj), ext(gu, u_traj), ext(gy, y_traj)
-        if gs is not None:
-            gs = gs.contiguous()
-        else:
-            gs = torch.zeros(plan.n_scalars, dtype=torch.float32, device=dev)
-        gflat = torch.empty_like(runner.arena.flat)
-        fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
-        L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
-                "nm_rollout_workspace_bytes")
-        ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
-        exo_ptrs = (C.c_void_p * max(ctx.n_exo, 1))(*[e.data_ptr() for e in exo])
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        want_x0 = ctx.needs_input_grad[1]
-        gx0 = torch.empty(B, p.nx, dtype=torch.float32, device=dev) if want_x0 else None
-        with torch.cuda.device(dev):
-            L.check(lib.nm_rollout_backward(
-                C.byref(p), _ptr(runner.arena.flat), exo_ptrs, _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(chk),
-                _ptr(gs), _ptr(gx), _ptr(gu), _ptr(gy), _ptr(gflat), _ptr(gx0), _ptr(ws), ws.numel(),
-                B, B * _WORLD["size"], stream), "nm_rollout_backward")
-        runner.launches += lib.nm_last_launch_count()
-        runner.last_grad_flat = gflat
-        grads = [None, gx0] + [None] * ctx.n_exo
-        for q, (off, n) in zip(plan.params, plan.param_slices):
-            grads.append(gflat[off:off + n].view(q.shape) if q.requires_grad else None)
-        return tuple(grads)
+def _runner(handle: int) -> "RolloutRunner":
+    ref = _RUNNERS.get(handle)
+    r = ref() if ref is not None else None
+    if r is None:
+        raise RuntimeError(f"nmfused: rollout plan handle {handle} is not alive")
+    return r
+
+
+def _empty(ref: torch.Tensor) -> torch.Tensor:
+    return ref.new_empty(0)
+
+
+@torch.library.custom_op("nmfused::rollout_fwd", mutates_args=(), device_types="cuda")
+def rollout_fwd(handle: int, x0: torch.Tensor, exo: Sequence[torch.Tensor], params: Sequence[torch.Tensor],
+                keep_checkpoints: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (x [B, T+1, nx], u [B, T, nu] | empty, y [B, T, ny] | empty, scalars [n_terms + 3], checkpoints | empty).
+    `params` are the module parameters (views of the runner's flat arena, which is what the kernels read)."""
+    runner = _runner(handle)
+    plan: RolloutPlan = runner.plan
+    p = plan.c
+    lib = L.load()
+    B, dev = x0.shape[0], x0.device
+    x_traj = torch.empty(B, p.nsteps + 1, p.nx, dtype=torch.float32, device=dev)
+    u_traj = torch.empty(B, p.nsteps, p.nu, dtype=torch.float32, device=dev) if p.nu else None
+    y_traj = torch.empty(B, p.nsteps, p.ny, dtype=torch.float32, device=dev) if p.ny else None
+    scalars = torch.empty(plan.n_scalars, dtype=torch.float32, device=dev)
+    fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
+    L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)), "nm_rollout_workspace_bytes")
+    ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
+    exo_ptrs = (C.c_void_p * max(len(exo), 1))(*[e.data_ptr() for e in exo])
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    chk = None
+    if keep_checkpoints:                              # a backward pass may follow: keep the checkpoints
+        cb = C.c_size_t()
+        L.check(lib.nm_rollout_checkpoint_bytes(C.byref(p), B, C.byref(cb)), "nm_rollout_checkpoint_bytes")
+        if cb.value:
+            chk = torch.empty(cb.value // 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.nm_rollout_forward(C.byref(p), _ptr(runner.arena.flat), _ptr(x0), exo_ptrs,
+                                       _ptr(x_traj), _ptr(u_traj), _ptr(y_traj), _ptr(scalars), _ptr(chk),
+                                       _ptr(ws), ws.numel(), B, stream), "nm_rollout_forward")
+    runner.launches += lib.nm_last_launch_count()
+    return (x_traj, u_traj if u_traj is not None else _empty(x_traj), y_traj if y_traj is not None else _empty(x_traj),
+            scalars, chk if chk is not None else _empty(x_traj))
+
+
+@rollout_fwd.register_fake
+def _(handle, x0, exo, params, keep_checkpoints):
+    runner = _runner(handle)
+    p, B = runner.plan.c, x0.shape[0]
+    lib = L.load()
+    n_chk = 0
+    if keep_checkpoints:
+        cb = C.c_size_t()
+        L.check(lib.nm_rollout_checkpoint_bytes(C.byref(p), B, C.byref(cb)), "nm_rollout_checkpoint_bytes")
+        n_chk = cb.value // 4
+    return (x0.new_empty(B, p.nsteps + 1, p.nx), x0.new_empty((B, p.nsteps, p.nu) if p.nu else (0,)),
+            x0.new_empty((B, p.nsteps, p.ny) if p.ny else (0,)), x0.new_empty(runner.plan.n_scalars), x0.new_empty(n_chk))
+
+
+@torch.library.custom_op("nmfused::rollout_bwd", mutates_args=(), device_types="cuda")
+def rollout_bwd(handle: int, exo: Sequence[torch.Tensor], x_traj: torch.Tensor, u_traj: torch.Tensor, y_traj: torch.Tensor,
+                checkpoints: torch.Tensor, grad_scalars: Optional[torch.Tensor], grad_x: Optional[torch.Tensor],
+                grad_u: Optional[torch.Tensor], grad_y: Optional[torch.Tensor], want_x0: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (flat parameter gradient [n_params], d loss / d x0 [B, nx] | empty).  grad_scalars: upstream gradient of the
+    [terms | objective | penalty | loss] scalars; grad_x/u/y: upstream gradients of the trajectories (torch-evaluated terms)."""
+    runner = _runner(handle)
+    plan: RolloutPlan = runner.plan
+    p = plan.c
+    lib = L.load()
+    dev, B = x_traj.device, x_traj.shape[0]
+    world = _WORLD["size"]
+
+    def ext(g):
+        # gradients of torch-evaluated terms (python_terms, BarrierLoss, user losses on the trajectories) are LOCAL means;
+        # the fused terms are divided by the global trajectory count in the kernel, and the data-parallel all-reduce
+        # SUMS -- scale the external part by 1 / world_size so that both follow DDP-average semantics
+        if g is None or g.numel() == 0:
+            return None
+        g = g.contiguous()
+        return g / world if world > 1 else g
+    gx, gu, gy = ext(grad_x), ext(grad_u) if p.nu else None, ext(grad_y) if p.ny else None
+    gs = grad_scalars.contiguous() if grad_scalars is not None else torch.zeros(plan.n_scalars, dtype=torch.float32, device=dev)
+    gflat = torch.empty_like(runner.arena.flat)
+    fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
+    L.check(lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)), "nm_rollout_workspace_bytes")
+    ws = runner.workspace.get(max(fwd_b.value, bwd_b.value), dev)
+    exo_ptrs = (C.c_void_p * max(len(exo), 1))(*[e.data_ptr() for e in exo])
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    gx0 = torch.empty(B, p.nx, dtype=torch.float32, device=dev) if want_x0 else None
+    with torch.cuda.device(dev):
+        L.check(lib.nm_rollout_backward(
+            C.byref(p), _ptr(runner.arena.flat), exo_ptrs, _ptr(x_traj), _ptr(u_traj if u_traj.numel() else None),
+            _ptr(y_traj if y_traj.numel() else None), _ptr(checkpoints if checkpoints.numel() else None),
+            _ptr(gs), _ptr(gx), _ptr(gu), _ptr(gy), _ptr(gflat), _ptr(gx0), _ptr(ws), ws.numel(),
+            B, B * world, stream), "nm_rollout_backward")
+    runner.launches += lib.nm_last_launch_count()
+    runner.last_grad_flat = gflat
+    return gflat, gx0 if gx0 is not None else _empty(gflat)
+
+
+@rollout_bwd.register_fake
+def _(handle, exo, x_traj, u_traj, y_traj, checkpoints, grad_scalars, grad_x, grad_u, grad_y, want_x0):
+    runner = _runner(handle)
+    return torch.empty_like(runner.arena.flat), x_traj.new_empty((x_traj.shape[0], runner.plan.c.nx) if want_x0 else (0,))
+
+
+def _fwd_setup_context(ctx, inputs, output):
+    handle, x0, exo, params, _keep = inputs
+    x_traj, u_traj, y_traj, _scalars, chk = output
+    ctx.handle, ctx.n_exo, ctx.n_params = handle, len(exo), len(params)
+    ctx.save_for_backward(x_traj, u_traj, y_traj, chk, *exo)
+    ctx.mark_non_differentiable(chk)
+
+
+def _fwd_backward(ctx, gx, gu, gy, gs, _gchk):
+    runner = _runner(ctx.handle)
+    plan = runner.plan
+    saved = ctx.saved_tensors
+    x_traj, u_traj, y_traj, chk = saved[:4]
+    exo = list(saved[4:])
+    want_x0 = bool(ctx.needs_input_grad[1])
+    gflat, gx0 = torch.ops.nmfused.rollout_bwd(ctx.handle, exo, x_traj, u_traj, y_traj, chk, gs, gx,
+                                               gu if u_traj.numel() else None, gy if y_traj.numel() else None, want_x0)
+    grads = [gflat[off:off + n].view(q.shape) if q.requires_grad else None
+             for q, (off, n) in zip(plan.params, plan.param_slices)]
+    return None, (gx0 if want_x0 else None), [None] * ctx.n_exo, grads, None
+
+
+rollout_fwd.register_autograd(_fwd_backward, setup_context=_fwd_setup_context)
 
 
 def _checked_exo(plan: RolloutPlan, data, x_in) -> List[torch.Tensor]:
@@ -198,6 +249,8 @@ class RolloutRunner:
         self.workspace = _Workspace()
         self.launches = 0
         self.last_grad_flat = None
+        self.handle = id(self)
+        _RUNNERS[self.handle] = weakref.ref(self, lambda _r, h=self.handle: _RUNNERS.pop(h, None))
         lib = L.load()
         if not lib.nm_has_kernel(C.byref(plan.c)):
             from . import build
@@ -222,7 +275,8 @@ class RolloutRunner:
         exo = _checked_exo(plan, data, x_in)
         if not self.arena.in_sync(plan.params):
             self.arena.adopt(plan.params)
-        x, u, y, scalars = FusedRollout.apply(self, x0, *exo, *plan.params)
+        keep = torch.is_grad_enabled() and (x0.requires_grad or any(q.requires_grad for q in plan.params))
+        x, u, y, scalars, _chk = torch.ops.nmfused.rollout_fwd(self.handle, x0, exo, list(plan.params), keep)
         return x, (u if lay.action_key is not None else None), (y if lay.output_key is not None else None), scalars
 
 

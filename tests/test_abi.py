@@ -77,12 +77,14 @@ def test_neural_ode_classes_are_served_by_the_tensor_core_kernels(nm_lib):
     assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "1xTF32-rn" in info
     info = nm_lib.nm_kernel_info(C.byref(configs.build_case("t_int_rkf_node").plan().c)).decode()
     assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "3xTF32" in info
-    # narrow closed-loop policies (tiny fan-in / fan-out, hidden layers >= 16 wide) run in policy mode; wide fan-in
-    # (c4: 193 inputs) stays on the FFMA kernels
+    # narrow closed-loop policies (tiny fan-in / fan-out, hidden layers >= 16 wide) run in policy mode
     for name in ("c1", "c2", "t_vdp_rk4_tanh_clamp"):
         info = nm_lib.nm_kernel_info(C.byref(configs.build_case(name).plan().c)).decode()
         assert "fwd[tcgen05" in info and "bwd[tcgen05" in info and "1xTF32-rn" in info, (name, info)
-    for name in ("c4", "t_int_luther_vdp", "t_node_policy_euler"):
+    # c4 (193 inputs, 192 of them exogenous): first layer hoisted out of the loop, the rest runs in policy mode
+    info = nm_lib.nm_kernel_info(C.byref(configs.build_case("c4").plan().c)).decode()
+    assert "fwd[tcgen05" in info and "bwd[tcgen05" in info, info
+    for name in ("c4p", "t_int_luther_vdp", "t_node_policy_euler"):
         assert "tcgen05" not in nm_lib.nm_kernel_info(C.byref(configs.build_case(name).plan().c)).decode(), name
     # the 128-wide policy of c5 runs on the wide-policy family (nm_wide_kernels.cuh): 3-product fp16 MMAs, weights
     # resident in shared memory, raw policy output as the checkpoint
@@ -98,5 +100,8 @@ def test_neural_ode_classes_are_served_by_the_tensor_core_kernels(nm_lib):
     # policy mode keeps the raw policy output o_t of every step
     assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c2").plan().c), 1000, C.byref(nbytes)) == L.NM_OK
     assert nbytes.value == 1000 * 30 * 2 * 4
+    # hoisted c4: the first-layer pre-activation E[32] and the raw policy output o[1] of every step
     assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c4").plan().c), 1000, C.byref(nbytes)) == L.NM_OK
+    assert nbytes.value == 1000 * 96 * (32 + 1) * 4
+    assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c4p").plan().c), 1000, C.byref(nbytes)) == L.NM_OK
     assert nbytes.value == 0
