@@ -567,10 +567,22 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_kernel(const __grid_cons
   const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
   const bool fused = S::NTERMS > 0 && args.fused_terms;
   const int NT = t_hi - t_lo + 1;
-  const int64_t n = args.B * NT;
-  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t b = idx / NT;
-    const int tt = int(idx - b * NT), t = t_lo + tt;
+  const int NTW = t_hi == T ? NT : NT - 1;              // rows worth computing: the x row of t_hi only matters at the end of the horizon
+  const int64_t n = args.B * NTW;
+  for (int64_t idx0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx0 < n; idx0 += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = idx0 / NTW;
+    const int tt = int(idx0 - b * NTW), t = t_lo + tt;
+    const int64_t idx = b * NT + tt;
+    // the term code reads its atoms entry by entry (4-byte loads): pull the rows of this (trajectory, time) into L1 first
+    asm volatile("prefetch.global.L1 [%0];\n" ::"l"(args.x_traj + (b * (T + 1) + t) * NX));
+    if (t < T) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(args.u_traj + (b * T + t) * NU));
+#pragma unroll
+    for (int e = 0; e < NM_MAX_EXO; ++e) {
+      if (e < p.n_exo) {
+        const int te = t < p.exo[e].steps ? t : p.exo[e].steps - 1;
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(args.exo[e] + (b * p.exo[e].steps + te) * p.exo[e].width));
+      }
+    }
     float gx[NX], gu[NU];
 #pragma unroll
     for (int i = 0; i < NX; ++i) gx[i] = 0.f;
