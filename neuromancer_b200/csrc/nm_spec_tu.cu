@@ -235,6 +235,37 @@ template <class Sp> struct Wide<Sp, true> {
     }
     return 0;
   }
+  // loss-term gradients of the chunk [t_lo, t_hi) into G; returns the number of kernels launched
+  static int launch_termgrad(const NmPlan& p, const BwdArgs& a, float* G, int t_lo, int t_hi, int sms, cudaStream_t st) {
+    const int T = p.nsteps;
+    int launches = 1;
+    const int64_t n = a.B * int64_t(t_hi - t_lo + 1);
+    int64_t g = (n + 255) / 256;
+    if (g > int64_t(sms) * 16) g = int64_t(sms) * 16;
+    nm_wide_termgrad_kernel<Sp><<<int(g), 256, 0, st>>>(p, a, G, t_lo, t_hi);
+    // time-broadcast atoms anchored inside this chunk: one warp per trajectory sums the range
+    WideTbAnchors an{};
+    for (int k = 0; k < p.n_terms && an.n < 8; ++k) {
+      const NmTerm& tm = p.terms[k];
+      const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
+      const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
+      for (int i = 0; i < 4 && an.n < 8; ++i) {
+        if (!live[i] || !(at[i]->var == NM_VAR_X || at[i]->var == NM_VAR_U) || !(at[i]->t_len == 1 && tm.t_len > 1)) continue;
+        const int t0 = at[i]->t_start;
+        const bool in_chunk = at[i]->var == NM_VAR_X ? (t0 >= t_lo && (t0 < t_hi || (t0 == t_hi && t_hi == T))) : (t0 >= t_lo && t0 < t_hi);
+        bool seen = false;
+        for (int q = 0; q < an.n; ++q) seen = seen || (an.var[q] == at[i]->var && an.t[q] == t0);
+        if (in_chunk && !seen) { an.var[an.n] = at[i]->var; an.t[an.n] = t0; ++an.n; }
+      }
+    }
+    if (an.n > 0) {
+      int64_t gw = (a.B * 32 + 255) / 256;
+      if (gw > int64_t(sms) * 16) gw = int64_t(sms) * 16;
+      nm_wide_termgrad_tb_kernel<Sp><<<int(gw), 256, 0, st>>>(p, a, an, G, t_lo, t_hi);
+      ++launches;
+    }
+    return launches;
+  }
   // returns the number of kernels launched; `extra` is the wide region of the backward workspace, `nblocks` gradient blocks are zeroed
   static int launch_bwd(const NmPlan& p, const BwdArgs& a, const float* params, void* wprep, char* extra, int sms, int nblocks, cudaStream_t st) {
     const int T = p.nsteps;
@@ -260,43 +291,19 @@ template <class Sp> struct Wide<Sp, true> {
     wd::nm_wide_prep_kernel<Sp><<<32, 256, 0, st>>>(p, params, static_cast<uint8_t*>(wprep));
     int launches = 3;
     const int grid = grid_for(a.B, sms);
+    // (Measured and dropped: the term-gradient kernels of chunk i+1 on a side stream next to the weight-gradient GEMM of
+    // chunk i -- both want DRAM bandwidth, the step got 3 % slower.)
     for (int t_hi = T; t_hi > 0; t_hi -= CS) {
       const int t_lo = t_hi - CS > 0 ? t_hi - CS : 0;
       WideBwdArgs w{};
       w.b = a; w.staging = staging; w.stash = stash; w.lam_carry = carry; w.scale = scale; w.G = G; w.t_lo = t_lo; w.t_hi = t_hi;
-      {
-        const int64_t n = a.B * int64_t(t_hi - t_lo + 1);
-        int64_t g = (n + 255) / 256;
-        if (g > int64_t(sms) * 16) g = int64_t(sms) * 16;
-        nm_wide_termgrad_kernel<Sp><<<int(g), 256, 0, st>>>(p, a, G, t_lo, t_hi);
-        // time-broadcast atoms anchored inside this chunk: one warp per trajectory sums the range
-        WideTbAnchors an{};
-        for (int k = 0; k < p.n_terms && an.n < 8; ++k) {
-          const NmTerm& tm = p.terms[k];
-          const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
-          const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
-          for (int i = 0; i < 4 && an.n < 8; ++i) {
-            if (!live[i] || !(at[i]->var == NM_VAR_X || at[i]->var == NM_VAR_U) || !(at[i]->t_len == 1 && tm.t_len > 1)) continue;
-            const int t0 = at[i]->t_start;
-            const bool in_chunk = at[i]->var == NM_VAR_X ? (t0 >= t_lo && (t0 < t_hi || (t0 == t_hi && t_hi == T))) : (t0 >= t_lo && t0 < t_hi);
-            bool seen = false;
-            for (int q = 0; q < an.n; ++q) seen = seen || (an.var[q] == at[i]->var && an.t[q] == t0);
-            if (in_chunk && !seen) { an.var[an.n] = at[i]->var; an.t[an.n] = t0; ++an.n; }
-          }
-        }
-        if (an.n > 0) {
-          int64_t gw = (a.B * 32 + 255) / 256;
-          if (gw > int64_t(sms) * 16) gw = int64_t(sms) * 16;
-          nm_wide_termgrad_tb_kernel<Sp><<<int(gw), 256, 0, st>>>(p, a, an, G, t_lo, t_hi);
-          ++launches;
-        }
-      }
+      launches += launch_termgrad(p, a, G, t_lo, t_hi, sms, st);
       nm_wide_bwd_kernel<Sp><<<grid, C::BWD_THREADS, C::SMEM_BYTES, st>>>(p, w);
       const int64_t n_items = tiles * int64_t(t_hi - t_lo);
       const int wgrid = int(n_items < sms ? n_items : sms);
       nm_wide_wgrad_kernel<Sp><<<wgrid, C::WG_THREADS, C::WG_SMEM_BYTES, st>>>(p, staging, n_items, scale, a.grad_partials);
       nm_wide_scale_update_kernel<<<1, 32, 0, st>>>(scale);
-      launches += 4;
+      launches += 3;
     }
     return launches;
   }

@@ -5,9 +5,10 @@
 //   * three 128x128 hidden layers as tf32 hi/lo images are 418 KB -- they do not fit an SM.  As FP16 hi/lo images they
 //     are 192 KB and stay RESIDENT in shared memory; kind::f16 MMAs cost the same cycles as kind::tf32 ones but
 //     contract K = 16 per instruction, and fp16 has the same 11-bit significand as tf32: the 3-product split
-//     A_lo*W_hi + A_hi*W_lo + A_hi*W_hi keeps 22 bits (the remainders are stored scaled by 2^11 so they stay in the
-//     normal range, their two products are accumulated first and folded in by the first main product through
-//     scale-input-d = 2^-11).  Range: |activation|, |weight| < 65504 (beyond that the result is inf/NaN, never wrong).
+//     A_hi*W_lo + A_lo*W_hi + A_hi*W_hi keeps 22 bits (the weight remainders are stored scaled by 2^11 so they stay in
+//     the normal range: their product is accumulated first and folded in through scale-input-d = 2^-11; the activation
+//     remainders are stored as they are -- see split2).  Range: |activation|, |weight| < 65504 (beyond that the result
+//     is inf/NaN, never wrong).
 //   * fp16 operands may be K-major or MN-major: ONE weight image serves the forward contraction (K-major) and the
 //     data-gradient contraction (the same bytes read MN-major) -- no transposed copies.
 //   * every layer of the policy runs on the tensor pipe (layer 0: K padded to 16, output layer: N padded to 16); the
@@ -74,8 +75,17 @@ __device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]
 // L2 residency: the derivative stash is rewritten and re-read every step (evict_last keeps it out of DRAM: 256-bit
 // accesses carry the priority as a qualifier -- a policy operand would cost two R2UR per access); the staging tiles are
 // written once and read by a later kernel (streaming stores: they must not push the stash out)
+#ifndef NM_TUNE_WSTPOL
+#define NM_TUNE_WSTPOL 0
+#endif
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#if NM_TUNE_WSTPOL == 0
   asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#elif NM_TUNE_WSTPOL == 1
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#else
+  asm volatile("st.global.cg.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#endif
 }
 struct alignas(32) float8 { float v[8]; };
 __device__ __forceinline__ void st_stash8(float8* p, const float* v) {
@@ -83,16 +93,36 @@ __device__ __forceinline__ void st_stash8(float8* p, const float* v) {
                "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 __device__ __forceinline__ void ld_stash8(const float8* p, float* v) {
+#ifdef NM_TUNE_WNOSTASH
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.5f;
+  return;
+#endif
   asm volatile("ld.global.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
                "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
-// fp16 split of two values: hi = rn16(a), lo = rn16((a - hi) * 2^11), packed (first value in the low half)
+// Packed fp32 pairs: Blackwell's FFMA2 / FMUL2 / FADD2 work on two fp32 lanes per instruction -- one issue slot instead of
+// two (the FMA pipe is busy just as long).  The epilogues below are issue-bound, so everything element-wise runs in pairs.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void up2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) { f2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// fp16 split of two values: hi = rn16(a), lo = rn16(a - hi), packed (first value in the low half).  The remainder is
+// NOT scaled: it is at most 2^-11 |a|, and where that falls below fp16's normal range (|a| < 2^-3) the subnormal
+// spacing 2^-24 bounds its error by 2^-25 absolute -- never worse than the 2^-22 relative of a scaled remainder.  (The
+// WEIGHT remainders stay scaled by 2^11: weights are small and constant, their images are prepared once.)
 __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a0, a1);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a0 - hf.x) * 2048.f, (a1 - hf.y) * 2048.f);
+  float d0, d1;
+  up2(sub2(pk2(a0, a1), pk2(hf.x, hf.y)), d0, d1);
+  const __half2 l = __floats2half2_rn(d0, d1);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -137,6 +167,122 @@ __device__ __forceinline__ void act_acc_pair(float acc, float bs, float prm, flo
     const float cdf = fmaf(copysignf(0.70710678118654752440f, x), s, 0.5f);
     d = fmaf(x * 0.56418958354775628695f, g, cdf);
   } else tc::act_ad<ACT>(acc + bs, prm, a, d);
+}
+
+// The same two epilogues on a PAIR of accumulator entries (bias pair pre-scaled like `bs`)
+__device__ __forceinline__ f2_t gelu_core2(f2_t x, float& ax0, float& ax1) {        // s = 1/sqrt2 - e, per lane
+  float x0, x1;
+  up2(x, x0, x1);
+  ax0 = fabsf(x0); ax1 = fabsf(x1);
+  const float t0 = fminf(ax0, 4.2f), t1 = fminf(ax1, 4.2f);
+  const f2_t t = pk2(t0, t1);
+  f2_t q = bc2(-1.476634237e-05f);
+  q = fma2(q, t, bc2(1.797868946e-04f));
+  q = fma2(q, t, bc2(-9.401043775e-04f));
+  q = fma2(q, t, bc2(2.438597105e-03f));
+  q = fma2(q, t, bc2(-2.483013238e-04f));
+  q = fma2(q, t, bc2(-2.763307886e-02f));
+  q = fma2(q, t, bc2(1.482808647e-01f));
+  q = fma2(q, t, bc2(9.184465932e-01f));
+  q = fma2(q, t, bc2(1.627907100e+00f));
+  float g0, g1;
+  up2(fma2(q, pk2(-t0, -t1), bc2(-0.5f)), g0, g1);
+  return sub2(bc2(0.70710678118654752440f), pk2(ex2_approx(g0), ex2_approx(g1)));
+}
+template <int ACT>
+__device__ __forceinline__ void act_acc2(float& v0, float& v1, float bs0, float bs1, float prm) {
+  if constexpr (ACT == NM_ACT_GELU) {
+    const f2_t c = bc2(0.70710678118654752440f);
+    const f2_t x = fma2(pk2(v0, v1), c, pk2(bs0, bs1));
+    float ax0, ax1;
+    const f2_t s = gelu_core2(x, ax0, ax1);
+    up2(fma2(pk2(ax0, ax1), s, mul2(x, c)), v0, v1);
+  } else { v0 = act_fwd<ACT>(v0 + bs0, prm); v1 = act_fwd<ACT>(v1 + bs1, prm); }
+}
+template <int ACT>
+__device__ __forceinline__ void act_acc_pair2(float& v0, float& v1, float bs0, float bs1, float prm, float& d0, float& d1) {
+  if constexpr (ACT == NM_ACT_GELU) {
+    const f2_t c = bc2(0.70710678118654752440f);
+    const f2_t x = fma2(pk2(v0, v1), c, pk2(bs0, bs1));
+    float ax0, ax1, x0, x1, g0, g1;
+    const f2_t s = gelu_core2(x, ax0, ax1);
+    up2(fma2(pk2(ax0, ax1), s, mul2(x, c)), v0, v1);
+    up2(x, x0, x1);
+    up2(mul2(x, mul2(x, bc2(-1.44269504088896340736f))), g0, g1);
+    const f2_t g = pk2(ex2_approx(g0), ex2_approx(g1));                    // exp(-x^2)
+    const f2_t cdf = fma2(pk2(copysignf(0.70710678118654752440f, x0), copysignf(0.70710678118654752440f, x1)), s, bc2(0.5f));
+    up2(fma2(mul2(x, bc2(0.56418958354775628695f)), g, cdf), d0, d1);
+  } else { tc::act_ad<ACT>(v0 + bs0, prm, v0, d0); tc::act_ad<ACT>(v1 + bs1, prm, v1, d1); }
+}
+
+// The epilogue of 2 NP consecutive accumulator entries v[O .. O + 2 NP), written "vertically": every step of the evaluation
+// runs across all NP pairs before the next one starts, so NP independent FFMA2 chains are in flight (written pair after
+// pair, the compiler interleaved two chains and every Horner step waited out the FFMA2 latency).  DERIV: also act'(z) -> d.
+template <int ACT, int O, int NP, bool DERIV>
+__device__ __forceinline__ void act_group(float (&v)[32], float (&d)[32], const float* __restrict__ bias, float prm) {
+  if constexpr (ACT == NM_ACT_GELU) {
+    const f2_t c = bc2(0.70710678118654752440f);
+    f2_t x[NP], t[NP], q[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p += 2) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias + O + 2 * p);
+      x[p] = fma2(pk2(v[O + 2 * p], v[O + 2 * p + 1]), c, pk2(bv.x, bv.y));
+      x[p + 1] = fma2(pk2(v[O + 2 * p + 2], v[O + 2 * p + 3]), c, pk2(bv.z, bv.w));
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      float x0, x1;
+      up2(x[p], x0, x1);
+      t[p] = pk2(fminf(fabsf(x0), 4.2f), fminf(fabsf(x1), 4.2f));
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(bc2(-1.476634237e-05f), t[p], bc2(1.797868946e-04f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(-9.401043775e-04f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(2.438597105e-03f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(-2.483013238e-04f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(-2.763307886e-02f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(1.482808647e-01f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(9.184465932e-01f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) q[p] = fma2(q[p], t[p], bc2(1.627907100e+00f));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {                      // s = 1/sqrt2 - 2^(-q t - 1/2)
+      float t0, t1, g0, g1;
+      up2(t[p], t0, t1);
+      up2(fma2(q[p], pk2(-t0, -t1), bc2(-0.5f)), g0, g1);
+      q[p] = sub2(c, pk2(ex2_approx(g0), ex2_approx(g1)));
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      float x0, x1;
+      up2(x[p], x0, x1);
+      up2(fma2(pk2(fabsf(x0), fabsf(x1)), q[p], mul2(x[p], c)), v[O + 2 * p], v[O + 2 * p + 1]);
+    }
+    if constexpr (DERIV) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        float x0, x1, g0, g1;
+        up2(x[p], x0, x1);
+        up2(mul2(x[p], mul2(x[p], bc2(-1.44269504088896340736f))), g0, g1);
+        const f2_t g = pk2(ex2_approx(g0), ex2_approx(g1));                  // exp(-x^2)
+        const f2_t cdf = fma2(pk2(copysignf(0.70710678118654752440f, x0), copysignf(0.70710678118654752440f, x1)), q[p], bc2(0.5f));
+        up2(fma2(mul2(x[p], bc2(0.56418958354775628695f)), g, cdf), d[O + 2 * p], d[O + 2 * p + 1]);
+      }
+    }
+  } else {
+    const float is = 1.f / bias_scale<ACT>();
+#pragma unroll
+    for (int i = O; i < O + 2 * NP; ++i) {
+      if constexpr (DERIV) tc::act_ad<ACT>(v[i] + bias[i] * is, prm, v[i], d[i]);
+      else v[i] = act_fwd<ACT>(v[i] + bias[i] * is, prm);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ static layout
@@ -260,14 +406,18 @@ __device__ __forceinline__ void issue_kmajor(uint32_t d, uint32_t a_hi, uint32_t
   constexpr uint32_t LBO = N * 16, SBO = 128, KSTEP = 2 * N * 16;
   const uint64_t wh = tc::smem_desc(img, LBO, SBO);
   const uint64_t wl = tc::desc_add(wh, N * KP * 2);
+  // smallest products first (the TMEM accumulator truncates): A_hi W_lo at scale 2^11, folded in by the first A_lo W_hi
   static_for<0, KP / 16>([&](auto kc) {
     constexpr int ks = decltype(kc)::value;
-    mma_ts<(ks > 0 ? 1 : 0)>(d, a_lo + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
-    mma_ts<1>(d, a_hi + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+    mma_ts<(ks > 0 ? 1 : 0)>(d, a_hi + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
   });
   static_for<0, KP / 16>([&](auto kc) {
     constexpr int ks = decltype(kc)::value;
-    mma_ts<(ks > 0 ? 1 : 2)>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+    mma_ts<(ks > 0 ? 1 : 2)>(d, a_lo + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+  });
+  static_for<0, KP / 16>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    mma_ts<1>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
   });
 }
 // D[128][NP] = A[128][ROWS] * W[:, 0:NP]: the same image [KPI/8][ROWS][8] read MN-major (contraction over its rows)
@@ -279,12 +429,15 @@ __device__ __forceinline__ void issue_mnmajor(uint32_t d, uint32_t a_hi, uint32_
   const uint64_t wl = tc::desc_add(wh, ROWS * KPI * 2);
   static_for<0, ROWS / 16>([&](auto kc) {
     constexpr int ks = decltype(kc)::value;
-    mma_ts<(ks > 0 ? 1 : 0)>(d, a_lo + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
-    mma_ts<1>(d, a_hi + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
+    mma_ts<(ks > 0 ? 1 : 0)>(d, a_hi + ks * 8, tc::desc_add(wl, ks * KSTEP), idesc);
   });
   static_for<0, ROWS / 16>([&](auto kc) {
     constexpr int ks = decltype(kc)::value;
-    mma_ts<(ks > 0 ? 1 : 2)>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+    mma_ts<(ks > 0 ? 1 : 2)>(d, a_lo + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
+  });
+  static_for<0, ROWS / 16>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    mma_ts<1>(d, a_hi + ks * 8, tc::desc_add(wh, ks * KSTEP), idesc);
   });
 }
 
@@ -411,6 +564,15 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::FWD_THREADS, 1) nm_wide_fwd_ke
         __syncwarp();
       }
     };
+    WP_DECL(w_arr); WP_DECL(w_wait); WP_DECL(w_epi); WP_DECL(w_out); WP_DECL(w_in);
+#ifdef NM_TUNE_WPROF
+    const long long w_begin = clock64();
+    long long tl[24];
+    int tli = 0;
+#define WP_MARK() do { if (r == 0 && (t == 100 || t == 101) && tli < 24) tl[tli++] = clock64() - w_begin; } while (0)
+#else
+#define WP_MARK()
+#endif
     for (int r = 0;; ++r) {
       const int tile = (r * int(gridDim.x) + int(blockIdx.x)) * 2 + slot;
       if (tile >= args.num_tiles) break;
@@ -424,67 +586,90 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::FWD_THREADS, 1) nm_wide_fwd_ke
       float in_pre[K0];
 #pragma unroll
       for (int q = 0; q < K0; ++q) in_pre[q] = 0.f;
-      wd::policy_exo<S, K0>(p, args.exo, b, 0, in_pre);
+      if (half == 0) wd::policy_exo<S, K0>(p, args.exo, b, 0, in_pre);
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
         float in[K0], yv[1] = {0.f};
 #pragma unroll
         for (int q = 0; q < K0; ++q) in[q] = in_pre[q];
-        tc_policy_state<S, K0>(x, yv, in);
-        if (half == 0) { uint32_t hi0[C::K0P / 2]; wd::put_input<C>(t_hi, t_lo, in, hi0); (void)hi0; }
-        arrive_ops(0);
-        if (t + 1 < T) wd::policy_exo<S, K0>(p, args.exo, b, t + 1, in_pre);     // exogenous inputs one step ahead
+        { WP_T0();
+        if (half == 0) {                          // the trajectory's scalars (state, policy input, dynamics) live on its first thread only
+          uint32_t hi0[C::K0P / 2];
+          tc_policy_state<S, K0>(x, yv, in);
+          wd::put_input<C>(t_hi, t_lo, in, hi0);
+          (void)hi0;
+        }
+        WP_ADD(w_in); }
+        { WP_T0(); arrive_ops(0); WP_ADD(w_arr); }
+        if (half == 0 && t + 1 < T) wd::policy_exo<S, K0>(p, args.exo, b, t + 1, in_pre);     // exogenous inputs one step ahead
         // hidden activations a_1 .. a_{NL-1}
 #pragma unroll 1
         for (int l = 0; l < NL - 1; ++l) {
           const float* __restrict__ bias = reinterpret_cast<const float*>(sm + C::bias_off(0)) + l * H;
-          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait); }
           tc::fence_after();
+          WP_MARK();
+          WP_T0();
 #pragma unroll 1
           for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
             float v[32];
             uint32_t hi[16], lo[16];
             tc::tmem_ld<32>(t_d + c0, v);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
-              v[i] = wd::act_acc<M::ACT>(v[i], bv.x, act_prm); v[i + 1] = wd::act_acc<M::ACT>(v[i + 1], bv.y, act_prm);
-              v[i + 2] = wd::act_acc<M::ACT>(v[i + 2], bv.z, act_prm); v[i + 3] = wd::act_acc<M::ACT>(v[i + 3], bv.w, act_prm);
-            }
+            wd::act_group<M::ACT, 0, 8, false>(v, v, bias + c0, act_prm);
+            wd::act_group<M::ACT, 16, 8, false>(v, v, bias + c0, act_prm);
 #pragma unroll
             for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
             wd::tmem_st16u(t_hi + c0 / 2, hi);
             wd::tmem_st16u(t_lo + c0 / 2, lo);
           }
-          arrive_ops(l + 1);
+          WP_ADD(w_epi);
+          WP_MARK();
+          { WP_T0(); arrive_ops(l + 1); WP_ADD(w_arr); }
         }
         // output layer
-        mbar_wait(bar_done, ph_done); ph_done ^= 1;
+        { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait); }
         tc::fence_after();
-        float o16[16], u[NU];
-        tc::tmem_ld<16>(t_d, o16);
-        const float* __restrict__ bo = reinterpret_cast<const float*>(sm + C::biaso_off());
+        WP_MARK();
+        WP_T0();
+        if (half == 0) {
+          float o16[16], u[NU];
+          tc::tmem_ld<16>(t_d, o16);
+          const float* __restrict__ bo = reinterpret_cast<const float*>(sm + C::biaso_off());
 #pragma unroll
-        for (int j = 0; j < NU; ++j) {
-          o16[j] += bo[j];
-          u[j] = bounds_fwd<M::BOUNDS>(o16[j], p.policy.bmin[j], p.policy.bmax[j]);
-        }
-        if (valid && half == 0) {
-          st_vec<NU>(args.u_traj + (b * T + t) * NU, u);
-          if (args.chk != nullptr) {
-            float oc[NU];
-#pragma unroll
-            for (int j = 0; j < NU; ++j) oc[j] = o16[j];
-            st_vec<NU>(args.chk + (b * T + t) * NU, oc);
+          for (int j = 0; j < NU; ++j) {
+            o16[j] += bo[j];
+            u[j] = bounds_fwd<M::BOUNDS>(o16[j], p.policy.bmin[j], p.policy.bmax[j]);
           }
-        }
-        float xn[NX], dv_[1] = {0.f};
-        Dyn<S>::step(p, x, u, dv_, xn);
+          if (valid) {
+            st_vec<NU>(args.u_traj + (b * T + t) * NU, u);
+            if (args.chk != nullptr) {
+              float oc[NU];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = xn[i];
-        if (valid && half == 0) st_vec<NX>(args.x_traj + (b * (T + 1) + t + 1) * NX, x);
+              for (int j = 0; j < NU; ++j) oc[j] = o16[j];
+              st_vec<NU>(args.chk + (b * T + t) * NU, oc);
+            }
+          }
+          float xn[NX], dv_[1] = {0.f};
+          Dyn<S>::step(p, x, u, dv_, xn);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = xn[i];
+          if (valid) st_vec<NX>(args.x_traj + (b * (T + 1) + t + 1) * NX, x);
+        }
+        WP_ADD(w_out);
+        WP_MARK();
       }
     }
+#ifdef NM_TUNE_WPROF
+    if (blockIdx.x == 0 && (tid == 0 || tid == 32 || tid == 128 || tid == 256))
+      printf("[wprof fwd tid %d] total %lld | input %lld  arrive+issue %lld  wait_mma %lld  epilogue %lld  out+dyn %lld (steps %d)\n", tid,
+             clock64() - w_begin, w_in, w_arr, w_wait, w_epi, w_out, T);
+    if (blockIdx.x == 0 && (tid == 32 || tid == 288)) {
+      // per step: [epilogue start, epilogue end] x (NL - 1), output-layer result ready, step end
+      printf("[wprof fwd timeline tid %d]", tid);
+      for (int i = 0; i < tli; ++i) printf(" %lld", tl[i] - tl[0]);
+      printf("\n");
+    }
+#endif
   }
   tc::fence_before();
   __syncthreads();
@@ -745,9 +930,11 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
 #endif
     // staging store of 32 consecutive features (16 packed words) of operand tile `toff`
     auto stage32 = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[16]) {
+#ifndef NM_TUNE_WNOSTAGE                               // (timing experiment: the adjoint without its staging stores -- results are wrong)
       uint8_t* q = item + toff + (c0 / 8) * C::GRP + m_ * 16;
 #pragma unroll
       for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+#endif
     };
 
     // Everything a step reads from HBM is requested one step ahead -- across tile boundaries too (with short chunks a
@@ -783,7 +970,11 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
       for (int i = 0; i < NX; ++i) lam[i] = valid ? lam_pre[i] : 0.f;
 #pragma unroll 1
       for (int t = t_hi - 1; t >= t_lo; --t) {
+#ifdef NM_TUNE_WSTWRAP                                 // (timing experiment: staging wrapped into an L2-sized window -- results are wrong)
+        uint8_t* item = wargs.staging + ((size_t(tile) * CSn + size_t(t - t_lo)) % NM_TUNE_WSTWRAP) * C::ITEM_BYTES;
+#else
         uint8_t* item = wargs.staging + (size_t(tile) * CSn + size_t(t - t_lo)) * C::ITEM_BYTES;
+#endif
         float x[NX], o_cur[NU], in[K0], g_cur[RW], yv[1] = {0.f};
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = x_pre[i];
@@ -857,20 +1048,18 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
             float v[32], d[32];
             uint32_t hi[16], lo[16];
             tc::tmem_ld<32>(t_d + c0, v);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
-              wd::act_acc_pair<M::ACT>(v[i], bv.x, act_prm, v[i], d[i]); wd::act_acc_pair<M::ACT>(v[i + 1], bv.y, act_prm, v[i + 1], d[i + 1]);
-              wd::act_acc_pair<M::ACT>(v[i + 2], bv.z, act_prm, v[i + 2], d[i + 2]); wd::act_acc_pair<M::ACT>(v[i + 3], bv.w, act_prm, v[i + 3], d[i + 3]);
-            }
+            wd::act_group<M::ACT, 0, 8, true>(v, d, bias + c0, act_prm);
+            wd::act_group<M::ACT, 16, 8, true>(v, d, bias + c0, act_prm);
 #pragma unroll
             for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
             stage32(item, C::a_off(1) + l * (H / 8) * C::GRP, c0, hi);                    // a_{l+1}
             if (!last) {
               wd::tmem_st16u(t_hi_ + c0 / 2, hi);
               wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+#ifndef NM_TUNE_WNOSTASH                               // (timing experiment: no derivative stash traffic -- results are wrong)
 #pragma unroll
               for (int i = 0; i < 32; i += 8) wd::st_stash8(stash + (l * (H / 8) + (c0 + i) / 8) * 128, d + i);
+#endif
             } else {
               // output layer backward on the CUDA cores: dA[k] = sum_j cot[j] W_out[j][k];  dZ_{NL-2} = dA * act'
 #pragma unroll
