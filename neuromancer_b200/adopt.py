@@ -59,8 +59,16 @@ def _inner_linear(layer):
     raise PlanError(f"linear map {_cls(layer)} is not dense (torch.nn.Linear / slim.Linear): not fused")
 
 
+def _is_structured(layer) -> bool:
+    """a slim map that is not a plain dense layer but can state its matrix (reference slim/linear.py:85-91)"""
+    if isinstance(layer, nn.Linear) or isinstance(getattr(layer, "linear", None), nn.Linear):
+        return False
+    return callable(getattr(layer, "effective_W", None)) and hasattr(layer, "in_features") and hasattr(layer, "out_features")
+
+
 def _adopt_mlp(ref):
-    lins = [_inner_linear(l) for l in ref.linear]
+    structured = [_is_structured(l) for l in ref.linear]
+    lins = [l if st else _inner_linear(l) for l, st in zip(ref.linear, structured)]
     sizes = [lins[0].in_features] + [l.out_features for l in lins]
     acts = list(ref.nonlin)
     hidden = {type(a) for a in acts[:-1]}
@@ -75,8 +83,14 @@ def _adopt_mlp(ref):
         mlp = _blocks.MLP(**kw)
     else:
         raise PlanError(f"block {_cls(ref)} is not fused (MLP / MLP_bounds are)")
-    # same Parameter objects: the adopted model trains the reference model
-    for (w, b), lin in zip(mlp.dense_layers(), lins):
+    # same Parameter objects: the adopted model trains the reference model.  A structured slim map is taken over as the
+    # module it is (the lowering materialises its effective_W() on every call)
+    for i, st in enumerate(structured):
+        if st:
+            mlp.linear[i] = lins[i]
+    for (w, b), lin, st in zip(mlp.dense_layers(), lins, structured):
+        if st:
+            continue
         _share(mlp, w, lin.weight)
         if b is not None:
             _share(mlp, b, lin.bias)

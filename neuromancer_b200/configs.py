@@ -272,13 +272,15 @@ def c5(seed=0, nsteps=200) -> Case:
 
 
 # ------------------------------------------------------------------------------------------- test shapes
-def t_vdp_rk4_tanh_clamp(seed=0, nsteps=12) -> Case:
+def t_vdp_rk4_tanh_clamp(seed=0, nsteps=12, linear_map=None, name="t_vdp_rk4_tanh_clamp") -> Case:
+    """``linear_map``: a structured slim map for every policy layer (t_slim_*: SURVEY 8 f3) -- same shape class"""
     torch.manual_seed(seed)
     plant = ode.VanDerPolControl()
     plant.mu = nn.Parameter(torch.tensor(1.0), requires_grad=False)
     model = Node(integrators.RK4(plant, h=0.1), ["x", "u"], ["x"], name="model")
+    extra = {} if linear_map is None else {"linear_map": linear_map}
     net = blocks.MLP_bounds(insize=4, outsize=1, hsizes=[16, 16], nonlin=nn.Tanh, min=-1., max=1.,
-                            method="relu_clamp")
+                            method="relu_clamp", **extra)
     system = System([Node(net, ["x", "r"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
     x, r, u = variable("x"), variable("r"), variable("u")
     obj = 3. * ((x == r) ^ 2)
@@ -293,7 +295,17 @@ def t_vdp_rk4_tanh_clamp(seed=0, nsteps=12) -> Case:
         g = _gen(device, 6000 + s)
         return {"x": torch.randn(Bn, 1, 2, generator=g).to(device),
                 "r": (0.5 * torch.randn(Bn, nsteps + 1, 2, generator=g)).to(device), "name": "train"}
-    return Case("t_vdp_rk4_tanh_clamp", problem, system, nsteps, 256, make_batch, 0, 0)
+    return Case(name, problem, system, nsteps, 256, make_batch, 0, 0)
+
+
+def t_slim_pf(seed=0, nsteps=12) -> Case:
+    from . import slim
+    return t_vdp_rk4_tanh_clamp(seed=seed, nsteps=nsteps, linear_map=slim.PerronFrobeniusLinear, name="t_slim_pf")
+
+
+def t_slim_svd(seed=0, nsteps=12) -> Case:
+    from . import slim
+    return t_vdp_rk4_tanh_clamp(seed=seed, nsteps=nsteps, linear_map=slim.SVDLinear, name="t_slim_svd")
 
 
 def t_vdp_euler_elu(seed=0, nsteps=9) -> Case:
@@ -559,6 +571,7 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_auto_brusselator": t_auto_brusselator, "t_auto_lotka": t_auto_lotka, "t_auto_lorenz": t_auto_lorenz,
     "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
     "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
+    "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd,
 }
 # shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
 EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index, "c4p": c4p}
@@ -575,5 +588,12 @@ def make_case(name: str, device, seed=0, **kw) -> Case:
     case = build_case(name, seed=seed, **kw)
     case.problem.to(device)
     plan = case.plan()
-    case.plan_params = list(plan.params)
+    # a structured slim map stands in the plan as its materialised matrix: the tests address its own parameters
+    # (registration order, the bias -- a plan entry of its own -- left out)
+    case.plan_params = []
+    for q in plan.params:
+        if hasattr(q, "materialise"):
+            case.plan_params += [t for n, t in q.module.named_parameters() if n != "bias"]
+        else:
+            case.plan_params.append(q)
     return case

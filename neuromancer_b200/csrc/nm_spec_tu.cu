@@ -281,13 +281,15 @@ template <class Sp> struct Wide<Sp, true> {
     float* stash = reinterpret_cast<float*>(extra + 256 + carry_bytes(a.B));
     float* G = reinterpret_cast<float*>(extra + 256 + carry_bytes(a.B) + stash_bytes(sms));
     uint8_t* staging = reinterpret_cast<uint8_t*>(extra + 256 + carry_bytes(a.B) + stash_bytes(sms) + g_bytes(a.B, T));
-    // initial cotangent scale: the largest term coefficient w / (B_total * t_len * d_len) goes to ~2^4
-    double cmax = 0.0;
-    for (int k = 0; k < p.n_terms; ++k) {
-      const double c = std::fabs(double(p.terms[k].weight)) / (double(a.b_total) * double(p.terms[k].t_len) * double(p.terms[k].d_len));
-      if (c > cmax) cmax = c;
-    }
-    int e0 = cmax > 0.0 ? 4 - int(std::floor(std::log2(cmax))) : int(std::floor(std::log2(double(a.b_total)))) + 10;
+    // Initial cotangent scale.  A term of weight w puts w / (B_total * t_len * d_len) on each of its t_len time entries --
+    // all on ONE entry when its atom is time-broadcast (terminal constraints), otherwise accumulating in the co-state
+    // along the sweep -- so sum_k |w_k| / (B_total * d_len_k) estimates the largest co-state of the first chunk; it goes to
+    // ~2^9: 2^7 of headroom below fp16's 65504 for quadratic penalties and growing dynamics, 23 binades of normal range
+    // below it (the per-chunk update then steers by the largest cotangent actually seen).  The former rule scaled the
+    // largest single coefficient to 2^4 and overflowed on a whole-horizon chunk with terminal terms (B = 300, 200 steps).
+    double mass = 0.0;
+    for (int k = 0; k < p.n_terms; ++k) mass += std::fabs(double(p.terms[k].weight)) / (double(a.b_total) * double(p.terms[k].d_len));
+    int e0 = mass > 0.0 ? 9 - int(std::floor(std::log2(mass))) : int(std::floor(std::log2(double(a.b_total)))) + 10;
     if (const char* s = getenv("NM_WIDE_GS0_LOG2")) e0 = atoi(s);
     if (e0 > 100) e0 = 100;
     if (e0 < -100) e0 = -100;

@@ -101,6 +101,11 @@ __device__ __forceinline__ void ld_stash8(const float8* p, float* v) {
   asm volatile("ld.global.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
                "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
 }
+// fire-and-forget add of two adjacent floats (8-byte aligned): the flush of the weight-gradient accumulators does not wait
+// for the old values (a read-modify-write exposed an L2 round trip per group of eight)
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
 // Packed fp32 pairs: Blackwell's FFMA2 / FMUL2 / FADD2 work on two fp32 lanes per instruction -- one issue slot instead of
@@ -1339,12 +1344,24 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::WG_THREADS, 1) nm_wide_wgrad_k
           constexpr int l = decltype(lc)::value;
           constexpr int Kl = C::kin(l);
           float* dst = gblock + C::p_off(l) + lane_n * Kl;
+          // this CTA's gradient block is private and every address has one owner thread: the order of the adds -- and the
+          // result -- is fixed whether they are read-modify-writes or reductions at the L2
+#ifdef NM_TUNE_WNORED
+          const bool pairs = false;
+#else
+          const bool pairs = Kl % 2 == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+#endif
 #pragma unroll 1
           for (int c0 = 0; c0 < Kl; c0 += 8) {
             float v[8];
             tc::tmem_ld<8>(tmem + lane_base + C::wg_col(l) + c0, v);
+            if (pairs) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (c0 + i < Kl) dst[c0 + i] += v[i] * inv_gs;
+              for (int i = 0; i < 8; i += 2) if (c0 + i < Kl) wd::red_add2(dst + c0 + i, v[i] * inv_gs, v[i + 1] * inv_gs);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) if (c0 + i < Kl) dst[c0 + i] += v[i] * inv_gs;
+            }
           }
           if constexpr (C::BIAS) {
             float v[8];

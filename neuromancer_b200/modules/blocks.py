@@ -53,9 +53,11 @@ def _dense_weight_bias(layer):
     inner = getattr(layer, "linear", None)
     if isinstance(inner, nn.Linear):
         return inner.weight, inner.bias
+    if callable(getattr(layer, "effective_W", None)) and hasattr(layer, "in_features") and hasattr(layer, "out_features"):
+        # structured slim map (ours or the reference's): the fused path sees the materialised effective_W()
+        return slim.DerivedWeight(layer), getattr(layer, "bias", None)
     raise NotImplementedError(
-        f"linear map {type(layer).__name__} is not a dense nn.Linear; structured slim maps are "
-        "outside the fused hot path")
+        f"linear map {type(layer).__name__} is neither a dense nn.Linear nor a slim map with effective_W()")
 
 
 class MLP(Block):

@@ -20,6 +20,7 @@ import torch
 
 from . import _lib as L
 from .plan import PlanError, RolloutPlan
+from .slim.linear import DerivedWeight
 
 _WORLD = {"size": 1}   # set by neuromancer_b200.distributed when gradients are all-reduced
 
@@ -59,6 +60,8 @@ class ParamArena:
 
     def adopt(self, params):
         for p, (off, n) in zip(params, self.slices):
+            if isinstance(p, DerivedWeight):
+                continue
             view = self.flat[off:off + n].view(p.shape)
             if p.data.data_ptr() != view.data_ptr() or p.data.device != self.flat.device:
                 view.copy_(p.data.to(self.flat.device, torch.float32))
@@ -66,7 +69,22 @@ class ParamArena:
 
     def in_sync(self, params) -> bool:
         base = self.flat.data_ptr()
-        return all(p.data.data_ptr() == base + 4 * off for p, (off, _) in zip(params, self.slices))
+        return all(isinstance(p, DerivedWeight) or p.data.data_ptr() == base + 4 * off for p, (off, _) in zip(params, self.slices))
+
+    def materialise(self, params) -> List[torch.Tensor]:
+        """The tensors of this call, in plan order: the module Parameters themselves (views of the arena) and, for every
+        structured slim map, its ``effective_W()^T`` evaluated now -- copied into its arena slot for the kernels, returned
+        with its autograd history so that the kernels' gradient w.r.t. it flows on to the map's own parameters."""
+        out = []
+        for p, (off, n) in zip(params, self.slices):
+            if isinstance(p, DerivedWeight):
+                w = p.materialise().to(self.flat.device, torch.float32)
+                with torch.no_grad():
+                    self.flat[off:off + n].copy_(w.reshape(-1))
+                out.append(w)
+            else:
+                out.append(p)
+        return out
 
 
 class _Workspace:
@@ -275,8 +293,9 @@ class RolloutRunner:
         exo = _checked_exo(plan, data, x_in)
         if not self.arena.in_sync(plan.params):
             self.arena.adopt(plan.params)
-        keep = torch.is_grad_enabled() and (x0.requires_grad or any(q.requires_grad for q in plan.params))
-        x, u, y, scalars, _chk = torch.ops.nmfused.rollout_fwd(self.handle, x0, exo, list(plan.params), keep)
+        call_params = self.arena.materialise(plan.params)
+        keep = torch.is_grad_enabled() and (x0.requires_grad or any(q.requires_grad for q in call_params))
+        x, u, y, scalars, _chk = torch.ops.nmfused.rollout_fwd(self.handle, x0, exo, call_params, keep)
         return x, (u if lay.action_key is not None else None), (y if lay.output_key is not None else None), scalars
 
 

@@ -114,6 +114,31 @@ def t_vdp_rk4_tanh_clamp(params, nsteps=12) -> dict:
     return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
 
 
+# structured slim maps: the tanh-clamp problem whose policy layers are slim maps; `params` holds, per layer,
+# the map's own parameters (registration order) and then its bias [1, out]
+def _slim_case(params, nsteps, per_layer, eff_w):
+    n_layers = len(params) // (per_layer + 1)
+
+    def policy(z):                                          # LinearBase.forward: x @ effective_W() + bias (slim/linear.py:94-101)
+        for l in range(n_layers):
+            chunk = params[l * (per_layer + 1):(l + 1) * (per_layer + 1)]
+            z = torch.matmul(z, eff_w(*chunk[:per_layer])) + chunk[per_layer]
+            if l < n_layers - 1:
+                z = torch.tanh(z)
+        return z
+    spec = t_vdp_rk4_tanh_clamp(params, nsteps=nsteps)
+    spec["nodes"][0] = dict(fn=lambda x, r: O.bounds_clamp(policy(torch.cat([x, r], dim=-1)), -1., 1.), inputs=["x", "r"], outputs=["u"])
+    return spec
+
+
+def t_slim_pf(params, nsteps=12) -> dict:
+    return _slim_case(params, nsteps, 2, lambda w, s: O.slim_perron_frobenius(w, s, 0.8, 1.0))
+
+
+def t_slim_svd(params, nsteps=12) -> dict:
+    return _slim_case(params, nsteps, 3, lambda u, v, s: O.slim_soft_svd(u, v, s, 0.1, 1.0))
+
+
 def t_vdp_euler_elu(params, nsteps=9) -> dict:
     mu = _t(0.7, params[0])
     rhs = lambda x, u: O.rhs_vdp(x, u, mu)
@@ -271,7 +296,8 @@ CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_int_luther_vdp": t_int_luther_vdp, "t_int_rkf_node": t_int_rkf_node, "t_open_duffing": t_open_duffing,
          "t_auto_brusselator": t_auto_brusselator, "t_auto_lotka": t_auto_lotka, "t_auto_lorenz": t_auto_lorenz,
          "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
-         "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect}
+         "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
+         "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd}
 
 
 def build(name: str, params: List[torch.Tensor], **kw) -> dict:

@@ -58,6 +58,19 @@ def mlp_forward(params: Sequence[torch.Tensor], x: torch.Tensor, act: str, bias:
     return x
 
 
+def slim_perron_frobenius(weight, scaling, sigma_min, sigma_max):
+    """``PerronFrobeniusLinear.effective_W`` (reference slim/linear.py:400-403): the ``[in, out]`` matrix"""
+    s_clamped = sigma_max - (sigma_max - sigma_min) * torch.sigmoid(scaling)
+    return s_clamped * F.softmax(weight, dim=1)
+
+
+def slim_soft_svd(U, V, sigma, sigma_min, sigma_max):
+    """``SVDLinear.effective_W`` (reference slim/linear.py:533-541): the ``[in, out]`` matrix"""
+    s = sigma_max - (sigma_max - sigma_min) * torch.sigmoid(sigma)
+    bounded = torch.eye(U.shape[0], V.shape[0], dtype=U.dtype) * s
+    return torch.mm(U, torch.mm(bounded, V))
+
+
 def bounds_scaling(x, xmin, xmax, scaling=1.0):
     """reference modules/functions.py:9-19"""
     return (xmax - xmin) * torch.sigmoid(scaling * x) + xmin

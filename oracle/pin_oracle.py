@@ -212,6 +212,28 @@ def ref_t_vdp_rk4_tanh_clamp(ns, nsteps=12):
     return problem, _mlp_params(net), data, ["x", "u"], ["obj", "eff", "du", "box"]
 
 
+def _slim_params(mlp):
+    """per layer: the structured map's own parameters in registration order, then its bias (reference slim/linear.py:42-61)"""
+    out = []
+    for lin in mlp.linear:
+        out += [p for n, p in lin.named_parameters() if n != "bias"]
+        out.append(lin.bias)
+    return out
+
+
+def _ref_t_slim(ns, linear_map, nsteps=12):
+    problem, _, data, traj_keys, names = ref_t_vdp_rk4_tanh_clamp(ns, nsteps)
+    net = ns.blocks.MLP_bounds(insize=4, outsize=1, hsizes=[16, 16], nonlin=torch.nn.Tanh, min=-1., max=1., method="relu_clamp",
+                               linear_map=linear_map)
+    old = problem.nodes[0].nodes[0]
+    problem.nodes[0].nodes[0] = ns.system.Node(net, old.input_keys, old.output_keys, name=old.name)
+    return problem, _slim_params(net), data, traj_keys, names
+
+
+def ref_t_slim_pf(ns): return _ref_t_slim(ns, ns.slim.maps["pf"])
+def ref_t_slim_svd(ns): return _ref_t_slim(ns, ns.slim.maps["softSVD"])
+
+
 def ref_t_vdp_euler_elu(ns, nsteps=9):
     ode = ns.ode.VanDerPolControl()
     ode.mu = nn.Parameter(torch.tensor(0.7), requires_grad=False)
@@ -420,6 +442,7 @@ REF_BUILDERS = {
     "t_auto_lotka": (ref_t_auto_lotka, 12), "t_auto_lorenz": (ref_t_auto_lorenz, 12),
     "t_preview_replicate": (ref_t_preview_replicate, 12), "t_preview_circular": (ref_t_preview_circular, 12),
     "t_preview_constant": (ref_t_preview_constant, 12), "t_preview_reflect": (ref_t_preview_reflect, 12),
+    "t_slim_pf": (ref_t_slim_pf, 16), "t_slim_svd": (ref_t_slim_svd, 16),
 }
 
 

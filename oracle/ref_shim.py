@@ -223,4 +223,5 @@ def load():
     ns.blocks = importlib.import_module("neuromancer.modules.blocks")
     ns.activations = importlib.import_module("neuromancer.modules.activations")
     ns.functions = importlib.import_module("neuromancer.modules.functions")
+    ns.slim = importlib.import_module("neuromancer.slim")
     return ns

@@ -115,7 +115,7 @@ def test_adopted_constraint_values_match_the_reference_on_cpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c2", "c5"])
+@pytest.mark.parametrize("name", ["c2", "c5", "t_slim_pf"])
 def test_reference_built_problem_runs_on_the_fused_kernels(name):
     """End of the drop-in chain on a GPU box (oracle/_ref travels with the snapshot): a problem built with the reference's
     classes, adopted, run through nmfused::rollout_fwd / rollout_bwd, against the golden recorded from the SAME reference

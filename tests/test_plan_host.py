@@ -140,3 +140,22 @@ def test_recognise_layouts():
     lay = recognise(list(configs.build_case("c4").system.nodes))
     assert (lay.state_key, lay.action_key, lay.output_key, lay.dist_key) == ("x", "u", "y", "d")
     assert lay.exo_keys[:4] == ["d_obs_lookahead", "ymin_lookahead", "ymax_lookahead", "price_lookahead"]
+
+
+def test_constant_division_of_the_rk4_combine_is_correctly_rounded():
+    """nm_dynamics.cuh::div_const replaces x / 6 and x / 3 by  q0 = RN(x r), q = RN(q0 + (x - d q0) r)  with r = RN(1 / d):
+    identical to the IEEE quotient on EVERY significand of a binade (division by a constant commutes with the exponent)
+    and on random values of other magnitudes -- emulated here with exact double arithmetic (a product of two floats and
+    the residual are exact in double)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    binade = np.arange(1 << 23, 1 << 24, dtype=np.int64).astype(np.float32)
+    spread = np.concatenate([rng.standard_normal(1 << 20).astype(np.float32) * np.float32(s) for s in (1.0, 1e-3, 1e3, 1e-20, 1e20)])
+    for d in (3.0, 6.0):
+        r = np.float32(1.0 / d)
+        for x in (binade, -binade, spread):
+            q0 = (x.astype(np.float64) * np.float64(r)).astype(np.float32)
+            rem = x.astype(np.float64) - np.float64(d) * q0.astype(np.float64)
+            assert np.array_equal(rem.astype(np.float32).astype(np.float64), rem)          # the FMA residual is exact
+            q = (q0.astype(np.float64) + rem * np.float64(r)).astype(np.float32)
+            assert np.array_equal(q, (x / np.float32(d)).astype(np.float32))
