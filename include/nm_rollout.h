@@ -282,6 +282,28 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
 /* Number of kernel launches the last forward / backward call issued (for bench.py gpu_launches). */
 int nm_last_launch_count(void);
 
+/* Fused gradient clipping + AdamW update over the flat parameter buffer the rollout kernels read and the flat gradient
+ * buffer nm_rollout_backward wrote (after the data-parallel all-reduce, if any).  Replaces, for the parameters of a fused
+ * problem, the tail of the reference's training step -- trainer.py:251-252:
+ *     torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip);  self.optimizer.step()
+ * with torch.optim.AdamW arithmetic (decoupled weight decay, bias-corrected moments):
+ *     coef = min(1, max_norm / (||g||_2 + 1e-6));  g <- coef * g
+ *     p <- p (1 - lr wd);  m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2
+ *     p <- p - lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+ * Two launches (sum of squares in a fixed order: deterministic; update), no host synchronisation.
+ *   params, exp_avg, exp_avg_sq  [n] device fp32, updated in place;  grads [n] device fp32 (read only)
+ *   step        1-based update count t
+ *   max_norm    <= 0: no clipping
+ *   mask        [n] device bytes or NULL: entries with mask[i] == 0 are left untouched (frozen parameters); they do not
+ *               enter the norm either
+ *   norm_out    [1] device fp32 or NULL: the gradient norm before clipping
+ *   workspace   device memory, >= nm_adamw_workspace_bytes(n) bytes, 256-byte aligned
+ */
+size_t nm_adamw_workspace_bytes(int64_t n);
+int nm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const unsigned char* mask, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float max_norm,
+                  float* norm_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,11 @@ def _declare(lib):
     lib.nm_struct_sizes.restype = C.c_int
     lib.nm_kernel_info.argtypes = [P(NmPlan)]
     lib.nm_kernel_info.restype = C.c_char_p
+    lib.nm_adamw_workspace_bytes.argtypes = [C.c_int64]
+    lib.nm_adamw_workspace_bytes.restype = C.c_size_t
+    lib.nm_adamw_step.argtypes = [fp, fp, fp, fp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_int64, C.c_float, fp, vp, C.c_size_t, vp]
+    lib.nm_adamw_step.restype = C.c_int
 
 
 EXPORTED_SYMBOLS = [

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <string>
+#include <cmath>
 #include <cuda_runtime.h>
 #include "nm_registry.h"
 #include "nm_terms.cuh"
@@ -295,6 +296,74 @@ void nm_register_kernel(NmKernelEntry* e) {
   e->next = g_head;
   g_head = e;
   ++g_count;
+}
+
+// ------------------------------------------------------------------------------------------------ fused clip + AdamW
+// (declared in include/nm_rollout.h; reference trainer.py:251-252).  n is a few thousand to a few hundred thousand
+// floats: the work is two tiny launches, what matters is that the training step never leaves the stream.
+static constexpr int kOptBlocks = 64, kOptThreads = 256;
+static __global__ void __launch_bounds__(kOptThreads) nm_adamw_sumsq_kernel(const float* __restrict__ g, const unsigned char* __restrict__ mask,
+                                                                              int64_t n, double* __restrict__ partial) {
+  __shared__ double red[kOptThreads / 32];
+  double s = 0.0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = (mask == nullptr || mask[i]) ? g[i] : 0.f;
+    s += double(v) * double(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kOptThreads / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+static __global__ void __launch_bounds__(kOptThreads) nm_adamw_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                                               float* __restrict__ v, const unsigned char* __restrict__ mask, int64_t n,
+                                                                               const double* __restrict__ partial, float lr, float b1, float b2, float eps,
+                                                                               float wd, float bc1, float bc2_sqrt, float max_norm, float* __restrict__ norm_out) {
+  double t = 0.0;
+  for (int b = 0; b < kOptBlocks; ++b) t += partial[b];            // same order in every thread
+  const float norm = float(sqrt(t));
+  float coef = 1.f;
+  if (max_norm > 0.f) { coef = max_norm / (norm + 1e-6f); coef = coef < 1.f ? coef : 1.f; }
+  if (norm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+  const float step_size = lr / bc1;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    if (mask != nullptr && !mask[i]) continue;
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;               // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;          //        exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+size_t nm_adamw_workspace_bytes(int64_t) { return 256 + sizeof(double) * kOptBlocks; }
+int nm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const unsigned char* mask, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float max_norm,
+                  float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || workspace == nullptr) {
+    nm_set_error("nm_adamw_step: null argument"); return NM_ERR_BAD_PLAN;
+  }
+  if (n < 0 || step < 1 || workspace_bytes < nm_adamw_workspace_bytes(n) || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    nm_set_error("nm_adamw_step: bad size, step count or workspace"); return NM_ERR_WORKSPACE;
+  }
+  if (n == 0) return NM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  nm_adamw_sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, mask, n, partial);
+  const float bc1 = 1.f - float(std::pow(double(beta1), double(step)));
+  const float bc2_sqrt = float(std::sqrt(1.0 - std::pow(double(beta2), double(step))));
+  nm_adamw_update_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, mask, n, partial, lr, beta1, beta2, eps,
+                                                             weight_decay, bc1, bc2_sqrt, max_norm, norm_out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
+  return NM_OK;
 }
 
 int nm_abi_version(void) { return NM_ABI_VERSION; }

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .dataset import DevicePrefetcher, move_batch_to_device
+from .optim import FusedAdamW
 
 
 class LaggedScalarReader:
@@ -62,6 +63,8 @@ class Trainer:
         self.best_devloss = np.finfo(np.float32).max if self._eval_min else 0.
         self.best_model = deepcopy(self.model.state_dict())
         self.device, self.grad_sync = device, grad_sync
+        if lr_scheduler and isinstance(self.optimizer, FusedAdamW):
+            raise ValueError("lr_scheduler=True needs a torch optimiser (ReduceLROnPlateau); set FusedAdamW.param_groups[0]['lr'] yourself")
         self.lr_scheduler = (torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=0.5, patience=100)
                              if lr_scheduler else None)
 
@@ -69,6 +72,15 @@ class Trainer:
         output = self.model(batch)
         self.optimizer.zero_grad()
         output[self.train_metric].backward()
+        if isinstance(self.optimizer, FusedAdamW):
+            # clip + AdamW in one call over the flat gradient the adjoint kernels wrote (all-reduced in place first)
+            if self.optimizer._runner is None:
+                self.optimizer._bind()
+            if self.grad_sync is not None:
+                self.grad_sync.allreduce_flat_(self.optimizer._runner.last_grad_flat)
+            self.optimizer.max_grad_norm = float(self.clip) if self.clip else 0.0
+            self.optimizer.step()
+            return output
         if self.grad_sync is not None:
             self.grad_sync.sync_gradients(self.model.parameters())
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
