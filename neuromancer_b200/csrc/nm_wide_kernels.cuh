@@ -72,6 +72,10 @@ __device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+template <int W> __device__ __forceinline__ void tmem_stu(uint32_t taddr, const uint32_t (&v)[W]) {
+  static_assert(W == 8 || W == 16, "tmem_stu: 8 or 16 words");
+  if constexpr (W == 16) tmem_st16u(taddr, v); else tmem_st8u(taddr, v);
+}
 // L2 residency: the derivative stash is rewritten and re-read every step (evict_last keeps it out of DRAM: 256-bit
 // accesses carry the priority as a qualifier -- a policy operand would cost two R2UR per access); the staging tiles are
 // written once and read by a later kernel (streaming stores: they must not push the stash out)
@@ -223,8 +227,8 @@ __device__ __forceinline__ void act_acc_pair2(float& v0, float& v1, float bs0, f
 // The epilogue of 2 NP consecutive accumulator entries v[O .. O + 2 NP), written "vertically": every step of the evaluation
 // runs across all NP pairs before the next one starts, so NP independent FFMA2 chains are in flight (written pair after
 // pair, the compiler interleaved two chains and every Horner step waited out the FFMA2 latency).  DERIV: also act'(z) -> d.
-template <int ACT, int O, int NP, bool DERIV>
-__device__ __forceinline__ void act_group(float (&v)[32], float (&d)[32], const float* __restrict__ bias, float prm) {
+template <int ACT, int O, int NP, bool DERIV, int N>
+__device__ __forceinline__ void act_group(float (&v)[N], float (&d)[N], const float* __restrict__ bias, float prm) {
   if constexpr (ACT == NM_ACT_GELU) {
     const f2_t c = bc2(0.70710678118654752440f);
     f2_t x[NP], t[NP], q[NP];
@@ -344,7 +348,7 @@ struct WideCfg {
 #ifdef NM_TUNE_WBT
   static constexpr int BWD_TPT = NM_TUNE_WBT;
 #else
-  static constexpr int BWD_TPT = 1;                                       // adjoint kernel: threads per trajectory (2 measured SLOWER: 19.0 vs 15.6 ms at B = 37,888 -- 128 registers spill the dynamics adjoint, and the primary thread serialises the scalar work)
+  static constexpr int BWD_TPT = 1;                                       // adjoint kernel: threads per trajectory (2 measured SLOWER, twice: 19.0 vs 15.6 ms at B = 37,888 with 384 B of spills; 13.8 vs 12.7 ms after the 16-column epilogue chunks and L2-hint prefetch cut them to 200 B -- the sweep is bound by its per-slot chain and memory round trips, not by warps per scheduler)
 #endif
   static constexpr int BWD_THREADS = 256 * BWD_TPT;
   // ---- adjoint: staging item (one tile-step), byte offsets of the operand tiles X[feature/8][128][8] halves
@@ -933,34 +937,63 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
 #ifdef NM_TUNE_WPROF
     const long long w_begin = clock64();
 #endif
-    // staging store of 32 consecutive features (16 packed words) of operand tile `toff`
-    auto stage32 = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[16]) {
+    // Epilogue chunk: CW accumulator columns at a time -- 32 with one thread per trajectory, 16 with two (128 registers:
+    // v / d / hi / lo / the stash double buffer of a 32-column chunk are 128 registers by themselves)
+    constexpr int CW = TPT == 1 ? 32 : 16;
+    // staging store of CW consecutive features (CW / 2 packed words) of operand tile `toff`
+    auto stage_cw = [&](uint8_t* item, int toff, int c0, const uint32_t (&hi)[CW / 2]) {
 #ifndef NM_TUNE_WNOSTAGE                               // (timing experiment: the adjoint without its staging stores -- results are wrong)
       uint8_t* q = item + toff + (c0 / 8) * C::GRP + m_ * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      for (int g = 0; g < CW / 8; ++g) wd::st_global_v4(q + g * C::GRP, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
 #endif
     };
 
     // Everything a step reads from HBM is requested one step ahead -- across tile boundaries too (with short chunks a
     // tile is only CSn steps long): rows of step t-1 of this trajectory, or the first rows of the next tile's trajectory
+    // One thread per trajectory has the registers to hold the next step's rows (REGPF); with two threads per trajectory
+    // (128 registers) the rows are only pulled into L2 ahead of time and loaded at the top of their step.
+    constexpr bool REGPF = TPT == 1;
     float lam_pre[NX] = {}, x_pre[NX] = {}, o_pre[NU] = {}, in_pre[K0] = {}, g_pre[RW] = {};
-    auto prefetch_rows = [&](int64_t bq, int tq) {
+    auto l2_hint = [&](const float* q, int n) {
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q));
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q + n - 1));
+    };
+    auto load_rows = [&](int64_t bq, int tq) {
       wd::ld_row<NX>(x_pre, args.x_traj + (bq * (T + 1) + tq) * NX);
       wd::ld_row<NU>(o_pre, args.chk + (bq * T + tq) * NU);
       wd::ld_row<RW>(g_pre, wargs.G + (bq * int64_t(CSn + 1) + (tq - t_lo)) * RW);
       wd::policy_exo<S, K0>(p, args.exo, bq, tq, in_pre);
     };
-    auto prefetch_tile = [&](int tile_q) {                 // first step of a tile + its incoming co-state
-      const int64_t bq_raw = int64_t(tile_q) * TILE + m_;
-      const int64_t bq = bq_raw < args.B ? bq_raw : args.B - 1;
-      prefetch_rows(bq, t_hi - 1);
+    auto load_lam = [&](int64_t bq) {
       if (t_hi == T) {
         float gT[RW];
         wd::ld_row<RW>(gT, wargs.G + (bq * int64_t(CSn + 1) + CSn) * RW);
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam_pre[i] = gT[i];
       } else wd::ld_row<NX>(lam_pre, wargs.lam_carry + bq * NX);
+    };
+    auto prefetch_rows = [&](int64_t bq, int tq) {
+      if constexpr (REGPF) load_rows(bq, tq);
+      else {
+        l2_hint(args.x_traj + (bq * (T + 1) + tq) * NX, NX);
+        l2_hint(args.chk + (bq * T + tq) * NU, NU);
+        l2_hint(wargs.G + (bq * int64_t(CSn + 1) + (tq - t_lo)) * RW, RW);
+        static_for<0, S::NSEG>([&](auto sc) {
+          constexpr int sg = decltype(sc)::value;
+          if constexpr (S::seg_kind(sg) == NM_SEG_EXO) {
+            constexpr int e = S::seg_index(sg), W = S::seg_width(sg);
+            l2_hint(args.exo[e] + (bq * p.exo[e].steps + tq) * W, W);
+          }
+        });
+      }
+    };
+    auto prefetch_tile = [&](int tile_q) {                 // first step of a tile + its incoming co-state
+      const int64_t bq_raw = int64_t(tile_q) * TILE + m_;
+      const int64_t bq = bq_raw < args.B ? bq_raw : args.B - 1;
+      prefetch_rows(bq, t_hi - 1);
+      if constexpr (REGPF) load_lam(bq);
+      else l2_hint(t_hi == T ? wargs.G + (bq * int64_t(CSn + 1) + CSn) * RW : wargs.lam_carry + bq * NX, NX);
     };
     if (primary && int(blockIdx.x) * 2 + slot < args.num_tiles) prefetch_tile(int(blockIdx.x) * 2 + slot);
     for (int r = 0;; ++r) {
@@ -970,11 +1003,13 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
       const int64_t b_raw = int64_t(tile) * TILE + m_;
       const bool valid = b_raw < args.B;
       const int64_t b = valid ? b_raw : args.B - 1;
+      if constexpr (!REGPF) { if (primary) load_lam(b); }
       float lam[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) lam[i] = valid ? lam_pre[i] : 0.f;
 #pragma unroll 1
       for (int t = t_hi - 1; t >= t_lo; --t) {
+        if constexpr (!REGPF) { if (primary) load_rows(b, t); }
 #ifdef NM_TUNE_WSTWRAP                                 // (timing experiment: staging wrapped into an L2-sized window -- results are wrong)
         uint8_t* item = wargs.staging + ((size_t(tile) * CSn + size_t(t - t_lo)) % NM_TUNE_WSTWRAP) * C::ITEM_BYTES;
 #else
@@ -1049,26 +1084,26 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
           tc::fence_after();
           WP_T0();
 #pragma unroll 1
-          for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
-            float v[32], d[32];
-            uint32_t hi[16], lo[16];
-            tc::tmem_ld<32>(t_d + c0, v);
+          for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += CW) {
+            float v[CW], d[CW];
+            uint32_t hi[CW / 2], lo[CW / 2];
+            tc::tmem_ld<CW>(t_d + c0, v);
             wd::act_group<M::ACT, 0, 8, true>(v, d, bias + c0, act_prm);
-            wd::act_group<M::ACT, 16, 8, true>(v, d, bias + c0, act_prm);
+            if constexpr (CW == 32) wd::act_group<M::ACT, 16, 8, true>(v, d, bias + c0, act_prm);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-            stage32(item, C::a_off(1) + l * (H / 8) * C::GRP, c0, hi);                    // a_{l+1}
+            for (int i = 0; i < CW / 2; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            stage_cw(item, C::a_off(1) + l * (H / 8) * C::GRP, c0, hi);                   // a_{l+1}
             if (!last) {
-              wd::tmem_st16u(t_hi_ + c0 / 2, hi);
-              wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+              wd::tmem_stu<CW / 2>(t_hi_ + c0 / 2, hi);
+              wd::tmem_stu<CW / 2>(t_lo_ + c0 / 2, lo);
 #ifndef NM_TUNE_WNOSTASH                               // (timing experiment: no derivative stash traffic -- results are wrong)
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) wd::st_stash8(stash + (l * (H / 8) + (c0 + i) / 8) * 128, d + i);
+              for (int i = 0; i < CW; i += 8) wd::st_stash8(stash + (l * (H / 8) + (c0 + i) / 8) * 128, d + i);
 #endif
             } else {
               // output layer backward on the CUDA cores: dA[k] = sum_j cot[j] W_out[j][k];  dZ_{NL-2} = dA * act'
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
+              for (int i = 0; i < CW; i += 4) {
                 float da0 = 0.f, da1 = 0.f, da2 = 0.f, da3 = 0.f;
 #pragma unroll
                 for (int j = 0; j < NOUT; ++j) {
@@ -1079,13 +1114,13 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
               }
               if (c0 == half * HC) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
+                for (int i = 0; i < CW; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
               }
 #pragma unroll
-              for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-              stage32(item, C::z_off(NL - 2), c0, hi);                                   // dZ_{NL-2}
-              wd::tmem_st16u(t_hi_ + c0 / 2, hi);
-              wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+              for (int i = 0; i < CW / 2; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+              stage_cw(item, C::z_off(NL - 2), c0, hi);                                  // dZ_{NL-2}
+              wd::tmem_stu<CW / 2>(t_hi_ + c0 / 2, hi);
+              wd::tmem_stu<CW / 2>(t_lo_ + c0 / 2, lo);
             }
           }
           WP_ADD(w_epi_rc);
@@ -1101,40 +1136,40 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
         // ---- data gradients: D = dA_l (cotangent of a_l), l = NL-2 .. 1;  dZ_{l-1} = dA_l * act'(z_{l-1})
 #pragma unroll 1
         for (int l = NL - 2; l >= 1; --l) {
-          // the stashed derivatives come from L2: two 32-column chunks are always in flight -- chunks 0 and 1 are
+          // the stashed derivatives come from L2: two CW-column chunks are always in flight -- chunks 0 and 1 are
           // requested before the wait for the MMAs, chunk c+2 when chunk c has been consumed
-          float dq[2][32];
+          float dq[2][CW];
           const wd::float8* __restrict__ sl = stash + ((l - 1) * (H / 8) + half * (HC / 8)) * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) wd::ld_stash8(sl + i * 128, dq[0] + 8 * i);
+          for (int i = 0; i < CW / 8; ++i) wd::ld_stash8(sl + i * 128, dq[0] + 8 * i);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) wd::ld_stash8(sl + (4 + i) * 128, dq[1] + 8 * i);
+          for (int i = 0; i < CW / 8; ++i) wd::ld_stash8(sl + (CW / 8 + i) * 128, dq[1] + 8 * i);
           { WP_T0(); mbar_wait(bar_done, ph_done); ph_done ^= 1; WP_ADD(w_wait_dg); }
           tc::fence_after();
           WP_T0();
 #pragma unroll 1
-          for (int c2 = 0; c2 < HC; c2 += 64) {
+          for (int c2 = 0; c2 < HC; c2 += 2 * CW) {
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
-              const int cl = c2 + hb * 32, c0 = half * HC + cl;      // column within this thread's range / within the layer
-              float v[32];
-              uint32_t hi[16], lo[16];
-              tc::tmem_ld<32>(t_d + c0, v);
+              const int cl = c2 + hb * CW, c0 = half * HC + cl;      // column within this thread's range / within the layer
+              float v[CW];
+              uint32_t hi[CW / 2], lo[CW / 2];
+              tc::tmem_ld<CW>(t_d + c0, v);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= dq[hb][i];
-              if (cl + 64 < HC) {
+              for (int i = 0; i < CW; ++i) v[i] *= dq[hb][i];
+              if (cl + 2 * CW < HC) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) wd::ld_stash8(sl + ((cl + 64) / 8 + i) * 128, dq[hb] + 8 * i);
+                for (int i = 0; i < CW / 8; ++i) wd::ld_stash8(sl + ((cl + 2 * CW) / 8 + i) * 128, dq[hb] + 8 * i);
               }
               if (cl == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
+                for (int i = 0; i < CW; ++i) dzmax = fmaxf(dzmax, fabsf(v[i]));
               }
 #pragma unroll
-              for (int i = 0; i < 16; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-              stage32(item, C::z_off(l - 1), c0, hi);                                     // dZ_{l-1}
-              wd::tmem_st16u(t_hi_ + c0 / 2, hi);
-              wd::tmem_st16u(t_lo_ + c0 / 2, lo);
+              for (int i = 0; i < CW / 2; ++i) wd::split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+              stage_cw(item, C::z_off(l - 1), c0, hi);                                    // dZ_{l-1}
+              wd::tmem_stu<CW / 2>(t_hi_ + c0 / 2, hi);
+              wd::tmem_stu<CW / 2>(t_lo_ + c0 / 2, lo);
             }
           }
           WP_ADD(w_epi_dg);
