@@ -400,7 +400,7 @@ def main():
     peak = fp16x3_peak if wide else tf32x3_peak
     achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12
     traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    traffic = None
+    traffic, tj = None, None
     if os.path.exists(traffic_path):                           # ncu capture of the adjoint launches, scaled to this batch
         tj = json.load(open(traffic_path))
         traffic = tj["bwd_dram_bytes_per_launch"] * (B / tj["batch"])
@@ -410,6 +410,8 @@ def main():
         bwd_kernel = "nm_tc_bwd_kernel" if "bwd[tcgen05" in kernel_info else "nm_bwd_kernel"
     roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": (f"dram read+write of the kernels named above from the committed ncu --set full capture at B = {tj['batch']} "
+                                   f"(profiles/traffic_{args.workload}.json), scaled to this batch; not measured in this run") if traffic is not None else None,
                 "peak_source": (f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 3 (3-product fp16 split, fp32-accurate)" if wide else
                                 f"{peaks['source']} bf16 {peaks['bf16_tflops']} TFLOP/s / 2 (tf32) / 3 (3xTF32 fp32-accurate split)"),
                 "frac_of_3xtf32_peak": achieved / tf32x3_peak, "tf32x3_peak": tf32x3_peak,

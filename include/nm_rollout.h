@@ -81,6 +81,9 @@ extern "C" {
 #define NM_INT_RK4_TRAP   4 /* integrators.py:214-235  predictor RK4, corrector trapezoid              */
 #define NM_INT_LUTHER     5 /* integrators.py:238-264  Luther's 6th-order 7-stage method               */
 #define NM_INT_RKF        6 /* integrators.py:267-301  Runge-Kutta-Fehlberg, 5th-order output          */
+/* second-order schemes  ddx = f(x[, u])  on the state X = [x, dx] (nx even; MLP right-hand side nx/2 [+ nu] -> nx/2)   */
+#define NM_INT_LEAPFROG   7 /* integrators.py:340-360  velocity Verlet / leapfrog, 2 right-hand-side evaluations */
+#define NM_INT_YOSHIDA4   8 /* integrators.py:363-404  4th-order Yoshida composition, 3 evaluations              */
 
 #define NM_RHS_NONE     0
 #define NM_RHS_TWOTANK  1 /* ode.py:216-237; rhs_const = {c1, c2}                            */

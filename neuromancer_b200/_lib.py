@@ -20,6 +20,7 @@ NM_SEG_STATE, NM_SEG_OUTPUT, NM_SEG_EXO, NM_SEG_PREVIEW = 0, 1, 2, 3
 NM_PAD_CONSTANT, NM_PAD_REPLICATE, NM_PAD_CIRCULAR, NM_PAD_REFLECT = 0, 1, 2, 3
 NM_DYN_SSM, NM_DYN_ODE = 0, 1
 NM_INT_EULER, NM_INT_RK4, NM_INT_RK2, NM_INT_EULER_TRAP, NM_INT_RK4_TRAP, NM_INT_LUTHER, NM_INT_RKF = 0, 1, 2, 3, 4, 5, 6
+NM_INT_LEAPFROG, NM_INT_YOSHIDA4 = 7, 8
 NM_RHS_NONE, NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 0, 1, 2, 3, 4, 5
 NM_VAR_CONST, NM_VAR_X, NM_VAR_U, NM_VAR_Y, NM_VAR_EXO0 = -1, 0, 1, 2, 3
 NM_OP_NONE, NM_OP_ADD, NM_OP_SUB, NM_OP_MUL = 0, 1, 2, 3

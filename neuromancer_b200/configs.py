@@ -462,6 +462,32 @@ def t_int_rkf_node(seed=0, nsteps=6) -> Case:
     return Case("t_int_rkf_node", problem, system, nsteps, 100, mb, 0, 0)
 
 
+def _t_second_order(integ, name, seed, nsteps) -> Case:
+    """Second-order neural ODE ddx = MLP([x, u]) on X = [x, dx] with a measured input (reference integrators.py:340-404)."""
+    torch.manual_seed(seed)
+    fx = blocks.MLP(3, 2, bias=True, linear_map=nn.Linear, nonlin=nn.Tanh, hsizes=[16, 16])
+    model = Node(integ(fx, h=0.1), ["xn", "U"], ["xn"], name="NODE")
+    system = System([model], name="system")                       # nsteps from data['X']
+    ref = (variable("xn")[:, :-1, :] == variable("X")) ^ 2
+    ref.name = "ref"
+    problem = Problem([system], PenaltyLoss([ref], []))
+
+    def mb(Bn, device, s=0):
+        g = _gen(device, 9700 + s)
+        X = torch.randn(Bn, nsteps, 4, generator=g)
+        return {"X": X.to(device), "xn": X[:, 0:1, :].contiguous().to(device), "U": torch.randn(Bn, nsteps, 1, generator=g).to(device),
+                "name": "train"}
+    return Case(name, problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_int_leapfrog_node(seed=0, nsteps=7) -> Case:
+    return _t_second_order(integrators.LeapFrog, "t_int_leapfrog_node", seed, nsteps)
+
+
+def t_int_yoshida_node(seed=0, nsteps=7) -> Case:
+    return _t_second_order(integrators.Yoshida4, "t_int_yoshida_node", seed, nsteps)
+
+
 def t_open_duffing(seed=0, nsteps=9) -> Case:
     torch.manual_seed(seed)
     model = Node(integrators.RK4(_freeze(ode.DuffingParam()), h=0.05), ["x", "t"], ["x"], name="model")
@@ -572,6 +598,7 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
     "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
     "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd,
+    "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node,
 }
 # shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
 EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index, "c4p": c4p}

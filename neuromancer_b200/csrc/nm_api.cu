@@ -429,7 +429,8 @@ int nm_load_plugin(const char* path) {
 // stage derivatives kept per integrator step for MLP right-hand sides
 static int integrator_stages(int integ) {
   switch (integ) { case NM_INT_EULER: return 1; case NM_INT_RK2: case NM_INT_EULER_TRAP: return 2; case NM_INT_RK4: return 4;
-                   case NM_INT_RK4_TRAP: return 5; case NM_INT_RKF: return 6; case NM_INT_LUTHER: return 7; default: return 1; }
+                   case NM_INT_RK4_TRAP: return 5; case NM_INT_RKF: return 6; case NM_INT_LUTHER: return 7;
+                   case NM_INT_LEAPFROG: return 2; case NM_INT_YOSHIDA4: return 3; default: return 1; }
 }
 int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes) {
   int rc = validate(plan);

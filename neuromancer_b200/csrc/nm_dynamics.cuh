@@ -233,6 +233,105 @@ template <> struct Tableau<NM_INT_RKF> {                     // integrators.py:2
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Second-order schemes (reference integrators.py:340-404): the block is ddx = f(x[, u]) on HALF = NX / 2 coordinates,
+// the state is X = [x, dx].  They are not Runge-Kutta tableaus on X (position and velocity advance with different
+// coefficients, LeapFrog even with h^2), so they get their own stage functions; k[j][0 .. HALF) holds a_j = f(q_j).
+//   LeapFrog:  q0 = x;  q1 = x + dx h + 0.5 a0 h^2;  X+ = [q1, dx + 0.5 (a0 + a1) h]
+//   Yoshida4:  q1 = x + c1 dx h;  v1 = dx + d1 a1 h;  q2 = q1 + c2 v1 h;  v2 = v1 + d2 a2 h;  q3 = q2 + c3 v2 h;
+//              v3 = v2 + d3 a3 h;  X+ = [q3 + c4 v3 h, v3]          (operation order of the reference expressions)
+template <int INTEG> constexpr bool second_order() { return INTEG == NM_INT_LEAPFROG || INTEG == NM_INT_YOSHIDA4; }
+template <> struct Tableau<NM_INT_LEAPFROG> {
+  static constexpr int NS = 2;
+  static constexpr double a(int, int) { return 0.0; }
+  static constexpr double b(int) { return 0.0; }
+};
+template <> struct Tableau<NM_INT_YOSHIDA4> {
+  static constexpr int NS = 3;
+  static constexpr double a(int, int) { return 0.0; }
+  static constexpr double b(int) { return 0.0; }
+};
+struct Yoshida {                                             // integrators.py:381-390, evaluated in double like the python floats
+  static constexpr double cbrt2 = 1.2599210498948731648;
+  static constexpr double w0 = -cbrt2 / (2.0 - cbrt2), w1 = 1.0 / (2.0 - cbrt2);
+  static constexpr float c(int i) { return static_cast<float>((i == 0 || i == 3) ? w1 / 2.0 : (w0 + w1) / 2.0); }   // c1..c4
+  static constexpr float d(int i) { return static_cast<float>(i == 1 ? w0 : w1); }                                   // d1..d3
+};
+// position q_St the right-hand side is evaluated at in stage St, from X and a_0 .. a_{St-1}
+template <int INTEG, int St, int NX>
+__device__ __forceinline__ void so_position(float h, const float (&X)[NX], const float (&k)[NM_MAX_STAGES][NX], float (&q)[NX / 2]) {
+  constexpr int HALF = NX / 2;
+  if constexpr (INTEG == NM_INT_LEAPFROG) {
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      if constexpr (St == 0) q[i] = X[i];
+      else q[i] = (X[i] + X[HALF + i] * h) + (0.5f * k[0][i]) * (h * h);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      float qq = X[i] + (Yoshida::c(0) * X[HALF + i]) * h, v = X[HALF + i];
+      static_for<0, St>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        v = v + (Yoshida::d(J) * k[J][i]) * h;
+        qq = qq + (Yoshida::c(J + 1) * v) * h;
+      });
+      q[i] = qq;
+    }
+  }
+}
+template <int INTEG, int NX>
+__device__ __forceinline__ void so_combine(float h, const float (&X)[NX], const float (&k)[NM_MAX_STAGES][NX], float (&Xn)[NX]) {
+  constexpr int HALF = NX / 2;
+  if constexpr (INTEG == NM_INT_LEAPFROG) {
+    float q1[HALF];
+    so_position<INTEG, 1, NX>(h, X, k, q1);
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) { Xn[i] = q1[i]; Xn[HALF + i] = X[HALF + i] + (0.5f * (k[0][i] + k[1][i])) * h; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      float qq = X[i] + (Yoshida::c(0) * X[HALF + i]) * h, v = X[HALF + i];
+      static_for<0, 3>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        v = v + (Yoshida::d(J) * k[J][i]) * h;
+        qq = qq + (Yoshida::c(J + 1) * v) * h;
+      });
+      Xn[i] = qq; Xn[HALF + i] = v;
+    }
+  }
+}
+// adjoint: running cotangents gq (of the current position) and gv (of the current velocity), stages in reverse;
+// ga is LeapFrog's pending cotangent of a0 (it enters both the position and the velocity update)
+template <int INTEG, int NX>
+__device__ __forceinline__ void so_adj_init(float h, const float (&lam)[NX], float (&gq)[NX / 2], float (&gv)[NX / 2], float (&ga)[NX / 2]) {
+  constexpr int HALF = NX / 2;
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    gq[i] = lam[i]; ga[i] = 0.f;
+    if constexpr (INTEG == NM_INT_LEAPFROG) gv[i] = lam[HALF + i];
+    else gv[i] = lam[HALF + i] + (Yoshida::c(3) * h) * lam[i];
+  }
+}
+template <int INTEG, int St, int NX>                         // cotangent w of a_St
+__device__ __forceinline__ void so_adj_cot(float h, const float (&gv)[NX / 2], const float (&ga)[NX / 2], float (&w)[NX / 2]) {
+#pragma unroll
+  for (int i = 0; i < NX / 2; ++i) {
+    if constexpr (INTEG == NM_INT_LEAPFROG) w[i] = St == 1 ? 0.5f * h * gv[i] : ga[i];
+    else w[i] = (Yoshida::d(St) * h) * gv[i];
+  }
+}
+template <int INTEG, int St, int NX>                         // gqs = (d f / d q_St)^T w arrived: step back over stage St
+__device__ __forceinline__ void so_adj_push(float h, const float (&gqs)[NX / 2], float (&gq)[NX / 2], float (&gv)[NX / 2], float (&ga)[NX / 2]) {
+#pragma unroll
+  for (int i = 0; i < NX / 2; ++i) {
+    gq[i] += gqs[i];
+    if constexpr (INTEG == NM_INT_LEAPFROG) {
+      if constexpr (St == 1) { ga[i] = 0.5f * h * gv[i] + 0.5f * (h * h) * gq[i]; gv[i] += h * gq[i]; }
+    } else gv[i] += (Yoshida::c(St) * h) * gq[i];
+  }
+}
+
 // stage input xs_S from x and the earlier stage derivatives k[0..S-1]
 template <int INTEG, int S_, int NX>
 __device__ __forceinline__ void stage_input(float h, const float (&x)[NX], const float (&k)[NM_MAX_STAGES][NX], float (&xs)[NX]) {

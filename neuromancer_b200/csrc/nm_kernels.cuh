@@ -121,7 +121,11 @@ struct KCfg {
   // prepared exogenous block of the hoist GEMMs: rows [KE exogenous inputs | bias][NPf] in the forward image layout
   static constexpr int EXO_NP = g_np(N0);
   static constexpr int EXO_W_FLOATS = HOIST ? round_up((KE + 1) * EXO_NP, 4) : 0;
-  using RhsCfg = std::conditional_t<HAS_RHS_MLP, MlpCfg<typename S::RhsM, TILE, THREADS, NX + NU>, NoMlpCfg<TILE, THREADS>>;
+  // second-order integrators (LeapFrog, Yoshida4): the right-hand side maps RX = NX / 2 positions [+ NU] to RX accelerations
+  static constexpr bool SO = HAS_RHS_MLP && second_order<S::INTEG>();
+  static constexpr int RX = SO ? NX / 2 : NX;
+  static_assert(!SO || NX % 2 == 0, "second-order integrators need an even state width");
+  using RhsCfg = std::conditional_t<HAS_RHS_MLP, MlpCfg<typename S::RhsM, TILE, THREADS, RX + NU>, NoMlpCfg<TILE, THREADS>>;
   static constexpr int W_FLOATS_FWD = round_up(PolCfg::FWD_W, 4) + round_up(RhsCfg::FWD_W, 4);
   static constexpr int RHS_WF_OFF = round_up(PolCfg::FWD_W, 4);                     // forward-kernel smem offset
   static constexpr int W_FLOATS_ALL = round_up(PolCfg::ALL_W, 4) + round_up(RhsCfg::ALL_W, 4);
@@ -673,34 +677,39 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
         // neural right-hand side: every stage is a CTA-cooperative MLP evaluation
         constexpr int NS = Tableau<S::INTEG>::NS;
         float k[NM_MAX_STAGES][NX];
+        constexpr int RX = KC::RX;                           // width of the right-hand side's state input / output
         static_for<0, NS>([&](auto sc) {
           constexpr int St = decltype(sc)::value;
           if (owner) {
-            float xs[NX];
-            stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
+            float xs[RX];
+            if constexpr (KC::SO) so_position<S::INTEG, St, NX>(p.h, x, k, xs);
+            else stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) pp0[i * LD + tid] = xs[i];
+            for (int i = 0; i < RX; ++i) pp0[i * LD + tid] = xs[i];
 #pragma unroll
-            for (int j = 0; j < NU; ++j) pp0[(NX + j) * LD + tid] = u[j];
+            for (int j = 0; j < NU; ++j) pp0[(RX + j) * LD + tid] = u[j];
           }
           __syncthreads();
           mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, false>(Wrhs, pp0, pp1, nullptr, nullptr, p.rhs_mlp.act_param, tid);
           if (owner) {
             const float* outp = (RhsCfg::NL & 1) ? pp1 : pp0;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) k[St][i] = outp[i * LD + tid];
+            for (int i = 0; i < RX; ++i) k[St][i] = outp[i * LD + tid];
             if constexpr (St + 1 < NS) {
               if (valid && args.chk != nullptr) {
                 float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
 #pragma unroll
-                for (int i = 0; i < NX; ++i) cp[i] = k[St][i];
+                for (int i = 0; i < RX; ++i) cp[i] = k[St][i];
               }
             }
           }
           // the next writer of pp0/pp1 is this same thread's own column (stage input) or, behind a
           // barrier, the next layer GEMM: no extra barrier needed here
         });
-        if (owner) combine_stages<S::INTEG, NX>(p.h, x, k, xn);
+        if (owner) {
+          if constexpr (KC::SO) so_combine<S::INTEG, NX>(p.h, x, k, xn);
+          else combine_stages<S::INTEG, NX>(p.h, x, k, xn);
+        }
       }
       if (owner) {
 #pragma unroll
@@ -893,7 +902,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
       if constexpr (!KC::HAS_RHS_MLP) {
         if (owner) Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
       } else {
-        constexpr int NS = Tableau<S::INTEG>::NS;
+        constexpr int NS = Tableau<S::INTEG>::NS, RX = KC::RX;
         const float h = p.h;
         float k[NM_MAX_STAGES][NX], gk[NM_MAX_STAGES][NX];
         // pass 1: stage derivatives k_0 .. k_{NS-2}
@@ -906,22 +915,23 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             if (owner) {
               const float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
 #pragma unroll
-              for (int i = 0; i < NX; ++i) k[St][i] = __ldg(cp + i);
+              for (int i = 0; i < RX; ++i) k[St][i] = __ldg(cp + i);
             }
            } else {
             if (owner) {
-              float xs[NX];
-              stage_input<S::INTEG, St, NX>(h, x, k, xs);
+              float xs[RX];
+              if constexpr (KC::SO) so_position<S::INTEG, St, NX>(h, x, k, xs);
+              else stage_input<S::INTEG, St, NX>(h, x, k, xs);
 #pragma unroll
-              for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
+              for (int i = 0; i < RX; ++i) keep_rhs[i * LD + tid] = xs[i];
 #pragma unroll
-              for (int j = 0; j < NU; ++j) keep_rhs[(NX + j) * LD + tid] = u[j];
+              for (int j = 0; j < NU; ++j) keep_rhs[(RX + j) * LD + tid] = u[j];
             }
             __syncthreads();
             mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
             if (owner) {
 #pragma unroll
-              for (int i = 0; i < NX; ++i) k[St][i] = dbuf0[i * LD + tid];
+              for (int i = 0; i < RX; ++i) k[St][i] = dbuf0[i * LD + tid];
             }
             __syncthreads();                                     // dbuf0 is rewritten by the next stage
            }
@@ -930,38 +940,48 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
         // pass 2: stages in reverse, recomputing each stage's activations
 #pragma unroll
         for (int i = 0; i < NX; ++i) gx[i] = lam[i];
+        constexpr int SOH = KC::SO ? NX / 2 : 1;                // second-order schemes: running cotangents of position / velocity
+        float so_gq[SOH], so_gv[SOH], so_ga[SOH];
+        if constexpr (KC::SO) so_adj_init<S::INTEG, NX>(h, lam, so_gq, so_gv, so_ga);
         static_for_rev<0, NS>([&](auto sc) {
           constexpr int St = decltype(sc)::value;
           if (owner) {
-            float xs[NX];
-            stage_input<S::INTEG, St, NX>(h, x, k, xs);
+            float xs[RX];
+            if constexpr (KC::SO) so_position<S::INTEG, St, NX>(h, x, k, xs);
+            else stage_input<S::INTEG, St, NX>(h, x, k, xs);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) keep_rhs[i * LD + tid] = xs[i];
+            for (int i = 0; i < RX; ++i) keep_rhs[i * LD + tid] = xs[i];
 #pragma unroll
-            for (int j = 0; j < NU; ++j) keep_rhs[(NX + j) * LD + tid] = u[j];
+            for (int j = 0; j < NU; ++j) keep_rhs[(RX + j) * LD + tid] = u[j];
           }
           __syncthreads();
           mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
           if (owner) {
-            float w[NX];
-            stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w);
+            float w[RX];
+            if constexpr (KC::SO) so_adj_cot<S::INTEG, St, NX>(h, so_gv, so_ga, w);
+            else stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) dbuf0[i * LD + tid] = valid ? w[i] : 0.f;
+            for (int i = 0; i < RX; ++i) dbuf0[i * LD + tid] = valid ? w[i] : 0.f;
           }
           __syncthreads();
           mlp_backward<RhsCfg, typename S::RhsM, TILE, THREADS, SPILL>(Wrhs, keep_rhs, dbuf0, dbuf1, rhs_dw, grhs,
                                                                         p.rhs_mlp.has_bias, rhs_train, p.rhs_mlp.act_param, tid);
           if (owner) {
             const float* gin = (RhsCfg::NL & 1) ? dbuf1 : dbuf0;
-            float gxs[NX];
+            float gxs[RX];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) gxs[i] = gin[i * LD + tid];
-            stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
+            for (int i = 0; i < RX; ++i) gxs[i] = gin[i * LD + tid];
+            if constexpr (KC::SO) so_adj_push<S::INTEG, St, NX>(h, gxs, so_gq, so_gv, so_ga);
+            else stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
 #pragma unroll
-            for (int j = 0; j < NU; ++j) gu[j] += gin[(NX + j) * LD + tid];
+            for (int j = 0; j < NU; ++j) gu[j] += gin[(RX + j) * LD + tid];
           }
           __syncthreads();                                       // gin buffer is rewritten by the next stage
         });
+        if constexpr (KC::SO) {
+#pragma unroll
+          for (int i = 0; i < NX / 2; ++i) { gx[i] = so_gq[i]; gx[NX / 2 + i] = so_gv[i]; }
+        }
       }
       // ---- loss-term gradients w.r.t. u_t and y_t
       if (valid) {

@@ -70,7 +70,7 @@ struct TcKCfg {
   using MD = TcMode<S>;
   using C = tc::TcCfg<typename MD::M>;
   static constexpr int NX = S::NX, NU = S::NU;
-  static constexpr bool ELIGIBLE_RHS = S::RHS == NM_RHS_MLP && S::Pol::NL == 0 && !S::HAS_OUTPUT && S::ND == 0 && C::shape_ok() &&
+  static constexpr bool ELIGIBLE_RHS = S::RHS == NM_RHS_MLP && !second_order<S::INTEG>() && S::Pol::NL == 0 && !S::HAS_OUTPUT && S::ND == 0 && C::shape_ok() &&
                                        C::K(0) == NX + NU && C::N(C::NL - 1) == NX;
   // (policy mode also carries an output node y = C x and an additive disturbance: both are register math of the
   // trajectory's thread)

@@ -1,6 +1,6 @@
 """
 Fixed-step explicit integrators on the hot path: ``Euler``, ``RK2``, ``RK4`` and ``Euler_Trap``,
-``RK4_Trap``, ``Luther``, ``Runge_Kutta_Fehlberg``.
+``RK4_Trap``, ``Luther``, ``Runge_Kutta_Fehlberg``, and the second-order schemes ``LeapFrog`` / ``Yoshida4``.
 
 API mirror of the reference's ``Integrator`` family (``dynamics/integrators.py``: base :14-43,
 ``Euler`` :144-156, ``RK2`` :180-193, ``RK4`` :196-211).  Inside a ``System`` an integrator node is
@@ -18,6 +18,7 @@ import warnings
 import torch.nn as nn
 
 NM_INT_EULER, NM_INT_RK4, NM_INT_RK2, NM_INT_EULER_TRAP, NM_INT_RK4_TRAP, NM_INT_LUTHER, NM_INT_RKF = 0, 1, 2, 3, 4, 5, 6
+NM_INT_LEAPFROG, NM_INT_YOSHIDA4 = 7, 8
 
 
 class Integrator(nn.Module):
@@ -139,5 +140,41 @@ class Runge_Kutta_Fehlberg(Integrator):
         return _butcher_step(self.block, x, self.h, table, [16 / 135, 0, 6656 / 12825, 28561 / 56430, -9 / 50, 2 / 55], args)
 
 
-integrators = {"Euler": Euler, "Euler_Trap": Euler_Trap, "RK2": RK2, "RK4": RK4, "RK4_Trap": RK4_Trap,
+class LeapFrog(Integrator):
+    """Leapfrog / velocity-Verlet step for ``ddx = f(x)`` on the state ``X = [x, dx]`` (reference integrators.py:340-360).
+    ``block`` maps the ``SysDim`` positions (plus inputs) to ``SysDim`` accelerations."""
+    nm_integrator_id = NM_INT_LEAPFROG
+    nm_second_order = True
+
+    def integrate(self, X, *args):
+        import torch
+        n = X.shape[-1] // 2
+        x, dx = X[:, :n], X[:, n:2 * n]
+        acc = self.block(x, *args)
+        x_new = x + dx * self.h + 0.5 * acc * self.h ** 2
+        dx_new = dx + 0.5 * (acc + self.block(x_new, *args)) * self.h
+        return torch.cat([x_new, dx_new], dim=-1)
+
+
+class Yoshida4(Integrator):
+    """4th-order Yoshida composition for ``ddx = f(x)`` on ``X = [x, dx]`` (reference integrators.py:363-404)."""
+    nm_integrator_id = NM_INT_YOSHIDA4
+    nm_second_order = True
+
+    def integrate(self, X, *args):
+        import torch
+        n = X.shape[-1] // 2
+        q, v = X[:, :n], X[:, n:2 * n]
+        w0 = -2 ** (1 / 3) / (2 - 2 ** (1 / 3))
+        w1 = 1 / (2 - 2 ** (1 / 3))
+        drift = [w1 / 2, (w0 + w1) / 2, (w0 + w1) / 2, w1 / 2]
+        kick = [w1, w0, w1]
+        for c, d in zip(drift[:3], kick):
+            q = q + c * v * self.h
+            v = v + d * self.block(q, *args) * self.h
+        q = q + drift[3] * v * self.h
+        return torch.cat([q, v], dim=-1)
+
+
+integrators = {"LeapFrog": LeapFrog, "Yoshida4": Yoshida4, "Euler": Euler, "Euler_Trap": Euler_Trap, "RK2": RK2, "RK4": RK4, "RK4_Trap": RK4_Trap,
                "Luther": Luther, "Runge_Kutta_Fehlberg": Runge_Kutta_Fehlberg}

@@ -359,7 +359,7 @@ def recognise(nodes, preview=None) -> SystemLayout:
         raise PlanError("the dynamics node must map [state, action?, disturbance?] -> [state]")
     lay.state_key, lay.dynamics = dyn.output_keys[0], dyn.callable
     fn = dyn.callable
-    lay.nx = int(fn.out_features)
+    lay.nx = int(fn.out_features) * (2 if getattr(fn, "nm_second_order", False) else 1)     # LeapFrog / Yoshida4: X = [x, dx]
 
     pol = nodes[kinds.index("policy")] if "policy" in kinds else None
     out = nodes[kinds.index("output")] if "output" in kinds else None
@@ -559,11 +559,17 @@ class RolloutPlan:
                 desc, plist = _mlp_descriptor(rhs, "MLP right-hand side")
                 if desc.bounds != L.NM_BOUNDS_NONE:
                     raise PlanError("a bounded MLP as ODE right-hand side is not fused")
-                if desc.sizes[0] != lay.nx + lay.nu or desc.sizes[desc.n_layers] != lay.nx:
+                if getattr(fn, "nm_second_order", False):
+                    # LeapFrog / Yoshida4 (reference integrators.py:340-404): X = [x, dx], the block is ddx = f(x[, u])
+                    if lay.nx % 2 or desc.sizes[0] != lay.nx // 2 + lay.nu or desc.sizes[desc.n_layers] != lay.nx // 2:
+                        raise PlanError(f"{type(fn).__name__}: the MLP right-hand side must map [x (nx/2), u] -> ddx (nx/2)")
+                elif desc.sizes[0] != lay.nx + lay.nu or desc.sizes[desc.n_layers] != lay.nx:
                     raise PlanError("MLP right-hand side must map [x, u] -> dx")
                 adopt(desc, plist)
                 p.rhs_mlp = desc
             elif isinstance(rhs, _ode.ODESystem) and rhs.nm_rhs_id is not None:
+                if getattr(fn, "nm_second_order", False):
+                    raise PlanError(f"{type(fn).__name__} integrates ddx = f(x): the white-box ODE systems are first-order")
                 p.rhs_kind = rhs.nm_rhs_id
                 for q in rhs.parameters():
                     _track(q)

@@ -234,6 +234,22 @@ def t_int_rkf_node(params, nsteps=6) -> dict:
     return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["xn"])
 
 
+def _t_second_order(params, nsteps, step):
+    """second-order neural ODE ddx = MLP([x, u]) on X = [x, dx] with a measured input (integrators.py:340-404)"""
+    f = lambda x, u: O.mlp_forward(params, torch.cat([x, u], dim=-1), "tanh")
+    nodes = [dict(fn=lambda X, u: step(f, X, 0.1, u), inputs=["xn", "U"], outputs=["xn"])]
+    terms = [_term("ref", True, "eq", 2, 1.0, lambda d: d["xn"][:, :-1, :], lambda d: d["X"])]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["xn"])
+
+
+def t_int_leapfrog_node(params, nsteps=7) -> dict:
+    return _t_second_order(params, nsteps, O.leapfrog_step)
+
+
+def t_int_yoshida_node(params, nsteps=7) -> dict:
+    return _t_second_order(params, nsteps, O.yoshida4_step)
+
+
 def t_open_duffing(params, nsteps=9) -> dict:
     a, b, dl, g, w = (_t([v], torch.zeros(1)) for v in (1.0, 5.0, 0.02, 8.0, 0.5))
     rhs = lambda x, t: O.rhs_duffing(x, t, a, b, dl, g, w)
@@ -297,7 +313,8 @@ CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_auto_brusselator": t_auto_brusselator, "t_auto_lotka": t_auto_lotka, "t_auto_lorenz": t_auto_lorenz,
          "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
          "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
-         "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd}
+         "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd,
+         "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node}
 
 
 def build(name: str, params: List[torch.Tensor], **kw) -> dict:

@@ -224,7 +224,40 @@ def rkf_step(f, x, h, *args):
     return x + h * (k1 * 16 / 135 + k3 * 6656 / 12825 + k4 * 28561 / 56430 - 9 / 50 * k5 + k6 * 2 / 55)
 
 
-INTEGRATORS = {"euler": euler_step, "rk2": rk2_step, "rk4": rk4_step, "euler_trap": euler_trap_step,
+def leapfrog_step(f, X, h, *args):
+    """``LeapFrog.integrate`` (reference dynamics/integrators.py:350-360): ddx = f(x) on X = [x, dx]"""
+    n = X.shape[-1] // 2
+    x, dx = X[:, :n], X[:, n:2 * n]
+    x_1 = x + dx * h + 0.5 * f(x, *args) * h ** 2
+    ddx_1 = f(x_1, *args)
+    dx_1 = dx + 0.5 * (f(x, *args) + ddx_1) * h
+    return torch.cat([x_1, dx_1], dim=-1)
+
+
+def yoshida4_step(f, X, h, *args):
+    """``Yoshida4.integrate`` (reference dynamics/integrators.py:373-404)"""
+    n = X.shape[-1] // 2
+    x, dx = X[:, :n], X[:, n:2 * n]
+    w0 = -2 ** (1 / 3) / (2 - 2 ** (1 / 3))
+    w1 = 1 / (2 - 2 ** (1 / 3))
+    c1 = w1 / 2
+    c4 = c1
+    c2 = (w0 + w1) / 2
+    c3 = c2
+    d1 = w1
+    d3 = d1
+    d2 = w0
+    x_1 = x + c1 * dx * h
+    dx_1 = dx + d1 * f(x_1, *args) * h
+    x_2 = x_1 + c2 * dx_1 * h
+    dx_2 = dx_1 + d2 * f(x_2, *args) * h
+    x_3 = x_2 + c3 * dx_2 * h
+    dx_3 = dx_2 + d3 * f(x_3, *args) * h
+    x_4 = x_3 + c4 * dx_3 * h
+    return torch.cat([x_4, dx_3], dim=-1)
+
+
+INTEGRATORS = {"leapfrog": leapfrog_step, "yoshida4": yoshida4_step, "euler": euler_step, "rk2": rk2_step, "rk4": rk4_step, "euler_trap": euler_trap_step,
                "rk4_trap": rk4_trap_step, "luther": luther_step, "rkf": rkf_step}
 
 

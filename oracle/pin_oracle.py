@@ -363,6 +363,25 @@ def ref_t_int_rkf_node(ns, nsteps=6):
     return problem, _mlp_params(fx), data, ["xn"], ["ref"]
 
 
+def _ref_t_second_order(ns, integ, nsteps=7):
+    fx = ns.blocks.MLP(3, 2, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh, hsizes=[16, 16])
+    model = ns.system.Node(integ(fx, h=0.1), ["xn", "U"], ["xn"], name="NODE")
+    system = ns.system.System([model], name="system")
+    v = ns.constraint.variable
+    ref = (v("xn")[:, :-1, :] == v("X")) ^ 2
+    _name([(ref, "ref")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([ref], []))
+
+    def data(B_, g):
+        X = torch.randn(B_, nsteps, 4, generator=g)
+        return {"X": X, "xn": X[:, 0:1, :].contiguous(), "U": torch.randn(B_, nsteps, 1, generator=g)}
+    return problem, _mlp_params(fx), data, ["xn"], ["ref"]
+
+
+def ref_t_int_leapfrog_node(ns): return _ref_t_second_order(ns, ns.integrators.LeapFrog)
+def ref_t_int_yoshida_node(ns): return _ref_t_second_order(ns, ns.integrators.Yoshida4)
+
+
 def ref_t_open_duffing(ns, nsteps=9):
     model = ns.system.Node(ns.integrators.RK4(_frz(ns.ode.DuffingParam()), h=0.05), ["x", "t"], ["x"], name="model")
     system = ns.system.System([model], nsteps=nsteps, name="sys")
@@ -443,6 +462,7 @@ REF_BUILDERS = {
     "t_preview_replicate": (ref_t_preview_replicate, 12), "t_preview_circular": (ref_t_preview_circular, 12),
     "t_preview_constant": (ref_t_preview_constant, 12), "t_preview_reflect": (ref_t_preview_reflect, 12),
     "t_slim_pf": (ref_t_slim_pf, 16), "t_slim_svd": (ref_t_slim_svd, 16),
+    "t_int_leapfrog_node": (ref_t_int_leapfrog_node, 12), "t_int_yoshida_node": (ref_t_int_yoshida_node, 12),
 }
 
 

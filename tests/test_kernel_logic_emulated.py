@@ -89,7 +89,9 @@ PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256"), (1, 150)),      # y = Cx no
          ("c5", ("EMU_TILE=32", "EMU_THREADS=256"), (40,)),          # 128-wide layers, weight gradients spilled to the CTA's gradient block, coupled VdP ring
          ("t_ssm_softplus", ("EMU_TILE=64", "EMU_THREADS=128"), (1, 150)),     # state after the exogenous segment, softplus derivative buffers
          ("t_preview_reflect", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),   # SystemPreview window gather with reflect padding
-         ("t_node_policy_euler", ("EMU_TILE=64", "EMU_THREADS=128"), (100,))]  # MLP policy AND MLP right-hand side
+         ("t_node_policy_euler", ("EMU_TILE=64", "EMU_THREADS=128"), (100,)),  # MLP policy AND MLP right-hand side
+         ("t_int_leapfrog_node", ("EMU_TILE=64", "EMU_THREADS=128"), (1, 100)),  # second-order scheme: positions / velocities, a0 enters twice
+         ("t_int_yoshida_node", ("EMU_TILE=64", "EMU_THREADS=128"), (100,))]     # 4th-order Yoshida composition, three evaluations
 
 
 @pytest.mark.parametrize("name,defines,batches", PLAIN, ids=[c[0] for c in PLAIN])

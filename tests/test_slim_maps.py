@@ -136,3 +136,20 @@ def test_gradients_reach_the_maps_own_parameters(name):
     opt.step()
     out2 = case.problem({**batch, "name": "train"})
     assert float(out2["train_loss"]) != float(out["train_loss"])
+
+
+@needs_reference
+@pytest.mark.parametrize("cls", ["LeapFrog", "Yoshida4"])
+def test_second_order_integrators_equal_the_reference_eagerly(cls):
+    """``LeapFrog`` / ``Yoshida4`` (reference integrators.py:340-404): the mirrored eager ``integrate`` is bit-identical to
+    the reference's on the same block; the fused lowering of the same step is covered by the t_int_*_node goldens."""
+    from neuromancer_b200.dynamics import integrators as mine
+    from neuromancer_b200.modules import blocks
+    ns = ref_shim.load()
+    torch.manual_seed(3)
+    block = blocks.MLP(3, 2, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh, hsizes=[8])
+    X, u = torch.randn(5, 4), torch.randn(5, 1)
+    got = getattr(mine, cls)(block, h=0.1)(X, u)
+    want = getattr(ns.integrators, cls)(block, h=0.1)(X, u)
+    assert torch.equal(got, want)
+    assert getattr(mine, cls).nm_second_order and mine.integrators[cls] is getattr(mine, cls)
