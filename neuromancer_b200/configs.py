@@ -534,6 +534,81 @@ def t_auto_lorenz(seed=0, nsteps=8) -> Case:
     return _t_auto("t_auto_lorenz", plant, integrators.RK4, 0.01, nsteps, 2, 0., seed, 10.0, -5.0)
 
 
+# ---- system identification: gradients w.r.t. the white-box constants (reference ode.py declares them
+# trainable nn.Parameters, examples/ODEs/Part_1_param_estim_ODE / Part_2_param_estim_ODE fit them to measured trajectories)
+def _t_sysid(name, plant, integ, h, nsteps, seed, x0_fn, u_fn=None, policy=None, norm=2) -> Case:
+    torch.manual_seed(seed)
+    nx = plant.out_features
+    if policy is not None:                       # closed loop: policy and plant constants are trained together
+        model = Node(integ(plant, h=h), ["x", "u"], ["x"], name="model")
+        system = System([Node(policy, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+        obj = (variable("x") == 0.) ^ 2
+        obj.name = "obj"
+        problem = Problem([system], PenaltyLoss([obj], []))
+        mb = lambda Bn, device, s=0: {"x": x0_fn(Bn, _gen(device, 9800 + s)).to(device), "name": "train"}
+        return Case(name, problem, system, nsteps, 100, mb, 0, 0)
+    keys = ["xn"] + (["U"] if u_fn is not None else [])
+    model = Node(integ(plant, h=h), keys, ["xn"], name="model")
+    system = System([model], name="system")                       # nsteps from data['X']
+    ref = (variable("xn")[:, :-1, :] == variable("X")) ^ norm
+    ref.name = "ref"
+    problem = Problem([system], PenaltyLoss([ref], []))
+
+    def mb(Bn, device, s=0):
+        g = _gen(device, 9800 + s)
+        x0 = x0_fn(Bn, g)
+        X = x0 + 0.1 * torch.randn(Bn, nsteps, nx, generator=g)    # "measured" trajectory around the initial condition
+        out = {"X": X.to(device), "xn": X[:, 0:1, :].contiguous().to(device), "name": "train"}
+        if u_fn is not None:
+            out["U"] = u_fn(Bn, g).to(device)
+        return out
+    return Case(name, problem, system, nsteps, 100, mb, 0, 0)
+
+
+def t_sysid_twotank(seed=0, nsteps=8) -> Case:
+    plant = ode.TwoTankParam()
+    plant.c1, plant.c2 = nn.Parameter(torch.tensor([0.08])), nn.Parameter(torch.tensor([0.04]))
+    return _t_sysid("t_sysid_twotank", plant, integrators.RK4, 1.0, nsteps, seed, lambda B, g: 0.2 + 0.5 * torch.rand(B, 1, 2, generator=g),
+                    u_fn=lambda B, g: torch.rand(B, nsteps, 2, generator=g))
+
+
+def t_sysid_lorenz(seed=0, nsteps=8) -> Case:
+    plant = ode.LorenzParam()
+    plant.rho, plant.sigma, plant.beta = (nn.Parameter(torch.tensor([v])) for v in (20.0, 8.0, 2.0))
+    return _t_sysid("t_sysid_lorenz", plant, integrators.RK4, 0.01, nsteps, seed, lambda B, g: -5.0 + 10.0 * torch.rand(B, 1, 3, generator=g))
+
+
+def t_sysid_cstr(seed=0, nsteps=6) -> Case:
+    """all ten CSTR constants trainable (they are in the reference): exercises the derived coefficient groups q/V, mdelH/(rho Cp), UA/V/rho/Cp"""
+    base = lambda B, g: torch.tensor([0.5, 330.0]) + torch.tensor([0.4, 20.0]) * torch.rand(B, 1, 2, generator=g)
+    return _t_sysid("t_sysid_cstr", ode.CSTR_Param(), integrators.Euler, 0.01, nsteps, seed, base,
+                    u_fn=lambda B, g: 290.0 + 20.0 * torch.rand(B, nsteps, 1, generator=g))
+
+
+def t_sysid_duffing(seed=0, nsteps=9) -> Case:
+    plant = ode.DuffingParam()
+    for q in plant.parameters():
+        q.requires_grad_(True)
+    tt = lambda B, g: (0.05 * torch.arange(nsteps, dtype=torch.float32)).reshape(1, nsteps, 1).repeat(B, 1, 1)
+    return _t_sysid("t_sysid_duffing", plant, integrators.RK2, 0.05, nsteps, seed, lambda B, g: torch.randn(B, 1, 2, generator=g), u_fn=tt)
+
+
+def t_sysid_brusselator(seed=0, nsteps=8) -> Case:
+    plant = ode.BrusselatorParam()
+    plant.alpha, plant.beta = nn.Parameter(torch.tensor([1.0])), nn.Parameter(torch.tensor([3.0]))
+    return _t_sysid("t_sysid_brusselator", plant, integrators.RK2, 0.05, nsteps, seed, lambda B, g: 0.5 + 2.0 * torch.rand(B, 1, 2, generator=g), norm=1)
+
+
+def t_sysid_lotka(seed=0, nsteps=8) -> Case:
+    return _t_sysid("t_sysid_lotka", ode.LotkaVolterraParam(), integrators.Euler, 0.1, nsteps, seed, lambda B, g: 0.5 + 3.0 * torch.rand(B, 1, 2, generator=g))
+
+
+def t_sysid_vdp_policy(seed=0, nsteps=10) -> Case:
+    torch.manual_seed(seed)
+    net = blocks.MLP(insize=2, outsize=1, hsizes=[16, 16], bias=True, linear_map=nn.Linear, nonlin=nn.Tanh)
+    return _t_sysid("t_sysid_vdp_policy", ode.VanDerPolControl(), integrators.RK4, 0.1, nsteps, seed, lambda B, g: torch.randn(B, 1, 2, generator=g), policy=net)
+
+
 def _t_preview(pad_mode, seed=0, nsteps=9) -> Case:
     """TwoTank tracking with a previewing policy (examples/control/Part_3_ref_tracking_ODE.py:93-105)."""
     torch.manual_seed(seed)
@@ -599,6 +674,8 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
     "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd,
     "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node,
+    "t_sysid_twotank": t_sysid_twotank, "t_sysid_lorenz": t_sysid_lorenz, "t_sysid_cstr": t_sysid_cstr, "t_sysid_duffing": t_sysid_duffing,
+    "t_sysid_brusselator": t_sysid_brusselator, "t_sysid_lotka": t_sysid_lotka, "t_sysid_vdp_policy": t_sysid_vdp_policy,
 }
 # shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
 EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index, "c4p": c4p}

@@ -161,6 +161,62 @@ struct Rhs {
   }
 };
 
+// gth[c] += sum_i w_i d f_i / d rhs_const[c]: gradient w.r.t. the white-box constants (system identification: reference
+// ode.py declares them nn.Parameters, several with requires_grad=True).  Same conventions as eval / vjp above.
+constexpr int NM_MAX_CONST = 8;
+template <class S> constexpr int rhs_num_const() {
+  return S::RHS == NM_RHS_TWOTANK ? 2 : S::RHS == NM_RHS_VDP ? 1 : S::RHS == NM_RHS_CVDP ? 2 : (S::RHS == NM_RHS_LORENZ_CTRL || S::RHS == NM_RHS_LORENZ) ? 3 :
+         S::RHS == NM_RHS_CSTR ? 7 : S::RHS == NM_RHS_DUFFING ? 5 : S::RHS == NM_RHS_BRUSSELATOR ? 2 : S::RHS == NM_RHS_LOTKA_VOLTERRA ? 1 : 0;
+}
+template <class S>
+__device__ __forceinline__ void rhs_vjp_theta(const NmPlan& p, const float (&x)[S::NX], const float (&u)[S::NU > 0 ? S::NU : 1],
+                                              const float (&w)[S::NX], float (&gth)[NM_MAX_CONST]) {
+  if constexpr (S::RHS == NM_RHS_TWOTANK) {
+    const float h1 = fminf(fmaxf(x[0], 0.f), 1.f), h2 = fminf(fmaxf(x[1], 0.f), 1.f);
+    const float pump = fminf(fmaxf(u[0], 0.f), 1.f), valve = fminf(fmaxf(u[1], 0.f), 1.f);
+    gth[0] += w[0] * ((1.0f - valve) * pump) + w[1] * (valve * pump);
+    gth[1] += (w[1] - w[0]) * sqrtf(h1) - w[1] * sqrtf(h2);
+  } else if constexpr (S::RHS == NM_RHS_VDP) {
+    gth[0] += w[1] * ((1.f - x[0] * x[0]) * x[1]);
+  } else if constexpr (S::RHS == NM_RHS_CVDP) {
+    constexpr int NO = S::NX / 2;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+      const float pos = x[2 * j], vel = x[2 * j + 1], nxt = x[2 * ((j + 1) % NO)];
+      gth[0] += w[2 * j + 1] * ((1.f - pos * pos) * vel);
+      gth[1] += w[2 * j + 1] * (nxt - pos);
+    }
+  } else if constexpr (S::RHS == NM_RHS_LORENZ_CTRL || S::RHS == NM_RHS_LORENZ) {
+    gth[0] += w[1] * x[0];
+    gth[1] += w[0] * (x[1] - x[0]);
+    gth[2] -= w[2] * x[2];
+  } else if constexpr (S::RHS == NM_RHS_CSTR) {              // constants: qV, Caf, Tf, k0, E/R, cH, cU
+    const float qV = p.rhs_const[0], Caf = p.rhs_const[1], Tf = p.rhs_const[2], k0 = p.rhs_const[3], EoverR = p.rhs_const[4], cH = p.rhs_const[5];
+    const float ex = expf(-EoverR / x[1]);
+    const float rA = k0 * ex * x[0];
+    const float g_rA = -w[0] + cH * w[1];
+    gth[0] += w[0] * (Caf - x[0]) + w[1] * (Tf - x[1]);
+    gth[1] += w[0] * qV;
+    gth[2] += w[1] * qV;
+    gth[3] += g_rA * (ex * x[0]);
+    gth[4] -= g_rA * (rA / x[1]);
+    gth[5] += w[1] * rA;
+    gth[6] += w[1] * (u[0] - x[1]);
+  } else if constexpr (S::RHS == NM_RHS_DUFFING) {
+    const float gamma = p.rhs_const[3], omega = p.rhs_const[4];
+    gth[0] -= w[1] * x[0];
+    gth[1] -= w[1] * (x[0] * x[0] * x[0]);
+    gth[2] -= w[1] * x[1];
+    gth[3] += w[1] * cosf(omega * u[0]);
+    gth[4] -= w[1] * gamma * u[0] * sinf(omega * u[0]);
+  } else if constexpr (S::RHS == NM_RHS_BRUSSELATOR) {
+    gth[0] += w[0];
+    gth[1] += (w[1] - w[0]) * x[0];
+  } else if constexpr (S::RHS == NM_RHS_LOTKA_VOLTERRA) {
+    gth[0] += w[0] * x[0];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // explicit Runge-Kutta schemes as Butcher tableaux:  xs_s = x + h * sum_{j<s} a(s,j) k_j ,  k_s = f(xs_s, u),
 // x+ = x + h * sum_s b(s) k_s.  Euler / RK2 / RK4 evaluate their stages in the reference's exact operation
@@ -452,6 +508,17 @@ struct Dyn {
   // given lam = dL/dx+ :  gx = (dx+/dx)^T lam,  gu = (dx+/du)^T lam   (gx, gu are overwritten)
   static __device__ __forceinline__ void step_vjp(const NmPlan& p, const float (&x)[NX], const float (&u)[NUA],
                                                   const float (&lam)[NX], float (&gx)[NX], float (&gu)[NUA]) {
+    float unused[NM_MAX_CONST];
+    step_vjp_impl<false>(p, x, u, lam, gx, gu, unused);
+  }
+  // the same, also accumulating the gradient w.r.t. the white-box constants into gth
+  static __device__ __forceinline__ void step_vjp_theta(const NmPlan& p, const float (&x)[NX], const float (&u)[NUA],
+                                                        const float (&lam)[NX], float (&gx)[NX], float (&gu)[NUA], float (&gth)[NM_MAX_CONST]) {
+    step_vjp_impl<true>(p, x, u, lam, gx, gu, gth);
+  }
+  template <bool THETA>
+  static __device__ __forceinline__ void step_vjp_impl(const NmPlan& p, const float (&x)[NX], const float (&u)[NUA],
+                                                       const float (&lam)[NX], float (&gx)[NX], float (&gu)[NUA], float (&gth)[NM_MAX_CONST]) {
 #pragma unroll
     for (int j = 0; j < NUA; ++j) gu[j] = 0.f;
     if constexpr (S::DYN == NM_DYN_SSM) {
@@ -489,6 +556,7 @@ struct Dyn {
 #pragma unroll
         for (int i = 0; i < NX; ++i) gxs[i] = 0.f;
         Rhs<S>::vjp(p, xs[St], u, w, gxs, gu);
+        if constexpr (THETA) rhs_vjp_theta<S>(p, xs[St], u, w, gth);
         stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
       });
     }

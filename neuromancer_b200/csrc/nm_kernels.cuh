@@ -823,6 +823,13 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
   float* grhs = gblock + (KC::HAS_RHS_MLP ? p.rhs_mlp.param_offset : 0);
   const bool pol_train = KC::HAS_POL && p.policy.trainable;
   const bool rhs_train = KC::HAS_RHS_MLP && p.rhs_mlp.trainable;
+  // trainable white-box constants (system identification): for a non-MLP right-hand side rhs_mlp.trainable / .param_offset
+  // say that -- and where in the flat gradient -- d loss / d rhs_const[0 .. NC) is wanted
+  constexpr int NC = KC::HAS_RHS_MLP ? 0 : rhs_num_const<S>();
+  const bool theta_train = NC > 0 && p.rhs_mlp.trainable;
+  float gth[NM_MAX_CONST];
+#pragma unroll
+  for (int c = 0; c < NM_MAX_CONST; ++c) gth[c] = 0.f;
 
   for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
     const int64_t b_raw = int64_t(tile) * TILE + tid;
@@ -900,7 +907,14 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
       }
       // ---- dynamics adjoint: (gx, gu) = (d x_{t+1} / d (x_t, u_t))^T lam
       if constexpr (!KC::HAS_RHS_MLP) {
-        if (owner) Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
+        if constexpr (NC > 0) {
+          if (owner) {
+            if (theta_train) Dyn<S>::step_vjp_theta(p, x, u, lam, gx, gu, gth);      // lam is zero for rows past the batch
+            else Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
+          }
+        } else {
+          if (owner) Dyn<S>::step_vjp(p, x, u, lam, gx, gu);
+        }
       } else {
         constexpr int NS = Tableau<S::INTEG>::NS, RX = KC::RX;
         const float h = p.h;
@@ -1072,6 +1086,31 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
     if (valid && args.grad_x0 != nullptr) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) args.grad_x0[b * NX + i] = lam[i];
+    }
+  }
+  // gradient of the white-box constants: fixed-order sum over the CTA's threads (deterministic) -> gradient block
+  if constexpr (NC > 0) {
+    if (theta_train) {
+      __syncthreads();                                           // everybody is done with the staging buffers
+#ifdef NM_HOST_EMU                                                // tests/emu: one block at a time, its threads are OS threads
+      static float red[(THREADS / 32) * (NC > 0 ? NC : 1)];
+#else
+      __shared__ float red[(THREADS / 32) * (NC > 0 ? NC : 1)];   // [warp][constant]
+#endif
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float v = gth[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[(tid >> 5) * NC + c] = v;
+      }
+      __syncthreads();
+      if (tid < NC) {
+        float v = 0.f;
+        for (int w = 0; w < THREADS / 32; ++w) v += red[w * NC + tid];
+        gblock[p.rhs_mlp.param_offset + tid] = v;
+      }
+      __syncthreads();
     }
   }
   // persistent accumulators -> this CTA's gradient block

@@ -521,8 +521,12 @@ int backward_fn(const NmPlan* p, NmBwdCall* c) {
     if (force != nullptr) tc_bwd = force[0] != '0';
     else if (!TB::WG3) tc_bwd = double(c->B) * double(p->nsteps) * double(TB::EVALS) >= 1048576.0;
   }
+  // trainable white-box constants (rhs_mlp.trainable on a non-MLP right-hand side): only the exact FFMA adjoint
+  // accumulates d loss / d rhs_const -- it runs whatever the batch size and whatever NM_TC_BWD says
+  const bool theta_train = !KC::HAS_RHS_MLP && rhs_num_const<NM_SPEC_NAME>() > 0 && p->rhs_mlp.trainable != 0;
+  if (theta_train) tc_bwd = false;
   // wide-policy classes: same rule (single-pass fp16 weight-gradient operands), NM_TC_BWD forces
-  bool wide_bwd = kWide && c->checkpoints != nullptr;
+  bool wide_bwd = kWide && c->checkpoints != nullptr && !theta_train;
   if (wide_bwd) {
     const char* force = getenv("NM_TC_BWD");
     if (force != nullptr) wide_bwd = force[0] != '0';

@@ -14,6 +14,8 @@ linear coupling ``kappa * (x1[j+1] - x1[j])``.
 import torch
 import torch.nn as nn
 
+from ..slim.linear import DerivedWeight
+
 NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 1, 2, 3, 4, 5
 NM_RHS_LORENZ_CTRL, NM_RHS_CSTR, NM_RHS_DUFFING, NM_RHS_BRUSSELATOR, NM_RHS_LOTKA_VOLTERRA, NM_RHS_LORENZ = 6, 7, 8, 9, 10, 11
 
@@ -51,9 +53,15 @@ class ODESystem(nn.Module):
     def ode_equations(self, x, *args):  # pragma: no cover - abstract
         raise NotImplementedError
 
+    def rhs_constants_tensor(self):
+        """The constants handed to the kernel (``NmPlan.rhs_const``) as ONE 1-d tensor, formed differentiably from the
+        module's parameters in the reference's own operation order: the kernels' gradient w.r.t. it (system identification)
+        flows on through this expression to the parameters."""
+        return torch.zeros(0)
+
     def rhs_constants(self):
-        """Constants handed to the kernel (``NmPlan.rhs_const``)."""
-        return []
+        """``rhs_constants_tensor()`` as python floats."""
+        return [float(v) for v in self.rhs_constants_tensor().detach().cpu().reshape(-1)]
 
     def forward(self, x, *args):
         assert x.dim() == 2
@@ -70,8 +78,8 @@ class TwoTankParam(ODESystem):
         self.c1 = nn.Parameter(torch.tensor([0.1]), requires_grad=True)
         self.c2 = nn.Parameter(torch.tensor([0.1]), requires_grad=True)
 
-    def rhs_constants(self):
-        return [float(self.c1), float(self.c2)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.c1.reshape(1), self.c2.reshape(1)])
 
     def ode_equations(self, x, u):
         lvl = torch.clip(x, min=0, max=1.0)
@@ -93,8 +101,8 @@ class VanDerPolControl(ODESystem):
         super().__init__(insize=insize, outsize=outsize)
         self.mu = nn.Parameter(torch.tensor([1.0]), requires_grad=True)
 
-    def rhs_constants(self):
-        return [float(self.mu)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.mu.reshape(1)])
 
     def ode_equations(self, x, u):
         pos, vel = x[:, 0:1], x[:, 1:2]
@@ -117,8 +125,8 @@ class CoupledVanDerPolControl(ODESystem):
         self.mu = nn.Parameter(torch.tensor([float(mu)]), requires_grad=False)
         self.kappa = nn.Parameter(torch.tensor([float(kappa)]), requires_grad=False)
 
-    def rhs_constants(self):
-        return [float(self.mu), float(self.kappa)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.mu.reshape(1), self.kappa.reshape(1)])
 
     def ode_equations(self, x, u):
         pos, vel = x[:, 0::2], x[:, 1::2]
@@ -137,8 +145,8 @@ class LorenzControl(ODESystem):
         self.sigma = nn.Parameter(torch.tensor([10.0]), requires_grad=True)
         self.beta = nn.Parameter(torch.tensor([2.66667]), requires_grad=True)
 
-    def rhs_constants(self):
-        return [float(self.rho), float(self.sigma), float(self.beta)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.rho.reshape(1), self.sigma.reshape(1), self.beta.reshape(1)])
 
     def ode_equations(self, x, u):
         a, b, c = x[:, 0:1], x[:, 1:2], x[:, 2:3]
@@ -155,8 +163,8 @@ class LorenzParam(ODESystem):
         self.sigma = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
         self.beta = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
 
-    def rhs_constants(self):
-        return [float(self.rho), float(self.sigma), float(self.beta)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.rho.reshape(1), self.sigma.reshape(1), self.beta.reshape(1)])
 
     def ode_equations(self, x):
         a, b, c = x[:, 0:1], x[:, 1:2], x[:, 2:3]
@@ -170,17 +178,18 @@ class CSTR_Param(ODESystem):
     def __init__(self, insize=3, outsize=2):
         super().__init__(insize=insize, outsize=outsize)
         mk = lambda v, g: nn.Parameter(torch.tensor([v]), requires_grad=g)
-        self.q, self.V, self.rho, self.Cp = mk(100.0, True), mk(100.0, False), mk(1000.0, True), mk(0.239, True)
-        self.mdelH, self.EoverR, self.k0 = mk(5e4, False), mk(8750.0, False), mk(7.2e10, False)
-        self.UA, self.Tf, self.Caf = mk(5e4, False), mk(350.0, False), mk(1.0, False)
+        # the reference writes nn.Parameter(torch.tensor([v], requires_grad=<flag>)): the inner flag is dropped, every
+        # constant of this class is a trainable Parameter there -- mirrored as it behaves
+        self.q, self.V, self.rho, self.Cp = mk(100.0, True), mk(100.0, True), mk(1000.0, True), mk(0.239, True)
+        self.mdelH, self.EoverR, self.k0 = mk(5e4, True), mk(8750.0, True), mk(7.2e10, True)
+        self.UA, self.Tf, self.Caf = mk(5e4, True), mk(350.0, True), mk(1.0, True)
 
-    def rhs_constants(self):
-        f = lambda t: float(t.detach())
+    def rhs_constants_tensor(self):
         # the coefficient groups are formed in fp32 exactly as the reference forms them per call
-        qV = f(self.q / self.V)
-        cH = f(self.mdelH / (self.rho * self.Cp))
-        cU = f(self.UA / self.V / self.rho / self.Cp)
-        return [qV, f(self.Caf), f(self.Tf), f(self.k0), f(self.EoverR), cH, cU]
+        qV = self.q / self.V
+        cH = self.mdelH / (self.rho * self.Cp)
+        cU = self.UA / self.V / self.rho / self.Cp
+        return torch.cat([t.reshape(1) for t in (qV, self.Caf, self.Tf, self.k0, self.EoverR, cH, cU)])
 
     def ode_equations(self, x, u):
         conc, temp = x[:, 0:1], x[:, 1:2]
@@ -200,8 +209,8 @@ class DuffingParam(ODESystem):
         mk = lambda v, g: nn.Parameter(torch.tensor([v]), requires_grad=g)
         self.alpha, self.beta, self.delta, self.gamma, self.omega = mk(1.0, False), mk(5.0, False), mk(0.02, False), mk(8.0, False), mk(0.5, True)
 
-    def rhs_constants(self):
-        return [float(v) for v in (self.alpha, self.beta, self.delta, self.gamma, self.omega)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.alpha.reshape(1), self.beta.reshape(1), self.delta.reshape(1), self.gamma.reshape(1), self.omega.reshape(1)])
 
     def ode_equations(self, x, u):
         pos, vel = x[:, 0:1], x[:, 1:2]
@@ -217,8 +226,8 @@ class BrusselatorParam(ODESystem):
         self.alpha = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
         self.beta = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
 
-    def rhs_constants(self):
-        return [float(self.alpha), float(self.beta)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.alpha.reshape(1), self.beta.reshape(1)])
 
     def ode_equations(self, x):
         a, b = x[:, 0:1], x[:, 1:2]
@@ -233,12 +242,30 @@ class LotkaVolterraParam(ODESystem):
         super().__init__(insize=insize, outsize=outsize)
         self.alpha = nn.Parameter(torch.tensor([1.0]), requires_grad=True)
 
-    def rhs_constants(self):
-        return [float(self.alpha)]
+    def rhs_constants_tensor(self):
+        return torch.cat([self.alpha.reshape(1)])
 
     def ode_equations(self, x):
         a, b = x[:, 0:1], x[:, 1:2]
         return torch.cat([self.alpha * a - 0.4 * a * b, 0.1 * a * b - 0.4 * b], dim=-1)
+
+
+class DerivedConstants(DerivedWeight):
+    """The constant vector of a white-box right-hand side with trainable parameters as the fused path sees it (system
+    identification; reference ode.py declares c1, c2, mu, rho ... ``nn.Parameter(requires_grad=True)``): a function of the
+    module's parameters re-evaluated differentiably on every rollout call.  The kernels read the values from
+    ``NmPlan.rhs_const`` (refreshed by the call) and write d loss / d constants into this entry's slot of the flat
+    gradient; autograd carries it on to the parameters."""
+
+    def __init__(self, module):
+        self.module = module
+        self.shape = torch.Size((len(module.rhs_constants()),))
+
+    def numel(self):
+        return self.shape[0]
+
+    def materialise(self):
+        return self.module.rhs_constants_tensor().to(torch.float32)
 
 
 ode = {"TwoTankParam": TwoTankParam, "LorenzControl": LorenzControl, "LorenzParam": LorenzParam, "CSTR_Param": CSTR_Param,

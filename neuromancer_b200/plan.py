@@ -571,15 +571,19 @@ class RolloutPlan:
                 if getattr(fn, "nm_second_order", False):
                     raise PlanError(f"{type(fn).__name__} integrates ddx = f(x): the white-box ODE systems are first-order")
                 p.rhs_kind = rhs.nm_rhs_id
-                for q in rhs.parameters():
-                    _track(q)
                 consts = rhs.rhs_constants()
                 for i, v in enumerate(consts):
                     p.rhs_const[i] = v
                 if any(q.requires_grad for q in rhs.parameters()):
-                    raise PlanError(
-                        f"{type(rhs).__name__} has trainable constants (requires_grad=True); gradients "
-                        "w.r.t. white-box ODE parameters are not fused yet -- freeze them")
+                    # system identification (reference ode.py:221-225, 357-361: the constants are trainable nn.Parameters):
+                    # the constant vector is a derived entry of the flat arena -- its values are refreshed into rhs_const on
+                    # every call (ParamArena.materialise), d loss / d rhs_const is written at rhs_mlp.param_offset by the
+                    # exact FFMA adjoint and autograd carries it on to the module's parameters
+                    p.rhs_mlp.trainable = 1
+                    adopt(p.rhs_mlp, [_ode.DerivedConstants(rhs)])
+                else:
+                    for q in rhs.parameters():
+                        _track(q)
                 if int(rhs.nu) != lay.nu:
                     raise PlanError(f"{type(rhs).__name__} expects nu={rhs.nu}, policy gives {lay.nu}")
             else:

@@ -20,6 +20,7 @@ import torch
 
 from . import _lib as L
 from .plan import PlanError, RolloutPlan
+from .dynamics.ode import DerivedConstants
 from .slim.linear import DerivedWeight
 
 _WORLD = {"size": 1}   # set by neuromancer_b200.distributed when gradients are all-reduced
@@ -56,6 +57,7 @@ class ParamArena:
         self.n = int(plan.c.n_params)
         self.flat = torch.empty(max(self.n, 1), dtype=torch.float32, device=device)
         self.slices = plan.param_slices
+        self.plan_c = plan.c
         self.adopt(plan.params)
 
     def adopt(self, params):
@@ -81,6 +83,9 @@ class ParamArena:
                 w = p.materialise().to(self.flat.device, torch.float32)
                 with torch.no_grad():
                     self.flat[off:off + n].copy_(w.reshape(-1))
+                if isinstance(p, DerivedConstants):        # the kernels read white-box constants from the plan, by value
+                    for i, v in enumerate(w.detach().cpu().reshape(-1).tolist()):
+                        self.plan_c.rhs_const[i] = v
                 out.append(w)
             else:
                 out.append(p)

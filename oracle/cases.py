@@ -282,6 +282,51 @@ def t_auto_lorenz(params, nsteps=8) -> dict:
     return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x"])
 
 
+# ---- gradients w.r.t. the white-box constants (system identification); `params` = the plant's
+# nn.Parameters in registration order (reference ode.py), each a leaf the loss is differentiated by
+def _t_sysid(params, nsteps, step, rhs, h, with_u, norm=2):
+    if with_u:
+        nodes = [dict(fn=lambda x, u: step(rhs, x, h, u), inputs=["xn", "U"], outputs=["xn"])]
+    else:
+        nodes = [dict(fn=lambda x: step(rhs, x, h), inputs=["xn"], outputs=["xn"])]
+    terms = [_term("ref", True, "eq", norm, 1.0, lambda d: d["xn"][:, :-1, :], lambda d: d["X"])]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["xn"])
+
+
+def t_sysid_twotank(params, nsteps=8) -> dict:
+    return _t_sysid(params, nsteps, O.rk4_step, lambda x, u: O.rhs_twotank(x, u, params[0], params[1]), 1.0, True)
+
+
+def t_sysid_lorenz(params, nsteps=8) -> dict:
+    return _t_sysid(params, nsteps, O.rk4_step, lambda x: O.rhs_lorenz(x, params[0], params[1], params[2]), 0.01, False)
+
+
+def t_sysid_cstr(params, nsteps=6) -> dict:
+    cc = dict(zip(("q", "V", "rho", "Cp", "mdelH", "EoverR", "k0", "UA", "Tf", "Caf"), params))
+    return _t_sysid(params, nsteps, O.euler_step, lambda x, u: O.rhs_cstr(x, u, cc), 0.01, True)
+
+
+def t_sysid_duffing(params, nsteps=9) -> dict:
+    return _t_sysid(params, nsteps, O.rk2_step, lambda x, t: O.rhs_duffing(x, t, *params[:5]), 0.05, True)
+
+
+def t_sysid_brusselator(params, nsteps=8) -> dict:
+    return _t_sysid(params, nsteps, O.rk2_step, lambda x: O.rhs_brusselator(x, params[0], params[1]), 0.05, False, norm=1)
+
+
+def t_sysid_lotka(params, nsteps=8) -> dict:
+    return _t_sysid(params, nsteps, O.euler_step, lambda x: O.rhs_lotka_volterra(x, params[0]), 0.1, False)
+
+
+def t_sysid_vdp_policy(params, nsteps=10) -> dict:
+    """closed loop: the policy (params[:-1]) and the plant's mu (params[-1]) are trained together"""
+    rhs = lambda x, u: O.rhs_vdp(x, u, params[-1])
+    nodes = [dict(fn=lambda x: O.mlp_forward(params[:-1], x, "tanh"), inputs=["x"], outputs=["u"]),
+             dict(fn=lambda x, u: O.rk4_step(rhs, x, 0.1, u), inputs=["x", "u"], outputs=["x"])]
+    terms = [_term("obj", True, "eq", 2, 1.0, lambda d: d["x"], lambda d: 0.)]
+    return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
+
+
 def _t_preview(params, nsteps, pad_mode):
     """examples/control/Part_3_ref_tracking_ODE.py:93-105 shape: TwoTank + RK4 with a policy that previews the
     reference `r` (2 signals, window L+1 = 6) and a 1-d price signal `p` (window 3); `r` is SHORTER than
@@ -314,7 +359,10 @@ CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_preview_replicate": t_preview_replicate, "t_preview_circular": t_preview_circular,
          "t_preview_constant": t_preview_constant, "t_preview_reflect": t_preview_reflect,
          "t_slim_pf": t_slim_pf, "t_slim_svd": t_slim_svd,
-         "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node}
+         "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node,
+         "t_sysid_twotank": t_sysid_twotank, "t_sysid_lorenz": t_sysid_lorenz, "t_sysid_cstr": t_sysid_cstr,
+         "t_sysid_duffing": t_sysid_duffing, "t_sysid_brusselator": t_sysid_brusselator, "t_sysid_lotka": t_sysid_lotka,
+         "t_sysid_vdp_policy": t_sysid_vdp_policy}
 
 
 def build(name: str, params: List[torch.Tensor], **kw) -> dict:

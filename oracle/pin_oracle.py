@@ -424,6 +424,75 @@ def ref_t_auto_lorenz(ns, nsteps=8):
     return _ref_t_auto(ns, plant, ns.integrators.RK4, 0.01, nsteps, 2, 0., 10.0, -5.0)
 
 
+# ---- system identification: the white-box constants are the trainable leaves (reference ode.py: nn.Parameters)
+def _ref_t_sysid(ns, plant, integ, h, nsteps, x0_fn, u_fn=None, norm=2):
+    nx = plant.out_features
+    keys = ["xn"] + (["U"] if u_fn is not None else [])
+    model = ns.system.Node(integ(plant, h=h), keys, ["xn"], name="model")
+    system = ns.system.System([model], name="system")
+    v = ns.constraint.variable
+    ref = (v("xn")[:, :-1, :] == v("X")) ^ norm
+    _name([(ref, "ref")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([ref], []))
+
+    def data(B_, g):
+        x0 = x0_fn(B_, g)
+        X = x0 + 0.1 * torch.randn(B_, nsteps, nx, generator=g)
+        out = {"X": X, "xn": X[:, 0:1, :].contiguous()}
+        if u_fn is not None:
+            out["U"] = u_fn(B_, g)
+        return out
+    return problem, list(plant.parameters()), data, ["xn"], ["ref"]
+
+
+def ref_t_sysid_twotank(ns, nsteps=8):
+    plant = ns.ode.TwoTankParam()
+    plant.c1, plant.c2 = nn.Parameter(torch.tensor([0.08])), nn.Parameter(torch.tensor([0.04]))
+    return _ref_t_sysid(ns, plant, ns.integrators.RK4, 1.0, nsteps, lambda B, g: 0.2 + 0.5 * torch.rand(B, 1, 2, generator=g),
+                        u_fn=lambda B, g: torch.rand(B, nsteps, 2, generator=g))
+
+
+def ref_t_sysid_lorenz(ns, nsteps=8):
+    plant = ns.ode.LorenzParam()
+    plant.rho, plant.sigma, plant.beta = (nn.Parameter(torch.tensor([v])) for v in (20.0, 8.0, 2.0))
+    return _ref_t_sysid(ns, plant, ns.integrators.RK4, 0.01, nsteps, lambda B, g: -5.0 + 10.0 * torch.rand(B, 1, 3, generator=g))
+
+
+def ref_t_sysid_cstr(ns, nsteps=6):
+    plant = ns.ode.CSTR_Param()                 # as shipped: all ten constants are trainable Parameters
+    base = lambda B, g: torch.tensor([0.5, 330.0]) + torch.tensor([0.4, 20.0]) * torch.rand(B, 1, 2, generator=g)
+    return _ref_t_sysid(ns, plant, ns.integrators.Euler, 0.01, nsteps, base, u_fn=lambda B, g: 290.0 + 20.0 * torch.rand(B, nsteps, 1, generator=g))
+
+
+def ref_t_sysid_duffing(ns, nsteps=9):
+    plant = ns.ode.DuffingParam()
+    for q in plant.parameters():
+        q.requires_grad_(True)
+    tt = lambda B, g: (0.05 * torch.arange(nsteps, dtype=torch.float32)).reshape(1, nsteps, 1).repeat(B, 1, 1)
+    return _ref_t_sysid(ns, plant, ns.integrators.RK2, 0.05, nsteps, lambda B, g: torch.randn(B, 1, 2, generator=g), u_fn=tt)
+
+
+def ref_t_sysid_brusselator(ns, nsteps=8):
+    plant = ns.ode.BrusselatorParam()
+    plant.alpha, plant.beta = nn.Parameter(torch.tensor([1.0])), nn.Parameter(torch.tensor([3.0]))
+    return _ref_t_sysid(ns, plant, ns.integrators.RK2, 0.05, nsteps, lambda B, g: 0.5 + 2.0 * torch.rand(B, 1, 2, generator=g), norm=1)
+
+
+def ref_t_sysid_lotka(ns, nsteps=8):
+    return _ref_t_sysid(ns, ns.ode.LotkaVolterraParam(), ns.integrators.Euler, 0.1, nsteps, lambda B, g: 0.5 + 3.0 * torch.rand(B, 1, 2, generator=g))
+
+
+def ref_t_sysid_vdp_policy(ns, nsteps=10):
+    net = ns.blocks.MLP(insize=2, outsize=1, hsizes=[16, 16], bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh)
+    plant = ns.ode.VanDerPolControl()
+    model = ns.system.Node(ns.integrators.RK4(plant, h=0.1), ["x", "u"], ["x"], name="model")
+    system = ns.system.System([ns.system.Node(net, ["x"], ["u"], name="policy"), model], nsteps=nsteps, name="sys")
+    obj = (ns.constraint.variable("x") == 0.) ^ 2
+    _name([(obj, "obj")])
+    problem = ns.problem.Problem([system], ns.loss.PenaltyLoss([obj], []))
+    return problem, _mlp_params(net) + list(plant.parameters()), (lambda B_, g: {"x": torch.randn(B_, 1, 2, generator=g)}), ["x", "u"], ["obj"]
+
+
 def _ref_t_preview(ns, pad_mode, nsteps=9):
     ode = ns.ode.TwoTankParam()
     ode.c1 = nn.Parameter(torch.tensor(0.08), requires_grad=False)
@@ -463,6 +532,9 @@ REF_BUILDERS = {
     "t_preview_constant": (ref_t_preview_constant, 12), "t_preview_reflect": (ref_t_preview_reflect, 12),
     "t_slim_pf": (ref_t_slim_pf, 16), "t_slim_svd": (ref_t_slim_svd, 16),
     "t_int_leapfrog_node": (ref_t_int_leapfrog_node, 12), "t_int_yoshida_node": (ref_t_int_yoshida_node, 12),
+    "t_sysid_twotank": (ref_t_sysid_twotank, 12), "t_sysid_lorenz": (ref_t_sysid_lorenz, 12), "t_sysid_cstr": (ref_t_sysid_cstr, 12),
+    "t_sysid_duffing": (ref_t_sysid_duffing, 12), "t_sysid_brusselator": (ref_t_sysid_brusselator, 12),
+    "t_sysid_lotka": (ref_t_sysid_lotka, 12), "t_sysid_vdp_policy": (ref_t_sysid_vdp_policy, 12),
 }
 
 

@@ -43,8 +43,9 @@ def run_emulated(name, B, exe, tmp):
     plan = case.system.plan_for(x_in, loss=case.problem.loss)
     p = plan.c
     flat = np.zeros(int(p.n_params), np.float32)
+    value = lambda q: (q.materialise() if hasattr(q, "materialise") else q).detach()    # derived entries: evaluated now
     for q, (off, n) in zip(plan.params, plan.param_slices):
-        flat[off:off + n] = q.detach().numpy().reshape(-1)
+        flat[off:off + n] = value(q).numpy().reshape(-1)
     lay = case.system.layout()
     fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
     with open(fin, "wb") as f:
@@ -68,17 +69,27 @@ def run_emulated(name, B, exe, tmp):
     traj = {lay.state_key: take(B * (T + 1) * nx).reshape(B, T + 1, nx), lay.action_key: take(B * T * nu).reshape(B, T, nu),
             lay.output_key: take(B * T * ny).reshape(B, T, ny)}
     tsum, grad = take(p.n_terms, np.float64), take(int(p.n_params))
-    ref = H.oracle_run(name, [q.detach().clone() for q in plan.params], batch)
+    # the oracle differentiates by the module parameters; a derived entry (white-box constants of a system-ID plant)
+    # stands for its module's parameters, the kernel's gradient w.r.t. it is chained through its expression
+    leaves = []
+    for q in plan.params:
+        leaves += list(q.module.parameters()) if hasattr(q, "materialise") else [q]
+    ref = H.oracle_run(name, [q.detach().clone() for q in leaves], batch)
     for k, v in ref["traj"].items():
         assert H.rel_err(torch.from_numpy(traj[k]), v) <= 1e-5, (name, B, k)
     loss = sum(p.terms[k].weight * tsum[k] / (B * p.terms[k].t_len * p.terms[k].d_len) for k in range(p.n_terms))
     assert abs(loss - float(ref["loss"].detach())) <= 1e-4 * abs(float(ref["loss"].detach())), (name, B, loss)
-    trainable = [q for q in plan.params if q.requires_grad]
+    trainable = [q for q in leaves if q.requires_grad]
+    want = lambda q: ref["grads"][[id(z) for z in trainable].index(id(q))]
     for q, (off, n) in zip(plan.params, plan.param_slices):
-        if q.requires_grad:
-            g = torch.from_numpy(grad[off:off + n]).view(q.shape)
-            r = ref["grads"][[id(z) for z in trainable].index(id(q))]
-            assert H.rel_err(g, r) <= 1e-4, (name, B, tuple(q.shape), H.rel_err(g, r))
+        g = torch.from_numpy(grad[off:off + n]).view(q.shape)
+        if hasattr(q, "materialise"):
+            mine = [z for z in q.module.parameters() if z.requires_grad]
+            for z, gz in zip(mine, torch.autograd.grad(q.materialise(), mine, grad_outputs=g, allow_unused=True)):
+                gz = torch.zeros_like(z) if gz is None else gz
+                assert H.rel_err(gz, want(z)) <= 1e-4, (name, B, "constants", H.rel_err(gz, want(z)))
+        elif q.requires_grad:
+            assert H.rel_err(g, want(q)) <= 1e-4, (name, B, tuple(q.shape), H.rel_err(g, want(q)))
 
 
 # (case, defines): tile / thread shapes as nm_spec_tu.cu picks them, weights read from the prepared global block
@@ -91,7 +102,11 @@ PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256"), (1, 150)),      # y = Cx no
          ("t_preview_reflect", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),   # SystemPreview window gather with reflect padding
          ("t_node_policy_euler", ("EMU_TILE=64", "EMU_THREADS=128"), (100,)),  # MLP policy AND MLP right-hand side
          ("t_int_leapfrog_node", ("EMU_TILE=64", "EMU_THREADS=128"), (1, 100)),  # second-order scheme: positions / velocities, a0 enters twice
-         ("t_int_yoshida_node", ("EMU_TILE=64", "EMU_THREADS=128"), (100,))]     # 4th-order Yoshida composition, three evaluations
+         ("t_int_yoshida_node", ("EMU_TILE=64", "EMU_THREADS=128"), (100,)),     # 4th-order Yoshida composition, three evaluations
+         ("t_sysid_twotank", ("EMU_TILE=128", "EMU_THREADS=128"), (1, 150)),     # gradient w.r.t. the white-box constants c1, c2 (clip / sqrt conventions)
+         ("t_sysid_cstr", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),          # ten parameters behind seven derived coefficient groups
+         ("t_sysid_duffing", ("EMU_TILE=64", "EMU_THREADS=64"), (100,)),         # cos(omega t): gradient w.r.t. a frequency
+         ("t_sysid_vdp_policy", ("EMU_TILE=128", "EMU_THREADS=128"), (150,))]    # policy weights AND the plant's mu trained together
 
 
 @pytest.mark.parametrize("name,defines,batches", PLAIN, ids=[c[0] for c in PLAIN])

@@ -369,3 +369,46 @@ def test_full_size_shard_additivity_and_determinism(name, B):
     for i, (g, a, b) in enumerate(zip(r_all["grads"], r_lo["grads"], r_hi["grads"])):
         assert torch.equal(g, r_again["grads"][i])
         assert_rel(g, 0.5 * (a + b), 2e-5, f"{name} B={B} gradient additivity, grad {i}")
+
+
+def test_white_box_constants_are_refreshed_and_identified():
+    """System identification on the fused path (reference ode.py:216-237: c1, c2 are trainable nn.Parameters; examples/ODEs
+    Part_1/2 param_estim): (a) an in-place change of a constant is seen by the next rollout (the kernels read the constants
+    by value from the plan, refreshed per call); (b) Adam on d loss / d constants, straight from the adjoint kernel, recovers
+    the constants that generated the data."""
+    case = H.make_case("t_sysid_twotank", DEV)
+    c1, c2 = case.plan_params
+    batch = to_dev(case.make_batch(512, "cpu", 11))
+    with torch.no_grad():
+        c1.fill_(0.08), c2.fill_(0.04)
+        truth = case.problem(batch)["train_xn"].clone()
+        c1.fill_(0.12)
+        moved = case.problem(batch)["train_xn"]
+        assert not torch.equal(moved, truth)                                   # (a)
+        c1.fill_(0.08)
+        assert torch.equal(case.problem(batch)["train_xn"], truth)
+        batch["X"] = truth[:, :-1, :].contiguous()
+        c1.fill_(0.12), c2.fill_(0.07)
+    opt = torch.optim.Adam([c1, c2], lr=2e-3)
+    first = None
+    for _ in range(400):
+        opt.zero_grad()
+        loss = case.problem(batch)["train_loss"]
+        loss.backward()
+        opt.step()
+        first = float(loss.detach()) if first is None else first
+    assert float(loss.detach()) < 1e-3 * first, (first, float(loss.detach()))
+    assert abs(float(c1) - 0.08) < 2e-3 and abs(float(c2) - 0.04) < 2e-3, (float(c1), float(c2))     # (b)
+
+
+def test_frozen_constants_get_no_gradient_entry():
+    """A plant whose constants are all frozen has no derived entry in the arena (and keeps the tensor-core adjoint);
+    freezing after the first call re-lowers the plan."""
+    case = H.make_case("t_sysid_lorenz", DEV)
+    batch = to_dev(case.make_batch(64, "cpu", 3))
+    out = case.problem(batch)
+    out["train_loss"].backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in case.plan_params)
+    assert case.plan().c.n_params == 3 and case.plan().c.rhs_mlp.trainable == 1
+    frozen = H.make_case("t_auto_lorenz", DEV)
+    assert frozen.plan().c.n_params == 0 and frozen.plan().c.rhs_mlp.trainable == 0

@@ -79,12 +79,30 @@ def test_misordered_nodes_and_missing_keys():
         good({"x": torch.zeros(2, 1, 2)})
 
 
-def test_trainable_white_box_constants_are_refused():
+def test_trainable_white_box_constants_become_a_derived_arena_entry():
+    """system identification (reference ode.py:357-361: mu is a trainable nn.Parameter): the constant vector is lowered as a
+    derived entry behind the policy's parameters, flagged through rhs_mlp.trainable / .param_offset; frozen constants are
+    plain plan values tracked by version"""
+    from neuromancer_b200.dynamics.ode import DerivedConstants
     plant = ode.VanDerPolControl()                          # mu requires_grad=True by default
     dyn = Node(integrators.RK4(plant, h=0.1), ["x", "u"], ["x"], name="model")
     pol = Node(blocks.MLP(2, 1, hsizes=[4], nonlin=nn.ReLU), ["x"], ["u"], name="pol")
-    with pytest.raises(PlanError, match="trainable constants"):
-        System([pol, dyn], nsteps=3).plan_for({"x": torch.zeros(2, 1, 2)})
+    system = System([pol, dyn], nsteps=3)
+    plan = system.plan_for({"x": torch.zeros(2, 1, 2)})
+    n_pol = sum(q.numel() for q in pol.callable.parameters())
+    assert isinstance(plan.params[-1], DerivedConstants) and plan.param_slices[-1] == (n_pol, 1)
+    assert plan.c.n_params == n_pol + 1 and plan.c.rhs_mlp.trainable == 1 and plan.c.rhs_mlp.param_offset == n_pol
+    w = plan.params[-1].materialise()
+    assert w.requires_grad and torch.autograd.grad(w.sum(), plant.mu)[0].item() == 1.0
+    with torch.no_grad():
+        plant.mu.add_(1.0)                                  # an optimiser step does not make the plan stale ...
+    assert not plan.values_stale()
+    plant.mu.requires_grad_(False)                          # ... frozen constants are carried by value and tracked
+    plan2 = System([pol, dyn], nsteps=3).plan_for({"x": torch.zeros(2, 1, 2)})
+    assert plan2.c.n_params == n_pol and plan2.c.rhs_mlp.trainable == 0 and plan2.c.rhs_const[0] == 2.0
+    with torch.no_grad():
+        plant.mu.add_(1.0)
+    assert plan2.values_stale()
 
 
 def test_unsupported_activation_and_structured_map():
