@@ -97,6 +97,11 @@ extern "C" {
 #define NM_RHS_BRUSSELATOR 9 /* ode.py:265-281; rhs_const = {alpha, beta}; autonomous                */
 #define NM_RHS_LOTKA_VOLTERRA 10 /* ode.py:333-349; rhs_const = {alpha}; autonomous                  */
 #define NM_RHS_LORENZ   11 /* ode.py:371-391; rhs_const = {rho, sigma, beta}; autonomous             */
+/* hybrid (grey-box) right-hand sides: a white-box equation with one unknown term m = rhs_mlp(x) (blocks.MLP 2 -> 1);  */
+/* rhs_mlp.trainable bit 0: the MLP's weights, bit 1: the constants (gradient behind the MLP's parameters)             */
+#define NM_RHS_BRUSS_HYBRID 12 /* ode.py:284-304; dx1 = alpha + m - beta x1 - x1, dx2 = beta x1 - m; rhs_const = {alpha, beta} */
+#define NM_RHS_LV_HYBRID    13 /* ode.py:307-331; dx1 = alpha x1 - beta m, dx2 = delta m - gamma x2; rhs_const = {alpha, beta, delta, gamma} */
+#define NM_RHS_HAS_MLP(k) ((k) == NM_RHS_MLP || (k) == NM_RHS_BRUSS_HYBRID || (k) == NM_RHS_LV_HYBRID)
 
 /* variables a loss-term atom can refer to */
 #define NM_VAR_CONST (-1)

@@ -22,6 +22,12 @@ NM_DYN_SSM, NM_DYN_ODE = 0, 1
 NM_INT_EULER, NM_INT_RK4, NM_INT_RK2, NM_INT_EULER_TRAP, NM_INT_RK4_TRAP, NM_INT_LUTHER, NM_INT_RKF = 0, 1, 2, 3, 4, 5, 6
 NM_INT_LEAPFROG, NM_INT_YOSHIDA4 = 7, 8
 NM_RHS_NONE, NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 0, 1, 2, 3, 4, 5
+NM_RHS_BRUSS_HYBRID, NM_RHS_LV_HYBRID = 12, 13
+
+
+def rhs_has_mlp(kind: int) -> bool:
+    """NM_RHS_HAS_MLP of include/nm_rollout.h: a neural or a hybrid (grey-box) right-hand side"""
+    return kind in (NM_RHS_MLP, NM_RHS_BRUSS_HYBRID, NM_RHS_LV_HYBRID)
 NM_VAR_CONST, NM_VAR_X, NM_VAR_U, NM_VAR_Y, NM_VAR_EXO0 = -1, 0, 1, 2, 3
 NM_OP_NONE, NM_OP_ADD, NM_OP_SUB, NM_OP_MUL = 0, 1, 2, 3
 NM_CMP_EQ, NM_CMP_LT, NM_CMP_GT = 0, 1, 2

@@ -128,6 +128,13 @@ def _adopt_rhs(ref):
         return _RHS_CONVERTERS[name](ref)
     if name in ("MLP", "MLP_bounds"):
         return _adopt_mlp(ref)
+    if name in ("BrusselatorHybrid", "LotkaVolterraHybrid") and hasattr(ref, "block"):       # grey-box: constants around an MLP
+        rhs = getattr(_ode, name)(_adopt_mlp(ref.block))
+        for k, v in ref._parameters.items():
+            if k not in rhs._parameters:
+                raise PlanError(f"{name}: constant '{k}' has no counterpart in the fused right-hand side")
+            rhs._parameters[k] = v
+        return rhs
     if name in _ODE_BY_NAME:
         rhs = _ODE_BY_NAME[name]()
         for k, v in ref._parameters.items():          # constants keep their Parameter objects (c1, c2, mu, ...)

@@ -67,7 +67,7 @@ def signature_of(p: L.NmPlan) -> str:
         s += ",".join(parts)
     integ = p.integrator if p.dyn_kind == L.NM_DYN_ODE else 0
     s += f"_out{1 if p.has_output else 0}_dyn{p.dyn_kind}_int{integ}_rhs{p.rhs_kind}"
-    if p.rhs_kind == L.NM_RHS_MLP:
+    if L.rhs_has_mlp(p.rhs_kind):
         s += _mlp_sig(p.rhs_mlp)
     nd = p.exo[p.dist_exo].width if p.dist_exo >= 0 else 0
     s += f"_dist{p.dist_exo}.{nd}_act{p.act_exo}"
@@ -178,7 +178,7 @@ def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
            f"#define NM_SPEC_NAME {name}\n", f"struct {name} {{\n",
            f"  static constexpr int NX = {p.nx}, NU = {p.nu}, NY = {p.ny}, ND = {nd};\n",
            _mlp_struct("Pol", p.policy, bool(p.has_policy)),
-           _mlp_struct("RhsM", p.rhs_mlp, p.rhs_kind == L.NM_RHS_MLP),
+           _mlp_struct("RhsM", p.rhs_mlp, L.rhs_has_mlp(p.rhs_kind)),
            f"  static constexpr bool HAS_OUTPUT = {'true' if p.has_output else 'false'};\n",
            f"  static constexpr int NSEG = {len(segs)};\n",
            _table("seg_kind", [s.kind for s in segs]),

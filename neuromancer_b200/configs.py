@@ -603,6 +603,19 @@ def t_sysid_lotka(seed=0, nsteps=8) -> Case:
     return _t_sysid("t_sysid_lotka", ode.LotkaVolterraParam(), integrators.Euler, 0.1, nsteps, seed, lambda B, g: 0.5 + 3.0 * torch.rand(B, 1, 2, generator=g))
 
 
+def t_ude_brusselator(seed=0, nsteps=6) -> Case:
+    """Universal differential equation (examples/ODEs/Part_3a_UDE.py:94-104): the Brusselator's x2*x1^2 term is an MLP."""
+    torch.manual_seed(seed)
+    net = blocks.MLP(2, 1, bias=True, linear_map=nn.Linear, nonlin=nn.GELU, hsizes=[20, 20])
+    return _t_sysid("t_ude_brusselator", ode.BrusselatorHybrid(net), integrators.RK4, 0.05, nsteps, seed, lambda B, g: 0.5 + 2.0 * torch.rand(B, 1, 2, generator=g))
+
+
+def t_ude_lotka(seed=0, nsteps=6) -> Case:
+    torch.manual_seed(seed)
+    net = blocks.MLP(2, 1, bias=True, linear_map=nn.Linear, nonlin=nn.Tanh, hsizes=[16])
+    return _t_sysid("t_ude_lotka", ode.LotkaVolterraHybrid(net), integrators.Euler, 0.1, nsteps, seed, lambda B, g: 0.5 + 3.0 * torch.rand(B, 1, 2, generator=g))
+
+
 def t_sysid_vdp_policy(seed=0, nsteps=10) -> Case:
     torch.manual_seed(seed)
     net = blocks.MLP(insize=2, outsize=1, hsizes=[16, 16], bias=True, linear_map=nn.Linear, nonlin=nn.Tanh)
@@ -676,6 +689,7 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node,
     "t_sysid_twotank": t_sysid_twotank, "t_sysid_lorenz": t_sysid_lorenz, "t_sysid_cstr": t_sysid_cstr, "t_sysid_duffing": t_sysid_duffing,
     "t_sysid_brusselator": t_sysid_brusselator, "t_sysid_lotka": t_sysid_lotka, "t_sysid_vdp_policy": t_sysid_vdp_policy,
+    "t_ude_brusselator": t_ude_brusselator, "t_ude_lotka": t_ude_lotka,
 }
 # shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
 EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index, "c4p": c4p}
@@ -697,7 +711,7 @@ def make_case(name: str, device, seed=0, **kw) -> Case:
     case.plan_params = []
     for q in plan.params:
         if hasattr(q, "materialise"):
-            case.plan_params += [t for n, t in q.module.named_parameters() if n != "bias"]
+            case.plan_params += q.own_parameters()
         else:
             case.plan_params.append(q)
     return case

@@ -48,7 +48,7 @@ int validate(const NmPlan* p) {
   if (p->nsteps < 1) { nm_set_error("nsteps must be >= 1"); return NM_ERR_BAD_PLAN; }
   if (p->n_exo < 0 || p->n_exo > NM_MAX_EXO || p->n_terms < 0 || p->n_terms > NM_MAX_TERMS || p->n_segs < 0 || p->n_segs > NM_MAX_SEGS) { nm_set_error("count field out of range"); return NM_ERR_BAD_PLAN; }
   if (p->has_policy && (p->policy.n_layers < 1 || p->policy.n_layers > NM_MAX_LAYERS)) { nm_set_error("policy layer count out of range"); return NM_ERR_BAD_PLAN; }
-  if (p->rhs_kind == NM_RHS_MLP && (p->rhs_mlp.n_layers < 1 || p->rhs_mlp.n_layers > NM_MAX_LAYERS)) { nm_set_error("rhs layer count out of range"); return NM_ERR_BAD_PLAN; }
+  if (NM_RHS_HAS_MLP(p->rhs_kind) && (p->rhs_mlp.n_layers < 1 || p->rhs_mlp.n_layers > NM_MAX_LAYERS)) { nm_set_error("rhs layer count out of range"); return NM_ERR_BAD_PLAN; }
   for (int i = 0; i < p->n_segs; ++i) {
     const NmSegment& s = p->segs[i];
     if (s.kind == NM_SEG_EXO && (s.index < 0 || s.index >= p->n_exo || p->exo[s.index].width != s.width)) { nm_set_error("policy segment refers to a bad exo input"); return NM_ERR_BAD_PLAN; }
@@ -127,7 +127,7 @@ std::string make_signature(const NmPlan* p) {
   }
   std::snprintf(buf, sizeof(buf), "_out%d_dyn%d_int%d_rhs%d", p->has_output ? 1 : 0, p->dyn_kind, p->dyn_kind == NM_DYN_ODE ? p->integrator : 0, p->rhs_kind);
   s += buf;
-  if (p->rhs_kind == NM_RHS_MLP) append_mlp(s, p->rhs_mlp);
+  if (NM_RHS_HAS_MLP(p->rhs_kind)) append_mlp(s, p->rhs_mlp);
   const int nd = p->dist_exo >= 0 ? p->exo[p->dist_exo].width : 0;
   std::snprintf(buf, sizeof(buf), "_dist%d.%d_act%d", p->dist_exo, nd, p->act_exo);
   s += buf;
@@ -445,7 +445,7 @@ int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes) {
     *bytes = size_t(B) * size_t(plan->nsteps) * size_t(e->chk_floats_per_step) * sizeof(float);
     return NM_OK;
   }
-  if (plan->dyn_kind == NM_DYN_ODE && plan->rhs_kind == NM_RHS_MLP) {
+  if (plan->dyn_kind == NM_DYN_ODE && NM_RHS_HAS_MLP(plan->rhs_kind)) {
     const int ns = integrator_stages(plan->integrator);
     *bytes = size_t(B) * size_t(plan->nsteps) * size_t(ns - 1) * size_t(plan->nx) * sizeof(float);
   }

@@ -166,7 +166,41 @@ struct Rhs {
 constexpr int NM_MAX_CONST = 8;
 template <class S> constexpr int rhs_num_const() {
   return S::RHS == NM_RHS_TWOTANK ? 2 : S::RHS == NM_RHS_VDP ? 1 : S::RHS == NM_RHS_CVDP ? 2 : (S::RHS == NM_RHS_LORENZ_CTRL || S::RHS == NM_RHS_LORENZ) ? 3 :
-         S::RHS == NM_RHS_CSTR ? 7 : S::RHS == NM_RHS_DUFFING ? 5 : S::RHS == NM_RHS_BRUSSELATOR ? 2 : S::RHS == NM_RHS_LOTKA_VOLTERRA ? 1 : 0;
+         S::RHS == NM_RHS_CSTR ? 7 : S::RHS == NM_RHS_DUFFING ? 5 : S::RHS == NM_RHS_BRUSSELATOR ? 2 : S::RHS == NM_RHS_LOTKA_VOLTERRA ? 1 :
+         S::RHS == NM_RHS_BRUSS_HYBRID ? 2 : S::RHS == NM_RHS_LV_HYBRID ? 4 : 0;
+}
+// hybrid (grey-box) right-hand sides (reference ode.py:284-331): white-box equations around one unknown term m = MLP(x)
+template <int RHS> constexpr bool rhs_hybrid() { return RHS == NM_RHS_BRUSS_HYBRID || RHS == NM_RHS_LV_HYBRID; }
+template <class S>
+__device__ __forceinline__ void hybrid_eval(const NmPlan& p, const float (&x)[2], float m, float (&dx)[2]) {
+  if constexpr (S::RHS == NM_RHS_BRUSS_HYBRID) {
+    const float alpha = p.rhs_const[0], beta = p.rhs_const[1];
+    dx[0] = ((alpha + m) - beta * x[0]) - x[0];
+    dx[1] = beta * x[0] - m;
+  } else {
+    const float alpha = p.rhs_const[0], beta = p.rhs_const[1], delta = p.rhs_const[2], gamma = p.rhs_const[3];
+    dx[0] = alpha * x[0] - beta * m;
+    dx[1] = delta * m - gamma * x[1];
+  }
+}
+// w = cotangent of dx: wm = cotangent of m, gdir = the equations' direct contribution to the cotangent of x,
+// gth += d / d rhs_const (THETA)
+template <class S, bool THETA>
+__device__ __forceinline__ void hybrid_vjp(const NmPlan& p, const float (&x)[2], float m, const float (&w)[2], float& wm, float (&gdir)[2],
+                                           float (&gth)[NM_MAX_CONST]) {
+  if constexpr (S::RHS == NM_RHS_BRUSS_HYBRID) {
+    const float beta = p.rhs_const[1];
+    wm = w[0] - w[1];
+    gdir[0] = beta * (w[1] - w[0]) - w[0];
+    gdir[1] = 0.f;
+    if constexpr (THETA) { gth[0] += w[0]; gth[1] += (w[1] - w[0]) * x[0]; }
+  } else {
+    const float alpha = p.rhs_const[0], beta = p.rhs_const[1], delta = p.rhs_const[2], gamma = p.rhs_const[3];
+    wm = delta * w[1] - beta * w[0];
+    gdir[0] = alpha * w[0];
+    gdir[1] = -gamma * w[1];
+    if constexpr (THETA) { gth[0] += w[0] * x[0]; gth[1] -= w[0] * m; gth[2] += w[1] * m; gth[3] -= w[1] * x[1]; }
+  }
 }
 template <class S>
 __device__ __forceinline__ void rhs_vjp_theta(const NmPlan& p, const float (&x)[S::NX], const float (&u)[S::NU > 0 ? S::NU : 1],

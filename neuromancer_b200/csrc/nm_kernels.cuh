@@ -93,7 +93,8 @@ struct KCfg {
   static constexpr int NX = S::NX, NU = S::NU, NY = S::NY, ND = S::ND;
   static constexpr int NUA = NU > 0 ? NU : 1, NYA = NY > 0 ? NY : 1, NDA = ND > 0 ? ND : 1;
   static constexpr bool HAS_POL = S::Pol::NL > 0;
-  static constexpr bool HAS_RHS_MLP = S::RHS == NM_RHS_MLP;
+  static constexpr bool HYB = rhs_hybrid<S::RHS>();                       // grey-box: white-box equations around m = MLP(x), 2 -> 1
+  static constexpr bool HAS_RHS_MLP = S::RHS == NM_RHS_MLP || HYB;
   static constexpr int THREADS = S::THREADS, TILE = S::TILE, LD = TILE + 4;
   // gradient is needed for the policy inputs up to the end of the last state/output segment
   static constexpr int pol_gw0() {
@@ -124,6 +125,8 @@ struct KCfg {
   // second-order integrators (LeapFrog, Yoshida4): the right-hand side maps RX = NX / 2 positions [+ NU] to RX accelerations
   static constexpr bool SO = HAS_RHS_MLP && second_order<S::INTEG>();
   static constexpr int RX = SO ? NX / 2 : NX;
+  static constexpr int RO = HYB ? 1 : RX;                                  // output width of the right-hand-side MLP
+  static_assert(!HYB || (NX == 2 && NU == 0 && !SO), "hybrid right-hand sides are autonomous two-state systems");
   static_assert(!SO || NX % 2 == 0, "second-order integrators need an even state width");
   using RhsCfg = std::conditional_t<HAS_RHS_MLP, MlpCfg<typename S::RhsM, TILE, THREADS, RX + NU>, NoMlpCfg<TILE, THREADS>>;
   static constexpr int W_FLOATS_FWD = round_up(PolCfg::FWD_W, 4) + round_up(RhsCfg::FWD_W, 4);
@@ -680,8 +683,8 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
         constexpr int RX = KC::RX;                           // width of the right-hand side's state input / output
         static_for<0, NS>([&](auto sc) {
           constexpr int St = decltype(sc)::value;
+          float xs[RX];
           if (owner) {
-            float xs[RX];
             if constexpr (KC::SO) so_position<S::INTEG, St, NX>(p.h, x, k, xs);
             else stage_input<S::INTEG, St, NX>(p.h, x, k, xs);
 #pragma unroll
@@ -693,8 +696,11 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_FWD) nm_fwd_kernel(const _
           mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, false>(Wrhs, pp0, pp1, nullptr, nullptr, p.rhs_mlp.act_param, tid);
           if (owner) {
             const float* outp = (RhsCfg::NL & 1) ? pp1 : pp0;
+            if constexpr (KC::HYB) hybrid_eval<S>(p, xs, outp[tid], k[St]);
+            else {
 #pragma unroll
-            for (int i = 0; i < RX; ++i) k[St][i] = outp[i * LD + tid];
+              for (int i = 0; i < RX; ++i) k[St][i] = outp[i * LD + tid];
+            }
             if constexpr (St + 1 < NS) {
               if (valid && args.chk != nullptr) {
                 float* cp = args.chk + ((b * T + t) * (NS - 1) + St) * NX;
@@ -822,11 +828,16 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
   float* gpol = gblock + (KC::HAS_POL ? p.policy.param_offset : 0);
   float* grhs = gblock + (KC::HAS_RHS_MLP ? p.rhs_mlp.param_offset : 0);
   const bool pol_train = KC::HAS_POL && p.policy.trainable;
-  const bool rhs_train = KC::HAS_RHS_MLP && p.rhs_mlp.trainable;
+  const bool rhs_train = KC::HAS_RHS_MLP && (p.rhs_mlp.trainable & 1);
   // trainable white-box constants (system identification): for a non-MLP right-hand side rhs_mlp.trainable / .param_offset
   // say that -- and where in the flat gradient -- d loss / d rhs_const[0 .. NC) is wanted
-  constexpr int NC = KC::HAS_RHS_MLP ? 0 : rhs_num_const<S>();
-  const bool theta_train = NC > 0 && p.rhs_mlp.trainable;
+  // (hybrid right-hand sides: bit 0 of .trainable is the MLP's weights, bit 1 the constants, stored behind the MLP's parameters)
+  constexpr int NC = (KC::HAS_RHS_MLP && !KC::HYB) ? 0 : rhs_num_const<S>();
+  const bool theta_train = NC > 0 && (KC::HYB ? (p.rhs_mlp.trainable & 2) != 0 : p.rhs_mlp.trainable != 0);
+  int theta_off = p.rhs_mlp.param_offset;
+  if constexpr (KC::HYB) {
+    for (int l = 0; l < p.rhs_mlp.n_layers; ++l) theta_off += p.rhs_mlp.sizes[l + 1] * (p.rhs_mlp.sizes[l] + (p.rhs_mlp.has_bias ? 1 : 0));
+  }
   float gth[NM_MAX_CONST];
 #pragma unroll
   for (int c = 0; c < NM_MAX_CONST; ++c) gth[c] = 0.f;
@@ -932,8 +943,8 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
               for (int i = 0; i < RX; ++i) k[St][i] = __ldg(cp + i);
             }
            } else {
+            float xs[RX];
             if (owner) {
-              float xs[RX];
               if constexpr (KC::SO) so_position<S::INTEG, St, NX>(h, x, k, xs);
               else stage_input<S::INTEG, St, NX>(h, x, k, xs);
 #pragma unroll
@@ -944,8 +955,11 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             __syncthreads();
             mlp_forward<RhsCfg, typename S::RhsM, TILE, THREADS, true>(Wrhs, nullptr, nullptr, keep_rhs, dbuf0, p.rhs_mlp.act_param, tid);
             if (owner) {
+              if constexpr (KC::HYB) hybrid_eval<S>(p, xs, dbuf0[tid], k[St]);
+              else {
 #pragma unroll
-              for (int i = 0; i < RX; ++i) k[St][i] = dbuf0[i * LD + tid];
+                for (int i = 0; i < RX; ++i) k[St][i] = dbuf0[i * LD + tid];
+              }
             }
             __syncthreads();                                     // dbuf0 is rewritten by the next stage
            }
@@ -959,8 +973,8 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
         if constexpr (KC::SO) so_adj_init<S::INTEG, NX>(h, lam, so_gq, so_gv, so_ga);
         static_for_rev<0, NS>([&](auto sc) {
           constexpr int St = decltype(sc)::value;
+          float xs[RX], gdir[RX];
           if (owner) {
-            float xs[RX];
             if constexpr (KC::SO) so_position<S::INTEG, St, NX>(h, x, k, xs);
             else stage_input<S::INTEG, St, NX>(h, x, k, xs);
 #pragma unroll
@@ -974,8 +988,19 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             float w[RX];
             if constexpr (KC::SO) so_adj_cot<S::INTEG, St, NX>(h, so_gv, so_ga, w);
             else stage_cotangent<S::INTEG, St, NX>(h, lam, gk, w);
+            if constexpr (KC::HYB) {
+              // grey-box: the stage cotangent goes through the white-box equations to the MLP's single output (rows past
+              // the batch carry w = 0: nothing reaches the weight or constant gradients)
+              float wm;
 #pragma unroll
-            for (int i = 0; i < RX; ++i) dbuf0[i * LD + tid] = valid ? w[i] : 0.f;
+              for (int i = 0; i < RX; ++i) w[i] = valid ? w[i] : 0.f;
+              if (theta_train) hybrid_vjp<S, true>(p, xs, dbuf0[tid], w, wm, gdir, gth);
+              else hybrid_vjp<S, false>(p, xs, dbuf0[tid], w, wm, gdir, gth);
+              dbuf0[tid] = wm;
+            } else {
+#pragma unroll
+              for (int i = 0; i < RX; ++i) dbuf0[i * LD + tid] = valid ? w[i] : 0.f;
+            }
           }
           __syncthreads();
           mlp_backward<RhsCfg, typename S::RhsM, TILE, THREADS, SPILL>(Wrhs, keep_rhs, dbuf0, dbuf1, rhs_dw, grhs,
@@ -985,6 +1010,10 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
             float gxs[RX];
 #pragma unroll
             for (int i = 0; i < RX; ++i) gxs[i] = gin[i * LD + tid];
+            if constexpr (KC::HYB) {
+#pragma unroll
+              for (int i = 0; i < RX; ++i) gxs[i] += gdir[i];
+            }
             if constexpr (KC::SO) so_adj_push<S::INTEG, St, NX>(h, gxs, so_gq, so_gv, so_ga);
             else stage_push<S::INTEG, St, NX>(h, gxs, gx, gk);
 #pragma unroll
@@ -1108,7 +1137,7 @@ __global__ void __launch_bounds__(S::THREADS, S::MINB_BWD) nm_bwd_kernel(const _
       if (tid < NC) {
         float v = 0.f;
         for (int w = 0; w < THREADS / 32; ++w) v += red[w * NC + tid];
-        gblock[p.rhs_mlp.param_offset + tid] = v;
+        gblock[theta_off + tid] = v;
       }
       __syncthreads();
     }

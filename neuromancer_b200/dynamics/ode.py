@@ -18,6 +18,7 @@ from ..slim.linear import DerivedWeight
 
 NM_RHS_TWOTANK, NM_RHS_VDP, NM_RHS_CVDP, NM_RHS_MLP, NM_RHS_LINEAR = 1, 2, 3, 4, 5
 NM_RHS_LORENZ_CTRL, NM_RHS_CSTR, NM_RHS_DUFFING, NM_RHS_BRUSSELATOR, NM_RHS_LOTKA_VOLTERRA, NM_RHS_LORENZ = 6, 7, 8, 9, 10, 11
+NM_RHS_BRUSS_HYBRID, NM_RHS_LV_HYBRID = 12, 13
 
 
 class SSM(nn.Module):
@@ -250,6 +251,53 @@ class LotkaVolterraParam(ODESystem):
         return torch.cat([self.alpha * a - 0.4 * a * b, 0.1 * a * b - 0.4 * b], dim=-1)
 
 
+class HybridODESystem(ODESystem):
+    """Grey-box right-hand sides: white-box equations with one unknown term ``block(x)`` (an MLP 2 -> 1) learned from data
+    next to the constants (reference ode.py:284-331)."""
+
+    def __init__(self, block, insize=2, outsize=2):
+        super().__init__(insize=insize, outsize=outsize)
+        self.block = block
+        assert self.block.in_features == 2
+        assert self.block.out_features == 1
+
+
+class BrusselatorHybrid(HybridODESystem):
+    """Brusselator with the ``x2 * x1**2`` term replaced by ``block(x)`` (reference ode.py:284-304)."""
+    nm_rhs_id = NM_RHS_BRUSS_HYBRID
+
+    def __init__(self, block, insize=2, outsize=2):
+        super().__init__(block, insize=insize, outsize=outsize)
+        self.alpha = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+        self.beta = nn.Parameter(torch.tensor([5.0]), requires_grad=True)
+
+    def rhs_constants_tensor(self):
+        return torch.cat([self.alpha.reshape(1), self.beta.reshape(1)])
+
+    def ode_equations(self, x):
+        a = x[:, 0:1]
+        m = self.block(x)
+        return torch.cat([self.alpha + m - self.beta * a - a, self.beta * a - m], dim=-1)
+
+
+class LotkaVolterraHybrid(HybridODESystem):
+    """Predator-prey model with the interaction term ``x1 * x2`` replaced by ``block(x)`` (reference ode.py:307-331)."""
+    nm_rhs_id = NM_RHS_LV_HYBRID
+
+    def __init__(self, block, insize=2, outsize=2):
+        super().__init__(block, insize=insize, outsize=outsize)
+        mk = lambda: nn.Parameter(torch.tensor([0.10]), requires_grad=True)
+        self.alpha, self.beta, self.delta, self.gamma = mk(), mk(), mk(), mk()
+
+    def rhs_constants_tensor(self):
+        return torch.cat([t.reshape(1) for t in (self.alpha, self.beta, self.delta, self.gamma)])
+
+    def ode_equations(self, x):
+        a, b = x[:, 0:1], x[:, 1:2]
+        m = self.block(x)
+        return torch.cat([self.alpha * a - self.beta * m, self.delta * m - self.gamma * b], dim=-1)
+
+
 class DerivedConstants(DerivedWeight):
     """The constant vector of a white-box right-hand side with trainable parameters as the fused path sees it (system
     identification; reference ode.py declares c1, c2, mu, rho ... ``nn.Parameter(requires_grad=True)``): a function of the
@@ -264,10 +312,14 @@ class DerivedConstants(DerivedWeight):
     def numel(self):
         return self.shape[0]
 
+    def own_parameters(self):
+        """the plant's constants (a hybrid right-hand side's ``block`` is lowered as an MLP of its own)"""
+        return [t for n, t in self.module.named_parameters() if not n.startswith("block.")]
+
     def materialise(self):
         return self.module.rhs_constants_tensor().to(torch.float32)
 
 
 ode = {"TwoTankParam": TwoTankParam, "LorenzControl": LorenzControl, "LorenzParam": LorenzParam, "CSTR_Param": CSTR_Param,
        "DuffingParam": DuffingParam, "BrusselatorParam": BrusselatorParam, "LotkaVolterraParam": LotkaVolterraParam, "VanDerPolControl": VanDerPolControl,
-       "CoupledVanDerPolControl": CoupledVanDerPolControl}
+       "CoupledVanDerPolControl": CoupledVanDerPolControl, "BrusselatorHybrid": BrusselatorHybrid, "LotkaVolterraHybrid": LotkaVolterraHybrid}

@@ -567,6 +567,31 @@ class RolloutPlan:
                     raise PlanError("MLP right-hand side must map [x, u] -> dx")
                 adopt(desc, plist)
                 p.rhs_mlp = desc
+            elif isinstance(rhs, _ode.HybridODESystem):
+                # grey-box right-hand side (reference ode.py:284-331): white-box equations around one unknown term
+                # m = block(x), an MLP 2 -> 1 evaluated by the kernels' right-hand-side stage loops
+                if getattr(fn, "nm_second_order", False):
+                    raise PlanError(f"{type(fn).__name__} integrates ddx = f(x): the hybrid ODE systems are first-order")
+                if lay.nx != 2 or lay.nu != 0:
+                    raise PlanError(f"{type(rhs).__name__} is an autonomous two-state system, got nx={lay.nx}, nu={lay.nu}")
+                if not isinstance(rhs.block, _blocks.MLP):
+                    raise PlanError(f"{type(rhs).__name__}: the unknown term must be a blocks.MLP, got {type(rhs.block).__name__}")
+                desc, plist = _mlp_descriptor(rhs.block, f"{type(rhs).__name__}.block")
+                if desc.bounds != L.NM_BOUNDS_NONE or desc.sizes[0] != 2 or desc.sizes[desc.n_layers] != 1:
+                    raise PlanError(f"{type(rhs).__name__}.block must be an unbounded MLP mapping x (2) -> 1")
+                p.rhs_kind = rhs.nm_rhs_id
+                for i, v in enumerate(rhs.rhs_constants()):
+                    p.rhs_const[i] = v
+                own = [q for n, q in rhs.named_parameters() if not n.startswith("block.")]
+                theta = any(q.requires_grad for q in own)
+                if theta:
+                    plist = plist + [_ode.DerivedConstants(rhs)]
+                else:
+                    for q in own:
+                        _track(q)
+                adopt(desc, plist)
+                desc.trainable = int(desc.trainable) | (2 if theta else 0)      # bit 0: MLP weights, bit 1: constants
+                p.rhs_mlp = desc
             elif isinstance(rhs, _ode.ODESystem) and rhs.nm_rhs_id is not None:
                 if getattr(fn, "nm_second_order", False):
                     raise PlanError(f"{type(fn).__name__} integrates ddx = f(x): the white-box ODE systems are first-order")
@@ -646,7 +671,7 @@ class RolloutPlan:
     def describe(self) -> str:
         p = self.c
         pol = [p.policy.sizes[i] for i in range(p.policy.n_layers + 1)] if p.has_policy else None
-        rhs = [p.rhs_mlp.sizes[i] for i in range(p.rhs_mlp.n_layers + 1)] if p.rhs_kind == L.NM_RHS_MLP else None
+        rhs = [p.rhs_mlp.sizes[i] for i in range(p.rhs_mlp.n_layers + 1)] if L.rhs_has_mlp(p.rhs_kind) else None
         return (f"RolloutPlan(nx={p.nx}, nu={p.nu}, ny={p.ny}, nsteps={p.nsteps}, policy={pol}, "
                 f"dyn={p.dyn_kind}, integ={p.integrator}, rhs={p.rhs_kind}, rhs_mlp={rhs}, "
                 f"exo={[(e.width, e.steps) for e in p.exo[:p.n_exo]]}, fused_terms={p.n_terms}, "

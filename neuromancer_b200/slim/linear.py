@@ -269,9 +269,13 @@ class DerivedWeight:
     def numel(self):
         return self.shape[0] * self.shape[1]
 
+    def own_parameters(self):
+        """the module Parameters this entry is a function of (the bias is a plan entry of its own)"""
+        return [t for n, t in self.module.named_parameters() if n != "bias"]
+
     @property
     def requires_grad(self):
-        return any(p.requires_grad for p in self.module.parameters())
+        return any(p.requires_grad for p in self.own_parameters())
 
     def materialise(self):
         w = self.module.effective_W()

@@ -318,6 +318,19 @@ def t_sysid_lotka(params, nsteps=8) -> dict:
     return _t_sysid(params, nsteps, O.euler_step, lambda x: O.rhs_lotka_volterra(x, params[0]), 0.1, False)
 
 
+def t_ude_brusselator(params, nsteps=6) -> dict:
+    """universal differential equation (examples/ODEs/Part_3a_UDE.py:94-104): MLP 2-20-20-1 GELU inside the Brusselator,
+    params = the MLP's W, b ... then alpha, beta"""
+    block = lambda x: O.mlp_forward(params[:-2], x, "gelu")
+    return _t_sysid(params, nsteps, O.rk4_step, lambda x: O.rhs_brusselator_hybrid(x, block, params[-2], params[-1]), 0.05, False)
+
+
+def t_ude_lotka(params, nsteps=6) -> dict:
+    """examples/ODEs/Part_3b_UDE.py: MLP inside Lotka-Volterra, params = the MLP's W, b ... then alpha, beta, delta, gamma"""
+    block = lambda x: O.mlp_forward(params[:-4], x, "tanh")
+    return _t_sysid(params, nsteps, O.euler_step, lambda x: O.rhs_lotka_volterra_hybrid(x, block, *params[-4:]), 0.1, False)
+
+
 def t_sysid_vdp_policy(params, nsteps=10) -> dict:
     """closed loop: the policy (params[:-1]) and the plant's mu (params[-1]) are trained together"""
     rhs = lambda x, u: O.rhs_vdp(x, u, params[-1])
@@ -362,7 +375,7 @@ CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node,
          "t_sysid_twotank": t_sysid_twotank, "t_sysid_lorenz": t_sysid_lorenz, "t_sysid_cstr": t_sysid_cstr,
          "t_sysid_duffing": t_sysid_duffing, "t_sysid_brusselator": t_sysid_brusselator, "t_sysid_lotka": t_sysid_lotka,
-         "t_sysid_vdp_policy": t_sysid_vdp_policy}
+         "t_sysid_vdp_policy": t_sysid_vdp_policy, "t_ude_brusselator": t_ude_brusselator, "t_ude_lotka": t_ude_lotka}
 
 
 def build(name: str, params: List[torch.Tensor], **kw) -> dict:

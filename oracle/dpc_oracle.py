@@ -152,6 +152,22 @@ def rhs_brusselator(x, alpha, beta):
     return torch.cat([alpha + x2 * x1 ** 2 - beta * x1 - x1, beta * x1 - x2 * x1 ** 2], dim=-1)
 
 
+def rhs_brusselator_hybrid(x, block, alpha, beta):
+    """``BrusselatorHybrid.ode_equations`` (reference dynamics/ode.py:299-304); ``block`` = the unknown-term MLP 2 -> 1"""
+    x1 = x[:, [0]]
+    dx1 = alpha + block(x) - beta * x1 - x1
+    dx2 = beta * x1 - block(x)
+    return torch.cat([dx1, dx2], dim=-1)
+
+
+def rhs_lotka_volterra_hybrid(x, block, alpha, beta, delta, gamma):
+    """``LotkaVolterraHybrid.ode_equations`` (reference dynamics/ode.py:325-331)"""
+    x1, x2 = x[:, [0]], x[:, [-1]]
+    dx1 = alpha * x1 - beta * block(x)
+    dx2 = delta * block(x) - gamma * x2
+    return torch.cat([dx1, dx2], dim=-1)
+
+
 def rhs_lotka_volterra(x, alpha):
     """``LotkaVolterraParam.ode_equations`` (reference dynamics/ode.py:344-349)"""
     x1, x2 = x[:, [0]], x[:, [-1]]

@@ -482,6 +482,24 @@ def ref_t_sysid_lotka(ns, nsteps=8):
     return _ref_t_sysid(ns, ns.ode.LotkaVolterraParam(), ns.integrators.Euler, 0.1, nsteps, lambda B, g: 0.5 + 3.0 * torch.rand(B, 1, 2, generator=g))
 
 
+def _own(plant):
+    return [q for n, q in plant.named_parameters() if not n.startswith("block.")]
+
+
+def ref_t_ude_brusselator(ns, nsteps=6):
+    net = ns.blocks.MLP(2, 1, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.GELU, hsizes=[20, 20])
+    plant = ns.ode.BrusselatorHybrid(net)
+    problem, _, data, tk, tn = _ref_t_sysid(ns, plant, ns.integrators.RK4, 0.05, nsteps, lambda B, g: 0.5 + 2.0 * torch.rand(B, 1, 2, generator=g))
+    return problem, _mlp_params(net) + _own(plant), data, tk, tn
+
+
+def ref_t_ude_lotka(ns, nsteps=6):
+    net = ns.blocks.MLP(2, 1, bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh, hsizes=[16])
+    plant = ns.ode.LotkaVolterraHybrid(net)
+    problem, _, data, tk, tn = _ref_t_sysid(ns, plant, ns.integrators.Euler, 0.1, nsteps, lambda B, g: 0.5 + 3.0 * torch.rand(B, 1, 2, generator=g))
+    return problem, _mlp_params(net) + _own(plant), data, tk, tn
+
+
 def ref_t_sysid_vdp_policy(ns, nsteps=10):
     net = ns.blocks.MLP(insize=2, outsize=1, hsizes=[16, 16], bias=True, linear_map=torch.nn.Linear, nonlin=torch.nn.Tanh)
     plant = ns.ode.VanDerPolControl()
@@ -535,6 +553,7 @@ REF_BUILDERS = {
     "t_sysid_twotank": (ref_t_sysid_twotank, 12), "t_sysid_lorenz": (ref_t_sysid_lorenz, 12), "t_sysid_cstr": (ref_t_sysid_cstr, 12),
     "t_sysid_duffing": (ref_t_sysid_duffing, 12), "t_sysid_brusselator": (ref_t_sysid_brusselator, 12),
     "t_sysid_lotka": (ref_t_sysid_lotka, 12), "t_sysid_vdp_policy": (ref_t_sysid_vdp_policy, 12),
+    "t_ude_brusselator": (ref_t_ude_brusselator, 12), "t_ude_lotka": (ref_t_ude_lotka, 12),
 }
 
 

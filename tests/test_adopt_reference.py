@@ -96,6 +96,31 @@ def test_reference_built_problem_lowers_to_the_same_plan(name):
         assert p is q
 
 
+@pytest.mark.parametrize("name", ["t_sysid_twotank", "t_sysid_cstr", "t_sysid_vdp_policy", "t_ude_brusselator", "t_ude_lotka"])
+def test_reference_built_identification_problem_lowers_to_the_same_plan(name):
+    """system identification / universal differential equations built with the reference's ode classes (trainable
+    nn.Parameter constants, ode.py:216-237, 284-331, 417-461): same NmPlan bytes as the native build, and the derived
+    constant entry differentiates the reference model's own Parameter objects"""
+    ref_problem, ref_params, batch = _build(name)
+    mine = adopt.from_reference(ref_problem)
+    system = [n for n in mine.nodes if hasattr(n, "plan_for")][0]
+    plan = system.plan_for(system.init(dict(batch)), loss=mine.loss)
+    want_case = configs.build_case(name)
+    with torch.no_grad():                                           # same values: the plan carries the constants by value
+        flat = []
+        for q in want_case.plan().params:
+            flat += q.own_parameters() if hasattr(q, "materialise") else [q]
+        for dst, src in zip(flat, ref_params):
+            dst.copy_(src)
+    want = want_case.system.plan_for(want_case.system.init(dict(batch)), loss=want_case.problem.loss)
+    assert bytes(plan.c) == bytes(want.c)
+    leaves = []
+    for q in plan.params:
+        leaves += q.own_parameters() if hasattr(q, "materialise") else [q]
+    assert len(leaves) == len(ref_params) and all(a is b for a, b in zip(leaves, ref_params))
+    assert plan.c.rhs_mlp.trainable in (1, 3)
+
+
 def test_adopted_constraint_values_match_the_reference_on_cpu():
     """the adopted loss terms evaluate (eagerly, torch CPU) to what the reference's own Constraint objects give"""
     ref_problem, _, batch = _build("c2")
@@ -115,7 +140,7 @@ def test_adopted_constraint_values_match_the_reference_on_cpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c2", "c5", "t_slim_pf"])
+@pytest.mark.parametrize("name", ["c2", "c5", "t_slim_pf", "t_sysid_cstr", "t_ude_brusselator"])
 def test_reference_built_problem_runs_on_the_fused_kernels(name):
     """End of the drop-in chain on a GPU box (oracle/_ref travels with the snapshot): a problem built with the reference's
     classes, adopted, run through nmfused::rollout_fwd / rollout_bwd, against the golden recorded from the SAME reference

@@ -73,7 +73,7 @@ def run_emulated(name, B, exe, tmp):
     # stands for its module's parameters, the kernel's gradient w.r.t. it is chained through its expression
     leaves = []
     for q in plan.params:
-        leaves += list(q.module.parameters()) if hasattr(q, "materialise") else [q]
+        leaves += q.own_parameters() if hasattr(q, "materialise") else [q]
     ref = H.oracle_run(name, [q.detach().clone() for q in leaves], batch)
     for k, v in ref["traj"].items():
         assert H.rel_err(torch.from_numpy(traj[k]), v) <= 1e-5, (name, B, k)
@@ -84,7 +84,7 @@ def run_emulated(name, B, exe, tmp):
     for q, (off, n) in zip(plan.params, plan.param_slices):
         g = torch.from_numpy(grad[off:off + n]).view(q.shape)
         if hasattr(q, "materialise"):
-            mine = [z for z in q.module.parameters() if z.requires_grad]
+            mine = [z for z in q.own_parameters() if z.requires_grad]
             for z, gz in zip(mine, torch.autograd.grad(q.materialise(), mine, grad_outputs=g, allow_unused=True)):
                 gz = torch.zeros_like(z) if gz is None else gz
                 assert H.rel_err(gz, want(z)) <= 1e-4, (name, B, "constants", H.rel_err(gz, want(z)))
@@ -106,7 +106,9 @@ PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256"), (1, 150)),      # y = Cx no
          ("t_sysid_twotank", ("EMU_TILE=128", "EMU_THREADS=128"), (1, 150)),     # gradient w.r.t. the white-box constants c1, c2 (clip / sqrt conventions)
          ("t_sysid_cstr", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),          # ten parameters behind seven derived coefficient groups
          ("t_sysid_duffing", ("EMU_TILE=64", "EMU_THREADS=64"), (100,)),         # cos(omega t): gradient w.r.t. a frequency
-         ("t_sysid_vdp_policy", ("EMU_TILE=128", "EMU_THREADS=128"), (150,))]    # policy weights AND the plant's mu trained together
+         ("t_sysid_vdp_policy", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),    # policy weights AND the plant's mu trained together
+         ("t_ude_brusselator", ("EMU_TILE=64", "EMU_THREADS=128"), (1, 100)),    # grey-box: MLP 2-20-20-1 inside the Brusselator, weights + alpha, beta
+         ("t_ude_lotka", ("EMU_TILE=64", "EMU_THREADS=128"), (100,))]            # grey-box Lotka-Volterra, four constants next to the MLP
 
 
 @pytest.mark.parametrize("name,defines,batches", PLAIN, ids=[c[0] for c in PLAIN])
