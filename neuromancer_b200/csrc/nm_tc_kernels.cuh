@@ -1311,6 +1311,18 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
 // interleaved operand tile  A[k/4][row][k%4]  (raw fp32 = the tf32 "hi" part once the tensor core has truncated it)
 // and its exact remainder tile, one elected lane issues the 3-product MMAs (remainder products first) into a
 // 32-column accumulator, and the epilogue writes the row back with the bias added.
+// exogenous segments in plan order: the first one, and the one after segment s (-1: none)
+template <class S> constexpr int exo_first_seg() { for (int i = 0; i < S::NSEG; ++i) if (S::seg_kind(i) == NM_SEG_EXO) return i; return -1; }
+template <class S> constexpr int exo_next_seg(int s) { for (int i = s + 1; i < S::NSEG; ++i) if (S::seg_kind(i) == NM_SEG_EXO) return i; return -1; }
+// this thread's row slice of exogenous segment s -> registers (all loads in flight at once; the row slice is 4 * PF bytes)
+template <class S, int s, int PF>
+__device__ __forceinline__ void exo_row_prefetch(const NmPlan& p, const ExoPtrs& exo, int64_t b, int t, float4 (&pre)[PF]) {
+  constexpr int W = S::seg_width(s), e = S::seg_index(s);
+  const float* __restrict__ src = exo.p[e] + (b * p.exo[e].steps + t) * W;
+#pragma unroll
+  for (int k4 = 0; k4 < W / 4; ++k4) pre[k4] = __ldg(reinterpret_cast<const float4*>(src + k4 * 4));
+}
+
 template <class S>
 struct ExoTcCfg {
   using KC = KCfg<S>;
@@ -1369,6 +1381,14 @@ __global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_fwd_kernel(const __grid
   const int64_t R = B * p.nsteps;
   const int64_t tiles = (R + 127) / 128;
   constexpr uint32_t idesc = tc::idesc_tf32(128, NP);
+  // software pipeline: the row slice of the NEXT segment (of the next tile after the last one) is loaded into registers
+  // while the tensor pipe works on the current one -- every load of a slice in flight at once
+  constexpr int PF = X::wmax() / 4, S0 = exo_first_seg<S>();
+  float4 pre[PF];
+  {
+    const int64_t r0 = int64_t(blockIdx.x) * 128 + tid < R ? int64_t(blockIdx.x) * 128 + tid : R - 1;
+    exo_row_prefetch<S, S0, PF>(p, exo, r0 / p.nsteps, int(r0 % p.nsteps), pre);
+  }
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t r = tile * 128 + tid < R ? tile * 128 + tid : R - 1;
     const int64_t b = r / p.nsteps;
@@ -1376,18 +1396,22 @@ __global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_fwd_kernel(const __grid
     static_for<0, S::NSEG>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
       if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
-        constexpr int W = S::seg_width(s), e = S::seg_index(s), OFF = exo_seg_off<S>(s), WP = round_up(W, 8);
-        const float* __restrict__ src = exo.p[e] + (b * p.exo[e].steps + t) * W;
-#pragma unroll 4
+        constexpr int W = S::seg_width(s), OFF = exo_seg_off<S>(s), WP = round_up(W, 8);
+#pragma unroll
         for (int k4 = 0; k4 < WP / 4; ++k4) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k4 * 4 < W) v = __ldg(reinterpret_cast<const float4*>(src + k4 * 4));
+          if (k4 * 4 < W) v = pre[k4];
           // the tensor core reads the hi tile truncated to tf32: the remainder is taken against the truncated value
           float4 l;
           l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
           l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
           *reinterpret_cast<float4*>(a_hi + (k4 * 128 + tid) * 4) = v;
           *reinterpret_cast<float4*>(a_lo + (k4 * 128 + tid) * 4) = l;
+        }
+        if constexpr (exo_next_seg<S>(s) >= 0) exo_row_prefetch<S, exo_next_seg<S>(s), PF>(p, exo, b, t, pre);
+        else if (tile + gridDim.x < tiles) {
+          const int64_t rn = (tile + gridDim.x) * 128 + tid < R ? (tile + gridDim.x) * 128 + tid : R - 1;
+          exo_row_prefetch<S, S0, PF>(p, exo, rn / p.nsteps, int(rn % p.nsteps), pre);
         }
         tc::fence_async_smem();
         tc::fence_before();
@@ -1521,6 +1545,21 @@ __global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_bwd_kernel(const __grid
     });
   };
   int since_flush = 0;
+  // software pipeline (as in the forward GEMM): the next segment's row slice and the next tile's dZ_1 row are loaded into
+  // registers while the tensor pipe contracts the current one
+  constexpr int PF = X::rx() / 4, S0 = exo_first_seg<S>(), PD = N0 / 4;
+  static_assert(N0 % 4 == 0, "hoisted first layer: N0 % 4 == 0 (KCfg::hoist_ok)");
+  float4 pre[PF], pre_d[PD];
+  auto dz_prefetch = [&](int64_t tile_) {
+    const bool ok = tile_ * 128 + tid < R;
+#pragma unroll
+    for (int n4 = 0; n4 < PD; ++n4) pre_d[n4] = ok ? __ldg(reinterpret_cast<const float4*>(dZ1 + (tile_ * 128 + tid) * N0 + n4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (int64_t(blockIdx.x) < tiles) {
+    const int64_t r0 = int64_t(blockIdx.x) * 128 + tid < R ? int64_t(blockIdx.x) * 128 + tid : R - 1;
+    dz_prefetch(blockIdx.x);
+    exo_row_prefetch<S, S0, PF>(p, exo, r0 / p.nsteps, int(r0 % p.nsteps), pre);
+  }
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const bool valid = tile * 128 + tid < R;
     const int64_t r = valid ? tile * 128 + tid : R - 1;
@@ -1528,21 +1567,25 @@ __global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_bwd_kernel(const __grid
     const int t = int(r - b * p.nsteps);
     const bool fresh = since_flush == 0;
     // DT <- dZ_1 rows (zero for rows past the end: they contribute nothing)
-#pragma unroll 2
-    for (int n4 = 0; n4 < N0; n4 += 4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) v = __ldg(reinterpret_cast<const float4*>(dZ1 + r * N0 + n4));
-      tstore(0, X::RD, n4 + 0, v.x); tstore(0, X::RD, n4 + 1, v.y); tstore(0, X::RD, n4 + 2, v.z); tstore(0, X::RD, n4 + 3, v.w);
+#pragma unroll
+    for (int n4 = 0; n4 < PD; ++n4) {
+      const float4 v = pre_d[n4];
+      tstore(0, X::RD, n4 * 4 + 0, v.x); tstore(0, X::RD, n4 * 4 + 1, v.y); tstore(0, X::RD, n4 * 4 + 2, v.z); tstore(0, X::RD, n4 * 4 + 3, v.w);
     }
+    if (tile + gridDim.x < tiles) dz_prefetch(tile + gridDim.x);
     static_for<0, S::NSEG>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
       if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
-        constexpr int W = S::seg_width(s), e = S::seg_index(s), RX = X::rx();
-        const float* __restrict__ src = exo.p[e] + (b * p.exo[e].steps + t) * W;
-#pragma unroll 2
-        for (int k4 = 0; k4 < W; k4 += 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + k4));
-          tstore(X::DT_BYTES, RX, k4 + 0, v.x); tstore(X::DT_BYTES, RX, k4 + 1, v.y); tstore(X::DT_BYTES, RX, k4 + 2, v.z); tstore(X::DT_BYTES, RX, k4 + 3, v.w);
+        constexpr int W = S::seg_width(s), RX = X::rx();
+#pragma unroll
+        for (int k4 = 0; k4 < W / 4; ++k4) {
+          const float4 v = pre[k4];
+          tstore(X::DT_BYTES, RX, k4 * 4 + 0, v.x); tstore(X::DT_BYTES, RX, k4 * 4 + 1, v.y); tstore(X::DT_BYTES, RX, k4 * 4 + 2, v.z); tstore(X::DT_BYTES, RX, k4 * 4 + 3, v.w);
+        }
+        if constexpr (exo_next_seg<S>(s) >= 0) exo_row_prefetch<S, exo_next_seg<S>(s), PF>(p, exo, b, t, pre);
+        else if (tile + gridDim.x < tiles) {
+          const int64_t rn = (tile + gridDim.x) * 128 + tid < R ? (tile + gridDim.x) * 128 + tid : R - 1;
+          exo_row_prefetch<S, S0, PF>(p, exo, rn / p.nsteps, int(rn % p.nsteps), pre);
         }
         tc::fence_async_smem();
         tc::fence_before();

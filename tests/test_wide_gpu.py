@@ -107,10 +107,11 @@ def test_c5_wide_adjoint_matches_exact_adjoint_at_scale_and_is_deterministic():
 
 
 # ------------------------------------------------------------------------------------------------ bench-size parity
-@pytest.mark.parametrize("name,B", [("c2", 65536), ("c3", 16384), ("c5", 5376)])
+@pytest.mark.parametrize("name,B", [("c2", 65536), ("c3", 16384), ("c4", 16384), ("c5", 5376)])
 def test_dispatcher_choice_at_bench_size_matches_the_oracle(name, B):
     """No forcing: whatever kernels the library picks at this size (c2: tcgen05 policy-mode adjoint with single-pass TF32
-    weight gradients; c3: tcgen05 RHS-mode adjoint; c5: wide adjoint, B * nsteps >= 2^20) against the CPU oracle on
+    weight gradients; c3: tcgen05 RHS-mode adjoint; c4: both first-layer hoist GEMMs on the tensor cores, B * nsteps >= 2^20 rows;
+    c5: wide adjoint, B * nsteps >= 2^20) against the CPU oracle on
     the same weights and inputs -- trajectories per time slice, loss, every gradient tensor element-wise."""
     case = H.make_case(name, DEV, seed=6)
     batch_cpu = case.make_batch(B, "cpu", 31)
