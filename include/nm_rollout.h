@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NM_ABI_VERSION 6
+#define NM_ABI_VERSION 7
 
 #define NM_MAX_LAYERS 8   /* linear layers per MLP                                   */
 #define NM_MAX_SEGS   8   /* concatenated inputs of the policy (blocks.py:39-43)     */
@@ -103,6 +103,18 @@ extern "C" {
 #define NM_RHS_LV_HYBRID    13 /* ode.py:307-331; dx1 = alpha x1 - beta m, dx2 = delta m - gamma x2; rhs_const = {alpha, beta, delta, gamma} */
 #define NM_RHS_HAS_MLP(k) ((k) == NM_RHS_MLP || (k) == NM_RHS_BRUSS_HYBRID || (k) == NM_RHS_LV_HYBRID)
 
+/* BarrierLoss (reference loss.py:184-257): an entry of a constraint with value v < 0 (satisfied) contributes
+ * clamp(barrier(v), 0, ub) (nan / +inf -> 0) instead of nothing, an entry with v >= 0 its penalty as before */
+#define NM_BARRIER_NONE     0
+#define NM_BARRIER_LOG10    1 /* -log10(-v)                                */
+#define NM_BARRIER_LOG      2 /* -log(-v)                                  */
+#define NM_BARRIER_INVERSE  3 /* 1 / (-v)                                  */
+#define NM_BARRIER_SOFTEXP  4 /* (exp(alpha v) - 1) / alpha + alpha        */
+#define NM_BARRIER_SOFTLOG  5 /* -log(1 + alpha (-v - alpha)) / alpha      */
+#define NM_BARRIER_EXPSHIFT 6 /* exp(v + shift)                            */
+#define NM_TERM_NORM(n)    ((n) & 15)
+#define NM_TERM_BARRIER(n) (((n) >> 4) & 15)
+
 /* variables a loss-term atom can refer to */
 #define NM_VAR_CONST (-1)
 #define NM_VAR_X      0   /* state trajectory   [B, nsteps+1, nx] */
@@ -165,7 +177,7 @@ typedef struct NmSide {
  * (reference constraint.py:307-324, loss.py:61-108) */
 typedef struct NmTerm {
   int32_t cmp;           /* NM_CMP_*                                  */
-  int32_t norm;          /* 1 or 2 (Constraint.__xor__)               */
+  int32_t norm;          /* bits 0-3: 1 or 2 (Constraint.__xor__); bits 4-7: NM_BARRIER_* of a BarrierLoss constraint (0: none) */
   float   weight;
   int32_t is_objective;  /* listed under objectives (else constraint) */
   int32_t t_len, d_len;  /* broadcast element shape per trajectory    */
@@ -200,6 +212,10 @@ typedef struct NmPlan {
   int64_t n_params;          /* total floats in params_flat                    */
   int32_t pad_mode;          /* NM_PAD_* for NM_SEG_PREVIEW segments           */
   float   pad_value;         /* NM_PAD_CONSTANT fill value                     */
+  float   barrier_alpha;     /* BarrierLoss(alpha=): softexp / softlog bending  (loss.py:196-214) */
+  float   barrier_shift;     /* BarrierLoss(shift=): expshift                                      */
+  float   barrier_ub;        /* BarrierLoss(upper_bound=): the barrier value is clamped to [0, ub] */
+  int32_t reserved0;
 } NmPlan;
 
 /* Library / build identification. */

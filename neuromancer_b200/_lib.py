@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-NM_ABI_VERSION = 6
+NM_ABI_VERSION = 7
 NM_MAX_LAYERS, NM_MAX_SEGS, NM_MAX_EXO, NM_MAX_TERMS, NM_MAX_DIM = 8, 8, 8, 16, 16
 
 NM_OK, NM_ERR_BAD_PLAN, NM_ERR_NO_KERNEL, NM_ERR_CUDA, NM_ERR_WORKSPACE, NM_ERR_ABI = 0, -1, -2, -3, -4, -5
@@ -31,6 +31,7 @@ def rhs_has_mlp(kind: int) -> bool:
 NM_VAR_CONST, NM_VAR_X, NM_VAR_U, NM_VAR_Y, NM_VAR_EXO0 = -1, 0, 1, 2, 3
 NM_OP_NONE, NM_OP_ADD, NM_OP_SUB, NM_OP_MUL = 0, 1, 2, 3
 NM_CMP_EQ, NM_CMP_LT, NM_CMP_GT = 0, 1, 2
+NM_BARRIERS = {"log10": 1, "log": 2, "inverse": 3, "softexp": 4, "softlog": 5, "expshift": 6}
 
 
 class NmMlp(C.Structure):
@@ -76,7 +77,8 @@ class NmPlan(C.Structure):
                 ("rhs_mlp", NmMlp), ("A", _MAT), ("Bm", _MAT), ("E", _MAT), ("C", _MAT),
                 ("n_exo", C.c_int32), ("exo", NmExo * NM_MAX_EXO), ("n_terms", C.c_int32),
                 ("terms", NmTerm * NM_MAX_TERMS), ("n_params", C.c_int64),
-                ("pad_mode", C.c_int32), ("pad_value", C.c_float)]
+                ("pad_mode", C.c_int32), ("pad_value", C.c_float),
+                ("barrier_alpha", C.c_float), ("barrier_shift", C.c_float), ("barrier_ub", C.c_float), ("reserved0", C.c_int32)]
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -308,6 +308,29 @@ def t_slim_svd(seed=0, nsteps=12) -> Case:
     return t_vdp_rk4_tanh_clamp(seed=seed, nsteps=nsteps, linear_map=slim.SVDLinear, name="t_slim_svd")
 
 
+def _t_barrier(barrier, seed=0, nsteps=12) -> Case:
+    """the tanh-clamp problem under a BarrierLoss (reference loss.py:184-257): box constraints on state and action"""
+    from .loss import BarrierLoss
+    case = t_vdp_rk4_tanh_clamp(seed=seed, nsteps=nsteps, name=f"t_barrier_{barrier}")
+    x, r, u = variable("x"), variable("r"), variable("u")
+    obj = 3. * ((x == r) ^ 2)
+    hi = 2. * ((x < 1.5) ^ 2)
+    lo = 1. * (x > -1.5)
+    umax = 0.5 * (u < 0.8)
+    for t_, n_ in ((obj, "obj"), (hi, "hi"), (lo, "lo"), (umax, "umax")):
+        t_.name = n_
+    case.problem = Problem([case.system], BarrierLoss([obj], [hi, lo, umax], barrier=barrier, upper_bound=2.0, shift=0.7, alpha=0.4))
+    return case
+
+
+def t_barrier_log10(seed=0, **kw): return _t_barrier("log10", seed, **kw)
+def t_barrier_log(seed=0, **kw): return _t_barrier("log", seed, **kw)
+def t_barrier_inverse(seed=0, **kw): return _t_barrier("inverse", seed, **kw)
+def t_barrier_softexp(seed=0, **kw): return _t_barrier("softexp", seed, **kw)
+def t_barrier_softlog(seed=0, **kw): return _t_barrier("softlog", seed, **kw)
+def t_barrier_expshift(seed=0, **kw): return _t_barrier("expshift", seed, **kw)
+
+
 def t_vdp_euler_elu(seed=0, nsteps=9) -> Case:
     torch.manual_seed(seed)
     plant = ode.VanDerPolControl()
@@ -690,6 +713,8 @@ CASES: Dict[str, Callable[..., Case]] = {
     "t_sysid_twotank": t_sysid_twotank, "t_sysid_lorenz": t_sysid_lorenz, "t_sysid_cstr": t_sysid_cstr, "t_sysid_duffing": t_sysid_duffing,
     "t_sysid_brusselator": t_sysid_brusselator, "t_sysid_lotka": t_sysid_lotka, "t_sysid_vdp_policy": t_sysid_vdp_policy,
     "t_ude_brusselator": t_ude_brusselator, "t_ude_lotka": t_ude_lotka,
+    "t_barrier_log10": t_barrier_log10, "t_barrier_log": t_barrier_log, "t_barrier_inverse": t_barrier_inverse,
+    "t_barrier_softexp": t_barrier_softexp, "t_barrier_softlog": t_barrier_softlog, "t_barrier_expshift": t_barrier_expshift,
 }
 # shape classes compiled ahead of time that have no oracle / golden counterpart (special-purpose probes)
 EXTRA_CASES: Dict[str, Callable[..., Case]] = {"t_preview_index": t_preview_index, "c4p": c4p}

@@ -66,7 +66,10 @@ int validate(const NmPlan* p) {
   const int D[3] = {p->nx, p->nu, p->ny};
   for (int k = 0; k < p->n_terms; ++k) {
     const NmTerm& t = p->terms[k];
-    if (t.norm != 1 && t.norm != 2) { nm_set_error("term norm must be 1 or 2"); return NM_ERR_BAD_PLAN; }
+    if ((NM_TERM_NORM(t.norm) != 1 && NM_TERM_NORM(t.norm) != 2) || NM_TERM_BARRIER(t.norm) > NM_BARRIER_EXPSHIFT || (t.norm >> 8) != 0 ||
+        (NM_TERM_BARRIER(t.norm) != NM_BARRIER_NONE && t.is_objective)) {
+      nm_set_error("term norm must be 1 or 2 (+ a barrier kind in bits 4-7, constraints only)"); return NM_ERR_BAD_PLAN;
+    }
     if (t.t_len < 1 || t.d_len < 1) { nm_set_error("term element shape invalid"); return NM_ERR_BAD_PLAN; }
     const NmAtom* atoms[4] = {&t.lhs.a, &t.lhs.b, &t.rhs.a, &t.rhs.b};
     const bool live[4] = {true, t.lhs.op != NM_OP_NONE, true, t.rhs.op != NM_OP_NONE};
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kScoreThreads) nm_term_score_kernel(const __gr
       const int te = int(idx - b * tmax);
       if (te < tm.t_len) {
         const nm::TermRef r = nm::term_ref(tm, vt, b, te);
-        for (int de = 0; de < tm.d_len; ++de) ts += nm::term_penalty(tm, nm::term_value_ref(tm, r, de));
+        for (int de = 0; de < tm.d_len; ++de) ts += nm::term_penalty(plan, tm, nm::term_value_ref(tm, r, de));
       }
     }
     double v = static_cast<double>(ts);

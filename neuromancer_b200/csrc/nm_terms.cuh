@@ -54,25 +54,48 @@ __device__ __forceinline__ float term_value(const NmTerm& tm, const VarTable& vt
   return tm.cmp == NM_CMP_GT ? r - l : l - r;
 }
 
-__device__ __forceinline__ float term_penalty(const NmTerm& tm, float v) {
-  if (tm.cmp == NM_CMP_EQ) return tm.norm == 1 ? fabsf(v) : v * v;
+// BarrierLoss entries with value v < 0 (reference loss.py:196-214, 240-246): barrier(v), nan / +inf -> 0, clamped to
+// [0, ub]; `df` = its derivative with autograd's conventions (the masked assignments and the clamp outside [0, ub] pass none)
+__device__ __forceinline__ float barrier_eval(const NmPlan& p, int kind, float v, float& df) {
+  const float a = p.barrier_alpha;
+  float f;
+  switch (kind) {
+    case NM_BARRIER_LOG10:    f = -log10f(-v); df = -0.4342944819032518f / v; break;
+    case NM_BARRIER_LOG:      f = -logf(-v); df = -1.f / v; break;
+    case NM_BARRIER_INVERSE:  f = 1.f / (-v); df = 1.f / (v * v); break;
+    case NM_BARRIER_SOFTEXP:  { const float e = expf(a * v); f = (e - 1.f) / a + a; df = e; } break;
+    case NM_BARRIER_SOFTLOG:  { const float q = 1.f + a * (-v - a); f = -logf(q) / a; df = 1.f / q; } break;
+    default:                  f = expf(v + p.barrier_shift); df = f; break;
+  }
+  if (!(f == f) || f == INFINITY) { f = 0.f; df = 0.f; }
+  if (f < 0.f) { f = 0.f; df = 0.f; }
+  else if (f > p.barrier_ub) { f = p.barrier_ub; df = 0.f; }
+  return f;
+}
+
+__device__ __forceinline__ float term_penalty(const NmPlan& pl, const NmTerm& tm, float v) {
+  const int norm = NM_TERM_NORM(tm.norm), bk = NM_TERM_BARRIER(tm.norm);
+  if (bk != NM_BARRIER_NONE && !(v >= 0.f)) { float df; return barrier_eval(pl, bk, v, df); }
+  if (tm.cmp == NM_CMP_EQ) return norm == 1 ? fabsf(v) : v * v;
   const float p = v > 0.f ? v : 0.f;
-  return tm.norm == 1 ? p : p * p;
+  return norm == 1 ? p : p * p;
 }
 
 // d penalty / d value with autograd's conventions: relu'(0) = 0, sign(0) = 0
-__device__ __forceinline__ float term_dpenalty(const NmTerm& tm, float v) {
-  if (tm.cmp == NM_CMP_EQ) return tm.norm == 1 ? (v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f)) : 2.f * v;
-  return tm.norm == 1 ? (v > 0.f ? 1.f : 0.f) : (v > 0.f ? 2.f * v : 0.f);
+__device__ __forceinline__ float term_dpenalty(const NmPlan& pl, const NmTerm& tm, float v) {
+  const int norm = NM_TERM_NORM(tm.norm), bk = NM_TERM_BARRIER(tm.norm);
+  if (bk != NM_BARRIER_NONE && !(v >= 0.f)) { float df; barrier_eval(pl, bk, v, df); return df; }
+  if (tm.cmp == NM_CMP_EQ) return norm == 1 ? (v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f)) : 2.f * v;
+  return norm == 1 ? (v > 0.f ? 1.f : 0.f) : (v > 0.f ? 2.f * v : 0.f);
 }
 
 __device__ __forceinline__ bool atom_is_tbcast(const NmAtom& at, const NmTerm& tm) { return at.t_len == 1 && tm.t_len > 1; }
 
 // sum over this trajectory's elements of term k
-__device__ __forceinline__ float term_sum_traj(const NmTerm& tm, const VarTable& vt, int64_t b) {
+__device__ __forceinline__ float term_sum_traj(const NmPlan& p, const NmTerm& tm, const VarTable& vt, int64_t b) {
   float s = 0.f;
   for (int te = 0; te < tm.t_len; ++te)
-    for (int de = 0; de < tm.d_len; ++de) s += term_penalty(tm, term_value(tm, vt, b, te, de));
+    for (int de = 0; de < tm.d_len; ++de) s += term_penalty(p, tm, term_value(tm, vt, b, te, de));
   return s;
 }
 
@@ -122,7 +145,7 @@ __device__ __forceinline__ void term_grad_accum(const NmPlan& p, const VarTable&
         for (int te = te_lo; te < te_hi; ++te)
           for (int de = de_lo; de < de_hi; ++de) {
             const float v = term_value(tm, vt, b, te, de);
-            float dv = term_dpenalty(tm, v) * side_sign;
+            float dv = term_dpenalty(p, tm, v) * side_sign;
             // d side / d atom
             if (side.op == NM_OP_SUB && second) dv = -dv;
             else if (side.op == NM_OP_MUL) dv *= atom_value(second ? side.a : side.b, vt, b, te, de);
@@ -167,7 +190,7 @@ __device__ __forceinline__ void term_grad_accum_tb_lanes(const NmPlan& p, const 
         for (int te = lane; te < tm.t_len; te += 32)
           for (int de = de_lo; de < de_hi; ++de) {
             const float v = term_value(tm, vt, b, te, de);
-            float dv = term_dpenalty(tm, v) * side_sign;
+            float dv = term_dpenalty(p, tm, v) * side_sign;
             if (side.op == NM_OP_SUB && second) dv = -dv;
             else if (side.op == NM_OP_MUL) dv *= atom_value(second ? side.a : side.b, vt, b, te, de);
             acc += dv;
@@ -244,7 +267,7 @@ __device__ __forceinline__ float term_grad_entry(const NmPlan& p, const VarTable
       for (int te = te_lo; te < te_hi; ++te) {
         const TermRef r = term_ref(tm, vt, b, te);
         for (int de = de_lo; de < de_hi; ++de) {
-          float dv = term_dpenalty(tm, term_value_ref(tm, r, de)) * side_sign;
+          float dv = term_dpenalty(p, tm, term_value_ref(tm, r, de)) * side_sign;
           if (side.op == NM_OP_SUB && second) dv = -dv;
           else if (side.op == NM_OP_MUL) dv *= ref_value(second ? (which < 2 ? r.la : r.ra) : (which < 2 ? r.lb : r.rb), de);
           acc += dv;
@@ -303,16 +326,20 @@ __device__ __forceinline__ float term_value_s(const NmTerm& tm, const VarTable& 
   if constexpr (S::t_cmp(K) == NM_CMP_GT) return r - l; else return l - r;
 }
 template <class S, int K>
-__device__ __forceinline__ float term_penalty_s(float v) {
-  if constexpr (S::t_cmp(K) == NM_CMP_EQ) { if constexpr (S::t_norm(K) == 1) return fabsf(v); else return v * v; }
-  else { const float p = v > 0.f ? v : 0.f; if constexpr (S::t_norm(K) == 1) return p; else return p * p; }
+__device__ __forceinline__ float term_penalty_s(const NmPlan& pl, float v) {
+  constexpr int NORM = NM_TERM_NORM(S::t_norm(K)), BK = NM_TERM_BARRIER(S::t_norm(K));
+  if constexpr (BK != NM_BARRIER_NONE) { if (!(v >= 0.f)) { float df; return barrier_eval(pl, BK, v, df); } }
+  if constexpr (S::t_cmp(K) == NM_CMP_EQ) { if constexpr (NORM == 1) return fabsf(v); else return v * v; }
+  else { const float p = v > 0.f ? v : 0.f; if constexpr (NORM == 1) return p; else return p * p; }
 }
 template <class S, int K>
-__device__ __forceinline__ float term_dpenalty_s(float v) {
+__device__ __forceinline__ float term_dpenalty_s(const NmPlan& pl, float v) {
+  constexpr int NORM = NM_TERM_NORM(S::t_norm(K)), BK = NM_TERM_BARRIER(S::t_norm(K));
+  if constexpr (BK != NM_BARRIER_NONE) { if (!(v >= 0.f)) { float df; barrier_eval(pl, BK, v, df); return df; } }
   if constexpr (S::t_cmp(K) == NM_CMP_EQ) {
-    if constexpr (S::t_norm(K) == 1) return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); else return 2.f * v;
+    if constexpr (NORM == 1) return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); else return 2.f * v;
   } else {
-    if constexpr (S::t_norm(K) == 1) return v > 0.f ? 1.f : 0.f; else return v > 0.f ? 2.f * v : 0.f;
+    if constexpr (NORM == 1) return v > 0.f ? 1.f : 0.f; else return v > 0.f ? 2.f * v : 0.f;
   }
 }
 
@@ -328,14 +355,14 @@ __device__ __forceinline__ void score_traj_s(const NmPlan& p, const VarTable& vt
     int te = 0;
     for (; te + 3 < tl; te += 4) {                      // four independent chains: the (L2-latency) loads overlap
       for (int de = 0; de < dl; ++de) {
-        s0 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
-        s1 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 1, de));
-        s2 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 2, de));
-        s3 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te + 3, de));
+        s0 += term_penalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te, de));
+        s1 += term_penalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te + 1, de));
+        s2 += term_penalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te + 2, de));
+        s3 += term_penalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te + 3, de));
       }
     }
     for (; te < tl; ++te)
-      for (int de = 0; de < dl; ++de) s0 += term_penalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+      for (int de = 0; de < dl; ++de) s0 += term_penalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te, de));
     s0 += s2; s1 += s3;
     tsum[K] += s0 + s1;
   });
@@ -369,7 +396,7 @@ __device__ __forceinline__ void term_grad_s(const NmPlan& p, const VarTable& vt,
             const int de = d - at.d_start;
             const bool in_d = de >= 0 && de < at.d_len;
             const int de_c = in_d ? de : 0;
-            float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te_c, de_c));
+            float dv = term_dpenalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te_c, de_c));
             if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te_c, de_c);
             g[d] = (act_t && in_d) ? fmaf(ck, dv, g[d]) : g[d];
           }
@@ -391,7 +418,7 @@ __device__ __forceinline__ void term_grad_s(const NmPlan& p, const VarTable& vt,
             float acc = 0.f;
             for (int te = te_lo + (A::TB ? te0 : 0); te < te_hi; te += (A::TB ? te_stride : 1))
               for (int de = de_lo; de < de_hi; ++de) {
-                float dv = term_dpenalty_s<S, K>(term_value_s<S, K>(tm, vt, b, te, de));
+                float dv = term_dpenalty_s<S, K>(p, term_value_s<S, K>(tm, vt, b, te, de));
                 if constexpr (OP == NM_OP_MUL) dv *= atom_value_s<S, K, (W ^ 1)>(tm, vt, b, te, de);
                 acc += dv;
               }

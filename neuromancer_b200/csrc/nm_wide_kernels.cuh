@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(256) nm_wide_score_kernel(const __grid_constan
       const NmTerm& tm = p.terms[K];
       if (te < tm.t_len) {
         float s = 0.f;
-        for (int de = 0; de < tm.d_len; ++de) s += term_penalty_s<S, K>(term_value_s<S, K>(tm, vtc, b, te, de));
+        for (int de = 0; de < tm.d_len; ++de) s += term_penalty_s<S, K>(p, term_value_s<S, K>(tm, vtc, b, te, de));
         ts[K] += s;
       }
     });

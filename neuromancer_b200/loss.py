@@ -122,9 +122,12 @@ class BarrierLoss(PenaltyLoss):
     """Barrier method (reference loss.py:184-257): a satisfied constraint (value < 0) contributes
     ``weight * mean(barrier(value))``, clamped to ``[0, upper_bound]``, a violated one its penalty.
 
-    Not lowered to the fused term kernels: inside a ``Problem`` the ``System`` rollout runs on the fused forward
-    kernel, this loss is evaluated with torch ops on the CUDA trajectories it wrote, and its gradient enters the
-    fused adjoint kernel through ``grad_*_ext`` (the path of every Python-evaluated term)."""
+    With one of the named barrier functions the constraints are lowered to ``NmTerm`` descriptors carrying the barrier
+    kind (``NM_BARRIER_*``) and scored / differentiated inside the fused kernels like PenaltyLoss terms
+    (``plan.py``; ``penalty_loss`` and ``loss`` come from the kernels, the per-constraint plain penalties, the
+    ``<name>_barrier`` tensors and ``barrier_loss`` are materialised lazily).  With a callable barrier, or a constraint
+    that cannot be lowered, this loss is evaluated with torch ops on the CUDA trajectories the fused rollout wrote and
+    its gradient enters the fused adjoint kernel through ``grad_*_ext`` (``forward`` below)."""
 
     def __init__(self, objectives, constraints, barrier="log10", upper_bound=1., shift=1., alpha=0.5):
         super().__init__(objectives, constraints)
@@ -135,6 +138,7 @@ class BarrierLoss(PenaltyLoss):
                          "softexp": lambda value: (torch.exp(self.alpha * value) - 1) / self.alpha + self.alpha,
                          "softlog": lambda value: -torch.log(1 + self.alpha * (-value - self.alpha)) / self.alpha,
                          "expshift": lambda value: torch.exp(value + self.shift)}
+        self.barrier_name = barrier if isinstance(barrier, str) and barrier in self.barriers else None     # (None: a callable)
         if barrier in self.barriers:
             self.barrier = self.barriers[barrier]
         else:

@@ -447,7 +447,8 @@ class RolloutPlan:
         self._term_weights = self._current_term_weights()
 
     def _current_term_weights(self):
-        return tuple(float(t.weight) for t, _ in getattr(self, "fused_terms", []))
+        extra = (float(self.loss.alpha), float(self.loss.shift), float(self.loss.upper_bound)) if getattr(self, "barrier", 0) else ()
+        return tuple(float(t.weight) for t, _ in getattr(self, "fused_terms", [])) + extra
 
     def values_stale(self) -> bool:
         """True when a tensor or term weight whose value the plan carries has changed since lowering."""
@@ -643,12 +644,20 @@ class RolloutPlan:
             self.var_shapes[k] = (p.exo[i].steps, p.exo[i].width)
         self.fused_terms: List[Tuple[object, bool]] = []      # (term, is_objective)
         self.python_terms: List[Tuple[object, bool]] = []
+        # BarrierLoss (reference loss.py:184-257) with one of its named barrier functions: the constraints are lowered with
+        # the barrier kind in NmTerm.norm, its parameters travel in the plan; a callable barrier stays in Python
+        barrier = L.NM_BARRIERS.get(getattr(loss, "barrier_name", None), 0) if loss is not None else 0
+        if barrier:
+            p.barrier_alpha, p.barrier_shift, p.barrier_ub = float(loss.alpha), float(loss.shift), float(loss.upper_bound)
+        self.barrier = barrier
         if loss is not None:
             listed = [(t, True) for t in loss.objectives] + [(t, False) for t in loss.constraints]
             for term, is_obj in listed:
                 low = None
                 if len(self.fused_terms) < L.NM_MAX_TERMS:
                     low = lower_term(term, is_obj, self.var_ids, self.var_shapes)
+                    if low is not None and barrier and not is_obj:
+                        low.norm |= barrier << 4          # NM_TERM_BARRIER: satisfied entries contribute the barrier value
                 if low is None:
                     self.python_terms.append((term, is_obj))
                 else:

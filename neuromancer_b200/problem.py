@@ -18,7 +18,7 @@ from typing import Callable, Dict, List
 import torch
 import torch.nn as nn
 
-from .loss import AggregateLoss, PenaltyLoss
+from .loss import AggregateLoss, BarrierLoss, PenaltyLoss
 from .system import System
 
 
@@ -78,10 +78,12 @@ class Problem(nn.Module):
             seen |= set(node.output_keys)
 
     def _fusable(self):
-        # (exactly PenaltyLoss: subclasses such as BarrierLoss redefine how constraints enter the loss and are
-        # evaluated with torch ops on the trajectories the fused rollout wrote)
-        return (len(self.nodes) == 1 and isinstance(self.nodes[0], System)
-                and type(self.loss) is PenaltyLoss)
+        # exactly PenaltyLoss, or exactly BarrierLoss with one of its named barrier functions (lowered with the barrier kind
+        # in the term descriptors); other subclasses redefine how constraints enter the loss and are evaluated with torch
+        # ops on the trajectories the fused rollout wrote
+        if len(self.nodes) != 1 or not isinstance(self.nodes[0], System):
+            return False
+        return type(self.loss) is PenaltyLoss or (type(self.loss) is BarrierLoss and self.loss.barrier_name is not None)
 
     def step(self, input_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Run the nodes (each a fused ``System``) and merge their outputs."""
@@ -97,6 +99,8 @@ class Problem(nn.Module):
             from .rollout import run_problem
             out = run_problem(self.nodes[0], self.loss, data)
         else:
+            out = None
+        if out is None:          # not fusable, or a BarrierLoss constraint that could not be lowered
             out = self.loss(self.step(data))
             if isinstance(out, torch.Tensor):
                 out = {self.loss.name: out}

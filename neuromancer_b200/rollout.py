@@ -331,12 +331,23 @@ def run_problem(system, loss, data):
     from .problem import LazyOutputs
     batch = system.init(dict(data))
     plan = system.plan_for(batch, loss=loss)
+    barrier = getattr(plan, "barrier", 0)
+    if barrier and any(not is_obj for _, is_obj in plan.python_terms):
+        return None                     # a BarrierLoss constraint that is not lowered: the caller evaluates the loss with torch ops
     traj, scalars = run_rollout(plan, batch)
     out = LazyOutputs(traj)
     n = plan.c.n_terms
     obj_total, pen_total = scalars[n], scalars[n + 1]
-    for i, (term, _) in enumerate(plan.fused_terms):
-        out[term.output_keys[0]] = scalars[i]
+
+    def plain_penalty(term):             # BarrierLoss reports the constraint's ordinary weighted penalty under its own key
+        def thunk():
+            return {term.output_keys[0]: term.evaluate(traj)[0]}
+        return thunk
+    for i, (term, is_obj) in enumerate(plan.fused_terms):
+        if barrier and not is_obj:       # scalars[i] is weight * mean(penalty | barrier): it enters penalty_loss, not this key
+            out.register(term.output_keys[:1], plain_penalty(term))
+        else:
+            out[term.output_keys[0]] = scalars[i]
     # terms that could not be lowered: evaluated with torch ops on the kernel's trajectories; their
     # gradient reaches the adjoint kernel through grad_x_ext / grad_u_ext / grad_y_ext
     per_constraint = {}
@@ -365,6 +376,24 @@ def run_problem(system, loss, data):
         return thunk
     for term, _ in plan.fused_terms:
         out.register(term.output_keys[1:], materialise_term(term))
+
+    if barrier:
+        # `<name>_barrier` tensors and `barrier_loss` of the reference's BarrierLoss.calculate_constraints: on demand, torch ops
+        def barrier_outputs():
+            res, b_loss = {}, 0.0
+            for con in loss.constraints:
+                _, value, _ = con.evaluate(traj)
+                cb = loss.barrier(value)
+                cb[cb != cb] = 0.0
+                cb[cb == float("Inf")] = 0.0
+                cb = torch.clamp(cb, min=0.0, max=loss.upper_bound)
+                res[f"{con.name}_barrier"] = cb
+                mask = value >= 0
+                if (~mask).any():
+                    b_loss = b_loss + con.weight * torch.mean(~mask * cb)
+            res["barrier_loss"] = b_loss
+            return res
+        out.register([f"{con.name}_barrier" for con in loss.constraints] + ["barrier_loss"], barrier_outputs)
 
     if len(loss.constraints):
         out_ref = weakref.ref(out)        # no reference cycle out -> thunk -> out: a step's outputs (and the batch tensors they

@@ -114,6 +114,27 @@ def t_vdp_rk4_tanh_clamp(params, nsteps=12) -> dict:
     return dict(nodes=nodes, terms=terms, nsteps=nsteps, params=params, traj_keys=["x", "u"])
 
 
+# BarrierLoss (reference loss.py:184-257) on the tanh-clamp problem: box constraints on the state (norm 2
+# upper, norm 1 lower) and on the action, every built-in barrier function
+def _t_barrier(params, nsteps, barrier):
+    spec = t_vdp_rk4_tanh_clamp(params, nsteps)
+    spec["terms"] = [_term("obj", True, "eq", 2, 3., lambda d: d["x"], lambda d: d["r"]),
+                     _term("hi", False, "lt", 2, 2., lambda d: d["x"], lambda d: 1.5),
+                     _term("lo", False, "gt", 1, 1., lambda d: d["x"], lambda d: -1.5),
+                     _term("umax", False, "lt", 1, 0.5, lambda d: d["u"], lambda d: 0.8)]
+    # (expshift: the reference's own backward raises on its in-place masked assignment -- see dpc_oracle.barrier_loss)
+    spec["barrier"] = dict(barrier=barrier, upper_bound=2.0, shift=0.7, alpha=0.4, out_of_place=barrier == "expshift")
+    return spec
+
+
+def t_barrier_log10(params, nsteps=12): return _t_barrier(params, nsteps, "log10")
+def t_barrier_log(params, nsteps=12): return _t_barrier(params, nsteps, "log")
+def t_barrier_inverse(params, nsteps=12): return _t_barrier(params, nsteps, "inverse")
+def t_barrier_softexp(params, nsteps=12): return _t_barrier(params, nsteps, "softexp")
+def t_barrier_softlog(params, nsteps=12): return _t_barrier(params, nsteps, "softlog")
+def t_barrier_expshift(params, nsteps=12): return _t_barrier(params, nsteps, "expshift")
+
+
 # structured slim maps: the tanh-clamp problem whose policy layers are slim maps; `params` holds, per layer,
 # the map's own parameters (registration order) and then its bias [1, out]
 def _slim_case(params, nsteps, per_layer, eff_w):
@@ -375,7 +396,9 @@ CASES = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5,
          "t_int_leapfrog_node": t_int_leapfrog_node, "t_int_yoshida_node": t_int_yoshida_node,
          "t_sysid_twotank": t_sysid_twotank, "t_sysid_lorenz": t_sysid_lorenz, "t_sysid_cstr": t_sysid_cstr,
          "t_sysid_duffing": t_sysid_duffing, "t_sysid_brusselator": t_sysid_brusselator, "t_sysid_lotka": t_sysid_lotka,
-         "t_sysid_vdp_policy": t_sysid_vdp_policy, "t_ude_brusselator": t_ude_brusselator, "t_ude_lotka": t_ude_lotka}
+         "t_sysid_vdp_policy": t_sysid_vdp_policy, "t_ude_brusselator": t_ude_brusselator, "t_ude_lotka": t_ude_lotka,
+         "t_barrier_log10": t_barrier_log10, "t_barrier_log": t_barrier_log, "t_barrier_inverse": t_barrier_inverse,
+         "t_barrier_softexp": t_barrier_softexp, "t_barrier_softlog": t_barrier_softlog, "t_barrier_expshift": t_barrier_expshift}
 
 
 def build(name: str, params: List[torch.Tensor], **kw) -> dict:

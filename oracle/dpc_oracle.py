@@ -390,6 +390,46 @@ def penalty_loss(terms: List[dict], data: Dict[str, torch.Tensor]) -> Dict[str, 
     return out
 
 
+def barrier_function(name: str, alpha: float, shift: float) -> Callable[[torch.Tensor], torch.Tensor]:
+    """the built-in barrier functions of ``BarrierLoss.__init__`` (reference loss.py:209-215)"""
+    return {"log10": lambda value: -torch.log10(-value),
+            "log": lambda value: -torch.log(-value),
+            "inverse": lambda value: 1 / (-value),
+            "softexp": lambda value: (torch.exp(alpha * value) - 1) / alpha + alpha,
+            "softlog": lambda value: -torch.log(1 + alpha * (-value - alpha)) / alpha,
+            "expshift": lambda value: torch.exp(value + shift)}[name]
+
+
+def barrier_loss(terms: List[dict], data: Dict[str, torch.Tensor], barrier: str, upper_bound: float = 1., shift: float = 1.,
+                 alpha: float = 0.5, out_of_place: bool = False) -> Dict[str, torch.Tensor]:
+    """``BarrierLoss`` (reference loss.py:184-257): ``PenaltyLoss.forward`` with ``calculate_constraints`` replaced --
+    entries with value >= 0 pay their violation, the others the barrier value (nan / inf -> 0, clamped to
+    [0, upper_bound]); each part a masked mean over ALL entries, the per-constraint keys keep the plain penalty.
+    ``out_of_place``: the reference's masked assignments modify the barrier function's output in place; for 'expshift'
+    that output is what ExpBackward saved and the reference's own ``loss.backward()`` raises.  Same values, with the
+    assignments on a copy, define the gradient the fused kernels are checked against for that barrier."""
+    out = penalty_loss(terms, data)
+    fn = barrier_function(barrier, alpha, shift)
+    loss, b_loss = 0.0, 0.0
+    for t in [t for t in terms if not t["objective"]]:
+        cvalue, cviolation = out[t["name"] + "_value"], out[t["name"] + "_violation"]
+        penalty_mask = cvalue >= 0
+        cbarrier = fn(cvalue).clone() if out_of_place else fn(cvalue)
+        cbarrier[cbarrier != cbarrier] = 0.0
+        cbarrier[cbarrier == float("Inf")] = 0.0
+        cbarrier = torch.clamp(cbarrier, min=0.0, max=upper_bound)
+        out[t["name"] + "_barrier"] = cbarrier
+        if penalty_mask.any():
+            loss = loss + t["weight"] * torch.mean(penalty_mask * cviolation)
+        if (~penalty_mask).any():
+            bl = t["weight"] * torch.mean(~penalty_mask * cbarrier)
+            b_loss = b_loss + bl
+            loss = loss + bl
+    out["barrier_loss"], out["penalty_loss"] = b_loss, loss
+    out["loss"] = out["objective_loss"] + loss
+    return out
+
+
 def run_case(spec: dict, data: Dict[str, torch.Tensor], want_grad: bool = True) -> Dict[str, object]:
     """Forward (+ backward) of one problem.  ``spec`` = {nodes, terms, nsteps, params (list of leaf
     tensors), traj_keys}.  Returns trajectories, per-term scalars, loss and parameter gradients."""
@@ -399,7 +439,7 @@ def run_case(spec: dict, data: Dict[str, torch.Tensor], want_grad: bool = True) 
                                       pv.get("pad_constant"))
     else:
         traj = system_forward(spec["nodes"], data, spec["nsteps"])
-    scored = penalty_loss(spec["terms"], traj)
+    scored = barrier_loss(spec["terms"], traj, **spec["barrier"]) if "barrier" in spec else penalty_loss(spec["terms"], traj)
     res = {"traj": {k: traj[k] for k in spec["traj_keys"]},
            "terms": {t["name"]: scored[t["name"]] for t in spec["terms"]},
            "objective_loss": scored["objective_loss"], "penalty_loss": scored["penalty_loss"],

@@ -212,6 +212,19 @@ def ref_t_vdp_rk4_tanh_clamp(ns, nsteps=12):
     return problem, _mlp_params(net), data, ["x", "u"], ["obj", "eff", "du", "box"]
 
 
+def _ref_t_barrier(ns, barrier, nsteps=12):
+    problem, params, data, traj_keys, _ = ref_t_vdp_rk4_tanh_clamp(ns, nsteps)
+    v = ns.constraint.variable
+    x, r, u = v("x"), v("r"), v("u")
+    obj = 3. * ((x == r) ^ 2)
+    hi = 2. * ((x < 1.5) ^ 2)
+    lo = 1. * (x > -1.5)
+    umax = 0.5 * (u < 0.8)
+    _name([(obj, "obj"), (hi, "hi"), (lo, "lo"), (umax, "umax")])
+    loss = ns.loss.BarrierLoss([obj], [hi, lo, umax], barrier=barrier, upper_bound=2.0, shift=0.7, alpha=0.4)
+    return ns.problem.Problem([problem.nodes[0]], loss), params, data, traj_keys, ["obj", "hi", "lo", "umax"]
+
+
 def _slim_params(mlp):
     """per layer: the structured map's own parameters in registration order, then its bias (reference slim/linear.py:42-61)"""
     out = []
@@ -554,6 +567,7 @@ REF_BUILDERS = {
     "t_sysid_duffing": (ref_t_sysid_duffing, 12), "t_sysid_brusselator": (ref_t_sysid_brusselator, 12),
     "t_sysid_lotka": (ref_t_sysid_lotka, 12), "t_sysid_vdp_policy": (ref_t_sysid_vdp_policy, 12),
     "t_ude_brusselator": (ref_t_ude_brusselator, 12), "t_ude_lotka": (ref_t_ude_lotka, 12),
+    **{f"t_barrier_{b}": ((lambda ns, b=b: _ref_t_barrier(ns, b)), 16) for b in ("log10", "log", "inverse", "softexp", "softlog", "expshift")},
 }
 
 
@@ -566,15 +580,20 @@ def run_reference(problem, params, batch, traj_keys, term_names):
     for p in params:
         p.grad = None
     out = problem({**batch, "name": "train"})
+    backward_error = None
     if params:
-        out["train_loss"].backward()
+        try:
+            out["train_loss"].backward()
+        except RuntimeError as e:       # BarrierLoss('expshift'): the reference modifies the output of exp in place
+            backward_error = str(e).split(":")[0]
     cmat = {k: out[f"train_{k}"].detach() for k in CMAT_KEYS if f"train_{k}" in out}
     return {"traj": {k: out[f"train_{k}"].detach() for k in traj_keys},
             "terms": {n: out[f"train_{n}"].detach() for n in term_names}, "cmat": cmat,
             "objective_loss": torch.as_tensor(out["train_objective_loss"]).detach(),
             "penalty_loss": torch.as_tensor(out["train_penalty_loss"]).detach(),
             "loss": out["train_loss"].detach(),
-            "grads": [p.grad.detach().clone() for p in params]}
+            "backward_error": backward_error,
+            "grads": [] if backward_error else [p.grad.detach().clone() for p in params]}
 
 
 def main() -> int:
@@ -614,6 +633,10 @@ def main() -> int:
         ok &= not bad
         report["cases"][name] = {"batch": B, "bit_exact": not bad, "mismatch": bad, "max_rel": worst,
                                  "loss": float(ref["loss"])}
+        if ref["backward_error"]:
+            # forward pinned; the stored gradients are the oracle's (out-of-place variant of the same expression)
+            report["cases"][name]["reference_backward"] = f"raises ({ref['backward_error']}); golden gradients are the oracle's"
+            ref["grads"] = [g.detach().clone() for g in ora["grads"]]
         arrays = {}
         for i, p in enumerate(params):
             arrays[f"param_{i}"] = p.detach().numpy()

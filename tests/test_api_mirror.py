@@ -137,7 +137,7 @@ def test_barrier_loss_matches_reference_golden(barrier):
     assert float(res["loss"]) == float(res["objective_loss"] + res["penalty_loss"])
 
 
-def test_problem_fuses_only_plain_penalty_loss():
+def test_problem_fuses_penalty_loss_and_named_barrier_loss():
     from neuromancer_b200 import BarrierLoss, Problem, System
     from neuromancer_b200.dynamics import integrators, ode
     from neuromancer_b200.modules import blocks
@@ -147,4 +147,11 @@ def test_problem_fuses_only_plain_penalty_loss():
     x = variable("x")
     con = (x < 1.0)
     assert Problem([system], PenaltyLoss([], [con]))._fusable()
-    assert not Problem([system], BarrierLoss([], [con], barrier="softexp"))._fusable()
+    # BarrierLoss with a named barrier is lowered (barrier kind in the term descriptors); a callable barrier, or any other
+    # subclass that redefines how constraints enter the loss, is evaluated with torch ops on the fused trajectories
+    assert Problem([system], BarrierLoss([], [con], barrier="softexp"))._fusable()
+    assert not Problem([system], BarrierLoss([], [con], barrier=lambda v: torch.exp(v)))._fusable()
+
+    class MyLoss(PenaltyLoss):
+        pass
+    assert not Problem([system], MyLoss([], [con]))._fusable()

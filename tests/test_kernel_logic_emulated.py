@@ -108,7 +108,10 @@ PLAIN = [("c4", ("EMU_TILE=128", "EMU_THREADS=256"), (1, 150)),      # y = Cx no
          ("t_sysid_duffing", ("EMU_TILE=64", "EMU_THREADS=64"), (100,)),         # cos(omega t): gradient w.r.t. a frequency
          ("t_sysid_vdp_policy", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),    # policy weights AND the plant's mu trained together
          ("t_ude_brusselator", ("EMU_TILE=64", "EMU_THREADS=128"), (1, 100)),    # grey-box: MLP 2-20-20-1 inside the Brusselator, weights + alpha, beta
-         ("t_ude_lotka", ("EMU_TILE=64", "EMU_THREADS=128"), (100,))]            # grey-box Lotka-Volterra, four constants next to the MLP
+         ("t_ude_lotka", ("EMU_TILE=64", "EMU_THREADS=128"), (100,)),            # grey-box Lotka-Volterra, four constants next to the MLP
+         ("t_barrier_log10", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),       # BarrierLoss terms: barrier value / derivative on satisfied entries
+         ("t_barrier_softexp", ("EMU_TILE=128", "EMU_THREADS=128"), (150,)),
+         ("t_barrier_expshift", ("EMU_TILE=128", "EMU_THREADS=128"), (150,))]
 
 
 @pytest.mark.parametrize("name,defines,batches", PLAIN, ids=[c[0] for c in PLAIN])

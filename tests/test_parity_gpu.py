@@ -412,3 +412,35 @@ def test_frozen_constants_get_no_gradient_entry():
     assert case.plan().c.n_params == 3 and case.plan().c.rhs_mlp.trainable == 1
     frozen = H.make_case("t_auto_lorenz", DEV)
     assert frozen.plan().c.n_params == 0 and frozen.plan().c.rhs_mlp.trainable == 0
+
+
+@pytest.mark.parametrize("barrier", ["log10", "softexp"])
+def test_barrier_loss_is_fused_and_reports_the_reference_keys(barrier):
+    """BarrierLoss with a named barrier (reference loss.py:184-257) is lowered: penalty_loss / loss come from the fused
+    kernels (no torch-evaluated term), the constraint keys keep the plain weighted penalty, `<name>_barrier` and
+    `barrier_loss` materialise on demand and agree with the torch evaluation of the same loss class (callable barrier ->
+    not lowered) on the same trajectories -- values and gradients."""
+    from neuromancer_b200 import BarrierLoss, Problem
+    name = f"t_barrier_{barrier}"
+    case = H.make_case(name, DEV, seed=2)
+    plan = case.plan()
+    assert plan.barrier and not plan.python_terms and plan.c.n_terms == 4
+    batch = to_dev(case.make_batch(300, "cpu", 5))
+    out = case.problem(batch)
+    fused_loss = case.problem.loss
+    eager_loss = BarrierLoss(list(fused_loss.objectives), list(fused_loss.constraints), barrier=fused_loss.barriers[barrier],
+                             upper_bound=fused_loss.upper_bound, shift=fused_loss.shift, alpha=fused_loss.alpha)
+    assert eager_loss.barrier_name is None
+    eager = Problem([case.system], eager_loss)
+    assert not eager._fusable()
+    ref = eager(batch)
+    for k in ("train_loss", "train_penalty_loss", "train_objective_loss", "train_barrier_loss"):
+        assert_rel(torch.as_tensor(out[k]).detach().cpu(), torch.as_tensor(ref[k]).detach().cpu(), GRAD_RTOL, f"{name} {k}")
+    for con in fused_loss.constraints:
+        assert_rel(out[f"train_{con.output_keys[0]}"].detach().cpu(), ref[f"train_{con.output_keys[0]}"].detach().cpu(), GRAD_RTOL, con.name)
+        assert torch.equal(out[f"train_{con.name}_barrier"], ref[f"train_{con.name}_barrier"])
+    params = [p for p in case.plan_params if p.requires_grad]
+    g_fused = torch.autograd.grad(out["train_loss"], params)
+    g_eager = torch.autograd.grad(ref["train_loss"], params)
+    for i, (a, b) in enumerate(zip(g_fused, g_eager)):
+        assert_rel(a.cpu(), b.cpu(), GRAD_RTOL, f"{name} grad {i} fused vs torch-evaluated barrier")
