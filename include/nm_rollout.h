@@ -328,6 +328,20 @@ int nm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float max_norm,
                   float* norm_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Constraint matrices of AggregateLoss.calculate_constraints (reference loss.py:86-106) for the plan's fused constraint
+ * terms, in list order: row b = the constraint values (C_values) / violations (C_violations) of trajectory b, each
+ * constraint contributing t_len * d_len columns (its [t][d] entries, row-major), and the same columns split into the
+ * equality (Eq comparator) and inequality partitions.  One pass over the trajectories, every output written once.
+ *   widths      [3] out (may be called with B = 0 and NULL buffers to query them): total, equality, inequality columns
+ *   c_values / c_violations            [B, widths[0]] device fp32 or NULL
+ *   c_eq_values / c_eq_violations      [B, widths[1]] device fp32 or NULL
+ *   c_ineq_values / c_ineq_violations  [B, widths[2]] device fp32 or NULL
+ * The violation of a BarrierLoss constraint is its plain penalty, as in the reference.
+ */
+int nm_constraint_matrices(const NmPlan* plan, const float* const* exo, const float* x_traj, const float* u_traj, const float* y_traj,
+                           float* c_values, float* c_violations, float* c_eq_values, float* c_eq_violations,
+                           float* c_ineq_values, float* c_ineq_violations, int64_t widths[3], int64_t B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,13 +128,15 @@ def _declare(lib):
     lib.nm_adamw_step.argtypes = [fp, fp, fp, fp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int64, C.c_float, fp, vp, C.c_size_t, vp]
     lib.nm_adamw_step.restype = C.c_int
+    lib.nm_constraint_matrices.argtypes = [P(NmPlan), P(C.c_void_p), fp, fp, fp, fp, fp, fp, fp, fp, fp, P(C.c_int64), C.c_int64, vp]
+    lib.nm_constraint_matrices.restype = C.c_int
 
 
 EXPORTED_SYMBOLS = [
     "nm_abi_version", "nm_last_error", "nm_plan_signature", "nm_has_kernel", "nm_num_kernels",
     "nm_kernel_signature", "nm_load_plugin", "nm_rollout_workspace_bytes", "nm_rollout_forward",
     "nm_rollout_backward", "nm_last_launch_count", "nm_kernel_info", "nm_struct_sizes",
-    "nm_plan_term_signature", "nm_rollout_checkpoint_bytes",
+    "nm_plan_term_signature", "nm_rollout_checkpoint_bytes", "nm_constraint_matrices",
 ]
 
 

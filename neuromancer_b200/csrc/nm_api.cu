@@ -207,6 +207,40 @@ __global__ void __launch_bounds__(kScoreThreads) nm_term_score_kernel(const __gr
   }
 }
 
+// Constraint matrices (reference loss.py:86-106): one thread per (trajectory, column) entry, columns fastest -- stores
+// are coalesced rows, loads follow the [t][d] order of the trajectories; every output is written exactly once.
+struct CMatArgs {
+  float* val; float* viol; float* eq_val; float* eq_viol; float* in_val; float* in_viol;
+  int64_t B; int64_t W, Weq, Win;
+  int n;                                            // constraint terms
+  int term[NM_MAX_TERMS];                           // index into plan.terms
+  int64_t col0[NM_MAX_TERMS + 1];                   // first column in C_values
+  int64_t part0[NM_MAX_TERMS];                      // first column in its partition (eq or ineq)
+};
+__global__ void __launch_bounds__(256) nm_constraint_matrices_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ nm::VarTable vt,
+                                                                     const __grid_constant__ CMatArgs a) {
+  const int64_t total = a.B * a.W;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = idx / a.W, col = idx - b * a.W;
+    int c = 0;
+    while (c + 1 < a.n && col >= a.col0[c + 1]) ++c;
+    NmTerm tm = plan.terms[a.term[c]];
+    const int e = int(col - a.col0[c]);
+    const int te = e / tm.d_len, de = e - te * tm.d_len;
+    const float v = nm::term_value(tm, vt, b, te, de);
+    tm.norm = NM_TERM_NORM(tm.norm);                // C_violations hold the plain penalty, BarrierLoss or not
+    const float pen = nm::term_penalty(plan, tm, v);
+    if (a.val) a.val[idx] = v;
+    if (a.viol) a.viol[idx] = pen;
+    const bool eq = tm.cmp == NM_CMP_EQ;
+    const int64_t pw = eq ? a.Weq : a.Win, pidx = b * pw + a.part0[c] + e;
+    float* pv = eq ? a.eq_val : a.in_val;
+    float* pp = eq ? a.eq_viol : a.in_viol;
+    if (pv) pv[pidx] = v;
+    if (pp) pp[pidx] = pen;
+  }
+}
+
 // Gradient of the scored scalar w.r.t. every trajectory entry: one thread per entry.  Output is one
 // row per trajectory,  G[b] = [ x(T+1, nx) | u(T, nu) | y(T, ny) ],  which the adjoint kernel reads.
 struct TermGradArgs {
@@ -372,6 +406,38 @@ int nm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
 int nm_abi_version(void) { return NM_ABI_VERSION; }
 const char* nm_last_error(void) { return g_err; }
 int nm_last_launch_count(void) { return g_launches; }
+
+int nm_constraint_matrices(const NmPlan* plan, const float* const* exo, const float* x_traj, const float* u_traj, const float* y_traj,
+                           float* c_values, float* c_violations, float* c_eq_values, float* c_eq_violations,
+                           float* c_ineq_values, float* c_ineq_violations, int64_t widths[3], int64_t B, void* stream) {
+  int rc = validate(plan);
+  if (rc != NM_OK) return rc;
+  if (!widths || B < 0) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
+  CMatArgs a{};
+  a.val = c_values; a.viol = c_violations; a.eq_val = c_eq_values; a.eq_viol = c_eq_violations; a.in_val = c_ineq_values; a.in_viol = c_ineq_violations;
+  a.B = B;
+  for (int k = 0; k < plan->n_terms; ++k) {
+    const NmTerm& t = plan->terms[k];
+    if (t.is_objective) continue;
+    const int64_t w = int64_t(t.t_len) * t.d_len;
+    a.term[a.n] = k; a.col0[a.n] = a.W;
+    if (t.cmp == NM_CMP_EQ) { a.part0[a.n] = a.Weq; a.Weq += w; } else { a.part0[a.n] = a.Win; a.Win += w; }
+    a.W += w; ++a.n;
+  }
+  a.col0[a.n] = a.W;
+  widths[0] = a.W; widths[1] = a.Weq; widths[2] = a.Win;
+  g_launches = 0;
+  if (B == 0 || a.W == 0) return NM_OK;
+  if (!x_traj || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj)) { nm_set_error("null trajectory pointer"); return NM_ERR_BAD_PLAN; }
+  const nm::VarTable vt = make_vartable(plan, x_traj, u_traj, y_traj, exo);
+  const int64_t total = B * a.W;
+  const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(148) * 16));
+  nm_constraint_matrices_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*plan, vt, a);
+  g_launches = 1;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
+  return NM_OK;
+}
 
 int nm_struct_sizes(int* out, int cap) {
   const int v[7] = {(int)sizeof(NmMlp), (int)sizeof(NmSegment), (int)sizeof(NmExo), (int)sizeof(NmAtom),

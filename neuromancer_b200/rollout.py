@@ -326,6 +326,29 @@ def run_rollout(plan: RolloutPlan, data):
     return out, scalars
 
 
+def constraint_matrices_fused(plan: RolloutPlan, x_traj, u_traj, y_traj, exo) -> Dict[str, torch.Tensor]:
+    """``C_values`` / ``C_violations`` and their equality / inequality column partitions (reference loss.py:86-106) of the
+    plan's fused constraints, written by ``nm_constraint_matrices`` (C ABI) in one pass over the trajectories."""
+    lib, p = L.load(), plan.c
+    B, dev = x_traj.shape[0], x_traj.device
+    widths = (C.c_int64 * 3)()
+    L.check(lib.nm_constraint_matrices(C.byref(p), None, None, None, None, None, None, None, None, None, None, widths, 0, None),
+            "nm_constraint_matrices")
+    W, Weq, Win = widths[0], widths[1], widths[2]
+    mats = {k: torch.empty(B, w, dtype=torch.float32, device=dev)
+            for k, w in (("C_values", W), ("C_violations", W), ("C_eq_values", Weq), ("C_eq_violations", Weq),
+                         ("C_ineq_values", Win), ("C_ineq_violations", Win))}
+    exo = [e.contiguous() for e in exo]
+    exo_ptrs = (C.c_void_p * max(len(exo), 1))(*[e.data_ptr() for e in exo])
+    args = [_ptr(t.contiguous()) if t is not None else None for t in (x_traj, u_traj, y_traj)]
+    with torch.cuda.device(dev):
+        L.check(lib.nm_constraint_matrices(C.byref(p), exo_ptrs, *args, _ptr(mats["C_values"]), _ptr(mats["C_violations"]),
+                                           _ptr(mats["C_eq_values"]), _ptr(mats["C_eq_violations"]), _ptr(mats["C_ineq_values"]),
+                                           _ptr(mats["C_ineq_violations"]), widths, B,
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "nm_constraint_matrices")
+    return mats
+
+
 def run_problem(system, loss, data):
     """Fused ``Problem.forward``: rollout + PenaltyLoss scoring (reference problem.py:197-202)."""
     from .problem import LazyOutputs
@@ -398,8 +421,17 @@ def run_problem(system, loss, data):
     if len(loss.constraints):
         out_ref = weakref.ref(out)        # no reference cycle out -> thunk -> out: a step's outputs (and the batch tensors they
                                           # carry) are released by refcount, not by the cyclic collector (10 GB per step on c4 / c5)
+        all_fused = not any(not is_obj for _, is_obj in plan.python_terms)
+        lay = plan.layout
+
         def c_matrices():
             o = out_ref()
+            x_t, u_t, y_t = traj[lay.state_key], (traj[lay.action_key] if lay.action_key else None), (traj[lay.output_key] if lay.output_key else None)
+            tracked = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x_t, u_t, y_t))
+            if all_fused and not tracked:
+                # one pass of nm_constraint_matrices_kernel over the trajectories (values only: under no_grad, or when nothing
+                # upstream is differentiated -- with autograd history wanted the torch expressions below are used)
+                return constraint_matrices_fused(plan, x_t, u_t, y_t, _checked_exo(plan, batch, batch[lay.state_key]))
             per = []
             for con in loss.constraints:
                 if id(con) in per_constraint:

@@ -163,6 +163,40 @@ def test_constraint_matrices_match_the_reference(name):
             torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-5 * max(scale, 1e-3))
 
 
+@pytest.mark.parametrize("name", ["c2", "c4", "c5", "t_vdp_rk4_tanh_clamp", "t_barrier_softexp", "t_preview_reflect"])
+def test_constraint_matrices_kernel_matches_the_torch_expressions(name):
+    """Under no_grad the C_* outputs come from nm_constraint_matrices (C ABI, one pass over the trajectories); with autograd
+    history wanted, from the torch expressions of the same Constraint objects.  Same trajectories -> the same numbers
+    (subtractions and relu / abs / square are exact in the same order; 1 ulp allowed for a fused multiply-add of a scaled
+    atom), identical shapes of the eq / ineq partitions -- and the kernel matches the reference golden too."""
+    from neuromancer_b200 import _lib
+    case = H.make_case(name, DEV, seed=4)
+    batch = to_dev(case.make_batch(257, "cpu", 13))
+    tracked = case.problem(batch)                              # grad mode: trajectories carry autograd history -> torch path
+    with torch.no_grad():
+        fused = case.problem(batch)
+        keys = [k for k in ("C_values", "C_violations", "C_eq_values", "C_eq_violations", "C_ineq_values", "C_ineq_violations")]
+        got = {k: fused[f"train_{k}"] for k in keys}
+        assert _lib.load().nm_last_launch_count() == 1         # the matrices kernel was the last C-ABI call
+    for k in keys:
+        want = tracked[f"train_{k}"].detach()
+        assert got[k].shape == want.shape, (name, k, got[k].shape, want.shape)
+        assert not got[k].requires_grad
+        if want.numel():
+            torch.testing.assert_close(got[k], want, rtol=2e-7, atol=1e-7 * float(want.abs().max()))
+    g = load_golden(name)
+    if g["cmat"]:
+        case = H.make_case(name, DEV)
+        load_params(case, g["params"])
+        with torch.no_grad():
+            out = case.problem(to_dev({**g["inputs"], "name": "train"}))
+            for key, want in g["cmat"].items():
+                got_k = out[f"train_{key}"].cpu()
+                assert got_k.shape == want.shape
+                if want.numel():
+                    torch.testing.assert_close(got_k, want, rtol=1e-5, atol=2e-5 * max(float(want.abs().max()), 1e-3))
+
+
 # ------------------------------------------------------------------------------------------------ Trainer on CUDA
 @pytest.mark.parametrize("name", ["c1", "c2"])
 def test_trainer_train_on_cuda_follows_the_oracle_loop(name):
