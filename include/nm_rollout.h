@@ -342,6 +342,24 @@ int nm_constraint_matrices(const NmPlan* plan, const float* const* exo, const fl
                            float* c_values, float* c_violations, float* c_eq_values, float* c_eq_violations,
                            float* c_ineq_values, float* c_ineq_violations, int64_t widths[3], int64_t B, void* stream);
 
+/* Data-parallel exchange of the path: in-kernel SUM over ranks of the flat [gradient | loss scalars]
+ * buffer through NVLink / NVSwitch peer memory -- replaces the NCCL all-reduce DDP would issue (reference trainer.py:49).
+ * The caller owns a SYMMETRIC buffer of nm_grad_allreduce_buffer_floats(n) floats per rank (zero-initialised, mapped on
+ * every peer; torch.distributed._symmetric_memory or cuMem* + IPC), lets nm_rollout_forward / nm_rollout_backward write
+ * scalars and gradients of step `epoch` into half (epoch & 1) of its own buffer (offset (epoch & 1) * npad floats,
+ * npad = n rounded up to 64), and calls this on every rank with the same epoch = 1, 2, 3, ...
+ *   peer_bufs      [world] host array: every rank's symmetric buffer as mapped in THIS process (peer_bufs[rank] = own)
+ *   multicast_ptr  the buffer's multicast address (NVLS: the sum is formed inside the switch by multimem.ld_reduce) or
+ *                  NULL (peer loads summed in rank order)
+ *   out            [n] device fp32, not part of the symmetric buffer; entries >= tail_from are multiplied by tail_scale
+ *                  (loss scalars are averaged, gradients summed)
+ * No host synchronisation; a peer that does not arrive within seconds sets status word
+ * ((uint32_t*)(own + 2 * npad))[17] instead of hanging the device.
+ */
+size_t nm_grad_allreduce_buffer_floats(int64_t n);
+int nm_grad_allreduce(void* const* peer_bufs, const void* multicast_ptr, float* out, int64_t n, int rank, int world,
+                      uint32_t epoch, int64_t tail_from, float tail_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,10 @@ def _declare(lib):
     lib.nm_adamw_step.restype = C.c_int
     lib.nm_constraint_matrices.argtypes = [P(NmPlan), P(C.c_void_p), fp, fp, fp, fp, fp, fp, fp, fp, fp, P(C.c_int64), C.c_int64, vp]
     lib.nm_constraint_matrices.restype = C.c_int
+    lib.nm_grad_allreduce_buffer_floats.argtypes = [C.c_int64]
+    lib.nm_grad_allreduce_buffer_floats.restype = C.c_size_t
+    lib.nm_grad_allreduce.argtypes = [P(C.c_void_p), vp, vp, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int64, C.c_float, vp]
+    lib.nm_grad_allreduce.restype = C.c_int
 
 
 EXPORTED_SYMBOLS = [
@@ -137,6 +141,7 @@ EXPORTED_SYMBOLS = [
     "nm_kernel_signature", "nm_load_plugin", "nm_rollout_workspace_bytes", "nm_rollout_forward",
     "nm_rollout_backward", "nm_last_launch_count", "nm_kernel_info", "nm_struct_sizes",
     "nm_plan_term_signature", "nm_rollout_checkpoint_bytes", "nm_constraint_matrices",
+    "nm_grad_allreduce", "nm_grad_allreduce_buffer_floats",
 ]
 
 

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include "nm_registry.h"
 #include "nm_terms.cuh"
+#include "nm_collective.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -406,6 +408,27 @@ int nm_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
 int nm_abi_version(void) { return NM_ABI_VERSION; }
 const char* nm_last_error(void) { return g_err; }
 int nm_last_launch_count(void) { return g_launches; }
+
+size_t nm_grad_allreduce_buffer_floats(int64_t n) { return size_t(2 * ((n + 63) / 64 * 64) + nm::kArFlagWords); }
+int nm_grad_allreduce(void* const* peer_bufs, const void* multicast_ptr, float* out, int64_t n, int rank, int world,
+                      uint32_t epoch, int64_t tail_from, float tail_scale, void* stream) {
+  if (!peer_bufs || !out || n < 1 || world < 1 || world > nm::kArMaxRanks || rank < 0 || rank >= world || epoch == 0) {
+    nm_set_error("nm_grad_allreduce: bad arguments (1 <= world <= 16, epoch >= 1)"); return NM_ERR_BAD_PLAN;
+  }
+  nm::ArPeers peers{};
+  for (int q = 0; q < world; ++q) {
+    if (!peer_bufs[q] || (reinterpret_cast<uintptr_t>(peer_bufs[q]) & 15)) { nm_set_error("nm_grad_allreduce: null / misaligned peer buffer"); return NM_ERR_BAD_PLAN; }
+    peers.buf[q] = static_cast<float*>(peer_bufs[q]);
+  }
+  const int64_t npad = (n + 63) / 64 * 64;                   // halves stay 256-byte aligned
+  const int blocks = int(std::min<int64_t>(nm::kArBlocks, std::max<int64_t>(1, (npad / 4 + nm::kArThreads - 1) / nm::kArThreads)));
+  nm::nm_grad_allreduce_kernel<<<blocks, nm::kArThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      peers, static_cast<const float*>(multicast_ptr), out, n, npad, rank, world, epoch, tail_scale, tail_from);
+  g_launches = 1;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { nm_set_error(cudaGetErrorString(ce)); return NM_ERR_CUDA; }
+  return NM_OK;
+}
 
 int nm_constraint_matrices(const NmPlan* plan, const float* const* exo, const float* x_traj, const float* u_traj, const float* y_traj,
                            float* c_values, float* c_violations, float* c_eq_values, float* c_eq_violations,

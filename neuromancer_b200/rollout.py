@@ -450,7 +450,7 @@ class RawTrainStep:
     (``[n_params | n_terms+3]``) so that data-parallel training needs a single all-reduce.
     Used by ``bench.py`` for the kernel-path throughput; the public API path is ``Problem.forward``."""
 
-    def __init__(self, plan: RolloutPlan, batch: Dict[str, torch.Tensor], world_size: int = 1):
+    def __init__(self, plan: RolloutPlan, batch: Dict[str, torch.Tensor], world_size: int = 1, peer_sync: bool = False):
         lay, p = plan.layout, plan.c
         self.plan, self.lib = plan, L.load()
         x_in = batch[lay.state_key]
@@ -470,6 +470,14 @@ class RawTrainStep:
         self.gbuf = torch.zeros(n + plan.n_scalars, dtype=torch.float32, device=dev)
         self.grad = self.gbuf[:n]
         self.scalars = self.gbuf[n:]
+        # data-parallel exchange inside a kernel over NVLink peer memory (distributed.PeerAllReduce): the kernels of a step
+        # write scalars and gradients straight into that step's half of the symmetric buffer, `all_reduce()` sums over
+        # ranks into gbuf -- no NCCL call, no staging copy
+        self.sync = None
+        if peer_sync and world_size > 1:
+            from .distributed import PeerAllReduce
+            self.sync = PeerAllReduce(n + plan.n_scalars, dev)
+            self._n = n
         fwd_b, bwd_b = C.c_size_t(), C.c_size_t()
         L.check(self.lib.nm_rollout_workspace_bytes(C.byref(p), B, C.byref(fwd_b), C.byref(bwd_b)),
                 "nm_rollout_workspace_bytes")
@@ -483,8 +491,21 @@ class RawTrainStep:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
+    def all_reduce(self):
+        """SUM over ranks of [gradient | scalars] of the step just computed -> ``gbuf`` (``grad`` / ``scalars`` views)."""
+        if self.sync is not None:
+            self.sync.all_reduce(self.gbuf)
+            self.grad, self.scalars = self.gbuf[:self._n], self.gbuf[self._n:]
+            self.launches += 1
+        elif self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.gbuf)
+
     def forward(self):
         p = self.plan.c
+        if self.sync is not None:                  # this step's half of the symmetric buffer receives scalars and gradients
+            half = self.sync.half()
+            self.grad, self.scalars = half[:self._n], half[self._n:]
         L.check(self.lib.nm_rollout_forward(
             C.byref(p), _ptr(self.runner.arena.flat), _ptr(self.x0), self.exo_ptrs, _ptr(self.x_traj),
             _ptr(self.u_traj), _ptr(self.y_traj), C.c_void_p(self.scalars.data_ptr()), _ptr(self.chk), _ptr(self.ws),
