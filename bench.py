@@ -264,14 +264,28 @@ def main():
     batch = make_inputs(case, B, dev, rank)                   # per-rank shard of the sampled batch, resident in HBM
     sync = GradientSync() if world > 1 else None
     plan = case.system.plan_for(case.system.init(dict(batch)), loss=case.problem.loss)
-    raw = nr.RawTrainStep(plan, batch, world_size=world)
+    # data-parallel exchange: in-kernel sum over NVLink peer memory (nm_grad_allreduce: NVLS multimem.ld_reduce), NCCL only
+    # when the symmetric allocation is not available on this box or NM_SYNC=nccl asks for it
+    exchange = "none (one rank)"
+    raw = None
+    if world > 1 and os.environ.get("NM_SYNC", "peer") != "nccl":
+        try:
+            raw = nr.RawTrainStep(plan, batch, world_size=world, peer_sync=True)
+            exchange = f"in-kernel all-reduce over symmetric memory ({raw.sync.mode}), {4 * raw.sync.n} B per step"
+        except Exception as e:                                 # noqa: BLE001
+            print(f"[bench] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            raw = None
+    if raw is None:
+        raw = nr.RawTrainStep(plan, batch, world_size=world)
+        if world > 1:
+            exchange = f"NCCL all-reduce, {4 * raw.gbuf.numel()} B per step"
+    cfg["exchange"] = exchange
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_raw():
         raw.forward()
         raw.backward()
-        if sync is not None:
-            sync.allreduce_flat_(raw.gbuf)
+        raw.all_reduce()
 
     def barrier():
         if world > 1:
@@ -295,8 +309,7 @@ def main():
         ev[i][1].record()
         raw.backward()
         ev[i][2].record()
-        if sync is not None:
-            sync.allreduce_flat_(raw.gbuf)
+        raw.all_reduce()
         ev[i][3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0

@@ -103,6 +103,11 @@ class GradientSync:
         self.rank = dist.get_rank(group)
         rollout.set_world_size(self.world_size)
         self._flat: Optional[torch.Tensor] = None
+        # CUDA buffers are summed by the in-kernel exchange over NVLink peer memory (PeerAllReduce); NCCL / gloo otherwise
+        # (NM_SYNC=nccl, CPU tensors, or a box without symmetric-memory support)
+        import os
+        self._peer_ok = os.environ.get("NM_SYNC", "peer") != "nccl"
+        self._peer = {}
 
     def shard(self, n_total: int):
         """Row range ``[lo, hi)`` of a global batch owned by this rank (equal shards)."""
@@ -114,6 +119,17 @@ class GradientSync:
     def allreduce_flat_(self, flat: torch.Tensor) -> torch.Tensor:
         """In-place SUM all-reduce of an already flat buffer (the adjoint kernel's output)."""
         if self.world_size > 1:
+            if self._peer_ok and flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous():
+                key = (flat.numel(), flat.device)
+                if key not in self._peer:
+                    try:
+                        self._peer[key] = PeerAllReduce(flat.numel(), flat.device, group=self.group)
+                    except Exception:                            # noqa: BLE001 -- no symmetric memory on this box
+                        self._peer_ok = False
+                sync = self._peer.get(key)
+                if sync is not None:
+                    sync.half().copy_(flat)
+                    return sync.all_reduce(flat)
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         return flat
 
