@@ -56,8 +56,9 @@ __device__ __forceinline__ float term_value(const NmTerm& tm, const VarTable& vt
 
 // BarrierLoss entries with value v < 0 (reference loss.py:196-214, 240-246): barrier(v), nan / +inf -> 0, clamped to
 // [0, ub]; `df` = its derivative with autograd's conventions (the masked assignments and the clamp outside [0, ub] pass none)
-__device__ __forceinline__ float barrier_eval(const NmPlan& p, int kind, float v, float& df) {
-  const float a = p.barrier_alpha;
+// (out of line on purpose: six transcendental variants inlined at every runtime-descriptor call site grew the FFMA adjoint
+// ten-fold; only BarrierLoss plans ever take the call)
+static __device__ __noinline__ float barrier_eval_ool(float a, float shift, float ub, int kind, float v, float& df) {
   float f;
   switch (kind) {
     case NM_BARRIER_LOG10:    f = -log10f(-v); df = -0.4342944819032518f / v; break;
@@ -65,12 +66,15 @@ __device__ __forceinline__ float barrier_eval(const NmPlan& p, int kind, float v
     case NM_BARRIER_INVERSE:  f = 1.f / (-v); df = 1.f / (v * v); break;
     case NM_BARRIER_SOFTEXP:  { const float e = expf(a * v); f = (e - 1.f) / a + a; df = e; } break;
     case NM_BARRIER_SOFTLOG:  { const float q = 1.f + a * (-v - a); f = -logf(q) / a; df = 1.f / q; } break;
-    default:                  f = expf(v + p.barrier_shift); df = f; break;
+    default:                  f = expf(v + shift); df = f; break;
   }
   if (!(f == f) || f == INFINITY) { f = 0.f; df = 0.f; }
   if (f < 0.f) { f = 0.f; df = 0.f; }
-  else if (f > p.barrier_ub) { f = p.barrier_ub; df = 0.f; }
+  else if (f > ub) { f = ub; df = 0.f; }
   return f;
+}
+__device__ __forceinline__ float barrier_eval(const NmPlan& p, int kind, float v, float& df) {
+  return barrier_eval_ool(p.barrier_alpha, p.barrier_shift, p.barrier_ub, kind, v, df);
 }
 
 __device__ __forceinline__ float term_penalty(const NmPlan& pl, const NmTerm& tm, float v) {
