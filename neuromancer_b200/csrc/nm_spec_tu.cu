@@ -217,7 +217,21 @@ template <class Sp> struct Wide<Sp, true> {
   static size_t staging_bytes(int64_t B, int T) { return a256(size_t((B + 127) / 128) * size_t(chunk_steps(B, T)) * size_t(C::ITEM_BYTES)); }
   static size_t stash_bytes(int sms) { return a256(size_t(sms) * 2 * size_t(C::STASH_SLOT_BYTES)); }
   static size_t carry_bytes(int64_t B) { return a256(size_t(B) * Sp::NX * sizeof(float)); }
-  static size_t g_bytes(int64_t B, int T) { return a256(size_t(B) * size_t(chunk_steps(B, T) + 1) * size_t(Sp::NX + Sp::NU) * sizeof(float)); }
+  // steps per term-gradient launch: a multiple of the chunk length, G capped at NM_WIDE_G_GB (default 6).  The trajectories are
+  // [B][T][nx] (the reference's layout): a launch that covers few steps reads 48-byte rows 9.6 KB apart and pays DRAM page
+  // misses for every one of them (measured 6x its HBM floor at 2 steps per launch) -- long groups read long contiguous runs
+  static int group_steps(int64_t B, int T) {
+    const int cs = chunk_steps(B, T);
+    double cap_gb = 6.0;
+    if (const char* s = getenv("NM_WIDE_G_GB")) { const double v = atof(s); if (v > 0.0) cap_gb = v; }
+    const double per_step = double(B) * double(Sp::NX + Sp::NU) * sizeof(float);
+    int64_t k = int64_t(cap_gb * 1073741824.0 / per_step - 1.0) / cs;
+    if (k < 1) k = 1;
+    int64_t gs = k * cs;
+    if (gs > T) gs = (T + cs - 1) / cs * cs;
+    return int(gs);
+  }
+  static size_t g_bytes(int64_t B, int T) { return a256(size_t(B) * size_t(group_steps(B, T) + 1) * size_t(Sp::NX + Sp::NU) * sizeof(float)); }
   // [scale state 256 B | co-state carry | derivative stash | chunk term gradients | staging]
   static size_t bwd_extra(int64_t B, int T, int sms) { return 256 + carry_bytes(B) + stash_bytes(sms) + g_bytes(B, T) + staging_bytes(B, T); }
   static int grid_for(int64_t B, int sms) { const int64_t pairs = ((B + 127) / 128 + 1) / 2; return int(pairs < sms ? pairs : sms); }
@@ -300,11 +314,17 @@ template <class Sp> struct Wide<Sp, true> {
     const int grid = grid_for(a.B, sms);
     // (Measured and dropped: the term-gradient kernels of chunk i+1 on a side stream next to the weight-gradient GEMM of
     // chunk i -- both want DRAM bandwidth, the step got 3 % slower.)
+    const int GS = group_steps(a.B, T);
+    int g_lo = T, g_hi = T;                                  // term gradients of [g_lo, g_hi] are in G
     for (int t_hi = T; t_hi > 0; t_hi -= CS) {
       const int t_lo = t_hi - CS > 0 ? t_hi - CS : 0;
+      if (t_lo < g_lo) {                                       // next group of chunks (GS is a multiple of CS: chunks never straddle groups)
+        g_hi = t_hi; g_lo = g_hi - GS > 0 ? g_hi - GS : 0;
+        launches += launch_termgrad(p, a, G, g_lo, g_hi, sms, st);
+      }
       WideBwdArgs w{};
       w.b = a; w.staging = staging; w.stash = stash; w.lam_carry = carry; w.scale = scale; w.G = G; w.t_lo = t_lo; w.t_hi = t_hi;
-      launches += launch_termgrad(p, a, G, t_lo, t_hi, sms, st);
+      w.g_lo = g_lo; w.g_nt = g_hi - g_lo + 1;
       nm_wide_bwd_kernel<Sp><<<grid, C::BWD_THREADS, C::SMEM_BYTES, st>>>(p, w);
       const int64_t n_items = tiles * int64_t(t_hi - t_lo);
       const int wgrid = int(n_items < sms ? n_items : sms);

@@ -732,7 +732,9 @@ struct WideBwdArgs {
   float* stash;                  // [grid * 2] slots of WideCfg::STASH_SLOT_BYTES
   float* lam_carry;              // [B][NX] co-state at the chunk boundary
   wd::ScaleState* scale;         // cotangent scale of this chunk (read), largest scaled cotangent seen (atomic max)
-  const float* G;                // loss-term gradients of this chunk [B][t_hi - t_lo + 1][NX + NU] (nm_wide_termgrad_kernel)
+  const float* G;                // loss-term gradients of this chunk's GROUP of chunks [B][g_nt][NX + NU], row tt = time g_lo + tt
+                                 // (nm_wide_termgrad_kernel: one launch per group -- long contiguous reads of every trajectory's rows)
+  int g_lo, g_nt;
   int t_lo, t_hi;                // this launch sweeps steps t_hi-1 .. t_lo  (t_hi == nsteps: the first chunk of the pass)
 };
 
@@ -962,13 +964,13 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
     auto load_rows = [&](int64_t bq, int tq) {
       wd::ld_row<NX>(x_pre, args.x_traj + (bq * (T + 1) + tq) * NX);
       wd::ld_row<NU>(o_pre, args.chk + (bq * T + tq) * NU);
-      wd::ld_row<RW>(g_pre, wargs.G + (bq * int64_t(CSn + 1) + (tq - t_lo)) * RW);
+      wd::ld_row<RW>(g_pre, wargs.G + (bq * int64_t(wargs.g_nt) + (tq - wargs.g_lo)) * RW);
       wd::policy_exo<S, K0>(p, args.exo, bq, tq, in_pre);
     };
     auto load_lam = [&](int64_t bq) {
       if (t_hi == T) {
         float gT[RW];
-        wd::ld_row<RW>(gT, wargs.G + (bq * int64_t(CSn + 1) + CSn) * RW);
+        wd::ld_row<RW>(gT, wargs.G + (bq * int64_t(wargs.g_nt) + (T - wargs.g_lo)) * RW);
 #pragma unroll
         for (int i = 0; i < NX; ++i) lam_pre[i] = gT[i];
       } else wd::ld_row<NX>(lam_pre, wargs.lam_carry + bq * NX);
@@ -978,7 +980,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
       else {
         l2_hint(args.x_traj + (bq * (T + 1) + tq) * NX, NX);
         l2_hint(args.chk + (bq * T + tq) * NU, NU);
-        l2_hint(wargs.G + (bq * int64_t(CSn + 1) + (tq - t_lo)) * RW, RW);
+        l2_hint(wargs.G + (bq * int64_t(wargs.g_nt) + (tq - wargs.g_lo)) * RW, RW);
         static_for<0, S::NSEG>([&](auto sc) {
           constexpr int sg = decltype(sc)::value;
           if constexpr (S::seg_kind(sg) == NM_SEG_EXO) {
@@ -993,7 +995,7 @@ __global__ void __launch_bounds__(wd::WideCfg<S>::BWD_THREADS, 1) nm_wide_bwd_ke
       const int64_t bq = bq_raw < args.B ? bq_raw : args.B - 1;
       prefetch_rows(bq, t_hi - 1);
       if constexpr (REGPF) load_lam(bq);
-      else l2_hint(t_hi == T ? wargs.G + (bq * int64_t(CSn + 1) + CSn) * RW : wargs.lam_carry + bq * NX, NX);
+      else l2_hint(t_hi == T ? wargs.G + (bq * int64_t(wargs.g_nt) + (T - wargs.g_lo)) * RW : wargs.lam_carry + bq * NX, NX);
     };
     if (primary && int(blockIdx.x) * 2 + slot < args.num_tiles) prefetch_tile(int(blockIdx.x) * 2 + slot);
     for (int r = 0;; ++r) {

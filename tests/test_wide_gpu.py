@@ -71,22 +71,29 @@ def test_c5_wide_forward_and_forced_tensor_core_adjoint_match_the_oracle(B):
         assert_slices(got["traj"][k], v.detach(), TRAJ_RTOL, f"c5 B={B} trajectory {k}")
 
 
-def test_c5_chunked_horizon_sweep_is_equivalent():
+@pytest.mark.parametrize("g_gb", [None, "0.00023", "0.00001"], ids=["one-group", "groups-of-4-chunks", "group-per-chunk"])
+def test_c5_chunked_horizon_sweep_is_equivalent(g_gb):
     """The adjoint sweeps the horizon in chunks (staging memory); the co-state crosses chunk boundaries through a buffer
     and the cotangent scale adapts per chunk.  Many short chunks must give the gradients of one long chunk (powers of
-    two scale exactly: only the fp16 rounding of the staged operands may differ by the subnormal range)."""
+    two scale exactly: only the fp16 rounding of the staged operands may differ by the subnormal range).  The loss-term
+    gradients are computed per GROUP of chunks (NM_WIDE_G_GB caps their buffer): one group for the horizon, groups of
+    four chunks, one group per chunk -- the same numbers."""
     case = H.make_case("c5", DEV, seed=4)
     batch = to_dev(case.make_batch(260, "cpu", 8))
     one = _grads_with(case, batch, "1")
-    old = os.environ.get("NM_WIDE_STAGING_GB")
-    os.environ["NM_WIDE_STAGING_GB"] = "0.003"          # 3 tiles x 268 KB per step -> chunks of 3 steps
+    env = {"NM_WIDE_STAGING_GB": "0.003"}               # 3 tiles x 268 KB per step -> chunks of 3 steps
+    if g_gb is not None:
+        env["NM_WIDE_G_GB"] = g_gb                      # 260 trajectories x 72 B per step: 12 steps / 1 step (-> one chunk) per group
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         many = _grads_with(case, batch, "1")
     finally:
-        if old is None:
-            os.environ.pop("NM_WIDE_STAGING_GB", None)
-        else:
-            os.environ["NM_WIDE_STAGING_GB"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     for i, (a, b) in enumerate(zip(many["grads"], one["grads"])):
         assert_rel(a, b, 2e-5, f"c5 chunked vs single sweep, grad {i}")
 
