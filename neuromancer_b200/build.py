@@ -171,6 +171,8 @@ def spec_header(p: L.NmPlan, tune_override: Dict[str, int] = None) -> str:
     name = spec_name(sig + "#" + term_signature_of(p))
     tune_map = tune_override if tune_override is not None else tuning_for(sig)
     tune = "".join(f"#define NM_TUNE_{k.upper()} {v}\n" for k, v in sorted(tune_map.items()))
+    # BarrierLoss terms among the compiled ones?  (nm_terms.cuh compiles the barrier branch out of the unit otherwise)
+    tune += f"#define NM_SPEC_BARRIER {int(any((p.terms[k].norm >> 4) & 15 for k in range(p.n_terms)))}\n"
     nd = p.exo[p.dist_exo].width if p.dist_exo >= 0 else 0
     segs = [p.segs[i] for i in range(p.n_segs)] if p.has_policy else []
     integ = p.integrator if p.dyn_kind == L.NM_DYN_ODE else 0

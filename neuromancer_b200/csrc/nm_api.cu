@@ -478,9 +478,31 @@ int nm_plan_signature(const NmPlan* plan, char* buf, int cap) {
   return (int)s.size();
 }
 
+// The (shape, term) lookup of every entry point.  A plan with BarrierLoss terms runs ONLY on a class compiled with its own
+// term structure: the per-class kernels carry the barrier code in their compiled term evaluators and nowhere else (the
+// runtime-descriptor branch inside them cost the tensor-core adjoints 2-4 %), so another class of the same shape cannot serve it.
+bool plan_has_barrier(const NmPlan* p) {
+  for (int k = 0; k < p->n_terms; ++k) if (NM_TERM_BARRIER(p->terms[k].norm) != NM_BARRIER_NONE) return true;
+  return false;
+}
+std::string no_kernel_message(const NmPlan* plan) {
+  return "no compiled specialisation for " + make_signature(plan) +
+         (plan_has_barrier(plan) ? " with this BarrierLoss plan's term structure (neuromancer_b200.build.ensure_specialisation builds it)" : "");
+}
+NmKernelEntry* lookup(const NmPlan* plan, int* fused = nullptr) {
+  int f = 0;
+  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &f);
+  if (fused) *fused = f;
+  if (e != nullptr && !f && plan_has_barrier(plan)) {
+    nm_set_error("BarrierLoss plan: no specialisation compiled with this term structure (neuromancer_b200.build.ensure_specialisation builds it)");
+    return nullptr;
+  }
+  return e;
+}
+
 int nm_has_kernel(const NmPlan* plan) {
   if (validate(plan) != NM_OK) return 0;
-  return find_entry(make_signature(plan).c_str()) != nullptr ? 1 : 0;
+  return lookup(plan) != nullptr ? 1 : 0;
 }
 
 int nm_num_kernels(void) { return g_count; }
@@ -496,7 +518,7 @@ const char* nm_kernel_signature(int i) {
 const char* nm_kernel_info(const NmPlan* plan) {
   if (validate(plan) != NM_OK) return nullptr;
   int fused = 0;
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &fused);
+  NmKernelEntry* e = lookup(plan, &fused);
   if (!e) return nullptr;
   static thread_local char buf[320];
   std::snprintf(buf, sizeof(buf), "%s fused_terms=%d", e->info, fused);
@@ -532,7 +554,7 @@ int nm_rollout_checkpoint_bytes(const NmPlan* plan, int64_t B, size_t* bytes) {
   // a shape class on the tensor-core path states what its kernels keep (policy mode: the raw policy output o_t)
   // (the same (shape, term) lookup as nm_rollout_forward / nm_rollout_backward: entries of one shape class may be
   // compiled with different tuning, and with it different checkpoint layouts)
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str());
+  NmKernelEntry* e = lookup(plan);
   if (e != nullptr && e->chk_floats_per_step >= 0) {
     *bytes = size_t(B) * size_t(plan->nsteps) * size_t(e->chk_floats_per_step) * sizeof(float);
     return NM_OK;
@@ -548,8 +570,8 @@ int nm_rollout_workspace_bytes(const NmPlan* plan, int64_t B, size_t* fwd_bytes,
   int rc = validate(plan);
   if (rc != NM_OK) return rc;
   if (B < 1 || !fwd_bytes || !bwd_bytes) { nm_set_error("bad arguments"); return NM_ERR_BAD_PLAN; }
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str());
-  if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  NmKernelEntry* e = lookup(plan);
+  if (!e) { nm_set_error(no_kernel_message(plan).c_str()); return NM_ERR_NO_KERNEL; }
   rc = e->workspace(plan, B, fwd_bytes, bwd_bytes);
   if (rc != NM_OK) return rc;
   // API-owned tail: block partials of the scoring kernel / precomputed term gradients
@@ -567,8 +589,8 @@ int nm_rollout_forward(const NmPlan* plan, const float* params, const float* x0,
   if (B < 1 || !x0 || !x_traj || !scalars || !workspace || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj) ||
       (plan->n_params > 0 && !params)) { nm_set_error("null pointer argument"); return NM_ERR_BAD_PLAN; }
   int fused = 0;
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &fused);
-  if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  NmKernelEntry* e = lookup(plan, &fused);
+  if (!e) { nm_set_error(no_kernel_message(plan).c_str()); return NM_ERR_NO_KERNEL; }
   size_t spec_f = 0, spec_b = 0;
   rc = e->workspace(plan, B, &spec_f, &spec_b);
   if (rc != NM_OK) return rc;
@@ -608,8 +630,8 @@ int nm_rollout_backward(const NmPlan* plan, const float* params, const float* co
   if (B < 1 || b_total < B || !x_traj || !workspace || (plan->nu > 0 && !u_traj) || (plan->ny > 0 && !y_traj) ||
       (plan->n_params > 0 && (!params || !grad_params))) { nm_set_error("null pointer / bad size argument"); return NM_ERR_BAD_PLAN; }
   int fused = 0;
-  NmKernelEntry* e = find_entry(make_signature(plan).c_str(), make_term_signature(plan).c_str(), &fused);
-  if (!e) { nm_set_error(("no compiled specialisation for " + make_signature(plan)).c_str()); return NM_ERR_NO_KERNEL; }
+  NmKernelEntry* e = lookup(plan, &fused);
+  if (!e) { nm_set_error(no_kernel_message(plan).c_str()); return NM_ERR_NO_KERNEL; }
   size_t spec_f = 0, spec_b = 0;
   rc = e->workspace(plan, B, &spec_f, &spec_b);
   if (rc != NM_OK) return rc;

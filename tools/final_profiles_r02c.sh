@@ -4,7 +4,7 @@ set -x
 python -m pytest tests -m gpu -q > gpurun_out/r02c_gpu_tests.txt 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02c_smoke.txt 2>&1
 # the default bench command (C5, global batch 4,194,304), plain, then its launch list
-/usr/bin/time -v python bench.py > gpurun_out/r02c_bench_c5_default.json 2> gpurun_out/r02c_bench_c5_default.err
+python bench.py > gpurun_out/r02c_bench_c5_default.json 2> gpurun_out/r02c_bench_c5_default.err
 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-per-config > gpurun_out/r02c_plain_a.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02c_c5_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-per-config > gpurun_out/r02c_ncu_launches.log 2>&1
