@@ -154,12 +154,20 @@ template <class Sp> struct TcBwd<Sp, true> {
   static constexpr size_t W_BYTES = TcBKCfg<Sp>::W_BYTES;
   static constexpr bool WG3 = TcBKCfg<Sp>::WG3;
   static constexpr int EVALS = TcMode<Sp>::EVALS, CTAS = TcBKCfg<Sp>::CTAS_PER_SM, THREADS = TcBKCfg<Sp>::THREADS;
+  static constexpr bool HAS_FO = Sp::NTERMS > 0;          // a second instantiation without any runtime-descriptor term code
   static cudaError_t setup() {
-    return cudaFuncSetAttribute(nm_tc_bwd_kernel<Sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcBKCfg<Sp>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(nm_tc_bwd_kernel<Sp, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcBKCfg<Sp>::SMEM_BYTES);
+    if constexpr (HAS_FO) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_tc_bwd_kernel<Sp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcBKCfg<Sp>::SMEM_BYTES);
+    }
+    return e;
   }
   static void launch(const NmPlan& p, const BwdArgs& a, const float* params, float* wprep, int grid, cudaStream_t st) {
     nm_tc_prep_bwd_kernel<Sp><<<16, 256, 0, st>>>(p, params, wprep);
-    nm_tc_bwd_kernel<Sp><<<grid, TcBKCfg<Sp>::THREADS, TcBKCfg<Sp>::SMEM_BYTES, st>>>(p, a);
+    if constexpr (HAS_FO) {
+      if (a.fused_terms) { nm_tc_bwd_kernel<Sp, true><<<grid, TcBKCfg<Sp>::THREADS, TcBKCfg<Sp>::SMEM_BYTES, st>>>(p, a); return; }
+    }
+    nm_tc_bwd_kernel<Sp, false><<<grid, TcBKCfg<Sp>::THREADS, TcBKCfg<Sp>::SMEM_BYTES, st>>>(p, a);
   }
 };
 template <class Sp, bool EL> struct TcBwdEligible { static constexpr bool value = false; };

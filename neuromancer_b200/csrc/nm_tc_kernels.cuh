@@ -512,7 +512,10 @@ __global__ void nm_tc_prep_bwd_kernel(const __grid_constant__ NmPlan plan, const
 }
 
 
-template <class S>
+// FUSED_ONLY: the instantiation for plans served by the class's COMPILED term structure -- no runtime-descriptor term code
+// (pre-computed G rows, time-broadcast lanes, out-of-line evaluators) in the kernel at all.  The adjoint is sensitive to the
+// mere presence of such code (profiles/r02c_barrier_ab.txt); the dispatcher picks the instantiation by args.fused_terms.
+template <class S, bool FUSED_ONLY = false>
 __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) nm_tc_bwd_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args) {
   using BK = TcBKCfg<S>;
   using MD = typename BK::MD;
@@ -539,17 +542,20 @@ __global__ void __launch_bounds__(TcBKCfg<S>::THREADS, TcBKCfg<S>::CTAS_PER_SM) 
   const NmPlan& p = plan;
   const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
   const int T = p.nsteps;
-  const bool fused = S::NTERMS > 0 && args.fused_terms;
-  const bool pre = !fused && args.G_x != nullptr;
+  constexpr bool FO = FUSED_ONLY && S::NTERMS > 0;
+  const bool fused = FO || (S::NTERMS > 0 && args.fused_terms);
+  const bool pre = !FO && !fused && args.G_x != nullptr;
   const int g_row = (T + 1) * NX + T * (NU + S::NY), g_yoff = (T + 1) * NX + T * NU;
   int tb_mask = 0;
-  for (int k = 0; k < p.n_terms; ++k) {
-    const NmTerm& tm = p.terms[k];
-    const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
-    const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
+  if constexpr (!FO) {
+    for (int k = 0; k < p.n_terms; ++k) {
+      const NmTerm& tm = p.terms[k];
+      const NmAtom* at[4] = {&tm.lhs.a, &tm.lhs.b, &tm.rhs.a, &tm.rhs.b};
+      const bool live[4] = {true, tm.lhs.op != NM_OP_NONE, true, tm.rhs.op != NM_OP_NONE};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (live[i] && at[i]->var >= 0 && at[i]->var <= NM_VAR_Y && atom_is_tbcast(*at[i], tm)) tb_mask |= 1 << at[i]->var;
+      for (int i = 0; i < 4; ++i)
+        if (live[i] && at[i]->var >= 0 && at[i]->var <= NM_VAR_Y && atom_is_tbcast(*at[i], tm)) tb_mask |= 1 << at[i]->var;
+    }
   }
   if (tid < NM_MAX_TERMS) coef[tid] = tid < p.n_terms ? term_coef(p, tid, args.grad_scalars, args.b_total) : 0.f;
   float* gblock = args.grad_partials + size_t(blockIdx.x) * size_t(p.n_params > 0 ? p.n_params : 1);
