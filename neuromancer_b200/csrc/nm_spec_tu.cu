@@ -269,7 +269,8 @@ template <class Sp> struct Wide<Sp, true> {
     const int64_t n = a.B * int64_t(t_hi - t_lo + 1);
     int64_t g = (n + 255) / 256;
     if (g > int64_t(sms) * 16) g = int64_t(sms) * 16;
-    nm_wide_termgrad_kernel<Sp><<<int(g), 256, 0, st>>>(p, a, G, t_lo, t_hi);
+    if (Sp::NTERMS > 0 && a.fused_terms) nm_wide_termgrad_kernel<Sp, true><<<int(g), 256, 0, st>>>(p, a, G, t_lo, t_hi);
+    else nm_wide_termgrad_kernel<Sp, false><<<int(g), 256, 0, st>>>(p, a, G, t_lo, t_hi);
     // time-broadcast atoms anchored inside this chunk: one warp per trajectory sums the range
     WideTbAnchors an{};
     for (int k = 0; k < p.n_terms && an.n < 8; ++k) {

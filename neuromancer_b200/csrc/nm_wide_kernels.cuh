@@ -742,7 +742,9 @@ struct WideBwdArgs {
 // tt <= t_hi - t_lo (the last row only matters when t_hi == nsteps), G[b][tt][NX:] = d loss / d u[b, t_lo + tt, :] for
 // tt < t_hi - t_lo.  Time-broadcast atoms (x[:, [-1], :] against a whole range) are left to the adjoint sweep, where all
 // lanes sit at the same time index (see term_grad_entry).  External gradients (Python-evaluated terms) are added here.
-template <class S>
+// (FUSED_ONLY: the instantiation for plans served by the compiled term structure -- no runtime-descriptor code, no VarTable in
+// shared memory; picked by the launcher from args.fused_terms)
+template <class S, bool FUSED_ONLY = false>
 __global__ void __launch_bounds__(256) nm_wide_termgrad_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args,
                                                                float* __restrict__ G, int t_lo, int t_hi) {
   constexpr int NX = S::NX, NU = S::NU, RW = NX + NU;
@@ -761,7 +763,8 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_kernel(const __grid_cons
   }
   __syncthreads();
   const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
-  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  constexpr bool FO = FUSED_ONLY && S::NTERMS > 0;
+  const bool fused = FO || (S::NTERMS > 0 && args.fused_terms);
   const int NT = t_hi - t_lo + 1;
   const int NTW = t_hi == T ? NT : NT - 1;              // rows worth computing: the x row of t_hi only matters at the end of the horizon
   const int64_t n = args.B * NTW;
@@ -790,7 +793,7 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_kernel(const __grid_cons
         if (want_x) term_grad_s<S, NM_VAR_X, NX, NX, 1>(p, vtc, coef, b, t, gx);
         if (want_u) term_grad_s<S, NM_VAR_U, NU, NU, 1>(p, vtc, coef, b, t, gu);
       }
-    } else {
+    } else if constexpr (!FO) {
       if (want_x) term_grad_accum<NX, 1>(p, vt, coef, b, NM_VAR_X, t, NX, gx);
       if (want_u) term_grad_accum<NU, 1>(p, vt, coef, b, NM_VAR_U, t, NU, gu);
     }
