@@ -289,7 +289,8 @@ template <class Sp> struct Wide<Sp, true> {
     if (an.n > 0) {
       int64_t gw = (a.B * 32 + 255) / 256;
       if (gw > int64_t(sms) * 16) gw = int64_t(sms) * 16;
-      nm_wide_termgrad_tb_kernel<Sp><<<int(gw), 256, 0, st>>>(p, a, an, G, t_lo, t_hi);
+      if (Sp::NTERMS > 0 && a.fused_terms) nm_wide_termgrad_tb_kernel<Sp, true><<<int(gw), 256, 0, st>>>(p, a, an, G, t_lo, t_hi);
+      else nm_wide_termgrad_tb_kernel<Sp, false><<<int(gw), 256, 0, st>>>(p, a, an, G, t_lo, t_hi);
       ++launches;
     }
     return launches;

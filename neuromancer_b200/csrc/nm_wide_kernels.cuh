@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_kernel(const __grid_cons
 // gradient of the anchored entry is a sum over the range -- one warp per trajectory, range strided over the lanes, fixed
 // shuffle order (deterministic), added to the rows nm_wide_termgrad_kernel wrote.  `anchor` lists the anchored times.
 struct WideTbAnchors { int n; int var[8]; int t[8]; };
-template <class S>
+template <class S, bool FUSED_ONLY = false>
 __global__ void __launch_bounds__(256) nm_wide_termgrad_tb_kernel(const __grid_constant__ NmPlan plan, const __grid_constant__ BwdArgs args,
                                                                   const __grid_constant__ WideTbAnchors anchors, float* __restrict__ G, int t_lo, int t_hi) {
   constexpr int NX = S::NX, NU = S::NU, RW = NX + NU, MAXD = NX > NU ? NX : NU;
@@ -838,7 +838,8 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_tb_kernel(const __grid_c
   const int lane = threadIdx.x & 31, NT = t_hi - t_lo + 1;
   const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const VarTable vtc = make_vartable_regs(p, args, S::NX, S::NU, S::NY);
-  const bool fused = S::NTERMS > 0 && args.fused_terms;
+  constexpr bool FO = FUSED_ONLY && S::NTERMS > 0;
+  const bool fused = FO || (S::NTERMS > 0 && args.fused_terms);
   for (int64_t b = warp0; b < args.B; b += nwarps) {
     for (int a = 0; a < anchors.n; ++a) {
       const int var = anchors.var[a], t = anchors.t[a], dim = var == NM_VAR_X ? NX : NU;
@@ -850,7 +851,7 @@ __global__ void __launch_bounds__(256) nm_wide_termgrad_tb_kernel(const __grid_c
           if (var == NM_VAR_X) term_grad_s<S, NM_VAR_X, NX, MAXD, 2>(p, vtc, coef, b, t, g, lane, 32);
           else term_grad_s<S, NM_VAR_U, NU, MAXD, 2>(p, vtc, coef, b, t, g, lane, 32);
         }
-      } else term_grad_accum_tb_lanes<MAXD>(p, vt, coef, b, var, t, dim, lane, g);
+      } else if constexpr (!FO) term_grad_accum_tb_lanes<MAXD>(p, vt, coef, b, var, t, dim, lane, g);
 #pragma unroll
       for (int d = 0; d < MAXD; ++d) {
 #pragma unroll
