@@ -1337,7 +1337,10 @@ struct ExoTcCfg {
   static constexpr int IMG_FLOATS = round_up(KE, 8) * NP;                 // one weight image [k/4][NP][4]
   static constexpr int W_FLOATS = 2 * IMG_FLOATS + round_up(NP, 32);      // hi | lo | bias
   static constexpr int A_FLOATS = wmax() * 128;                           // one operand tile [k/4][128][4]
-  static constexpr size_t SMEM_BYTES = size_t(W_FLOATS + 2 * A_FLOATS) * 4 + 256;
+  static constexpr int NRAW = 3, RAW_FLOATS = wmax() * 128;               // ring of raw 128-row slices as they lie in global memory
+  static constexpr int nsx() { int n = 0; for (int i = 0; i < S::NSEG; ++i) if (S::seg_kind(i) == NM_SEG_EXO) ++n; return n > 0 ? n : 1; }
+  static constexpr int ACC_COLS = tc::pow2_ceil(2 * NP) < 32 ? 32 : tc::pow2_ceil(2 * NP);   // two accumulators (alternating tiles)
+  static constexpr size_t SMEM_BYTES = size_t(W_FLOATS + 4 * A_FLOATS + NRAW * RAW_FLOATS) * 4 + 256;
   static constexpr bool OK = KC::HOIST && NP <= 256 && SMEM_BYTES <= 227 * 1024 && KE % 8 == 0;
 };
 
@@ -1358,118 +1361,190 @@ __global__ void nm_exo_tc_prep_kernel(const __grid_constant__ NmPlan plan, const
   for (int idx = gtid; idx < round_up(X::NP, 32); idx += gthreads) wexo[2 * X::IMG_FLOATS + idx] = (idx < X::N0 && plan.policy.has_bias) ? bg[idx] : 0.f;
 }
 
+// TMA-fed: the 128 x W row slices of a tile are CONTIGUOUS in global memory (rows r = b * T + t of a [B][T][W] tensor), so
+// one elected thread streams them as 1-D bulk copies (cp.async.bulk, SASS UBLKCP) into a ring of raw tiles, NRAW items
+// (tile, segment) ahead, completion on an mbarrier.  The 128 threads turn a raw tile into the K-major operand tile and
+// its remainder tile (bank-conflict-free: thread = row, the k-chunk rotated by the row), double-buffered, so the MMAs of
+// item i run while item i + 1 is converted; two accumulators alternate between tiles, the epilogue of a tile overlaps
+// the next tile's first MMAs.  (The register-prefetch version before it sat at 40 % of the DRAM peak on long-scoreboard
+// stalls with 8 warps per SM: profiles/r02c_c4_ncu_summary.txt.)
 template <class S>
-__global__ void __launch_bounds__(128, 2) nm_exo_gemm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ wexo,
+__global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ wexo,
                                                                     const __grid_constant__ ExoPtrs exo, float* __restrict__ E, int64_t B) {
   using X = ExoTcCfg<S>;
-  constexpr int N0 = X::N0, NP = X::NP;
+  constexpr int N0 = X::N0, NP = X::NP, NRAW = X::NRAW, NSX = X::nsx();
   extern __shared__ __align__(128) float smem[];
   float* sm_w = smem;                                           // hi | lo | bias
-  float* a_hi = smem + X::W_FLOATS;
-  float* a_lo = a_hi + X::A_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_lo + X::A_FLOATS);      // [0] weight TMA, [1] MMA completion
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* a_hi = smem + X::W_FLOATS;                             // [2][A_FLOATS]
+  float* a_lo = a_hi + 2 * X::A_FLOATS;                         // [2][A_FLOATS]
+  float* raw = a_lo + 2 * X::A_FLOATS;                          // [NRAW][RAW_FLOATS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + NRAW * X::RAW_FLOATS);
+  uint64_t* mma_done = bars + 1;                                // [2]  MMAs that read operand buffer 0 / 1 have completed (tcgen05.commit)
+  uint64_t* a_ready = bars + 3;                                 // [2]  the 128 converters have written operand buffer 0 / 1 (and drained its raw tile)
+  uint64_t* full = bars + 5;                                    // [NRAW]  raw tile landed (TMA transaction bytes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + NRAW);
   const int tid = threadIdx.x, warp = tid >> 5;
   const NmPlan& p = plan;
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-  if (warp == 0) tc::tmem_alloc<32>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+    mbar_init(&a_ready[0], 128); mbar_init(&a_ready[1], 128);
+    for (int i = 0; i < NRAW; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<X::ACC_COLS>(tmem_slot);
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = uint32_t(warp * 32) << 16;
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], uint32_t(X::W_FLOATS) * 4);
-    tma_bulk_g2s(sm_w, wexo, uint32_t(X::W_FLOATS) * 4, &bars[0]);
-  }
-  mbar_wait(&bars[0], 0);
-  uint32_t phase = 0;
-  const int64_t R = B * p.nsteps;
+  const int T = p.nsteps;
+  const int64_t R = B * T;
   const int64_t tiles = (R + 127) / 128;
   constexpr uint32_t idesc = tc::idesc_tf32(128, NP);
-  // software pipeline: the row slice of the NEXT segment (of the next tile after the last one) is loaded into registers
-  // while the tensor pipe works on the current one -- every load of a slice in flight at once
-  constexpr int PF = X::wmax() / 4, S0 = exo_first_seg<S>();
-  float4 pre[PF];
-  {
-    const int64_t r0 = int64_t(blockIdx.x) * 128 + tid < R ? int64_t(blockIdx.x) * 128 + tid : R - 1;
-    exo_row_prefetch<S, S0, PF>(p, exo, r0 / p.nsteps, int(r0 % p.nsteps), pre);
-  }
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t r = tile * 128 + tid < R ? tile * 128 + tid : R - 1;
-    const int64_t b = r / p.nsteps;
-    const int t = int(r - b * p.nsteps);
-    static_for<0, S::NSEG>([&](auto sc) {
-      constexpr int s = decltype(sc)::value;
-      if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
-        constexpr int W = S::seg_width(s), OFF = exo_seg_off<S>(s), WP = round_up(W, 8);
-#pragma unroll
-        for (int k4 = 0; k4 < WP / 4; ++k4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k4 * 4 < W) v = pre[k4];
-          // the tensor core reads the hi tile truncated to tf32: the remainder is taken against the truncated value
-          float4 l;
-          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          *reinterpret_cast<float4*>(a_hi + (k4 * 128 + tid) * 4) = v;
-          *reinterpret_cast<float4*>(a_lo + (k4 * 128 + tid) * 4) = l;
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------- producer + MMA issuer
+    // One lane streams the raw tiles (NRAW items ahead) and issues the MMAs of every item as soon as its operand tiles are
+    // written; its state advances incrementally (no divisions in the loop).
+    if (tc::elect_one()) {
+      int segw[NSX], sege[NSX], segoff[NSX];
+      {
+        int n = 0;
+        static_for<0, S::NSEG>([&](auto sc) {
+          constexpr int sg = decltype(sc)::value;
+          if constexpr (S::seg_kind(sg) == NM_SEG_EXO) { segw[n] = S::seg_width(sg); sege[n] = S::seg_index(sg); segoff[n] = exo_seg_off<S>(sg); ++n; }
+        });
+      }
+      int64_t p_tile = blockIdx.x;
+      int p_sx = 0, p_slot = 0;
+      const int64_t stride_rows = int64_t(gridDim.x) * 128;
+      const int64_t p_db = stride_rows / T;
+      const int p_dt = int(stride_rows - p_db * T);
+      int64_t p_b = (int64_t(blockIdx.x) * 128) / T;
+      int p_t = int(int64_t(blockIdx.x) * 128 - p_b * T);
+      auto issue_next = [&]() {
+        if (p_tile < tiles) {
+          const int W = segw[p_sx], e = sege[p_sx];
+          float* dst = raw + p_slot * X::RAW_FLOATS;
+          const int64_t left = R - p_tile * 128;
+          const int rows = left < 128 ? int(left) : 128;
+          mbar_expect_tx(&full[p_slot], uint32_t(rows) * uint32_t(W) * 4u);
+          const int64_t steps_e = p.exo[e].steps;
+          int rr = 0, tt = p_t;
+          int64_t bb = p_b;
+          while (rr < rows) {                                   // one copy per trajectory piece (rows of one trajectory are contiguous)
+            const int n = (T - tt) < (rows - rr) ? (T - tt) : (rows - rr);
+            tma_bulk_g2s(dst + rr * W, exo.p[e] + (bb * steps_e + tt) * W, uint32_t(n) * uint32_t(W) * 4u, &full[p_slot]);
+            rr += n; ++bb; tt = 0;
+          }
         }
-        if constexpr (exo_next_seg<S>(s) >= 0) exo_row_prefetch<S, exo_next_seg<S>(s), PF>(p, exo, b, t, pre);
-        else if (tile + gridDim.x < tiles) {
-          const int64_t rn = (tile + gridDim.x) * 128 + tid < R ? (tile + gridDim.x) * 128 + tid : R - 1;
-          exo_row_prefetch<S, S0, PF>(p, exo, rn / p.nsteps, int(rn % p.nsteps), pre);
+        p_slot = p_slot + 1 == NRAW ? 0 : p_slot + 1;
+        if (++p_sx == NSX) {
+          p_sx = 0; p_tile += gridDim.x;
+          p_b += p_db; p_t += p_dt;
+          if (p_t >= T) { p_t -= T; ++p_b; }
         }
-        tc::fence_async_smem();
-        tc::fence_before();
-        __syncthreads();
-        if (tid < 32) {
+      };
+      mbar_expect_tx(&bars[0], uint32_t(X::W_FLOATS) * 4);
+      tma_bulk_g2s(sm_w, wexo, uint32_t(X::W_FLOATS) * 4, &bars[0]);
+      for (int i = 0; i < NRAW; ++i) issue_next();
+      mbar_wait(&bars[0], 0);
+      constexpr uint32_t A_LBO = 128 * 16, A_KSTEP = 2 * 128 * 16, B_LBO = NP * 16, B_KSTEP = 2 * NP * 16;
+      int64_t it = 0;
+      int tl = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tmem + uint32_t((tl & 1) * NP);
+        for (int sx = 0; sx < NSX; ++sx, ++it) {
+          const int ab = int(it & 1);
+          mbar_wait(&a_ready[ab], uint32_t(it >> 1) & 1u);      // operand tiles of this item written, its raw tile drained
           tc::fence_after();
-          constexpr uint32_t A_LBO = 128 * 16, A_KSTEP = 2 * 128 * 16, B_LBO = NP * 16, B_KSTEP = 2 * NP * 16;
-          const uint64_t ah = tc::smem_desc(smem_u32(a_hi), A_LBO, 128), al = tc::smem_desc(smem_u32(a_lo), A_LBO, 128);
-          const uint64_t wh = tc::smem_desc(smem_u32(sm_w) + (OFF / 4) * NP * 16, B_LBO, 128);
+          issue_next();                                         // item it + NRAW into the ring slot just drained
+          const int wp8 = (segw[sx] + 7) / 8;
+          const uint64_t dh = tc::smem_desc(smem_u32(a_hi + ab * X::A_FLOATS), A_LBO, 128);
+          const uint64_t dl = tc::smem_desc(smem_u32(a_lo + ab * X::A_FLOATS), A_LBO, 128);
+          const uint64_t wh = tc::smem_desc(smem_u32(sm_w) + (segoff[sx] / 4) * NP * 16, B_LBO, 128);
           const uint64_t wl = tc::desc_add(wh, X::IMG_FLOATS * 4);
-          if (tc::elect_one()) {
-            static_for<0, WP / 8>([&](auto kc) {
-              constexpr int ks = decltype(kc)::value;
-              tc::mma_ss(tmem, tc::desc_add(al, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, (OFF == 0 && ks == 0) ? 0u : 1u);
-              tc::mma_ss(tmem, tc::desc_add(ah, ks * A_KSTEP), tc::desc_add(wl, ks * B_KSTEP), idesc, 1u);
-            });
-            static_for<0, WP / 8>([&](auto kc) {
-              constexpr int ks = decltype(kc)::value;
-              tc::mma_ss(tmem, tc::desc_add(ah, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, 1u);
-            });
-            tc::commit(&bars[1]);
+          for (int ks = 0; ks < wp8; ++ks) {                    // remainder products first (the accumulator truncates)
+            tc::mma_ss(acc, tc::desc_add(dl, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, (sx == 0 && ks == 0) ? 0u : 1u);
+            tc::mma_ss(acc, tc::desc_add(dh, ks * A_KSTEP), tc::desc_add(wl, ks * B_KSTEP), idesc, 1u);
           }
-          __syncwarp();
+          for (int ks = 0; ks < wp8; ++ks) tc::mma_ss(acc, tc::desc_add(dh, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, 1u);
+          tc::commit(&mma_done[ab]);
         }
-        mbar_wait(&bars[1], phase);                             // the operand tiles are free again
-        phase ^= 1;
-        tc::fence_after();
       }
-    });
-    // epilogue: this thread's row of the accumulator + bias -> E
-    const bool valid = tile * 128 + tid < R;
-    static_for<0, NP / 16>([&](auto cc) {
-      constexpr int c0 = decltype(cc)::value * 16;
-      float v[16];
-      tc::tmem_ld<16>(tmem + lane_base + c0, v);
-      if (valid) {
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------- converters (thread = row) + epilogue
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    mbar_wait(&bars[0], 0);                                     // the bias is read in the epilogue
+    int64_t it = 0;
+    int tl = 0, c_slot = 0;
+    uint32_t c_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tmem + uint32_t((tl & 1) * NP);
+      int last_ab = 0;
+      int64_t last_it = 0;
+      static_for<0, S::NSEG>([&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+          constexpr int W = S::seg_width(s), WP = round_up(W, 8), NK4 = W / 4;
+          const int st = c_slot, ab = int(it & 1);
+          mbar_wait(&full[st], c_phase);                        // the raw tile has landed
+          if (it >= 2) { mbar_wait(&mma_done[ab], uint32_t((it >> 1) - 1) & 1u); tc::fence_after(); }   // operand buffer ab is free again
+          const float* __restrict__ rw = raw + st * X::RAW_FLOATS + tid * W;
+          float* __restrict__ ah = a_hi + ab * X::A_FLOATS;
+          float* __restrict__ al = a_lo + ab * X::A_FLOATS;
+          int k4 = tid % NK4;                                    // rotated start: conflict-free reads (row stride W floats) and writes
 #pragma unroll
-        for (int i4 = 0; i4 < 16; i4 += 4) {
-          if (c0 + i4 < N0) {
-            const float4 bb = *reinterpret_cast<const float4*>(sm_w + 2 * X::IMG_FLOATS + c0 + i4);
-            *reinterpret_cast<float4*>(E + r * N0 + c0 + i4) = make_float4(v[i4] + bb.x, v[i4 + 1] + bb.y, v[i4 + 2] + bb.z, v[i4 + 3] + bb.w);
+          for (int j = 0; j < NK4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(rw + 4 * k4);
+            // the tensor core reads the hi tile truncated to tf32: the remainder is taken against the truncated value
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(ah + (k4 * 128 + tid) * 4) = v;
+            *reinterpret_cast<float4*>(al + (k4 * 128 + tid) * 4) = l;
+            k4 = k4 + 1 < NK4 ? k4 + 1 : 0;
+          }
+          if constexpr (WP > W) {                                // zero columns up to the MMA's K granularity
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(ah + (NK4 * 128 + tid) * 4) = z;
+            *reinterpret_cast<float4*>(al + (NK4 * 128 + tid) * 4) = z;
+          }
+          tc::fence_async_smem();                                // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
+          tc::fence_before();
+          mbar_arrive(&a_ready[ab]);
+          last_ab = ab; last_it = it;
+          ++it;
+          if (++c_slot == NRAW) { c_slot = 0; c_phase ^= 1u; }
+        }
+      });
+      // epilogue: the tile's MMAs are done (they complete in order) -> this thread's accumulator row + bias -> E.  The next
+      // tile accumulates into the OTHER accumulator; this one is overwritten two tiles later, behind this thread's
+      // fence_before + arrive of the items in between.
+      mbar_wait(&mma_done[last_ab], uint32_t(last_it >> 1) & 1u);
+      tc::fence_after();
+      const int64_t r = tile * 128 + tid;
+      const bool valid = r < R;
+      static_for<0, NP / 16>([&](auto cc) {
+        constexpr int c0 = decltype(cc)::value * 16;
+        float v[16];
+        tc::tmem_ld<16>(acc + lane_base + c0, v);
+        if (valid) {
+#pragma unroll
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+            if (c0 + i4 < N0) {
+              const float4 bb = *reinterpret_cast<const float4*>(sm_w + 2 * X::IMG_FLOATS + c0 + i4);
+              *reinterpret_cast<float4*>(E + r * N0 + c0 + i4) = make_float4(v[i4] + bb.x, v[i4 + 1] + bb.y, v[i4 + 2] + bb.z, v[i4 + 3] + bb.w);
+            }
           }
         }
-      }
-    });
-    tc::fence_before();
-    __syncthreads();                                            // every row has been read before the next tile's first MMA overwrites the accumulator
-    tc::fence_after();
+      });
+    }
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<32>(tmem);
+  if (warp == 0) tc::tmem_dealloc<X::ACC_COLS>(tmem);
 }
 
 
