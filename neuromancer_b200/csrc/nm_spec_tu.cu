@@ -507,7 +507,7 @@ int forward_fn(const NmPlan* p, NmFwdCall* c) {
       const int64_t tiles128 = (c->B * p->nsteps + 127) / 128;
       int tgrid = d->sms; if (tgrid > tiles128) tgrid = int(tiles128); if (tgrid < 1) tgrid = 1;      // one CTA per SM (220 KB: operand double buffer + raw ring)
       nm_exo_tc_prep_kernel<SB><<<8, 256, 0, c->stream>>>(*p, c->params, wexo);
-      nm_exo_gemm_tc_fwd_kernel<SB><<<tgrid, 160, exo_tc_smem<kExoTc>(), c->stream>>>(*p, wexo, ep, E, c->B);
+      nm_exo_gemm_tc_fwd_kernel<SB><<<tgrid, 288, exo_tc_smem<kExoTc>(), c->stream>>>(*p, wexo, ep, E, c->B);
       c->extra_launches = 2;
     } else {
       nm_exo_gemm_fwd_kernel<SB><<<ggrid, SB::THREADS, kExoSmem, c->stream>>>(*p, wprep_ffma, ep, E, c->B);

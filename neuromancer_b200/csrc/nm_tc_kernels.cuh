@@ -1369,7 +1369,7 @@ __global__ void nm_exo_tc_prep_kernel(const __grid_constant__ NmPlan plan, const
 // the next tile's first MMAs.  (The register-prefetch version before it sat at 40 % of the DRAM peak on long-scoreboard
 // stalls with 8 warps per SM: profiles/r02c_c4_ncu_summary.txt.)
 template <class S>
-__global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ wexo,
+__global__ void __launch_bounds__(288, 1) nm_exo_gemm_tc_fwd_kernel(const __grid_constant__ NmPlan plan, const float* __restrict__ wexo,
                                                                     const __grid_constant__ ExoPtrs exo, float* __restrict__ E, int64_t B) {
   using X = ExoTcCfg<S>;
   constexpr int N0 = X::N0, NP = X::NP, NRAW = X::NRAW, NSX = X::nsx();
@@ -1401,7 +1401,7 @@ __global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid
   const int64_t tiles = (R + 127) / 128;
   constexpr uint32_t idesc = tc::idesc_tf32(128, NP);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---------------------------------------------------------------------------------------- producer + MMA issuer
     // One lane streams the raw tiles (NRAW items ahead) and issues the MMAs of every item as soon as its operand tiles are
     // written; its state advances incrementally (no divisions in the loop).
@@ -1449,33 +1449,45 @@ __global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid
       for (int i = 0; i < NRAW; ++i) issue_next();
       mbar_wait(&bars[0], 0);
       constexpr uint32_t A_LBO = 128 * 16, A_KSTEP = 2 * 128 * 16, B_LBO = NP * 16, B_KSTEP = 2 * NP * 16;
+      const uint64_t dh0 = tc::smem_desc(smem_u32(a_hi), A_LBO, 128), dl0 = tc::smem_desc(smem_u32(a_lo), A_LBO, 128);
+      const uint64_t wbase = tc::smem_desc(smem_u32(sm_w), B_LBO, 128);
       int64_t it = 0;
       int tl = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
         const uint32_t acc = tmem + uint32_t((tl & 1) * NP);
-        for (int sx = 0; sx < NSX; ++sx, ++it) {
-          const int ab = int(it & 1);
-          mbar_wait(&a_ready[ab], uint32_t(it >> 1) & 1u);      // operand tiles of this item written, its raw tile drained
-          tc::fence_after();
-          issue_next();                                         // item it + NRAW into the ring slot just drained
-          const int wp8 = (segw[sx] + 7) / 8;
-          const uint64_t dh = tc::smem_desc(smem_u32(a_hi + ab * X::A_FLOATS), A_LBO, 128);
-          const uint64_t dl = tc::smem_desc(smem_u32(a_lo + ab * X::A_FLOATS), A_LBO, 128);
-          const uint64_t wh = tc::smem_desc(smem_u32(sm_w) + (segoff[sx] / 4) * NP * 16, B_LBO, 128);
-          const uint64_t wl = tc::desc_add(wh, X::IMG_FLOATS * 4);
-          for (int ks = 0; ks < wp8; ++ks) {                    // remainder products first (the accumulator truncates)
-            tc::mma_ss(acc, tc::desc_add(dl, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, (sx == 0 && ks == 0) ? 0u : 1u);
-            tc::mma_ss(acc, tc::desc_add(dh, ks * A_KSTEP), tc::desc_add(wl, ks * B_KSTEP), idesc, 1u);
+        static_for<0, S::NSEG>([&](auto sc) {
+          constexpr int s = decltype(sc)::value;
+          if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
+            constexpr int W = S::seg_width(s), OFF = exo_seg_off<S>(s), WP = round_up(W, 8);
+            const int ab = int(it & 1);
+            mbar_wait(&a_ready[ab], uint32_t(it >> 1) & 1u);    // operand tiles of this item written, its raw tile drained
+            tc::fence_after();
+            issue_next();                                       // item it + NRAW into the ring slot just drained
+            const uint64_t dh = tc::desc_add(dh0, ab * X::A_FLOATS * 4), dl = tc::desc_add(dl0, ab * X::A_FLOATS * 4);
+            const uint64_t wh = tc::desc_add(wbase, (OFF / 4) * NP * 16);
+            const uint64_t wl = tc::desc_add(wh, X::IMG_FLOATS * 4);
+            static_for<0, WP / 8>([&](auto kc) {                // remainder products first (the accumulator truncates)
+              constexpr int ks = decltype(kc)::value;
+              tc::mma_ss(acc, tc::desc_add(dl, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, (OFF == 0 && ks == 0) ? 0u : 1u);
+              tc::mma_ss(acc, tc::desc_add(dh, ks * A_KSTEP), tc::desc_add(wl, ks * B_KSTEP), idesc, 1u);
+            });
+            static_for<0, WP / 8>([&](auto kc) {
+              constexpr int ks = decltype(kc)::value;
+              tc::mma_ss(acc, tc::desc_add(dh, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, 1u);
+            });
+            tc::commit(&mma_done[ab]);
+            ++it;
           }
-          for (int ks = 0; ks < wp8; ++ks) tc::mma_ss(acc, tc::desc_add(dh, ks * A_KSTEP), tc::desc_add(wh, ks * B_KSTEP), idesc, 1u);
-          tc::commit(&mma_done[ab]);
-        }
+        });
       }
     }
     __syncwarp();
   } else {
     // ---------------------------------------------------------------------------------------- converters (thread = row) + epilogue
-    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    // Two groups of 128 threads: group g converts the items with parity g into operand buffer g -- two items in flight on
+    // the CUDA cores while the tensor pipe works on the previous ones; the group of a tile's last item writes its rows of E.
+    const int grp = warp >> 2, row = tid & 127;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     mbar_wait(&bars[0], 0);                                     // the bias is read in the epilogue
     int64_t it = 0;
     int tl = 0, c_slot = 0;
@@ -1489,12 +1501,13 @@ __global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid
         if constexpr (S::seg_kind(s) == NM_SEG_EXO) {
           constexpr int W = S::seg_width(s), WP = round_up(W, 8), NK4 = W / 4;
           const int st = c_slot, ab = int(it & 1);
+          if (ab == grp) {
           mbar_wait(&full[st], c_phase);                        // the raw tile has landed
           if (it >= 2) { mbar_wait(&mma_done[ab], uint32_t((it >> 1) - 1) & 1u); tc::fence_after(); }   // operand buffer ab is free again
-          const float* __restrict__ rw = raw + st * X::RAW_FLOATS + tid * W;
+          const float* __restrict__ rw = raw + st * X::RAW_FLOATS + row * W;
           float* __restrict__ ah = a_hi + ab * X::A_FLOATS;
           float* __restrict__ al = a_lo + ab * X::A_FLOATS;
-          int k4 = tid % NK4;                                    // rotated start: conflict-free reads (row stride W floats) and writes
+          int k4 = row % NK4;                                    // rotated start: conflict-free reads (row stride W floats) and writes
 #pragma unroll
           for (int j = 0; j < NK4; ++j) {
             const float4 v = *reinterpret_cast<const float4*>(rw + 4 * k4);
@@ -1502,18 +1515,19 @@ __global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid
             float4 l;
             l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(ah + (k4 * 128 + tid) * 4) = v;
-            *reinterpret_cast<float4*>(al + (k4 * 128 + tid) * 4) = l;
+            *reinterpret_cast<float4*>(ah + (k4 * 128 + row) * 4) = v;
+            *reinterpret_cast<float4*>(al + (k4 * 128 + row) * 4) = l;
             k4 = k4 + 1 < NK4 ? k4 + 1 : 0;
           }
           if constexpr (WP > W) {                                // zero columns up to the MMA's K granularity
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(ah + (NK4 * 128 + tid) * 4) = z;
-            *reinterpret_cast<float4*>(al + (NK4 * 128 + tid) * 4) = z;
+            *reinterpret_cast<float4*>(ah + (NK4 * 128 + row) * 4) = z;
+            *reinterpret_cast<float4*>(al + (NK4 * 128 + row) * 4) = z;
           }
           tc::fence_async_smem();                                // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
           tc::fence_before();
           mbar_arrive(&a_ready[ab]);
+          }
           last_ab = ab; last_it = it;
           ++it;
           if (++c_slot == NRAW) { c_slot = 0; c_phase ^= 1u; }
@@ -1522,9 +1536,10 @@ __global__ void __launch_bounds__(160, 1) nm_exo_gemm_tc_fwd_kernel(const __grid
       // epilogue: the tile's MMAs are done (they complete in order) -> this thread's accumulator row + bias -> E.  The next
       // tile accumulates into the OTHER accumulator; this one is overwritten two tiles later, behind this thread's
       // fence_before + arrive of the items in between.
+      if (last_ab != grp) continue;
       mbar_wait(&mma_done[last_ab], uint32_t(last_it >> 1) & 1u);
       tc::fence_after();
-      const int64_t r = tile * 128 + tid;
+      const int64_t r = tile * 128 + row;
       const bool valid = r < R;
       static_for<0, NP / 16>([&](auto cc) {
         constexpr int c0 = decltype(cc)::value * 16;

@@ -75,7 +75,7 @@ int main(int argc, char** argv) {
     static_assert(X::OK, "tensor-core hoist GEMM not available for this class");
     std::vector<float> wexo(size_t(X::W_FLOATS) + 64, 0.f);
     emu::launch(4, 256, [&] { nm_exo_tc_prep_kernel<SB>(plan, params.data(), wexo.data()); });
-    emu::launch(grid, 160, [&] { nm_exo_gemm_tc_fwd_kernel<SB>(plan, wexo.data(), ep, chk.data(), B); });
+    emu::launch(grid, 288, [&] { nm_exo_gemm_tc_fwd_kernel<SB>(plan, wexo.data(), ep, chk.data(), B); });
 #else
     emu::launch(grid, SB::THREADS, [&] { nm_exo_gemm_fwd_kernel<SB>(plan, wprep_ffma.data(), ep, chk.data(), B); });
 #endif
