@@ -12,7 +12,8 @@ unmodified reference wherever ``/root/reference`` exists, and writes the golden 
 the reference's ``loss.backward()`` (trainer.py:250) differentiates.
 
 PARITY PIN: pinned against the real reference (torch.equal on trajectories, every loss term, the
-total loss and all parameter gradients) for the ten cases of ``oracle/cases.py`` -- see
+total loss and all parameter gradients) for the 41 cases of ``oracle/cases.py`` (benchmark configurations, integrators,
+white-box / hybrid right-hand sides, system identification, BarrierLoss, preview padding, structured maps) -- see
 ``tests/golden/PINNED.json`` written by ``oracle/pin_oracle.py``.  The reference's own test-suite
 holds no value-level golden vectors for this path, so the fixtures generated
 from the reference are the pin.
