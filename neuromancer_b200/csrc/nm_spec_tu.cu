@@ -197,9 +197,11 @@ template <class Sp> struct Wide<Sp, true> {
     if (e == cudaSuccess) {
       // L2 set-aside for the evict_last derivative stash (58 MB on 148 SMs).  Measured on B200 (C5, B = 4,194,304,
       // profiles/r02_l2_carveout_sweep.txt): the adjoint window takes 1.60 s with a 48-56 MB carve-out, 1.72 s with 64 MB
-      // and 1.90 s from 72 MB up (the maximum, 126 MB, leaves the streaming staging stores and the row loads no room)
+      // and 1.90 s from 72 MB up (the maximum, 126 MB, leaves the streaming staging stores and the row loads no room).
+      // Re-swept after the grouped term gradients (profiles/r02c_l2_carveout_sweep.txt): 44 MB 1.574 s, 52 MB 1.530-1.534 s,
+      // 56 MB 1.514 s, 60 MB 1.510-1.516 s, 64 MB 1.604 s -> 56 MB, clear of the cliff at 64.
       int dev = 0, maxp = 0;
-      size_t want = size_t(52) << 20;
+      size_t want = size_t(56) << 20;
       if (const char* sv = getenv("NM_WIDE_L2_PERSIST_MB")) want = size_t(atol(sv)) << 20;        // experiments: 0 = no carve-out
       if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && maxp > 0)
         (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want < size_t(maxp) ? want : size_t(maxp));
