@@ -162,10 +162,14 @@ def load():
         raise NmError(f"libnm_rollout.so ABI {got} != python binding ABI {NM_ABI_VERSION}; rebuild")
     _lib = lib
     # specialisations built on demand for shapes outside the ahead-of-time registry
+    # (a plugin older than the library was built from older kernel sources -- its checkpoint / workspace layouts may differ:
+    # it is left alone and rebuilt on demand by build.ensure_specialisation)
     if os.path.isdir(LIB_DIR) and not os.environ.get("NM_LIB_PATH"):
+        built = os.path.getmtime(LIB_PATH)
         for fn in sorted(os.listdir(LIB_DIR)):
-            if fn.startswith("nm_spec_") and fn.endswith(".so"):
-                lib.nm_load_plugin(os.path.join(LIB_DIR, fn).encode())
+            path = os.path.join(LIB_DIR, fn)
+            if fn.startswith("nm_spec_") and fn.endswith(".so") and os.path.getmtime(path) >= built:
+                lib.nm_load_plugin(path.encode())
     return lib
 
 
