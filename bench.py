@@ -313,6 +313,8 @@ def main():
         ev[i][3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    if getattr(raw, "sync", None) is not None and raw.sync.status() != 0:
+        raise RuntimeError("in-kernel exchange: a peer did not arrive within the kernel's time-out (status word set)")
     step_ms = [e[0].elapsed_time(e[3]) for e in ev]
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps

@@ -353,7 +353,7 @@ int nm_constraint_matrices(const NmPlan* plan, const float* const* exo, const fl
  *                  NULL (peer loads summed in rank order)
  *   out            [n] device fp32, not part of the symmetric buffer; entries >= tail_from are multiplied by tail_scale
  *                  (loss scalars are averaged, gradients summed)
- * No host synchronisation; a peer that does not arrive within seconds sets status word
+ * No host synchronisation; a peer that does not arrive within ~30 s sets status word
  * ((uint32_t*)(own + 2 * npad))[17] instead of hanging the device.
  */
 size_t nm_grad_allreduce_buffer_floats(int64_t n);

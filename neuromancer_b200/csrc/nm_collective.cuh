@@ -25,7 +25,7 @@ constexpr int kArBlocks = 16, kArThreads = 256;
 // symmetric buffer layout (floats): [half 0: npad][half 1: npad][kArFlagWords 32-bit words], npad = n rounded up to 64
 //   word q < kArMaxRanks: arrival flag of rank q;  word kArMaxRanks: block release flag;  word kArMaxRanks + 1: status
 constexpr int kArFlagWords = 64;
-constexpr long long kArTimeoutCycles = 8000000000LL;      // ~4 s: a missing peer is an error, not a hang
+constexpr long long kArTimeoutCycles = 60000000000LL;     // ~30 s (first-step skew between ranks can be seconds): a missing peer is an error, not a hang
 
 struct ArPeers { float* buf[kArMaxRanks]; };
 
