@@ -177,3 +177,56 @@ def test_constant_division_of_the_rk4_combine_is_correctly_rounded():
             assert np.array_equal(rem.astype(np.float32).astype(np.float64), rem)          # the FMA residual is exact
             q = (q0.astype(np.float64) + rem * np.float64(r)).astype(np.float32)
             assert np.array_equal(q, (x / np.float32(d)).astype(np.float32))
+
+
+def test_hybrid_right_hand_side_lowering():
+    """grey-box right-hand sides (reference ode.py:284-331): the block is lowered as the right-hand-side MLP, the constants as a
+    derived entry behind it; rhs_mlp.trainable bit 0 = weights, bit 1 = constants"""
+    from neuromancer_b200.dynamics.ode import DerivedConstants
+    net = blocks.MLP(2, 1, bias=True, linear_map=nn.Linear, nonlin=nn.GELU, hsizes=[8])
+    plant = ode.BrusselatorHybrid(net)
+    system = System([Node(integrators.RK4(plant, h=0.05), ["x"], ["x"], name="ude")], nsteps=4)
+    plan = system.plan_for({"x": torch.zeros(3, 1, 2)})
+    p = plan.c
+    n_mlp = sum(q.numel() for q in net.parameters())
+    assert p.rhs_kind == L.NM_RHS_BRUSS_HYBRID and L.rhs_has_mlp(p.rhs_kind) and p.has_policy == 0
+    assert [p.rhs_mlp.sizes[i] for i in range(p.rhs_mlp.n_layers + 1)] == [2, 8, 1]
+    assert p.rhs_mlp.trainable == 3 and p.n_params == n_mlp + 2
+    assert isinstance(plan.params[-1], DerivedConstants) and plan.param_slices[-1] == (n_mlp, 2)
+    assert [q is r for q, r in zip(plan.params[-1].own_parameters(), (plant.alpha, plant.beta))] == [True, True]
+    assert (p.rhs_const[0], p.rhs_const[1]) == (5.0, 5.0)
+    for q in (plant.alpha, plant.beta):
+        q.requires_grad_(False)
+    frozen = System([Node(integrators.RK4(plant, h=0.05), ["x"], ["x"], name="ude")], nsteps=4).plan_for({"x": torch.zeros(3, 1, 2)})
+    assert frozen.c.rhs_mlp.trainable == 1 and frozen.c.n_params == n_mlp
+    for q in net.parameters():
+        q.requires_grad_(False)
+    plant.alpha.requires_grad_(True)
+    only_theta = System([Node(integrators.RK4(plant, h=0.05), ["x"], ["x"], name="ude")], nsteps=4).plan_for({"x": torch.zeros(3, 1, 2)})
+    assert only_theta.c.rhs_mlp.trainable == 2 and only_theta.c.n_params == n_mlp + 2
+    with pytest.raises(PlanError, match="first-order"):
+        System([Node(integrators.LeapFrog(plant, h=0.05), ["x"], ["x"], name="ude")], nsteps=4).plan_for({"x": torch.zeros(3, 1, 2)})
+    with pytest.raises(AssertionError):
+        ode.LotkaVolterraHybrid(blocks.MLP(3, 1, hsizes=[4], nonlin=nn.Tanh))          # the block maps x (2) -> 1
+
+
+def test_barrier_loss_lowering():
+    """BarrierLoss with a named barrier (reference loss.py:184-257): kind in NmTerm.norm bits 4-7 of the CONSTRAINTS only,
+    parameters in the plan; a change of a parameter makes the cached plan stale; a callable barrier is not lowered"""
+    from neuromancer_b200 import BarrierLoss
+    case = configs.build_case("t_barrier_softlog")
+    plan = case.plan()
+    p = plan.c
+    assert plan.barrier == L.NM_BARRIERS["softlog"] == 5 and not plan.python_terms
+    assert [p.terms[k].norm for k in range(p.n_terms)] == [2, 2 | 5 << 4, 1 | 5 << 4, 1 | 5 << 4]
+    assert [bool(p.terms[k].is_objective) for k in range(p.n_terms)] == [True, False, False, False]
+    assert (round(p.barrier_alpha, 6), round(p.barrier_shift, 6), p.barrier_ub) == (0.4, 0.7, 2.0)
+    assert not plan.values_stale()
+    case.problem.loss.upper_bound = 3.0
+    assert plan.values_stale()
+    loss = case.problem.loss
+    eager = BarrierLoss(list(loss.objectives), list(loss.constraints), barrier=lambda v: torch.exp(v))
+    assert eager.barrier_name is None
+    batch = case.make_batch(2, "cpu", 0)
+    unfused = case.system.plan_for(case.system.init(dict(batch)), loss=eager)
+    assert unfused.barrier == 0 and all(unfused.c.terms[k].norm in (1, 2) for k in range(unfused.c.n_terms))
