@@ -105,3 +105,23 @@ def test_neural_ode_classes_are_served_by_the_tensor_core_kernels(nm_lib):
     assert nbytes.value == 1000 * 96 * (32 + 1) * 4
     assert nm_lib.nm_rollout_checkpoint_bytes(C.byref(configs.build_case("c4p").plan().c), 1000, C.byref(nbytes)) == L.NM_OK
     assert nbytes.value == 0
+
+
+def test_constraint_matrix_widths_and_exchange_argument_checks(nm_lib):
+    """No GPU needed: nm_constraint_matrices answers the width query without a launch (B = 0); nm_grad_allreduce validates
+    its arguments before touching the device."""
+    plan = configs.build_case("c2").plan()
+    w = (C.c_int64 * 3)()
+    assert nm_lib.nm_constraint_matrices(C.byref(plan.c), None, None, None, None, None, None, None, None, None, None, w, 0, None) == L.NM_OK
+    cons = [plan.c.terms[k] for k in range(plan.c.n_terms) if not plan.c.terms[k].is_objective]
+    total = sum(t.t_len * t.d_len for t in cons)
+    eq = sum(t.t_len * t.d_len for t in cons if t.cmp == L.NM_CMP_EQ)
+    assert (w[0], w[1], w[2]) == (total, eq, total - eq) and total > 0
+    assert nm_lib.nm_grad_allreduce_buffer_floats(1290) == 2 * 1344 + 64            # halves padded to 64 floats + flag words
+    peers = (C.c_void_p * 2)(0, 0)
+    assert nm_lib.nm_grad_allreduce(peers, None, None, 10, 0, 2, 1, 10, 1.0, None) == L.NM_ERR_BAD_PLAN      # null output
+    out = C.c_void_p(4096)
+    assert nm_lib.nm_grad_allreduce(peers, None, out, 10, 0, 2, 0, 10, 1.0, None) == L.NM_ERR_BAD_PLAN       # epoch 0
+    assert nm_lib.nm_grad_allreduce(peers, None, out, 10, 2, 2, 1, 10, 1.0, None) == L.NM_ERR_BAD_PLAN       # rank out of range
+    assert nm_lib.nm_grad_allreduce(peers, None, out, 10, 0, 2, 1, 10, 1.0, None) == L.NM_ERR_BAD_PLAN       # null peer buffers
+    assert b"nm_grad_allreduce" in nm_lib.nm_last_error()
